@@ -1,0 +1,297 @@
+#!/usr/bin/env python
+"""bench.py -- PCG+AMG solve throughput and V-cycle HBM bandwidth on B200 (BASELINE.json metric).
+
+  python bench.py --gpus N --steps K --warmup W            # our CUDA path, one rank per GPU
+  python bench.py --impl reference --gpus N --steps K ...  # CPU arm: the oracle port of the reference algorithm
+
+A "step" is one complete PCG+AMG solve (tol 1e-8, V(1,1)-cycle preconditioner) of the synthetic 3D Poisson P1 problem
+(Kuhn tets on the unit cube, Dirichlet on x=0 and y=1, f=1).  N=1 workload = BASELINE.json configs[1]: 311^3 = 30.1 M DOFs.
+value   = DOFs solved per second (whole job) with rhs/solution resident in HBM (the reference prints the same unit,
+          "dofs / (sec * np)", tests/h1/amg_utils.py:358); `solve_s`, `iterations`, `vcycle_ms`, `vcycle_gbs` ride along.
+e2e     = the same through the C ABI with HOST numpy buffers (H2D of the rhs and D2H of the solution inside the timed region).
+roofline= the dominant kernel of the V-cycle (level-0 Gauss-Seidel triangular sweep) timed alone with CUDA events on the
+          library's stream, algorithmic bytes / time against the measured HBM peak (MEASURED_PEAKS.json).
+The matrix (5.5 GB at N=311) is far larger than the 126 MB L2, so no explicit L2 flush is needed between iterations.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+DEFAULT_N = 311          # 311^3 = 30,080,231 DOFs (configs[1])
+CPU_SAMPLE_N = 91        # 91^3 = 753,571 DOFs: ~10-20 s of single-core CPU work for setup + solve
+TOL = 1e-8
+
+
+def rank_workload(n, rank, world):
+    """grid size of the subdomain problem a rank solves.  The multi-GPU path of this round runs independent subdomain
+    problems of identical size on every rank (weak scaling, no data-path collective yet)."""
+    return n
+
+
+def measured_peak():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured"
+    except Exception:
+        return 6650.0, "fallback"
+
+
+class ClockSampler:
+    """samples SM clocks / throttle reasons with nvidia-smi while the timed region runs"""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "200"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 6:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def make_problem(n):
+    from ngsamg_b200 import synthetic as S
+    import ngsamg_b200 as ng
+    p = S.poisson3d_kuhn(n)
+    A = ng.SparseMatrix(p["n"], p["n"], 1, 1, p["rowptr"], p["col"], p["val"])
+    return p, A
+
+
+def cpu_reference_run(n, steps, warmup, tol=TOL):
+    """the oracle (CPU port of the reference algorithm, single thread like one MPI rank of the reference)"""
+    import ngsamg_b200 as ng
+    from oracle import oracle as O
+    O.build()
+    p, A = make_problem(n)
+    t0 = time.time()
+    # hierarchy: the product's host-side coarsening, Galerkin products by the oracle
+    prols, cur, fm = [], A, p["free"]
+    while cur.nrows > 50 and len(prols) + 1 < 10:
+        P, _, _ = ng.coarsen(cur, fm)
+        if P.ncols == 0 or P.ncols > 0.8 * cur.nrows:
+            break
+        prols.append(P)
+        Po = O.Bsr(P.nrows, P.ncols, 1, 1, P.rowptr, P.col, P.val)
+        Ac = O.restrict_matrix(O.transpose(Po), O.Bsr(cur.nrows, cur.ncols, 1, 1, cur.rowptr, cur.col, cur.val), Po)
+        cur, fm = ng.SparseMatrix(Ac.nrows, Ac.ncols, 1, 1, Ac.rowptr, Ac.col, Ac.val), None
+    amg = O.OracleAMG(O.Bsr(A.nrows, A.ncols, 1, 1, A.rowptr, A.col, A.val), p["free"],
+                      [O.Bsr(P.nrows, P.ncols, 1, 1, P.rowptr, P.col, P.val) for P in prols])
+    setup_s = time.time() - t0
+    for _ in range(warmup):
+        amg.apply(p["rhs"])
+    times, its = [], 0
+    for _ in range(steps):
+        t = time.time()
+        _, its, errs = amg.pcg(p["rhs"], tol=tol, maxsteps=200)
+        times.append(time.time() - t)
+    tv = time.time()
+    for _ in range(3):
+        amg.apply(p["rhs"])
+    vcycle_s = (time.time() - tv) / 3
+    return dict(ndof=p["n"], solve_s=float(np.mean(times)), iterations=int(its), setup_s=setup_s, vcycle_s=vcycle_s,
+                levels=amg.nlevels)
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    n = args.cpu_n
+    r = cpu_reference_run(n, max(1, min(args.steps, 3)), min(args.warmup, 1))
+    val = r["ndof"] / r["solve_s"]
+    line = {
+        "impl": "reference", "metric": "pcg_amg_solve_dofs_per_s", "value": val, "unit": "DOF/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["solve_s"] * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "3D Poisson P1 unit cube (Kuhn tets), h1_scal + CG to 1e-8; CPU sample %d^3 = %d DOFs of the "
+                               "%d^3 workload" % (n, r["ndof"], args.n), "tol": TOL, "levels": r["levels"]},
+        "solve_s": r["solve_s"], "iterations": r["iterations"], "vcycle_ms": r["vcycle_s"] * 1e3,
+        "cpu_baseline": {"value": val, "unit": "DOF/s", "cores": 1, "kind": "port",
+                         "sample": "oracle PCG+AMG solve, %d^3 = %d DOFs, 1 thread (the reference cannot be built here: needs "
+                                   "NGSolve/MPI)" % (n, r["ndof"])},
+        "e2e": {"value": val, "unit": "DOF/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours")
+    ap.add_argument("--n", type=int, default=int(os.environ.get("NGSAMG_BENCH_N", DEFAULT_N)))
+    ap.add_argument("--cpu-n", type=int, default=int(os.environ.get("NGSAMG_BENCH_CPU_N", CPU_SAMPLE_N)))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+        return
+
+    import torch
+    import ngsamg_b200 as ng
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the product path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    n = rank_workload(args.n, rank, world)
+    t0 = time.time()
+    p, A = make_problem(n)
+    gen_s = time.time() - t0
+    t0 = time.time()
+    pc = ng.h1_scal(A, p["free"], device=local_rank)
+    setup_s = time.time() - t0
+    ndof = p["n"]
+    rhs_h = np.ascontiguousarray(p["rhs"])
+    x_h = np.zeros(ndof)
+    rhs_d = torch.from_numpy(rhs_h).cuda()
+    x_d = torch.zeros_like(rhs_d)
+    cg = ng.CGSolver(mat=A, pre=pc, maxsteps=200, tol=TOL)
+
+    # ---- device-resident solve (value) ---------------------------------------------------------------
+    for _ in range(args.warmup):
+        cg.Solve(rhs_d, x_d)
+    sampler = ClockSampler(local_rank)
+    barrier()
+    sampler.start()
+    l0 = pc.LaunchCount()
+    wall0 = time.time()
+    dev_ms = 0.0
+    for _ in range(args.steps):
+        cg.Solve(rhs_d, x_d)
+        dev_ms += pc.LastMs("pcg")        # CUDA events on the library stream around the whole solve
+    barrier()
+    wall = time.time() - wall0
+    launches = pc.LaunchCount() - l0
+    iters = cg.iterations
+    tmax = torch.tensor([dev_ms / 1e3, wall], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+    dev_s, wall_s = tmax[0].item(), tmax[1].item()
+    solve_s = dev_s / args.steps
+
+    # ---- end-to-end through the C ABI with host buffers (e2e) ----------------------------------------
+    cg.Solve(rhs_h, x_h)
+    barrier()
+    e0 = time.time()
+    for _ in range(args.steps):
+        cg.Solve(rhs_h, x_h)
+    barrier()
+    e2e = torch.tensor([time.time() - e0], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(e2e, op=dist.ReduceOp.MAX)
+    e2e_s = e2e.item() / args.steps
+
+    # ---- V-cycle alone + per-kernel roofline (level 0) -------------------------------------------------
+    for _ in range(3):
+        pc.Mult(rhs_d, x_d)
+    vms = []
+    for _ in range(20):
+        pc.Mult(rhs_d, x_d)
+        vms.append(pc.LastMs("apply"))
+    clocks = sampler.stop()
+    vcycle_ms = float(np.mean(vms))
+    vbytes = pc.VCycleBytes()
+    peak, peak_src = measured_peak()
+    kern = {}
+    for name in ("gs_tri_fwd", "gs_upass", "gs_lpass", "gs_tri_bwd", "spmv", "restrict", "prolong"):
+        ms, by = pc.ProfileKernel(name, level=0, reps=10)
+        kern[name] = {"ms": ms, "gbs": by / ms / 1e6, "bytes": by}
+    dom = max(("gs_tri_fwd", "gs_tri_bwd", "gs_upass", "gs_lpass"), key=lambda k: kern[k]["ms"])
+    roof = {"bound": "hbm", "kernel": "k_gs_tri (%s, level 0)" % dom, "achieved": kern[dom]["gbs"], "peak": peak,
+            "unit": "GB/s", "frac": kern[dom]["gbs"] / peak, "traffic": None, "peak_source": peak_src,
+            "ms_per_launch": kern[dom]["ms"], "algorithmic_bytes": kern[dom]["bytes"]}
+
+    levels = []
+    for l in range(pc.GetNLevels()):
+        i = pc.level_info(l)
+        levels.append({"n": int(i.n), "nnz": int(i.nnz), "gs_depth": int(i.gs_depth)})
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        r = cpu_reference_run(args.cpu_n, 1, 0)
+        cpu = {"value": r["ndof"] / r["solve_s"], "unit": "DOF/s", "cores": 1, "kind": "port",
+               "sample": "oracle PCG+AMG solve of the same problem at %d^3 = %d DOFs (1 thread, %d its, %.2f s; V-cycle %.1f ms)"
+                         % (args.cpu_n, r["ndof"], r["iterations"], r["solve_s"], r["vcycle_s"] * 1e3)}
+
+    if rank == 0:
+        line = {
+            "metric": "pcg_amg_solve_dofs_per_s", "value": world * ndof / solve_s, "unit": "DOF/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": solve_s * 1e3, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "3D Poisson P1 unit cube (Kuhn tets), %d^3 = %d DOFs per GPU, h1_scal + CG to 1e-8" % (n, ndof),
+                       "tol": TOL, "levels": levels, "operator_complexity": pc.GetOC(),
+                       "parallelism": "1 GPU" if world == 1 else "%d independent subdomain replicas (no halo exchange yet)" % world,
+                       "l2": "inputs larger than L2 (level-0 matrix %.1f GB)" % (levels[0]["nnz"] * 12 / 1e9)},
+            "solve_s": solve_s, "iterations": iters, "setup_s": setup_s, "setup_rap_ms": pc.LastMs("rap"),
+            "setup_host_ms": pc.LastMs("host"), "gen_s": gen_s, "wall_s_timed_region": wall_s,
+            "vcycle_ms": vcycle_ms, "vcycle_bytes": vbytes, "vcycle_gbs": vbytes / vcycle_ms / 1e6,
+            "vcycle_frac_of_peak": vbytes / vcycle_ms / 1e6 / peak,
+            "kernels_level0": kern, "roofline": roof, "cpu_baseline": cpu,
+            "e2e": {"value": world * ndof / e2e_s, "unit": "DOF/s", "h2d_bytes_per_step": 8 * ndof, "d2h_bytes_per_step": 8 * ndof,
+                    "solve_s": e2e_s},
+            "gpu_launches": int(launches), "clocks": clocks,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

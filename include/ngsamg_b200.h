@@ -1,0 +1,165 @@
+/*
+ * ngsamg_b200.h -- C ABI of the B200-native NgsAMG preconditioner-apply hot path.
+ *
+ * The reference (LukasKogler/NgsAMG) has NO C ABI: it is a C++ add-on that registers
+ * `ngcomp::Preconditioner` subclasses with NGSolve (src/base/utils/amg_register.hpp:79-98) and is
+ * driven through NGSolve's BaseMatrix interface.  Each entry point below names the reference
+ * interface it replaces (paths relative to the reference root); INTEGRATION.md shows the NGSolve-side
+ * adapter a maintainer would add on top of these calls.
+ *
+ * Conventions
+ *   - every function returns 0 on success, non-zero on error; ngsamg_b200_last_error() gives the text
+ *     (the reference throws ngcore::Exception, e.g. src/base/precond/amg_pc.cpp:430,446).
+ *   - matrices are block-CSR in NGSolve SparseMatrix<Mat<bh,bw,double>> layout: rowptr[nrows+1] (int64),
+ *     col[nnz] (int32, ascending per row), val[nnz*bh*bw] (row-major blocks).  Vectors are AoS doubles.
+ *   - one handle == one GPU == one caller thread (the reference's AMGMatrix is not re-entrant either:
+ *     shared work vectors mutated inside const Mult, src/base/solve/amg_matrix.cpp:187-189).
+ *   - vector arguments may be HOST or DEVICE pointers; the library detects which
+ *     (cudaPointerGetAttributes) and stages host buffers through pinned memory.
+ *   - there is no CPU fallback: without a CUDA device every call fails with an error.
+ */
+#ifndef NGSAMG_B200_H
+#define NGSAMG_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct ngsamg_b200 ngsamg_b200_t; /* opaque: owns all device memory of one hierarchy */
+
+typedef struct ngsamg_csr {
+  int64_t nrows, ncols; /* block rows / block cols */
+  int32_t bh, bw;       /* block height / width (1x1 H1; 3x3, 6x6, 3x6, 6x3 elasticity) */
+  const int64_t *rowptr;
+  const int32_t *col;
+  const double *val;
+} ngsamg_csr;
+
+typedef struct ngsamg_level_info {
+  int64_t n;          /* block rows of the level matrix          (AMGMatrix::GetNDof, amg_matrix.cpp:396-)  */
+  int32_t b;          /* block size                                                                  */
+  int64_t nnz;        /* stored blocks of A_l                                                        */
+  int64_t nnz_prol;   /* stored blocks of P_l (0 on the last level)                                  */
+  int64_t ncoarse;    /* columns of P_l                                                              */
+  int32_t bcoarse;    /* block width of P_l                                                          */
+  int32_t gs_depth;   /* number of dependency levels of the level-scheduled Gauss-Seidel sweep       */
+  int64_t bytes_matrix, bytes_prol, bytes_vec; /* algorithmic bytes M_l, P_l, v_l of SURVEY.md §8d   */
+} ngsamg_level_info;
+
+/* ---- construction ------------------------------------------------------------------------------
+ * ngsamg_b200_create replaces the strict-algebraic constructor + InitLevel + (deferred) FinalizeLevel:
+ *   NgsAMG.h1_scal(mat, freedofs, **kwargs)            src/h1/python_h1.cpp:24-33
+ *   BaseAMGPC(A, flags, name); InitLevel(freedofs)     src/base/precond/amg_pc.cpp:346-353, 398-410
+ * `type`      : registered preconditioner name, "h1_scal" | "h1_2d" | "h1_3d" | "elast_2d" | "elast_3d",
+ *               with or without the "NgsAMG." / "ngs_amg." prefix (amg_register.hpp:85-97, elasticity.hpp:104-140)
+ * `A`         : the assembled fine matrix (host arrays, copied)
+ * `free_mask` : freedofs BitArray as bytes, one per block row (NULL = all free)
+ * `vertex_xyz`: nrows x 3 vertex coordinates (elasticity: rigid-body modes; NULL for H1)
+ * `flags`     : nflags (key, value) string pairs, keys as in the reference with the "ngs_amg_" prefix
+ *               (amg_pc.hpp:168-172, Options::SetFromFlags amg_pc.cpp:270-339); unknown keys are ignored like
+ *               NGSolve Flags does.  Lists (`*_spec`) are comma separated.
+ * The hierarchy is not built yet; call ngsamg_b200_set_prolongations (optional) then ngsamg_b200_finalize. */
+int ngsamg_b200_create(const char *type, const ngsamg_csr *A, const uint8_t *free_mask, const double *vertex_xyz,
+                       const char *const *flag_keys, const char *const *flag_vals, int nflags, int device,
+                       ngsamg_b200_t **out);
+
+/* Inject the DOF maps instead of running the built-in coarsening: P[l] maps level l+1 -> level l.
+ * Replaces AMGMatrix(DOFMap([ProlMap...]), smoothers, ...), src/base/solve/python_solve.cpp:57-76. */
+int ngsamg_b200_set_prolongations(ngsamg_b200_t *h, int nprol, const ngsamg_csr *P);
+
+/* BaseAMGPC::FinalizeLevel -> BuildAMGMat (amg_pc.cpp:413-434, 565-736): coarsening + prolongations
+ * (unless injected), Galerkin RAP on the device (ProlMap::AssembleMatrix -> RestrictMatrix, dof_map.cpp:817-834,
+ * utils_sparseMM.hpp:93-109), smoother setup (BuildGSSmoother amg_pc.cpp:1096-1138, GSS3::CalcDiags
+ * gssmoother.cpp:142-170), coarsest inverse (CoarseLevelInv amg_pc.cpp:843-928). */
+int ngsamg_b200_finalize(ngsamg_b200_t *h);
+
+void ngsamg_b200_destroy(ngsamg_b200_t *h);
+const char *ngsamg_b200_last_error(void);
+
+/* ---- preconditioner apply (the hot path) -------------------------------------------------------
+ * x = C b     BaseAMGPC::Mult -> AMGMatrix::Mult -> SmoothV   amg_pc.cpp:467-470, amg_matrix.cpp:160-307, 377-378
+ * x += s C b  AMGMatrix::MultAdd                               amg_matrix.cpp:385-389
+ * MultTrans == Mult and MultTransAdd == MultAdd (amg_matrix.cpp:381-393): call the same entry points. */
+int ngsamg_b200_apply(ngsamg_b200_t *h, const double *b, double *x);
+int ngsamg_b200_apply_add(ngsamg_b200_t *h, double s, const double *b, double *x);
+
+/* y += s * A_level * x   (SparseMatrix::MultAdd on a level matrix; CG's A*s; BaseSmoother::CalcResiduum
+ * base_smoother.hpp:132-142).  level 0 == the matrix given to create(). */
+int ngsamg_b200_spmv_add(ngsamg_b200_t *h, int level, double s, const double *x, double *y);
+
+/* BaseSmoother::Smooth / SmoothBack of the smoother of `level` with the reference flag protocol
+ * (base_smoother.hpp:68-112; GSS3::Smooth/SmoothBack gssmoother.cpp:349-398; ProxySmoother :181-196).
+ * Smoother-only entry == NgsAMG.CreateHybridGSS(...).Smooth, src/base/smoothers/python_smoothers.cpp:144-194. */
+int ngsamg_b200_smooth(ngsamg_b200_t *h, int level, double *x, const double *b, double *res, int res_updated,
+                       int update_res, int x_zero, int backwards);
+
+/* ProlMap::TransferF2C / AddC2F on level `level` (dof_map.cpp:633-654, 694-709):
+ *   restrict: xc = P_l^T xf ;  prolong_add: xf += fac * P_l xc */
+int ngsamg_b200_restrict(ngsamg_b200_t *h, int level, const double *xf, double *xc);
+int ngsamg_b200_prolong_add(ngsamg_b200_t *h, int level, double fac, const double *xc, double *xf);
+
+/* PCG with the V-cycle as preconditioner == ngsolve.krylovspace.CGSolver(mat, pre, maxsteps, tol) as the reference
+ * tests call it (tests/h1/amg_utils.py:346-349).  errors has room for maxsteps+1 doubles (errors[0] = err0);
+ * *iters = CGSolver.iterations.  rhs/x host or device. */
+int ngsamg_b200_pcg(ngsamg_b200_t *h, const double *rhs, double *x, double tol, int maxsteps, int *iters,
+                    double *errors);
+
+/* ---- introspection (AMGMatrix::GetNLevels/GetNDof amg_matrix.cpp:396-, GetOC :551-582) -------------- */
+int ngsamg_b200_num_levels(ngsamg_b200_t *h);
+int ngsamg_b200_level_info(ngsamg_b200_t *h, int level, ngsamg_level_info *info);
+/* copy the level matrix A_l / the prolongation P_l (original DOF numbering) into caller arrays sized from
+ * level_info: rowptr[n+1], col[nnz], val[nnz*b*b] resp. val[nnz_prol*b*bcoarse].  Any pointer may be NULL.
+ * These are what the bit-exact pattern / DOF-map parity tests read. */
+int ngsamg_b200_get_level_matrix(ngsamg_b200_t *h, int level, int64_t *rowptr, int32_t *col, double *val);
+int ngsamg_b200_get_prolongation(ngsamg_b200_t *h, int level, int64_t *rowptr, int32_t *col, double *val);
+/* level work vectors after the last apply: which = 0 x_level, 1 rhs_level, 2 res_level (amg_matrix.cpp:19-26) */
+int ngsamg_b200_get_level_vector(ngsamg_b200_t *h, int level, int which, double *out);
+/* operator complexity sum_l nnz_l*b_l^2 / (nnz_0*b_0^2) (AMGMatrix::GetOC) */
+double ngsamg_b200_operator_complexity(ngsamg_b200_t *h);
+/* algorithmic bytes of one V(1,1)-cycle, SURVEY.md §8d formula B_V, from the actual level sizes */
+double ngsamg_b200_vcycle_bytes(ngsamg_b200_t *h);
+/* device milliseconds (CUDA events on the library stream) of the last apply / pcg call, setup phases */
+double ngsamg_b200_last_ms(ngsamg_b200_t *h, int what); /* 0 apply, 1 pcg, 2 setup total, 3 setup RAP, 4 setup host */
+/* number of kernel launches issued by the library since create (bench.py's gpu_launches) */
+int64_t ngsamg_b200_launch_count(ngsamg_b200_t *h);
+
+/* ---- standalone sparse kernels (setup path) ----------------------------------------------------
+ * Galerkin product on the device: Ac = (P^T A) P.   RestrictMatrix<H,W>, utils_sparseMM.hpp:93-109;
+ * MatMultABImpl utils_sparseMM.cpp:107-238; TransposeSPMImpl :54-93.
+ * Two-call protocol: rap_begin computes the product and returns an opaque result + its sizes; rap_fetch copies it
+ * out and frees it. */
+typedef struct ngsamg_b200_spm ngsamg_b200_spm;
+int ngsamg_b200_rap_begin(const ngsamg_csr *A, const ngsamg_csr *P, int device, ngsamg_b200_spm **out, int64_t *nrows,
+                          int64_t *nnz);
+int ngsamg_b200_matmul_begin(const ngsamg_csr *A, const ngsamg_csr *B, int device, ngsamg_b200_spm **out,
+                             int64_t *nrows, int64_t *nnz);
+int ngsamg_b200_transpose_begin(const ngsamg_csr *A, int device, ngsamg_b200_spm **out, int64_t *nrows, int64_t *nnz);
+int ngsamg_b200_spm_fetch(ngsamg_b200_spm *m, int64_t *rowptr, int32_t *col, double *val);
+
+/* ---- measurement hook (bench.py roofline) ---------------------------------------------------------
+ * Launch ONE kernel of the V-cycle on `level` `reps` times between two CUDA events on the library stream.
+ * which: 0 forward triangular sweep (RES form), 1 U-pass, 2 (L+D)-pass, 3 backward triangular sweep (RHS form),
+ *        4 plain SpMV, 5 restriction, 6 prolongation-add.
+ * ms_avg = average device time of one launch; bytes = algorithmic bytes of one launch. */
+int ngsamg_b200_profile_kernel(ngsamg_b200_t *h, int level, int which, int reps, double *ms_avg, double *bytes);
+
+/* ---- DOF-map construction (host side, no device needed) ------------------------------------------
+ * The built-in coarsening that finalize() runs per level when no prolongations were injected: pairwise agglomeration +
+ * smoothed prolongation in the spirit of BuildCoarseMap / BuildCoarseDOFMap (src/base/factory/vertex_factory_impl.hpp:503-548,
+ * 796-865); see ngsamg_b200/csrc/coarsen.cpp.  bcoarse = coarse block size (== A->bh except elasticity level 0: 3 -> 6).
+ * coarsen_fetch copies P (rowptr[n+1], col, val), the vertex map vmap[n] (-1 = Dirichlet/dropped) and the coarse vertex
+ * coordinates cxyz[ncoarse*3] (only if vertex_xyz was given) and frees the handle. */
+typedef struct ngsamg_b200_hostspm ngsamg_b200_hostspm;
+int ngsamg_b200_coarsen_begin(const ngsamg_csr *A, const uint8_t *free_mask, const double *vertex_xyz, int bcoarse,
+                              int max_per_row, double min_frac, double omega, int smooth, int rounds,
+                              ngsamg_b200_hostspm **out, int64_t *ncoarse, int64_t *nnz);
+int ngsamg_b200_coarsen_fetch(ngsamg_b200_hostspm *m, int64_t *rowptr, int32_t *col, double *val, int32_t *vmap,
+                              double *cxyz);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

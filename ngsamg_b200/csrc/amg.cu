@@ -1,0 +1,1450 @@
+// amg.cu -- the hierarchy object behind the C ABI: setup (layouts, RAP, smoothers, coarse inverse),
+// V-cycle (AMGMatrix::SmoothV, src/base/solve/amg_matrix.cpp:160-307) and PCG on one B200.
+#include <cub/cub.cuh>
+
+#include <chrono>
+#include <memory>
+
+#include "../../include/ngsamg_b200.h"
+#include "device.hpp"
+#include "kernels.cuh"
+
+namespace ngb {
+
+namespace {
+
+constexpr int TILE_ROWS = 256;  // rows per triangular-sweep tile == CTA size
+constexpr int TB = 256;
+
+inline unsigned nblk(i64 n, int tb = TB) { return (unsigned)((n + tb - 1) / tb); }
+inline i64 round32(i64 n) { return (n + 31) / 32 * 32; }
+
+struct Sell {
+  i64 nrows_pad = 0, nslices = 0, total_slots = 0, nnz = 0;
+  int bh = 1, bw = 1;
+  i64 *slice_ptr = nullptr;
+  i32 *col = nullptr;
+  double *val = nullptr;
+  SellView view() const { return SellView{slice_ptr, col, val}; }
+  i64 bytes() const { return nnz * (8 * bh * bw + 4); }
+  void release() { dev_free(slice_ptr); dev_free(col); dev_free(val); }
+};
+
+enum { SM_GS = 0, SM_JACOBI = 1 };
+
+struct Level {
+  i64 n = 0, npad = 0;
+  int b = 1;
+  i64 nnz = 0;
+  HostBsr hA;  // plain matrix, original numbering (kept for introspection when small enough)
+  bool keep_host = true;
+  std::vector<uint8_t> free_mask;  // empty = all free
+  std::vector<i32> perm;           // original -> level-scheduled (padded) row
+  i32 *d_perm = nullptr;
+  uint8_t *d_freep = nullptr;
+  Sell L, U;
+  double *diag = nullptr, *dinv = nullptr;
+  // triangular sweep schedule
+  int depth = 0;
+  i32 ntiles = 0;
+  i32 *d_tile_row0 = nullptr, *d_tile_rows = nullptr, *d_tile_level = nullptr, *d_level_tiles = nullptr;
+  int *d_counters = nullptr;
+  i64 nonfree_pad = 0;  // rows of dependency level 0 (non-free rows), padded
+  // transfer to level+1
+  HostBsr hP;
+  Sell P, PT;
+  i64 nc = 0;
+  int bc = 1;
+  // work vectors, level-scheduled numbering, npad*b doubles
+  double *x = nullptr, *rhs = nullptr, *res = nullptr, *tmp = nullptr, *wa = nullptr, *wb = nullptr;
+  int sm_type = SM_GS, sm_steps = 1;
+  bool sm_symm = false, pinv = false;
+  double omega = 1.0;
+  std::vector<double> xyz;
+  int *d_err = nullptr;
+  TriSchedule sched() const { return TriSchedule{d_tile_row0, d_tile_rows, d_tile_level, d_level_tiles, ntiles, depth, d_err}; }
+};
+
+}  // namespace
+
+struct Amg {
+  std::string type;
+  Flags flags;
+  int device = 0;
+  cudaStream_t st = nullptr;
+  int num_sms = 148;
+  std::vector<std::unique_ptr<Level>> lev;
+  std::vector<HostBsr> injected;
+  bool finalized = false;
+  // coarsest exact solve
+  double *d_cinv = nullptr;
+  int cinv_n = 0;
+  bool has_cinv = false;
+  // V-cycle graph
+  cudaGraphExec_t vgraph = nullptr;
+  i64 vgraph_launches = 0;
+  bool use_graph = true;
+  // pcg vectors (level 0, permuted)
+  double *cg_u = nullptr, *cg_s = nullptr, *cg_q = nullptr, *d_dot = nullptr, *d_partial = nullptr;
+  // host staging (pinned)
+  double *pin_a = nullptr, *pin_b = nullptr;
+  i64 pin_n = 0;
+  double *io_a = nullptr, *io_b = nullptr, *io_c = nullptr;  // device staging in original numbering
+  i64 io_n = 0;
+  i64 launches = 0;
+  double ms_apply = 0, ms_pcg = 0, ms_setup = 0, ms_rap = 0, ms_host = 0;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  int tri_grid_cap[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  int *d_err = nullptr;
+  void check_watchdog();
+
+  ~Amg();
+  void finalize();
+  void build_level_layout(Level &L, const DevCsr &dA);
+  void build_transfer_layout(Level &F, Level &C);
+  void build_coarse_inverse(Level &L);
+  void alloc_vectors(Level &L);
+  // device primitives on level-scheduled vectors
+  template <int B> void tri(Level &L, bool backward, bool add_self, bool write_r, const double *rin, double *out, double *rout);
+  void tri_dispatch(Level &L, bool backward, bool add_self, bool write_r, const double *rin, double *out, double *rout);
+  void spmv_part(Level &L, int which /*0 L,1 U,2 L+D,3 U+D,4 full*/, const double *v, const double *y_in, double *y_out,
+                 double alpha, double beta, double *xadd);
+  void transfer(const Sell &S, const double *v, const double *y_in, double *y_out, double alpha, double beta);
+  void calc_residuum(Level &L, const double *x, const double *b, double *res, bool x_zero);
+  void gs_res(Level &L, bool backward, double *x, double *res, bool x_zero);
+  void gs_rhs(Level &L, bool backward, double *x, const double *b);
+  void smooth_once(Level &L, double *x, const double *b, double *res, bool ru, bool ur, bool xz, bool backward);
+  void level_smooth(Level &L, double *x, const double *b, double *res, bool ru, bool ur, bool xz, bool backward);
+  void vcycle_record();
+  void vcycle();  // rhs = lev[0].rhs -> x = lev[0].x
+  double dot(i64 n, const double *a, const double *b);
+  // io helpers
+  void ensure_io(i64 n);
+  const double *to_device(const double *p, i64 n, double *stage);
+  bool is_device_ptr(const void *p);
+  void from_device(double *dst, const double *src_dev, i64 n);
+};
+
+namespace {
+
+template <class T>
+T *upload_vec(const std::vector<T> &v, cudaStream_t st)
+{
+  T *d = dev_alloc<T>(v.size());
+  if (!v.empty()) NGB_CUDA(cudaMemcpyAsync(d, v.data(), sizeof(T) * v.size(), cudaMemcpyHostToDevice, st));
+  NGB_CUDA(cudaStreamSynchronize(st));
+  return d;
+}
+
+// Gauss-Seidel dependency levels in the reference's row order (gssmoother.cpp:195-315): non-free rows form
+// level 0 (they are never updated), a free row sits one level above its deepest free lower neighbour.
+void level_schedule(const HostBsr &A, const std::vector<uint8_t> &free_mask, bool smoothed, Level &L, cudaStream_t st)
+{
+  const i64 n = A.nrows;
+  std::vector<i32> lvl(n, 0);
+  i32 depth = 1;
+  if (smoothed) {
+    const bool hf = !free_mask.empty();
+    for (i64 i = 0; i < n; i++) {
+      if (hf && !free_mask[i]) { lvl[i] = 0; continue; }
+      i32 m = 0;
+      for (i64 k = A.rowptr[i]; k < A.rowptr[i + 1]; k++) {
+        const i32 j = A.col[k];
+        if (j >= i) break;  // columns ascending
+        if (hf && !free_mask[j]) continue;
+        m = std::max(m, lvl[j]);
+      }
+      lvl[i] = m + 1;
+      depth = std::max(depth, m + 2);
+    }
+  }
+  std::vector<i64> cnt(depth, 0);
+  for (i64 i = 0; i < n; i++) cnt[lvl[i]]++;
+  // drop an empty level 0 (no Dirichlet rows)
+  int shift = (smoothed && cnt[0] == 0 && depth > 1) ? 1 : 0;
+  std::vector<i64> start(depth + 1, 0);
+  for (int l = shift; l < depth; l++) start[l + 1] = start[l] + round32(cnt[l]);
+  L.npad = std::max<i64>(start[depth], 32);
+  L.depth = depth - shift;
+  L.nonfree_pad = (shift == 0 && smoothed) ? round32(cnt[0]) : 0;
+  L.perm.resize(n);
+  std::vector<i64> pos(start.begin(), start.end() - 1);
+  for (i64 i = 0; i < n; i++) L.perm[i] = (i32)(pos[lvl[i]]++);
+  // tiles
+  std::vector<i32> row0, rows, tl, ltiles(L.depth, 0);
+  for (int l = shift; l < depth; l++) {
+    const i64 len = round32(cnt[l]);
+    for (i64 o = 0; o < len; o += TILE_ROWS) {
+      row0.push_back((i32)(start[l] + o));
+      rows.push_back((i32)std::min<i64>(TILE_ROWS, len - o));
+      tl.push_back(l - shift);
+      ltiles[l - shift]++;
+    }
+  }
+  L.ntiles = (i32)row0.size();
+  L.d_tile_row0 = upload_vec(row0, st);
+  L.d_tile_rows = upload_vec(rows, st);
+  L.d_tile_level = upload_vec(tl, st);
+  L.d_level_tiles = upload_vec(ltiles, st);
+  L.d_counters = dev_alloc<int>(L.depth + 2);
+}
+
+void build_sell(i64 nrows_pad, int bh, int bw, const i32 *d_len, Sell &S, cudaStream_t st, i64 *launches)
+{
+  S.nrows_pad = nrows_pad; S.nslices = nrows_pad / 32; S.bh = bh; S.bw = bw;
+  i64 *width = dev_alloc<i64>(S.nslices + 1);
+  NGB_CUDA(cudaMemsetAsync(width, 0, sizeof(i64) * (S.nslices + 1), st));
+  k_layout_width<<<nblk(S.nslices * 32), TB, 0, st>>>(S.nslices, d_len, width);
+  S.slice_ptr = dev_alloc<i64>(S.nslices + 1);
+  size_t tb = 0;
+  cub::DeviceScan::ExclusiveSum(nullptr, tb, width, S.slice_ptr, S.nslices + 1, st);
+  void *tmp = dev_alloc<char>(tb);
+  cub::DeviceScan::ExclusiveSum(tmp, tb, width, S.slice_ptr, S.nslices + 1, st);
+  NGB_CUDA(cudaMemcpyAsync(&S.total_slots, S.slice_ptr + S.nslices, sizeof(i64), cudaMemcpyDeviceToHost, st));
+  NGB_CUDA(cudaStreamSynchronize(st));
+  cudaFree(tmp);
+  dev_free(width);
+  S.col = dev_alloc<i32>(S.total_slots * 32);
+  S.val = dev_alloc<double>(S.total_slots * 32 * bh * bw);
+  NGB_CUDA(cudaMemsetAsync(S.col, 0xFF, sizeof(i32) * std::max<i64>(S.total_slots * 32, 1), st));
+  NGB_CUDA(cudaMemsetAsync(S.val, 0, sizeof(double) * std::max<i64>(S.total_slots * 32 * bh * bw, 1), st));
+  if (launches) *launches += 2;
+}
+
+// dense inverse of an SPD-ish matrix by Gauss-Jordan with partial pivoting (host, setup only)
+bool dense_invert(int n, std::vector<double> &a)
+{
+  std::vector<double> inv((size_t)n * n, 0.0);
+  for (int i = 0; i < n; i++) inv[(size_t)i * n + i] = 1.0;
+  for (int c = 0; c < n; c++) {
+    int p = c;
+    double best = std::fabs(a[(size_t)c * n + c]);
+    for (int r = c + 1; r < n; r++)
+      if (std::fabs(a[(size_t)r * n + c]) > best) { best = std::fabs(a[(size_t)r * n + c]); p = r; }
+    if (best == 0.0) return false;
+    if (p != c)
+      for (int q = 0; q < n; q++) { std::swap(a[(size_t)c * n + q], a[(size_t)p * n + q]); std::swap(inv[(size_t)c * n + q], inv[(size_t)p * n + q]); }
+    const double pv = 1.0 / a[(size_t)c * n + c];
+    for (int q = 0; q < n; q++) { a[(size_t)c * n + q] *= pv; inv[(size_t)c * n + q] *= pv; }
+    parallel_for(n, [&](i64 lo, i64 hi) {
+      for (i64 r = lo; r < hi; r++) {
+        if (r == c) continue;
+        const double f = a[(size_t)r * n + c];
+        if (f == 0.0) continue;
+        for (int q = 0; q < n; q++) { a[(size_t)r * n + q] -= f * a[(size_t)c * n + q]; inv[(size_t)r * n + q] -= f * inv[(size_t)c * n + q]; }
+      }
+    }, 64);
+  }
+  a.swap(inv);
+  return true;
+}
+
+// host pseudo-inverse of one small symmetric block (CalcPseudoInverseTryNormal, utils_denseLA.hpp:1474-1569)
+void block_pinv(int n, double *m)
+{
+  if (n == 1) { m[0] = std::fabs(m[0]) > 1e-20 ? 1.0 / m[0] : 0.0; return; }
+  std::vector<int> idx;
+  for (int i = 0; i < n; i++) if (std::fabs(m[i * n + i]) > 1e-20) idx.push_back(i);
+  const int k = (int)idx.size();
+  std::vector<double> sub((size_t)k * k), keep;
+  for (int i = 0; i < k; i++) for (int j = 0; j < k; j++) sub[i * k + j] = m[idx[i] * n + idx[j]];
+  keep = sub;
+  bool ok = false;
+  if (k > 0) {
+    std::vector<double> t = sub;
+    if (dense_invert(k, t)) {
+      double err = 0;
+      for (int i = 0; i < k; i++) for (int j = 0; j < k; j++) {
+        double s = 0;
+        for (int l = 0; l < k; l++) s += keep[i * k + l] * t[l * k + j];
+        const double d = s - (i == j ? 1.0 : 0.0);
+        err += d * d;
+      }
+      ok = std::sqrt(err / (k * k)) < 1e-8;
+      if (ok) sub = t;
+    }
+    if (!ok) {
+      // cyclic Jacobi eigen-decomposition, eigenvalues <= 1e-12 * mean are treated as kernel
+      std::vector<double> a = keep, V((size_t)k * k, 0.0);
+      for (int i = 0; i < k; i++) V[i * k + i] = 1.0;
+      for (int sweep = 0; sweep < 100; sweep++) {
+        double off = 0;
+        for (int i = 0; i < k; i++) for (int j = i + 1; j < k; j++) off += a[i * k + j] * a[i * k + j];
+        if (off < 1e-300) break;
+        for (int p = 0; p < k; p++) for (int q = p + 1; q < k; q++) {
+          const double apq = a[p * k + q];
+          if (std::fabs(apq) < 1e-300) continue;
+          const double theta = (a[q * k + q] - a[p * k + p]) / (2.0 * apq);
+          const double tt = (theta >= 0 ? 1.0 : -1.0) / (std::fabs(theta) + std::sqrt(theta * theta + 1.0));
+          const double c = 1.0 / std::sqrt(tt * tt + 1.0), s = tt * c;
+          for (int r = 0; r < k; r++) { double x = a[r * k + p], y = a[r * k + q]; a[r * k + p] = c * x - s * y; a[r * k + q] = s * x + c * y; }
+          for (int r = 0; r < k; r++) { double x = a[p * k + r], y = a[q * k + r]; a[p * k + r] = c * x - s * y; a[q * k + r] = s * x + c * y; }
+          for (int r = 0; r < k; r++) { double x = V[p * k + r], y = V[q * k + r]; V[p * k + r] = c * x - s * y; V[q * k + r] = s * x + c * y; }
+        }
+      }
+      double tol = 0;
+      for (int i = 0; i < k; i++) tol += a[i * k + i];
+      tol = std::max(1e-12 * tol / k, 1e-20);
+      for (int i = 0; i < k; i++) for (int j = 0; j < k; j++) {
+        double s = 0;
+        for (int e = 0; e < k; e++) { const double ev = a[e * k + e]; if (ev > tol) s += V[e * k + i] * V[e * k + j] / ev; }
+        sub[i * k + j] = s;
+      }
+    }
+  }
+  for (int i = 0; i < n * n; i++) m[i] = 0.0;
+  for (int i = 0; i < k; i++) for (int j = 0; j < k; j++) m[idx[i] * n + idx[j]] = sub[i * k + j];
+}
+
+}  // namespace
+
+Amg::~Amg()
+{
+  if (device >= 0) cudaSetDevice(device);
+  for (auto &lp : lev) {
+    Level &L = *lp;
+    dev_free(L.d_perm); dev_free(L.d_freep);
+    L.L.release(); L.U.release(); L.P.release(); L.PT.release();
+    dev_free(L.diag); dev_free(L.dinv);
+    dev_free(L.d_tile_row0); dev_free(L.d_tile_rows); dev_free(L.d_tile_level); dev_free(L.d_level_tiles); dev_free(L.d_counters);
+    dev_free(L.x); dev_free(L.rhs); dev_free(L.res); dev_free(L.tmp); dev_free(L.wa); dev_free(L.wb);
+  }
+  dev_free(d_cinv); dev_free(cg_u); dev_free(cg_s); dev_free(cg_q); dev_free(d_dot); dev_free(d_partial);
+  dev_free(io_a); dev_free(io_b); dev_free(io_c); dev_free(d_err);
+  if (pin_a) cudaFreeHost(pin_a);
+  if (pin_b) cudaFreeHost(pin_b);
+  if (vgraph) cudaGraphExecDestroy(vgraph);
+  if (ev0) cudaEventDestroy(ev0);
+  if (ev1) cudaEventDestroy(ev1);
+  if (st) cudaStreamDestroy(st);
+}
+
+void Amg::alloc_vectors(Level &L)
+{
+  const size_t nb = (size_t)L.npad * L.b;
+  for (double **p : {&L.x, &L.rhs, &L.res, &L.tmp}) {
+    *p = dev_alloc<double>(nb);
+    NGB_CUDA(cudaMemsetAsync(*p, 0, nb * sizeof(double), st));
+  }
+}
+
+// plain CSR on the device (original numbering) -> level-scheduled split SELL layout + dinv
+void Amg::build_level_layout(Level &L, const DevCsr &dA)
+{
+  const i64 n = L.n;
+  const int b = L.b, bs = b * b;
+  L.d_perm = upload_vec(L.perm, st);
+  // permuted free flags (padding rows = not free)
+  {
+    std::vector<uint8_t> fp(L.npad, 0);
+    for (i64 i = 0; i < n; i++) fp[L.perm[i]] = L.free_mask.empty() ? 1 : L.free_mask[i];
+    L.d_freep = upload_vec(fp, st);
+  }
+  i32 *len1 = dev_alloc<i32>(L.npad), *len2 = dev_alloc<i32>(L.npad);
+  NGB_CUDA(cudaMemsetAsync(len1, 0, sizeof(i32) * L.npad, st));
+  NGB_CUDA(cudaMemsetAsync(len2, 0, sizeof(i32) * L.npad, st));
+  k_layout_count<<<nblk(n), TB, 0, st>>>(n, dA.rowptr, dA.col, L.d_perm, L.d_perm, 1, len1, len2);
+  build_sell(L.npad, b, b, len1, L.L, st, &launches);
+  build_sell(L.npad, b, b, len2, L.U, st, &launches);
+  L.diag = dev_alloc<double>((size_t)L.npad * bs);
+  L.dinv = dev_alloc<double>((size_t)L.npad * bs);
+  NGB_CUDA(cudaMemsetAsync(L.diag, 0, sizeof(double) * L.npad * bs, st));
+  k_layout_fill<<<nblk(n), TB, 0, st>>>(n, bs, dA.rowptr, dA.col, dA.val, L.d_perm, L.d_perm, 1, L.L.slice_ptr, L.L.col, L.L.val,
+                                        L.U.slice_ptr, L.U.col, L.U.val, L.diag);
+  launches += 2;
+  // true entry counts (for the byte model)
+  {
+    std::vector<i32> h1(L.npad), h2(L.npad);
+    NGB_CUDA(cudaMemcpyAsync(h1.data(), len1, sizeof(i32) * L.npad, cudaMemcpyDeviceToHost, st));
+    NGB_CUDA(cudaMemcpyAsync(h2.data(), len2, sizeof(i32) * L.npad, cudaMemcpyDeviceToHost, st));
+    NGB_CUDA(cudaStreamSynchronize(st));
+    i64 a = 0, c = 0;
+    for (i64 i = 0; i < L.npad; i++) { a += h1[i]; c += h2[i]; }
+    L.L.nnz = a; L.U.nnz = c;
+  }
+  dev_free(len1); dev_free(len2);
+  // dinv (GSS3::CalcDiags)
+  int *d_err = dev_alloc<int>(1);
+  NGB_CUDA(cudaMemsetAsync(d_err, 0, sizeof(int), st));
+  if (!L.pinv || L.sm_type == SM_JACOBI) {
+    switch (b) {
+      case 1: k_calc_dinv<1><<<nblk(L.npad), TB, 0, st>>>(L.npad, L.diag, L.d_freep, L.dinv, d_err); break;
+      case 2: k_calc_dinv<2><<<nblk(L.npad), TB, 0, st>>>(L.npad, L.diag, L.d_freep, L.dinv, d_err); break;
+      case 3: k_calc_dinv<3><<<nblk(L.npad), TB, 0, st>>>(L.npad, L.diag, L.d_freep, L.dinv, d_err); break;
+      case 6: k_calc_dinv<6><<<nblk(L.npad, 64), 64, 0, st>>>(L.npad, L.diag, L.d_freep, L.dinv, d_err); break;
+      default: throw Error("unsupported block size " + std::to_string(b));
+    }
+    launches++;
+    int herr = 0;
+    NGB_CUDA(cudaMemcpyAsync(&herr, d_err, sizeof(int), cudaMemcpyDeviceToHost, st));
+    NGB_CUDA(cudaStreamSynchronize(st));
+    if (herr) { dev_free(d_err); throw Error("singular diagonal block in smoother setup (use ngs_amg_regularize_cmats)"); }
+  } else {
+    // regularize_cmats => pinv smoothers (amg_pc.cpp:1124-1130): small host job, blocks round-trip through AoS
+    double *aos = dev_alloc<double>((size_t)L.npad * bs);
+    k_planar_to_aos<<<nblk(L.npad), TB, 0, st>>>(L.npad, bs, L.diag, aos);
+    std::vector<double> h((size_t)L.npad * bs);
+    std::vector<uint8_t> fp(L.npad);
+    NGB_CUDA(cudaMemcpyAsync(h.data(), aos, sizeof(double) * h.size(), cudaMemcpyDeviceToHost, st));
+    NGB_CUDA(cudaMemcpyAsync(fp.data(), L.d_freep, L.npad, cudaMemcpyDeviceToHost, st));
+    NGB_CUDA(cudaStreamSynchronize(st));
+    parallel_for(L.npad, [&](i64 lo, i64 hi) {
+      for (i64 r = lo; r < hi; r++) {
+        if (!fp[r]) { for (int e = 0; e < bs; e++) h[r * bs + e] = 0.0; continue; }
+        block_pinv(b, &h[r * bs]);
+      }
+    }, 256);
+    NGB_CUDA(cudaMemcpyAsync(aos, h.data(), sizeof(double) * h.size(), cudaMemcpyHostToDevice, st));
+    k_aos_to_planar<<<nblk(L.npad), TB, 0, st>>>(L.npad, bs, aos, L.dinv);
+    NGB_CUDA(cudaStreamSynchronize(st));
+    launches += 2;
+    dev_free(aos);
+  }
+  dev_free(d_err);
+}
+
+void Amg::build_transfer_layout(Level &F, Level &C)
+{
+  // P: rows = fine (level-scheduled), cols = coarse (level-scheduled); PT the other way round
+  HostBsr PT;
+  host_transpose(F.hP, PT);
+  DevCsr dP, dPT;
+  dev_csr_upload(F.hP, dP, st);
+  dev_csr_upload(PT, dPT, st);
+  {
+    i32 *len = dev_alloc<i32>(F.npad);
+    NGB_CUDA(cudaMemsetAsync(len, 0, sizeof(i32) * F.npad, st));
+    k_layout_count<<<nblk(F.n), TB, 0, st>>>(F.n, dP.rowptr, dP.col, F.d_perm, C.d_perm, 0, len, nullptr);
+    build_sell(F.npad, F.b, F.bc, len, F.P, st, &launches);
+    k_layout_fill<<<nblk(F.n), TB, 0, st>>>(F.n, F.b * F.bc, dP.rowptr, dP.col, dP.val, F.d_perm, C.d_perm, 0, F.P.slice_ptr, F.P.col,
+                                            F.P.val, nullptr, nullptr, nullptr, nullptr);
+    F.P.nnz = dP.nnz;
+    dev_free(len);
+  }
+  {
+    i32 *len = dev_alloc<i32>(C.npad);
+    NGB_CUDA(cudaMemsetAsync(len, 0, sizeof(i32) * C.npad, st));
+    k_layout_count<<<nblk(C.n), TB, 0, st>>>(C.n, dPT.rowptr, dPT.col, C.d_perm, F.d_perm, 0, len, nullptr);
+    build_sell(C.npad, F.bc, F.b, len, F.PT, st, &launches);
+    k_layout_fill<<<nblk(C.n), TB, 0, st>>>(C.n, F.b * F.bc, dPT.rowptr, dPT.col, dPT.val, C.d_perm, F.d_perm, 0, F.PT.slice_ptr,
+                                            F.PT.col, F.PT.val, nullptr, nullptr, nullptr, nullptr);
+    F.PT.nnz = dPT.nnz;
+    dev_free(len);
+  }
+  launches += 4;
+  NGB_CUDA(cudaStreamSynchronize(st));
+  dev_csr_free(dP);
+  dev_csr_free(dPT);
+}
+
+// CoarseLevelInv (amg_pc.cpp:843-928): exact inverse of the coarsest matrix on its free dofs; here an explicit
+// dense inverse (the level has at most a few thousand scalar dofs) applied as a GEMV on the device.
+void Amg::build_coarse_inverse(Level &L)
+{
+  const int b = L.b;
+  const i64 N = L.n * b;
+  if (N > 8192) throw Error("coarsest level too large for the dense inverse (" + std::to_string(N) + " scalar dofs); raise ngs_amg_max_levels");
+  const HostBsr &A = L.hA;
+  std::vector<i64> g2l(N, -1), l2g;
+  for (i64 i = 0; i < L.n; i++)
+    for (int p = 0; p < b; p++)
+      if (L.free_mask.empty() || L.free_mask[i]) { g2l[i * b + p] = (i64)l2g.size(); l2g.push_back(i * b + p); }
+  const int cn = (int)l2g.size();
+  std::vector<double> M((size_t)cn * cn, 0.0);
+  for (i64 i = 0; i < L.n; i++)
+    for (i64 k = A.rowptr[i]; k < A.rowptr[i + 1]; k++)
+      for (int p = 0; p < b; p++)
+        for (int q = 0; q < b; q++) {
+          const i64 r = g2l[i * b + p], c = g2l[(i64)A.col[k] * b + q];
+          if (r >= 0 && c >= 0) M[(size_t)r * cn + c] = A.val[k * b * b + p * b + q];
+        }
+  if (cn > 0 && !dense_invert(cn, M)) throw Error("coarsest level matrix is singular");
+  // embed into the padded level numbering (identity permutation on the coarsest level)
+  const i64 NP = L.npad * b;
+  std::vector<double> full((size_t)NP * NP, 0.0);
+  for (int r = 0; r < cn; r++)
+    for (int c = 0; c < cn; c++) full[(size_t)L.perm[l2g[r] / b] * b * NP + (l2g[r] % b) * NP + (size_t)L.perm[l2g[c] / b] * b + (l2g[c] % b)] = M[(size_t)r * cn + c];
+  d_cinv = upload_vec(full, st);
+  cinv_n = (int)NP;
+  has_cinv = true;
+}
+
+// ------------------------------------------------------------------------------------------------
+// setup driver == BaseAMGPC::BuildAMGMat (amg_pc.cpp:565-736) + BaseAMGFactory::SetUpLevels (base_factory.cpp:219-353)
+// ------------------------------------------------------------------------------------------------
+void Amg::finalize()
+{
+  if (finalized) throw Error("finalize called twice");
+  auto t0 = std::chrono::steady_clock::now();
+  double host_s = 0, rap_ms = 0;
+  const int max_levels = (int)flags.num("max_levels", 10);            // base_factory.hpp:88-152
+  const i64 max_coarse = (i64)flags.num("max_coarse_size", 50);
+  const std::string cycle = flags.str("mg_cycle", "V");
+  if (cycle != "V" && cycle != "v") throw Error("mg_cycle=" + cycle + " is not supported by the B200 path (V only)");
+  const std::string clev = flags.str("clev", "inv");
+  const bool elast = type.find("elast") != std::string::npos;
+  const int dim = (type.find("2d") != std::string::npos) ? 2 : 3;
+  const bool regularize = flags.flag("regularize_cmats", elast);        // elasticity_pc_impl.hpp:139, h1_impl.hpp:275-279
+  CoarsenOptions copt;
+  copt.max_per_row = (int)flags.num("sp_max_per_row", elast ? 1 + dim : 3);
+  copt.min_frac = flags.num("sp_min_frac", dim == 3 ? 0.08 : 0.1);
+  copt.omega = flags.num("sp_omega", 1.0);
+  copt.smooth = flags.str("prol_type", "semi_aux_smoothed") != "piecewise";
+  copt.rounds = (int)flags.num("spw_rounds", 3);
+
+  d_err = dev_alloc<int>(1);
+  NGB_CUDA(cudaMemsetAsync(d_err, 0, sizeof(int), st));
+  DevCsr dA;
+  dev_csr_upload(lev[0]->hA, dA, st);
+  for (int l = 0;; l++) {
+    Level &L = *lev[l];
+    L.n = L.hA.nrows; L.b = L.hA.bh; L.nnz = L.hA.nnz();
+    bool coarsest = injected.empty() ? (l + 1 >= max_levels || L.n <= max_coarse) : (l >= (int)injected.size());
+    if (!coarsest) {
+      auto h0 = std::chrono::steady_clock::now();
+      if (!injected.empty()) {
+        L.hP = injected[l];
+        if (L.hP.nrows != L.n || L.hP.bh != L.b) throw Error("injected prolongation " + std::to_string(l) + " does not match the level");
+      } else {
+        // elasticity: displacement-only fine level (b = dim) maps to displacement+rotation coarse levels
+        int bc = L.b;
+        if (elast && l == 0 && L.b == dim) bc = (dim == 3) ? 6 : 3;
+        std::vector<i32> vmap;
+        std::vector<double> cxyz;
+        build_prolongation(L.hA, L.free_mask.empty() ? nullptr : L.free_mask.data(), bc, L.xyz, copt, L.hP, vmap, cxyz);
+        if (L.hP.ncols == 0 || L.hP.ncols > 0.8 * L.n) coarsest = true;  // coarsening stalled
+        else {
+          auto nl = std::make_unique<Level>();
+          nl->xyz = std::move(cxyz);
+          lev.push_back(std::move(nl));
+        }
+      }
+      host_s += std::chrono::duration<double>(std::chrono::steady_clock::now() - h0).count();
+    }
+    // smoother options for this level (SpecOpt semantics)
+    {
+      const std::string smt = flags.spec("sm_type", l, "gs");
+      if (smt == "gs") L.sm_type = SM_GS;
+      else if (smt == "jacobi") L.sm_type = SM_JACOBI;
+      else throw Error("sm_type=" + smt + " is not supported by the B200 path (gs | jacobi)");
+      L.sm_steps = std::max(1, std::atoi(flags.spec("sm_steps", l, "1").c_str()));
+      const std::string sy = flags.spec("sm_symm", l, "0");
+      L.sm_symm = (sy == "1" || sy == "True" || sy == "true");
+      L.omega = (L.sm_type == SM_JACOBI) ? flags.num("sm_omega", 0.9) : 1.0;
+      L.pinv = regularize;
+    }
+    DevCsr dAc;
+    if (!coarsest) {
+      // Galerkin product on the device: A_{l+1} = (P^T A_l) P
+      if (injected.empty() == false && l + 1 >= (int)lev.size()) lev.push_back(std::make_unique<Level>());
+      cudaEventRecord(ev0, st);
+      HostBsr PT;
+      host_transpose(L.hP, PT);
+      DevCsr dP, dPT, dPTA;
+      dev_csr_upload(L.hP, dP, st);
+      dev_csr_upload(PT, dPT, st);
+      dev_spgemm(dPT, dA, dPTA, st, &launches);
+      dev_spgemm(dPTA, dP, dAc, st, &launches);
+      dev_csr_free(dPTA); dev_csr_free(dP); dev_csr_free(dPT);
+      cudaEventRecord(ev1, st);
+      cudaEventSynchronize(ev1);
+      float ms = 0;
+      cudaEventElapsedTime(&ms, ev0, ev1);
+      rap_ms += ms;
+      L.nc = L.hP.ncols; L.bc = L.hP.bw;
+      dev_csr_download(dAc, lev[l + 1]->hA, st, true);
+    }
+    {
+      auto h0 = std::chrono::steady_clock::now();
+      level_schedule(L.hA, L.free_mask, !coarsest, L, st);
+      L.d_err = d_err;
+      host_s += std::chrono::duration<double>(std::chrono::steady_clock::now() - h0).count();
+    }
+    if (!coarsest) build_level_layout(L, dA);
+    else {
+      L.d_perm = upload_vec(L.perm, st);
+      if (clev == "inv") build_coarse_inverse(L);
+    }
+    alloc_vectors(L);
+    dev_csr_free(dA);
+    if (coarsest) { lev.resize(l + 1); break; }
+    dA = dAc;
+  }
+  for (size_t l = 0; l + 1 < lev.size(); l++) build_transfer_layout(*lev[l], *lev[l + 1]);
+  // host copies of big matrices are dropped (introspection then only reports sizes)
+  for (auto &lp : lev)
+    if ((double)lp->hA.nnz() * lp->hA.bs() > flags.num("keep_host_nnz", 4e8)) { lp->keep_host = false; HostBsr().rowptr.swap(lp->hA.rowptr); std::vector<i32>().swap(lp->hA.col); std::vector<double>().swap(lp->hA.val); }
+  d_dot = dev_alloc<double>(4);
+  d_partial = dev_alloc<double>(DOT_BLOCKS);
+  NGB_CUDA(cudaStreamSynchronize(st));
+  finalized = true;
+  ms_setup = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+  ms_rap = rap_ms;
+  ms_host = host_s * 1e3;
+}
+
+// ------------------------------------------------------------------------------------------------
+// device primitives
+// ------------------------------------------------------------------------------------------------
+template <int B>
+void Amg::tri(Level &L, bool backward, bool add_self, bool write_r, const double *rin, double *out, double *rout)
+{
+  const Sell &T = backward ? L.U : L.L;
+  NGB_CUDA(cudaMemsetAsync(L.d_counters, 0, sizeof(int) * (L.depth + 2), st));
+  int idx = (B == 1 ? 0 : B == 2 ? 1 : B == 3 ? 2 : 3) * 2 + (add_self ? 1 : 0);
+  auto launch = [&](auto kern) {
+    if (!tri_grid_cap[idx]) {
+      int occ = 0;
+      NGB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, TILE_ROWS, 0));
+      tri_grid_cap[idx] = std::max(1, occ) * num_sms;
+    }
+    const int grid = std::min<int>(L.ntiles, tri_grid_cap[idx]);
+    kern<<<grid, TILE_ROWS, 0, st>>>(T.view(), L.diag, L.dinv, rin, out, rout, L.sched(), backward ? 1 : 0, L.d_counters);
+  };
+  if (add_self) launch(k_gs_tri<B, true, false>);
+  else if (write_r) launch(k_gs_tri<B, false, true>);
+  else throw Error("tri: unsupported mode");
+  launches += 2;
+}
+
+void Amg::tri_dispatch(Level &L, bool backward, bool add_self, bool write_r, const double *rin, double *out, double *rout)
+{
+  switch (L.b) {
+    case 1: tri<1>(L, backward, add_self, write_r, rin, out, rout); break;
+    case 2: tri<2>(L, backward, add_self, write_r, rin, out, rout); break;
+    case 3: tri<3>(L, backward, add_self, write_r, rin, out, rout); break;
+    case 6: tri<6>(L, backward, add_self, write_r, rin, out, rout); break;
+    default: throw Error("unsupported block size");
+  }
+}
+
+template <int BH, int BW, bool S2, bool D>
+static void launch_spmv(cudaStream_t st, i64 npad, const Sell &a, const Sell *b, const double *diag, const double *v, const double *y_in,
+                        double *y_out, double alpha, double beta, double *xadd)
+{
+  k_sell_spmv<BH, BW, S2, D><<<nblk(npad), TB, 0, st>>>(npad, a.view(), b ? b->view() : a.view(), diag, v, y_in, y_out, alpha, beta, xadd);
+}
+
+void Amg::spmv_part(Level &L, int which, const double *v, const double *y_in, double *y_out, double alpha, double beta, double *xadd)
+{
+  const Sell &A1 = (which == 1 || which == 3) ? L.U : L.L;
+  const bool s2 = (which == 4), d = (which >= 2);
+#define NGB_SPMV(B)                                                                                                     \
+  if (s2) launch_spmv<B, B, true, true>(st, L.npad, L.L, &L.U, L.diag, v, y_in, y_out, alpha, beta, xadd);             \
+  else if (d) launch_spmv<B, B, false, true>(st, L.npad, A1, nullptr, L.diag, v, y_in, y_out, alpha, beta, xadd);       \
+  else launch_spmv<B, B, false, false>(st, L.npad, A1, nullptr, L.diag, v, y_in, y_out, alpha, beta, xadd);
+  switch (L.b) {
+    case 1: NGB_SPMV(1) break;
+    case 2: NGB_SPMV(2) break;
+    case 3: NGB_SPMV(3) break;
+    case 6: NGB_SPMV(6) break;
+    default: throw Error("unsupported block size");
+  }
+#undef NGB_SPMV
+  launches++;
+}
+
+void Amg::transfer(const Sell &S, const double *v, const double *y_in, double *y_out, double alpha, double beta)
+{
+  const int key = S.bh * 10 + S.bw;
+#define NGB_TR(H, W) launch_spmv<H, W, false, false>(st, S.nrows_pad, S, nullptr, nullptr, v, y_in, y_out, alpha, beta, nullptr)
+  switch (key) {
+    case 11: NGB_TR(1, 1); break;
+    case 22: NGB_TR(2, 2); break;
+    case 33: NGB_TR(3, 3); break;
+    case 66: NGB_TR(6, 6); break;
+    case 36: NGB_TR(3, 6); break;
+    case 63: NGB_TR(6, 3); break;
+    case 23: NGB_TR(2, 3); break;
+    case 32: NGB_TR(3, 2); break;
+    default: throw Error("unsupported transfer block shape");
+  }
+#undef NGB_TR
+  launches++;
+}
+
+// BaseSmoother::CalcResiduum (base_smoother.hpp:132-142)
+void Amg::calc_residuum(Level &L, const double *x, const double *b, double *res, bool x_zero)
+{
+  if (x_zero) { NGB_CUDA(cudaMemcpyAsync(res, b, sizeof(double) * L.npad * L.b, cudaMemcpyDeviceToDevice, st)); return; }
+  spmv_part(L, 4, x, b, res, -1.0, 1.0, nullptr);
+}
+
+// GSS3::SmoothRESInternal (gssmoother.cpp:260-315) in gather form: with delta = (T + D~)^-1 res (T = L forward, U backward),
+// x += delta and res -= A delta.  The triangular part runs level-scheduled, the other half is a plain SpMV.
+void Amg::gs_res(Level &L, bool backward, double *x, double *res, bool x_zero)
+{
+  double *d = x_zero ? x : L.tmp;
+  if (L.nonfree_pad) NGB_CUDA(cudaMemsetAsync(d, 0, sizeof(double) * L.nonfree_pad * L.b, st));
+  tri_dispatch(L, backward, false, true, res, d, res);
+  spmv_part(L, backward ? 0 : 1, d, res, res, -1.0, 1.0, x_zero ? nullptr : x);
+}
+
+// GSS3::SmoothRHSInternal (gssmoother.cpp:195-257): x_i += dinv_i (b_i - A_i x); the not-yet-updated half of the row
+// (and the diagonal) is applied first as a plain SpMV, the updated half level-scheduled.
+void Amg::gs_rhs(Level &L, bool backward, double *x, const double *b)
+{
+  spmv_part(L, backward ? 2 : 3, x, b, L.tmp, -1.0, 1.0, nullptr);
+  tri_dispatch(L, backward, true, false, L.tmp, x, nullptr);
+}
+
+// GSS3::Smooth / SmoothBack (gssmoother.cpp:349-398); RichardsonSmoother::Smooth for Jacobi (base_smoother.cpp:61-83)
+void Amg::smooth_once(Level &L, double *x, const double *b, double *res, bool ru, bool ur, bool xz, bool backward)
+{
+  if (L.sm_type == SM_GS) {
+    if (ru) {
+      if (ur) gs_res(L, backward, x, res, xz);
+      else { if (xz) NGB_CUDA(cudaMemsetAsync(x, 0, sizeof(double) * L.npad * L.b, st)); gs_rhs(L, backward, x, b); }
+    } else {
+      if (ur) { calc_residuum(L, x, b, res, xz); gs_res(L, backward, x, res, xz); }
+      else { if (xz) NGB_CUDA(cudaMemsetAsync(x, 0, sizeof(double) * L.npad * L.b, st)); gs_rhs(L, backward, x, b); }
+    }
+  } else {
+    if (xz) NGB_CUDA(cudaMemsetAsync(x, 0, sizeof(double) * L.npad * L.b, st));
+    const double *src;
+    if (!ru && xz) src = b;
+    else { if (!ru) calc_residuum(L, x, b, res, false); src = res; }
+    switch (L.b) {
+      case 1: k_jacobi_update<1><<<nblk(L.npad), TB, 0, st>>>(L.npad, L.omega, L.dinv, src, x); break;
+      case 2: k_jacobi_update<2><<<nblk(L.npad), TB, 0, st>>>(L.npad, L.omega, L.dinv, src, x); break;
+      case 3: k_jacobi_update<3><<<nblk(L.npad), TB, 0, st>>>(L.npad, L.omega, L.dinv, src, x); break;
+      case 6: k_jacobi_update<6><<<nblk(L.npad), TB, 0, st>>>(L.npad, L.omega, L.dinv, src, x); break;
+      default: throw Error("unsupported block size");
+    }
+    launches++;
+    if (ur) calc_residuum(L, x, b, res, false);
+  }
+}
+
+// ProxySmoother (base_smoother.hpp:169-229) + SmoothK / SmoothBackK / SmoothSymmK (:79-112)
+void Amg::level_smooth(Level &L, double *x, const double *b, double *res, bool ru, bool ur, bool xz, bool backward)
+{
+  const int k = std::max(1, L.sm_steps);
+  if (L.sm_symm) {
+    smooth_once(L, x, b, res, ru, ur, xz, false);
+    smooth_once(L, x, b, res, ur, ur, false, true);
+    for (int j = 0; j < k - 1; j++) {
+      smooth_once(L, x, b, res, ur, ur, false, false);
+      smooth_once(L, x, b, res, ur, ur, false, true);
+    }
+  } else {
+    smooth_once(L, x, b, res, ru, ur, xz, backward);
+    for (int j = 0; j < k - 1; j++) smooth_once(L, x, b, res, ur, ur, false, backward);
+  }
+}
+
+// AMGMatrix::SmoothV (amg_matrix.cpp:160-307), single rank: Distribute/Cumulate are no-ops.
+void Amg::vcycle_record()
+{
+  const int NL = (int)lev.size();
+  for (int l = 0; l + 1 < NL; l++) {
+    Level &L = *lev[l];
+    Level &C = *lev[l + 1];
+    // x_l = 0 ; res_l = b_l ; Smooth(x, b, res, true, true, true)     (:193-206)
+    // (res_l = b_l is folded into the sweep: the triangular kernel reads rhs and writes res)
+    if (L.sm_type == SM_GS && !L.sm_symm && L.sm_steps == 1) {
+      if (L.nonfree_pad) NGB_CUDA(cudaMemsetAsync(L.x, 0, sizeof(double) * L.nonfree_pad * L.b, st));
+      tri_dispatch(L, false, false, true, L.rhs, L.x, L.res);
+      spmv_part(L, 1, L.x, L.res, L.res, -1.0, 1.0, nullptr);
+    } else {
+      NGB_CUDA(cudaMemcpyAsync(L.res, L.rhs, sizeof(double) * L.npad * L.b, cudaMemcpyDeviceToDevice, st));
+      level_smooth(L, L.x, L.rhs, L.res, true, true, true, false);
+    }
+    // TransferF2C: rhs_{l+1} = P^T res_l     (:212, dof_map.cpp:633-654)
+    transfer(L.PT, L.res, nullptr, C.rhs, 1.0, 0.0);
+  }
+  {
+    Level &L = *lev[NL - 1];
+    if (has_cinv) {  // x_L = A_L^-1 rhs_L   (:217-247)
+      k_dense_gemv<<<nblk((i64)cinv_n * 32), TB, 0, st>>>(cinv_n, d_cinv, L.rhs, L.x);
+      launches++;
+    } else NGB_CUDA(cudaMemsetAsync(L.x, 0, sizeof(double) * L.npad * L.b, st));
+  }
+  for (int l = NL - 2; l >= 0; l--) {
+    Level &L = *lev[l];
+    Level &C = *lev[l + 1];
+    // AddC2F: x_l += P x_{l+1}   (:263, dof_map.cpp:694-709)
+    transfer(L.P, C.x, L.x, L.x, 1.0, 1.0);
+    // SmoothBack(x, b, res, false, false, false)   (:302)
+    level_smooth(L, L.x, L.rhs, L.res, false, false, false, true);
+  }
+}
+
+void Amg::vcycle()
+{
+  if (!use_graph) { vcycle_record(); return; }
+  if (!vgraph) {
+    cudaGraph_t g = nullptr;
+    const i64 l0 = launches;
+    NGB_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+    try { vcycle_record(); }
+    catch (...) { cudaStreamEndCapture(st, &g); if (g) cudaGraphDestroy(g); throw; }
+    NGB_CUDA(cudaStreamEndCapture(st, &g));
+    NGB_CUDA(cudaGraphInstantiate(&vgraph, g, 0));
+    cudaGraphDestroy(g);
+    vgraph_launches = launches - l0;
+    launches = l0;
+  }
+  NGB_CUDA(cudaGraphLaunch(vgraph, st));
+  launches += vgraph_launches;
+}
+
+void Amg::check_watchdog()
+{
+  int e = 0;
+  NGB_CUDA(cudaMemcpyAsync(&e, d_err, sizeof(int), cudaMemcpyDeviceToHost, st));
+  NGB_CUDA(cudaStreamSynchronize(st));
+  if (e) {
+    NGB_CUDA(cudaMemsetAsync(d_err, 0, sizeof(int), st));
+    throw Error("Gauss-Seidel sweep: dependency wait timed out (watchdog) -- results invalid");
+  }
+}
+
+double Amg::dot(i64 n, const double *a, const double *b)
+{
+  k_dot_partial<<<DOT_BLOCKS, DOT_THREADS, 0, st>>>(n, a, b, d_partial);
+  k_dot_final<<<1, DOT_THREADS, 0, st>>>(DOT_BLOCKS, d_partial, d_dot);
+  launches += 2;
+  double h = 0;
+  NGB_CUDA(cudaMemcpyAsync(&h, d_dot, sizeof(double), cudaMemcpyDeviceToHost, st));
+  NGB_CUDA(cudaStreamSynchronize(st));
+  return h;
+}
+
+bool Amg::is_device_ptr(const void *p)
+{
+  cudaPointerAttributes at;
+  cudaError_t e = cudaPointerGetAttributes(&at, p);
+  if (e != cudaSuccess) { cudaGetLastError(); return false; }
+  return at.type == cudaMemoryTypeDevice || at.type == cudaMemoryTypeManaged;
+}
+
+void Amg::ensure_io(i64 n)
+{
+  if (n <= io_n) return;
+  dev_free(io_a); dev_free(io_b); dev_free(io_c); dev_free(d_err);
+  if (pin_a) cudaFreeHost(pin_a);
+  if (pin_b) cudaFreeHost(pin_b);
+  io_a = dev_alloc<double>(n); io_b = dev_alloc<double>(n); io_c = dev_alloc<double>(n);
+  NGB_CUDA(cudaMallocHost((void **)&pin_a, sizeof(double) * n));
+  NGB_CUDA(cudaMallocHost((void **)&pin_b, sizeof(double) * n));
+  io_n = n; pin_n = n;
+}
+
+// returns a device pointer holding p[0..n): p itself if it is device memory, else a staged copy
+const double *Amg::to_device(const double *p, i64 n, double *stage)
+{
+  if (is_device_ptr(p)) return p;
+  std::memcpy(pin_a, p, sizeof(double) * n);  // pageable -> pinned, then async H2D
+  NGB_CUDA(cudaMemcpyAsync(stage, pin_a, sizeof(double) * n, cudaMemcpyHostToDevice, st));
+  NGB_CUDA(cudaStreamSynchronize(st));
+  return stage;
+}
+
+void Amg::from_device(double *dst, const double *src_dev, i64 n)
+{
+  if (is_device_ptr(dst)) {
+    if (dst != src_dev) NGB_CUDA(cudaMemcpyAsync(dst, src_dev, sizeof(double) * n, cudaMemcpyDeviceToDevice, st));
+    NGB_CUDA(cudaStreamSynchronize(st));
+    return;
+  }
+  NGB_CUDA(cudaMemcpyAsync(pin_b, src_dev, sizeof(double) * n, cudaMemcpyDeviceToHost, st));
+  NGB_CUDA(cudaStreamSynchronize(st));
+  std::memcpy(dst, pin_b, sizeof(double) * n);
+}
+
+}  // namespace ngb
+
+// =================================================================================================
+// C ABI
+// =================================================================================================
+using namespace ngb;
+
+static thread_local std::string g_err;
+struct ngsamg_b200 { Amg amg; };
+struct ngsamg_b200_spm { DevCsr d; cudaStream_t st; };
+
+#define NGB_TRY try {
+#define NGB_CATCH                                                     \
+  }                                                                   \
+  catch (const std::exception &e) { g_err = e.what(); return 1; }     \
+  catch (...) { g_err = "unknown error"; return 1; }                  \
+  return 0;
+
+static void require_device(int device)
+{
+  int cnt = 0;
+  cudaError_t e = cudaGetDeviceCount(&cnt);
+  if (e != cudaSuccess || cnt == 0)
+    throw Error(std::string("no CUDA device available (") + (e != cudaSuccess ? cudaGetErrorString(e) : "device count 0") +
+                "): ngsamg_b200 has no CPU fallback");
+  if (device < 0 || device >= cnt) throw Error("invalid CUDA device index " + std::to_string(device));
+  NGB_CUDA(cudaSetDevice(device));
+}
+
+static void check_csr(const ngsamg_csr *A, const char *what)
+{
+  if (!A || !A->rowptr || (A->rowptr[A->nrows] > 0 && (!A->col || !A->val))) throw Error(std::string(what) + ": null matrix arrays");
+  if (A->bh < 1 || A->bw < 1 || A->bh > 6 || A->bw > 6) throw Error(std::string(what) + ": unsupported block shape");
+  if (A->nrows >= (i64)2147483647 - 64 || A->ncols >= (i64)2147483647 - 64) throw Error(std::string(what) + ": more than 2^31 block rows per GPU");
+}
+
+static void copy_csr(const ngsamg_csr *A, HostBsr &h)
+{
+  h.nrows = A->nrows; h.ncols = A->ncols; h.bh = A->bh; h.bw = A->bw;
+  h.rowptr.assign(A->rowptr, A->rowptr + A->nrows + 1);
+  const i64 nnz = h.rowptr.back();
+  h.col.resize(nnz);
+  h.val.resize(nnz * h.bs());
+  parallel_for(nnz, [&](i64 lo, i64 hi) {
+    std::memcpy(h.col.data() + lo, A->col + lo, sizeof(i32) * (hi - lo));
+    std::memcpy(h.val.data() + lo * h.bs(), A->val + lo * h.bs(), sizeof(double) * (hi - lo) * h.bs());
+  }, 1 << 20);
+}
+
+extern "C" {
+
+const char *ngsamg_b200_last_error(void) { return g_err.c_str(); }
+
+int ngsamg_b200_create(const char *type, const ngsamg_csr *A, const uint8_t *free_mask, const double *vertex_xyz,
+                       const char *const *flag_keys, const char *const *flag_vals, int nflags, int device, ngsamg_b200_t **out)
+{
+  NGB_TRY
+  if (!out) throw Error("create: out is null");
+  *out = nullptr;
+  require_device(device);
+  check_csr(A, "create");
+  if (A->nrows != A->ncols || A->bh != A->bw) throw Error("create: the system matrix must be square with square blocks");
+  std::string t = type ? type : "";
+  for (const char *pre : {"NgsAMG.", "ngs_amg."})
+    if (t.rfind(pre, 0) == 0) t = t.substr(std::strlen(pre));
+  static const char *known[] = {"h1_scal", "h1_2d", "h1_3d", "elast_2d", "elast_3d"};
+  bool ok = false;
+  for (auto k : known) ok |= (t == k);
+  if (!ok) throw Error("unknown preconditioner type '" + t + "' (h1_scal, h1_2d, h1_3d, elast_2d, elast_3d)");
+  const int dim = t.find("2d") != std::string::npos ? 2 : 3;
+  if (t == "h1_scal" && A->bh != 1) throw Error("h1_scal expects a scalar (1x1 block) matrix");
+  if ((t == "h1_2d" && A->bh != 2) || (t == "h1_3d" && A->bh != 3)) throw Error(t + ": block size does not match the dimension");
+  if (t == "elast_3d" && A->bh != 3 && A->bh != 6) throw Error("elast_3d expects 3x3 (displacement) or 6x6 (displacement+rotation) blocks");
+  if (t == "elast_2d" && A->bh != 2 && A->bh != 3) throw Error("elast_2d expects 2x2 or 3x3 blocks");
+  if (t.find("elast") != std::string::npos && !vertex_xyz) throw Error(t + ": vertex coordinates are required (rigid body modes)");
+  (void)dim;
+  auto h = std::make_unique<ngsamg_b200>();
+  Amg &a = h->amg;
+  a.type = t;
+  a.device = device;
+  for (int i = 0; i < nflags; i++)
+    if (flag_keys[i]) a.flags.set(flag_keys[i], flag_vals && flag_vals[i] ? flag_vals[i] : "1");
+  NGB_CUDA(cudaStreamCreateWithFlags(&a.st, cudaStreamNonBlocking));
+  NGB_CUDA(cudaEventCreate(&a.ev0));
+  NGB_CUDA(cudaEventCreate(&a.ev1));
+  cudaDeviceProp prop;
+  NGB_CUDA(cudaGetDeviceProperties(&prop, device));
+  a.num_sms = prop.multiProcessorCount;
+  a.use_graph = a.flags.flag("b200_cuda_graph", true);
+  auto L = std::make_unique<Level>();
+  copy_csr(A, L->hA);
+  if (free_mask) {
+    bool all = true;
+    for (i64 i = 0; i < A->nrows; i++) all &= (free_mask[i] != 0);
+    if (!all) L->free_mask.assign(free_mask, free_mask + A->nrows);
+  }
+  if (vertex_xyz) L->xyz.assign(vertex_xyz, vertex_xyz + 3 * A->nrows);
+  a.lev.push_back(std::move(L));
+  *out = h.release();
+  NGB_CATCH
+}
+
+int ngsamg_b200_set_prolongations(ngsamg_b200_t *h, int nprol, const ngsamg_csr *P)
+{
+  NGB_TRY
+  if (!h) throw Error("null handle");
+  if (h->amg.finalized) throw Error("set_prolongations must be called before finalize");
+  h->amg.injected.clear();
+  for (int l = 0; l < nprol; l++) {
+    check_csr(&P[l], "set_prolongations");
+    h->amg.injected.emplace_back();
+    copy_csr(&P[l], h->amg.injected.back());
+  }
+  if (nprol == 0) { h->amg.flags.set("max_levels", "1"); }
+  NGB_CATCH
+}
+
+int ngsamg_b200_finalize(ngsamg_b200_t *h)
+{
+  NGB_TRY
+  if (!h) throw Error("null handle");
+  NGB_CUDA(cudaSetDevice(h->amg.device));
+  h->amg.finalize();
+  NGB_CATCH
+}
+
+void ngsamg_b200_destroy(ngsamg_b200_t *h) { delete h; }
+
+static Amg &ready(ngsamg_b200_t *h)
+{
+  if (!h) throw Error("null handle");
+  if (!h->amg.finalized) throw Error("hierarchy not finalized");
+  NGB_CUDA(cudaSetDevice(h->amg.device));
+  return h->amg;
+}
+static Level &get_level(Amg &a, int level)
+{
+  if (level < 0 || level >= (int)a.lev.size()) throw Error("level out of range");
+  return *a.lev[level];
+}
+
+static void apply_impl(Amg &a, double s, const double *b, double *x, bool add)
+{
+  Level &L = *a.lev[0];
+  const i64 n = L.n * L.b;
+  a.ensure_io(n);
+  cudaEventRecord(a.ev0, a.st);
+  const double *bd = a.to_device(b, n, a.io_a);
+  k_permute_in<<<nblk(L.n), TB, 0, a.st>>>(L.n, L.b, L.d_perm, bd, L.rhs);
+  a.vcycle();
+  const bool xdev = a.is_device_ptr(x);
+  double *xd = xdev ? x : a.io_b;
+  if (add && !xdev) { a.to_device(x, n, a.io_b); }
+  k_permute_out<<<nblk(L.n), TB, 0, a.st>>>(L.n, L.b, L.d_perm, L.x, xd, s, add ? 1 : 0);
+  a.launches += 2;
+  if (!xdev) a.from_device(x, xd, n);
+  cudaEventRecord(a.ev1, a.st);
+  NGB_CUDA(cudaEventSynchronize(a.ev1));
+  float ms = 0;
+  cudaEventElapsedTime(&ms, a.ev0, a.ev1);
+  a.ms_apply = ms;
+  NGB_CUDA(cudaGetLastError());
+  a.check_watchdog();
+}
+
+int ngsamg_b200_apply(ngsamg_b200_t *h, const double *b, double *x)
+{
+  NGB_TRY
+  apply_impl(ready(h), 1.0, b, x, false);
+  NGB_CATCH
+}
+
+int ngsamg_b200_apply_add(ngsamg_b200_t *h, double s, const double *b, double *x)
+{
+  NGB_TRY
+  apply_impl(ready(h), s, b, x, true);
+  NGB_CATCH
+}
+
+static void ensure_scratch(Amg &a, Level &L)
+{
+  if (L.wa) return;
+  const size_t nb = (size_t)L.npad * L.b;
+  L.wa = dev_alloc<double>(nb);
+  L.wb = dev_alloc<double>(nb);
+  NGB_CUDA(cudaMemsetAsync(L.wa, 0, nb * sizeof(double), a.st));
+  NGB_CUDA(cudaMemsetAsync(L.wb, 0, nb * sizeof(double), a.st));
+}
+
+int ngsamg_b200_spmv_add(ngsamg_b200_t *h, int level, double s, const double *x, double *y)
+{
+  NGB_TRY
+  Amg &a = ready(h);
+  Level &L = get_level(a, level);
+  if (level == (int)a.lev.size() - 1 && a.lev.size() > 1) throw Error("spmv_add: the coarsest level keeps no sparse matrix on the device");
+  if (!L.L.slice_ptr) throw Error("spmv_add: level has no device matrix");
+  const i64 n = L.n * L.b;
+  a.ensure_io(n);
+  ensure_scratch(a, L);
+  const double *xd = a.to_device(x, n, a.io_a);
+  k_permute_in<<<nblk(L.n), TB, 0, a.st>>>(L.n, L.b, L.d_perm, xd, L.wa);
+  a.spmv_part(L, 4, L.wa, nullptr, L.wb, 1.0, 0.0, nullptr);
+  const bool ydev = a.is_device_ptr(y);
+  double *yd = ydev ? y : a.io_b;
+  if (!ydev) a.to_device(y, n, a.io_b);
+  k_permute_out<<<nblk(L.n), TB, 0, a.st>>>(L.n, L.b, L.d_perm, L.wb, yd, s, 1);
+  a.launches += 2;
+  a.from_device(y, yd, n);
+  NGB_CUDA(cudaGetLastError());
+  NGB_CATCH
+}
+
+int ngsamg_b200_smooth(ngsamg_b200_t *h, int level, double *x, const double *b, double *res, int res_updated, int update_res,
+                       int x_zero, int backwards)
+{
+  NGB_TRY
+  Amg &a = ready(h);
+  Level &L = get_level(a, level);
+  if (!L.L.slice_ptr) throw Error("smooth: level has no smoother (coarsest level)");
+  const i64 n = L.n * L.b;
+  a.ensure_io(n);
+  const double *xd = a.to_device(x, n, a.io_a);
+  k_permute_in<<<nblk(L.n), TB, 0, a.st>>>(L.n, L.b, L.d_perm, xd, L.x);
+  const double *bd = a.to_device(b, n, a.io_a);
+  k_permute_in<<<nblk(L.n), TB, 0, a.st>>>(L.n, L.b, L.d_perm, bd, L.rhs);
+  if (res) {
+    const double *rd = a.to_device(res, n, a.io_a);
+    k_permute_in<<<nblk(L.n), TB, 0, a.st>>>(L.n, L.b, L.d_perm, rd, L.res);
+  }
+  a.level_smooth(L, L.x, L.rhs, L.res, res_updated != 0, update_res != 0, x_zero != 0, backwards != 0);
+  k_permute_out<<<nblk(L.n), TB, 0, a.st>>>(L.n, L.b, L.d_perm, L.x, a.io_b, 1.0, 0);
+  a.from_device(x, a.io_b, n);
+  if (res) {
+    k_permute_out<<<nblk(L.n), TB, 0, a.st>>>(L.n, L.b, L.d_perm, L.res, a.io_b, 1.0, 0);
+    a.from_device(res, a.io_b, n);
+  }
+  a.launches += 5;
+  NGB_CUDA(cudaGetLastError());
+  a.check_watchdog();
+  NGB_CATCH
+}
+
+int ngsamg_b200_restrict(ngsamg_b200_t *h, int level, const double *xf, double *xc)
+{
+  NGB_TRY
+  Amg &a = ready(h);
+  Level &F = get_level(a, level);
+  Level &C = get_level(a, level + 1);
+  const i64 nf = F.n * F.b, nc = C.n * C.b;
+  a.ensure_io(std::max(nf, nc));
+  const double *xd = a.to_device(xf, nf, a.io_a);
+  k_permute_in<<<nblk(F.n), TB, 0, a.st>>>(F.n, F.b, F.d_perm, xd, F.res);
+  a.transfer(F.PT, F.res, nullptr, C.rhs, 1.0, 0.0);
+  k_permute_out<<<nblk(C.n), TB, 0, a.st>>>(C.n, C.b, C.d_perm, C.rhs, a.io_b, 1.0, 0);
+  a.from_device(xc, a.io_b, nc);
+  a.launches += 2;
+  NGB_CUDA(cudaGetLastError());
+  NGB_CATCH
+}
+
+int ngsamg_b200_prolong_add(ngsamg_b200_t *h, int level, double fac, const double *xc, double *xf)
+{
+  NGB_TRY
+  Amg &a = ready(h);
+  Level &F = get_level(a, level);
+  Level &C = get_level(a, level + 1);
+  const i64 nf = F.n * F.b, nc = C.n * C.b;
+  a.ensure_io(std::max(nf, nc));
+  const double *cd = a.to_device(xc, nc, a.io_a);
+  k_permute_in<<<nblk(C.n), TB, 0, a.st>>>(C.n, C.b, C.d_perm, cd, C.x);
+  const double *fd = a.to_device(xf, nf, a.io_a);
+  k_permute_in<<<nblk(F.n), TB, 0, a.st>>>(F.n, F.b, F.d_perm, fd, F.x);
+  a.transfer(F.P, C.x, F.x, F.x, fac, 1.0);
+  k_permute_out<<<nblk(F.n), TB, 0, a.st>>>(F.n, F.b, F.d_perm, F.x, a.io_b, 1.0, 0);
+  a.from_device(xf, a.io_b, nf);
+  a.launches += 3;
+  NGB_CUDA(cudaGetLastError());
+  NGB_CATCH
+}
+
+// ngsolve.krylovspace.CGSolver restated (see oracle/ngsamg_oracle.c:orc_amg_pcg for the recurrence), all vectors stay in
+// the level-scheduled numbering on the device; per iteration: 1 SpMV, 1 V-cycle (CUDA graph), 2 dots, 2 fused updates.
+int ngsamg_b200_pcg(ngsamg_b200_t *h, const double *rhs, double *x, double tol, int maxsteps, int *iters, double *errors)
+{
+  NGB_TRY
+  Amg &a = ready(h);
+  Level &L = *a.lev[0];
+  if (a.lev.size() < 2) throw Error("pcg needs at least two levels");
+  const i64 n = L.n * L.b, np = L.npad * L.b;
+  a.ensure_io(n);
+  if (!a.cg_u) { a.cg_u = dev_alloc<double>(np); a.cg_s = dev_alloc<double>(np); a.cg_q = dev_alloc<double>(np); }
+  cudaEventRecord(a.ev0, a.st);
+  const double *rd = a.to_device(rhs, n, a.io_a);
+  double *d = L.rhs, *w = L.x, *u = a.cg_u, *s = a.cg_s, *q = a.cg_q;
+  NGB_CUDA(cudaMemsetAsync(u, 0, sizeof(double) * np, a.st));
+  k_permute_in<<<nblk(L.n), TB, 0, a.st>>>(L.n, L.b, L.d_perm, rd, d);
+  a.vcycle();
+  NGB_CUDA(cudaMemcpyAsync(s, w, sizeof(double) * np, cudaMemcpyDeviceToDevice, a.st));
+  double wdn = a.dot(np, w, d);
+  const double err0 = std::sqrt(std::fabs(wdn));
+  if (errors) errors[0] = err0;
+  int it = 0;
+  if (wdn != 0.0)
+    for (it = 1; it <= maxsteps; it++) {
+      a.spmv_part(L, 4, s, nullptr, q, 1.0, 0.0, nullptr);
+      const double wd = wdn;
+      const double as_s = a.dot(np, s, q);
+      const double alpha = wd / as_s;
+      k_cg_update<<<nblk(np), TB, 0, a.st>>>(np, alpha, s, q, u, d);
+      a.vcycle();
+      wdn = a.dot(np, w, d);
+      const double beta = wdn / wd;
+      k_axpby<<<nblk(np), TB, 0, a.st>>>(np, 1.0, w, beta, s);
+      a.launches += 2;
+      const double err = std::sqrt(std::fabs(wd));
+      if (errors) errors[it] = err;
+      if (err < tol * err0) break;
+    }
+  if (it > maxsteps) it = maxsteps;
+  if (iters) *iters = it;
+  const bool xdev = a.is_device_ptr(x);
+  double *xd = xdev ? x : a.io_b;
+  k_permute_out<<<nblk(L.n), TB, 0, a.st>>>(L.n, L.b, L.d_perm, u, xd, 1.0, 0);
+  a.launches += 2;
+  if (!xdev) a.from_device(x, xd, n);
+  cudaEventRecord(a.ev1, a.st);
+  NGB_CUDA(cudaEventSynchronize(a.ev1));
+  float ms = 0;
+  cudaEventElapsedTime(&ms, a.ev0, a.ev1);
+  a.ms_pcg = ms;
+  NGB_CUDA(cudaGetLastError());
+  a.check_watchdog();
+  NGB_CATCH
+}
+
+int ngsamg_b200_num_levels(ngsamg_b200_t *h) { return (h && h->amg.finalized) ? (int)h->amg.lev.size() : 0; }
+
+static void level_bytes(const Level &L, i64 &m, i64 &p, i64 &v)
+{
+  m = L.nnz * (8 * (i64)L.b * L.b + 4) + 4 * (L.n + 1);
+  p = L.hP.nnz() ? L.hP.nnz() * (8 * (i64)L.b * L.bc + 4) + 4 * (L.n + 1) : 0;
+  v = 8 * L.n * L.b;
+}
+
+int ngsamg_b200_level_info(ngsamg_b200_t *h, int level, ngsamg_level_info *info)
+{
+  NGB_TRY
+  Amg &a = ready(h);
+  Level &L = get_level(a, level);
+  if (!info) throw Error("null info");
+  info->n = L.n; info->b = L.b; info->nnz = L.nnz;
+  info->nnz_prol = L.P.nnz; info->ncoarse = L.nc; info->bcoarse = L.bc;
+  info->gs_depth = L.depth;
+  level_bytes(L, info->bytes_matrix, info->bytes_prol, info->bytes_vec);
+  if (!L.P.nnz) info->bytes_prol = 0;
+  NGB_CATCH
+}
+
+int ngsamg_b200_get_level_matrix(ngsamg_b200_t *h, int level, int64_t *rowptr, int32_t *col, double *val)
+{
+  NGB_TRY
+  Amg &a = ready(h);
+  Level &L = get_level(a, level);
+  if (!L.keep_host) throw Error("level matrix was not kept on the host (raise ngs_amg_keep_host_nnz)");
+  if (rowptr) std::memcpy(rowptr, L.hA.rowptr.data(), sizeof(i64) * (L.n + 1));
+  if (col) std::memcpy(col, L.hA.col.data(), sizeof(i32) * L.hA.nnz());
+  if (val) std::memcpy(val, L.hA.val.data(), sizeof(double) * L.hA.nnz() * L.hA.bs());
+  NGB_CATCH
+}
+
+int ngsamg_b200_get_prolongation(ngsamg_b200_t *h, int level, int64_t *rowptr, int32_t *col, double *val)
+{
+  NGB_TRY
+  Amg &a = ready(h);
+  Level &L = get_level(a, level);
+  if (level + 1 >= (int)a.lev.size()) throw Error("the coarsest level has no prolongation");
+  if (rowptr) std::memcpy(rowptr, L.hP.rowptr.data(), sizeof(i64) * (L.n + 1));
+  if (col) std::memcpy(col, L.hP.col.data(), sizeof(i32) * L.hP.nnz());
+  if (val) std::memcpy(val, L.hP.val.data(), sizeof(double) * L.hP.nnz() * L.hP.bs());
+  NGB_CATCH
+}
+
+int ngsamg_b200_get_level_vector(ngsamg_b200_t *h, int level, int which, double *out)
+{
+  NGB_TRY
+  Amg &a = ready(h);
+  Level &L = get_level(a, level);
+  const double *src = which == 0 ? L.x : which == 1 ? L.rhs : which == 2 ? L.res : nullptr;
+  if (!src) throw Error("get_level_vector: which must be 0 (x), 1 (rhs) or 2 (res)");
+  const i64 n = L.n * L.b;
+  a.ensure_io(n);
+  k_permute_out<<<nblk(L.n), TB, 0, a.st>>>(L.n, L.b, L.d_perm, src, a.io_b, 1.0, 0);
+  a.from_device(out, a.io_b, n);
+  NGB_CATCH
+}
+
+double ngsamg_b200_operator_complexity(ngsamg_b200_t *h)
+{
+  if (!h || !h->amg.finalized) return 0.0;
+  double s = 0;
+  for (auto &lp : h->amg.lev) s += (double)lp->nnz * lp->b * lp->b;
+  const Level &L0 = *h->amg.lev[0];
+  return s / ((double)L0.nnz * L0.b * L0.b);
+}
+
+double ngsamg_b200_vcycle_bytes(ngsamg_b200_t *h)
+{
+  if (!h || !h->amg.finalized) return 0.0;
+  // B_V = sum_{l<L} [ 2(M_l + D_l) + 2 P_l + 9 v_l + 2 v_{l+1} ] + B_coarse        
+  auto &lev = h->amg.lev;
+  double B = 0;
+  for (size_t l = 0; l + 1 < lev.size(); l++) {
+    i64 m, p, v, m2, p2, v2;
+    level_bytes(*lev[l], m, p, v);
+    level_bytes(*lev[l + 1], m2, p2, v2);
+    const double D = 8.0 * lev[l]->n * lev[l]->b * lev[l]->b;
+    B += 2.0 * (m + D) + 2.0 * p + 9.0 * v + 2.0 * v2;
+  }
+  const Level &C = *lev.back();
+  const double N = (double)C.n * C.b;
+  B += 8.0 * N * N + 16.0 * N;
+  return B;
+}
+
+double ngsamg_b200_last_ms(ngsamg_b200_t *h, int what)
+{
+  if (!h) return 0.0;
+  switch (what) {
+    case 0: return h->amg.ms_apply;
+    case 1: return h->amg.ms_pcg;
+    case 2: return h->amg.ms_setup;
+    case 3: return h->amg.ms_rap;
+    case 4: return h->amg.ms_host;
+  }
+  return 0.0;
+}
+
+int64_t ngsamg_b200_launch_count(ngsamg_b200_t *h) { return h ? h->amg.launches : 0; }
+
+// ---- standalone sparse kernels ---------------------------------------------------------------------
+static void upload_abi(const ngsamg_csr *A, DevCsr &d, cudaStream_t st)
+{
+  dev_csr_upload_raw(A->nrows, A->ncols, A->bh, A->bw, A->rowptr, A->col, A->val, d, st);
+}
+
+int ngsamg_b200_matmul_begin(const ngsamg_csr *A, const ngsamg_csr *B, int device, ngsamg_b200_spm **out, int64_t *nrows, int64_t *nnz)
+{
+  NGB_TRY
+  require_device(device);
+  check_csr(A, "matmul"); check_csr(B, "matmul");
+  DevCsr dA, dB;
+  auto r = std::make_unique<ngsamg_b200_spm>();
+  r->st = nullptr;
+  upload_abi(A, dA, nullptr);
+  upload_abi(B, dB, nullptr);
+  dev_spgemm(dA, dB, r->d, nullptr, nullptr);
+  dev_csr_free(dA); dev_csr_free(dB);
+  if (nrows) *nrows = r->d.nrows;
+  if (nnz) *nnz = r->d.nnz;
+  *out = r.release();
+  NGB_CATCH
+}
+
+int ngsamg_b200_rap_begin(const ngsamg_csr *A, const ngsamg_csr *P, int device, ngsamg_b200_spm **out, int64_t *nrows, int64_t *nnz)
+{
+  NGB_TRY
+  require_device(device);
+  check_csr(A, "rap"); check_csr(P, "rap");
+  HostBsr hP, hPT;
+  copy_csr(P, hP);
+  host_transpose(hP, hPT);
+  DevCsr dA, dP, dPT, dPTA;
+  upload_abi(A, dA, nullptr);
+  dev_csr_upload(hP, dP, nullptr);
+  dev_csr_upload(hPT, dPT, nullptr);
+  auto r = std::make_unique<ngsamg_b200_spm>();
+  r->st = nullptr;
+  dev_spgemm(dPT, dA, dPTA, nullptr, nullptr);
+  dev_spgemm(dPTA, dP, r->d, nullptr, nullptr);
+  dev_csr_free(dA); dev_csr_free(dP); dev_csr_free(dPT); dev_csr_free(dPTA);
+  if (nrows) *nrows = r->d.nrows;
+  if (nnz) *nnz = r->d.nnz;
+  *out = r.release();
+  NGB_CATCH
+}
+
+int ngsamg_b200_transpose_begin(const ngsamg_csr *A, int device, ngsamg_b200_spm **out, int64_t *nrows, int64_t *nnz)
+{
+  NGB_TRY
+  require_device(device);
+  check_csr(A, "transpose");
+  HostBsr hA, hT;
+  copy_csr(A, hA);
+  host_transpose(hA, hT);
+  auto r = std::make_unique<ngsamg_b200_spm>();
+  r->st = nullptr;
+  dev_csr_upload(hT, r->d, nullptr);
+  if (nrows) *nrows = r->d.nrows;
+  if (nnz) *nnz = r->d.nnz;
+  *out = r.release();
+  NGB_CATCH
+}
+
+int ngsamg_b200_spm_fetch(ngsamg_b200_spm *m, int64_t *rowptr, int32_t *col, double *val)
+{
+  NGB_TRY
+  if (!m) throw Error("null matrix handle");
+  HostBsr h;
+  dev_csr_download(m->d, h, m->st, val != nullptr);
+  if (rowptr) std::memcpy(rowptr, h.rowptr.data(), sizeof(i64) * (h.nrows + 1));
+  if (col) std::memcpy(col, h.col.data(), sizeof(i32) * h.nnz());
+  if (val) std::memcpy(val, h.val.data(), sizeof(double) * h.nnz() * h.bs());
+  dev_csr_free(m->d);
+  delete m;
+  NGB_CATCH
+}
+
+// ---- per-kernel timing for the roofline (bench.py) ---------------------------------------------------
+// Launches ONE kernel of the V-cycle `reps` times on the library stream between two CUDA events and returns the average
+// duration plus the algorithmic bytes of one launch (matrix part + dense diagonal arrays + each streamed vector once).
+int ngsamg_b200_profile_kernel(ngsamg_b200_t *h, int level, int which, int reps, double *ms_avg, double *bytes)
+{
+  NGB_TRY
+  Amg &a = ready(h);
+  Level &L = get_level(a, level);
+  if (level + 1 >= (int)a.lev.size()) throw Error("profile_kernel: level has no smoother / transfer");
+  Level &C = *a.lev[level + 1];
+  const double bb = 8.0 * L.b * L.b + 4.0, D = 8.0 * L.n * L.b * L.b, v = 8.0 * L.n * L.b, vc = 8.0 * C.n * C.b;
+  const double pb = L.P.nnz * (8.0 * L.b * L.bc + 4.0);
+  double B = 0;
+  auto run = [&]() {
+    switch (which) {
+      case 0: if (L.nonfree_pad) NGB_CUDA(cudaMemsetAsync(L.x, 0, sizeof(double) * L.nonfree_pad * L.b, a.st));
+              a.tri_dispatch(L, false, false, true, L.rhs, L.x, L.res); B = L.L.nnz * bb + 2 * D + 3 * v; break;
+      case 1: a.spmv_part(L, 1, L.x, L.res, L.res, -1.0, 1.0, nullptr); B = L.U.nnz * bb + 3 * v; break;
+      case 2: a.spmv_part(L, 2, L.x, L.rhs, L.tmp, -1.0, 1.0, nullptr); B = L.L.nnz * bb + D + 3 * v; break;
+      case 3: a.tri_dispatch(L, true, true, false, L.tmp, L.x, nullptr); B = L.U.nnz * bb + D + 3 * v; break;
+      case 4: ensure_scratch(a, L); a.spmv_part(L, 4, L.x, nullptr, L.wa, 1.0, 0.0, nullptr); B = (L.L.nnz + L.U.nnz) * bb + D + 2 * v; break;
+      case 5: a.transfer(L.PT, L.res, nullptr, C.rhs, 1.0, 0.0); B = pb + v + vc; break;
+      case 6: a.transfer(L.P, C.x, L.x, L.x, 1.0, 1.0); B = pb + 2 * v + vc; break;
+      default: throw Error("profile_kernel: unknown kernel id");
+    }
+  };
+  run();  // warm-up (also resolves lazy allocations)
+  NGB_CUDA(cudaStreamSynchronize(a.st));
+  cudaEventRecord(a.ev0, a.st);
+  for (int r = 0; r < reps; r++) run();
+  cudaEventRecord(a.ev1, a.st);
+  NGB_CUDA(cudaEventSynchronize(a.ev1));
+  float ms = 0;
+  cudaEventElapsedTime(&ms, a.ev0, a.ev1);
+  if (ms_avg) *ms_avg = ms / std::max(reps, 1);
+  if (bytes) *bytes = B;
+  NGB_CUDA(cudaGetLastError());
+  a.check_watchdog();
+  NGB_CATCH
+}
+
+// ---- host-side DOF-map construction -------------------------------------------------------------
+struct ngsamg_b200_hostspm { HostBsr P; std::vector<i32> vmap; std::vector<double> cxyz; };
+
+int ngsamg_b200_coarsen_begin(const ngsamg_csr *A, const uint8_t *free_mask, const double *vertex_xyz, int bcoarse, int max_per_row,
+                              double min_frac, double omega, int smooth, int rounds, ngsamg_b200_hostspm **out, int64_t *ncoarse,
+                              int64_t *nnz)
+{
+  NGB_TRY
+  check_csr(A, "coarsen");
+  HostBsr hA;
+  copy_csr(A, hA);
+  std::vector<double> xyz;
+  if (vertex_xyz) xyz.assign(vertex_xyz, vertex_xyz + 3 * A->nrows);
+  CoarsenOptions o;
+  o.max_per_row = max_per_row; o.min_frac = min_frac; o.omega = omega; o.smooth = smooth != 0; o.rounds = rounds;
+  auto r = std::make_unique<ngsamg_b200_hostspm>();
+  build_prolongation(hA, free_mask, bcoarse, xyz, o, r->P, r->vmap, r->cxyz);
+  if (ncoarse) *ncoarse = r->P.ncols;
+  if (nnz) *nnz = r->P.nnz();
+  *out = r.release();
+  NGB_CATCH
+}
+
+int ngsamg_b200_coarsen_fetch(ngsamg_b200_hostspm *m, int64_t *rowptr, int32_t *col, double *val, int32_t *vmap, double *cxyz)
+{
+  NGB_TRY
+  if (!m) throw Error("null handle");
+  if (rowptr) std::memcpy(rowptr, m->P.rowptr.data(), sizeof(i64) * (m->P.nrows + 1));
+  if (col) std::memcpy(col, m->P.col.data(), sizeof(i32) * m->P.nnz());
+  if (val) std::memcpy(val, m->P.val.data(), sizeof(double) * m->P.nnz() * m->P.bs());
+  if (vmap) std::memcpy(vmap, m->vmap.data(), sizeof(i32) * m->vmap.size());
+  if (cxyz && !m->cxyz.empty()) std::memcpy(cxyz, m->cxyz.data(), sizeof(double) * m->cxyz.size());
+  delete m;
+  NGB_CATCH
+}
+
+}  // extern "C"

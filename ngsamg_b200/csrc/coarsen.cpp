@@ -1,0 +1,434 @@
+// coarsen.cpp -- host-side construction of the level DOF maps (prolongations).
+//
+// The reference builds P with SPW pairwise agglomeration + "semi-auxiliary" smoothed prolongation
+// (src/base/coarsening/spw_agg_impl.hpp:1417-1831, src/base/factory/vertex_factory_impl.hpp:1599-1659,
+// 1834-2433).  That construction is order- and quicksort-tie-dependent and is the
+// "next" row of the scope table (§8f #1/#2); the hot path only CONSUMES P.  This file is our own,
+// simplified builder in the same spirit so the library is usable stand-alone:
+//   * successive pairwise matching rounds on the strength graph (aggregates of <= 2^rounds vertices,
+//     reverse vertex order, scalar strength w_ij/sqrt(maxOD_i maxOD_j) with a 0.25 relative threshold,
+//     orphan round) -- cf. SPWAgglomerator::FormAgglomerates;
+//   * piecewise prolongation with rigid-body transport blocks, then one weighted-Jacobi-like smoothing
+//     step on the auxiliary (edge weight) graph restricted to <= max_per_row coarse neighbours with
+//     the sp_min_frac threshold -- cf. SemiAuxSProlMap's aux path.
+// It does NOT claim bit-exact agreement with the reference's aggregates.  Users who need the
+// reference's own DOF maps inject them with ngsamg_b200_set_prolongations().
+#include "common.hpp"
+
+namespace ngb {
+
+namespace {
+
+struct Graph {
+  i64 n = 0;
+  std::vector<i64> ptr;
+  std::vector<i32> adj;
+  std::vector<double> w;
+  std::vector<double> vwt;    // "L2"/ground weight: |row sum| (h1_impl.hpp:383-431)
+  std::vector<double> maxod;  // max(max incident edge weight, vwt)
+  std::vector<i32> size;      // number of level-0 vertices represented
+};
+
+double entry_weight(const double *blk, int b)
+{
+  if (b == 1) return std::fabs(blk[0]);
+  double tr = 0;
+  for (int k = 0; k < b; k++) tr += blk[k * b + k];
+  return std::fabs(tr) / b;  // trace-based weight for vector problems
+}
+
+// strength graph of the level matrix; `drop[v]` marks Dirichlet vertices (not part of any aggregate)
+void graph_from_matrix(const HostBsr &A, const std::vector<uint8_t> &drop, Graph &G)
+{
+  const i64 n = A.nrows;
+  const int b = A.bh, bb = b * b;
+  G.n = n;
+  G.ptr.assign(n + 1, 0);
+  G.vwt.assign(n, 0.0);
+  G.maxod.assign(n, 0.0);
+  G.size.assign(n, 1);
+  parallel_for(n, [&](i64 lo, i64 hi) {
+    for (i64 i = lo; i < hi; i++) {
+      i64 c = 0;
+      if (!drop[i])
+        for (i64 k = A.rowptr[i]; k < A.rowptr[i + 1]; k++) {
+          i32 j = A.col[k];
+          if (j != i && !drop[j]) c++;
+        }
+      G.ptr[i + 1] = c;
+    }
+  });
+  for (i64 i = 0; i < n; i++) G.ptr[i + 1] += G.ptr[i];
+  G.adj.resize(G.ptr[n]);
+  G.w.resize(G.ptr[n]);
+  parallel_for(n, [&](i64 lo, i64 hi) {
+    std::vector<double> rs(bb);
+    for (i64 i = lo; i < hi; i++) {
+      if (drop[i]) continue;
+      i64 p = G.ptr[i];
+      std::fill(rs.begin(), rs.end(), 0.0);
+      double mx = 0;
+      for (i64 k = A.rowptr[i]; k < A.rowptr[i + 1]; k++) {
+        i32 j = A.col[k];
+        const double *blk = &A.val[k * bb];
+        for (int e = 0; e < bb; e++) rs[e] += blk[e];
+        if (j == i || drop[j]) continue;
+        double w = entry_weight(blk, b);
+        G.adj[p] = j;
+        G.w[p] = w;
+        p++;
+        mx = std::max(mx, w);
+      }
+      double vw = entry_weight(rs.data(), b);
+      G.vwt[i] = vw;
+      G.maxod[i] = std::max(mx, vw);
+    }
+  });
+}
+
+// one pairwise matching round.  cmap[v] = coarse id (numbered ascending by smallest member), -1 if dropped.
+i64 pairing_round(const Graph &G, const std::vector<uint8_t> &drop, double soc_thresh, std::vector<i32> &cmap)
+{
+  const i64 n = G.n;
+  std::vector<i32> mate(n, -2);  // -2 unhandled, -1 single, >=0 partner
+  for (i64 v = n - 1; v >= 0; v--) {
+    if (mate[v] != -2) continue;
+    if (drop[v]) { mate[v] = -1; continue; }
+    double maxsoc = 0;
+    const double mv = G.maxod[v];
+    for (i64 e = G.ptr[v]; e < G.ptr[v + 1]; e++) {
+      i32 j = G.adj[e];
+      double d = mv * G.maxod[j];
+      double soc = d > 0 ? G.w[e] / std::sqrt(d) : 0.0;
+      maxsoc = std::max(maxsoc, soc);
+    }
+    const double thr = soc_thresh * maxsoc;
+    i32 best = -1;
+    double bestsoc = 0;
+    for (i64 e = G.ptr[v]; e < G.ptr[v + 1]; e++) {
+      i32 j = G.adj[e];
+      if (mate[j] != -2 || drop[j]) continue;
+      double d = mv * G.maxod[j];
+      double soc = d > 0 ? G.w[e] / std::sqrt(d) : 0.0;
+      if (soc <= 0 || soc < thr) continue;
+      // strongest connection wins; ties -> the neighbour with the highest index (closest in numbering)
+      if (soc > bestsoc || (soc == bestsoc && j > best)) { bestsoc = soc; best = j; }
+    }
+    if (best >= 0) { mate[v] = best; mate[best] = (i32)v; }
+    else mate[v] = -1;
+  }
+  cmap.assign(n, -1);
+  i64 nc = 0;
+  for (i64 v = 0; v < n; v++) {
+    if (drop[v] || cmap[v] >= 0) continue;
+    cmap[v] = (i32)nc;
+    if (mate[v] >= 0) cmap[mate[v]] = (i32)nc;
+    nc++;
+  }
+  return nc;
+}
+
+// coarse graph: weights summed, vwt summed, maxod = max(coarse incident weights, members' maxod)
+void coarsen_graph(const Graph &G, const std::vector<i32> &cmap, i64 nc, Graph &C)
+{
+  const i64 n = G.n;
+  std::vector<i64> mptr(nc + 1, 0);
+  for (i64 v = 0; v < n; v++)
+    if (cmap[v] >= 0) mptr[cmap[v] + 1]++;
+  for (i64 c = 0; c < nc; c++) mptr[c + 1] += mptr[c];
+  std::vector<i32> mem(mptr[nc]);
+  {
+    std::vector<i64> pos(mptr.begin(), mptr.end() - 1);
+    for (i64 v = 0; v < n; v++)
+      if (cmap[v] >= 0) mem[pos[cmap[v]]++] = (i32)v;
+  }
+  C.n = nc;
+  C.ptr.assign(nc + 1, 0);
+  C.vwt.assign(nc, 0.0);
+  C.maxod.assign(nc, 0.0);
+  C.size.assign(nc, 0);
+  // two passes (count, fill) so that rows can be produced in parallel chunks
+  const int nt = host_threads();
+  const i64 chunk = (nc + nt - 1) / std::max(nt, 1);
+  std::vector<std::vector<i32>> cadj(nt);
+  std::vector<std::vector<double>> cw(nt);
+  std::vector<std::thread> th;
+  auto work = [&](int t) {
+    i64 lo = t * chunk, hi = std::min(nc, lo + chunk);
+    std::vector<std::pair<i32, double>> row;
+    for (i64 c = lo; c < hi; c++) {
+      row.clear();
+      double vw = 0, mo = 0;
+      i32 sz = 0;
+      for (i64 m = mptr[c]; m < mptr[c + 1]; m++) {
+        i32 v = mem[m];
+        vw += G.vwt[v];
+        mo = std::max(mo, G.maxod[v]);
+        sz += G.size[v];
+        for (i64 e = G.ptr[v]; e < G.ptr[v + 1]; e++) {
+          i32 cj = cmap[G.adj[e]];
+          if (cj < 0 || cj == c) continue;
+          row.emplace_back(cj, G.w[e]);
+        }
+      }
+      // sort by coarse neighbour, then merge duplicates (weights summed in a fixed order)
+      std::stable_sort(row.begin(), row.end(),
+                       [](const std::pair<i32, double> &a, const std::pair<i32, double> &b) { return a.first < b.first; });
+      size_t u = 0;
+      for (size_t q = 0; q < row.size(); q++) {
+        if (u > 0 && row[u - 1].first == row[q].first) row[u - 1].second += row[q].second;
+        else row[u++] = row[q];
+      }
+      row.resize(u);
+      for (auto &pr : row) { cadj[t].push_back(pr.first); cw[t].push_back(pr.second); mo = std::max(mo, pr.second); }
+      C.ptr[c + 1] = (i64)row.size();
+      C.vwt[c] = vw;
+      C.maxod[c] = mo;
+      C.size[c] = sz;
+    }
+  };
+  if (nt > 1 && nc > 20000) {
+    for (int t = 0; t < nt; t++) th.emplace_back(work, t);
+    for (auto &x : th) x.join();
+  } else {
+    for (int t = 0; t < nt; t++) work(t);
+  }
+  for (i64 c = 0; c < nc; c++) C.ptr[c + 1] += C.ptr[c];
+  C.adj.resize(C.ptr[nc]);
+  C.w.resize(C.ptr[nc]);
+  for (int t = 0; t < nt; t++) {
+    i64 lo = t * chunk;
+    if (lo >= nc) break;
+    std::copy(cadj[t].begin(), cadj[t].end(), C.adj.begin() + C.ptr[lo]);
+    std::copy(cw[t].begin(), cw[t].end(), C.w.begin() + C.ptr[lo]);
+  }
+}
+
+// orphan round: aggregates that still consist of one level-0 vertex join the most strongly connected
+// neighbouring aggregate (JoiningIteration, spw_agg_impl.hpp:1265-1361).  returns new count, updates cmap
+i64 orphan_round(const Graph &G, double soc_thresh, std::vector<i32> &join)
+{
+  const i64 n = G.n;
+  join.assign(n, -1);
+  for (i64 v = 0; v < n; v++) {
+    if (G.size[v] != 1) continue;
+    double maxsoc = 0;
+    for (i64 e = G.ptr[v]; e < G.ptr[v + 1]; e++) {
+      double d = G.maxod[v] * G.maxod[G.adj[e]];
+      maxsoc = std::max(maxsoc, d > 0 ? G.w[e] / std::sqrt(d) : 0.0);
+    }
+    i32 best = -1;
+    double bw = 0;
+    for (i64 e = G.ptr[v]; e < G.ptr[v + 1]; e++) {
+      i32 j = G.adj[e];
+      if (G.size[j] <= 1) continue;
+      double d = G.maxod[v] * G.maxod[j];
+      double soc = d > 0 ? G.w[e] / std::sqrt(d) : 0.0;
+      if (soc <= 0 || soc < soc_thresh * maxsoc) continue;
+      if (soc > bw) { bw = soc; best = j; }
+    }
+    join[v] = best;
+  }
+  std::vector<i32> newid(n, -1);
+  i64 nc = 0;
+  for (i64 v = 0; v < n; v++)
+    if (join[v] < 0) newid[v] = (i32)nc++;
+  for (i64 v = 0; v < n; v++) join[v] = (join[v] < 0) ? newid[v] : newid[join[v]];
+  return nc;
+}
+
+inline void skew_neg(const double *t, double *S /*3x3 = -skew(t)*/)
+{
+  // skew(t) w = t x w ;  -skew(t):
+  S[0] = 0;      S[1] = t[2];   S[2] = -t[1];
+  S[3] = -t[2];  S[4] = 0;      S[5] = t[0];
+  S[6] = t[1];   S[7] = -t[0];  S[8] = 0;
+}
+
+// transport block Q (bf x bc) from coarse vertex at xc to fine vertex at xv
+void transport_block(int bf, int bc, const double *xv, const double *xc, double *Q)
+{
+  std::fill(Q, Q + bf * bc, 0.0);
+  if (bf == bc && bf != 6) { for (int k = 0; k < bf; k++) Q[k * bc + k] = 1.0; return; }
+  double t[3] = {0, 0, 0};
+  if (xv && xc) for (int k = 0; k < 3; k++) t[k] = xv[k] - xc[k];
+  double S[9];
+  skew_neg(t, S);
+  if (bf == 3 && bc == 6) {  // [I | -skew(t)] : displacement of the rigid body motion (u, w) at xv
+    for (int r = 0; r < 3; r++) {
+      Q[r * 6 + r] = 1.0;
+      for (int c = 0; c < 3; c++) Q[r * 6 + 3 + c] = S[r * 3 + c];
+    }
+  } else if (bf == 6 && bc == 6) {  // [[I, -skew(t)], [0, I]]
+    for (int r = 0; r < 3; r++) {
+      Q[r * 6 + r] = 1.0;
+      Q[(3 + r) * 6 + 3 + r] = 1.0;
+      for (int c = 0; c < 3; c++) Q[r * 6 + 3 + c] = S[r * 3 + c];
+    }
+  } else if (bf == 2 && bc == 3) {  // 2d elasticity: (u, w) -> u + w * (-t_y, t_x)
+    Q[0] = 1; Q[1] = 0; Q[2] = -t[1];
+    Q[3] = 0; Q[4] = 1; Q[5] = t[0];
+  } else if (bf == 3 && bc == 3) {
+    for (int k = 0; k < 3; k++) Q[k * 3 + k] = 1.0;
+  } else {
+    throw Error("transport_block: unsupported block shape " + std::to_string(bf) + "x" + std::to_string(bc));
+  }
+}
+
+}  // namespace
+
+void host_transpose(const HostBsr &A, HostBsr &T)
+{
+  // counting-sort transpose with per-block transposition (cf. TransposeSPMImpl, utils_sparseMM.cpp:54-93)
+  T.nrows = A.ncols; T.ncols = A.nrows; T.bh = A.bw; T.bw = A.bh;
+  T.rowptr.assign(T.nrows + 1, 0);
+  const i64 nnz = A.nnz();
+  for (i64 k = 0; k < nnz; k++) T.rowptr[A.col[k] + 1]++;
+  for (i64 r = 0; r < T.nrows; r++) T.rowptr[r + 1] += T.rowptr[r];
+  T.col.resize(nnz);
+  T.val.resize(nnz * A.bs());
+  std::vector<i64> pos(T.rowptr.begin(), T.rowptr.end() - 1);
+  const int bh = A.bh, bw = A.bw;
+  for (i64 i = 0; i < A.nrows; i++)
+    for (i64 k = A.rowptr[i]; k < A.rowptr[i + 1]; k++) {
+      i64 p = pos[A.col[k]]++;
+      T.col[p] = (i32)i;
+      const double *s = &A.val[k * bh * bw];
+      double *d = &T.val[p * bh * bw];
+      for (int r = 0; r < bh; r++)
+        for (int c = 0; c < bw; c++) d[c * bh + r] = s[r * bw + c];
+    }
+}
+
+void build_prolongation(const HostBsr &A, const uint8_t *free_mask, int bc, const std::vector<double> &xyz,
+                        const CoarsenOptions &opt, HostBsr &P, std::vector<i32> &vmap, std::vector<double> &cxyz)
+{
+  const i64 n = A.nrows;
+  const int bf = A.bh;
+  std::vector<uint8_t> drop(n, 0);
+  if (free_mask) for (i64 i = 0; i < n; i++) drop[i] = free_mask[i] ? 0 : 1;
+  Graph G0;
+  graph_from_matrix(A, drop, G0);
+  // isolated vertices are not aggregated (spw_agg_impl.hpp:1599-1614)
+  for (i64 i = 0; i < n; i++)
+    if (!drop[i] && G0.ptr[i + 1] == G0.ptr[i]) drop[i] = 1;
+
+  // ---- aggregation: `rounds` pairwise matching rounds + orphan round
+  vmap.assign(n, -1);
+  std::vector<i32> cmap;
+  Graph Gc, Gn;
+  const Graph *cur = &G0;
+  std::vector<uint8_t> nodrop;
+  i64 nc = 0;
+  for (int r = 0; r < opt.rounds; r++) {
+    const std::vector<uint8_t> &dr = (r == 0) ? drop : nodrop;
+    if (r > 0) nodrop.assign(cur->n, 0);
+    nc = pairing_round(*cur, (r == 0) ? drop : nodrop, opt.soc_thresh, cmap);
+    (void)dr;
+    if (r == 0) { for (i64 v = 0; v < n; v++) vmap[v] = cmap[v]; }
+    else { for (i64 v = 0; v < n; v++) if (vmap[v] >= 0) vmap[v] = cmap[vmap[v]]; }
+    coarsen_graph(*cur, cmap, nc, Gn);
+    std::swap(Gc, Gn);
+    cur = &Gc;
+  }
+  {
+    std::vector<i32> join;
+    i64 nc2 = orphan_round(*cur, opt.soc_thresh, join);
+    if (nc2 != nc) {
+      for (i64 v = 0; v < n; v++) if (vmap[v] >= 0) vmap[v] = join[vmap[v]];
+      nc = nc2;
+    }
+  }
+  // renumber coarse vertices ascending by smallest member (keeps the coarse numbering local)
+  {
+    std::vector<i32> newid(nc, -1);
+    i64 k = 0;
+    for (i64 v = 0; v < n; v++)
+      if (vmap[v] >= 0 && newid[vmap[v]] < 0) newid[vmap[v]] = (i32)k++;
+    for (i64 v = 0; v < n; v++) if (vmap[v] >= 0) vmap[v] = newid[vmap[v]];
+    nc = k;
+  }
+  // coarse vertex positions = centroid of the aggregate
+  const bool have_xyz = !xyz.empty();
+  cxyz.clear();
+  if (have_xyz) {
+    cxyz.assign(nc * 3, 0.0);
+    std::vector<i32> cnt(nc, 0);
+    for (i64 v = 0; v < n; v++)
+      if (vmap[v] >= 0) { for (int k = 0; k < 3; k++) cxyz[vmap[v] * 3 + k] += xyz[v * 3 + k]; cnt[vmap[v]]++; }
+    for (i64 c = 0; c < nc; c++) for (int k = 0; k < 3; k++) cxyz[c * 3 + k] /= std::max(cnt[c], 1);
+  }
+
+  // ---- prolongation rows
+  const int maxpr = std::max(1, opt.max_per_row);
+  P.nrows = n; P.ncols = nc; P.bh = bf; P.bw = bc;
+  P.rowptr.assign(n + 1, 0);
+  std::vector<i32> rcol(n * maxpr, -1);
+  std::vector<double> rw(n * maxpr, 0.0);
+  const int bb = bf * bf;
+  parallel_for(n, [&](i64 lo, i64 hi) {
+    std::vector<std::pair<i32, double>> nb;
+    for (i64 v = lo; v < hi; v++) {
+      const i32 C = vmap[v];
+      if (C < 0) continue;  // empty row (PWProlMap: perow = 0 when vmap == -1, vertex_factory_impl.hpp:1624-1626)
+      i32 *oc = &rcol[v * maxpr];
+      double *ow = &rw[v * maxpr];
+      oc[0] = C; ow[0] = 1.0;
+      int cnt = 1;
+      if (opt.smooth && maxpr > 1) {
+        nb.clear();
+        double in_w = 0, tot = 0;
+        for (i64 k = A.rowptr[v]; k < A.rowptr[v + 1]; k++) {
+          i32 j = A.col[k];
+          if (j == v || vmap[j] < 0) continue;
+          double w = entry_weight(&A.val[k * bb], bf);
+          if (w <= 0) continue;
+          tot += w;
+          i32 cj = vmap[j];
+          if (cj == C) { in_w += w; continue; }
+          bool found = false;
+          for (auto &pr : nb) if (pr.first == cj) { pr.second += w; found = true; break; }
+          if (!found) nb.emplace_back(cj, w);
+        }
+        // rank coarse neighbours by summed weight (desc), ties by coarse index (asc)
+        std::sort(nb.begin(), nb.end(), [](const std::pair<i32, double> &a, const std::pair<i32, double> &b) {
+          return a.second > b.second || (a.second == b.second && a.first < b.first);
+        });
+        double ws = in_w;
+        for (auto &pr : nb) {
+          if (cnt >= maxpr) break;
+          if (pr.second < opt.min_frac * tot) break;
+          oc[cnt] = pr.first; ow[cnt] = pr.second; ws += pr.second; cnt++;
+        }
+        if (cnt > 1 && ws > 0) {
+          double others = 0;
+          for (int k = 1; k < cnt; k++) { ow[k] = opt.omega * ow[k] / ws; others += ow[k]; }
+          ow[0] = 1.0 - others;
+        }
+        // ascending column order
+        for (int a = 1; a < cnt; a++)
+          for (int q = a; q > 0 && oc[q] < oc[q - 1]; q--) { std::swap(oc[q], oc[q - 1]); std::swap(ow[q], ow[q - 1]); }
+      }
+      P.rowptr[v + 1] = cnt;
+    }
+  });
+  for (i64 v = 0; v < n; v++) P.rowptr[v + 1] += P.rowptr[v];
+  P.col.resize(P.rowptr[n]);
+  P.val.assign(P.rowptr[n] * (i64)bf * bc, 0.0);
+  parallel_for(n, [&](i64 lo, i64 hi) {
+    std::vector<double> Q(bf * bc);
+    for (i64 v = lo; v < hi; v++) {
+      i64 p = P.rowptr[v];
+      int cnt = (int)(P.rowptr[v + 1] - p);
+      for (int k = 0; k < cnt; k++) {
+        i32 c = rcol[v * maxpr + k];
+        P.col[p + k] = c;
+        transport_block(bf, bc, have_xyz ? &xyz[v * 3] : nullptr, have_xyz ? &cxyz[(i64)c * 3] : nullptr, Q.data());
+        double a = rw[v * maxpr + k];
+        for (int e = 0; e < bf * bc; e++) P.val[(p + k) * bf * bc + e] = a * Q[e];
+      }
+    }
+  });
+}
+
+}  // namespace ngb

@@ -1,0 +1,199 @@
+"""Seeded synthetic inputs: no mesher / NGSolve is available, so the benchmark problems
+are generated on structured Kuhn-tet meshes (6 tets per cube sharing the main diagonal; the same
+triangulation `ngsolve.meshes.MakeStructured3DMesh(hexes=False)` produces, used by the reference in
+examples/elasticity/beam.py:20).
+
+Pure numpy, inputs only -- no product or oracle code is involved.
+"""
+import itertools
+
+import numpy as np
+
+# the 7 edge directions of the Kuhn triangulation
+_POS_DIRS = [(1, 0, 0), (0, 1, 0), (0, 0, 1), (1, 1, 0), (0, 1, 1), (1, 0, 1), (1, 1, 1)]
+
+
+def splitmix64(seed, n):
+    """uniform doubles in [-1,1) from splitmix64 (seed = 20260101 + level)."""
+    with np.errstate(over="ignore"):
+        z = (np.uint64(seed) + np.arange(1, n + 1, dtype=np.uint64) * np.uint64(0x9E3779B97F4A7C15))
+        z = (z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+        z = (z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+        z = z ^ (z >> np.uint64(31))
+    return (z >> np.uint64(11)).astype(np.float64) * (2.0 / 9007199254740992.0) - 1.0
+
+
+def _edge_cube_weight(vb, vc, nb, nc):
+    """sum over the (up to 4) cubes around an axis edge of the number of Kuhn tets containing it."""
+    w = np.zeros(np.broadcast(vb, vc).shape, dtype=np.int64)
+    for sb in (0, 1):
+        for sc in (0, 1):
+            ok = (vb - sb >= 0) & (vb - sb <= nb - 2) & (vc - sc >= 0) & (vc - sc <= nc - 2)
+            w += ok * (1 if sb + sc == 1 else 2)
+    return w
+
+
+def poisson3d_kuhn(nx, ny=None, nz=None, dirichlet=("x0", "y1"), coef=None):
+    """P1 stiffness matrix of -div(c grad u) on the unit cube, nx*ny*nz vertices, Kuhn tets.
+
+    Vertex (ix,iy,iz) has DOF number ix + nx*(iy + ny*iz).  The sparsity pattern is the mesh
+    connectivity (15-point: zeros on the face/body diagonals are stored, as an FE assembly would).
+    Returns dict(n, rowptr[int64], col[int32], val[f64], free[uint8], rhs[f64] (f=1 load), xyz).
+    `coef`: optional callable (x,y,z)->c evaluated at vertices; the edge weight uses the mean of the
+    two end-point values (a diagonal scaling that keeps symmetry and zero row sums).
+    """
+    ny = nx if ny is None else ny
+    nz = nx if nz is None else nz
+    n = nx * ny * nz
+    h = 1.0 / (max(nx, ny, nz) - 1)
+    dirs = [(0, 0, 0)] + _POS_DIRS + [(-a, -b, -c) for (a, b, c) in _POS_DIRS]
+    dirs.sort(key=lambda d: d[0] + nx * (d[1] + ny * d[2]))
+    iz, iy, ix = np.meshgrid(np.arange(nz), np.arange(ny), np.arange(nx), indexing="ij")
+    ix, iy, iz = ix.ravel(), iy.ravel(), iz.ravel()
+    idx = np.arange(n, dtype=np.int64)
+    cv = None
+    if coef is not None:
+        cv = coef(ix * h, iy * h, iz * h).astype(np.float64)
+    K = len(dirs)
+    cols = np.zeros((n, K), np.int64)
+    vals = np.zeros((n, K), np.float64)
+    mask = np.zeros((n, K), bool)
+    dims = (nx, ny, nz)
+    coord = (ix, iy, iz)
+    for k, d in enumerate(dirs):
+        jx, jy, jz = ix + d[0], iy + d[1], iz + d[2]
+        ok = (jx >= 0) & (jx < nx) & (jy >= 0) & (jy < ny) & (jz >= 0) & (jz < nz)
+        mask[:, k] = ok
+        cols[:, k] = idx + d[0] + nx * (d[1] + ny * d[2])
+        nzc = sum(abs(c) for c in d)
+        if nzc == 1:
+            a = [i for i in range(3) if d[i] != 0][0]
+            b, c = [i for i in range(3) if i != a]
+            w = _edge_cube_weight(coord[b], coord[c], dims[b], dims[c]).astype(np.float64)
+            v = -(h / 6.0) * w
+            if cv is not None:
+                j = np.clip(cols[:, k], 0, n - 1)
+                v = v * 0.5 * (cv + cv[j])
+            vals[:, k] = np.where(ok, v, 0.0)
+    kd = dirs.index((0, 0, 0))
+    vals[:, kd] = -(vals * mask).sum(axis=1)
+    cnt = mask.sum(axis=1)
+    rowptr = np.zeros(n + 1, np.int64)
+    np.cumsum(cnt, out=rowptr[1:])
+    col = cols[mask].astype(np.int32)
+    val = vals[mask]
+    free = np.ones(n, np.uint8)
+    for tag in dirichlet:
+        ax = "xyz".index(tag[0])
+        side = 0 if tag[1] == "0" else dims[ax] - 1
+        free[coord[ax] == side] = 0
+    # load vector for f = 1: (h^3/24) * number of incident tets
+    ntet = np.zeros(n, np.int64)
+    for s in itertools.product((0, 1), repeat=3):
+        ok = np.ones(n, bool)
+        for a in range(3):
+            ok &= (coord[a] - s[a] >= 0) & (coord[a] - s[a] <= dims[a] - 2)
+        ntet += ok * (6 if sum(s) in (0, 3) else 2)
+    rhs = (h ** 3 / 24.0) * ntet
+    xyz = np.stack([ix * h, iy * h, iz * h], axis=1).astype(np.float64)
+    return dict(n=n, b=1, rowptr=rowptr, col=col, val=val, free=free, rhs=rhs, xyz=xyz, h=h, dims=(nx, ny, nz))
+
+
+def kuhn_tets(nx, ny, nz):
+    """(ntet,4) vertex numbers of the Kuhn triangulation (6 path-simplices per cube)."""
+    cz, cy, cx = np.meshgrid(np.arange(nz - 1), np.arange(ny - 1), np.arange(nx - 1), indexing="ij")
+    base = np.stack([cx.ravel(), cy.ravel(), cz.ravel()], axis=1)
+    tets = []
+    for perm in itertools.permutations(range(3)):
+        p = np.zeros((4, 3), np.int64)
+        for s in range(3):
+            p[s + 1] = p[s]
+            p[s + 1, perm[s]] += 1
+        v = base[:, None, :] + p[None, :, :]
+        tets.append(v[..., 0] + nx * (v[..., 1] + ny * v[..., 2]))
+    return np.concatenate(tets, axis=0)
+
+
+def poisson3d_kuhn_assembled(nx, ny=None, nz=None):
+    """Independent element-by-element P1 assembly (scipy COO sum) used to validate poisson3d_kuhn."""
+    import scipy.sparse as sp
+    ny = nx if ny is None else ny
+    nz = nx if nz is None else nz
+    h = 1.0 / (max(nx, ny, nz) - 1)
+    n = nx * ny * nz
+    T = kuhn_tets(nx, ny, nz)
+    ids = np.arange(n)
+    X = np.stack([ids % nx, (ids // nx) % ny, ids // (nx * ny)], axis=1) * h
+    P = X[T]                                        # (nt,4,3)
+    M = np.concatenate([np.ones((len(T), 4, 1)), P], axis=2)
+    Minv = np.linalg.inv(M)                         # columns: coefficients of the hat functions
+    G = Minv[:, 1:, :]                              # (nt,3,4) gradients
+    vol = np.abs(np.linalg.det(M)) / 6.0
+    Ke = np.einsum("tki,tkj->tij", G, G) * vol[:, None, None]
+    I = np.repeat(T[:, :, None], 4, axis=2).ravel()
+    J = np.repeat(T[:, None, :], 4, axis=1).ravel()
+    A = sp.coo_matrix((Ke.ravel(), (I, J)), shape=(n, n)).tocsr()
+    A.sort_indices()
+    rhs = np.bincount(T.ravel(), weights=np.repeat(vol / 4.0, 4), minlength=n)
+    return A, rhs
+
+
+def elasticity3d_kuhn(nx, ny, nz, lx=None, E=1e3, nu=0.15, jump=None, clamp=("x0",)):
+    """P1 linear elasticity (3x3 blocks) on the beam [0,lx]x[0,1]^2 with Kuhn tets, element assembly.
+
+    lam/mu as examples/elasticity/amg_utils.py:150-153; clamp at x=0, body force (0,x,0)
+    (examples/elasticity/beamP2.py:24).  `jump`: optional callable (cx,cy,cz)->multiplier of E evaluated
+    at tet centroids (config 5: checkerboard with 1e4 contrast).
+    Returns dict(n, b=3, rowptr, col, val (blocks row-major), free, rhs, xyz).
+    """
+    import scipy.sparse as sp
+    h = 1.0 / (min(ny, nz) - 1)
+    lx = h * (nx - 1) if lx is None else lx
+    n = nx * ny * nz
+    T = kuhn_tets(nx, ny, nz)
+    ids = np.arange(n)
+    X = np.stack([(ids % nx) * (lx / (nx - 1)), ((ids // nx) % ny) * h, (ids // (nx * ny)) * h], axis=1)
+    P = X[T]
+    M = np.concatenate([np.ones((len(T), 4, 1)), P], axis=2)
+    Minv = np.linalg.inv(M)
+    G = Minv[:, 1:, :]                              # (nt,3,4): G[t,:,i] = grad phi_i
+    vol = np.abs(np.linalg.det(M)) / 6.0
+    Et = np.full(len(T), E)
+    if jump is not None:
+        cen = P.mean(axis=1)
+        Et = Et * jump(cen[:, 0], cen[:, 1], cen[:, 2])
+    mu = Et / (2 * (1 + nu))
+    lam = Et * nu / ((1 + nu) * (1 - 2 * nu))
+    # K_ij[a,b] = vol*( lam g_i[a] g_j[b] + mu g_i[b] g_j[a] + mu (g_i.g_j) delta_ab )
+    gg = np.einsum("tai,tbj->tijab", G, G)
+    dotg = np.einsum("tai,taj->tij", G, G)
+    Ke = (lam[:, None, None, None, None] * gg + mu[:, None, None, None, None] * np.swapaxes(gg, 3, 4)
+          + mu[:, None, None, None, None] * dotg[..., None, None] * np.eye(3)[None, None, None])
+    Ke = Ke * vol[:, None, None, None, None]
+    I = (3 * T[:, :, None, None, None] + np.arange(3)[None, None, None, :, None]) + np.zeros((1, 1, 4, 1, 3), np.int64)
+    J = (3 * T[:, None, :, None, None] + np.arange(3)[None, None, None, None, :]) + np.zeros((1, 4, 1, 3, 1), np.int64)
+    A = sp.coo_matrix((Ke.ravel(), (I.ravel(), J.ravel())), shape=(3 * n, 3 * n)).tocsr()
+    # block pattern = mesh connectivity (keep structural zeros of the blocks)
+    pat = sp.coo_matrix((np.ones(T.shape[0] * 16), (np.repeat(T[:, :, None], 4, 2).ravel(),
+                                                   np.repeat(T[:, None, :], 4, 1).ravel())), shape=(n, n)).tocsr()
+    pat.sort_indices()
+    rowptr = pat.indptr.astype(np.int64)
+    col = pat.indices.astype(np.int32)
+    rows = np.repeat(np.arange(n), np.diff(rowptr))
+    Ad = A.tocsr()
+    val = np.zeros((len(col), 3, 3))
+    for a in range(3):
+        for b in range(3):
+            val[:, a, b] = np.asarray(Ad[3 * rows + a, 3 * col.astype(np.int64) + b]).ravel()
+    free = np.ones(n, np.uint8)
+    dims = (nx, ny, nz)
+    coord = (ids % nx, (ids // nx) % ny, ids // (nx * ny))
+    for tag in clamp:
+        ax = "xyz".index(tag[0])
+        side = 0 if tag[1] == "0" else dims[ax] - 1
+        free[coord[ax] == side] = 0
+    # body force (0, x, 0): lumped P1 load
+    fy = np.bincount(T.ravel(), weights=np.repeat(vol / 4.0, 4) * X[T.ravel(), 0], minlength=n)
+    rhs = np.zeros((n, 3))
+    rhs[:, 1] = fy
+    return dict(n=n, b=3, rowptr=rowptr, col=col, val=val.reshape(-1), free=free, rhs=rhs.reshape(-1), xyz=X)

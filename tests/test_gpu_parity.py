@@ -1,0 +1,310 @@
+"""GPU parity tests (`-m gpu`): the CUDA path, called through the C ABI (ctypes), against the CPU oracle on the same
+seeded inputs.  Bars (BASELINE.json north_star / SURVEY.md §8c): bit-exact coarse sparsity patterns and DOF maps,
+<= 1e-10 relative agreement of every V-cycle vector in fp64, identical PCG iteration counts at 1e-8."""
+import numpy as np
+import pytest
+
+import ngsamg_b200 as ng
+from helpers import assert_same_pattern, elasticity, host_hierarchy, poisson, rand, rel, to_oracle, to_product
+from oracle import oracle as O
+
+pytestmark = pytest.mark.gpu
+
+TOL_VCYCLE = 1e-10   # north_star: residual-vector agreement <= 1e-10 relative per V-cycle in fp64
+TOL_VALUES = 1e-12   # RAP values
+
+
+@pytest.fixture(scope="module")
+def pois():
+    """Poisson P1, 13^3 vertices, Dirichlet on x=0 and y=1; built-in coarsening; oracle fed the SAME prolongations."""
+    p, A = poisson(13)
+    pc = ng.h1_scal(A, p["free"], ngs_amg_max_coarse_size=20)
+    prols = pc.GetMap()
+    amg = O.OracleAMG(to_oracle(A), p["free"], [to_oracle(P) for P in prols])
+    return p, A, pc, prols, amg
+
+
+def test_library_loaded_is_in_tree():
+    from ngsamg_b200 import _lib
+    assert _lib.lib() is not None and "ngsamg_b200/lib/libngsamg_b200.so" in _lib.LIB_PATH
+
+
+@pytest.mark.parametrize("shape", [(1, 1, 1), (3, 3, 3), (6, 6, 6), (6, 3, 3), (6, 3, 6)])
+def test_spgemm_bit_exact(shape):
+    import scipy.sparse as sp
+    ah, aw, bw = shape
+    rng = np.random.default_rng(11)
+
+    def rnd(n, m, h, w, dens):
+        pat = sp.random(n, m, density=dens, random_state=rng, format="csr")
+        pat.sort_indices()
+        return O.Bsr(n, m, h, w, pat.indptr, pat.indices, rng.standard_normal((pat.nnz, h, w)))
+
+    A, B = rnd(300, 200, ah, aw, 0.05), rnd(200, 257, aw, bw, 0.06)
+    Cg = ng.matmul(to_product(A), to_product(B))
+    Co = O.matmul(A, B)
+    assert_same_pattern(Cg, Co)
+    assert np.array_equal(Cg.val, Co.val), "values must agree bit-for-bit (same accumulation order, no FMA contraction)"
+
+
+def test_spgemm_large_rows_use_global_hash():
+    """rows whose merged length exceeds the shared-memory table (dense-ish A*B)"""
+    import scipy.sparse as sp
+    rng = np.random.default_rng(5)
+    pa = sp.random(40, 3000, density=0.05, random_state=rng, format="csr")
+    pb = sp.random(3000, 5000, density=0.01, random_state=rng, format="csr")
+    pa.sort_indices(); pb.sort_indices()
+    A = O.Bsr(40, 3000, 1, 1, pa.indptr, pa.indices, pa.data)
+    B = O.Bsr(3000, 5000, 1, 1, pb.indptr, pb.indices, pb.data)
+    Cg, Co = ng.matmul(to_product(A), to_product(B)), O.matmul(A, B)
+    assert_same_pattern(Cg, Co)
+    assert np.array_equal(Cg.val, Co.val)
+
+
+def test_rap_and_transpose(pois):
+    p, A, pc, prols, amg = pois
+    Ac = ng.rap(A, prols[0])
+    Ao = amg.level_matrix(1)
+    assert_same_pattern(Ac, Ao)
+    assert rel(Ac.val, Ao.val) < TOL_VALUES
+    T = ng.transpose(prols[0])
+    To = O.transpose(to_oracle(prols[0]))
+    assert_same_pattern(T, To)
+    assert np.array_equal(T.val, To.val)
+
+
+def test_level_matrices_and_dof_maps(pois):
+    p, A, pc, prols, amg = pois
+    assert pc.GetNLevels() == amg.nlevels >= 3
+    for l in range(pc.GetNLevels()):
+        Ag, Ao = pc.GetLevelMatrix(l), amg.level_matrix(l)
+        assert_same_pattern(Ag, Ao)                      # bit-exact coarse sparsity patterns
+        assert rel(Ag.val, Ao.val) < TOL_VALUES
+        assert pc.GetNDof(l) == Ao.nrows and pc.GetBlockSize(l) == 1
+    # DOF maps: the prolongations the device hierarchy uses are the ones the host builder produced, bit for bit
+    hp = host_hierarchy(A, p["free"], max_coarse=20)
+    assert len(hp) == len(prols)
+    for a, b in zip(hp, prols):
+        assert_same_pattern(a, b)
+        assert np.array_equal(a.val, b.val)
+
+
+def test_spmv_levels(pois):
+    p, A, pc, prols, amg = pois
+    for l in range(pc.GetNLevels() - 1):
+        Ao = amg.level_matrix(l)
+        x, y = rand(10 + l, Ao.nrows), rand(20 + l, Ao.nrows)
+        yo = y.copy()
+        O.spmv_add(Ao, -0.7, x, yo)
+        pc.LevelMultAdd(l, -0.7, x, y)
+        assert rel(y, yo) < 1e-13
+
+
+def test_transfers(pois):
+    p, A, pc, prols, amg = pois
+    for l in range(pc.GetNLevels() - 1):
+        P = to_oracle(prols[l])
+        xf, xc = rand(30 + l, P.nrows), rand(40 + l, P.ncols)
+        rc = np.zeros(P.ncols)
+        pc.TransferF2C(l, xf, rc)
+        ro = np.zeros(P.ncols)
+        O.spmv_add(O.transpose(P), 1.0, xf, ro)
+        assert rel(rc, ro) < 1e-13
+        yf, yo = xf.copy(), xf.copy()
+        pc.AddC2F(l, 0.5, yf, xc)
+        O.spmv_add(P, 0.5, xc, yo)
+        assert rel(yf, yo) < 1e-13
+
+
+@pytest.mark.parametrize("backwards", [False, True])
+@pytest.mark.parametrize("mode", ["res_xzero", "res", "rhs", "calcres"])
+def test_gauss_seidel_sweeps(pois, backwards, mode):
+    """GSS3::Smooth / SmoothBack in all flag combinations, level 0 (Dirichlet rows) and level 1"""
+    p, A, pc, prols, amg = pois
+    for l in (0, 1):
+        Ao = amg.level_matrix(l)
+        n = Ao.nrows
+        b = rand(50 + l, n)
+        x = rand(60 + l, n)
+        if l == 0:
+            x[p["free"] == 0] = 0.0
+        if mode == "res_xzero":
+            x[:] = 0
+            flags = (True, True, True)
+        elif mode == "res":
+            flags = (True, True, False)
+        elif mode == "rhs":
+            flags = (False, False, False)
+        else:
+            flags = (False, True, False)
+        res = b - Ao.to_scipy() @ x
+        xg, rg, xo, ro = x.copy(), res.copy(), x.copy(), res.copy()
+        pc._smooth(l, xg, b, rg, *flags, backwards)
+        amg.smooth(l, xo, b, ro, *flags, backwards=backwards)
+        assert rel(xg, xo) < 1e-12, (l, mode, backwards)
+        if flags[1]:
+            assert rel(rg, ro) < 1e-12, (l, mode, backwards)
+
+
+def test_vcycle_all_level_vectors(pois):
+    p, A, pc, prols, amg = pois
+    b = rand(70, p["n"])
+    xg = np.zeros(p["n"])
+    pc.Mult(b, xg)
+    xo = amg.apply(b)
+    assert rel(xg, xo) < TOL_VCYCLE
+    for l in range(pc.GetNLevels()):
+        for which in ("x", "rhs", "res"):
+            if l == 0 and which in ("x", "rhs"):
+                continue   # the oracle works in the caller's x/b on level 0
+            if which == "res" and l == pc.GetNLevels() - 1:
+                continue
+            assert rel(pc.GetLevelVector(which, l), amg.level_vec(which, l)) < TOL_VCYCLE, (which, l)
+    # MultAdd: x += s * C b (x is not zeroed, amg_matrix.cpp:385-389); MultTrans == Mult
+    y = rand(71, p["n"])
+    yo = y.copy()
+    pc.MultAdd(-2.5, b, y)
+    amg.apply_add(-2.5, b, yo)
+    assert rel(y, yo) < TOL_VCYCLE
+    xt = np.zeros(p["n"])
+    pc.MultTrans(b, xt)
+    assert np.array_equal(xt, xg)
+    # deterministic: a second application gives the identical bits
+    x2 = np.zeros(p["n"])
+    pc.Mult(b, x2)
+    assert np.array_equal(x2, xg)
+
+
+def test_vcycle_symmetric(pois):
+    p, A, pc, prols, amg = pois
+    b1, b2 = rand(72, p["n"]), rand(73, p["n"])
+    assert abs((pc * b1) @ b2 - b1 @ (pc * b2)) < 1e-10 * np.linalg.norm(b1) * np.linalg.norm(b2)
+
+
+def test_pcg_iteration_parity(pois):
+    p, A, pc, prols, amg = pois
+    cg = ng.CGSolver(mat=A, pre=pc, maxsteps=50, tol=1e-8)
+    u = cg.Solve(p["rhs"])
+    uo, ito, erro = amg.pcg(p["rhs"], tol=1e-8, maxsteps=50)
+    assert cg.iterations == ito                      # identical PCG iteration counts at 1e-8
+    assert cg.iterations < 30                        # ceiling of tests/h1/simple/test_2d_lo.py:11
+    assert rel(cg.errors, erro) < 1e-8
+    assert rel(u, uo) < 1e-9
+    assert cg.errors[-1] < 1e-8 * cg.errors[0]
+
+
+@pytest.mark.parametrize("cfg", [dict(ngs_amg_sm_steps=2), dict(ngs_amg_sm_symm=True),
+                                 dict(ngs_amg_sm_type="jacobi", ngs_amg_sm_steps=2),
+                                 dict(ngs_amg_sm_type_spec=["gs", "jacobi"], ngs_amg_sm_steps_spec=[1, 3])])
+def test_smoother_options(cfg):
+    """ProxySmoother wrapping (sm_steps / sm_symm), Jacobi, per-level SpecOpt lists"""
+    p, A = poisson(9)
+    pc = ng.h1_scal(A, p["free"], ngs_amg_max_coarse_size=20, **cfg)
+    prols = pc.GetMap()
+    nl = len(prols)
+    okw = {}
+    if "ngs_amg_sm_type_spec" in cfg:
+        pytest.skip("per-level oracle config is exercised through uniform settings") if False else None
+    st = cfg.get("ngs_amg_sm_type", "gs")
+    amg = O.OracleAMG(to_oracle(A), p["free"], [to_oracle(P) for P in prols], sm_type=st,
+                      sm_steps=cfg.get("ngs_amg_sm_steps", 1), sm_symm=cfg.get("ngs_amg_sm_symm", False))
+    if "ngs_amg_sm_type_spec" in cfg:
+        L = O.lib()
+        for l in range(nl):
+            smt = O.SM_GS if l == 0 else O.SM_JACOBI
+            L.orc_amg_set_smoother(amg.h, l, smt, 1 if l == 0 else 3, 0, 0, 1.0 if l == 0 else 0.9)
+    b = rand(80, p["n"])
+    assert rel(pc * b, amg.apply(b)) < TOL_VCYCLE
+    cg = ng.CGSolver(mat=A, pre=pc, maxsteps=80, tol=1e-8)
+    cg.Solve(p["rhs"])
+    _, ito, _ = amg.pcg(p["rhs"], tol=1e-8, maxsteps=80)
+    assert cg.iterations == ito
+
+
+def test_injected_prolongations_and_clev_none():
+    """DOF maps injected by the caller (python_solve.cpp:57-76 analogue); clev=none => x_L = 0 (amg_matrix.cpp:228-229)"""
+    p, A = poisson(8)
+    hp = host_hierarchy(A, p["free"], max_coarse=30, smooth=False)   # piecewise-constant maps
+    pc = ng.h1_scal(A, p["free"], prolongations=hp)
+    assert pc.GetNLevels() == len(hp) + 1
+    amg = O.OracleAMG(to_oracle(A), p["free"], [to_oracle(P) for P in hp])
+    b = rand(90, p["n"])
+    assert rel(pc * b, amg.apply(b)) < TOL_VCYCLE
+    pc2 = ng.h1_scal(A, p["free"], prolongations=hp, ngs_amg_clev="none")
+    amg2 = O.OracleAMG(to_oracle(A), p["free"], [to_oracle(P) for P in hp], clev="none")
+    assert rel(pc2 * b, amg2.apply(b)) < TOL_VCYCLE
+
+
+def test_edge_cases():
+    # all dofs free (pure Neumann matrix is singular -> add mass), no Dirichlet level
+    p, A = poisson(6, dirichlet=())
+    A2 = ng.SparseMatrix(A.nrows, A.ncols, 1, 1, A.rowptr, A.col, A.val + (A.col == np.repeat(np.arange(A.nrows), np.diff(A.rowptr))) * 0.1)
+    pc = ng.h1_scal(A2, None, ngs_amg_max_coarse_size=10)
+    amg = O.OracleAMG(to_oracle(A2), None, [to_oracle(P) for P in pc.GetMap()])
+    b = rand(91, p["n"])
+    assert rel(pc * b, amg.apply(b)) < TOL_VCYCLE
+    # single level: only the exact coarse solve
+    pc1 = ng.h1_scal(A2, None, ngs_amg_max_levels=1)
+    assert pc1.GetNLevels() == 1
+    x = pc1 * b
+    assert rel(A2.to_scipy() @ x, b) < 1e-9
+    # ragged / anisotropic grid and Dirichlet on three faces
+    p3, A3 = poisson(9, ny=5, nz=4, dirichlet=("x0", "y1", "z0"))
+    pc3 = ng.h1_scal(A3, p3["free"], ngs_amg_max_coarse_size=10)
+    amg3 = O.OracleAMG(to_oracle(A3), p3["free"], [to_oracle(P) for P in pc3.GetMap()])
+    b3 = rand(92, p3["n"])
+    assert rel(pc3 * b3, amg3.apply(b3)) < TOL_VCYCLE
+    # errors are reported, not swallowed
+    with pytest.raises(ng.NgsAMGError):
+        ng.h1_scal(A3, p3["free"], ngs_amg_mg_cycle="W")
+    with pytest.raises(ng.NgsAMGError):
+        ng.h1_scal(A3, p3["free"], ngs_amg_sm_type="bgs")
+
+
+def test_device_pointers_torch():
+    torch = pytest.importorskip("torch")
+    p, A = poisson(9)
+    pc = ng.h1_scal(A, p["free"], ngs_amg_max_coarse_size=20)
+    b = rand(93, p["n"])
+    xh = pc * b
+    bd = torch.from_numpy(b).cuda()
+    xd = torch.zeros_like(bd)
+    pc.Mult(bd, xd)
+    torch.cuda.synchronize()
+    assert np.array_equal(xd.cpu().numpy(), xh)
+
+
+def test_config1_size_properties():
+    """config 1 (Poisson P1, 59^3 = 205k DOFs): iteration parity at full size, symmetric operator, true residual"""
+    p, A = poisson(59)
+    pc = ng.h1_scal(A, p["free"])
+    amg = O.OracleAMG(to_oracle(A), p["free"], [to_oracle(P) for P in pc.GetMap()])
+    cg = ng.CGSolver(mat=A, pre=pc, maxsteps=100, tol=1e-8)
+    u = cg.Solve(p["rhs"])
+    uo, ito, erro = amg.pcg(p["rhs"], tol=1e-8, maxsteps=100)
+    assert cg.iterations == ito and ito < 30
+    b = rand(94, p["n"])
+    assert rel(pc * b, amg.apply(b)) < TOL_VCYCLE
+    fr = p["free"] == 1
+    r = p["rhs"] - A.to_scipy() @ u
+    assert np.linalg.norm(r[fr]) < 1e-6 * np.linalg.norm(p["rhs"][fr])
+    assert 1.0 < pc.GetOC() < 2.0
+
+
+def test_elasticity_3d():
+    """elast_3d: 3x3 fine blocks, 3x6 first prolongation, 6x6 coarse blocks (elasticity_pc_impl.hpp:668-685)"""
+    p, A = elasticity(9, 4, 4)
+    pc = ng.elast_3d(A, p["free"], vertex_xyz=p["xyz"], ngs_amg_max_coarse_size=8)
+    prols = pc.GetMap()
+    assert prols[0].bh == 3 and prols[0].bw == 6 and pc.GetBlockSize(1) == 6
+    amg = O.OracleAMG(to_oracle(A), p["free"], [to_oracle(P) for P in prols], pinv=True)
+    for l in range(pc.GetNLevels()):
+        Ag, Ao = pc.GetLevelMatrix(l), amg.level_matrix(l)
+        assert_same_pattern(Ag, Ao)
+        assert rel(Ag.val, Ao.val) < TOL_VALUES
+    b = rand(95, p["n"] * 3)
+    assert rel(pc * b, amg.apply(b)) < 1e-9
+    cg = ng.CGSolver(mat=A, pre=pc, maxsteps=100, tol=1e-6)
+    cg.Solve(p["rhs"])
+    _, ito, _ = amg.pcg(p["rhs"], tol=1e-6, maxsteps=100)
+    assert cg.iterations == ito and ito < 40          # ceiling of tests/elasticity/mdim/simple/test_3d_lo.py:10
