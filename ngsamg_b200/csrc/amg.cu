@@ -822,7 +822,7 @@ bool Amg::is_device_ptr(const void *p)
 void Amg::ensure_io(i64 n)
 {
   if (n <= io_n) return;
-  dev_free(io_a); dev_free(io_b); dev_free(io_c); dev_free(d_err);
+  dev_free(io_a); dev_free(io_b); dev_free(io_c);
   if (pin_a) cudaFreeHost(pin_a);
   if (pin_b) cudaFreeHost(pin_b);
   io_a = dev_alloc<double>(n); io_b = dev_alloc<double>(n); io_c = dev_alloc<double>(n);
