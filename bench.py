@@ -195,7 +195,12 @@ def main():
     p, A = make_problem(n)
     gen_s = time.time() - t0
     t0 = time.time()
-    pc = ng.h1_scal(A, p["free"], device=local_rank)
+    extra = {}
+    for kv in os.environ.get("NGSAMG_FLAGS", "").split(","):
+        if "=" in kv:
+            k, v = kv.split("=", 1)
+            extra["ngs_amg_" + k.strip()] = v.strip()
+    pc = ng.h1_scal(A, p["free"], device=local_rank, **extra)
     setup_s = time.time() - t0
     ndof = p["n"]
     rhs_h = np.ascontiguousarray(p["rhs"])
@@ -253,6 +258,13 @@ def main():
     for name in ("gs_tri_fwd", "gs_upass", "gs_lpass", "gs_tri_bwd", "spmv", "restrict", "prolong"):
         ms, by = pc.ProfileKernel(name, level=0, reps=10)
         kern[name] = {"ms": ms, "gbs": by / ms / 1e6, "bytes": by}
+    by_level = []
+    for l in range(pc.GetNLevels() - 1):
+        row = {}
+        for name in ("gs_tri_fwd", "gs_upass", "restrict", "prolong", "gs_lpass", "gs_tri_bwd"):
+            ms, by = pc.ProfileKernel(name, level=l, reps=5)
+            row[name] = round(ms, 4)
+        by_level.append(row)
     dom = max(("gs_tri_fwd", "gs_tri_bwd", "gs_upass", "gs_lpass"), key=lambda k: kern[k]["ms"])
     roof = {"bound": "hbm", "kernel": "k_gs_tri (%s, level 0)" % dom, "achieved": kern[dom]["gbs"], "peak": peak,
             "unit": "GB/s", "frac": kern[dom]["gbs"] / peak, "traffic": None, "peak_source": peak_src,
@@ -283,10 +295,10 @@ def main():
             "setup_host_ms": pc.LastMs("host"), "gen_s": gen_s, "wall_s_timed_region": wall_s,
             "vcycle_ms": vcycle_ms, "vcycle_bytes": vbytes, "vcycle_gbs": vbytes / vcycle_ms / 1e6,
             "vcycle_frac_of_peak": vbytes / vcycle_ms / 1e6 / peak,
-            "kernels_level0": kern, "roofline": roof, "cpu_baseline": cpu,
+            "kernels_level0": kern, "kernel_ms_by_level": by_level, "roofline": roof, "cpu_baseline": cpu,
             "e2e": {"value": world * ndof / e2e_s, "unit": "DOF/s", "h2d_bytes_per_step": 8 * ndof, "d2h_bytes_per_step": 8 * ndof,
                     "solve_s": e2e_s},
-            "gpu_launches": int(launches), "clocks": clocks,
+            "gpu_launches": int(launches), "clocks": clocks, "flags": extra,
         }
         print(json.dumps(line))
     if world > 1:

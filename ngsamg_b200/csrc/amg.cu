@@ -44,25 +44,23 @@ struct Level {
   uint8_t *d_freep = nullptr;
   Sell L, U;
   double *diag = nullptr, *dinv = nullptr;
-  // triangular sweep schedule
-  int depth = 0;
-  i32 ntiles = 0;
-  i32 *d_tile_row0 = nullptr, *d_tile_rows = nullptr, *d_tile_level = nullptr, *d_level_tiles = nullptr;
-  int *d_counters = nullptr;
+  // Gauss-Seidel dependency structure
+  int depth = 0;        // number of dependency levels (length of the critical path of a sweep)
   i64 nonfree_pad = 0;  // rows of dependency level 0 (non-free rows), padded
+  int pre_l = 8, pre_u = 8;  // register slot cache of the triangular sweeps (scalar matrices)
   // transfer to level+1
   HostBsr hP;
   Sell P, PT;
   i64 nc = 0;
   int bc = 1;
   // work vectors, level-scheduled numbering, npad*b doubles
-  double *x = nullptr, *rhs = nullptr, *res = nullptr, *tmp = nullptr, *wa = nullptr, *wb = nullptr;
+  double *x = nullptr, *y = nullptr, *rhs = nullptr, *res = nullptr, *tmp = nullptr, *wa = nullptr, *wb = nullptr;
+  double *result = nullptr;  // where the level's solution lives after a V-cycle (x or y)
   int sm_type = SM_GS, sm_steps = 1;
   bool sm_symm = false, pinv = false;
   double omega = 1.0;
   std::vector<double> xyz;
   int *d_err = nullptr;
-  TriSchedule sched() const { return TriSchedule{d_tile_row0, d_tile_rows, d_tile_level, d_level_tiles, ntiles, depth, d_err}; }
 };
 
 }  // namespace
@@ -94,7 +92,7 @@ struct Amg {
   i64 launches = 0;
   double ms_apply = 0, ms_pcg = 0, ms_setup = 0, ms_rap = 0, ms_host = 0;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-  int tri_grid_cap[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  int tri_grid_cap[24] = {0};
   int *d_err = nullptr;
   void check_watchdog();
 
@@ -105,14 +103,18 @@ struct Amg {
   void build_coarse_inverse(Level &L);
   void alloc_vectors(Level &L);
   // device primitives on level-scheduled vectors
-  template <int B> void tri(Level &L, bool backward, bool add_self, bool write_r, const double *rin, double *out, double *rout);
-  void tri_dispatch(Level &L, bool backward, bool add_self, bool write_r, const double *rin, double *out, double *rout);
+  template <int B> void tri(Level &L, bool backward, bool add_self, bool write_r, const double *rin, const double *self, double *out, double *rout);
+  void tri_dispatch(Level &L, bool backward, bool add_self, bool write_r, const double *rin, const double *self, double *out, double *rout);
+  unsigned tri_sleep_ns = 100;
+  int tri_prepoll = 1;
+  int tri_gate_all = 1;
+  int tri_ctas_per_sm = 0;
   void spmv_part(Level &L, int which /*0 L,1 U,2 L+D,3 U+D,4 full*/, const double *v, const double *y_in, double *y_out,
                  double alpha, double beta, double *xadd);
   void transfer(const Sell &S, const double *v, const double *y_in, double *y_out, double alpha, double beta);
   void calc_residuum(Level &L, const double *x, const double *b, double *res, bool x_zero);
   void gs_res(Level &L, bool backward, double *x, double *res, bool x_zero);
-  void gs_rhs(Level &L, bool backward, double *x, const double *b);
+  void gs_rhs(Level &L, bool backward, const double *x, const double *b, double *xout);
   void smooth_once(Level &L, double *x, const double *b, double *res, bool ru, bool ur, bool xz, bool backward);
   void level_smooth(Level &L, double *x, const double *b, double *res, bool ru, bool ur, bool xz, bool backward);
   void vcycle_record();
@@ -170,23 +172,7 @@ void level_schedule(const HostBsr &A, const std::vector<uint8_t> &free_mask, boo
   L.perm.resize(n);
   std::vector<i64> pos(start.begin(), start.end() - 1);
   for (i64 i = 0; i < n; i++) L.perm[i] = (i32)(pos[lvl[i]]++);
-  // tiles
-  std::vector<i32> row0, rows, tl, ltiles(L.depth, 0);
-  for (int l = shift; l < depth; l++) {
-    const i64 len = round32(cnt[l]);
-    for (i64 o = 0; o < len; o += TILE_ROWS) {
-      row0.push_back((i32)(start[l] + o));
-      rows.push_back((i32)std::min<i64>(TILE_ROWS, len - o));
-      tl.push_back(l - shift);
-      ltiles[l - shift]++;
-    }
-  }
-  L.ntiles = (i32)row0.size();
-  L.d_tile_row0 = upload_vec(row0, st);
-  L.d_tile_rows = upload_vec(rows, st);
-  L.d_tile_level = upload_vec(tl, st);
-  L.d_level_tiles = upload_vec(ltiles, st);
-  L.d_counters = dev_alloc<int>(L.depth + 2);
+  (void)st;
 }
 
 void build_sell(i64 nrows_pad, int bh, int bw, const i32 *d_len, Sell &S, cudaStream_t st, i64 *launches)
@@ -296,6 +282,91 @@ void block_pinv(int n, double *m)
   for (int i = 0; i < k; i++) for (int j = 0; j < k; j++) m[idx[i] * n + idx[j]] = sub[i * k + j];
 }
 
+// ---- coarse-level numbering -------------------------------------------------------------------------
+// The numbering of a COARSE level is an output of the hierarchy builder (the reference's comes from its agglomeration
+// order).  We number coarse vertices colour-major from a greedy colouring of the Galerkin matrix graph, so that the
+// sequential Gauss-Seidel sweep in that numbering has a dependency depth equal to the number of colours instead of
+// O(n^(1/3)).  The sweep itself stays "rows in increasing number", exactly what GSS3 does.
+void greedy_coloring_perm(const HostBsr &A, std::vector<i32> &perm, int &ncolors)
+{
+  const i64 n = A.nrows;
+  std::vector<i32> color(n, -1);
+  std::vector<i64> mark(1024, -1);
+  ncolors = 0;
+  for (i64 i = 0; i < n; i++) {
+    for (i64 k = A.rowptr[i]; k < A.rowptr[i + 1]; k++) {
+      const i32 j = A.col[k];
+      if (j != i && color[j] >= 0) {
+        if ((size_t)color[j] >= mark.size()) mark.resize(2 * color[j] + 2, -1);
+        mark[color[j]] = i;
+      }
+    }
+    i32 c = 0;
+    while ((size_t)c < mark.size() && mark[c] == i) c++;
+    if ((size_t)c >= mark.size()) mark.resize(2 * c + 2, -1);
+    color[i] = c;
+    ncolors = std::max(ncolors, c + 1);
+  }
+  std::vector<i64> start(ncolors + 1, 0);
+  for (i64 i = 0; i < n; i++) start[color[i] + 1]++;
+  for (int c = 0; c < ncolors; c++) start[c + 1] += start[c];
+  perm.resize(n);
+  for (i64 i = 0; i < n; i++) perm[i] = (i32)(start[color[i]]++);
+}
+
+// B = Pi A Pi^T (rows and columns renumbered old -> perm[old]), columns re-sorted ascending
+void permute_symmetric(HostBsr &A, const std::vector<i32> &perm)
+{
+  const i64 n = A.nrows;
+  const int bs = A.bs();
+  std::vector<i32> inv(n);
+  for (i64 i = 0; i < n; i++) inv[perm[i]] = (i32)i;
+  HostBsr B;
+  B.nrows = A.nrows; B.ncols = A.ncols; B.bh = A.bh; B.bw = A.bw;
+  B.rowptr.assign(n + 1, 0);
+  for (i64 r = 0; r < n; r++) B.rowptr[r + 1] = B.rowptr[r] + (A.rowptr[inv[r] + 1] - A.rowptr[inv[r]]);
+  B.col.resize(A.nnz());
+  B.val.resize(A.nnz() * bs);
+  parallel_for(n, [&](i64 lo, i64 hi) {
+    std::vector<std::pair<i32, i64>> ent;
+    for (i64 r = lo; r < hi; r++) {
+      const i64 o = inv[r];
+      ent.clear();
+      for (i64 k = A.rowptr[o]; k < A.rowptr[o + 1]; k++) ent.emplace_back(perm[A.col[k]], k);
+      std::sort(ent.begin(), ent.end());
+      i64 p = B.rowptr[r];
+      for (auto &e : ent) {
+        B.col[p] = e.first;
+        std::memcpy(&B.val[p * bs], &A.val[e.second * bs], sizeof(double) * bs);
+        p++;
+      }
+    }
+  }, 1024);
+  A = std::move(B);
+}
+
+// P <- P Pi^T (columns renumbered), rows re-sorted
+void renumber_columns(HostBsr &P, const std::vector<i32> &perm)
+{
+  const int bs = P.bs();
+  parallel_for(P.nrows, [&](i64 lo, i64 hi) {
+    std::vector<std::pair<i32, i64>> ent;
+    std::vector<double> tmp;
+    for (i64 r = lo; r < hi; r++) {
+      const i64 b0 = P.rowptr[r], b1 = P.rowptr[r + 1];
+      if (b1 == b0) continue;
+      ent.clear();
+      for (i64 k = b0; k < b1; k++) ent.emplace_back(perm[P.col[k]], k);
+      std::sort(ent.begin(), ent.end());
+      tmp.assign(P.val.begin() + b0 * bs, P.val.begin() + b1 * bs);
+      for (size_t q = 0; q < ent.size(); q++) {
+        P.col[b0 + q] = ent[q].first;
+        std::memcpy(&P.val[(b0 + q) * bs], &tmp[(ent[q].second - b0) * bs], sizeof(double) * bs);
+      }
+    }
+  }, 4096);
+}
+
 }  // namespace
 
 Amg::~Amg()
@@ -306,8 +377,7 @@ Amg::~Amg()
     dev_free(L.d_perm); dev_free(L.d_freep);
     L.L.release(); L.U.release(); L.P.release(); L.PT.release();
     dev_free(L.diag); dev_free(L.dinv);
-    dev_free(L.d_tile_row0); dev_free(L.d_tile_rows); dev_free(L.d_tile_level); dev_free(L.d_level_tiles); dev_free(L.d_counters);
-    dev_free(L.x); dev_free(L.rhs); dev_free(L.res); dev_free(L.tmp); dev_free(L.wa); dev_free(L.wb);
+    dev_free(L.x); dev_free(L.y); dev_free(L.rhs); dev_free(L.res); dev_free(L.tmp); dev_free(L.wa); dev_free(L.wb);
   }
   dev_free(d_cinv); dev_free(cg_u); dev_free(cg_s); dev_free(cg_q); dev_free(d_dot); dev_free(d_partial);
   dev_free(io_a); dev_free(io_b); dev_free(io_c); dev_free(d_err);
@@ -322,7 +392,8 @@ Amg::~Amg()
 void Amg::alloc_vectors(Level &L)
 {
   const size_t nb = (size_t)L.npad * L.b;
-  for (double **p : {&L.x, &L.rhs, &L.res, &L.tmp}) {
+  L.result = nullptr;
+  for (double **p : {&L.x, &L.y, &L.rhs, &L.res, &L.tmp}) {
     *p = dev_alloc<double>(nb);
     NGB_CUDA(cudaMemsetAsync(*p, 0, nb * sizeof(double), st));
   }
@@ -351,7 +422,14 @@ void Amg::build_level_layout(Level &L, const DevCsr &dA)
   NGB_CUDA(cudaMemsetAsync(L.diag, 0, sizeof(double) * L.npad * bs, st));
   k_layout_fill<<<nblk(n), TB, 0, st>>>(n, bs, dA.rowptr, dA.col, dA.val, L.d_perm, L.d_perm, 1, L.L.slice_ptr, L.L.col, L.L.val,
                                         L.U.slice_ptr, L.U.col, L.U.val, L.diag);
-  launches += 2;
+  {
+    const int flip = (int)flags.num("b200_sort_flip", 0);
+    if (flip < 2) {
+      k_sell_sort_rows<<<nblk(L.npad), TB, 0, st>>>(L.npad, bs, L.L.slice_ptr, L.L.col, L.L.val, flip ? 1 : 0);
+      k_sell_sort_rows<<<nblk(L.npad), TB, 0, st>>>(L.npad, bs, L.U.slice_ptr, L.U.col, L.U.val, flip ? 0 : 1);
+    }
+  }
+  launches += 4;
   // true entry counts (for the byte model)
   {
     std::vector<i32> h1(L.npad), h2(L.npad);
@@ -363,6 +441,25 @@ void Amg::build_level_layout(Level &L, const DevCsr &dA)
     L.L.nnz = a; L.U.nnz = c;
   }
   dev_free(len1); dev_free(len2);
+  {
+    // slice width histogram -> register slot cache size of the sweeps: the smallest of 8 / 12 / 16 covering >= 97 % of the
+    // slices (wider slices spill into the chunked path)
+    auto pick = [&](const Sell &S) {
+      std::vector<i64> sp(S.nslices + 1);
+      NGB_CUDA(cudaMemcpyAsync(sp.data(), S.slice_ptr, sizeof(i64) * (S.nslices + 1), cudaMemcpyDeviceToHost, st));
+      NGB_CUDA(cudaStreamSynchronize(st));
+      i64 le8 = 0, le12 = 0, le16 = 0;
+      for (i64 s = 0; s < S.nslices; s++) { const i64 w = sp[s + 1] - sp[s]; le8 += (w <= 8); le12 += (w <= 12); le16 += (w <= 16); }
+      const double n = (double)std::max<i64>(S.nslices, 1);
+      if (le8 >= 0.97 * n) return 8;
+      if (le12 >= 0.97 * n) return 12;
+      (void)le16;
+      return 16;
+    };
+    const int force = (int)flags.num("b200_tri_pre", 0);
+    L.pre_l = force ? force : pick(L.L);
+    L.pre_u = force ? force : pick(L.U);
+  }
   // dinv (GSS3::CalcDiags)
   int *d_err = dev_alloc<int>(1);
   NGB_CUDA(cudaMemsetAsync(d_err, 0, sizeof(int), st));
@@ -553,6 +650,24 @@ void Amg::finalize()
       rap_ms += ms;
       L.nc = L.hP.ncols; L.bc = L.hP.bw;
       dev_csr_download(dAc, lev[l + 1]->hA, st, true);
+      if (injected.empty() && flags.flag("b200_color_coarse", true)) {
+        // colour-major coarse numbering (shallow Gauss-Seidel dependency DAG on the coarse level)
+        auto h0 = std::chrono::steady_clock::now();
+        std::vector<i32> cperm;
+        int ncol = 0;
+        greedy_coloring_perm(lev[l + 1]->hA, cperm, ncol);
+        permute_symmetric(lev[l + 1]->hA, cperm);
+        renumber_columns(L.hP, cperm);
+        std::vector<double> &cx = lev[l + 1]->xyz;
+        if (!cx.empty()) {
+          std::vector<double> nx(cx.size());
+          for (i64 i = 0; i < L.nc; i++) for (int k = 0; k < 3; k++) nx[(i64)cperm[i] * 3 + k] = cx[i * 3 + k];
+          cx.swap(nx);
+        }
+        dev_csr_free(dAc);
+        dev_csr_upload(lev[l + 1]->hA, dAc, st);
+        host_s += std::chrono::duration<double>(std::chrono::steady_clock::now() - h0).count();
+      }
     }
     {
       auto h0 = std::chrono::steady_clock::now();
@@ -587,33 +702,45 @@ void Amg::finalize()
 // device primitives
 // ------------------------------------------------------------------------------------------------
 template <int B>
-void Amg::tri(Level &L, bool backward, bool add_self, bool write_r, const double *rin, double *out, double *rout)
+void Amg::tri(Level &L, bool backward, bool add_self, bool write_r, const double *rin, const double *self, double *out, double *rout)
 {
   const Sell &T = backward ? L.U : L.L;
-  NGB_CUDA(cudaMemsetAsync(L.d_counters, 0, sizeof(int) * (L.depth + 2), st));
-  int idx = (B == 1 ? 0 : B == 2 ? 1 : B == 3 ? 2 : 3) * 2 + (add_self ? 1 : 0);
+  // sentinel-fill the output: a row is "published" once its entry is no longer the all-ones NaN
+  NGB_CUDA(cudaMemsetAsync(out, 0xFF, sizeof(double) * L.npad * L.b, st));
+  // register slot cache: smallest of 8/12/16 that covers (almost) all slices of this part
+  const int pre = (B == 1) ? (backward ? L.pre_u : L.pre_l) : 0;
+  const int idx = ((B == 1 ? 0 : B == 2 ? 1 : B == 3 ? 2 : 3) * 2 + (add_self ? 1 : 0)) * 3 + (pre == 16 ? 2 : pre == 12 ? 1 : 0);
   auto launch = [&](auto kern) {
     if (!tri_grid_cap[idx]) {
       int occ = 0;
-      NGB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, TILE_ROWS, 0));
-      tri_grid_cap[idx] = std::max(1, occ) * num_sms;
+      NGB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 256, 0));
+      occ = std::max(1, occ);
+      if (tri_ctas_per_sm > 0) occ = std::min(occ, tri_ctas_per_sm);
+      tri_grid_cap[idx] = occ * num_sms;   // the whole grid must be resident (see k_gs_tri)
     }
-    const int grid = std::min<int>(L.ntiles, tri_grid_cap[idx]);
-    kern<<<grid, TILE_ROWS, 0, st>>>(T.view(), L.diag, L.dinv, rin, out, rout, L.sched(), backward ? 1 : 0, L.d_counters);
+    const i64 nslices = L.npad / 32;
+    const int grid = (int)std::min<i64>((nslices + 7) / 8, tri_grid_cap[idx]);
+    TriParams prm{nslices, backward ? 1 : 0, tri_sleep_ns, tri_prepoll, tri_gate_all, L.nonfree_pad, d_err};
+    kern<<<grid, 256, 0, st>>>(T.view(), L.diag, L.dinv, rin, self, out, rout, prm);
   };
-  if (add_self) launch(k_gs_tri<B, true, false>);
-  else if (write_r) launch(k_gs_tri<B, false, true>);
-  else throw Error("tri: unsupported mode");
+  if (!add_self && !write_r) throw Error("tri: unsupported mode");
+  if constexpr (B == 1) {
+    if (add_self) { if (pre == 16) launch(k_gs_tri<1, true, false, 16>); else if (pre == 12) launch(k_gs_tri<1, true, false, 12>); else launch(k_gs_tri<1, true, false, 8>); }
+    else { if (pre == 16) launch(k_gs_tri<1, false, true, 16>); else if (pre == 12) launch(k_gs_tri<1, false, true, 12>); else launch(k_gs_tri<1, false, true, 8>); }
+  } else {
+    if (add_self) launch(k_gs_tri<B, true, false, 0>);
+    else launch(k_gs_tri<B, false, true, 0>);
+  }
   launches += 2;
 }
 
-void Amg::tri_dispatch(Level &L, bool backward, bool add_self, bool write_r, const double *rin, double *out, double *rout)
+void Amg::tri_dispatch(Level &L, bool backward, bool add_self, bool write_r, const double *rin, const double *self, double *out, double *rout)
 {
   switch (L.b) {
-    case 1: tri<1>(L, backward, add_self, write_r, rin, out, rout); break;
-    case 2: tri<2>(L, backward, add_self, write_r, rin, out, rout); break;
-    case 3: tri<3>(L, backward, add_self, write_r, rin, out, rout); break;
-    case 6: tri<6>(L, backward, add_self, write_r, rin, out, rout); break;
+    case 1: tri<1>(L, backward, add_self, write_r, rin, self, out, rout); break;
+    case 2: tri<2>(L, backward, add_self, write_r, rin, self, out, rout); break;
+    case 3: tri<3>(L, backward, add_self, write_r, rin, self, out, rout); break;
+    case 6: tri<6>(L, backward, add_self, write_r, rin, self, out, rout); break;
     default: throw Error("unsupported block size");
   }
 }
@@ -675,17 +802,17 @@ void Amg::calc_residuum(Level &L, const double *x, const double *b, double *res,
 void Amg::gs_res(Level &L, bool backward, double *x, double *res, bool x_zero)
 {
   double *d = x_zero ? x : L.tmp;
-  if (L.nonfree_pad) NGB_CUDA(cudaMemsetAsync(d, 0, sizeof(double) * L.nonfree_pad * L.b, st));
-  tri_dispatch(L, backward, false, true, res, d, res);
+  tri_dispatch(L, backward, false, true, res, nullptr, d, res);
   spmv_part(L, backward ? 0 : 1, d, res, res, -1.0, 1.0, x_zero ? nullptr : x);
 }
 
 // GSS3::SmoothRHSInternal (gssmoother.cpp:195-257): x_i += dinv_i (b_i - A_i x); the not-yet-updated half of the row
-// (and the diagonal) is applied first as a plain SpMV, the updated half level-scheduled.
-void Amg::gs_rhs(Level &L, bool backward, double *x, const double *b)
+// (and the diagonal) is applied first as a plain SpMV, the updated half by the sync-free triangular sweep, which
+// writes the new iterate to a second buffer (xout != x) because the output doubles as the dependency flags.
+void Amg::gs_rhs(Level &L, bool backward, const double *x, const double *b, double *xout)
 {
   spmv_part(L, backward ? 2 : 3, x, b, L.tmp, -1.0, 1.0, nullptr);
-  tri_dispatch(L, backward, true, false, L.tmp, x, nullptr);
+  tri_dispatch(L, backward, true, false, L.tmp, x, xout, nullptr);
 }
 
 // GSS3::Smooth / SmoothBack (gssmoother.cpp:349-398); RichardsonSmoother::Smooth for Jacobi (base_smoother.cpp:61-83)
@@ -694,10 +821,10 @@ void Amg::smooth_once(Level &L, double *x, const double *b, double *res, bool ru
   if (L.sm_type == SM_GS) {
     if (ru) {
       if (ur) gs_res(L, backward, x, res, xz);
-      else { if (xz) NGB_CUDA(cudaMemsetAsync(x, 0, sizeof(double) * L.npad * L.b, st)); gs_rhs(L, backward, x, b); }
+      else { if (xz) NGB_CUDA(cudaMemsetAsync(x, 0, sizeof(double) * L.npad * L.b, st)); gs_rhs(L, backward, x, b, L.y); NGB_CUDA(cudaMemcpyAsync(x, L.y, sizeof(double) * L.npad * L.b, cudaMemcpyDeviceToDevice, st)); }
     } else {
       if (ur) { calc_residuum(L, x, b, res, xz); gs_res(L, backward, x, res, xz); }
-      else { if (xz) NGB_CUDA(cudaMemsetAsync(x, 0, sizeof(double) * L.npad * L.b, st)); gs_rhs(L, backward, x, b); }
+      else { if (xz) NGB_CUDA(cudaMemsetAsync(x, 0, sizeof(double) * L.npad * L.b, st)); gs_rhs(L, backward, x, b, L.y); NGB_CUDA(cudaMemcpyAsync(x, L.y, sizeof(double) * L.npad * L.b, cudaMemcpyDeviceToDevice, st)); }
     }
   } else {
     if (xz) NGB_CUDA(cudaMemsetAsync(x, 0, sizeof(double) * L.npad * L.b, st));
@@ -743,8 +870,7 @@ void Amg::vcycle_record()
     // x_l = 0 ; res_l = b_l ; Smooth(x, b, res, true, true, true)     (:193-206)
     // (res_l = b_l is folded into the sweep: the triangular kernel reads rhs and writes res)
     if (L.sm_type == SM_GS && !L.sm_symm && L.sm_steps == 1) {
-      if (L.nonfree_pad) NGB_CUDA(cudaMemsetAsync(L.x, 0, sizeof(double) * L.nonfree_pad * L.b, st));
-      tri_dispatch(L, false, false, true, L.rhs, L.x, L.res);
+      tri_dispatch(L, false, false, true, L.rhs, nullptr, L.x, L.res);
       spmv_part(L, 1, L.x, L.res, L.res, -1.0, 1.0, nullptr);
     } else {
       NGB_CUDA(cudaMemcpyAsync(L.res, L.rhs, sizeof(double) * L.npad * L.b, cudaMemcpyDeviceToDevice, st));
@@ -759,14 +885,21 @@ void Amg::vcycle_record()
       k_dense_gemv<<<nblk((i64)cinv_n * 32), TB, 0, st>>>(cinv_n, d_cinv, L.rhs, L.x);
       launches++;
     } else NGB_CUDA(cudaMemsetAsync(L.x, 0, sizeof(double) * L.npad * L.b, st));
+    L.result = L.x;
   }
   for (int l = NL - 2; l >= 0; l--) {
     Level &L = *lev[l];
     Level &C = *lev[l + 1];
     // AddC2F: x_l += P x_{l+1}   (:263, dof_map.cpp:694-709)
-    transfer(L.P, C.x, L.x, L.x, 1.0, 1.0);
+    transfer(L.P, C.result, L.x, L.x, 1.0, 1.0);
     // SmoothBack(x, b, res, false, false, false)   (:302)
-    level_smooth(L, L.x, L.rhs, L.res, false, false, false, true);
+    if (L.sm_type == SM_GS && !L.sm_symm && L.sm_steps == 1) {
+      gs_rhs(L, true, L.x, L.rhs, L.y);   // the new iterate is produced in the second buffer
+      L.result = L.y;
+    } else {
+      level_smooth(L, L.x, L.rhs, L.res, false, false, false, true);
+      L.result = L.x;
+    }
   }
 }
 
@@ -942,6 +1075,14 @@ int ngsamg_b200_create(const char *type, const ngsamg_csr *A, const uint8_t *fre
   NGB_CUDA(cudaGetDeviceProperties(&prop, device));
   a.num_sms = prop.multiProcessorCount;
   a.use_graph = a.flags.flag("b200_cuda_graph", true);
+  a.tri_sleep_ns = (unsigned)a.flags.num("b200_tri_sleep_ns", 100);
+  a.tri_ctas_per_sm = (int)a.flags.num("b200_tri_ctas_per_sm", 0);
+  a.tri_prepoll = (int)a.flags.num("b200_tri_prepoll", 1);
+  a.tri_gate_all = (int)a.flags.num("b200_tri_gate_all", 1);
+  {
+    int pm = (int)a.flags.num("b200_tri_pollmode", 0);
+    NGB_CUDA(cudaMemcpyToSymbol(g_pollmode, &pm, sizeof(int)));
+  }
   auto L = std::make_unique<Level>();
   copy_csr(A, L->hA);
   if (free_mask) {
@@ -1006,7 +1147,7 @@ static void apply_impl(Amg &a, double s, const double *b, double *x, bool add)
   const bool xdev = a.is_device_ptr(x);
   double *xd = xdev ? x : a.io_b;
   if (add && !xdev) { a.to_device(x, n, a.io_b); }
-  k_permute_out<<<nblk(L.n), TB, 0, a.st>>>(L.n, L.b, L.d_perm, L.x, xd, s, add ? 1 : 0);
+  k_permute_out<<<nblk(L.n), TB, 0, a.st>>>(L.n, L.b, L.d_perm, L.result, xd, s, add ? 1 : 0);
   a.launches += 2;
   if (!xdev) a.from_device(x, xd, n);
   cudaEventRecord(a.ev1, a.st);
@@ -1146,10 +1287,11 @@ int ngsamg_b200_pcg(ngsamg_b200_t *h, const double *rhs, double *x, double tol, 
   if (!a.cg_u) { a.cg_u = dev_alloc<double>(np); a.cg_s = dev_alloc<double>(np); a.cg_q = dev_alloc<double>(np); }
   cudaEventRecord(a.ev0, a.st);
   const double *rd = a.to_device(rhs, n, a.io_a);
-  double *d = L.rhs, *w = L.x, *u = a.cg_u, *s = a.cg_s, *q = a.cg_q;
+  double *d = L.rhs, *u = a.cg_u, *s = a.cg_s, *q = a.cg_q;
   NGB_CUDA(cudaMemsetAsync(u, 0, sizeof(double) * np, a.st));
   k_permute_in<<<nblk(L.n), TB, 0, a.st>>>(L.n, L.b, L.d_perm, rd, d);
   a.vcycle();
+  const double *w = L.result;   // fixed by the (captured) cycle: x or y buffer of level 0
   NGB_CUDA(cudaMemcpyAsync(s, w, sizeof(double) * np, cudaMemcpyDeviceToDevice, a.st));
   double wdn = a.dot(np, w, d);
   const double err0 = std::sqrt(std::fabs(wdn));
@@ -1240,7 +1382,7 @@ int ngsamg_b200_get_level_vector(ngsamg_b200_t *h, int level, int which, double 
   NGB_TRY
   Amg &a = ready(h);
   Level &L = get_level(a, level);
-  const double *src = which == 0 ? L.x : which == 1 ? L.rhs : which == 2 ? L.res : nullptr;
+  const double *src = which == 0 ? (L.result ? L.result : L.x) : which == 1 ? L.rhs : which == 2 ? L.res : nullptr;
   if (!src) throw Error("get_level_vector: which must be 0 (x), 1 (rhs) or 2 (res)");
   const i64 n = L.n * L.b;
   a.ensure_io(n);
@@ -1385,14 +1527,15 @@ int ngsamg_b200_profile_kernel(ngsamg_b200_t *h, int level, int which, int reps,
   double B = 0;
   auto run = [&]() {
     switch (which) {
-      case 0: if (L.nonfree_pad) NGB_CUDA(cudaMemsetAsync(L.x, 0, sizeof(double) * L.nonfree_pad * L.b, a.st));
-              a.tri_dispatch(L, false, false, true, L.rhs, L.x, L.res); B = L.L.nnz * bb + 2 * D + 3 * v; break;
+      case 0: a.tri_dispatch(L, false, false, true, L.rhs, nullptr, L.x, L.res); B = L.L.nnz * bb + 2 * D + 3 * v; break;
       case 1: a.spmv_part(L, 1, L.x, L.res, L.res, -1.0, 1.0, nullptr); B = L.U.nnz * bb + 3 * v; break;
       case 2: a.spmv_part(L, 2, L.x, L.rhs, L.tmp, -1.0, 1.0, nullptr); B = L.L.nnz * bb + D + 3 * v; break;
-      case 3: a.tri_dispatch(L, true, true, false, L.tmp, L.x, nullptr); B = L.U.nnz * bb + D + 3 * v; break;
+      case 3: a.tri_dispatch(L, true, true, false, L.tmp, L.x, L.y, nullptr); B = L.U.nnz * bb + D + 3 * v; break;
       case 4: ensure_scratch(a, L); a.spmv_part(L, 4, L.x, nullptr, L.wa, 1.0, 0.0, nullptr); B = (L.L.nnz + L.U.nnz) * bb + D + 2 * v; break;
       case 5: a.transfer(L.PT, L.res, nullptr, C.rhs, 1.0, 0.0); B = pb + v + vc; break;
       case 6: a.transfer(L.P, C.x, L.x, L.x, 1.0, 1.0); B = pb + 2 * v + vc; break;
+      case 7: a.tri_dispatch(L, false, true, false, L.tmp, L.x, L.y, nullptr); B = L.L.nnz * bb + D + 3 * v; break;   // forward, RHS form
+      case 8: a.tri_dispatch(L, true, false, true, L.rhs, nullptr, L.x, L.res); B = L.U.nnz * bb + 2 * D + 3 * v; break;  // backward, RES form
       default: throw Error("profile_kernel: unknown kernel id");
     }
   };

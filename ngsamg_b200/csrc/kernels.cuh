@@ -142,102 +142,206 @@ __global__ void __launch_bounds__(256) k_sell_spmv(i64 nrows_pad, SellView S1, S
 }
 
 // ------------------------------------------------------------------------------------------------
-// K2/K3: level-scheduled triangular half-sweep of Gauss-Seidel (persistent, dependency counters).
-//   out_i = (ADD_SELF ? out_i : 0) + dinv_i * ( rin_i - sum_{k in T_i} A_ik out_k )        [T = L fwd, U bwd]
+// K2/K3: triangular half-sweep of Gauss-Seidel in the reference's row order -- sync-free, "data is the flag".
+//   out_i  = (ADD_SELF ? self_i : 0) + dinv_i * ( rin_i - sum_{k in T_i} A_ik out_k )      [T = L forward, U backward]
 //   rout_i = ( rin_i - sum_T A_ik out_k ) - D_ii * delta_i                               [RES form only]
-// Tiles = up to TILE_ROWS rows of ONE dependency level, taken in sweep order from a ticket counter;
-// a tile waits until the previous level's tiles have all published (`done[level]` counters, release/acquire),
-// so every claimed tile only waits on tiles that are already held by running CTAs (deadlock-free for any grid).
-// The tile's matrix rows do not depend on `out`, so they are pulled towards L2 before the wait.
+// `out` is filled with a sentinel (all-ones NaN) before the launch; a row polls the entries of `out` it depends on
+// until they are no longer the sentinel, computes, and publishes its own value with a plain 8-byte store: no
+// barriers, counters, atomics or fences anywhere.  Rows are stored in dependency-level order, so the rows of a
+// slice (= warp) are mutually independent and their dependencies lie in earlier slices.  Slices are dealt to the
+// resident warps round-robin in sweep order; every warp walks its slices in that order, hence the earliest
+// unfinished slice always has all its dependencies finished and the sweep cannot deadlock as long as the whole grid
+// is resident (the host sizes it from the occupancy calculator).  Each warp loads its matrix entries BEFORE it starts
+// polling, so HBM latency is off the dependency chain; the chain costs one L2 store->load hop per dependency level.
 // ------------------------------------------------------------------------------------------------
-struct TriSchedule {
-  const i32 *tile_row0;   // first (padded) row of the tile
-  const i32 *tile_rows;   // rows in the tile (multiple of 32)
-  const i32 *tile_level;  // dependency level of the tile
-  const i32 *level_tiles; // [nlevels] tiles per level
-  i32 ntiles, nlevels;
-  int *err;               // set to 1 if a dependency wait timed out (watchdog; never in a healthy run)
+__device__ int g_pollmode;  // experiment switch: flavour of the polling load
+__device__ __forceinline__ double ld_poll(const double *p)
+{
+  double v;
+  const int m = g_pollmode;
+  if (m == 0) asm volatile("ld.relaxed.gpu.global.f64 %0, [%1];" : "=d"(v) : "l"(p));
+  else if (m == 1) asm volatile("ld.volatile.global.f64 %0, [%1];" : "=d"(v) : "l"(p));
+  else if (m == 2) asm volatile("ld.acquire.gpu.global.f64 %0, [%1];" : "=d"(v) : "l"(p));
+  else asm volatile("ld.global.cv.f64 %0, [%1];" : "=d"(v) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ bool is_sentinel(double v) { return __double_as_longlong(v) == -1LL; }
+
+struct TriParams {
+  i64 nslices;
+  int backward;
+  unsigned sleep_ns;  // back-off of the single-address pre-poll
+  int prepoll;        // 1: gate on the latest dependency with one polling lane before the gather
+  int gate_all;       // 1: gate every chunk on its newest entry, 0: only the last chunk of the row
+  i64 nonfree;        // rows [0, nonfree) are the non-free rows (dependency level 0)
+  int *err;           // watchdog flag (set if a wait exceeds ~2^26 polls; never in a healthy run)
 };
 
-template <int B, bool ADD_SELF, bool WRITE_R>
+template <int B, bool ADD_SELF, bool WRITE_R, int PRE>
 __global__ void __launch_bounds__(256) k_gs_tri(SellView T, const double *__restrict__ diag, const double *__restrict__ dinv,
-                                               const double *rin, double *out, double *rout, TriSchedule sch,
-                                               int backward, int *counters /* [0]=ticket, [1+l]=done[l] */)
+                                               const double *rin, const double *__restrict__ self, double *out,
+                                               double *rout, TriParams prm)
 {
-  __shared__ int s_tile;
-  int *ticket = counters;
-  int *done = counters + 1;
+  // PRE = slots cached in registers across the wait (scalar case only; the host picks 8, 12 or 16 from the slice widths)
+  static_assert(B == 1 || PRE == 0, "register slot cache is implemented for scalar matrices");
   const int lane = threadIdx.x & 31;
-  for (;;) {
-    if (threadIdx.x == 0) s_tile = atomicAdd(ticket, 1);
-    __syncthreads();
-    const int tk = s_tile;
-    if (tk >= sch.ntiles) break;
-    const int t = backward ? (sch.ntiles - 1 - tk) : tk;
-    const int lvl = sch.tile_level[t];
-    const i64 row = (i64)sch.tile_row0[t] + threadIdx.x;
-    const bool active = (int)threadIdx.x < sch.tile_rows[t];
-    const i64 slice = row >> 5;
-    double r[B], self[B];
-    if (active) {
-      // warm L2 with this slice's entries while the dependency is still pending
-      const i64 base = T.slice_ptr[slice];
-      const int width = (int)(T.slice_ptr[slice + 1] - base);
-      const char *cb = (const char *)(T.col + base * 32);
-      const char *vb = (const char *)(T.val + base * (i64)(B * B) * 32);
-      const int nlc = width;                 // 128 B lines of column indices
-      const int nlv = width * B * B * 2;     // 128 B lines of values
-      for (int l = lane; l < nlc; l += 32) asm volatile("prefetch.global.L2 [%0];" ::"l"(cb + (i64)l * 128));
-      for (int l = lane; l < nlv; l += 32) asm volatile("prefetch.global.L2 [%0];" ::"l"(vb + (i64)l * 128));
+  const i64 gw = ((i64)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const i64 nw = ((i64)gridDim.x * blockDim.x) >> 5;
+  for (i64 s = gw; s < prm.nslices; s += nw) {
+    const i64 slice = prm.backward ? (prm.nslices - 1 - s) : s;
+    const i64 row = slice * 32 + lane;
+    const i64 base = T.slice_ptr[slice];
+    const int width = (int)(T.slice_ptr[slice + 1] - base);
+    const i32 *cp = T.col + base * 32 + lane;
+    const double *vp = T.val + base * (i64)(B * B) * 32 + lane;
+    // a non-free row is never updated (dinv = 0) and the increments of non-free rows are zero, so couplings between two
+    // non-free rows contribute nothing: skip them (they would otherwise chain the boundary rows one after another)
+    const i32 cut = (row < prm.nonfree) ? (i32)prm.nonfree : 0;
+    // ---- everything that does not depend on `out`: own rhs, diagonal blocks, matrix entries
+    double acc[B];
 #pragma unroll
-      for (int p = 0; p < B; p++) r[p] = rin[row * B + p];
-      if (ADD_SELF) {
+    for (int p = 0; p < B; p++) acc[p] = rin[row * B + p];
+    double sv[B];
+    if (ADD_SELF) {
 #pragma unroll
-        for (int p = 0; p < B; p++) self[p] = ld_cg(out + row * B + p);
+      for (int p = 0; p < B; p++) sv[p] = self[row * B + p];
+    }
+    const double *dp = dinv + slice * (i64)(B * B) * 32 + lane;
+    double di0 = 0.0;
+    if (B == 1) di0 = dp[0];
+    i32 pc[PRE > 0 ? PRE : 1];
+    double pv[PRE > 0 ? PRE : 1];
+    if (PRE > 0) {
+#pragma unroll
+      for (int k = 0; k < PRE; k++) {
+        pc[k] = (k < width) ? cp[(i64)k * 32] : -1;
+        if (pc[k] < cut) pc[k] = -1;
+        pv[k] = (k < width) ? vp[(i64)k * 32] : 0.0;
       }
     }
-    const int dep = backward ? lvl + 1 : lvl - 1;
-    if (threadIdx.x == 0 && dep >= 0 && dep < sch.nlevels) {
-      const int need = sch.level_tiles[dep];
-      unsigned spins = 0;
-      while (ld_acquire(done + dep) < need) {
-        __nanosleep(20);
-        if (++spins > (1u << 27)) { atomicExch(sch.err, 1); break; }  // watchdog: report instead of hanging the GPU
-      }
+    if (width > PRE) {
+      // entries that do not fit the register cache: pull their lines into L1 now, they are consumed after the wait
+      const char *cb = (const char *)(T.col + (base + PRE) * 32);
+      const char *vb = (const char *)(T.val + (base + PRE) * (i64)(B * B) * 32);
+      const int nlc = width - PRE, nlv = (width - PRE) * B * B * 2;  // 128 B lines
+      for (int l = lane; l < nlc; l += 32) asm volatile("prefetch.global.L1 [%0];" ::"l"(cb + (i64)l * 128));
+      for (int l = lane; l < nlv; l += 32) asm volatile("prefetch.global.L1 [%0];" ::"l"(vb + (i64)l * 128));
     }
-    __syncthreads();
-    if (active) {
-      double acc[B];
+    constexpr int CH = (B == 1) ? 8 : (B == 2 ? 4 : (B == 3 ? 2 : 1));
+    // Entries are sorted by age (oldest dependency first), so within every chunk of slots the dependency published last
+    // is the chunk's last valid entry.  Before a chunk is gathered ONE lane gates on the warp's newest entry of that
+    // chunk with back-off (1 sector per poll instead of 32 x chunk); after the gate the chunk's polls are issued
+    // together and a straggler is simply re-polled.  Old chunks pass their gate at once, so a wide row is gathered
+    // while the sweep is still waiting for the row's newest dependencies, without hammering L2 during the wait.
+    const int last0 = (width <= PRE) ? 0 : PRE + ((width - PRE - 1) / CH) * CH;   // first slot of the last chunk
+    auto gate = [&](i32 mylast, int k0) {
+      if (!prm.prepoll || (!prm.gate_all && k0 != last0)) return;
+      i32 f = (mylast >= cut && (mylast >> 5) != slice) ? mylast : -1;
+      if (prm.backward) { if (f < 0) f = 0x7fffffff; }
 #pragma unroll
-      for (int p = 0; p < B; p++) acc[p] = r[p];
-      if (B == 1) acc[0] -= sell_row_dot1<true>(T, slice, lane, out);
-      else sell_row_mac<B, B, true>(T, slice, lane, out, acc, -1.0);
-      const double *dp = dinv + slice * (i64)(B * B) * 32 + lane;
-      double dl[B];
-#pragma unroll
-      for (int p = 0; p < B; p++) {
-        double s = 0.0;
-#pragma unroll
-        for (int q = 0; q < B; q++) s = fma(dp[(p * B + q) * 32], acc[q], s);
-        dl[p] = s;
+      for (int o = 16; o; o >>= 1) {
+        const i32 g = __shfl_xor_sync(0xffffffffu, f, o);
+        f = prm.backward ? min(f, g) : max(f, g);
       }
+      if (prm.backward && f == 0x7fffffff) f = -1;
+      if (f >= 0 && lane == 0) {
+        unsigned spins = 0;
+        while (is_sentinel(ld_poll(out + (i64)f * B))) {
+          if (prm.sleep_ns) __nanosleep(prm.sleep_ns);
+          if (++spins > (1u << 26)) { atomicExch(prm.err, 1); break; }
+        }
+      }
+      __syncwarp();
+    };
+    if (PRE > 0) {
+      {
+        i32 mylast = -1;
 #pragma unroll
-      for (int p = 0; p < B; p++) out[row * B + p] = ADD_SELF ? self[p] + dl[p] : dl[p];
-      if (WRITE_R) {
-        const double *gp = diag + slice * (i64)(B * B) * 32 + lane;
+        for (int k = 0; k < PRE; k++) if (pc[k] >= 0) mylast = pc[k];
+        gate(mylast, 0);
+      }
+      double xk[PRE > 0 ? PRE : 1];
 #pragma unroll
-        for (int p = 0; p < B; p++) {
-          double s = acc[p];
+      for (int k = 0; k < PRE; k++) xk[k] = (pc[k] >= 0) ? ld_poll(out + pc[k]) : 0.0;
 #pragma unroll
-          for (int q = 0; q < B; q++) s = fma(-gp[(p * B + q) * 32], dl[q], s);
-          rout[row * B + p] = s;
+      for (int k = 0; k < PRE; k++) {
+        if (pc[k] >= 0) {
+          unsigned spins = 0;
+          while (is_sentinel(xk[k])) {
+            xk[k] = ld_poll(out + pc[k]);
+            if (++spins > (1u << 26)) { atomicExch(prm.err, 1); break; }
+          }
+          acc[0] = fma(-pv[k], xk[k], acc[0]);
         }
       }
     }
-    __syncthreads();  // all stores of the tile issued (and s_tile free for reuse)
-    if (threadIdx.x == 0) {
-      __threadfence();
-      red_release_add(done + lvl, 1);
+    for (int k0 = PRE; k0 < width; k0 += CH) {
+      i32 c[CH];
+      double xv[CH][B];
+#pragma unroll
+      for (int j = 0; j < CH; j++) {
+        c[j] = (k0 + j < width) ? cp[(i64)(k0 + j) * 32] : -1;
+        if (c[j] < cut) c[j] = -1;
+      }
+      double av[CH][B * B];   // the chunk's matrix blocks, loaded before the polls so their latency overlaps
+#pragma unroll
+      for (int j = 0; j < CH; j++)
+#pragma unroll
+        for (int e = 0; e < B * B; e++) av[j][e] = (k0 + j < width) ? vp[((i64)(k0 + j) * (B * B) + e) * 32] : 0.0;
+      {
+        i32 mylast = -1;
+#pragma unroll
+        for (int j = 0; j < CH; j++) if (c[j] >= 0) mylast = c[j];
+        gate(mylast, k0);
+      }
+#pragma unroll
+      for (int j = 0; j < CH; j++)
+        if (c[j] >= 0) {
+#pragma unroll
+          for (int q = 0; q < B; q++) xv[j][q] = ld_poll(out + (i64)c[j] * B + q);
+        }
+#pragma unroll
+      for (int j = 0; j < CH; j++)
+        if (c[j] >= 0) {
+#pragma unroll
+          for (int q = 0; q < B; q++) {
+            unsigned spins = 0;
+            while (is_sentinel(xv[j][q])) {
+              xv[j][q] = ld_poll(out + (i64)c[j] * B + q);
+              if (++spins > (1u << 26)) { atomicExch(prm.err, 1); break; }
+            }
+          }
+#pragma unroll
+          for (int p = 0; p < B; p++) {
+            double t = 0.0;
+#pragma unroll
+            for (int q = 0; q < B; q++) t = fma(av[j][p * B + q], xv[j][q], t);
+            acc[p] -= t;
+          }
+        }
+    }
+    double dl[B];
+    if (B == 1) dl[0] = di0 * acc[0];
+    else {
+#pragma unroll
+      for (int p = 0; p < B; p++) {
+        double t = 0.0;
+#pragma unroll
+        for (int q = 0; q < B; q++) t = fma(dp[(p * B + q) * 32], acc[q], t);
+        dl[p] = t;
+      }
+    }
+#pragma unroll
+    for (int p = 0; p < B; p++) __stcg(out + row * B + p, ADD_SELF ? sv[p] + dl[p] : dl[p]);
+    if (WRITE_R) {
+      const double *gp = diag + slice * (i64)(B * B) * 32 + lane;
+#pragma unroll
+      for (int p = 0; p < B; p++) {
+        double t = acc[p];
+#pragma unroll
+        for (int q = 0; q < B; q++) t = fma(-gp[(p * B + q) * 32], dl[q], t);
+        rout[row * B + p] = t;
+      }
     }
   }
 }
@@ -303,6 +407,43 @@ __global__ void k_layout_fill(i64 n, int bs, const i64 *__restrict__ rowptr, con
       for (int e = 0; e < bs; e++) val2[(k2 * bs + e) * 32 + lane] = src[e];
       k2++;
     }
+  }
+}
+
+// pass 4 (L and U only): order the entries of every row by the age of the dependency in the sweep that uses the part --
+// ascending row number for L (forward sweep), descending for U (backward sweep) -- so that the dependency published
+// LAST sits in the last valid slot and everything before it can be gathered while the sweep is still waiting for it.
+// In-place insertion sort over the slots of the row (rows are short; setup only).
+__global__ void k_sell_sort_rows(i64 nrows_pad, int bs, const i64 *__restrict__ sp, i32 *col, double *val, int descending)
+{
+  const i64 row = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+  if (row >= nrows_pad) return;
+  const i64 slice = row >> 5;
+  const int lane = row & 31;
+  const i64 base = sp[slice];
+  const int width = (int)(sp[slice + 1] - base);
+  i32 *cp = col + base * 32 + lane;
+  double *vp = val + base * (i64)bs * 32 + lane;
+  int len = 0;
+  while (len < width && cp[(i64)len * 32] >= 0) len++;
+  for (int a = 1; a < len; a++) {
+    const i32 ck = cp[(i64)a * 32];
+    int q = a;
+    while (q > 0) {
+      const i32 cq = cp[(i64)(q - 1) * 32];
+      const bool before = descending ? (cq < ck) : (cq > ck);   // entry q-1 must move behind the key
+      if (!before) break;
+      q--;
+    }
+    if (q == a) continue;
+    // rotate slots [q, a] right by one, element by element (values are planar with stride 32)
+    for (int e = 0; e < bs; e++) {
+      const double key = vp[((i64)a * bs + e) * 32];
+      for (int m = a; m > q; m--) vp[((i64)m * bs + e) * 32] = vp[((i64)(m - 1) * bs + e) * 32];
+      vp[((i64)q * bs + e) * 32] = key;
+    }
+    for (int m = a; m > q; m--) cp[(i64)m * 32] = cp[(i64)(m - 1) * 32];
+    cp[(i64)q * 32] = ck;
   }
 }
 

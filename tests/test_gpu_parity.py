@@ -81,12 +81,20 @@ def test_level_matrices_and_dof_maps(pois):
         assert_same_pattern(Ag, Ao)                      # bit-exact coarse sparsity patterns
         assert rel(Ag.val, Ao.val) < TOL_VALUES
         assert pc.GetNDof(l) == Ao.nrows and pc.GetBlockSize(l) == 1
-    # DOF maps: the prolongations the device hierarchy uses are the ones the host builder produced, bit for bit
+    # DOF maps: without the colour-major coarse renumbering the prolongations the device hierarchy uses are the ones the
+    # host builder produces, bit for bit; with it (default) they differ only by a renumbering of the coarse vertices.
     hp = host_hierarchy(A, p["free"], max_coarse=20)
-    assert len(hp) == len(prols)
-    for a, b in zip(hp, prols):
+    pc2 = ng.h1_scal(A, p["free"], ngs_amg_max_coarse_size=20, ngs_amg_b200_color_coarse=False)
+    prols2 = pc2.GetMap()
+    assert len(hp) == len(prols2) == len(prols)
+    for a, b in zip(hp, prols2):
         assert_same_pattern(a, b)
         assert np.array_equal(a.val, b.val)
+    assert np.array_equal(np.diff(hp[0].rowptr), np.diff(prols[0].rowptr))
+    assert np.array_equal(np.sort(np.bincount(hp[0].col)), np.sort(np.bincount(prols[0].col)))
+    for l in range(1, pc.GetNLevels() - 1):
+        # colour-major numbering: the Gauss-Seidel dependency depth of a coarse level is its number of colours
+        assert pc.level_info(l).gs_depth < 64 <= 10 * pc2.level_info(l).gs_depth + 64
 
 
 def test_spmv_levels(pois):
