@@ -19,7 +19,7 @@ if not diri:   # regularise the pure Neumann matrix
 A = ng.SparseMatrix(p["n"], p["n"], 1, 1, p["rowptr"], p["col"], val)
 print("dirichlet", diri)
 pc = ng.h1_scal(A, p["free"], **extra)
-for lvl in (0,):
-    for name in ("gs_tri_fwd", "gs_tri_bwd", "gs_tri_fwd_rhs", "gs_tri_bwd_res"):
+for lvl in [int(x) for x in os.environ.get('LEVELS', '0').split(',')]:
+    for name in os.environ.get("KERNELS", "gs_tri_fwd,gs_tri_bwd").split(","):
         ms, by = pc.ProfileKernel(name, level=lvl, reps=5)
         print(extra, lvl, name, "%.3f ms" % ms, "%.0f GB/s" % (by / ms / 1e6), "depth", pc.level_info(lvl).gs_depth)

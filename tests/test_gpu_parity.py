@@ -316,3 +316,30 @@ def test_elasticity_3d():
     cg.Solve(p["rhs"])
     _, ito, _ = amg.pcg(p["rhs"], tol=1e-6, maxsteps=100)
     assert cg.iterations == ito and ito < 40          # ceiling of tests/elasticity/mdim/simple/test_3d_lo.py:10
+
+
+def test_golden_fixtures_gpu():
+    """the committed golden vectors (tests/golden/make_golden.py): GPU RAP pattern bit-exact, V-cycle and PCG count equal"""
+    import os
+    gold = os.path.join(os.path.dirname(__file__), "golden")
+    g = np.load(os.path.join(gold, "poisson_n7.npz"))
+    n = int(g["n"])
+    A = ng.SparseMatrix(n, n, 1, 1, g["rowptr"], g["col"], g["val"])
+    P = ng.SparseMatrix(n, int(g["nc0"]), 1, 1, g["p0_rowptr"], g["p0_col"], g["p0_val"])
+    pc = ng.h1_scal(A, g["free"], prolongations=[P])
+    Ac = pc.GetLevelMatrix(1)
+    assert np.array_equal(Ac.rowptr, g["ac_rowptr"]) and np.array_equal(Ac.col, g["ac_col"])
+    assert rel(Ac.val, g["ac_val"]) < TOL_VALUES
+    assert rel(pc * g["b"], g["vcycle_x"]) < TOL_VCYCLE
+    cg = ng.CGSolver(mat=A, pre=pc, maxsteps=50, tol=1e-8)
+    cg.Solve(g["b"])
+    assert cg.iterations == int(g["pcg_iters"])
+    e = np.load(os.path.join(gold, "elast_5x3x3.npz"))
+    n = int(e["n"])
+    A = ng.SparseMatrix(n, n, 3, 3, e["rowptr"], e["col"], e["val"])
+    P = ng.SparseMatrix(n, int(e["nc0"]), 3, 6, e["p0_rowptr"], e["p0_col"], e["p0_val"])
+    pc = ng.elast_3d(A, e["free"], vertex_xyz=e["xyz"], prolongations=[P])
+    Ac = pc.GetLevelMatrix(1)
+    assert np.array_equal(Ac.rowptr, e["ac_rowptr"]) and np.array_equal(Ac.col, e["ac_col"])
+    assert rel(Ac.val, e["ac_val"]) < TOL_VALUES
+    assert rel(pc * e["b"], e["vcycle_x"]) < 1e-9

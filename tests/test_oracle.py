@@ -228,3 +228,15 @@ def test_golden_fixtures():
     assert rel(amg.apply(g["b"]), g["vcycle_x"]) < 1e-13
     u, it, errs = amg.pcg(g["b"], tol=1e-8, maxsteps=50)
     assert it == int(g["pcg_iters"])
+
+
+def test_golden_elasticity_fixture():
+    f = os.path.join(GOLD, "elast_5x3x3.npz")
+    g = np.load(f)
+    A = O.Bsr(int(g["n"]), int(g["n"]), 3, 3, g["rowptr"], g["col"], g["val"])
+    P = [O.Bsr(int(g["n"]), int(g["nc0"]), 3, 6, g["p0_rowptr"], g["p0_col"], g["p0_val"])]
+    amg = O.OracleAMG(A, g["free"], P, pinv=True)
+    Ac = amg.level_matrix(1)
+    assert Ac.bh == 6 and np.array_equal(Ac.rowptr, g["ac_rowptr"]) and np.array_equal(Ac.col, g["ac_col"])
+    assert rel(Ac.val, g["ac_val"]) < 1e-14
+    assert rel(amg.apply(g["b"]), g["vcycle_x"]) < 1e-12
