@@ -92,7 +92,8 @@ struct Amg {
   i64 launches = 0;
   double ms_apply = 0, ms_pcg = 0, ms_setup = 0, ms_rap = 0, ms_host = 0;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-  int tri_grid_cap[24] = {0};
+  int tri_grid_cap[32] = {0};
+  i64 tri_small_rows = 131072;
   int *d_err = nullptr;
   void check_watchdog();
 
@@ -170,8 +171,32 @@ void level_schedule(const HostBsr &A, const std::vector<uint8_t> &free_mask, boo
   L.depth = depth - shift;
   L.nonfree_pad = (shift == 0 && smoothed) ? round32(cnt[0]) : 0;
   L.perm.resize(n);
-  std::vector<i64> pos(start.begin(), start.end() - 1);
-  for (i64 i = 0; i < n; i++) L.perm[i] = (i32)(pos[lvl[i]]++);
+  if (!smoothed) {
+    std::vector<i64> pos(start.begin(), start.end() - 1);
+    for (i64 i = 0; i < n; i++) L.perm[i] = (i32)(pos[lvl[i]]++);
+  } else {
+    // Rows of one dependency level are mutually independent, so their order inside the level is free.  Group rows with the
+    // same (lower, upper) entry counts -- slices (32 consecutive rows) then have uniform widths: less SELL padding and all lanes
+    // of a warp reach their newest dependency in the same chunk -- and keep the original order inside a group (locality).
+    std::vector<uint64_t> key(n);
+    parallel_for(n, [&](i64 lo, i64 hi) {
+      for (i64 i = lo; i < hi; i++) {
+        unsigned nl = 0, nu = 0;
+        for (i64 k = A.rowptr[i]; k < A.rowptr[i + 1]; k++) {
+          const i32 j = A.col[k];
+          if (j == i) continue;
+          if (lvl[j] < lvl[i] || (lvl[j] == lvl[i] && j < i)) nl++; else nu++;
+        }
+        nl = std::min(nl, 1023u); nu = std::min(nu, 1023u);
+        key[i] = ((uint64_t)lvl[i] << 40) | ((uint64_t)nl << 30) | ((uint64_t)nu << 20);
+      }
+    });
+    std::vector<i32> order(n);
+    for (i64 i = 0; i < n; i++) order[i] = (i32)i;
+    std::stable_sort(order.begin(), order.end(), [&](i32 a, i32 b) { return key[a] < key[b]; });
+    std::vector<i64> pos(start.begin(), start.end() - 1);
+    for (i64 q = 0; q < n; q++) { const i32 i = order[q]; L.perm[i] = (i32)(pos[lvl[i]]++); }
+  }
   (void)st;
 }
 
@@ -307,11 +332,18 @@ void greedy_coloring_perm(const HostBsr &A, std::vector<i32> &perm, int &ncolors
     color[i] = c;
     ncolors = std::max(ncolors, c + 1);
   }
-  std::vector<i64> start(ncolors + 1, 0);
-  for (i64 i = 0; i < n; i++) start[color[i] + 1]++;
-  for (int c = 0; c < ncolors; c++) start[c + 1] += start[c];
+  // colour-major; inside a colour by the number of lower-coloured neighbours (uniform row lengths per slice), then by index
+  std::vector<uint64_t> key(n);
+  for (i64 i = 0; i < n; i++) {
+    unsigned low = 0, up = 0;
+    for (i64 k = A.rowptr[i]; k < A.rowptr[i + 1]; k++) { low += (color[A.col[k]] < color[i]); up += (color[A.col[k]] > color[i]); }
+    key[i] = ((uint64_t)color[i] << 40) | ((uint64_t)std::min(low, 1048575u) << 20) | std::min(up, 1048575u);
+  }
+  std::vector<i32> order(n);
+  for (i64 i = 0; i < n; i++) order[i] = (i32)i;
+  std::stable_sort(order.begin(), order.end(), [&](i32 a, i32 b) { return key[a] < key[b]; });
   perm.resize(n);
-  for (i64 i = 0; i < n; i++) perm[i] = (i32)(start[color[i]]++);
+  for (i64 q = 0; q < n; q++) perm[order[q]] = (i32)q;
 }
 
 // B = Pi A Pi^T (rows and columns renumbered old -> perm[old]), columns re-sorted ascending
@@ -707,6 +739,26 @@ void Amg::tri(Level &L, bool backward, bool add_self, bool write_r, const double
   const Sell &T = backward ? L.U : L.L;
   // sentinel-fill the output: a row is "published" once its entry is no longer the all-ones NaN
   NGB_CUDA(cudaMemsetAsync(out, 0xFF, sizeof(double) * L.npad * L.b, st));
+  if (L.npad <= tri_small_rows) {
+    // small level: warp-per-row variant (chain cost independent of the row width)
+    const int sidx = 24 + (B == 1 ? 0 : B == 2 ? 1 : B == 3 ? 2 : 3) * 2 + (add_self ? 1 : 0);
+    auto launch_small = [&](auto kern) {
+      if (!tri_grid_cap[sidx]) {
+        int occ = 0;
+        NGB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 256, 0));
+        tri_grid_cap[sidx] = std::max(1, occ) * num_sms;
+      }
+      const i64 want = (L.npad + 8 * 16 - 1) / (8 * 16);   // >= 16 rows per warp
+      const int grid = (int)std::max<i64>(1, std::min<i64>(want, tri_grid_cap[sidx]));
+      TriParams prm{L.npad / 32, backward ? 1 : 0, tri_sleep_ns, tri_prepoll, tri_gate_all, L.nonfree_pad, d_err};
+      kern<<<grid, 256, 0, st>>>(T.view(), L.diag, L.dinv, rin, self, out, rout, prm);
+    };
+    if (!add_self && !write_r) throw Error("tri: unsupported mode");
+    if (add_self) launch_small(k_gs_tri_small<B, true, false>);
+    else launch_small(k_gs_tri_small<B, false, true>);
+    launches += 2;
+    return;
+  }
   // register slot cache: smallest of 8/12/16 that covers (almost) all slices of this part
   const int pre = (B == 1) ? (backward ? L.pre_u : L.pre_l) : 0;
   const int idx = ((B == 1 ? 0 : B == 2 ? 1 : B == 3 ? 2 : 3) * 2 + (add_self ? 1 : 0)) * 3 + (pre == 16 ? 2 : pre == 12 ? 1 : 0);
@@ -1079,6 +1131,7 @@ int ngsamg_b200_create(const char *type, const ngsamg_csr *A, const uint8_t *fre
   a.tri_ctas_per_sm = (int)a.flags.num("b200_tri_ctas_per_sm", 0);
   a.tri_prepoll = (int)a.flags.num("b200_tri_prepoll", 1);
   a.tri_gate_all = (int)a.flags.num("b200_tri_gate_all", 1);
+  a.tri_small_rows = (i64)a.flags.num("b200_tri_small_rows", 131072);
   {
     int pm = (int)a.flags.num("b200_tri_pollmode", 0);
     NGB_CUDA(cudaMemcpyToSymbol(g_pollmode, &pm, sizeof(int)));

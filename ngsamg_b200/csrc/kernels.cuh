@@ -347,6 +347,90 @@ __global__ void __launch_bounds__(256) k_gs_tri(SellView T, const double *__rest
 }
 
 // ------------------------------------------------------------------------------------------------
+// K4-like variant of the triangular half-sweep for SMALL levels (coarse levels, wide rows, few rows per dependency level):
+// one WARP per row, the lanes split the row's entries, a fixed shuffle tree sums the partial products (deterministic).
+// The chain then costs one L2 poll + one warp reduction per dependency level, independent of the row width.
+// Same sync-free protocol as k_gs_tri (sentinel-filled output, rows dealt round-robin in sweep order).
+// ------------------------------------------------------------------------------------------------
+template <int B, bool ADD_SELF, bool WRITE_R>
+__global__ void __launch_bounds__(256) k_gs_tri_small(SellView T, const double *__restrict__ diag, const double *__restrict__ dinv,
+                                                     const double *rin, const double *__restrict__ self, double *out, double *rout,
+                                                     TriParams prm)
+{
+  const int lane = threadIdx.x & 31;
+  const i64 gw = ((i64)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const i64 nw = ((i64)gridDim.x * blockDim.x) >> 5;
+  const i64 nrows = prm.nslices * 32;
+  for (i64 r = gw; r < nrows; r += nw) {
+    const i64 row = prm.backward ? (nrows - 1 - r) : r;
+    const i64 slice = row >> 5;
+    const int lr = (int)(row & 31);
+    const i64 base = T.slice_ptr[slice];
+    const int width = (int)(T.slice_ptr[slice + 1] - base);
+    const i32 cut = (row < prm.nonfree) ? (i32)prm.nonfree : 0;
+    double acc[B];
+#pragma unroll
+    for (int p = 0; p < B; p++) acc[p] = 0.0;
+    for (int k = lane; k < width; k += 32) {
+      const i32 c = T.col[(base + k) * 32 + lr];
+      if (c < cut) continue;
+      double a[B * B];
+#pragma unroll
+      for (int e = 0; e < B * B; e++) a[e] = T.val[((base + k) * (i64)(B * B) + e) * 32 + lr];
+      double xv[B];
+#pragma unroll
+      for (int q = 0; q < B; q++) {
+        double v = ld_poll(out + (i64)c * B + q);
+        unsigned spins = 0;
+        while (is_sentinel(v)) {
+          if (prm.sleep_ns) __nanosleep(prm.sleep_ns);
+          v = ld_poll(out + (i64)c * B + q);
+          if (++spins > (1u << 26)) { atomicExch(prm.err, 1); break; }
+        }
+        xv[q] = v;
+      }
+#pragma unroll
+      for (int p = 0; p < B; p++) {
+        double t = 0.0;
+#pragma unroll
+        for (int q = 0; q < B; q++) t = fma(a[p * B + q], xv[q], t);
+        acc[p] -= t;
+      }
+    }
+    __syncwarp();
+#pragma unroll
+    for (int p = 0; p < B; p++)
+#pragma unroll
+      for (int o = 16; o; o >>= 1) acc[p] += __shfl_xor_sync(0xffffffffu, acc[p], o);
+    if (lane == 0) {
+#pragma unroll
+      for (int p = 0; p < B; p++) acc[p] += rin[row * B + p];
+      const double *dp = dinv + slice * (i64)(B * B) * 32 + lr;
+      double dl[B];
+#pragma unroll
+      for (int p = 0; p < B; p++) {
+        double t = 0.0;
+#pragma unroll
+        for (int q = 0; q < B; q++) t = fma(dp[(p * B + q) * 32], acc[q], t);
+        dl[p] = t;
+      }
+#pragma unroll
+      for (int p = 0; p < B; p++) __stcg(out + row * B + p, ADD_SELF ? self[row * B + p] + dl[p] : dl[p]);
+      if (WRITE_R) {
+        const double *gp = diag + slice * (i64)(B * B) * 32 + lr;
+#pragma unroll
+        for (int p = 0; p < B; p++) {
+          double t = acc[p];
+#pragma unroll
+          for (int q = 0; q < B; q++) t = fma(-gp[(p * B + q) * 32], dl[q], t);
+          rout[row * B + p] = t;
+        }
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // layout construction (K15): plain CSR (original numbering) -> permuted SELL-32 split L / D / U
 // ------------------------------------------------------------------------------------------------
 // pass 1: per permuted row, number of entries going to S1 (lower, or everything if !SPLIT) and S2 (upper)
