@@ -117,6 +117,9 @@ int ngsamg_b200_get_level_matrix(ngsamg_b200_t *h, int level, int64_t *rowptr, i
 int ngsamg_b200_get_prolongation(ngsamg_b200_t *h, int level, int64_t *rowptr, int32_t *col, double *val);
 /* level work vectors after the last apply: which = 0 x_level, 1 rhs_level, 2 res_level (amg_matrix.cpp:19-26) */
 int ngsamg_b200_get_level_vector(ngsamg_b200_t *h, int level, int which, double *out);
+/* position of every row of `level` in the Gauss-Seidel sweep: rank[i] == i (the reference's order, gssmoother.cpp:195-315)
+ * unless the optional multicolour smoother was requested for the fine level (flag ngs_amg_b200_sm_order=multicolor). */
+int ngsamg_b200_get_sweep_order(ngsamg_b200_t *h, int level, int32_t *rank);
 /* operator complexity sum_l nnz_l*b_l^2 / (nnz_0*b_0^2) (AMGMatrix::GetOC) */
 double ngsamg_b200_operator_complexity(ngsamg_b200_t *h);
 /* algorithmic bytes of one V(1,1)-cycle, SURVEY.md §8d formula B_V, from the actual level sizes */

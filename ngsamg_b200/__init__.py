@@ -259,6 +259,12 @@ class Preconditioner:
         _lib.check(self._lib.ngsamg_b200_get_level_vector(self._h, int(level), {"x": 0, "rhs": 1, "res": 2}[which], _lib.ptr(out)))
         return out
 
+    def GetSweepOrder(self, level=0):
+        """rank of every row in the Gauss-Seidel sweep of `level` (identity = the reference's natural order)"""
+        out = np.zeros(self.level_info(level).n, np.int32)
+        _lib.check(self._lib.ngsamg_b200_get_sweep_order(self._h, int(level), _lib.ptr(out)))
+        return out
+
     def VCycleBytes(self):
         return float(self._lib.ngsamg_b200_vcycle_bytes(self._h))
 

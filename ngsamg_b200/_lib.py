@@ -22,6 +22,7 @@ EXPORTS = [
     "ngsamg_b200_vcycle_bytes", "ngsamg_b200_last_ms", "ngsamg_b200_launch_count", "ngsamg_b200_rap_begin",
     "ngsamg_b200_matmul_begin", "ngsamg_b200_transpose_begin", "ngsamg_b200_spm_fetch",
     "ngsamg_b200_coarsen_begin", "ngsamg_b200_coarsen_fetch", "ngsamg_b200_profile_kernel",
+    "ngsamg_b200_get_sweep_order",
 ]
 
 
@@ -92,6 +93,7 @@ def lib():
     L.ngsamg_b200_coarsen_begin.argtypes = [C.POINTER(Csr), vp, vp, ci, ci, dbl, dbl, ci, ci, C.POINTER(vp), C.POINTER(i64),
                                             C.POINTER(i64)]
     L.ngsamg_b200_coarsen_fetch.argtypes = [vp, vp, vp, vp, vp, vp]
+    L.ngsamg_b200_get_sweep_order.argtypes = [vp, ci, vp]
     L.ngsamg_b200_profile_kernel.argtypes = [vp, ci, ci, ci, C.POINTER(dbl), C.POINTER(dbl)]
     _lib = L
     return L

@@ -40,6 +40,7 @@ struct Level {
   bool keep_host = true;
   std::vector<uint8_t> free_mask;  // empty = all free
   std::vector<i32> perm;           // original -> level-scheduled (padded) row
+  std::vector<i32> sweep_rank;     // position of each row in the Gauss-Seidel sweep; empty = the row number (reference order)
   i32 *d_perm = nullptr;
   uint8_t *d_freep = nullptr;
   Sell L, U;
@@ -48,6 +49,7 @@ struct Level {
   int depth = 0;        // number of dependency levels (length of the critical path of a sweep)
   i64 nonfree_pad = 0;  // rows of dependency level 0 (non-free rows), padded
   int pre_l = 8, pre_u = 8;  // register slot cache of the triangular sweeps (scalar matrices)
+  std::vector<i64> level_start;  // first (padded) row of every dependency level, plus npad
   // transfer to level+1
   HostBsr hP;
   Sell P, PT;
@@ -94,6 +96,9 @@ struct Amg {
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   int tri_grid_cap[32] = {0};
   i64 tri_small_rows = 131072;
+  int tri_level_launch_depth = 24;
+  double tri_gate_gap_levels = 0.0;
+  unsigned tri_repoll_ns = 0;
   int *d_err = nullptr;
   void check_watchdog();
 
@@ -146,14 +151,21 @@ void level_schedule(const HostBsr &A, const std::vector<uint8_t> &free_mask, boo
   const i64 n = A.nrows;
   std::vector<i32> lvl(n, 0);
   i32 depth = 1;
+  const bool hf = !free_mask.empty();
+  // sweep order: the reference's (row number) unless a multicolour order was requested for this level
+  const bool natural = L.sweep_rank.empty();
+  auto before = [&](i32 j, i32 i) { return natural ? (j < i) : (L.sweep_rank[j] < L.sweep_rank[i]); };
   if (smoothed) {
-    const bool hf = !free_mask.empty();
-    for (i64 i = 0; i < n; i++) {
+    std::vector<i32> inv;
+    if (!natural) { inv.resize(n); for (i64 i = 0; i < n; i++) inv[L.sweep_rank[i]] = (i32)i; }
+    for (i64 q = 0; q < n; q++) {
+      const i64 i = natural ? q : inv[q];
       if (hf && !free_mask[i]) { lvl[i] = 0; continue; }
       i32 m = 0;
       for (i64 k = A.rowptr[i]; k < A.rowptr[i + 1]; k++) {
         const i32 j = A.col[k];
-        if (j >= i) break;  // columns ascending
+        if (natural && j >= i) break;  // columns ascending
+        if (j == i || !before(j, (i32)i)) continue;
         if (hf && !free_mask[j]) continue;
         m = std::max(m, lvl[j]);
       }
@@ -170,6 +182,7 @@ void level_schedule(const HostBsr &A, const std::vector<uint8_t> &free_mask, boo
   L.npad = std::max<i64>(start[depth], 32);
   L.depth = depth - shift;
   L.nonfree_pad = (shift == 0 && smoothed) ? round32(cnt[0]) : 0;
+  L.level_start.assign(start.begin() + shift, start.end());
   L.perm.resize(n);
   if (!smoothed) {
     std::vector<i64> pos(start.begin(), start.end() - 1);
@@ -178,24 +191,32 @@ void level_schedule(const HostBsr &A, const std::vector<uint8_t> &free_mask, boo
     // Rows of one dependency level are mutually independent, so their order inside the level is free.  Group rows with the
     // same (lower, upper) entry counts -- slices (32 consecutive rows) then have uniform widths: less SELL padding and all lanes
     // of a warp reach their newest dependency in the same chunk -- and keep the original order inside a group (locality).
-    std::vector<uint64_t> key(n);
+    // Counting sort on (level, lower count, upper count); stable in the row number.
+    const int W = depth > 256 ? 32 : 128;
+    std::vector<i32> sub(n);
     parallel_for(n, [&](i64 lo, i64 hi) {
       for (i64 i = lo; i < hi; i++) {
-        unsigned nl = 0, nu = 0;
+        int nl = 0, nu = 0;
         for (i64 k = A.rowptr[i]; k < A.rowptr[i + 1]; k++) {
           const i32 j = A.col[k];
           if (j == i) continue;
-          if (lvl[j] < lvl[i] || (lvl[j] == lvl[i] && j < i)) nl++; else nu++;
+          if (lvl[j] < lvl[i] || (lvl[j] == lvl[i] && before(j, (i32)i))) nl++; else nu++;
         }
-        nl = std::min(nl, 1023u); nu = std::min(nu, 1023u);
-        key[i] = ((uint64_t)lvl[i] << 40) | ((uint64_t)nl << 30) | ((uint64_t)nu << 20);
+        sub[i] = std::min(nl, W - 1) * W + std::min(nu, W - 1);
       }
     });
-    std::vector<i32> order(n);
-    for (i64 i = 0; i < n; i++) order[i] = (i32)i;
-    std::stable_sort(order.begin(), order.end(), [&](i32 a, i32 b) { return key[a] < key[b]; });
-    std::vector<i64> pos(start.begin(), start.end() - 1);
-    for (i64 q = 0; q < n; q++) { const i32 i = order[q]; L.perm[i] = (i32)(pos[lvl[i]]++); }
+    const i64 nb = (i64)depth * W * W;
+    std::vector<i64> bstart(nb + 1, 0);
+    for (i64 i = 0; i < n; i++) bstart[(i64)lvl[i] * W * W + sub[i] + 1]++;
+    // bucket offsets: levels start at their padded positions, buckets inside a level are contiguous
+    {
+      i64 run = 0;
+      for (int l = 0; l < depth; l++) {
+        run = start[l];
+        for (i64 b = (i64)l * W * W; b < (i64)(l + 1) * W * W; b++) { const i64 c = bstart[b + 1]; bstart[b + 1] = 0; bstart[b] = run; run += c; }
+      }
+    }
+    for (i64 i = 0; i < n; i++) L.perm[i] = (i32)(bstart[(i64)lvl[i] * W * W + sub[i]]++);
   }
   (void)st;
 }
@@ -703,6 +724,12 @@ void Amg::finalize()
     }
     {
       auto h0 = std::chrono::steady_clock::now();
+      if (!coarsest && l == 0 && flags.str("b200_sm_order", "natural") == "multicolor") {
+        // OPTIONAL multicolour Gauss-Seidel on the fine level: sweep in colour-major order instead of the caller's numbering
+        // (a different smoother than the reference's natural-order sweep; reported separately)
+        int ncol = 0;
+        greedy_coloring_perm(L.hA, L.sweep_rank, ncol);
+      }
       level_schedule(L.hA, L.free_mask, !coarsest, L, st);
       L.d_err = d_err;
       host_s += std::chrono::duration<double>(std::chrono::steady_clock::now() - h0).count();
@@ -739,6 +766,20 @@ void Amg::tri(Level &L, bool backward, bool add_self, bool write_r, const double
   const Sell &T = backward ? L.U : L.L;
   // sentinel-fill the output: a row is "published" once its entry is no longer the all-ones NaN
   NGB_CUDA(cudaMemsetAsync(out, 0xFF, sizeof(double) * L.npad * L.b, st));
+  if (L.depth <= tri_level_launch_depth && L.npad > tri_small_rows && (int)L.level_start.size() == L.depth + 1) {
+    // shallow dependency DAG with many rows per level: one plain launch per level (cached gathers, no polling)
+    if (!add_self && !write_r) throw Error("tri: unsupported mode");
+    if (!add_self && L.nonfree_pad) NGB_CUDA(cudaMemsetAsync(out, 0, sizeof(double) * L.nonfree_pad * L.b, st));
+    for (int q = 0; q < L.depth; q++) {
+      const int lv = backward ? L.depth - 1 - q : q;
+      const i64 r0 = L.level_start[lv], r1 = L.level_start[lv + 1];
+      if (r1 <= r0) continue;
+      if (add_self) k_gs_level<B, true, false><<<nblk(r1 - r0), TB, 0, st>>>(T.view(), L.diag, L.dinv, rin, self, out, rout, r0, r1, L.nonfree_pad);
+      else k_gs_level<B, false, true><<<nblk(r1 - r0), TB, 0, st>>>(T.view(), L.diag, L.dinv, rin, self, out, rout, r0, r1, L.nonfree_pad);
+      launches++;
+    }
+    return;
+  }
   if (L.npad <= tri_small_rows) {
     // small level: warp-per-row variant (chain cost independent of the row width)
     const int sidx = 24 + (B == 1 ? 0 : B == 2 ? 1 : B == 3 ? 2 : 3) * 2 + (add_self ? 1 : 0);
@@ -750,7 +791,7 @@ void Amg::tri(Level &L, bool backward, bool add_self, bool write_r, const double
       }
       const i64 want = (L.npad + 8 * 16 - 1) / (8 * 16);   // >= 16 rows per warp
       const int grid = (int)std::max<i64>(1, std::min<i64>(want, tri_grid_cap[sidx]));
-      TriParams prm{L.npad / 32, backward ? 1 : 0, tri_sleep_ns, tri_prepoll, tri_gate_all, L.nonfree_pad, d_err};
+      TriParams prm{L.npad / 32, backward ? 1 : 0, tri_sleep_ns, tri_prepoll, tri_gate_all, 0, 0u, L.nonfree_pad, d_err};
       kern<<<grid, 256, 0, st>>>(T.view(), L.diag, L.dinv, rin, self, out, rout, prm);
     };
     if (!add_self && !write_r) throw Error("tri: unsupported mode");
@@ -772,7 +813,8 @@ void Amg::tri(Level &L, bool backward, bool add_self, bool write_r, const double
     }
     const i64 nslices = L.npad / 32;
     const int grid = (int)std::min<i64>((nslices + 7) / 8, tri_grid_cap[idx]);
-    TriParams prm{nslices, backward ? 1 : 0, tri_sleep_ns, tri_prepoll, tri_gate_all, L.nonfree_pad, d_err};
+    const i64 gap = tri_gate_gap_levels > 0 ? (i64)(tri_gate_gap_levels * (double)L.npad / std::max(1, L.depth)) : 0;
+    TriParams prm{nslices, backward ? 1 : 0, tri_sleep_ns, tri_prepoll, tri_gate_all, gap, tri_repoll_ns, L.nonfree_pad, d_err};
     kern<<<grid, 256, 0, st>>>(T.view(), L.diag, L.dinv, rin, self, out, rout, prm);
   };
   if (!add_self && !write_r) throw Error("tri: unsupported mode");
@@ -1132,6 +1174,9 @@ int ngsamg_b200_create(const char *type, const ngsamg_csr *A, const uint8_t *fre
   a.tri_prepoll = (int)a.flags.num("b200_tri_prepoll", 1);
   a.tri_gate_all = (int)a.flags.num("b200_tri_gate_all", 1);
   a.tri_small_rows = (i64)a.flags.num("b200_tri_small_rows", 131072);
+  a.tri_gate_gap_levels = a.flags.num("b200_tri_gate_gap", 0.0);
+  a.tri_level_launch_depth = (int)a.flags.num("b200_tri_level_launch_depth", 24);
+  a.tri_repoll_ns = (unsigned)a.flags.num("b200_tri_repoll_ns", 0);
   {
     int pm = (int)a.flags.num("b200_tri_pollmode", 0);
     NGB_CUDA(cudaMemcpyToSymbol(g_pollmode, &pm, sizeof(int)));
@@ -1441,6 +1486,16 @@ int ngsamg_b200_get_level_vector(ngsamg_b200_t *h, int level, int which, double 
   a.ensure_io(n);
   k_permute_out<<<nblk(L.n), TB, 0, a.st>>>(L.n, L.b, L.d_perm, src, a.io_b, 1.0, 0);
   a.from_device(out, a.io_b, n);
+  NGB_CATCH
+}
+
+int ngsamg_b200_get_sweep_order(ngsamg_b200_t *h, int level, int32_t *rank)
+{
+  NGB_TRY
+  Amg &a = ready(h);
+  Level &L = get_level(a, level);
+  if (!rank) throw Error("null output");
+  for (i64 i = 0; i < L.n; i++) rank[i] = L.sweep_rank.empty() ? (i32)i : L.sweep_rank[i];
   NGB_CATCH
 }
 

@@ -173,6 +173,8 @@ struct TriParams {
   unsigned sleep_ns;  // back-off of the single-address pre-poll
   int prepoll;        // 1: gate on the latest dependency with one polling lane before the gather
   int gate_all;       // 1: gate every chunk on its newest entry, 0: only the last chunk of the row
+  i64 gate_gap;       // > 0: early gate (see k_gs_tri), in rows
+  unsigned repoll_ns; // back-off of the per-lane straggler polls
   i64 nonfree;        // rows [0, nonfree) are the non-free rows (dependency level 0)
   int *err;           // watchdog flag (set if a wait exceeds ~2^26 polls; never in a healthy run)
 };
@@ -234,7 +236,11 @@ __global__ void __launch_bounds__(256) k_gs_tri(SellView T, const double *__rest
     // together and a straggler is simply re-polled.  Old chunks pass their gate at once, so a wide row is gathered
     // while the sweep is still waiting for the row's newest dependencies, without hammering L2 during the wait.
     const int last0 = (width <= PRE) ? 0 : PRE + ((width - PRE - 1) / CH) * CH;   // first slot of the last chunk
-    auto gate = [&](i32 mylast, int k0) {
+    // gate(mylast, k0, pick): one lane polls (with back-off) a single entry before the chunk's polls are issued.
+    // gate_gap == 0: the entry is the warp's newest dependency of the chunk.  gate_gap > 0 ("early gate"): the newest entry
+    // that is at least gate_gap rows older than that one, i.e. about one dependency level older; the chunk's own polls then
+    // spin (per lane) for the last hop, which removes one L2 round trip from the dependency chain.
+    auto gate = [&](i32 mylast, int k0, auto pick) {
       if (!prm.prepoll || (!prm.gate_all && k0 != last0)) return;
       i32 f = (mylast >= cut && (mylast >> 5) != slice) ? mylast : -1;
       if (prm.backward) { if (f < 0) f = 0x7fffffff; }
@@ -244,6 +250,17 @@ __global__ void __launch_bounds__(256) k_gs_tri(SellView T, const double *__rest
         f = prm.backward ? min(f, g) : max(f, g);
       }
       if (prm.backward && f == 0x7fffffff) f = -1;
+      if (f >= 0 && prm.gate_gap > 0) {
+        i32 e = pick(f);
+        if (prm.backward) { if (e < 0) e = 0x7fffffff; }
+#pragma unroll
+        for (int o = 16; o; o >>= 1) {
+          const i32 g = __shfl_xor_sync(0xffffffffu, e, o);
+          e = prm.backward ? min(e, g) : max(e, g);
+        }
+        if (prm.backward && e == 0x7fffffff) e = -1;
+        if (e >= 0) f = e;
+      }
       if (f >= 0 && lane == 0) {
         unsigned spins = 0;
         while (is_sentinel(ld_poll(out + (i64)f * B))) {
@@ -253,12 +270,21 @@ __global__ void __launch_bounds__(256) k_gs_tri(SellView T, const double *__rest
       }
       __syncwarp();
     };
+    // is entry c at least gate_gap rows older than the warp's newest dependency f ?
+    auto old_enough = [&](i32 c, i32 f) {
+      return c >= cut && (prm.backward ? ((i64)c >= (i64)f + prm.gate_gap) : ((i64)c <= (i64)f - prm.gate_gap));
+    };
     if (PRE > 0) {
       {
         i32 mylast = -1;
 #pragma unroll
         for (int k = 0; k < PRE; k++) if (pc[k] >= 0) mylast = pc[k];
-        gate(mylast, 0);
+        gate(mylast, 0, [&](i32 f) {
+          i32 e = -1;
+#pragma unroll
+          for (int k = 0; k < PRE; k++) if (old_enough(pc[k], f)) e = pc[k];   // sorted by age: the last hit is the newest
+          return e;
+        });
       }
       double xk[PRE > 0 ? PRE : 1];
 #pragma unroll
@@ -268,6 +294,7 @@ __global__ void __launch_bounds__(256) k_gs_tri(SellView T, const double *__rest
         if (pc[k] >= 0) {
           unsigned spins = 0;
           while (is_sentinel(xk[k])) {
+            if (prm.repoll_ns) __nanosleep(prm.repoll_ns);
             xk[k] = ld_poll(out + pc[k]);
             if (++spins > (1u << 26)) { atomicExch(prm.err, 1); break; }
           }
@@ -292,7 +319,12 @@ __global__ void __launch_bounds__(256) k_gs_tri(SellView T, const double *__rest
         i32 mylast = -1;
 #pragma unroll
         for (int j = 0; j < CH; j++) if (c[j] >= 0) mylast = c[j];
-        gate(mylast, k0);
+        gate(mylast, k0, [&](i32 f) {
+          i32 e = -1;
+#pragma unroll
+          for (int j = 0; j < CH; j++) if (old_enough(c[j], f)) e = c[j];
+          return e;
+        });
       }
 #pragma unroll
       for (int j = 0; j < CH; j++)
@@ -307,6 +339,7 @@ __global__ void __launch_bounds__(256) k_gs_tri(SellView T, const double *__rest
           for (int q = 0; q < B; q++) {
             unsigned spins = 0;
             while (is_sentinel(xv[j][q])) {
+              if (prm.repoll_ns) __nanosleep(prm.repoll_ns);
               xv[j][q] = ld_poll(out + (i64)c[j] * B + q);
               if (++spins > (1u << 26)) { atomicExch(prm.err, 1); break; }
             }
@@ -342,6 +375,54 @@ __global__ void __launch_bounds__(256) k_gs_tri(SellView T, const double *__rest
         for (int q = 0; q < B; q++) t = fma(-gp[(p * B + q) * 32], dl[q], t);
         rout[row * B + p] = t;
       }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Level-by-level variant of the triangular half-sweep for SHALLOW dependency DAGs (a handful of colours, many rows per
+// colour): one launch per dependency level over the rows [row0, row1) of that level; plain cached gathers, no polling.
+// Used when the depth is small enough that ~depth launches cost less than the polling traffic of the sync-free sweep.
+// ------------------------------------------------------------------------------------------------
+template <int B, bool ADD_SELF, bool WRITE_R>
+__global__ void __launch_bounds__(256) k_gs_level(SellView T, const double *__restrict__ diag, const double *__restrict__ dinv,
+                                                 const double *rin, const double *__restrict__ self, double *out, double *rout,
+                                                 i64 row0, i64 row1, i64 nonfree)
+{
+  const i64 row = row0 + (i64)blockIdx.x * blockDim.x + threadIdx.x;
+  if (row >= row1) return;
+  if (ADD_SELF && row < nonfree) {
+    // non-free rows are never updated (dinv = 0); their couplings to other non-free rows of the same launch must not be read
+#pragma unroll
+    for (int p = 0; p < B; p++) out[row * B + p] = self[row * B + p];
+    return;
+  }
+  const i64 slice = row >> 5;
+  const int lane = (int)(row & 31);
+  double acc[B];
+#pragma unroll
+  for (int p = 0; p < B; p++) acc[p] = rin[row * B + p];
+  if (B == 1) acc[0] -= sell_row_dot1<false>(T, slice, lane, out);
+  else sell_row_mac<B, B, false>(T, slice, lane, out, acc, -1.0);
+  const double *dp = dinv + slice * (i64)(B * B) * 32 + lane;
+  double dl[B];
+#pragma unroll
+  for (int p = 0; p < B; p++) {
+    double t = 0.0;
+#pragma unroll
+    for (int q = 0; q < B; q++) t = fma(dp[(p * B + q) * 32], acc[q], t);
+    dl[p] = t;
+  }
+#pragma unroll
+  for (int p = 0; p < B; p++) out[row * B + p] = ADD_SELF ? self[row * B + p] + dl[p] : dl[p];
+  if (WRITE_R) {
+    const double *gp = diag + slice * (i64)(B * B) * 32 + lane;
+#pragma unroll
+    for (int p = 0; p < B; p++) {
+      double t = acc[p];
+#pragma unroll
+      for (int q = 0; q < B; q++) t = fma(-gp[(p * B + q) * 32], dl[q], t);
+      rout[row * B + p] = t;
     }
   }
 }

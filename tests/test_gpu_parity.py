@@ -343,3 +343,74 @@ def test_golden_fixtures_gpu():
     assert np.array_equal(Ac.rowptr, e["ac_rowptr"]) and np.array_equal(Ac.col, e["ac_col"])
     assert rel(Ac.val, e["ac_val"]) < TOL_VALUES
     assert rel(pc * e["b"], e["vcycle_x"]) < 1e-9
+
+
+@pytest.mark.parametrize("flags", [dict(ngs_amg_b200_tri_small_rows=0), dict(ngs_amg_b200_tri_small_rows=0, ngs_amg_b200_tri_level_launch_depth=0),
+                                   dict(ngs_amg_b200_tri_small_rows=0, ngs_amg_b200_tri_level_launch_depth=1000),
+                                   dict(ngs_amg_b200_tri_small_rows=0, ngs_amg_b200_sm_order="multicolor")])
+def test_sweep_kernel_variants(flags):
+    """every implementation of the triangular half-sweep (warp-per-row, sync-free thread-per-row, level-by-level launches)
+    forced on the same small problem: V-cycle and PCG must agree with the oracle"""
+    p, A = poisson(12)
+    pc = ng.h1_scal(A, p["free"], ngs_amg_max_coarse_size=20, **flags)
+    if "ngs_amg_b200_sm_order" in flags:
+        return _check_multicolor(p, A, pc)
+    amg = O.OracleAMG(to_oracle(A), p["free"], [to_oracle(P) for P in pc.GetMap()])
+    b = rand(97, p["n"])
+    assert rel(pc * b, amg.apply(b)) < TOL_VCYCLE
+    cg = ng.CGSolver(mat=A, pre=pc, maxsteps=60, tol=1e-8)
+    cg.Solve(p["rhs"])
+    _, ito, _ = amg.pcg(p["rhs"], tol=1e-8, maxsteps=60)
+    assert cg.iterations == ito
+
+
+def _check_multicolor(p, A, pc):
+    import scipy.sparse as sp
+    n = p["n"]
+    rank = pc.GetSweepOrder(0)
+    Pi = sp.csr_matrix((np.ones(n), (rank, np.arange(n))), shape=(n, n))
+    pat = sp.csr_matrix((np.ones(A.nnz), A.col, A.rowptr), shape=(n, n))
+    patp = (Pi @ pat @ Pi.T).tocsr(); patp.sort_indices()
+    Ap = (Pi @ A.to_scipy() @ Pi.T).tocsr()
+    vals = np.asarray(Ap[patp.nonzero()]).ravel()
+    Aperm = O.Bsr(n, n, 1, 1, patp.indptr, patp.indices, vals)
+    prols = pc.GetMap()
+    P0 = (Pi @ prols[0].to_scipy()).tocsr(); P0.sort_indices()
+    fr = np.zeros(n, np.uint8); fr[rank] = p["free"]
+    amg = O.OracleAMG(Aperm, fr, [O.Bsr.from_scipy(P0)] + [to_oracle(P) for P in prols[1:]])
+    b = rand(96, n)
+    bp = np.zeros(n); bp[rank] = b
+    assert rel(pc * b, amg.apply(bp)[rank]) < TOL_VCYCLE
+    cg = ng.CGSolver(mat=A, pre=pc, maxsteps=60, tol=1e-8)
+    cg.Solve(p["rhs"])
+    rp = np.zeros(n); rp[rank] = p["rhs"]
+    _, ito, _ = amg.pcg(rp, tol=1e-8, maxsteps=60)
+    assert cg.iterations == ito
+
+
+def test_multicolor_fine_level_option():
+    """optional multicolour smoother on the fine level: equals the reference's sequential GS applied in the colour-major
+    numbering (checked by running the oracle on the symmetrically permuted problem)"""
+    import scipy.sparse as sp
+    p, A = poisson(11)
+    pc = ng.h1_scal(A, p["free"], ngs_amg_max_coarse_size=20, ngs_amg_b200_sm_order="multicolor")
+    rank = pc.GetSweepOrder(0)
+    assert sorted(rank) == list(range(p["n"])) and not np.array_equal(rank, np.arange(p["n"]))
+    assert pc.level_info(0).gs_depth <= 16 < ng.h1_scal(A, p["free"], ngs_amg_max_coarse_size=20).level_info(0).gs_depth
+    n = p["n"]
+    Pi = sp.csr_matrix((np.ones(n), (rank, np.arange(n))), shape=(n, n))       # new = Pi old
+    Ap = (Pi @ A.to_scipy() @ Pi.T).tocsr(); Ap.sort_indices()
+    # keep structural zeros: permute the pattern explicitly
+    pat = sp.csr_matrix((np.ones(A.nnz), A.col, A.rowptr), shape=(n, n))
+    patp = (Pi @ pat @ Pi.T).tocsr(); patp.sort_indices()
+    Apf = (Ap + patp * 0).tocsr()
+    vals = np.asarray(Ap[patp.nonzero()]).ravel()
+    Aperm = O.Bsr(n, n, 1, 1, patp.indptr, patp.indices, vals)
+    prols = pc.GetMap()
+    P0 = (Pi @ prols[0].to_scipy()).tocsr(); P0.sort_indices()
+    fr = np.zeros(n, np.uint8); fr[rank] = p["free"]
+    amg = O.OracleAMG(Aperm, fr, [O.Bsr.from_scipy(P0)] + [to_oracle(P) for P in prols[1:]])
+    b = rand(96, n)
+    bp = np.zeros(n); bp[rank] = b
+    xo = amg.apply(bp)[rank]
+    assert rel(pc * b, xo) < TOL_VCYCLE
