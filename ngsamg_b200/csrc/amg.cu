@@ -95,7 +95,7 @@ struct Amg {
   double ms_apply = 0, ms_pcg = 0, ms_setup = 0, ms_rap = 0, ms_host = 0;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   int tri_grid_cap[32] = {0};
-  i64 tri_small_rows = 131072;
+  i64 tri_small_rows = 1000000;
   int tri_level_launch_depth = 24;
   double tri_gate_gap_levels = 0.0;
   unsigned tri_repoll_ns = 0;
@@ -1173,7 +1173,7 @@ int ngsamg_b200_create(const char *type, const ngsamg_csr *A, const uint8_t *fre
   a.tri_ctas_per_sm = (int)a.flags.num("b200_tri_ctas_per_sm", 0);
   a.tri_prepoll = (int)a.flags.num("b200_tri_prepoll", 1);
   a.tri_gate_all = (int)a.flags.num("b200_tri_gate_all", 1);
-  a.tri_small_rows = (i64)a.flags.num("b200_tri_small_rows", 131072);
+  a.tri_small_rows = (i64)a.flags.num("b200_tri_small_rows", 1000000);
   a.tri_gate_gap_levels = a.flags.num("b200_tri_gate_gap", 0.0);
   a.tri_level_launch_depth = (int)a.flags.num("b200_tri_level_launch_depth", 24);
   a.tri_repoll_ns = (unsigned)a.flags.num("b200_tri_repoll_ns", 0);

@@ -127,3 +127,32 @@ print("ok", dist.get_rank())
     procs = [subprocess.Popen([sys.executable, "-c", code, str(r)], stdout=subprocess.PIPE, stderr=subprocess.STDOUT) for r in range(2)]
     outs = [p.communicate(timeout=120)[0].decode() for p in procs]
     assert all(p.returncode == 0 for p in procs), outs
+
+
+def _build_cpp_test(tmp_path):
+    import subprocess
+    exe = os.path.join(str(tmp_path), "test_hpp")
+    libdir = os.path.dirname(_lib.LIB_PATH)
+    subprocess.check_call(["g++", "-std=c++17", "-O1", "-I", os.path.join(ROOT, "include"), os.path.join(ROOT, "tests", "cpp", "test_hpp.cpp"),
+                           "-o", exe, "-L", libdir, "-lngsamg_b200", "-Wl,-rpath," + libdir])
+    return exe
+
+
+@pytest.mark.skipif(_has_gpu(), reason="checks the no-device failure mode of the C++ host mirror")
+def test_cpp_host_mirror_compiles_and_fails_loudly(tmp_path):
+    """include/ngsamg_b200.hpp (C++ mirror of BaseAMGPC / CGSolver / RestrictMatrix) links against the C ABI; without a
+    device it raises amg::Exception("no CUDA device ...") -> exit code 3"""
+    import subprocess
+    exe = _build_cpp_test(tmp_path)
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 3, (r.returncode, r.stdout, r.stderr)
+    assert "no CUDA device" in r.stdout
+
+
+@pytest.mark.gpu
+def test_cpp_host_mirror_on_gpu(tmp_path):
+    import subprocess
+    exe = _build_cpp_test(tmp_path)
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, (r.returncode, r.stdout, r.stderr)
+    assert "rap_pattern_same=1" in r.stdout
