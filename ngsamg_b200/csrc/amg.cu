@@ -43,7 +43,7 @@ struct Level {
   std::vector<i32> sweep_rank;     // position of each row in the Gauss-Seidel sweep; empty = the row number (reference order)
   i32 *d_perm = nullptr;
   uint8_t *d_freep = nullptr;
-  Sell L, U;
+  Sell L, U, N;   // strictly lower / strictly upper / free-row couplings to non-free rows
   double *diag = nullptr, *dinv = nullptr;
   // Gauss-Seidel dependency structure
   int depth = 0;        // number of dependency levels (length of the critical path of a sweep)
@@ -200,6 +200,7 @@ void level_schedule(const HostBsr &A, const std::vector<uint8_t> &free_mask, boo
         for (i64 k = A.rowptr[i]; k < A.rowptr[i + 1]; k++) {
           const i32 j = A.col[k];
           if (j == i) continue;
+          if (hf && free_mask[i] && !free_mask[j]) continue;   // stored in the separate N part
           if (lvl[j] < lvl[i] || (lvl[j] == lvl[i] && before(j, (i32)i))) nl++; else nu++;
         }
         sub[i] = std::min(nl, W - 1) * W + std::min(nu, W - 1);
@@ -428,7 +429,7 @@ Amg::~Amg()
   for (auto &lp : lev) {
     Level &L = *lp;
     dev_free(L.d_perm); dev_free(L.d_freep);
-    L.L.release(); L.U.release(); L.P.release(); L.PT.release();
+    L.L.release(); L.U.release(); L.N.release(); L.P.release(); L.PT.release();
     dev_free(L.diag); dev_free(L.dinv);
     dev_free(L.x); dev_free(L.y); dev_free(L.rhs); dev_free(L.res); dev_free(L.tmp); dev_free(L.wa); dev_free(L.wb);
   }
@@ -467,14 +468,20 @@ void Amg::build_level_layout(Level &L, const DevCsr &dA)
   i32 *len1 = dev_alloc<i32>(L.npad), *len2 = dev_alloc<i32>(L.npad);
   NGB_CUDA(cudaMemsetAsync(len1, 0, sizeof(i32) * L.npad, st));
   NGB_CUDA(cudaMemsetAsync(len2, 0, sizeof(i32) * L.npad, st));
-  k_layout_count<<<nblk(n), TB, 0, st>>>(n, dA.rowptr, dA.col, L.d_perm, L.d_perm, 1, len1, len2);
+  const bool has_n = L.nonfree_pad > 0;
+  i32 *len3 = has_n ? dev_alloc<i32>(L.npad) : nullptr;
+  if (has_n) NGB_CUDA(cudaMemsetAsync(len3, 0, sizeof(i32) * L.npad, st));
+  k_layout_count<<<nblk(n), TB, 0, st>>>(n, dA.rowptr, dA.col, L.d_perm, L.d_perm, 1, len1, len2, (i32)L.nonfree_pad, len3);
   build_sell(L.npad, b, b, len1, L.L, st, &launches);
   build_sell(L.npad, b, b, len2, L.U, st, &launches);
+  if (has_n) build_sell(L.npad, b, b, len3, L.N, st, &launches);
   L.diag = dev_alloc<double>((size_t)L.npad * bs);
   L.dinv = dev_alloc<double>((size_t)L.npad * bs);
   NGB_CUDA(cudaMemsetAsync(L.diag, 0, sizeof(double) * L.npad * bs, st));
   k_layout_fill<<<nblk(n), TB, 0, st>>>(n, bs, dA.rowptr, dA.col, dA.val, L.d_perm, L.d_perm, 1, L.L.slice_ptr, L.L.col, L.L.val,
-                                        L.U.slice_ptr, L.U.col, L.U.val, L.diag);
+                                        L.U.slice_ptr, L.U.col, L.U.val, L.diag, (i32)L.nonfree_pad, has_n ? L.N.slice_ptr : nullptr,
+                                        L.N.col, L.N.val);
+  dev_free(len3);
   {
     const int flip = (int)flags.num("b200_sort_flip", 0);
     if (flip < 2) {
@@ -564,20 +571,20 @@ void Amg::build_transfer_layout(Level &F, Level &C)
   {
     i32 *len = dev_alloc<i32>(F.npad);
     NGB_CUDA(cudaMemsetAsync(len, 0, sizeof(i32) * F.npad, st));
-    k_layout_count<<<nblk(F.n), TB, 0, st>>>(F.n, dP.rowptr, dP.col, F.d_perm, C.d_perm, 0, len, nullptr);
+    k_layout_count<<<nblk(F.n), TB, 0, st>>>(F.n, dP.rowptr, dP.col, F.d_perm, C.d_perm, 0, len, nullptr, 0, nullptr);
     build_sell(F.npad, F.b, F.bc, len, F.P, st, &launches);
     k_layout_fill<<<nblk(F.n), TB, 0, st>>>(F.n, F.b * F.bc, dP.rowptr, dP.col, dP.val, F.d_perm, C.d_perm, 0, F.P.slice_ptr, F.P.col,
-                                            F.P.val, nullptr, nullptr, nullptr, nullptr);
+                                            F.P.val, nullptr, nullptr, nullptr, nullptr, 0, nullptr, nullptr, nullptr);
     F.P.nnz = dP.nnz;
     dev_free(len);
   }
   {
     i32 *len = dev_alloc<i32>(C.npad);
     NGB_CUDA(cudaMemsetAsync(len, 0, sizeof(i32) * C.npad, st));
-    k_layout_count<<<nblk(C.n), TB, 0, st>>>(C.n, dPT.rowptr, dPT.col, C.d_perm, F.d_perm, 0, len, nullptr);
+    k_layout_count<<<nblk(C.n), TB, 0, st>>>(C.n, dPT.rowptr, dPT.col, C.d_perm, F.d_perm, 0, len, nullptr, 0, nullptr);
     build_sell(C.npad, F.bc, F.b, len, F.PT, st, &launches);
     k_layout_fill<<<nblk(C.n), TB, 0, st>>>(C.n, F.b * F.bc, dPT.rowptr, dPT.col, dPT.val, C.d_perm, F.d_perm, 0, F.PT.slice_ptr,
-                                            F.PT.col, F.PT.val, nullptr, nullptr, nullptr, nullptr);
+                                            F.PT.col, F.PT.val, nullptr, nullptr, nullptr, nullptr, 0, nullptr, nullptr, nullptr);
     F.PT.nnz = dPT.nnz;
     dev_free(len);
   }
@@ -841,9 +848,11 @@ void Amg::tri_dispatch(Level &L, bool backward, bool add_self, bool write_r, con
 
 template <int BH, int BW, bool S2, bool D>
 static void launch_spmv(cudaStream_t st, i64 npad, const Sell &a, const Sell *b, const double *diag, const double *v, const double *y_in,
-                        double *y_out, double alpha, double beta, double *xadd)
+                        double *y_out, double alpha, double beta, double *xadd, const Sell *nfp = nullptr)
 {
-  k_sell_spmv<BH, BW, S2, D><<<nblk(npad), TB, 0, st>>>(npad, a.view(), b ? b->view() : a.view(), diag, v, y_in, y_out, alpha, beta, xadd);
+  const SellView none{nullptr, nullptr, nullptr};
+  k_sell_spmv<BH, BW, S2, D><<<nblk(npad), TB, 0, st>>>(npad, a.view(), b ? b->view() : a.view(), diag, v, y_in, y_out, alpha, beta, xadd,
+                                                       (nfp && nfp->slice_ptr) ? nfp->view() : none);
 }
 
 void Amg::spmv_part(Level &L, int which, const double *v, const double *y_in, double *y_out, double alpha, double beta, double *xadd)
@@ -851,8 +860,8 @@ void Amg::spmv_part(Level &L, int which, const double *v, const double *y_in, do
   const Sell &A1 = (which == 1 || which == 3) ? L.U : L.L;
   const bool s2 = (which == 4), d = (which >= 2);
 #define NGB_SPMV(B)                                                                                                     \
-  if (s2) launch_spmv<B, B, true, true>(st, L.npad, L.L, &L.U, L.diag, v, y_in, y_out, alpha, beta, xadd);             \
-  else if (d) launch_spmv<B, B, false, true>(st, L.npad, A1, nullptr, L.diag, v, y_in, y_out, alpha, beta, xadd);       \
+  if (s2) launch_spmv<B, B, true, true>(st, L.npad, L.L, &L.U, L.diag, v, y_in, y_out, alpha, beta, xadd, &L.N);       \
+  else if (d) launch_spmv<B, B, false, true>(st, L.npad, A1, nullptr, L.diag, v, y_in, y_out, alpha, beta, xadd, &L.N); \
   else launch_spmv<B, B, false, false>(st, L.npad, A1, nullptr, L.diag, v, y_in, y_out, alpha, beta, xadd);
   switch (L.b) {
     case 1: NGB_SPMV(1) break;

@@ -101,7 +101,7 @@ __device__ __forceinline__ double sell_row_dot1(const SellView &S, i64 slice, in
 template <int BH, int BW, bool HAS_S2, bool HAS_D>
 __global__ void __launch_bounds__(256) k_sell_spmv(i64 nrows_pad, SellView S1, SellView S2, const double *__restrict__ diag,
                                                   const double *__restrict__ v, const double *y_in, double *y_out,
-                                                  double alpha, double beta, double *xadd)
+                                                  double alpha, double beta, double *xadd, SellView S3)
 {
   const i64 row = (i64)blockIdx.x * blockDim.x + threadIdx.x;
   if (row >= nrows_pad) return;
@@ -116,6 +116,10 @@ __global__ void __launch_bounds__(256) k_sell_spmv(i64 nrows_pad, SellView S1, S
   } else {
     sell_row_mac<BH, BW, false>(S1, slice, lane, v, acc, 1.0);
     if (HAS_S2) sell_row_mac<BH, BW, false>(S2, slice, lane, v, acc, 1.0);
+  }
+  if (HAS_D && S3.slice_ptr) {   // couplings to non-free rows travel with the diagonal (see k_layout_count)
+    if (BH == 1 && BW == 1) acc[0] += sell_row_dot1<false>(S3, slice, lane, v);
+    else sell_row_mac<BH, BW, false>(S3, slice, lane, v, acc, 1.0);
   }
   if (HAS_D || xadd) {
     double vi[BW];
@@ -516,21 +520,27 @@ __global__ void __launch_bounds__(256) k_gs_tri_small(SellView T, const double *
 // ------------------------------------------------------------------------------------------------
 // pass 1: per permuted row, number of entries going to S1 (lower, or everything if !SPLIT) and S2 (upper)
 __global__ void k_layout_count(i64 n, const i64 *__restrict__ rowptr, const i32 *__restrict__ col,
-                               const i32 *__restrict__ rperm, const i32 *__restrict__ cperm, int split, i32 *len1, i32 *len2)
+                               const i32 *__restrict__ rperm, const i32 *__restrict__ cperm, int split, i32 *len1, i32 *len2,
+                               i32 nonfree, i32 *len3)
 {
+  // split: S1 = strictly lower, S2 = strictly upper, S3 = couplings of a free row to non-free rows (rows [0,nonfree) of the
+  // level-scheduled numbering).  Non-free values never change during a sweep, so S3 is applied with the parallel half.
   const i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const i32 pi = rperm[i];
-  int n1 = 0, n2 = 0;
+  int n1 = 0, n2 = 0, n3 = 0;
   for (i64 k = rowptr[i]; k < rowptr[i + 1]; k++) {
     const i32 c = col[k];
     if (split) {
       if (c == i) continue;
-      if (cperm[c] < pi) n1++; else n2++;
+      const i32 pc = cperm[c];
+      if (pi >= nonfree && pc < nonfree) n3++;
+      else if (pc < pi) n1++;
+      else n2++;
     } else n1++;
   }
   len1[pi] = n1;
-  if (split) len2[pi] = n2;
+  if (split) { len2[pi] = n2; if (len3) len3[pi] = n3; }
 }
 
 // pass 2: slice width = max row length in the slice (one warp per slice)
@@ -547,14 +557,14 @@ __global__ void k_layout_width(i64 nslices, const i32 *__restrict__ len, i64 *wi
 __global__ void k_layout_fill(i64 n, int bs, const i64 *__restrict__ rowptr, const i32 *__restrict__ col,
                               const double *__restrict__ val, const i32 *__restrict__ rperm, const i32 *__restrict__ cperm,
                               int split, const i64 *__restrict__ sp1, i32 *col1, double *val1, const i64 *__restrict__ sp2,
-                              i32 *col2, double *val2, double *diag)
+                              i32 *col2, double *val2, double *diag, i32 nonfree, const i64 *__restrict__ sp3, i32 *col3, double *val3)
 {
   const i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const i32 pi = rperm[i];
   const i64 slice = pi >> 5;
   const int lane = pi & 31;
-  i64 k1 = sp1[slice], k2 = split ? sp2[slice] : 0;
+  i64 k1 = sp1[slice], k2 = split ? sp2[slice] : 0, k3 = (split && sp3) ? sp3[slice] : 0;
   for (i64 k = rowptr[i]; k < rowptr[i + 1]; k++) {
     const i32 c = col[k];
     const double *src = val + k * bs;
@@ -563,7 +573,11 @@ __global__ void k_layout_fill(i64 n, int bs, const i64 *__restrict__ rowptr, con
       continue;
     }
     const i32 pc = cperm[c];
-    if (!split || pc < pi) {
+    if (split && sp3 && pi >= nonfree && pc < nonfree) {
+      col3[k3 * 32 + lane] = pc;
+      for (int e = 0; e < bs; e++) val3[(k3 * bs + e) * 32 + lane] = src[e];
+      k3++;
+    } else if (!split || pc < pi) {
       col1[k1 * 32 + lane] = pc;
       for (int e = 0; e < bs; e++) val1[(k1 * bs + e) * 32 + lane] = src[e];
       k1++;
