@@ -53,6 +53,7 @@ struct Level {
   // transfer to level+1
   HostBsr hP;
   Sell P, PT;
+  i32 *d_pt_rowmap = nullptr;  // PT is stored with its rows sorted by length: storage row -> coarse (level-scheduled) row
   i64 nc = 0;
   int bc = 1;
   // work vectors, level-scheduled numbering, npad*b doubles
@@ -117,7 +118,7 @@ struct Amg {
   int tri_ctas_per_sm = 0;
   void spmv_part(Level &L, int which /*0 L,1 U,2 L+D,3 U+D,4 full*/, const double *v, const double *y_in, double *y_out,
                  double alpha, double beta, double *xadd);
-  void transfer(const Sell &S, const double *v, const double *y_in, double *y_out, double alpha, double beta);
+  void transfer(const Sell &S, const double *v, const double *y_in, double *y_out, double alpha, double beta, const i32 *rowmap = nullptr);
   void calc_residuum(Level &L, const double *x, const double *b, double *res, bool x_zero);
   void gs_res(Level &L, bool backward, double *x, double *res, bool x_zero);
   void gs_rhs(Level &L, bool backward, const double *x, const double *b, double *xout);
@@ -428,7 +429,7 @@ Amg::~Amg()
   if (device >= 0) cudaSetDevice(device);
   for (auto &lp : lev) {
     Level &L = *lp;
-    dev_free(L.d_perm); dev_free(L.d_freep);
+    dev_free(L.d_perm); dev_free(L.d_freep); dev_free(L.d_pt_rowmap);
     L.L.release(); L.U.release(); L.N.release(); L.P.release(); L.PT.release();
     dev_free(L.diag); dev_free(L.dinv);
     dev_free(L.x); dev_free(L.y); dev_free(L.rhs); dev_free(L.res); dev_free(L.tmp); dev_free(L.wa); dev_free(L.wb);
@@ -579,14 +580,36 @@ void Amg::build_transfer_layout(Level &F, Level &C)
     dev_free(len);
   }
   {
-    i32 *len = dev_alloc<i32>(C.npad);
-    NGB_CUDA(cudaMemsetAsync(len, 0, sizeof(i32) * C.npad, st));
-    k_layout_count<<<nblk(C.n), TB, 0, st>>>(C.n, dPT.rowptr, dPT.col, C.d_perm, F.d_perm, 0, len, nullptr, 0, nullptr);
-    build_sell(C.npad, F.bc, F.b, len, F.PT, st, &launches);
-    k_layout_fill<<<nblk(C.n), TB, 0, st>>>(C.n, F.b * F.bc, dPT.rowptr, dPT.col, dPT.val, C.d_perm, F.d_perm, 0, F.PT.slice_ptr,
+    // restriction matrix: rows stored sorted by length (uniform slices => little SELL padding); the kernel scatters its result
+    // through rowmap.  Counting sort on the row length, stable in the coarse (level-scheduled) row number.
+    const i64 npt = round32(C.n);
+    std::vector<i32> order(C.n), inv(C.npad, -1);
+    for (i64 c = 0; c < C.n; c++) inv[C.perm[c]] = (i32)c;
+    i64 maxlen = 0;
+    for (i64 c = 0; c < C.n; c++) maxlen = std::max<i64>(maxlen, PT.rowptr[c + 1] - PT.rowptr[c]);
+    std::vector<i64> bucket(maxlen + 2, 0);
+    for (i64 c = 0; c < C.n; c++) bucket[PT.rowptr[c + 1] - PT.rowptr[c] + 1]++;
+    for (i64 l = 0; l <= maxlen; l++) bucket[l + 1] += bucket[l];
+    std::vector<i32> spos(C.n), rowmap(npt, -1);
+    for (i64 pc = 0; pc < C.npad; pc++) {
+      const i32 c = inv[pc];
+      if (c < 0) continue;
+      const i64 s = bucket[PT.rowptr[c + 1] - PT.rowptr[c]]++;
+      spos[c] = (i32)s;
+      rowmap[s] = (i32)pc;
+    }
+    i32 *d_spos = upload_vec(spos, st);
+    F.d_pt_rowmap = upload_vec(rowmap, st);
+    i32 *len = dev_alloc<i32>(npt);
+    NGB_CUDA(cudaMemsetAsync(len, 0, sizeof(i32) * npt, st));
+    k_layout_count<<<nblk(C.n), TB, 0, st>>>(C.n, dPT.rowptr, dPT.col, d_spos, F.d_perm, 0, len, nullptr, 0, nullptr);
+    build_sell(npt, F.bc, F.b, len, F.PT, st, &launches);
+    k_layout_fill<<<nblk(C.n), TB, 0, st>>>(C.n, F.b * F.bc, dPT.rowptr, dPT.col, dPT.val, d_spos, F.d_perm, 0, F.PT.slice_ptr,
                                             F.PT.col, F.PT.val, nullptr, nullptr, nullptr, nullptr, 0, nullptr, nullptr, nullptr);
     F.PT.nnz = dPT.nnz;
+    NGB_CUDA(cudaStreamSynchronize(st));
     dev_free(len);
+    dev_free(d_spos);
   }
   launches += 4;
   NGB_CUDA(cudaStreamSynchronize(st));
@@ -848,11 +871,11 @@ void Amg::tri_dispatch(Level &L, bool backward, bool add_self, bool write_r, con
 
 template <int BH, int BW, bool S2, bool D>
 static void launch_spmv(cudaStream_t st, i64 npad, const Sell &a, const Sell *b, const double *diag, const double *v, const double *y_in,
-                        double *y_out, double alpha, double beta, double *xadd, const Sell *nfp = nullptr)
+                        double *y_out, double alpha, double beta, double *xadd, const Sell *nfp = nullptr, const i32 *rowmap = nullptr)
 {
   const SellView none{nullptr, nullptr, nullptr};
   k_sell_spmv<BH, BW, S2, D><<<nblk(npad), TB, 0, st>>>(npad, a.view(), b ? b->view() : a.view(), diag, v, y_in, y_out, alpha, beta, xadd,
-                                                       (nfp && nfp->slice_ptr) ? nfp->view() : none);
+                                                       (nfp && nfp->slice_ptr) ? nfp->view() : none, rowmap);
 }
 
 void Amg::spmv_part(Level &L, int which, const double *v, const double *y_in, double *y_out, double alpha, double beta, double *xadd)
@@ -874,10 +897,10 @@ void Amg::spmv_part(Level &L, int which, const double *v, const double *y_in, do
   launches++;
 }
 
-void Amg::transfer(const Sell &S, const double *v, const double *y_in, double *y_out, double alpha, double beta)
+void Amg::transfer(const Sell &S, const double *v, const double *y_in, double *y_out, double alpha, double beta, const i32 *rowmap)
 {
   const int key = S.bh * 10 + S.bw;
-#define NGB_TR(H, W) launch_spmv<H, W, false, false>(st, S.nrows_pad, S, nullptr, nullptr, v, y_in, y_out, alpha, beta, nullptr)
+#define NGB_TR(H, W) launch_spmv<H, W, false, false>(st, S.nrows_pad, S, nullptr, nullptr, v, y_in, y_out, alpha, beta, nullptr, nullptr, rowmap)
   switch (key) {
     case 11: NGB_TR(1, 1); break;
     case 22: NGB_TR(2, 2); break;
@@ -980,7 +1003,7 @@ void Amg::vcycle_record()
       level_smooth(L, L.x, L.rhs, L.res, true, true, true, false);
     }
     // TransferF2C: rhs_{l+1} = P^T res_l     (:212, dof_map.cpp:633-654)
-    transfer(L.PT, L.res, nullptr, C.rhs, 1.0, 0.0);
+    transfer(L.PT, L.res, nullptr, C.rhs, 1.0, 0.0, L.d_pt_rowmap);
   }
   {
     Level &L = *lev[NL - 1];
@@ -1353,7 +1376,7 @@ int ngsamg_b200_restrict(ngsamg_b200_t *h, int level, const double *xf, double *
   a.ensure_io(std::max(nf, nc));
   const double *xd = a.to_device(xf, nf, a.io_a);
   k_permute_in<<<nblk(F.n), TB, 0, a.st>>>(F.n, F.b, F.d_perm, xd, F.res);
-  a.transfer(F.PT, F.res, nullptr, C.rhs, 1.0, 0.0);
+  a.transfer(F.PT, F.res, nullptr, C.rhs, 1.0, 0.0, F.d_pt_rowmap);
   k_permute_out<<<nblk(C.n), TB, 0, a.st>>>(C.n, C.b, C.d_perm, C.rhs, a.io_b, 1.0, 0);
   a.from_device(xc, a.io_b, nc);
   a.launches += 2;
@@ -1649,7 +1672,7 @@ int ngsamg_b200_profile_kernel(ngsamg_b200_t *h, int level, int which, int reps,
       case 2: a.spmv_part(L, 2, L.x, L.rhs, L.tmp, -1.0, 1.0, nullptr); B = L.L.nnz * bb + D + 3 * v; break;
       case 3: a.tri_dispatch(L, true, true, false, L.tmp, L.x, L.y, nullptr); B = L.U.nnz * bb + D + 3 * v; break;
       case 4: ensure_scratch(a, L); a.spmv_part(L, 4, L.x, nullptr, L.wa, 1.0, 0.0, nullptr); B = (L.L.nnz + L.U.nnz) * bb + D + 2 * v; break;
-      case 5: a.transfer(L.PT, L.res, nullptr, C.rhs, 1.0, 0.0); B = pb + v + vc; break;
+      case 5: a.transfer(L.PT, L.res, nullptr, C.rhs, 1.0, 0.0, L.d_pt_rowmap); B = pb + v + vc; break;
       case 6: a.transfer(L.P, C.x, L.x, L.x, 1.0, 1.0); B = pb + 2 * v + vc; break;
       case 7: a.tri_dispatch(L, false, true, false, L.tmp, L.x, L.y, nullptr); B = L.L.nnz * bb + D + 3 * v; break;   // forward, RHS form
       case 8: a.tri_dispatch(L, true, false, true, L.rhs, nullptr, L.x, L.res); B = L.U.nnz * bb + 2 * D + 3 * v; break;  // backward, RES form

@@ -101,8 +101,9 @@ __device__ __forceinline__ double sell_row_dot1(const SellView &S, i64 slice, in
 template <int BH, int BW, bool HAS_S2, bool HAS_D>
 __global__ void __launch_bounds__(256) k_sell_spmv(i64 nrows_pad, SellView S1, SellView S2, const double *__restrict__ diag,
                                                   const double *__restrict__ v, const double *y_in, double *y_out,
-                                                  double alpha, double beta, double *xadd, SellView S3)
+                                                  double alpha, double beta, double *xadd, SellView S3, const i32 *__restrict__ rowmap)
 {
+  // rowmap (restriction only): the SELL rows are stored sorted by length; rowmap[row] is the output row (-1 = padding)
   const i64 row = (i64)blockIdx.x * blockDim.x + threadIdx.x;
   if (row >= nrows_pad) return;
   const i64 slice = row >> 5;
@@ -137,11 +138,13 @@ __global__ void __launch_bounds__(256) k_sell_spmv(i64 nrows_pad, SellView S1, S
       for (int q = 0; q < BW; q++) xadd[row * BW + q] += vi[q];
     }
   }
+  i64 orow = row;
+  if (rowmap) { orow = rowmap[row]; if (orow < 0) return; }
 #pragma unroll
   for (int p = 0; p < BH; p++) {
     double y = alpha * acc[p];
-    if (beta != 0.0) y = fma(beta, y_in[row * BH + p], y);
-    y_out[row * BH + p] = y;
+    if (beta != 0.0) y = fma(beta, y_in[orow * BH + p], y);
+    y_out[orow * BH + p] = y;
   }
 }
 
