@@ -167,6 +167,7 @@ def main():
     ap.add_argument("--n", type=int, default=int(os.environ.get("NGSAMG_BENCH_N", DEFAULT_N)))
     ap.add_argument("--cpu-n", type=int, default=int(os.environ.get("NGSAMG_BENCH_CPU_N", CPU_SAMPLE_N)))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-multicolor", action="store_true", help="skip the separately reported multicolour-smoother variant")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
@@ -266,14 +267,48 @@ def main():
             row[name] = round(ms, 4)
         by_level.append(row)
     dom = max(("gs_tri_fwd", "gs_tri_bwd", "gs_upass", "gs_lpass"), key=lambda k: kern[k]["ms"])
+    traffic = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as f:
+            tj = json.load(f)
+        if tj.get("n") == n:
+            traffic = tj.get(dom)
+    except Exception:
+        pass
     roof = {"bound": "hbm", "kernel": "k_gs_tri (%s, level 0)" % dom, "achieved": kern[dom]["gbs"], "peak": peak,
-            "unit": "GB/s", "frac": kern[dom]["gbs"] / peak, "traffic": None, "peak_source": peak_src,
+            "unit": "GB/s", "frac": kern[dom]["gbs"] / peak, "traffic": traffic, "peak_source": peak_src,
             "ms_per_launch": kern[dom]["ms"], "algorithmic_bytes": kern[dom]["bytes"]}
 
     levels = []
     for l in range(pc.GetNLevels()):
         i = pc.level_info(l)
         levels.append({"n": int(i.n), "nnz": int(i.nnz), "gs_depth": int(i.gs_depth)})
+
+    # ---- optional variant, reported separately: multicolour Gauss-Seidel on the fine level ------------------------------
+    variant = None
+    if world == 1 and not args.no_multicolor and "ngs_amg_b200_sm_order" not in extra:
+        del cg
+        t0 = time.time()
+        pcm = ng.h1_scal(A, p["free"], device=local_rank, ngs_amg_b200_sm_order="multicolor", **extra)
+        cgm = ng.CGSolver(mat=A, pre=pcm, maxsteps=200, tol=TOL)
+        setup_m = time.time() - t0
+        for _ in range(2):
+            cgm.Solve(rhs_d, x_d)
+        ms = 0.0
+        for _ in range(args.steps):
+            cgm.Solve(rhs_d, x_d)
+            ms += pcm.LastMs("pcg")
+        vm = []
+        for _ in range(10):
+            pcm.Mult(rhs_d, x_d)
+            vm.append(pcm.LastMs("apply"))
+        vb = pcm.VCycleBytes()
+        variant = {"smoother": "multicolour Gauss-Seidel on the fine level (ngs_amg_b200_sm_order=multicolor); NOT the reference's "
+                               "natural-order sweep", "solve_s": ms / 1e3 / args.steps, "iterations": cgm.iterations,
+                   "dofs_per_s": ndof / (ms / 1e3 / args.steps), "vcycle_ms": float(np.mean(vm)), "vcycle_gbs": vb / np.mean(vm) / 1e6,
+                   "vcycle_frac_of_peak": vb / np.mean(vm) / 1e6 / peak, "gs_depth_level0": int(pcm.level_info(0).gs_depth),
+                   "setup_s": setup_m}
+        del pcm, cgm
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -295,7 +330,7 @@ def main():
             "setup_host_ms": pc.LastMs("host"), "gen_s": gen_s, "wall_s_timed_region": wall_s,
             "vcycle_ms": vcycle_ms, "vcycle_bytes": vbytes, "vcycle_gbs": vbytes / vcycle_ms / 1e6,
             "vcycle_frac_of_peak": vbytes / vcycle_ms / 1e6 / peak,
-            "kernels_level0": kern, "kernel_ms_by_level": by_level, "roofline": roof, "cpu_baseline": cpu,
+            "kernels_level0": kern, "kernel_ms_by_level": by_level, "roofline": roof, "variant_multicolor": variant, "cpu_baseline": cpu,
             "e2e": {"value": world * ndof / e2e_s, "unit": "DOF/s", "h2d_bytes_per_step": 8 * ndof, "d2h_bytes_per_step": 8 * ndof,
                     "solve_s": e2e_s},
             "gpu_launches": int(launches), "clocks": clocks, "flags": extra,

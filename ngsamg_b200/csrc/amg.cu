@@ -657,6 +657,8 @@ void Amg::finalize()
   if (finalized) throw Error("finalize called twice");
   auto t0 = std::chrono::steady_clock::now();
   double host_s = 0, rap_ms = 0;
+  const bool verbose = flags.str("log_level", "none") != "none";   // factory log levels, base_factory.cpp:83-199
+  auto tick = [](std::chrono::steady_clock::time_point t) { return std::chrono::duration<double>(std::chrono::steady_clock::now() - t).count(); };
   const int max_levels = (int)flags.num("max_levels", 10);            // base_factory.hpp:88-152
   const i64 max_coarse = (i64)flags.num("max_coarse_size", 50);
   const std::string cycle = flags.str("mg_cycle", "V");
@@ -699,7 +701,8 @@ void Amg::finalize()
           lev.push_back(std::move(nl));
         }
       }
-      host_s += std::chrono::duration<double>(std::chrono::steady_clock::now() - h0).count();
+      host_s += tick(h0);
+      if (verbose) std::fprintf(stderr, "[ngsamg_b200] level %d: n=%lld nnz=%lld  prolongation %.2f s (nc=%lld)\n", l, (long long)L.n, (long long)L.nnz, tick(h0), (long long)L.hP.ncols);
     }
     // smoother options for this level (SpecOpt semantics)
     {
@@ -749,7 +752,8 @@ void Amg::finalize()
         }
         dev_csr_free(dAc);
         dev_csr_upload(lev[l + 1]->hA, dAc, st);
-        host_s += std::chrono::duration<double>(std::chrono::steady_clock::now() - h0).count();
+        host_s += tick(h0);
+        if (verbose) std::fprintf(stderr, "[ngsamg_b200] level %d: colouring + renumbering of the coarse level %.2f s (%d colours)\n", l, tick(h0), ncol);
       }
     }
     {
@@ -762,7 +766,8 @@ void Amg::finalize()
       }
       level_schedule(L.hA, L.free_mask, !coarsest, L, st);
       L.d_err = d_err;
-      host_s += std::chrono::duration<double>(std::chrono::steady_clock::now() - h0).count();
+      host_s += tick(h0);
+      if (verbose) std::fprintf(stderr, "[ngsamg_b200] level %d: level schedule %.2f s (depth %d)\n", l, tick(h0), L.depth);
     }
     if (!coarsest) build_level_layout(L, dA);
     else {

@@ -14,6 +14,7 @@
 // It does NOT claim bit-exact agreement with the reference's aggregates.  Users who need the
 // reference's own DOF maps inject them with ngsamg_b200_set_prolongations().
 #include "common.hpp"
+#include <chrono>
 
 namespace ngb {
 
@@ -307,8 +308,17 @@ void build_prolongation(const HostBsr &A, const uint8_t *free_mask, int bc, cons
   const int bf = A.bh;
   std::vector<uint8_t> drop(n, 0);
   if (free_mask) for (i64 i = 0; i < n; i++) drop[i] = free_mask[i] ? 0 : 1;
+  const bool timing = std::getenv("NGSAMG_B200_TIMING") != nullptr;
+  auto t_last = std::chrono::steady_clock::now();
+  auto lap = [&](const char *what) {
+    if (!timing) return;
+    auto now = std::chrono::steady_clock::now();
+    std::fprintf(stderr, "[coarsen] %-28s %.3f s\n", what, std::chrono::duration<double>(now - t_last).count());
+    t_last = now;
+  };
   Graph G0;
   graph_from_matrix(A, drop, G0);
+  lap("graph_from_matrix");
   // isolated vertices are not aggregated (spw_agg_impl.hpp:1599-1614)
   for (i64 i = 0; i < n; i++)
     if (!drop[i] && G0.ptr[i + 1] == G0.ptr[i]) drop[i] = 1;
@@ -324,10 +334,12 @@ void build_prolongation(const HostBsr &A, const uint8_t *free_mask, int bc, cons
     const std::vector<uint8_t> &dr = (r == 0) ? drop : nodrop;
     if (r > 0) nodrop.assign(cur->n, 0);
     nc = pairing_round(*cur, (r == 0) ? drop : nodrop, opt.soc_thresh, cmap);
+    lap("pairing_round");
     (void)dr;
     if (r == 0) { for (i64 v = 0; v < n; v++) vmap[v] = cmap[v]; }
     else { for (i64 v = 0; v < n; v++) if (vmap[v] >= 0) vmap[v] = cmap[vmap[v]]; }
     coarsen_graph(*cur, cmap, nc, Gn);
+    lap("coarsen_graph");
     std::swap(Gc, Gn);
     cur = &Gc;
   }
@@ -359,6 +371,7 @@ void build_prolongation(const HostBsr &A, const uint8_t *free_mask, int bc, cons
     for (i64 c = 0; c < nc; c++) for (int k = 0; k < 3; k++) cxyz[c * 3 + k] /= std::max(cnt[c], 1);
   }
 
+  lap("orphans + renumber");
   // ---- prolongation rows
   const int maxpr = std::max(1, opt.max_per_row);
   P.nrows = n; P.ncols = nc; P.bh = bf; P.bw = bc;
@@ -413,6 +426,7 @@ void build_prolongation(const HostBsr &A, const uint8_t *free_mask, int bc, cons
     }
   });
   for (i64 v = 0; v < n; v++) P.rowptr[v + 1] += P.rowptr[v];
+  lap("prolongation rows");
   P.col.resize(P.rowptr[n]);
   P.val.assign(P.rowptr[n] * (i64)bf * bc, 0.0);
   parallel_for(n, [&](i64 lo, i64 hi) {
