@@ -100,6 +100,8 @@ struct Amg {
   int tri_level_launch_depth = 24;
   double tri_gate_gap_levels = 0.0;
   unsigned tri_repoll_ns = 0;
+  int tri_regate = 1;
+  unsigned long long *tri_trace = nullptr;  // debug tracing of the sync-free sweep (NGSAMG_B200_TRACE_FILE)
   int *d_err = nullptr;
   void check_watchdog();
 
@@ -194,6 +196,7 @@ void level_schedule(const HostBsr &A, const std::vector<uint8_t> &free_mask, boo
     // of a warp reach their newest dependency in the same chunk -- and keep the original order inside a group (locality).
     // Counting sort on (level, lower count, upper count); stable in the row number.
     const int W = depth > 256 ? 32 : 128;
+    const bool deep = depth > 64;
     std::vector<i32> sub(n);
     parallel_for(n, [&](i64 lo, i64 hi) {
       for (i64 i = lo; i < hi; i++) {
@@ -204,6 +207,9 @@ void level_schedule(const HostBsr &A, const std::vector<uint8_t> &free_mask, boo
           if (hf && free_mask[i] && !free_mask[j]) continue;   // stored in the separate N part
           if (lvl[j] < lvl[i] || (lvl[j] == lvl[i] && before(j, (i32)i))) nl++; else nu++;
         }
+        // deep DAGs (natural orderings): keep the row order (spatially compact slices keep the wavefront regions decoupled) and
+        // only move rows that are wider than the register slot cache into slices of their own
+        if (deep) { nl = nl <= 8 ? 0 : nl; nu = nu <= 8 ? 0 : nu; }
         sub[i] = std::min(nl, W - 1) * W + std::min(nu, W - 1);
       }
     });
@@ -826,7 +832,7 @@ void Amg::tri(Level &L, bool backward, bool add_self, bool write_r, const double
       }
       const i64 want = (L.npad + 8 * 16 - 1) / (8 * 16);   // >= 16 rows per warp
       const int grid = (int)std::max<i64>(1, std::min<i64>(want, tri_grid_cap[sidx]));
-      TriParams prm{L.npad / 32, backward ? 1 : 0, tri_sleep_ns, tri_prepoll, tri_gate_all, 0, 0u, L.nonfree_pad, d_err};
+      TriParams prm{L.npad / 32, backward ? 1 : 0, tri_sleep_ns, tri_prepoll, tri_gate_all, 0, 0u, 0, L.nonfree_pad, d_err, nullptr};
       kern<<<grid, 256, 0, st>>>(T.view(), L.diag, L.dinv, rin, self, out, rout, prm);
     };
     if (!add_self && !write_r) throw Error("tri: unsupported mode");
@@ -849,7 +855,7 @@ void Amg::tri(Level &L, bool backward, bool add_self, bool write_r, const double
     const i64 nslices = L.npad / 32;
     const int grid = (int)std::min<i64>((nslices + 7) / 8, tri_grid_cap[idx]);
     const i64 gap = tri_gate_gap_levels > 0 ? (i64)(tri_gate_gap_levels * (double)L.npad / std::max(1, L.depth)) : 0;
-    TriParams prm{nslices, backward ? 1 : 0, tri_sleep_ns, tri_prepoll, tri_gate_all, gap, tri_repoll_ns, L.nonfree_pad, d_err};
+    TriParams prm{nslices, backward ? 1 : 0, tri_sleep_ns, tri_prepoll, tri_gate_all, gap, tri_repoll_ns, tri_regate, L.nonfree_pad, d_err, tri_trace};
     kern<<<grid, 256, 0, st>>>(T.view(), L.diag, L.dinv, rin, self, out, rout, prm);
   };
   if (!add_self && !write_r) throw Error("tri: unsupported mode");
@@ -1214,6 +1220,7 @@ int ngsamg_b200_create(const char *type, const ngsamg_csr *A, const uint8_t *fre
   a.tri_gate_gap_levels = a.flags.num("b200_tri_gate_gap", 0.0);
   a.tri_level_launch_depth = (int)a.flags.num("b200_tri_level_launch_depth", 24);
   a.tri_repoll_ns = (unsigned)a.flags.num("b200_tri_repoll_ns", 0);
+  a.tri_regate = (int)a.flags.num("b200_tri_regate", 1);
   {
     int pm = (int)a.flags.num("b200_tri_pollmode", 0);
     NGB_CUDA(cudaMemcpyToSymbol(g_pollmode, &pm, sizeof(int)));
@@ -1694,6 +1701,28 @@ int ngsamg_b200_profile_kernel(ngsamg_b200_t *h, int level, int which, int reps,
   cudaEventElapsedTime(&ms, a.ev0, a.ev1);
   if (ms_avg) *ms_avg = ms / std::max(reps, 1);
   if (bytes) *bytes = B;
+  if (const char *tf = std::getenv("NGSAMG_B200_TRACE_FILE")) {
+    if (which == 0 || which == 3) {
+      const i64 ns = L.npad / 32;
+      a.tri_trace = dev_alloc<unsigned long long>(ns * 3);
+      NGB_CUDA(cudaMemsetAsync(a.tri_trace, 0, sizeof(unsigned long long) * ns * 3, a.st));
+      run();
+      NGB_CUDA(cudaStreamSynchronize(a.st));
+      std::vector<unsigned long long> ht(ns * 3);
+      NGB_CUDA(cudaMemcpy(ht.data(), a.tri_trace, sizeof(unsigned long long) * ns * 3, cudaMemcpyDeviceToHost));
+      dev_free(a.tri_trace);
+      a.tri_trace = nullptr;
+      std::string fn = std::string(tf) + (which == 0 ? ".fwd" : ".bwd");
+      if (FILE *f = std::fopen(fn.c_str(), "wb")) {
+        const i64 nl = (i64)L.level_start.size();
+        std::fwrite(&ns, sizeof(i64), 1, f);
+        std::fwrite(&nl, sizeof(i64), 1, f);
+        std::fwrite(L.level_start.data(), sizeof(i64), nl, f);
+        std::fwrite(ht.data(), sizeof(unsigned long long), ht.size(), f);
+        std::fclose(f);
+      }
+    }
+  }
   NGB_CUDA(cudaGetLastError());
   a.check_watchdog();
   NGB_CATCH

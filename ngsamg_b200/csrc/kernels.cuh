@@ -182,9 +182,18 @@ struct TriParams {
   int gate_all;       // 1: gate every chunk on its newest entry, 0: only the last chunk of the row
   i64 gate_gap;       // > 0: early gate (see k_gs_tri), in rows
   unsigned repoll_ns; // back-off of the per-lane straggler polls
+  int regate;         // 1: stragglers are waited for with a single polling lane (re-gate) instead of all lanes spinning
   i64 nonfree;        // rows [0, nonfree) are the non-free rows (dependency level 0)
   int *err;           // watchdog flag (set if a wait exceeds ~2^26 polls; never in a healthy run)
+  unsigned long long *trace;  // debug: per slice {pick-up, gate passed, published} globaltimer stamps (NULL = off)
 };
+
+__device__ __forceinline__ unsigned long long gtimer()
+{
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
 
 template <int B, bool ADD_SELF, bool WRITE_R, int PRE>
 __global__ void __launch_bounds__(256) k_gs_tri(SellView T, const double *__restrict__ diag, const double *__restrict__ dinv,
@@ -206,6 +215,7 @@ __global__ void __launch_bounds__(256) k_gs_tri(SellView T, const double *__rest
     // a non-free row is never updated (dinv = 0) and the increments of non-free rows are zero, so couplings between two
     // non-free rows contribute nothing: skip them (they would otherwise chain the boundary rows one after another)
     const i32 cut = (row < prm.nonfree) ? (i32)prm.nonfree : 0;
+    if (prm.trace && lane == 0) prm.trace[slice * 3 + 0] = gtimer();
     // ---- everything that does not depend on `out`: own rhs, diagonal blocks, matrix entries
     double acc[B];
 #pragma unroll
@@ -293,9 +303,38 @@ __global__ void __launch_bounds__(256) k_gs_tri(SellView T, const double *__rest
           return e;
         });
       }
+      if (prm.trace && lane == 0) prm.trace[slice * 3 + 1] = gtimer();
       double xk[PRE > 0 ? PRE : 1];
 #pragma unroll
       for (int k = 0; k < PRE; k++) xk[k] = (pc[k] >= 0) ? ld_poll(out + pc[k]) : 0.0;
+      if (prm.regate) {
+        // stragglers (the wavefront is not perfectly ordered): instead of spinning with all lanes, gate again with one
+        // lane on an entry that is still unpublished, then re-poll only the missing entries
+        for (unsigned round = 0;; round++) {
+          i32 u = -1;
+#pragma unroll
+          for (int k = 0; k < PRE; k++) if (pc[k] >= 0 && is_sentinel(xk[k])) u = pc[k];
+          if (prm.backward && u < 0) u = 0x7fffffff;
+#pragma unroll
+          for (int o = 16; o; o >>= 1) {
+            const i32 g = __shfl_xor_sync(0xffffffffu, u, o);
+            u = prm.backward ? min(u, g) : max(u, g);
+          }
+          if (prm.backward && u == 0x7fffffff) u = -1;
+          if (u < 0) break;
+          if (lane == 0 && (u >> 5) != slice) {
+            unsigned spins = 0;
+            while (is_sentinel(ld_poll(out + u))) {
+              if (prm.sleep_ns) __nanosleep(prm.sleep_ns);
+              if (++spins > (1u << 26)) { atomicExch(prm.err, 1); break; }
+            }
+          }
+          __syncwarp();
+#pragma unroll
+          for (int k = 0; k < PRE; k++) if (pc[k] >= 0 && is_sentinel(xk[k])) xk[k] = ld_poll(out + pc[k]);
+          if (round > (1u << 22)) { atomicExch(prm.err, 1); break; }
+        }
+      }
 #pragma unroll
       for (int k = 0; k < PRE; k++) {
         if (pc[k] >= 0) {
@@ -373,6 +412,7 @@ __global__ void __launch_bounds__(256) k_gs_tri(SellView T, const double *__rest
     }
 #pragma unroll
     for (int p = 0; p < B; p++) __stcg(out + row * B + p, ADD_SELF ? sv[p] + dl[p] : dl[p]);
+    if (prm.trace && lane == 0) prm.trace[slice * 3 + 2] = gtimer();
     if (WRITE_R) {
       const double *gp = diag + slice * (i64)(B * B) * 32 + lane;
 #pragma unroll
