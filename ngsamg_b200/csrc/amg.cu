@@ -50,6 +50,7 @@ struct Level {
   i64 nonfree_pad = 0;  // rows of dependency level 0 (non-free rows), padded
   int pre_l = 8, pre_u = 8;  // register slot cache of the triangular sweeps (scalar matrices)
   std::vector<i64> level_start;  // first (padded) row of every dependency level, plus npad
+  i32 *d_bnd_fwd = nullptr, *d_bnd_bwd = nullptr;  // split-gate boundaries per slice (see k_gs_tri)
   // transfer to level+1
   HostBsr hP;
   Sell P, PT;
@@ -101,6 +102,7 @@ struct Amg {
   double tri_gate_gap_levels = 0.0;
   unsigned tri_repoll_ns = 0;
   int tri_regate = 1;
+  int tri_split = 0;
   unsigned long long *tri_trace = nullptr;  // debug tracing of the sync-free sweep (NGSAMG_B200_TRACE_FILE)
   int *d_err = nullptr;
   void check_watchdog();
@@ -225,6 +227,18 @@ void level_schedule(const HostBsr &A, const std::vector<uint8_t> &free_mask, boo
       }
     }
     for (i64 i = 0; i < n; i++) L.perm[i] = (i32)(bstart[(i64)lvl[i] * W * W + sub[i]]++);
+  }
+  if (smoothed && L.b == 1) {
+    const i64 ns = L.npad / 32;
+    const int nl = (int)L.level_start.size() - 1;
+    std::vector<i32> bf(ns, 0), bb(ns, 0);
+    for (int lv = 0; lv < nl; lv++) {
+      const i32 f = (i32)(lv >= 1 ? L.level_start[lv - 1] : 0);
+      const i32 e = (i32)(lv + 2 <= nl ? L.level_start[lv + 2] : L.npad);
+      for (i64 s2 = L.level_start[lv] / 32; s2 < L.level_start[lv + 1] / 32; s2++) { bf[s2] = f; bb[s2] = e; }
+    }
+    L.d_bnd_fwd = upload_vec(bf, st);
+    L.d_bnd_bwd = upload_vec(bb, st);
   }
   (void)st;
 }
@@ -435,7 +449,7 @@ Amg::~Amg()
   if (device >= 0) cudaSetDevice(device);
   for (auto &lp : lev) {
     Level &L = *lp;
-    dev_free(L.d_perm); dev_free(L.d_freep); dev_free(L.d_pt_rowmap);
+    dev_free(L.d_perm); dev_free(L.d_freep); dev_free(L.d_pt_rowmap); dev_free(L.d_bnd_fwd); dev_free(L.d_bnd_bwd);
     L.L.release(); L.U.release(); L.N.release(); L.P.release(); L.PT.release();
     dev_free(L.diag); dev_free(L.dinv);
     dev_free(L.x); dev_free(L.y); dev_free(L.rhs); dev_free(L.res); dev_free(L.tmp); dev_free(L.wa); dev_free(L.wb);
@@ -832,7 +846,7 @@ void Amg::tri(Level &L, bool backward, bool add_self, bool write_r, const double
       }
       const i64 want = (L.npad + 8 * 16 - 1) / (8 * 16);   // >= 16 rows per warp
       const int grid = (int)std::max<i64>(1, std::min<i64>(want, tri_grid_cap[sidx]));
-      TriParams prm{L.npad / 32, backward ? 1 : 0, tri_sleep_ns, tri_prepoll, tri_gate_all, 0, 0u, 0, L.nonfree_pad, d_err, nullptr};
+      TriParams prm{L.npad / 32, backward ? 1 : 0, tri_sleep_ns, tri_prepoll, tri_gate_all, 0, 0u, 0, L.nonfree_pad, d_err, nullptr, nullptr};
       kern<<<grid, 256, 0, st>>>(T.view(), L.diag, L.dinv, rin, self, out, rout, prm);
     };
     if (!add_self && !write_r) throw Error("tri: unsupported mode");
@@ -855,7 +869,7 @@ void Amg::tri(Level &L, bool backward, bool add_self, bool write_r, const double
     const i64 nslices = L.npad / 32;
     const int grid = (int)std::min<i64>((nslices + 7) / 8, tri_grid_cap[idx]);
     const i64 gap = tri_gate_gap_levels > 0 ? (i64)(tri_gate_gap_levels * (double)L.npad / std::max(1, L.depth)) : 0;
-    TriParams prm{nslices, backward ? 1 : 0, tri_sleep_ns, tri_prepoll, tri_gate_all, gap, tri_repoll_ns, tri_regate, L.nonfree_pad, d_err, tri_trace};
+    TriParams prm{nslices, backward ? 1 : 0, tri_sleep_ns, tri_prepoll, tri_gate_all, gap, tri_repoll_ns, tri_regate, L.nonfree_pad, d_err, tri_split ? (backward ? L.d_bnd_bwd : L.d_bnd_fwd) : nullptr, tri_trace};
     kern<<<grid, 256, 0, st>>>(T.view(), L.diag, L.dinv, rin, self, out, rout, prm);
   };
   if (!add_self && !write_r) throw Error("tri: unsupported mode");
@@ -1221,6 +1235,7 @@ int ngsamg_b200_create(const char *type, const ngsamg_csr *A, const uint8_t *fre
   a.tri_level_launch_depth = (int)a.flags.num("b200_tri_level_launch_depth", 24);
   a.tri_repoll_ns = (unsigned)a.flags.num("b200_tri_repoll_ns", 0);
   a.tri_regate = (int)a.flags.num("b200_tri_regate", 1);
+  a.tri_split = (int)a.flags.num("b200_tri_split", 0);
   {
     int pm = (int)a.flags.num("b200_tri_pollmode", 0);
     NGB_CUDA(cudaMemcpyToSymbol(g_pollmode, &pm, sizeof(int)));

@@ -185,6 +185,7 @@ struct TriParams {
   int regate;         // 1: stragglers are waited for with a single polling lane (re-gate) instead of all lanes spinning
   i64 nonfree;        // rows [0, nonfree) are the non-free rows (dependency level 0)
   int *err;           // watchdog flag (set if a wait exceeds ~2^26 polls; never in a healthy run)
+  const i32 *bnd;     // split gate: per slice, first row of the previous level (forward) / end row of the next level (backward)
   unsigned long long *trace;  // debug: per slice {pick-up, gate passed, published} globaltimer stamps (NULL = off)
 };
 
@@ -292,10 +293,16 @@ __global__ void __launch_bounds__(256) k_gs_tri(SellView T, const double *__rest
       return c >= cut && (prm.backward ? ((i64)c >= (i64)f + prm.gate_gap) : ((i64)c <= (i64)f - prm.gate_gap));
     };
     if (PRE > 0) {
+      // split gate (prm.bnd): entries in the dependency level processed just before this one ("new") are polled directly by
+      // all lanes -- their poll result IS the data, one L2 round trip per hop -- while the single-lane gate with back-off
+      // waits for the newest OLDER entry, which is published about one hop earlier.
+      const bool split = prm.bnd != nullptr && width <= PRE;
+      const i32 bnd = split ? prm.bnd[slice] : 0;
+      auto is_new = [&](i32 c) { return split && c >= 0 && (prm.backward ? (c < bnd) : (c >= bnd)); };
       {
         i32 mylast = -1;
 #pragma unroll
-        for (int k = 0; k < PRE; k++) if (pc[k] >= 0) mylast = pc[k];
+        for (int k = 0; k < PRE; k++) if (pc[k] >= 0 && !is_new(pc[k])) mylast = pc[k];
         gate(mylast, 0, [&](i32 f) {
           i32 e = -1;
 #pragma unroll
@@ -313,7 +320,7 @@ __global__ void __launch_bounds__(256) k_gs_tri(SellView T, const double *__rest
         for (unsigned round = 0;; round++) {
           i32 u = -1;
 #pragma unroll
-          for (int k = 0; k < PRE; k++) if (pc[k] >= 0 && is_sentinel(xk[k])) u = pc[k];
+          for (int k = 0; k < PRE; k++) if (pc[k] >= 0 && !is_new(pc[k]) && is_sentinel(xk[k])) u = pc[k];
           if (prm.backward && u < 0) u = 0x7fffffff;
 #pragma unroll
           for (int o = 16; o; o >>= 1) {
@@ -333,6 +340,16 @@ __global__ void __launch_bounds__(256) k_gs_tri(SellView T, const double *__rest
 #pragma unroll
           for (int k = 0; k < PRE; k++) if (pc[k] >= 0 && is_sentinel(xk[k])) xk[k] = ld_poll(out + pc[k]);
           if (round > (1u << 22)) { atomicExch(prm.err, 1); break; }
+        }
+      }
+      if (split) {
+        for (unsigned it = 0;; it++) {
+          bool un = false;
+#pragma unroll
+          for (int k = 0; k < PRE; k++)
+            if (pc[k] >= 0 && is_sentinel(xk[k])) { xk[k] = ld_poll(out + pc[k]); un |= is_sentinel(xk[k]); }
+          if (!__any_sync(0xffffffffu, un)) break;
+          if (it > (1u << 26)) { atomicExch(prm.err, 1); break; }
         }
       }
 #pragma unroll
