@@ -164,7 +164,7 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours")
-    ap.add_argument("--n", type=int, default=int(os.environ.get("NGSAMG_BENCH_N", DEFAULT_N)))
+    ap.add_argument("--size", dest="n", type=int, default=int(os.environ.get("NGSAMG_BENCH_N", DEFAULT_N)))
     ap.add_argument("--cpu-n", type=int, default=int(os.environ.get("NGSAMG_BENCH_CPU_N", CPU_SAMPLE_N)))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-multicolor", action="store_true", help="skip the separately reported multicolour-smoother variant")

@@ -1119,7 +1119,7 @@ void Amg::ensure_io(i64 n)
 const double *Amg::to_device(const double *p, i64 n, double *stage)
 {
   if (is_device_ptr(p)) return p;
-  std::memcpy(pin_a, p, sizeof(double) * n);  // pageable -> pinned, then async H2D
+  parallel_for(n, [&](i64 lo, i64 hi) { std::memcpy(pin_a + lo, p + lo, sizeof(double) * (hi - lo)); }, 1 << 18);  // pageable -> pinned (threads), then async H2D
   NGB_CUDA(cudaMemcpyAsync(stage, pin_a, sizeof(double) * n, cudaMemcpyHostToDevice, st));
   NGB_CUDA(cudaStreamSynchronize(st));
   return stage;
@@ -1134,7 +1134,7 @@ void Amg::from_device(double *dst, const double *src_dev, i64 n)
   }
   NGB_CUDA(cudaMemcpyAsync(pin_b, src_dev, sizeof(double) * n, cudaMemcpyDeviceToHost, st));
   NGB_CUDA(cudaStreamSynchronize(st));
-  std::memcpy(dst, pin_b, sizeof(double) * n);
+  parallel_for(n, [&](i64 lo, i64 hi) { std::memcpy(dst + lo, pin_b + lo, sizeof(double) * (hi - lo)); }, 1 << 18);
 }
 
 }  // namespace ngb

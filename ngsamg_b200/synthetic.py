@@ -33,7 +33,7 @@ def _edge_cube_weight(vb, vc, nb, nc):
     return w
 
 
-def poisson3d_kuhn(nx, ny=None, nz=None, dirichlet=("x0", "y1"), coef=None):
+def poisson3d_kuhn(nx, ny=None, nz=None, dirichlet=("x0", "y1"), coef=None, zchunk=8):
     """P1 stiffness matrix of -div(c grad u) on the unit cube, nx*ny*nz vertices, Kuhn tets.
 
     Vertex (ix,iy,iz) has DOF number ix + nx*(iy + ny*iz).  The sparsity pattern is the mesh
@@ -41,6 +41,7 @@ def poisson3d_kuhn(nx, ny=None, nz=None, dirichlet=("x0", "y1"), coef=None):
     Returns dict(n, rowptr[int64], col[int32], val[f64], free[uint8], rhs[f64] (f=1 load), xyz).
     `coef`: optional callable (x,y,z)->c evaluated at vertices; the edge weight uses the mean of the
     two end-point values (a diagonal scaling that keeps symmetry and zero row sums).
+    Generated in slabs of `zchunk` vertex planes so that the peak memory stays close to the size of the result.
     """
     ny = nx if ny is None else ny
     nz = nx if nz is None else nz
@@ -48,54 +49,80 @@ def poisson3d_kuhn(nx, ny=None, nz=None, dirichlet=("x0", "y1"), coef=None):
     h = 1.0 / (max(nx, ny, nz) - 1)
     dirs = [(0, 0, 0)] + _POS_DIRS + [(-a, -b, -c) for (a, b, c) in _POS_DIRS]
     dirs.sort(key=lambda d: d[0] + nx * (d[1] + ny * d[2]))
-    iz, iy, ix = np.meshgrid(np.arange(nz), np.arange(ny), np.arange(nx), indexing="ij")
-    ix, iy, iz = ix.ravel(), iy.ravel(), iz.ravel()
-    idx = np.arange(n, dtype=np.int64)
-    cv = None
-    if coef is not None:
-        cv = coef(ix * h, iy * h, iz * h).astype(np.float64)
     K = len(dirs)
-    cols = np.zeros((n, K), np.int64)
-    vals = np.zeros((n, K), np.float64)
-    mask = np.zeros((n, K), bool)
-    dims = (nx, ny, nz)
-    coord = (ix, iy, iz)
-    for k, d in enumerate(dirs):
-        jx, jy, jz = ix + d[0], iy + d[1], iz + d[2]
-        ok = (jx >= 0) & (jx < nx) & (jy >= 0) & (jy < ny) & (jz >= 0) & (jz < nz)
-        mask[:, k] = ok
-        cols[:, k] = idx + d[0] + nx * (d[1] + ny * d[2])
-        nzc = sum(abs(c) for c in d)
-        if nzc == 1:
-            a = [i for i in range(3) if d[i] != 0][0]
-            b, c = [i for i in range(3) if i != a]
-            w = _edge_cube_weight(coord[b], coord[c], dims[b], dims[c]).astype(np.float64)
-            v = -(h / 6.0) * w
-            if cv is not None:
-                j = np.clip(cols[:, k], 0, n - 1)
-                v = v * 0.5 * (cv + cv[j])
-            vals[:, k] = np.where(ok, v, 0.0)
     kd = dirs.index((0, 0, 0))
-    vals[:, kd] = -(vals * mask).sum(axis=1)
-    cnt = mask.sum(axis=1)
+    dims = (nx, ny, nz)
+    # rows per vertex = number of in-bounds directions: separable count
+    def nb(k, m):  # number of in-range offsets in {-1,0,1} along one axis
+        return (k > 0).astype(np.int64) + 1 + (k < m - 1).astype(np.int64)
     rowptr = np.zeros(n + 1, np.int64)
-    np.cumsum(cnt, out=rowptr[1:])
-    col = cols[mask].astype(np.int32)
-    val = vals[mask]
+    col = None
+    val = None
     free = np.ones(n, np.uint8)
-    for tag in dirichlet:
-        ax = "xyz".index(tag[0])
-        side = 0 if tag[1] == "0" else dims[ax] - 1
-        free[coord[ax] == side] = 0
-    # load vector for f = 1: (h^3/24) * number of incident tets
-    ntet = np.zeros(n, np.int64)
-    for s in itertools.product((0, 1), repeat=3):
-        ok = np.ones(n, bool)
-        for a in range(3):
-            ok &= (coord[a] - s[a] >= 0) & (coord[a] - s[a] <= dims[a] - 2)
-        ntet += ok * (6 if sum(s) in (0, 3) else 2)
-    rhs = (h ** 3 / 24.0) * ntet
-    xyz = np.stack([ix * h, iy * h, iz * h], axis=1).astype(np.float64)
+    rhs = np.zeros(n)
+    # pass 1: counts (needs the actual in-bounds test of the 15 directions, done per slab below), pass 2: fill
+    chunks = [(z0, min(nz, z0 + zchunk)) for z0 in range(0, nz, zchunk)]
+    cnt_all = np.zeros(n, np.int64)
+    slabs = []
+    for (z0, z1) in chunks:
+        iz, iy, ix = np.meshgrid(np.arange(z0, z1), np.arange(ny), np.arange(nx), indexing="ij")
+        ix, iy, iz = ix.ravel(), iy.ravel(), iz.ravel()
+        m = np.zeros(ix.shape[0], np.int64)
+        for d in dirs:
+            jx, jy, jz = ix + d[0], iy + d[1], iz + d[2]
+            m += (jx >= 0) & (jx < nx) & (jy >= 0) & (jy < ny) & (jz >= 0) & (jz < nz)
+        cnt_all[z0 * nx * ny:z1 * nx * ny] = m
+    np.cumsum(cnt_all, out=rowptr[1:])
+    del cnt_all
+    nnz = int(rowptr[-1])
+    col = np.empty(nnz, np.int32)
+    val = np.empty(nnz, np.float64)
+    cvfun = coef
+    for (z0, z1) in chunks:
+        iz, iy, ix = np.meshgrid(np.arange(z0, z1), np.arange(ny), np.arange(nx), indexing="ij")
+        ix, iy, iz = ix.ravel(), iy.ravel(), iz.ravel()
+        m = ix.shape[0]
+        idx = ix + nx * (iy + ny * iz)
+        coord = (ix, iy, iz)
+        cv = cvfun(ix * h, iy * h, iz * h).astype(np.float64) if cvfun is not None else None
+        cols = np.zeros((m, K), np.int64)
+        vals = np.zeros((m, K), np.float64)
+        mask = np.zeros((m, K), bool)
+        for k, d in enumerate(dirs):
+            jx, jy, jz = ix + d[0], iy + d[1], iz + d[2]
+            ok = (jx >= 0) & (jx < nx) & (jy >= 0) & (jy < ny) & (jz >= 0) & (jz < nz)
+            mask[:, k] = ok
+            cols[:, k] = idx + d[0] + nx * (d[1] + ny * d[2])
+            if sum(abs(c) for c in d) == 1:
+                a = [i for i in range(3) if d[i] != 0][0]
+                b_, c_ = [i for i in range(3) if i != a]
+                w = _edge_cube_weight(coord[b_], coord[c_], dims[b_], dims[c_]).astype(np.float64)
+                v = -(h / 6.0) * w
+                if cv is not None:
+                    cj = cvfun(np.clip(jx, 0, nx - 1) * h, np.clip(jy, 0, ny - 1) * h, np.clip(jz, 0, nz - 1) * h).astype(np.float64)
+                    v = v * 0.5 * (cv + cj)
+                vals[:, k] = np.where(ok, v, 0.0)
+        vals[:, kd] = -(vals * mask).sum(axis=1)
+        lo, hi = int(rowptr[z0 * nx * ny]), int(rowptr[z1 * nx * ny])
+        col[lo:hi] = cols[mask]
+        val[lo:hi] = vals[mask]
+        sl = slice(z0 * nx * ny, z1 * nx * ny)
+        fr = np.ones(m, np.uint8)
+        for tag in dirichlet:
+            ax = "xyz".index(tag[0])
+            side = 0 if tag[1] == "0" else dims[ax] - 1
+            fr[coord[ax] == side] = 0
+        free[sl] = fr
+        # load vector for f = 1: (h^3/24) * number of incident tets
+        ntet = np.zeros(m, np.int64)
+        for s3 in itertools.product((0, 1), repeat=3):
+            ok = np.ones(m, bool)
+            for a in range(3):
+                ok &= (coord[a] - s3[a] >= 0) & (coord[a] - s3[a] <= dims[a] - 2)
+            ntet += ok * (6 if sum(s3) in (0, 3) else 2)
+        rhs[sl] = (h ** 3 / 24.0) * ntet
+    ids = np.arange(n)
+    xyz = np.stack([(ids % nx) * h, ((ids // nx) % ny) * h, (ids // (nx * ny)) * h], axis=1).astype(np.float64)
     return dict(n=n, b=1, rowptr=rowptr, col=col, val=val, free=free, rhs=rhs, xyz=xyz, h=h, dims=(nx, ny, nz))
 
 
