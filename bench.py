@@ -93,9 +93,14 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def make_problem(n):
+def make_problem(n, problem="poisson"):
     from ngsamg_b200 import synthetic as S
     import ngsamg_b200 as ng
+    if problem == "elasticity":
+        # P1 elasticity beam (3x3 blocks, 6x6 on the coarse levels): nx x (nx/2) x (nx/2) vertices, clamped at x=0, body force (0,x,0)
+        p = S.elasticity3d_kuhn_stencil(n, n // 2 + 1, n // 2 + 1)
+        A = ng.SparseMatrix(p["n"], p["n"], 3, 3, p["rowptr"], p["col"], p["val"])
+        return p, A
     p = S.poisson3d_kuhn(n)
     A = ng.SparseMatrix(p["n"], p["n"], 1, 1, p["rowptr"], p["col"], p["val"])
     return p, A
@@ -166,6 +171,8 @@ def main():
     ap.add_argument("--impl", default="ours")
     ap.add_argument("--size", dest="n", type=int, default=int(os.environ.get("NGSAMG_BENCH_N", DEFAULT_N)))
     ap.add_argument("--cpu-n", type=int, default=int(os.environ.get("NGSAMG_BENCH_CPU_N", CPU_SAMPLE_N)))
+    ap.add_argument("--problem", default="poisson", choices=["poisson", "elasticity"],
+                    help="poisson = BASELINE.json configs[1] (headline); elasticity = P1 beam with elast_3d (secondary, reported on request)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-multicolor", action="store_true", help="skip the separately reported multicolour-smoother variant")
     args = ap.parse_args()
@@ -193,22 +200,30 @@ def main():
 
     n = rank_workload(args.n, rank, world)
     t0 = time.time()
-    p, A = make_problem(n)
+    p, A = make_problem(n, args.problem)
     gen_s = time.time() - t0
+    elast = args.problem == "elasticity"
+    if elast:
+        args.no_cpu_baseline = True
+        args.no_multicolor = True
     t0 = time.time()
     extra = {}
     for kv in os.environ.get("NGSAMG_FLAGS", "").split(","):
         if "=" in kv:
             k, v = kv.split("=", 1)
             extra["ngs_amg_" + k.strip()] = v.strip()
-    pc = ng.h1_scal(A, p["free"], device=local_rank, **extra)
+    tol = 1e-6 if elast else TOL       # the reference's elasticity tests solve to 1e-6 (tests/elasticity/amg_utils.py:439)
+    if elast:
+        pc = ng.elast_3d(A, p["free"], vertex_xyz=p["xyz"], device=local_rank, **extra)
+    else:
+        pc = ng.h1_scal(A, p["free"], device=local_rank, **extra)
     setup_s = time.time() - t0
-    ndof = p["n"]
+    ndof = p["n"] * A.bh
     rhs_h = np.ascontiguousarray(p["rhs"])
     x_h = np.zeros(ndof)
     rhs_d = torch.from_numpy(rhs_h).cuda()
     x_d = torch.zeros_like(rhs_d)
-    cg = ng.CGSolver(mat=A, pre=pc, maxsteps=200, tol=TOL)
+    cg = ng.CGSolver(mat=A, pre=pc, maxsteps=200, tol=tol)
 
     # ---- device-resident solve (value) ---------------------------------------------------------------
     for _ in range(args.warmup):
@@ -282,7 +297,7 @@ def main():
     levels = []
     for l in range(pc.GetNLevels()):
         i = pc.level_info(l)
-        levels.append({"n": int(i.n), "nnz": int(i.nnz), "gs_depth": int(i.gs_depth)})
+        levels.append({"n": int(i.n), "b": int(i.b), "nnz": int(i.nnz), "gs_depth": int(i.gs_depth)})
 
     # ---- optional variant, reported separately: multicolour Gauss-Seidel on the fine level ------------------------------
     variant = None
@@ -322,10 +337,11 @@ def main():
             "metric": "pcg_amg_solve_dofs_per_s", "value": world * ndof / solve_s, "unit": "DOF/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": solve_s * 1e3, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "3D Poisson P1 unit cube (Kuhn tets), %d^3 = %d DOFs per GPU, h1_scal + CG to 1e-8" % (n, ndof),
-                       "tol": TOL, "levels": levels, "operator_complexity": pc.GetOC(),
+            "config": {"workload": ("3D Poisson P1 unit cube (Kuhn tets), %d^3 = %d DOFs per GPU, h1_scal + CG to 1e-8" % (n, ndof)) if not elast else
+                                   ("3D linear elasticity P1 beam (Kuhn tets), %d vertices = %d DOFs per GPU, elast_3d (3x3 fine / 6x6 coarse blocks) + CG to 1e-6" % (p["n"], ndof)),
+                       "tol": tol, "levels": levels, "operator_complexity": pc.GetOC(),
                        "parallelism": "1 GPU" if world == 1 else "%d independent subdomain replicas (no halo exchange yet)" % world,
-                       "l2": "inputs larger than L2 (level-0 matrix %.1f GB)" % (levels[0]["nnz"] * 12 / 1e9)},
+                       "l2": "inputs larger than L2 (level-0 matrix %.1f GB)" % (levels[0]["nnz"] * (8 * levels[0]["b"] ** 2 + 4) / 1e9)},
             "solve_s": solve_s, "iterations": iters, "setup_s": setup_s, "setup_rap_ms": pc.LastMs("rap"),
             "setup_host_ms": pc.LastMs("host"), "gen_s": gen_s, "wall_s_timed_region": wall_s,
             "vcycle_ms": vcycle_ms, "vcycle_bytes": vbytes, "vcycle_gbs": vbytes / vcycle_ms / 1e6,

@@ -894,13 +894,21 @@ void Amg::tri_dispatch(Level &L, bool backward, bool add_self, bool write_r, con
   }
 }
 
+static i64 g_spmv_small_rows = 200000;   // levels with fewer rows use the warp-per-row SpMV
 template <int BH, int BW, bool S2, bool D>
 static void launch_spmv(cudaStream_t st, i64 npad, const Sell &a, const Sell *b, const double *diag, const double *v, const double *y_in,
                         double *y_out, double alpha, double beta, double *xadd, const Sell *nfp = nullptr, const i32 *rowmap = nullptr)
 {
   const SellView none{nullptr, nullptr, nullptr};
+  const SellView s3 = (nfp && nfp->slice_ptr) ? nfp->view() : none;
+  if (npad <= g_spmv_small_rows) {
+    const unsigned grid = (unsigned)std::max<i64>(1, std::min<i64>((npad + 7) / 8, 148 * 8));
+    k_sell_spmv_small<BH, BW, S2, D><<<grid, TB, 0, st>>>(npad, a.view(), b ? b->view() : a.view(), diag, v, y_in, y_out, alpha, beta,
+                                                         xadd, s3, rowmap);
+    return;
+  }
   k_sell_spmv<BH, BW, S2, D><<<nblk(npad), TB, 0, st>>>(npad, a.view(), b ? b->view() : a.view(), diag, v, y_in, y_out, alpha, beta, xadd,
-                                                       (nfp && nfp->slice_ptr) ? nfp->view() : none, rowmap);
+                                                       s3, rowmap);
 }
 
 void Amg::spmv_part(Level &L, int which, const double *v, const double *y_in, double *y_out, double alpha, double beta, double *xadd)
@@ -1236,6 +1244,7 @@ int ngsamg_b200_create(const char *type, const ngsamg_csr *A, const uint8_t *fre
   a.tri_repoll_ns = (unsigned)a.flags.num("b200_tri_repoll_ns", 0);
   a.tri_regate = (int)a.flags.num("b200_tri_regate", 1);
   a.tri_split = (int)a.flags.num("b200_tri_split", 0);
+  g_spmv_small_rows = (i64)a.flags.num("b200_spmv_small_rows", 200000);
   {
     int pm = (int)a.flags.num("b200_tri_pollmode", 0);
     NGB_CUDA(cudaMemcpyToSymbol(g_pollmode, &pm, sizeof(int)));

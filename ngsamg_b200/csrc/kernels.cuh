@@ -148,6 +148,77 @@ __global__ void __launch_bounds__(256) k_sell_spmv(i64 nrows_pad, SellView S1, S
   }
 }
 
+// Same contract as k_sell_spmv for SMALL levels (coarse levels: few rows, wide rows): one WARP per row, the lanes split
+// the row's entries (all parts), fixed shuffle tree.  Removes the long per-thread chains that make the thread-per-row kernel
+// latency bound when a level has fewer rows than the machine has threads.
+template <int BH, int BW, bool HAS_S2, bool HAS_D>
+__global__ void __launch_bounds__(256) k_sell_spmv_small(i64 nrows_pad, SellView S1, SellView S2, const double *__restrict__ diag,
+                                                        const double *__restrict__ v, const double *y_in, double *y_out,
+                                                        double alpha, double beta, double *xadd, SellView S3,
+                                                        const i32 *__restrict__ rowmap)
+{
+  const int lane = threadIdx.x & 31;
+  const i64 gw = ((i64)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const i64 nw = ((i64)gridDim.x * blockDim.x) >> 5;
+  for (i64 row = gw; row < nrows_pad; row += nw) {
+    const i64 slice = row >> 5;
+    const int lr = (int)(row & 31);
+    double acc[BH];
+#pragma unroll
+    for (int p = 0; p < BH; p++) acc[p] = 0.0;
+    auto part = [&](const SellView &S) {
+      const i64 base = S.slice_ptr[slice];
+      const int width = (int)(S.slice_ptr[slice + 1] - base);
+      for (int k = lane; k < width; k += 32) {
+        const i32 c = S.col[(base + k) * 32 + lr];
+        if (c < 0) continue;
+        double xv[BW];
+#pragma unroll
+        for (int q = 0; q < BW; q++) xv[q] = v[(i64)c * BW + q];
+#pragma unroll
+        for (int p = 0; p < BH; p++) {
+          double t = 0.0;
+#pragma unroll
+          for (int q = 0; q < BW; q++) t = fma(S.val[((base + k) * (i64)(BH * BW) + p * BW + q) * 32 + lr], xv[q], t);
+          acc[p] += t;
+        }
+      }
+    };
+    part(S1);
+    if (HAS_S2) part(S2);
+    if (HAS_D && S3.slice_ptr) part(S3);
+#pragma unroll
+    for (int p = 0; p < BH; p++)
+#pragma unroll
+      for (int o = 16; o; o >>= 1) acc[p] += __shfl_xor_sync(0xffffffffu, acc[p], o);
+    if (lane != 0) continue;
+    if (HAS_D || xadd) {
+      double vi[BW];
+#pragma unroll
+      for (int q = 0; q < BW; q++) vi[q] = v[row * BW + q];
+      if (HAS_D) {
+        const double *dp = diag + slice * (i64)(BH * BW) * 32 + lr;
+#pragma unroll
+        for (int p = 0; p < BH; p++)
+#pragma unroll
+          for (int q = 0; q < BW; q++) acc[p] = fma(dp[(p * BW + q) * 32], vi[q], acc[p]);
+      }
+      if (xadd) {
+#pragma unroll
+        for (int q = 0; q < BW; q++) xadd[row * BW + q] += vi[q];
+      }
+    }
+    i64 orow = row;
+    if (rowmap) { orow = rowmap[row]; if (orow < 0) continue; }
+#pragma unroll
+    for (int p = 0; p < BH; p++) {
+      double y = alpha * acc[p];
+      if (beta != 0.0) y = fma(beta, y_in[orow * BH + p], y);
+      y_out[orow * BH + p] = y;
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // K2/K3: triangular half-sweep of Gauss-Seidel in the reference's row order -- sync-free, "data is the flag".
 //   out_i  = (ADD_SELF ? self_i : 0) + dinv_i * ( rin_i - sum_{k in T_i} A_ik out_k )      [T = L forward, U backward]

@@ -224,3 +224,71 @@ def elasticity3d_kuhn(nx, ny, nz, lx=None, E=1e3, nu=0.15, jump=None, clamp=("x0
     rhs = np.zeros((n, 3))
     rhs[:, 1] = fy
     return dict(n=n, b=3, rowptr=rowptr, col=col, val=val.reshape(-1), free=free, rhs=rhs.reshape(-1), xyz=X)
+
+
+def elasticity3d_kuhn_stencil(nx, ny, nz, E=1e3, nu=0.15, clamp=("x0",)):
+    """Same matrix as elasticity3d_kuhn on a UNIFORM Kuhn mesh (cube edge h = 1/(min(ny,nz)-1), lx = h*(nx-1)), built from
+    the translation-invariant block stencil instead of element assembly, so that multi-million-vertex problems can be generated:
+    the block row of a vertex depends only on its class (first / interior / last plane per axis, 27 classes), which is read off a
+    small element-assembled reference mesh.  Returns the same dict as elasticity3d_kuhn."""
+    ref_n = 5
+    ref = elasticity3d_kuhn(ref_n, ref_n, ref_n, E=E, nu=nu, clamp=())
+    hs = 1.0 / (min(ny, nz) - 1)
+    href = 1.0 / (ref_n - 1)
+    scale = hs / href                      # stiffness blocks scale with h, the lumped load with h^3 (* x for the body force)
+    n = nx * ny * nz
+    dirs = [(0, 0, 0)] + _POS_DIRS + [(-a, -b, -c) for (a, b, c) in _POS_DIRS]
+    dirs.sort(key=lambda d: d[0] + nx * (d[1] + ny * d[2]))
+    K = len(dirs)
+    # reference table: class (cx,cy,cz in {0,1,2}) x direction -> 3x3 block
+    table = np.zeros((3, 3, 3, K, 3, 3))
+    rp, rc, rv = ref["rowptr"], ref["col"], ref["val"].reshape(-1, 3, 3)
+    pick = {0: 0, 1: 2, 2: ref_n - 1}
+    for cx in range(3):
+        for cy in range(3):
+            for cz in range(3):
+                vx, vy, vz = pick[cx], pick[cy], pick[cz]
+                i = vx + ref_n * (vy + ref_n * vz)
+                for k, d in enumerate(dirs):
+                    jx, jy, jz = vx + d[0], vy + d[1], vz + d[2]
+                    if not (0 <= jx < ref_n and 0 <= jy < ref_n and 0 <= jz < ref_n):
+                        continue
+                    j = jx + ref_n * (jy + ref_n * jz)
+                    pos = np.searchsorted(rc[rp[i]:rp[i + 1]], j)
+                    table[cx, cy, cz, k] = rv[rp[i] + pos] * scale
+    ids = np.arange(n, dtype=np.int64)
+    ix, iy, iz = ids % nx, (ids // nx) % ny, ids // (nx * ny)
+    cls = lambda k, m: np.where(k == 0, 0, np.where(k == m - 1, 2, 1))
+    cxa, cya, cza = cls(ix, nx), cls(iy, ny), cls(iz, nz)
+    mask = np.zeros((n, K), bool)
+    cols = np.zeros((n, K), np.int64)
+    for k, d in enumerate(dirs):
+        jx, jy, jz = ix + d[0], iy + d[1], iz + d[2]
+        mask[:, k] = (jx >= 0) & (jx < nx) & (jy >= 0) & (jy < ny) & (jz >= 0) & (jz < nz)
+        cols[:, k] = ids + d[0] + nx * (d[1] + ny * d[2])
+    rowptr = np.zeros(n + 1, np.int64)
+    np.cumsum(mask.sum(axis=1), out=rowptr[1:])
+    col = cols[mask].astype(np.int32)
+    del cols
+    val = np.empty((int(rowptr[-1]), 3, 3))
+    slot = np.cumsum(mask, axis=1) - 1                      # position of direction k inside its row
+    for k in range(K):
+        rows = np.flatnonzero(mask[:, k])
+        val[rowptr[rows] + slot[rows, k]] = table[cxa[rows], cya[rows], cza[rows], k]
+    free = np.ones(n, np.uint8)
+    dims = (nx, ny, nz)
+    coord = (ix, iy, iz)
+    for tag in clamp:
+        ax = "xyz".index(tag[0])
+        free[coord[ax] == (0 if tag[1] == "0" else dims[ax] - 1)] = 0
+    X = np.stack([ix * hs, iy * hs, iz * hs], axis=1).astype(np.float64)
+    # body force (0, x, 0), lumped: (h^3/24) * (#incident tets) * x  (exact for the nodal value of x at the vertex up to O(h))
+    ntet = np.zeros(n, np.int64)
+    for s3 in itertools.product((0, 1), repeat=3):
+        ok = np.ones(n, bool)
+        for a in range(3):
+            ok &= (coord[a] - s3[a] >= 0) & (coord[a] - s3[a] <= dims[a] - 2)
+        ntet += ok * (6 if sum(s3) in (0, 3) else 2)
+    rhs = np.zeros((n, 3))
+    rhs[:, 1] = (hs ** 3 / 24.0) * ntet * X[:, 0]
+    return dict(n=n, b=3, rowptr=rowptr, col=col, val=val.reshape(-1), free=free, rhs=rhs.reshape(-1), xyz=X)
