@@ -99,6 +99,7 @@ struct Amg {
   int tri_grid_cap[32] = {0};
   i64 tri_small_rows = 1000000;
   int tri_level_launch_depth = 24;
+  i64 tri_level_launch_rows = 131072;
   double tri_gate_gap_levels = 0.0;
   unsigned tri_repoll_ns = 0;
   int tri_regate = 1;
@@ -821,7 +822,7 @@ void Amg::tri(Level &L, bool backward, bool add_self, bool write_r, const double
   const Sell &T = backward ? L.U : L.L;
   // sentinel-fill the output: a row is "published" once its entry is no longer the all-ones NaN
   NGB_CUDA(cudaMemsetAsync(out, 0xFF, sizeof(double) * L.npad * L.b, st));
-  if (L.depth <= tri_level_launch_depth && L.npad > tri_small_rows && (int)L.level_start.size() == L.depth + 1) {
+  if (L.depth <= tri_level_launch_depth && L.npad > tri_level_launch_rows && (int)L.level_start.size() == L.depth + 1) {
     // shallow dependency DAG with many rows per level: one plain launch per level (cached gathers, no polling)
     if (!add_self && !write_r) throw Error("tri: unsupported mode");
     if (!add_self && L.nonfree_pad) NGB_CUDA(cudaMemsetAsync(out, 0, sizeof(double) * L.nonfree_pad * L.b, st));
@@ -1241,6 +1242,7 @@ int ngsamg_b200_create(const char *type, const ngsamg_csr *A, const uint8_t *fre
   a.tri_small_rows = (i64)a.flags.num("b200_tri_small_rows", 1000000);
   a.tri_gate_gap_levels = a.flags.num("b200_tri_gate_gap", 0.0);
   a.tri_level_launch_depth = (int)a.flags.num("b200_tri_level_launch_depth", 24);
+  a.tri_level_launch_rows = (i64)a.flags.num("b200_tri_level_launch_rows", 131072);
   a.tri_repoll_ns = (unsigned)a.flags.num("b200_tri_repoll_ns", 0);
   a.tri_regate = (int)a.flags.num("b200_tri_regate", 1);
   a.tri_split = (int)a.flags.num("b200_tri_split", 0);

@@ -346,8 +346,9 @@ def test_golden_fixtures_gpu():
 
 
 @pytest.mark.parametrize("flags", [dict(ngs_amg_b200_tri_small_rows=0), dict(ngs_amg_b200_tri_small_rows=0, ngs_amg_b200_tri_level_launch_depth=0),
-                                   dict(ngs_amg_b200_tri_small_rows=0, ngs_amg_b200_tri_level_launch_depth=1000),
-                                   dict(ngs_amg_b200_tri_small_rows=0, ngs_amg_b200_sm_order="multicolor")])
+                                   dict(ngs_amg_b200_tri_small_rows=0, ngs_amg_b200_tri_level_launch_depth=1000, ngs_amg_b200_tri_level_launch_rows=0),
+                                   dict(ngs_amg_b200_tri_small_rows=0, ngs_amg_b200_tri_level_launch_rows=0, ngs_amg_b200_sm_order="multicolor"),
+                                   dict(ngs_amg_b200_spmv_small_rows=0)])
 def test_sweep_kernel_variants(flags):
     """every implementation of the triangular half-sweep (warp-per-row, sync-free thread-per-row, level-by-level launches)
     forced on the same small problem: V-cycle and PCG must agree with the oracle"""
