@@ -129,6 +129,77 @@ double ngsamg_b200_last_ms(ngsamg_b200_t *h, int what); /* 0 apply, 1 pcg, 2 set
 /* number of kernel launches issued by the library since create (bench.py's gpu_launches) */
 int64_t ngsamg_b200_launch_count(ngsamg_b200_t *h);
 
+/* ---- multi-rank (one rank == one GPU) ---------------------------------------------------------------
+ * The reference runs one MPI rank per subdomain: ParallelDofs lists the DOFs shared with every neighbour rank, the fine
+ * matrix is the rank's sub-assembled (DISTRIBUTED) contribution, and vectors are exchanged through the DCCMap
+ * (src/base/linalg/dcc_map.cpp:76-302, 494-543).  The B200 path keeps that decomposition: one process and one handle per GPU.
+ *
+ * ngsamg_halo  == ParallelDofs::GetDistantProcs() + GetExchangeDofs(p): for neighbour k the shared local DOFs
+ *   ex_dofs[ex_ptr[k] .. ex_ptr[k+1]), ascending, and the k-th DOF shared with rank p here is the k-th DOF shared with this
+ *   rank on p (NGSolve's convention).  peers ascending.
+ * ngsamg_comm  == the communicator.  Setup-phase (host) traffic goes through two caller-supplied callbacks -- an NGSolve
+ *   adapter implements them with its NgMPI_Comm, the test harness with torch.distributed / threads:
+ *     exchange      : post sendbuf[k] (sendbytes[k] bytes) to peers[k] and receive recvbytes[k] bytes from it into recvbuf[k],
+ *                     for all k, then return (MPI_Isend/Irecv + Waitall); sizes are known to both sides.
+ *     allreduce_sum : in-place sum over all ranks of n doubles (every rank receives the result).
+ *   The per-sweep device traffic (DIS2CO / CO2CU halo exchange, CG dot products, coarse-level gather) uses NCCL point-to-point
+ *   over NVLink when `nccl` holds an ncclComm_t (see ngsamg_b200_nccl_*); with nccl == NULL it is staged through host memory
+ *   and the two callbacks (any MPI; also how several ranks share ONE GPU in the parity tests).
+ *   Callbacks return 0 on success. */
+typedef struct ngsamg_halo {
+  int32_t npeers;
+  const int32_t *peers;
+  const int64_t *ex_ptr;   /* npeers + 1 */
+  const int32_t *ex_dofs;
+} ngsamg_halo;
+
+typedef struct ngsamg_comm {
+  int32_t rank, size;
+  void *ctx;
+  int (*exchange)(void *ctx, int32_t npeers, const int32_t *peers, const void *const *sendbuf, const int64_t *sendbytes,
+                  void *const *recvbuf, const int64_t *recvbytes);
+  int (*allreduce_sum)(void *ctx, double *vals, int32_t n);
+  void *nccl; /* ncclComm_t of the same ranks, or NULL */
+} ngsamg_comm;
+
+/* Multi-rank constructor: like ngsamg_b200_create, with A the rank's LOCAL sub-assembled matrix over its local DOFs (shared
+ * interface DOFs are duplicated on every sharer; the global matrix is the sum over the ranks), free_mask / vertex_xyz over the
+ * local DOFs (consistent on shared DOFs).  Replaces BaseAMGPC on a ParallelMatrix (amg_pc.cpp:398-434) + the hybrid smoother
+ * setup (HybridMatrix / HybridGSSmoother, hybrid_matrix.cpp:17-307, gssmoother.cpp:603-700) + CtrMap coarse-level
+ * redistribution (dof_contract.cpp).  finalize / apply / pcg are then COLLECTIVE over the ranks of `comm`:
+ *   apply: b is the rank's DISTRIBUTED rhs, x the CUMULATED result (AMGMatrix::SmoothV amg_matrix.cpp:160-307)
+ *   pcg  : rhs DISTRIBUTED, x CUMULATED; dot products are all-reduced.
+ * `comm` (and the callback context) must stay valid for the life of the handle. */
+int ngsamg_b200_create_parallel(const char *type, const ngsamg_csr *A, const uint8_t *free_mask, const double *vertex_xyz,
+                                const ngsamg_halo *halo, const ngsamg_comm *comm, const char *const *flag_keys,
+                                const char *const *flag_vals, int nflags, int device, ngsamg_b200_t **out);
+
+/* NCCL plumbing for the device data path (the library dlopens libnccl.so.2; no torch types): rank 0 creates the 128-byte
+ * unique id, the host application broadcasts it, every rank calls comm_init with its device.  comm_destroy frees it. */
+int ngsamg_b200_nccl_unique_id(char id[128]);
+int ngsamg_b200_nccl_comm_init(const char id[128], int rank, int size, int device, void **nccl_comm);
+int ngsamg_b200_nccl_comm_destroy(void *nccl_comm);
+
+/* multi-rank introspection (parity tests): sharing information of `level` on this rank (two-call: NULL arrays -> sizes). */
+int ngsamg_b200_get_halo(ngsamg_b200_t *h, int level, int32_t *npeers, int32_t *peers, int64_t *ex_ptr, int32_t *ex_dofs);
+/* which = 0: M, 1: G of the hybrid split of `level` (local numbering of the level), 2: sizes only; mod_diag: n*b*b doubles */
+int ngsamg_b200_get_hybrid(ngsamg_b200_t *h, int level, int which, int64_t *nnz, int64_t *rowptr, int32_t *col, double *val,
+                           double *mod_diag);
+/* number of distributed levels (levels 0 .. npar-1 are smoothed on every rank; level npar is contracted onto rank 0) */
+int ngsamg_b200_num_parallel_levels(ngsamg_b200_t *h);
+/* rank 0 only: the serial hierarchy below the contracted level (borrowed handle; all single-rank entry points work on it) and,
+ * for every rank r, the map local DOF of the contracted level -> DOF of the merged level (CtrMap dof_maps). */
+ngsamg_b200_t *ngsamg_b200_get_contracted(ngsamg_b200_t *h);
+int ngsamg_b200_get_contraction_map(ngsamg_b200_t *h, int rank, int64_t *n, int32_t *map);
+
+/* host-only pieces of the multi-rank setup (no device needed; collective over comm) -- the CPU tests drive them over gloo:
+ * hybrid split + modified diagonal of one level.  Results are fetched with ngsamg_b200_hybrid_host_fetch. */
+typedef struct ngsamg_b200_hybrid_host ngsamg_b200_hybrid_host;
+int ngsamg_b200_hybrid_host_begin(const ngsamg_csr *A, const uint8_t *free_mask, const ngsamg_halo *halo, const ngsamg_comm *comm,
+                                  ngsamg_b200_hybrid_host **out, int64_t *nnz_m, int64_t *nnz_g);
+int ngsamg_b200_hybrid_host_fetch(ngsamg_b200_hybrid_host *m, int64_t *m_rowptr, int32_t *m_col, double *m_val, int64_t *g_rowptr,
+                                  int32_t *g_col, double *g_val, double *mod_diag, int32_t *sweep_rank, uint8_t *master);
+
 /* ---- standalone sparse kernels (setup path) ----------------------------------------------------
  * Galerkin product on the device: Ac = (P^T A) P.   RestrictMatrix<H,W>, utils_sparseMM.hpp:93-109;
  * MatMultABImpl utils_sparseMM.cpp:107-238; TransposeSPMImpl :54-93.

@@ -23,6 +23,9 @@ EXPORTS = [
     "ngsamg_b200_matmul_begin", "ngsamg_b200_transpose_begin", "ngsamg_b200_spm_fetch",
     "ngsamg_b200_coarsen_begin", "ngsamg_b200_coarsen_fetch", "ngsamg_b200_profile_kernel",
     "ngsamg_b200_get_sweep_order",
+    "ngsamg_b200_create_parallel", "ngsamg_b200_nccl_unique_id", "ngsamg_b200_nccl_comm_init", "ngsamg_b200_nccl_comm_destroy",
+    "ngsamg_b200_get_halo", "ngsamg_b200_get_hybrid", "ngsamg_b200_num_parallel_levels", "ngsamg_b200_get_contracted",
+    "ngsamg_b200_get_contraction_map", "ngsamg_b200_hybrid_host_begin", "ngsamg_b200_hybrid_host_fetch",
 ]
 
 
@@ -95,6 +98,20 @@ def lib():
     L.ngsamg_b200_coarsen_fetch.argtypes = [vp, vp, vp, vp, vp, vp]
     L.ngsamg_b200_get_sweep_order.argtypes = [vp, ci, vp]
     L.ngsamg_b200_profile_kernel.argtypes = [vp, ci, ci, ci, C.POINTER(dbl), C.POINTER(dbl)]
+    # multi-rank
+    L.ngsamg_b200_create_parallel.argtypes = [C.c_char_p, C.POINTER(Csr), vp, vp, vp, vp, C.POINTER(C.c_char_p), C.POINTER(C.c_char_p),
+                                              ci, ci, C.POINTER(vp)]
+    L.ngsamg_b200_nccl_unique_id.argtypes = [vp]
+    L.ngsamg_b200_nccl_comm_init.argtypes = [vp, ci, ci, ci, C.POINTER(vp)]
+    L.ngsamg_b200_nccl_comm_destroy.argtypes = [vp]
+    L.ngsamg_b200_get_halo.argtypes = [vp, ci, vp, vp, vp, vp]
+    L.ngsamg_b200_get_hybrid.argtypes = [vp, ci, ci, vp, vp, vp, vp, vp]
+    L.ngsamg_b200_num_parallel_levels.argtypes = [vp]
+    L.ngsamg_b200_get_contracted.argtypes = [vp]
+    L.ngsamg_b200_get_contracted.restype = vp
+    L.ngsamg_b200_get_contraction_map.argtypes = [vp, ci, vp, vp]
+    L.ngsamg_b200_hybrid_host_begin.argtypes = [C.POINTER(Csr), vp, vp, vp, C.POINTER(vp), C.POINTER(i64), C.POINTER(i64)]
+    L.ngsamg_b200_hybrid_host_fetch.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]
     _lib = L
     return L
 

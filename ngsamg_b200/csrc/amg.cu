@@ -5,9 +5,13 @@
 #include <chrono>
 #include <memory>
 
+#include <dlfcn.h>
+#include <nccl.h>   // types only: the library is dlopen'ed (libnccl.so.2), nothing links against it
+
 #include "../../include/ngsamg_b200.h"
 #include "device.hpp"
 #include "kernels.cuh"
+#include "par.hpp"
 
 namespace ngb {
 
@@ -65,7 +69,63 @@ struct Level {
   double omega = 1.0;
   std::vector<double> xyz;
   int *d_err = nullptr;
+  // ---- multi-rank (hybrid) level: smoothing runs on M = master x master block, G is applied additively
+  bool par = false;
+  ParDofs pd;
+  HostBsr hM, hG;                  // hybrid split in the level's local numbering (kept for introspection on small levels)
+  std::vector<double> mod_diag;    // replacement diagonal of the hybrid smoother (AoS, local numbering)
+  std::vector<uint8_t> gs_mask;    // rows smoothed on this rank: master & free
+  Sell G;
+  i64 nnz_m = 0, nnz_g = 0;
+  // DCC halo lists (level-scheduled numbering), flattened per neighbour
+  std::vector<i32> peers;
+  std::vector<i64> m_off, g_off;   // npeers + 1 offsets (dofs) into the flattened lists / exchange buffers
+  i32 *d_m_idx = nullptr, *d_g_idx = nullptr, *d_mu_dof = nullptr;
+  i64 *d_mu_ptr = nullptr, *d_mu_pos = nullptr;
+  i64 n_mu = 0;
+  double *sendbuf = nullptr, *recvbuf = nullptr, *h_send = nullptr, *h_recv = nullptr;
+  const std::vector<uint8_t> &mask() const { return par ? gs_mask : free_mask; }
 };
+
+// libnccl.so.2 entry points, resolved at run time
+struct NcclApi {
+  ncclResult_t (*GetUniqueId)(ncclUniqueId *) = nullptr;
+  ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
+  ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  ncclResult_t (*Send)(const void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*Recv)(void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*GroupStart)() = nullptr;
+  ncclResult_t (*GroupEnd)() = nullptr;
+  const char *(*GetErrorString)(ncclResult_t) = nullptr;
+};
+NcclApi &nccl_api()
+{
+  static NcclApi api;
+  static bool loaded = false;
+  if (loaded) return api;
+  void *h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD | RTLD_GLOBAL);   // the copy the host application already loaded, if any
+  if (!h) h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+  if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+  if (!h) throw Error(std::string("cannot load libnccl.so.2: ") + dlerror());
+  auto sym = [&](const char *n) { void *f = dlsym(h, n); if (!f) throw Error(std::string("libnccl: missing symbol ") + n); return f; };
+  api.GetUniqueId = (decltype(api.GetUniqueId))sym("ncclGetUniqueId");
+  api.CommInitRank = (decltype(api.CommInitRank))sym("ncclCommInitRank");
+  api.CommDestroy = (decltype(api.CommDestroy))sym("ncclCommDestroy");
+  api.Send = (decltype(api.Send))sym("ncclSend");
+  api.Recv = (decltype(api.Recv))sym("ncclRecv");
+  api.AllReduce = (decltype(api.AllReduce))sym("ncclAllReduce");
+  api.GroupStart = (decltype(api.GroupStart))sym("ncclGroupStart");
+  api.GroupEnd = (decltype(api.GroupEnd))sym("ncclGroupEnd");
+  api.GetErrorString = (decltype(api.GetErrorString))sym("ncclGetErrorString");
+  loaded = true;
+  return api;
+}
+#define NGB_NCCL(call)                                                                                                   \
+  do {                                                                                                                   \
+    ncclResult_t r__ = (call);                                                                                           \
+    if (r__ != ncclSuccess) throw ::ngb::Error(std::string("NCCL error: ") + nccl_api().GetErrorString(r__) + " (" #call ")"); \
+  } while (0)
 
 }  // namespace
 
@@ -107,6 +167,26 @@ struct Amg {
   unsigned long long *tri_trace = nullptr;  // debug tracing of the sync-free sweep (NGSAMG_B200_TRACE_FILE)
   int *d_err = nullptr;
   void check_watchdog();
+  // ---- multi-rank
+  bool par = false;
+  bool owns_stream = true;
+  Comm comm;
+  ncclComm_t nccl = nullptr;
+  int npar = 0;                       // levels 0..npar-1 are distributed (hybrid smoothers), level npar is contracted onto rank 0
+  std::unique_ptr<Amg> nested;        // rank 0: the serial hierarchy below the contracted level
+  Contraction ctr;                    // rank 0: dof maps of the contraction
+  std::vector<i32 *> d_ctr_map;       // rank 0: device copies of ctr.dof_maps
+  std::vector<i64> ctr_off;           // rank 0: offsets (doubles) of the ranks' segments in the gather buffers
+  double *ctr_buf = nullptr, *h_ctr = nullptr;
+  i64 exchanges = 0;
+  void finalize_parallel();
+  void build_halo(Level &L);
+  void dev_exchange(const std::vector<i32> &peers, const double *sendbuf, const std::vector<i64> &soff, double *recvbuf,
+                    const std::vector<i64> &roff, double *h_send, double *h_recv);
+  void dis2co(Level &L, double *v);   // DCCMap::StartDIS2CO + ApplyDIS2CO: ghost values travel to the master and are added there
+  void co2cu(Level &L, double *v);    // DCCMap::StartCO2CU + ApplyCO2CU: master values overwrite the ghosts
+  void contracted_solve(Level &L);
+  void allreduce_scalars(double *h, int n);
 
   ~Amg();
   void finalize();
@@ -450,6 +530,11 @@ Amg::~Amg()
   if (device >= 0) cudaSetDevice(device);
   for (auto &lp : lev) {
     Level &L = *lp;
+    L.G.release();
+    dev_free(L.d_m_idx); dev_free(L.d_g_idx); dev_free(L.d_mu_dof); dev_free(L.d_mu_ptr); dev_free(L.d_mu_pos);
+    dev_free(L.sendbuf); dev_free(L.recvbuf);
+    if (L.h_send) cudaFreeHost(L.h_send);
+    if (L.h_recv) cudaFreeHost(L.h_recv);
     dev_free(L.d_perm); dev_free(L.d_freep); dev_free(L.d_pt_rowmap); dev_free(L.d_bnd_fwd); dev_free(L.d_bnd_bwd);
     L.L.release(); L.U.release(); L.N.release(); L.P.release(); L.PT.release();
     dev_free(L.diag); dev_free(L.dinv);
@@ -462,7 +547,11 @@ Amg::~Amg()
   if (vgraph) cudaGraphExecDestroy(vgraph);
   if (ev0) cudaEventDestroy(ev0);
   if (ev1) cudaEventDestroy(ev1);
-  if (st) cudaStreamDestroy(st);
+  for (auto &m : d_ctr_map) dev_free(m);
+  dev_free(ctr_buf);
+  if (h_ctr) cudaFreeHost(h_ctr);
+  nested.reset();
+  if (st && owns_stream) cudaStreamDestroy(st);
 }
 
 void Amg::alloc_vectors(Level &L)
@@ -484,7 +573,7 @@ void Amg::build_level_layout(Level &L, const DevCsr &dA)
   // permuted free flags (padding rows = not free)
   {
     std::vector<uint8_t> fp(L.npad, 0);
-    for (i64 i = 0; i < n; i++) fp[L.perm[i]] = L.free_mask.empty() ? 1 : L.free_mask[i];
+    for (i64 i = 0; i < n; i++) fp[L.perm[i]] = L.mask().empty() ? 1 : L.mask()[i];
     L.d_freep = upload_vec(fp, st);
   }
   i32 *len1 = dev_alloc<i32>(L.npad), *len2 = dev_alloc<i32>(L.npad);
@@ -542,9 +631,20 @@ void Amg::build_level_layout(Level &L, const DevCsr &dA)
     L.pre_l = force ? force : pick(L.L);
     L.pre_u = force ? force : pick(L.U);
   }
-  // dinv (GSS3::CalcDiags)
+  // dinv (GSS3::CalcDiags); the hybrid smoother passes a replacement diagonal (GSS3(A, repl_diag, ...), gssmoother.cpp:93-107)
   int *d_err = dev_alloc<int>(1);
   NGB_CUDA(cudaMemsetAsync(d_err, 0, sizeof(int), st));
+  double *true_diag = L.diag, *md_planar = nullptr;
+  if (L.par && !L.mod_diag.empty()) {
+    double *aos = upload_vec(L.mod_diag, st);
+    md_planar = dev_alloc<double>((size_t)L.npad * bs);
+    NGB_CUDA(cudaMemsetAsync(md_planar, 0, sizeof(double) * L.npad * bs, st));
+    k_aos_perm_to_planar<<<nblk(n), TB, 0, st>>>(n, bs, L.d_perm, aos, md_planar);
+    NGB_CUDA(cudaStreamSynchronize(st));
+    dev_free(aos);
+    L.diag = md_planar;   // only while the inverses are computed
+  }
+  struct Restore { Level &L; double *t; double *&m; ~Restore() { L.diag = t; dev_free(m); } } restore{L, true_diag, md_planar};
   if (!L.pinv || L.sm_type == SM_JACOBI) {
     switch (b) {
       case 1: k_calc_dinv<1><<<nblk(L.npad), TB, 0, st>>>(L.npad, L.diag, L.d_freep, L.dinv, d_err); break;
@@ -676,6 +776,7 @@ void Amg::build_coarse_inverse(Level &L)
 void Amg::finalize()
 {
   if (finalized) throw Error("finalize called twice");
+  if (par) { finalize_parallel(); return; }
   auto t0 = std::chrono::steady_clock::now();
   double host_s = 0, rap_ms = 0;
   const bool verbose = flags.str("log_level", "none") != "none";   // factory log levels, base_factory.cpp:83-199
@@ -785,7 +886,7 @@ void Amg::finalize()
         int ncol = 0;
         greedy_coloring_perm(L.hA, L.sweep_rank, ncol);
       }
-      level_schedule(L.hA, L.free_mask, !coarsest, L, st);
+      level_schedule(L.hA, L.mask(), !coarsest, L, st);
       L.d_err = d_err;
       host_s += tick(h0);
       if (verbose) std::fprintf(stderr, "[ngsamg_b200] level %d: level schedule %.2f s (depth %d)\n", l, tick(h0), L.depth);
@@ -804,6 +905,390 @@ void Amg::finalize()
   // host copies of big matrices are dropped (introspection then only reports sizes)
   for (auto &lp : lev)
     if ((double)lp->hA.nnz() * lp->hA.bs() > flags.num("keep_host_nnz", 4e8)) { lp->keep_host = false; HostBsr().rowptr.swap(lp->hA.rowptr); std::vector<i32>().swap(lp->hA.col); std::vector<double>().swap(lp->hA.val); }
+  d_dot = dev_alloc<double>(4);
+  d_partial = dev_alloc<double>(DOT_BLOCKS);
+  NGB_CUDA(cudaStreamSynchronize(st));
+  finalized = true;
+  ms_setup = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+  ms_rap = rap_ms;
+  ms_host = host_s * 1e3;
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// multi-rank setup.  Per distributed level: assembled local matrix -> class-respecting coarsening (purely local P, identical
+// rows on all sharers) -> local Galerkin product on the device (the coarse matrix is again a distributed sum) -> hybrid
+// split M/G + modified diagonal -> the single-rank layout machinery on M with the hybrid stage order as sweep order.
+// When the global size falls below ngs_amg_b200_ctr_nv (or max_levels is hit) the level is contracted onto rank 0, which
+// continues with a serial hierarchy (CtrMap, dof_contract.cpp; the reference's redistribution policy base_factory.cpp:573-682
+// is replaced by this one threshold -- on one NVSwitch box 8 -> 1 is the only step worth taking).
+// ------------------------------------------------------------------------------------------------
+namespace {
+void build_plain_sell(const HostBsr &H, const i32 *d_rperm, const i32 *d_cperm, i64 nrows_pad, Sell &S, cudaStream_t st, i64 *launches)
+{
+  DevCsr d;
+  dev_csr_upload(H, d, st);
+  i32 *len = dev_alloc<i32>(nrows_pad);
+  NGB_CUDA(cudaMemsetAsync(len, 0, sizeof(i32) * nrows_pad, st));
+  if (H.nrows) k_layout_count<<<nblk(H.nrows), TB, 0, st>>>(H.nrows, d.rowptr, d.col, d_rperm, d_cperm, 0, len, nullptr, 0, nullptr);
+  build_sell(nrows_pad, H.bh, H.bw, len, S, st, launches);
+  if (H.nrows) k_layout_fill<<<nblk(H.nrows), TB, 0, st>>>(H.nrows, H.bh * H.bw, d.rowptr, d.col, d.val, d_rperm, d_cperm, 0, S.slice_ptr, S.col, S.val,
+                                                          nullptr, nullptr, nullptr, nullptr, 0, nullptr, nullptr, nullptr);
+  S.nnz = H.nnz();
+  NGB_CUDA(cudaStreamSynchronize(st));
+  dev_free(len);
+  dev_csr_free(d);
+}
+}  // namespace
+
+void Amg::build_halo(Level &L)
+{
+  const ParDofs &pd = L.pd;
+  const size_t np = pd.peers.size();
+  L.peers = pd.peers;
+  L.m_off.assign(np + 1, 0);
+  L.g_off.assign(np + 1, 0);
+  std::vector<i32> mi, gi;
+  for (size_t kp = 0; kp < np; kp++) {
+    for (i32 d : pd.m_ex[kp]) mi.push_back(L.perm[d]);
+    for (i32 d : pd.g_ex[kp]) gi.push_back(L.perm[d]);
+    L.m_off[kp + 1] = (i64)mi.size();
+    L.g_off[kp + 1] = (i64)gi.size();
+  }
+  // master side of DIS2CO: per distinct master dof the buffer positions that are added to it, neighbours ascending
+  std::vector<std::pair<i32, i64>> pr;
+  for (i64 k = 0; k < (i64)mi.size(); k++) pr.emplace_back(mi[k], k);
+  std::sort(pr.begin(), pr.end());
+  std::vector<i32> mu;
+  std::vector<i64> mptr{0}, mpos;
+  for (size_t q = 0; q < pr.size(); q++) {
+    if (q == 0 || pr[q].first != pr[q - 1].first) { if (q) mptr.push_back((i64)mpos.size()); mu.push_back(pr[q].first); }
+    mpos.push_back(pr[q].second);
+  }
+  if (!pr.empty()) mptr.push_back((i64)mpos.size());
+  L.n_mu = (i64)mu.size();
+  L.d_m_idx = upload_vec(mi, st);
+  L.d_g_idx = upload_vec(gi, st);
+  L.d_mu_dof = upload_vec(mu, st);
+  L.d_mu_ptr = upload_vec(mptr, st);
+  L.d_mu_pos = upload_vec(mpos, st);
+  const size_t cap = (size_t)std::max<i64>(std::max(L.m_off[np], L.g_off[np]), 1) * L.b;
+  L.sendbuf = dev_alloc<double>(cap);
+  L.recvbuf = dev_alloc<double>(cap);
+  if (!nccl) {
+    NGB_CUDA(cudaMallocHost((void **)&L.h_send, sizeof(double) * cap));
+    NGB_CUDA(cudaMallocHost((void **)&L.h_recv, sizeof(double) * cap));
+  }
+}
+
+// One neighbour exchange of doubles on the library stream.  NCCL point-to-point (NVLink) when a communicator was given, else
+// staged through pinned host memory and the caller's exchange callback.
+void Amg::dev_exchange(const std::vector<i32> &peers, const double *sendbuf, const std::vector<i64> &soff, double *recvbuf,
+                       const std::vector<i64> &roff, double *h_send, double *h_recv)
+{
+  const size_t np = peers.size();
+  exchanges++;
+  if (nccl) {
+    if (np == 0) return;
+    NcclApi &api = nccl_api();
+    NGB_NCCL(api.GroupStart());
+    for (size_t k = 0; k < np; k++) {
+      const i64 sc = soff[k + 1] - soff[k], rc = roff[k + 1] - roff[k];
+      if (sc > 0) NGB_NCCL(api.Send(sendbuf + soff[k], (size_t)sc, ncclDouble, peers[k], nccl, st));
+      if (rc > 0) NGB_NCCL(api.Recv(recvbuf + roff[k], (size_t)rc, ncclDouble, peers[k], nccl, st));
+    }
+    NGB_NCCL(api.GroupEnd());
+    return;
+  }
+  std::vector<i32> ap;
+  std::vector<const void *> sp;
+  std::vector<void *> rp;
+  std::vector<i64> sb, rb;
+  if (np && soff[np] > 0) NGB_CUDA(cudaMemcpyAsync(h_send, sendbuf, sizeof(double) * soff[np], cudaMemcpyDeviceToHost, st));
+  NGB_CUDA(cudaStreamSynchronize(st));
+  for (size_t k = 0; k < np; k++) {
+    const i64 sc = soff[k + 1] - soff[k], rc = roff[k + 1] - roff[k];
+    if (sc == 0 && rc == 0) continue;
+    ap.push_back(peers[k]);
+    sp.push_back(h_send + soff[k]); sb.push_back(sc * (i64)sizeof(double));
+    rp.push_back(h_recv + roff[k]); rb.push_back(rc * (i64)sizeof(double));
+  }
+  comm.exchange_fixed(ap, sp, sb, rp, rb);
+  if (np && roff[np] > 0) NGB_CUDA(cudaMemcpyAsync(recvbuf, h_recv, sizeof(double) * roff[np], cudaMemcpyHostToDevice, st));
+}
+
+static std::vector<i64> scaled(const std::vector<i64> &off, int b)
+{
+  std::vector<i64> r(off);
+  for (auto &x : r) x *= b;
+  return r;
+}
+
+void Amg::dis2co(Level &L, double *v)
+{
+  const size_t np = L.peers.size();
+  if (np == 0) { exchanges++; if (!nccl) NGB_CUDA(cudaStreamSynchronize(st)); return; }
+  const i64 ng = L.g_off[np], nm = L.m_off[np];
+  if (ng) { k_halo_pack<<<nblk(ng * L.b), TB, 0, st>>>(ng, L.b, L.d_g_idx, v, L.sendbuf, 1); launches++; }
+  dev_exchange(L.peers, L.sendbuf, scaled(L.g_off, L.b), L.recvbuf, scaled(L.m_off, L.b), L.h_send, L.h_recv);
+  if (nm) { k_halo_add<<<nblk(L.n_mu * L.b), TB, 0, st>>>(L.n_mu, L.b, L.d_mu_dof, L.d_mu_ptr, L.d_mu_pos, L.recvbuf, v); launches++; }
+}
+
+void Amg::co2cu(Level &L, double *v)
+{
+  const size_t np = L.peers.size();
+  if (np == 0) { exchanges++; if (!nccl) NGB_CUDA(cudaStreamSynchronize(st)); return; }
+  const i64 ng = L.g_off[np], nm = L.m_off[np];
+  if (nm) { k_halo_pack<<<nblk(nm * L.b), TB, 0, st>>>(nm, L.b, L.d_m_idx, v, L.sendbuf, 0); launches++; }
+  dev_exchange(L.peers, L.sendbuf, scaled(L.m_off, L.b), L.recvbuf, scaled(L.g_off, L.b), L.h_send, L.h_recv);
+  if (ng) { k_halo_set<<<nblk(ng * L.b), TB, 0, st>>>(ng, L.b, L.d_g_idx, L.recvbuf, v); launches++; }
+}
+
+void Amg::allreduce_scalars(double *h, int n)
+{
+  if (!par) return;
+  comm.allreduce_sum(h, n);
+}
+
+// Level npar: CtrMap::TransferF2C (members send their local DISTRIBUTED vector to the group master, which adds them through
+// the dof maps), the serial V-cycle of the contracted hierarchy on rank 0, CtrMap::TransferC2F (the master sends every member
+// its CUMULATED values back)   -- dof_contract.cpp:49-228.
+void Amg::contracted_solve(Level &L)
+{
+  const int R = comm.size(), me = comm.rank();
+  const i64 nl = L.n * L.b;
+  if (me != 0) {
+    std::vector<i32> p0{0};
+    std::vector<i64> so{0, nl}, ro{0, 0};
+    dev_exchange(p0, L.rhs, so, ctr_buf, ro, h_ctr, h_ctr);
+    std::vector<i64> so2{0, 0}, ro2{0, nl};
+    dev_exchange(p0, ctr_buf, so2, L.x, ro2, h_ctr, h_ctr);
+    L.result = L.x;
+    return;
+  }
+  std::vector<i32> others;
+  for (int r = 1; r < R; r++) others.push_back(r);
+  std::vector<i64> zero(R, 0), off(ctr_off.begin() + 1, ctr_off.end());   // segments of ranks 1..R-1 (rank 0 is local)
+  for (auto &x : off) x -= ctr_off[1];
+  dev_exchange(others, ctr_buf, zero, ctr_buf, off, h_ctr, h_ctr);
+  Level &N0 = *nested->lev[0];
+  NGB_CUDA(cudaMemsetAsync(N0.rhs, 0, sizeof(double) * N0.npad * N0.b, st));
+  for (int r = 0; r < R; r++) {
+    const i64 nr = ctr.n_local[r];
+    if (!nr) continue;
+    const double *src = (r == 0) ? L.rhs : ctr_buf + (ctr_off[r] - ctr_off[1]);
+    k_ctr_scatter_add<<<nblk(nr * L.b), TB, 0, st>>>(nr, L.b, d_ctr_map[r], N0.d_perm, src, N0.rhs);
+    launches++;
+  }
+  nested->vcycle();
+  for (int r = 0; r < R; r++) {
+    const i64 nr = ctr.n_local[r];
+    if (!nr) continue;
+    double *dst = (r == 0) ? L.x : ctr_buf + (ctr_off[r] - ctr_off[1]);
+    k_ctr_gather<<<nblk(nr * L.b), TB, 0, st>>>(nr, L.b, d_ctr_map[r], N0.d_perm, N0.result, dst);
+    launches++;
+  }
+  dev_exchange(others, ctr_buf, off, ctr_buf, zero, h_ctr, h_ctr);
+  L.result = L.x;
+}
+
+void Amg::finalize_parallel()
+{
+  auto t0 = std::chrono::steady_clock::now();
+  double host_s = 0, rap_ms = 0;
+  auto tick = [](std::chrono::steady_clock::time_point t) { return std::chrono::duration<double>(std::chrono::steady_clock::now() - t).count(); };
+  const bool verbose = flags.str("log_level", "none") != "none";
+  const int me = comm.rank(), R = comm.size();
+  const int max_levels = (int)flags.num("max_levels", 10);
+  const std::string cycle = flags.str("mg_cycle", "V");
+  if (cycle != "V" && cycle != "v") throw Error("mg_cycle=" + cycle + " is not supported by the B200 path (V only)");
+  const bool elast = type.find("elast") != std::string::npos;
+  const int dim = (type.find("2d") != std::string::npos) ? 2 : 3;
+  const bool regularize = flags.flag("regularize_cmats", elast);
+  const i64 ctr_nv = (i64)flags.num("b200_ctr_nv", 1000000);   // contract onto rank 0 once the GLOBAL level has at most this many vertices
+  CoarsenOptions copt;
+  copt.max_per_row = (int)flags.num("sp_max_per_row", elast ? 1 + dim : 3);
+  copt.min_frac = flags.num("sp_min_frac", dim == 3 ? 0.08 : 0.1);
+  copt.omega = flags.num("sp_omega", 1.0);
+  copt.smooth = flags.str("prol_type", "semi_aux_smoothed") != "piecewise";
+  copt.rounds = (int)flags.num("spw_rounds", 3);
+  use_graph = flags.flag("b200_cuda_graph_par", false) && nccl;   // halo exchanges inside a captured graph: opt-in
+
+  d_err = dev_alloc<int>(1);
+  NGB_CUDA(cudaMemsetAsync(d_err, 0, sizeof(int), st));
+  DevCsr dA;
+  dev_csr_upload(lev[0]->hA, dA, st);
+  bool force_contract = false;
+  for (int l = 0;; l++) {
+    Level &L = *lev[l];
+    L.n = L.hA.nrows; L.b = L.hA.bh; L.nnz = L.hA.nnz();
+    L.par = true;
+    const ParDofs &pd = L.pd;
+    i64 nmaster = 0;
+    for (i64 d = 0; d < L.n; d++) nmaster += pd.master_of[d] < 0 ? 1 : 0;
+    const i64 nglobal = comm.allreduce_sum(nmaster);
+    const bool contract = force_contract || (l > 0 && nglobal <= ctr_nv) || (l + 1 >= max_levels) || R == 1;
+    if (verbose) std::fprintf(stderr, "[ngsamg_b200 r%d] level %d: n_local=%lld n_global=%lld%s\n", me, l, (long long)L.n, (long long)nglobal, contract ? "  -> contracted onto rank 0" : "");
+    if (contract) {
+      // ---- contraction: rank 0 receives the level, everybody keeps a stub level holding its local vectors
+      auto h0 = std::chrono::steady_clock::now();
+      contract_to_root(comm, pd, L.hA, L.free_mask, L.xyz, ctr);
+      host_s += tick(h0);
+      dev_csr_free(dA);
+      L.par = false;
+      L.npad = std::max<i64>(round32(L.n), 32);
+      L.perm.resize(L.n);
+      for (i64 i = 0; i < L.n; i++) L.perm[i] = (i32)i;
+      L.d_perm = upload_vec(L.perm, st);
+      L.depth = 0;
+      alloc_vectors(L);
+      lev.resize(l + 1);
+      npar = l;
+      std::vector<double> sizes(R, 0.0);
+      sizes[me] = (double)(L.n * L.b);
+      comm.allreduce_sum(sizes.data(), R);
+      ctr_off.assign(R + 1, 0);
+      for (int r = 0; r < R; r++) ctr_off[r + 1] = ctr_off[r] + (i64)sizes[r];
+      const size_t cap = (size_t)std::max<i64>(me == 0 ? ctr_off[R] - ctr_off[1] : L.n * L.b, 1);
+      ctr_buf = dev_alloc<double>(cap);
+      if (!nccl) NGB_CUDA(cudaMallocHost((void **)&h_ctr, sizeof(double) * cap));
+      if (me == 0) {
+        ctr.n_local.resize(R);
+        for (int r = 0; r < R; r++) { d_ctr_map.push_back(upload_vec(ctr.dof_maps[r], st)); }
+        nested = std::make_unique<Amg>();
+        Amg &N = *nested;
+        N.type = type; N.device = device; N.flags = flags;
+        N.flags.set("max_levels", std::to_string(std::max(1, max_levels - l)));
+        N.st = st; N.owns_stream = false;
+        NGB_CUDA(cudaEventCreate(&N.ev0));
+        NGB_CUDA(cudaEventCreate(&N.ev1));
+        N.num_sms = num_sms; N.use_graph = flags.flag("b200_cuda_graph", true) && !use_graph;
+        N.tri_sleep_ns = tri_sleep_ns; N.tri_ctas_per_sm = tri_ctas_per_sm; N.tri_prepoll = tri_prepoll; N.tri_gate_all = tri_gate_all;
+        N.tri_small_rows = tri_small_rows; N.tri_gate_gap_levels = tri_gate_gap_levels; N.tri_level_launch_depth = tri_level_launch_depth;
+        N.tri_level_launch_rows = tri_level_launch_rows; N.tri_repoll_ns = tri_repoll_ns; N.tri_regate = tri_regate; N.tri_split = tri_split;
+        auto NL = std::make_unique<Level>();
+        NL->hA = std::move(ctr.A);
+        NL->free_mask = ctr.free_mask;
+        bool all = true;
+        for (auto f : NL->free_mask) all &= (f != 0);
+        if (all) NL->free_mask.clear();
+        NL->xyz = ctr.xyz;
+        N.lev.push_back(std::move(NL));
+        N.finalize();
+        launches += N.launches;
+        rap_ms += N.ms_rap;
+        host_s += N.ms_host * 1e-3;
+      }
+      break;
+    }
+    // ---- distributed level
+    auto h0 = std::chrono::steady_clock::now();
+    HostBsr Acum;
+    cumulate_matrix(comm, pd, L.hA, Acum);
+    std::vector<double> rowsum;
+    assembled_row_sums(comm, pd, L.hA, rowsum);
+    int bc = L.b;
+    if (elast && l == 0 && L.b == dim) bc = (dim == 3) ? 6 : 3;
+    std::vector<i32> vmap;
+    std::vector<double> cxyz;
+    ParCoarsen pc;
+    pc.pd = &pd; pc.rowsum = &rowsum; pc.rank = me;
+    build_prolongation(Acum, L.free_mask.empty() ? nullptr : L.free_mask.data(), bc, L.xyz, copt, L.hP, vmap, cxyz, &pc);
+    {
+      // coarsening stalled anywhere?  then contract this level instead (collective decision)
+      i64 ncm = 0;
+      std::vector<uint8_t> seen(L.hP.ncols, 0);
+      for (i64 v = 0; v < L.n; v++) if (vmap[v] >= 0 && pd.master_of[v] < 0 && !seen[vmap[v]]) { seen[vmap[v]] = 1; ncm++; }
+      const i64 ncg = comm.allreduce_sum(ncm);
+      if (ncg == 0 || (double)ncg > 0.8 * (double)nglobal) { force_contract = true; l--; host_s += tick(h0); continue; }
+    }
+    auto nl = std::make_unique<Level>();
+    nl->xyz = std::move(cxyz);
+    coarse_pardofs(pd, vmap, L.hP.ncols, nl->pd, me);
+    lev.push_back(std::move(nl));
+    Level &C = *lev[l + 1];
+    // hybrid split + modified diagonal + stage order
+    hybrid_split(pd, L.hA, Acum, L.hM, L.hG);
+    hybrid_mod_diag(comm, pd, Acum, L.hG, L.free_mask.empty() ? nullptr : L.free_mask.data(), L.mod_diag);
+    hybrid_sweep_order(pd, L.free_mask.empty() ? nullptr : L.free_mask.data(), L.sweep_rank, L.gs_mask, nullptr);
+    L.nnz_m = L.hM.nnz(); L.nnz_g = L.hG.nnz();
+    HostBsr().rowptr.swap(Acum.rowptr); std::vector<i32>().swap(Acum.col); std::vector<double>().swap(Acum.val);
+    host_s += tick(h0);
+    {
+      const std::string smt = flags.spec("sm_type", l, "gs");
+      if (smt != "gs") throw Error("multi-rank levels support sm_type=gs only (BuildJacobiSmoother throws in parallel, amg_pc.cpp:1220-1223)");
+      L.sm_type = SM_GS;
+      L.sm_steps = std::max(1, std::atoi(flags.spec("sm_steps", l, "1").c_str()));
+      const std::string sy = flags.spec("sm_symm", l, "0");
+      L.sm_symm = (sy == "1" || sy == "True" || sy == "true");
+      L.omega = 1.0;
+      L.pinv = regularize;
+    }
+    // Galerkin product of the DISTRIBUTED local matrix: A_{l+1}^loc = P^T A_l^loc P (P rows are identical on all sharers)
+    DevCsr dAc;
+    {
+      cudaEventRecord(ev0, st);
+      HostBsr PT;
+      host_transpose(L.hP, PT);
+      DevCsr dP, dPT, dPTA;
+      dev_csr_upload(L.hP, dP, st);
+      dev_csr_upload(PT, dPT, st);
+      dev_spgemm(dPT, dA, dPTA, st, &launches);
+      dev_spgemm(dPTA, dP, dAc, st, &launches);
+      dev_csr_free(dPTA); dev_csr_free(dP); dev_csr_free(dPT);
+      cudaEventRecord(ev1, st);
+      cudaEventSynchronize(ev1);
+      float ms = 0;
+      cudaEventElapsedTime(&ms, ev0, ev1);
+      rap_ms += ms;
+      L.nc = L.hP.ncols; L.bc = L.hP.bw;
+      dev_csr_download(dAc, C.hA, st, true);
+    }
+    if (flags.flag("b200_color_coarse", true) && C.hA.nrows > 0) {
+      // local renumbering of the coarse level (colour-major, see the single-rank path); the sharing lists follow
+      auto h1 = std::chrono::steady_clock::now();
+      std::vector<i32> cperm;
+      int ncol = 0;
+      greedy_coloring_perm(C.hA, cperm, ncol);
+      permute_symmetric(C.hA, cperm);
+      renumber_columns(L.hP, cperm);
+      permute_pardofs(C.pd, cperm);
+      if (!C.xyz.empty()) {
+        std::vector<double> nx(C.xyz.size());
+        for (i64 i = 0; i < L.nc; i++) for (int k = 0; k < 3; k++) nx[(i64)cperm[i] * 3 + k] = C.xyz[i * 3 + k];
+        C.xyz.swap(nx);
+      }
+      dev_csr_free(dAc);
+      dev_csr_upload(C.hA, dAc, st);
+      host_s += tick(h1);
+    }
+    {
+      auto h1 = std::chrono::steady_clock::now();
+      level_schedule(L.hM, L.gs_mask, true, L, st);
+      L.d_err = d_err;
+      host_s += tick(h1);
+      if (verbose) std::fprintf(stderr, "[ngsamg_b200 r%d] level %d: hybrid level, nnz(M)=%lld nnz(G)=%lld, sweep depth %d\n", me, l, (long long)L.nnz_m, (long long)L.nnz_g, L.depth);
+    }
+    {
+      DevCsr dM;
+      dev_csr_upload(L.hM, dM, st);
+      build_level_layout(L, dM);
+      dev_csr_free(dM);
+    }
+    build_plain_sell(L.hG, L.d_perm, L.d_perm, L.npad, L.G, st, &launches);
+    build_halo(L);
+    alloc_vectors(L);
+    dev_csr_free(dA);
+    dA = dAc;
+  }
+  for (int l = 0; l < npar; l++) build_transfer_layout(*lev[l], *lev[l + 1]);
+  for (auto &lp : lev) {
+    const bool big = (double)lp->hA.nnz() * lp->hA.bs() > flags.num("keep_host_nnz", 4e8);
+    if (big) {
+      lp->keep_host = false;
+      for (HostBsr *m : {&lp->hA, &lp->hM, &lp->hG}) { HostBsr().rowptr.swap(m->rowptr); std::vector<i32>().swap(m->col); std::vector<double>().swap(m->val); }
+    }
+  }
   d_dot = dev_alloc<double>(4);
   d_partial = dev_alloc<double>(DOT_BLOCKS);
   NGB_CUDA(cudaStreamSynchronize(st));
@@ -1023,6 +1508,37 @@ void Amg::level_smooth(Level &L, double *x, const double *b, double *res, bool r
 // AMGMatrix::SmoothV (amg_matrix.cpp:160-307), single rank: Distribute/Cumulate are no-ops.
 void Amg::vcycle_record()
 {
+  if (par) {
+    // AMGMatrix::SmoothV on a distributed hierarchy; the smoother calls are HybridBaseSmoother::SmoothImplRES / SmoothImplRHS
+    // (hybrid_base_smoother.cpp:294-446) with CallStageKernelsImpl's stage order folded into the sweep order of M:
+    //   pre : res = b (DISTRIBUTED) ; DIS2CO(res) ; forward sweep on M (x = 0) ; CO2CU(x) ; res -= G x ; restrict
+    //   post: x += P x_c ; t = b - G x ; DIS2CO(t) ; backward sweep on M against t ; CO2CU(x)
+    for (int l = 0; l < npar; l++) {
+      Level &L = *lev[l];
+      Level &C = *lev[l + 1];
+      if (L.sm_symm || L.sm_steps != 1) throw Error("multi-rank levels support one non-symmetric Gauss-Seidel step per smoothing call");
+      NGB_CUDA(cudaMemcpyAsync(L.res, L.rhs, sizeof(double) * L.npad * L.b, cudaMemcpyDeviceToDevice, st));
+      dis2co(L, L.res);
+      tri_dispatch(L, false, false, true, L.res, nullptr, L.x, L.res);
+      spmv_part(L, 1, L.x, L.res, L.res, -1.0, 1.0, nullptr);
+      co2cu(L, L.x);
+      if (L.G.nnz) transfer(L.G, L.x, L.res, L.res, -1.0, 1.0);
+      transfer(L.PT, L.res, nullptr, C.rhs, 1.0, 0.0, L.d_pt_rowmap);
+    }
+    contracted_solve(*lev[npar]);
+    for (int l = npar - 1; l >= 0; l--) {
+      Level &L = *lev[l];
+      Level &C = *lev[l + 1];
+      transfer(L.P, C.result, L.x, L.x, 1.0, 1.0);
+      if (L.G.nnz) transfer(L.G, L.x, L.rhs, L.res, -1.0, 1.0);
+      else NGB_CUDA(cudaMemcpyAsync(L.res, L.rhs, sizeof(double) * L.npad * L.b, cudaMemcpyDeviceToDevice, st));
+      dis2co(L, L.res);
+      gs_rhs(L, true, L.x, L.res, L.y);
+      co2cu(L, L.y);
+      L.result = L.y;
+    }
+    return;
+  }
   const int NL = (int)lev.size();
   for (int l = 0; l + 1 < NL; l++) {
     Level &L = *lev[l];
@@ -1099,8 +1615,13 @@ double Amg::dot(i64 n, const double *a, const double *b)
   k_dot_final<<<1, DOT_THREADS, 0, st>>>(DOT_BLOCKS, d_partial, d_dot);
   launches += 2;
   double h = 0;
+  if (par && nccl) {   // InnerProduct(cumulated, distributed): local dot over all local dofs, summed over the ranks
+    NGB_NCCL(nccl_api().AllReduce(d_dot, d_dot, 1, ncclDouble, ncclSum, nccl, st));
+    exchanges++;
+  }
   NGB_CUDA(cudaMemcpyAsync(&h, d_dot, sizeof(double), cudaMemcpyDeviceToHost, st));
   NGB_CUDA(cudaStreamSynchronize(st));
+  if (par && !nccl) allreduce_scalars(&h, 1);
   return h;
 }
 
@@ -1199,10 +1720,9 @@ extern "C" {
 
 const char *ngsamg_b200_last_error(void) { return g_err.c_str(); }
 
-int ngsamg_b200_create(const char *type, const ngsamg_csr *A, const uint8_t *free_mask, const double *vertex_xyz,
-                       const char *const *flag_keys, const char *const *flag_vals, int nflags, int device, ngsamg_b200_t **out)
+static void create_impl(const char *type, const ngsamg_csr *A, const uint8_t *free_mask, const double *vertex_xyz,
+                        const char *const *flag_keys, const char *const *flag_vals, int nflags, int device, ngsamg_b200_t **out)
 {
-  NGB_TRY
   if (!out) throw Error("create: out is null");
   *out = nullptr;
   require_device(device);
@@ -1261,6 +1781,191 @@ int ngsamg_b200_create(const char *type, const ngsamg_csr *A, const uint8_t *fre
   if (vertex_xyz) L->xyz.assign(vertex_xyz, vertex_xyz + 3 * A->nrows);
   a.lev.push_back(std::move(L));
   *out = h.release();
+}
+
+int ngsamg_b200_create(const char *type, const ngsamg_csr *A, const uint8_t *free_mask, const double *vertex_xyz,
+                       const char *const *flag_keys, const char *const *flag_vals, int nflags, int device, ngsamg_b200_t **out)
+{
+  NGB_TRY
+  create_impl(type, A, free_mask, vertex_xyz, flag_keys, flag_vals, nflags, device, out);
+  NGB_CATCH
+}
+
+static void halo_to_pardofs(const ngsamg_halo *halo, i64 n, int rank, ParDofs &pd)
+{
+  pd = ParDofs();
+  pd.n = n;
+  if (halo) {
+    if (halo->npeers < 0 || (halo->npeers > 0 && (!halo->peers || !halo->ex_ptr))) throw Error("halo: null arrays");
+    for (int k = 0; k < halo->npeers; k++) {
+      pd.peers.push_back(halo->peers[k]);
+      pd.ex.emplace_back(halo->ex_dofs + halo->ex_ptr[k], halo->ex_dofs + halo->ex_ptr[k + 1]);
+      for (size_t q = 1; q < pd.ex.back().size(); q++)
+        if (pd.ex.back()[q] <= pd.ex.back()[q - 1]) throw Error("halo: the shared dof lists must be ascending");
+    }
+  }
+  pd.derive(rank);
+}
+
+int ngsamg_b200_create_parallel(const char *type, const ngsamg_csr *A, const uint8_t *free_mask, const double *vertex_xyz,
+                                const ngsamg_halo *halo, const ngsamg_comm *comm, const char *const *flag_keys,
+                                const char *const *flag_vals, int nflags, int device, ngsamg_b200_t **out)
+{
+  NGB_TRY
+  if (!comm) throw Error("create_parallel: comm is null");
+  if (comm->size < 1 || comm->rank < 0 || comm->rank >= comm->size) throw Error("create_parallel: invalid rank / size");
+  if (comm->size > 1 && (!comm->exchange || !comm->allreduce_sum)) throw Error("create_parallel: the communicator needs both callbacks");
+  create_impl(type, A, free_mask, vertex_xyz, flag_keys, flag_vals, nflags, device, out);
+  Amg &a = (*out)->amg;
+  try {
+    a.par = true;
+    a.comm.c = *comm;
+    a.nccl = (ncclComm_t)comm->nccl;
+    if (a.nccl) nccl_api();
+    Level &L = *a.lev[0];
+    // the reference keeps the freedofs mask even when every dof is free; the stage split depends on it (gssmoother.cpp:664-678)
+    if (free_mask && L.free_mask.empty()) L.free_mask.assign(free_mask, free_mask + A->nrows);
+    halo_to_pardofs(halo, A->nrows, comm->rank, L.pd);
+  } catch (...) { delete *out; *out = nullptr; throw; }
+  NGB_CATCH
+}
+
+int ngsamg_b200_nccl_unique_id(char id[128])
+{
+  NGB_TRY
+  static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is expected to be 128 bytes");
+  ncclUniqueId u;
+  NGB_NCCL(nccl_api().GetUniqueId(&u));
+  std::memcpy(id, &u, 128);
+  NGB_CATCH
+}
+
+int ngsamg_b200_nccl_comm_init(const char id[128], int rank, int size, int device, void **nccl_comm)
+{
+  NGB_TRY
+  if (!nccl_comm) throw Error("null output");
+  require_device(device);
+  ncclUniqueId u;
+  std::memcpy(&u, id, 128);
+  ncclComm_t c = nullptr;
+  NGB_NCCL(nccl_api().CommInitRank(&c, size, u, rank));
+  *nccl_comm = (void *)c;
+  NGB_CATCH
+}
+
+int ngsamg_b200_nccl_comm_destroy(void *nccl_comm)
+{
+  NGB_TRY
+  if (nccl_comm) NGB_NCCL(nccl_api().CommDestroy((ncclComm_t)nccl_comm));
+  NGB_CATCH
+}
+
+int ngsamg_b200_get_halo(ngsamg_b200_t *h, int level, int32_t *npeers, int32_t *peers, int64_t *ex_ptr, int32_t *ex_dofs)
+{
+  NGB_TRY
+  if (!h) throw Error("null handle");
+  Amg &a = h->amg;
+  if (!a.par) throw Error("get_halo: not a multi-rank hierarchy");
+  if (level < 0 || level >= (int)a.lev.size()) throw Error("level out of range");
+  const ParDofs &pd = a.lev[level]->pd;
+  if (npeers) *npeers = (i32)pd.peers.size();
+  i64 off = 0;
+  for (size_t k = 0; k < pd.peers.size(); k++) {
+    if (peers) peers[k] = pd.peers[k];
+    if (ex_ptr) ex_ptr[k] = off;
+    if (ex_dofs) std::memcpy(ex_dofs + off, pd.ex[k].data(), sizeof(i32) * pd.ex[k].size());
+    off += (i64)pd.ex[k].size();
+  }
+  if (ex_ptr) ex_ptr[pd.peers.size()] = off;
+  NGB_CATCH
+}
+
+int ngsamg_b200_get_hybrid(ngsamg_b200_t *h, int level, int which, int64_t *nnz, int64_t *rowptr, int32_t *col, double *val,
+                           double *mod_diag)
+{
+  NGB_TRY
+  if (!h) throw Error("null handle");
+  Amg &a = h->amg;
+  if (!a.par || level < 0 || level >= a.npar) throw Error("get_hybrid: not a distributed level");
+  Level &L = *a.lev[level];
+  if (which == 2) { if (nnz) { nnz[0] = L.nnz_m; nnz[1] = L.nnz_g; } }
+  else {
+    if (!L.keep_host) throw Error("hybrid matrices were not kept on the host (raise ngs_amg_keep_host_nnz)");
+    const HostBsr &M = which == 0 ? L.hM : L.hG;
+    if (nnz) *nnz = M.nnz();
+    if (rowptr) std::memcpy(rowptr, M.rowptr.data(), sizeof(i64) * (M.nrows + 1));
+    if (col) std::memcpy(col, M.col.data(), sizeof(i32) * M.nnz());
+    if (val) std::memcpy(val, M.val.data(), sizeof(double) * M.nnz() * M.bs());
+  }
+  if (mod_diag) std::memcpy(mod_diag, L.mod_diag.data(), sizeof(double) * L.mod_diag.size());
+  NGB_CATCH
+}
+
+int ngsamg_b200_num_parallel_levels(ngsamg_b200_t *h) { return (h && h->amg.finalized && h->amg.par) ? h->amg.npar : 0; }
+
+ngsamg_b200_t *ngsamg_b200_get_contracted(ngsamg_b200_t *h)
+{
+  // the nested hierarchy lives inside the parent; hand out a view that shares its storage
+  if (!h || !h->amg.par || !h->amg.nested) return nullptr;
+  return reinterpret_cast<ngsamg_b200_t *>(h->amg.nested.get());
+}
+
+int ngsamg_b200_get_contraction_map(ngsamg_b200_t *h, int rank, int64_t *n, int32_t *map)
+{
+  NGB_TRY
+  if (!h) throw Error("null handle");
+  Amg &a = h->amg;
+  if (!a.par || a.comm.rank() != 0) throw Error("get_contraction_map: only on rank 0 of a multi-rank hierarchy");
+  if (rank < 0 || rank >= (int)a.ctr.dof_maps.size()) throw Error("rank out of range");
+  if (n) *n = (i64)a.ctr.dof_maps[rank].size();
+  if (map) std::memcpy(map, a.ctr.dof_maps[rank].data(), sizeof(i32) * a.ctr.dof_maps[rank].size());
+  NGB_CATCH
+}
+
+struct ngsamg_b200_hybrid_host { HostBsr M, G; std::vector<double> md; std::vector<i32> sweep; std::vector<uint8_t> master; };
+
+int ngsamg_b200_hybrid_host_begin(const ngsamg_csr *A, const uint8_t *free_mask, const ngsamg_halo *halo, const ngsamg_comm *comm,
+                                  ngsamg_b200_hybrid_host **out, int64_t *nnz_m, int64_t *nnz_g)
+{
+  NGB_TRY
+  if (!comm || !out) throw Error("null argument");
+  check_csr(A, "hybrid_host");
+  HostBsr hA, Acum;
+  copy_csr(A, hA);
+  ParDofs pd;
+  halo_to_pardofs(halo, A->nrows, comm->rank, pd);
+  Comm c;
+  c.c = *comm;
+  auto r = std::make_unique<ngsamg_b200_hybrid_host>();
+  cumulate_matrix(c, pd, hA, Acum);
+  hybrid_split(pd, hA, Acum, r->M, r->G);
+  hybrid_mod_diag(c, pd, Acum, r->G, free_mask, r->md);
+  std::vector<uint8_t> sm;
+  hybrid_sweep_order(pd, free_mask, r->sweep, sm, nullptr);
+  r->master.resize(A->nrows);
+  for (i64 d = 0; d < A->nrows; d++) r->master[d] = pd.master_of[d] < 0 ? 1 : 0;
+  if (nnz_m) *nnz_m = r->M.nnz();
+  if (nnz_g) *nnz_g = r->G.nnz();
+  *out = r.release();
+  NGB_CATCH
+}
+
+int ngsamg_b200_hybrid_host_fetch(ngsamg_b200_hybrid_host *m, int64_t *m_rowptr, int32_t *m_col, double *m_val, int64_t *g_rowptr,
+                                  int32_t *g_col, double *g_val, double *mod_diag, int32_t *sweep_rank, uint8_t *master)
+{
+  NGB_TRY
+  if (!m) throw Error("null handle");
+  auto cp = [](const HostBsr &H, int64_t *rp, int32_t *ci, double *v) {
+    if (rp) std::memcpy(rp, H.rowptr.data(), sizeof(i64) * (H.nrows + 1));
+    if (ci) std::memcpy(ci, H.col.data(), sizeof(i32) * H.nnz());
+    if (v) std::memcpy(v, H.val.data(), sizeof(double) * H.nnz() * H.bs());
+  };
+  cp(m->M, m_rowptr, m_col, m_val);
+  cp(m->G, g_rowptr, g_col, g_val);
+  if (mod_diag) std::memcpy(mod_diag, m->md.data(), sizeof(double) * m->md.size());
+  if (sweep_rank) std::memcpy(sweep_rank, m->sweep.data(), sizeof(i32) * m->sweep.size());
+  if (master) std::memcpy(master, m->master.data(), m->master.size());
+  delete m;
   NGB_CATCH
 }
 
@@ -1449,7 +2154,8 @@ int ngsamg_b200_pcg(ngsamg_b200_t *h, const double *rhs, double *x, double tol, 
   NGB_TRY
   Amg &a = ready(h);
   Level &L = *a.lev[0];
-  if (a.lev.size() < 2) throw Error("pcg needs at least two levels");
+  if (a.lev.size() < 2 && !(a.par && a.npar == 0)) throw Error("pcg needs at least two levels");
+  if (a.par && a.npar == 0) throw Error("pcg: the hierarchy was contracted at level 0 (single rank?) -- use the single-rank constructor");
   const i64 n = L.n * L.b, np = L.npad * L.b;
   a.ensure_io(n);
   if (!a.cg_u) { a.cg_u = dev_alloc<double>(np); a.cg_s = dev_alloc<double>(np); a.cg_q = dev_alloc<double>(np); }
@@ -1468,6 +2174,7 @@ int ngsamg_b200_pcg(ngsamg_b200_t *h, const double *rhs, double *x, double tol, 
   if (wdn != 0.0)
     for (it = 1; it <= maxsteps; it++) {
       a.spmv_part(L, 4, s, nullptr, q, 1.0, 0.0, nullptr);
+      if (a.par && L.par && L.G.nnz) a.transfer(L.G, s, q, q, 1.0, 1.0);   // HybridBaseMatrix::Mult: (M + G) x, x CUMULATED -> DISTRIBUTED
       const double wd = wdn;
       const double as_s = a.dot(np, s, q);
       const double alpha = wd / as_s;

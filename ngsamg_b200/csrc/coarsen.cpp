@@ -14,7 +14,9 @@
 // It does NOT claim bit-exact agreement with the reference's aggregates.  Users who need the
 // reference's own DOF maps inject them with ngsamg_b200_set_prolongations().
 #include "common.hpp"
+#include "par.hpp"
 #include <chrono>
+#include <numeric>
 
 namespace ngb {
 
@@ -39,8 +41,10 @@ double entry_weight(const double *blk, int b)
 }
 
 // strength graph of the level matrix; `drop[v]` marks Dirichlet vertices (not part of any aggregate)
-void graph_from_matrix(const HostBsr &A, const std::vector<uint8_t> &drop, Graph &G)
+void graph_from_matrix(const HostBsr &A, const std::vector<uint8_t> &drop, Graph &G, const double *rowsum = nullptr,
+                       const i32 *cls = nullptr)
 {
+  // rowsum: externally supplied (assembled) row sums; cls: only couplings inside one sharing class become graph edges
   const i64 n = A.nrows;
   const int b = A.bh, bb = b * b;
   G.n = n;
@@ -54,7 +58,7 @@ void graph_from_matrix(const HostBsr &A, const std::vector<uint8_t> &drop, Graph
       if (!drop[i])
         for (i64 k = A.rowptr[i]; k < A.rowptr[i + 1]; k++) {
           i32 j = A.col[k];
-          if (j != i && !drop[j]) c++;
+          if (j != i && !drop[j] && (!cls || cls[j] == cls[i])) c++;
         }
       G.ptr[i + 1] = c;
     }
@@ -73,14 +77,14 @@ void graph_from_matrix(const HostBsr &A, const std::vector<uint8_t> &drop, Graph
         i32 j = A.col[k];
         const double *blk = &A.val[k * bb];
         for (int e = 0; e < bb; e++) rs[e] += blk[e];
-        if (j == i || drop[j]) continue;
+        if (j == i || drop[j] || (cls && cls[j] != cls[i])) continue;
         double w = entry_weight(blk, b);
         G.adj[p] = j;
         G.w[p] = w;
         p++;
         mx = std::max(mx, w);
       }
-      double vw = entry_weight(rs.data(), b);
+      double vw = entry_weight(rowsum ? rowsum + i * bb : rs.data(), b);
       G.vwt[i] = vw;
       G.maxod[i] = std::max(mx, vw);
     }
@@ -301,8 +305,12 @@ void host_transpose(const HostBsr &A, HostBsr &T)
     }
 }
 
-void build_prolongation(const HostBsr &A, const uint8_t *free_mask, int bc, const std::vector<double> &xyz,
-                        const CoarsenOptions &opt, HostBsr &P, std::vector<i32> &vmap, std::vector<double> &cxyz)
+// The builder proper.  `pc` (multi-rank mode, canonical vertex labels): pc->cls[v] = sharing class of v, pc->rowsum = assembled row
+// sums; `A` then only holds the couplings a vertex may use (see build_prolongation below) and aggregation is restricted to
+// vertices of the same class.
+static void build_prolongation_canonical(const HostBsr &A, const uint8_t *free_mask, int bc, const std::vector<double> &xyz,
+                                         const CoarsenOptions &opt, HostBsr &P, std::vector<i32> &vmap, std::vector<double> &cxyz,
+                                         const ParCoarsen *pc)
 {
   const i64 n = A.nrows;
   const int bf = A.bh;
@@ -317,11 +325,18 @@ void build_prolongation(const HostBsr &A, const uint8_t *free_mask, int bc, cons
     t_last = now;
   };
   Graph G0;
-  graph_from_matrix(A, drop, G0);
+  graph_from_matrix(A, drop, G0, pc ? pc->rowsum->data() : nullptr, pc ? pc->cls->data() : nullptr);
   lap("graph_from_matrix");
   // isolated vertices are not aggregated (spw_agg_impl.hpp:1599-1614)
-  for (i64 i = 0; i < n; i++)
-    if (!drop[i] && G0.ptr[i + 1] == G0.ptr[i]) drop[i] = 1;
+  for (i64 i = 0; i < n; i++) {
+    if (drop[i] || G0.ptr[i + 1] != G0.ptr[i]) continue;
+    if (!pc) { drop[i] = 1; continue; }
+    // multi-rank: the graph only holds same-class edges; a vertex is isolated if it is unshared and has no neighbour at all
+    if ((*pc->cls)[i] != 0) continue;
+    bool any = false;
+    for (i64 k = A.rowptr[i]; k < A.rowptr[i + 1] && !any; k++) any = (A.col[k] != i && !(free_mask && !free_mask[A.col[k]]));
+    if (!any) drop[i] = 1;
+  }
 
   // ---- aggregation: `rounds` pairwise matching rounds + orphan round
   vmap.assign(n, -1);
@@ -443,6 +458,94 @@ void build_prolongation(const HostBsr &A, const uint8_t *free_mask, int bc, cons
       }
     }
   });
+}
+
+// Multi-rank mode (par != nullptr): `A` is the ASSEMBLED local matrix (cumulate_matrix) and the coarsening respects the sharing
+// classes the way the reference's EQC-wise agglomeration does: vertices are only merged with vertices shared by
+// the same set of ranks, and a vertex interpolates only from coarse vertices shared by at least its own set of ranks
+// (vertex_factory_impl.hpp:1845-1848), so every sharer computes bit-identical aggregates and prolongation rows from data it
+// holds: the class-restricted graph is built in a canonical vertex order that is the same on every sharer.
+void build_prolongation(const HostBsr &A_in, const uint8_t *free_mask, int bc, const std::vector<double> &xyz_in,
+                        const CoarsenOptions &opt, HostBsr &P, std::vector<i32> &vmap, std::vector<double> &cxyz,
+                        const ParCoarsen *par)
+{
+  if (par) {
+    const ParDofs &pd = *par->pd;
+    const i64 n = A_in.nrows;
+    const int bs = A_in.bs();
+    // consistent order of the classes: lexicographic on the full rank set (sharers + this rank)
+    const size_t ncls = pd.sharers.size();
+    std::vector<std::vector<i32>> full(ncls);
+    for (size_t c = 0; c < ncls; c++) { full[c] = pd.sharers[c]; full[c].push_back(par->rank); std::sort(full[c].begin(), full[c].end()); }
+    std::vector<i32> cord(ncls), cls_order(ncls);
+    std::iota(cord.begin(), cord.end(), 0);
+    std::sort(cord.begin(), cord.end(), [&](i32 a, i32 b) { return full[a] < full[b]; });
+    for (size_t q = 0; q < ncls; q++) cls_order[cord[q]] = (i32)q;
+    // canonical labels: class-major, canonical key inside a class
+    std::vector<i32> order(n), lab(n);
+    std::iota(order.begin(), order.end(), 0);
+    std::sort(order.begin(), order.end(), [&](i32 a, i32 b) {
+      const i32 ca = cls_order[pd.eqc[a]], cb = cls_order[pd.eqc[b]];
+      return ca < cb || (ca == cb && pd.canon[a] < pd.canon[b]);
+    });
+    for (i64 q = 0; q < n; q++) lab[order[q]] = (i32)q;
+    // relabelled matrix restricted to the couplings a vertex may use: columns of a class that is shared by at least the row's ranks
+    HostBsr B;
+    B.nrows = n; B.ncols = n; B.bh = A_in.bh; B.bw = A_in.bw;
+    B.rowptr.assign(n + 1, 0);
+    for (i64 q = 0; q < n; q++) {
+      const i64 i = order[q];
+      i64 c = 0;
+      for (i64 e = A_in.rowptr[i]; e < A_in.rowptr[i + 1]; e++) c += pd.finer_or_equal(pd.eqc[i], pd.eqc[A_in.col[e]]) ? 1 : 0;
+      B.rowptr[q + 1] = B.rowptr[q] + c;
+    }
+    B.col.resize(B.rowptr[n]);
+    B.val.resize((size_t)B.rowptr[n] * bs);
+    parallel_for(n, [&](i64 lo, i64 hi) {
+      std::vector<std::pair<i32, i64>> ent;
+      for (i64 q = lo; q < hi; q++) {
+        const i64 i = order[q];
+        ent.clear();
+        for (i64 e = A_in.rowptr[i]; e < A_in.rowptr[i + 1]; e++)
+          if (pd.finer_or_equal(pd.eqc[i], pd.eqc[A_in.col[e]])) ent.emplace_back(lab[A_in.col[e]], e);
+        std::sort(ent.begin(), ent.end());
+        i64 p = B.rowptr[q];
+        for (auto &x : ent) { B.col[p] = x.first; std::memcpy(&B.val[p * bs], &A_in.val[x.second * bs], sizeof(double) * bs); p++; }
+      }
+    });
+    std::vector<uint8_t> fm;
+    if (free_mask) { fm.resize(n); for (i64 q = 0; q < n; q++) fm[q] = free_mask[order[q]]; }
+    std::vector<double> xyz, rs((size_t)n * bs);
+    if (!xyz_in.empty()) { xyz.resize((size_t)n * 3); for (i64 q = 0; q < n; q++) std::memcpy(&xyz[q * 3], &xyz_in[(i64)order[q] * 3], sizeof(double) * 3); }
+    for (i64 q = 0; q < n; q++) std::memcpy(&rs[q * bs], &(*par->rowsum)[(i64)order[q] * bs], sizeof(double) * bs);
+    std::vector<i32> cls(n);
+    for (i64 q = 0; q < n; q++) cls[q] = pd.eqc[order[q]];
+    ParCoarsen inner;
+    inner.rowsum = &rs; inner.cls = &cls; inner.rank = par->rank;
+    HostBsr Pq;
+    std::vector<i32> vq;
+    build_prolongation_canonical(B, free_mask ? fm.data() : nullptr, bc, xyz, opt, Pq, vq, cxyz, &inner);
+    // back to the local numbering (rows only; coarse vertices keep the numbering of the canonical run)
+    vmap.resize(n);
+    for (i64 i = 0; i < n; i++) vmap[i] = vq[lab[i]];
+    P = HostBsr();
+    P.nrows = n; P.ncols = Pq.ncols; P.bh = Pq.bh; P.bw = Pq.bw;
+    P.rowptr.assign(n + 1, 0);
+    for (i64 i = 0; i < n; i++) P.rowptr[i + 1] = P.rowptr[i] + (Pq.rowptr[lab[i] + 1] - Pq.rowptr[lab[i]]);
+    P.col.resize(Pq.nnz());
+    P.val.resize(Pq.val.size());
+    const int pbs = Pq.bs();
+    parallel_for(n, [&](i64 lo, i64 hi) {
+      for (i64 i = lo; i < hi; i++) {
+        const i64 s0 = Pq.rowptr[lab[i]], len = Pq.rowptr[lab[i] + 1] - s0;
+        if (!len) continue;
+        std::memcpy(&P.col[P.rowptr[i]], &Pq.col[s0], sizeof(i32) * len);
+        std::memcpy(&P.val[P.rowptr[i] * pbs], &Pq.val[s0 * pbs], sizeof(double) * len * pbs);
+      }
+    });
+    return;
+  }
+  build_prolongation_canonical(A_in, free_mask, bc, xyz_in, opt, P, vmap, cxyz, nullptr);
 }
 
 }  // namespace ngb

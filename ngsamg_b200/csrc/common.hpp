@@ -119,8 +119,10 @@ struct CoarsenOptions {
 // bf = fine block size, bc = coarse block size (bf==bc except elasticity level 0: 3 -> 6).
 // xyz: fine vertex coordinates (n x 3) or empty; cxyz: out, coarse vertex coordinates (elasticity).
 // vmap out: fine vertex -> coarse vertex (-1 = Dirichlet / dropped).
+struct ParCoarsen;  // par.hpp: sharing classes for the multi-rank (class-respecting) mode, nullptr = single rank
 void build_prolongation(const HostBsr &A, const uint8_t *free_mask, int bc, const std::vector<double> &xyz,
-                        const CoarsenOptions &opt, HostBsr &P, std::vector<i32> &vmap, std::vector<double> &cxyz);
+                        const CoarsenOptions &opt, HostBsr &P, std::vector<i32> &vmap, std::vector<double> &cxyz,
+                        const ParCoarsen *par = nullptr);
 
 void host_transpose(const HostBsr &A, HostBsr &T);
 

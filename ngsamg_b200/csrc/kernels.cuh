@@ -929,4 +929,66 @@ __global__ void k_dense_gemv(int n, const double *__restrict__ M, const double *
   if (lane == 0) y[row] = s;
 }
 
+// ------------------------------------------------------------------------------------------------
+// multi-rank halo exchange (DCCMap, src/base/linalg/dcc_map.cpp:225-300): pack / unpack of the shared dofs.
+// Index lists are in the level-scheduled numbering; one thread per (dof, component).
+// ------------------------------------------------------------------------------------------------
+// BufferG (zero = 1: buf = v, v = 0) / BufferM (zero = 0: buf = v)
+__global__ void k_halo_pack(i64 cnt, int b, const i32 *__restrict__ idx, double *v, double *__restrict__ buf, int zero)
+{
+  const i64 t = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= cnt * b) return;
+  const i64 k = t / b;
+  const int q = (int)(t - k * b);
+  const i64 p = (i64)idx[k] * b + q;
+  buf[t] = v[p];
+  if (zero) v[p] = 0.0;
+}
+// ApplyM: v[dof] += received values, neighbours in ascending order (a master dof can have several ghosts)
+__global__ void k_halo_add(i64 nuniq, int b, const i32 *__restrict__ dof, const i64 *__restrict__ src_ptr,
+                           const i64 *__restrict__ src_pos, const double *__restrict__ buf, double *v)
+{
+  const i64 t = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= nuniq * b) return;
+  const i64 k = t / b;
+  const int q = (int)(t - k * b);
+  double s = v[(i64)dof[k] * b + q];
+  for (i64 e = src_ptr[k]; e < src_ptr[k + 1]; e++) s += buf[src_pos[e] * b + q];
+  v[(i64)dof[k] * b + q] = s;
+}
+// ApplyG: v[dof] = received value
+__global__ void k_halo_set(i64 cnt, int b, const i32 *__restrict__ idx, const double *__restrict__ buf, double *v)
+{
+  const i64 t = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= cnt * b) return;
+  const i64 k = t / b;
+  const int q = (int)(t - k * b);
+  v[(i64)idx[k] * b + q] = buf[t];
+}
+// CtrMap transfers (dof_contract.cpp:49-228): dst[perm[map[i]]] += src[i]  /  dst[i] = src[perm[map[i]]]
+__global__ void k_ctr_scatter_add(i64 n, int b, const i32 *__restrict__ map, const i32 *__restrict__ perm, const double *__restrict__ src, double *dst)
+{
+  const i64 t = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n * b) return;
+  const i64 i = t / b;
+  const int q = (int)(t - i * b);
+  dst[(i64)perm[map[i]] * b + q] += src[t];
+}
+__global__ void k_ctr_gather(i64 n, int b, const i32 *__restrict__ map, const i32 *__restrict__ perm, const double *__restrict__ src, double *dst)
+{
+  const i64 t = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n * b) return;
+  const i64 i = t / b;
+  const int q = (int)(t - i * b);
+  dst[t] = src[(i64)perm[map[i]] * b + q];
+}
+// AoS blocks in the original numbering -> planar blocks in the level-scheduled numbering (replacement diagonal of the hybrid smoother)
+__global__ void k_aos_perm_to_planar(i64 n, int bs, const i32 *__restrict__ perm, const double *__restrict__ aos, double *planar)
+{
+  const i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const i64 row = perm[i];
+  for (int e = 0; e < bs; e++) planar[((row >> 5) * bs + e) * 32 + (row & 31)] = aos[i * bs + e];
+}
+
 }  // namespace ngb

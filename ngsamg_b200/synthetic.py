@@ -33,7 +33,7 @@ def _edge_cube_weight(vb, vc, nb, nc):
     return w
 
 
-def poisson3d_kuhn(nx, ny=None, nz=None, dirichlet=("x0", "y1"), coef=None, zchunk=8):
+def poisson3d_kuhn(nx, ny=None, nz=None, dirichlet=("x0", "y1"), coef=None, zchunk=8, h=None, origin=(0, 0, 0)):
     """P1 stiffness matrix of -div(c grad u) on the unit cube, nx*ny*nz vertices, Kuhn tets.
 
     Vertex (ix,iy,iz) has DOF number ix + nx*(iy + ny*iz).  The sparsity pattern is the mesh
@@ -42,11 +42,14 @@ def poisson3d_kuhn(nx, ny=None, nz=None, dirichlet=("x0", "y1"), coef=None, zchu
     `coef`: optional callable (x,y,z)->c evaluated at vertices; the edge weight uses the mean of the
     two end-point values (a diagonal scaling that keeps symmetry and zero row sums).
     Generated in slabs of `zchunk` vertex planes so that the peak memory stays close to the size of the result.
+    `h`, `origin`: mesh width and vertex-index offset of a SUB-BOX of a larger mesh -- the matrix is then the sub-assembled
+    (Neumann) matrix of that sub-box, i.e. one rank's local matrix of a box partition (partition_poisson3d).
     """
     ny = nx if ny is None else ny
     nz = nx if nz is None else nz
     n = nx * ny * nz
-    h = 1.0 / (max(nx, ny, nz) - 1)
+    h = 1.0 / (max(nx, ny, nz) - 1) if h is None else float(h)
+    ox, oy, oz = origin
     dirs = [(0, 0, 0)] + _POS_DIRS + [(-a, -b, -c) for (a, b, c) in _POS_DIRS]
     dirs.sort(key=lambda d: d[0] + nx * (d[1] + ny * d[2]))
     K = len(dirs)
@@ -84,7 +87,7 @@ def poisson3d_kuhn(nx, ny=None, nz=None, dirichlet=("x0", "y1"), coef=None, zchu
         m = ix.shape[0]
         idx = ix + nx * (iy + ny * iz)
         coord = (ix, iy, iz)
-        cv = cvfun(ix * h, iy * h, iz * h).astype(np.float64) if cvfun is not None else None
+        cv = cvfun((ix + ox) * h, (iy + oy) * h, (iz + oz) * h).astype(np.float64) if cvfun is not None else None
         cols = np.zeros((m, K), np.int64)
         vals = np.zeros((m, K), np.float64)
         mask = np.zeros((m, K), bool)
@@ -99,7 +102,7 @@ def poisson3d_kuhn(nx, ny=None, nz=None, dirichlet=("x0", "y1"), coef=None, zchu
                 w = _edge_cube_weight(coord[b_], coord[c_], dims[b_], dims[c_]).astype(np.float64)
                 v = -(h / 6.0) * w
                 if cv is not None:
-                    cj = cvfun(np.clip(jx, 0, nx - 1) * h, np.clip(jy, 0, ny - 1) * h, np.clip(jz, 0, nz - 1) * h).astype(np.float64)
+                    cj = cvfun((np.clip(jx, 0, nx - 1) + ox) * h, (np.clip(jy, 0, ny - 1) + oy) * h, (np.clip(jz, 0, nz - 1) + oz) * h).astype(np.float64)
                     v = v * 0.5 * (cv + cj)
                 vals[:, k] = np.where(ok, v, 0.0)
         vals[:, kd] = -(vals * mask).sum(axis=1)
@@ -122,8 +125,78 @@ def poisson3d_kuhn(nx, ny=None, nz=None, dirichlet=("x0", "y1"), coef=None, zchu
             ntet += ok * (6 if sum(s3) in (0, 3) else 2)
         rhs[sl] = (h ** 3 / 24.0) * ntet
     ids = np.arange(n)
-    xyz = np.stack([(ids % nx) * h, ((ids // nx) % ny) * h, (ids // (nx * ny)) * h], axis=1).astype(np.float64)
+    xyz = np.stack([(ids % nx + ox) * h, ((ids // nx) % ny + oy) * h, (ids // (nx * ny) + oz) * h], axis=1).astype(np.float64)
     return dict(n=n, b=1, rowptr=rowptr, col=col, val=val, free=free, rhs=rhs, xyz=xyz, h=h, dims=(nx, ny, nz))
+
+
+def _split(ncells, parts):
+    """cell ranges of `parts` nearly equal slabs of `ncells` cells"""
+    cuts = [(ncells * k) // parts for k in range(parts + 1)]
+    return [(cuts[k], cuts[k + 1]) for k in range(parts)]
+
+
+def box_partition(dims, grid):
+    """Box partition of the CELLS of an nx*ny*nz-vertex mesh into grid = (px, py, pz) sub-boxes (rank = bx + px*(by + py*bz)).
+    Returns per rank dict(origin, dims (local vertex counts), gidx (local -> global vertex number, local numbering x-fastest))
+    -- interface vertices are duplicated on every sharer, exactly like NGSolve's ParallelDofs."""
+    nx, ny, nz = dims
+    px, py, pz = grid
+    parts = []
+    for bz, (z0, z1) in enumerate(_split(nz - 1, pz)):
+        for by, (y0, y1) in enumerate(_split(ny - 1, py)):
+            for bx, (x0, x1) in enumerate(_split(nx - 1, px)):
+                lx, ly, lz = x1 - x0 + 1, y1 - y0 + 1, z1 - z0 + 1
+                iz, iy, ix = np.meshgrid(np.arange(z0, z1 + 1), np.arange(y0, y1 + 1), np.arange(x0, x1 + 1), indexing="ij")
+                gidx = (ix + nx * (iy + ny * iz)).ravel().astype(np.int64)
+                parts.append(dict(origin=(x0, y0, z0), dims=(lx, ly, lz), gidx=gidx, box=(bx, by, bz)))
+    return parts
+
+
+def halos_from_global_ids(gidx_per_rank, rank):
+    """(peers, ex) of `rank`: DOFs with the same global number on two ranks are shared; lists ascending in the local number, which
+    is monotone in the global number here, so the k-th shared DOF agrees on both sides."""
+    mine = gidx_per_rank[rank]
+    peers, ex = [], []
+    for r, other in enumerate(gidx_per_rank):
+        if r == rank:
+            continue
+        common = np.intersect1d(mine, other, assume_unique=True)
+        if len(common) == 0:
+            continue
+        pos = np.searchsorted(mine, common)       # local numbering is ascending in the global number
+        peers.append(r)
+        ex.append(pos.astype(np.int32))
+    return peers, ex
+
+
+def partition_poisson3d(nx, ny=None, nz=None, grid=(1, 1, 2), rank=None, dirichlet=("x0", "y1"), coef=None):
+    """Local problems of a box partition of poisson3d_kuhn(nx, ny, nz): for every rank (or only `rank`) a dict with the
+    sub-assembled local matrix (rowptr/col/val), free, rhs (DISTRIBUTED load vector), xyz, gidx and the halo (peers, ex).
+    The sum of the local matrices / load vectors over the ranks is the global matrix / load vector."""
+    ny = nx if ny is None else ny
+    nz = nx if nz is None else nz
+    h = 1.0 / (max(nx, ny, nz) - 1)
+    parts = box_partition((nx, ny, nz), grid)
+    gids = [p["gidx"] for p in parts]
+    dims = (nx, ny, nz)
+    out = []
+    for r, p in enumerate(parts):
+        if rank is not None and r != rank:
+            out.append(None)
+            continue
+        # Dirichlet faces of the global cube that this sub-box touches
+        tags = []
+        for tag in dirichlet:
+            ax = "xyz".index(tag[0])
+            if tag[1] == "0" and p["origin"][ax] == 0:
+                tags.append(tag)
+            if tag[1] == "1" and p["origin"][ax] + p["dims"][ax] == dims[ax]:
+                tags.append(tag)
+        loc = poisson3d_kuhn(*p["dims"], dirichlet=tuple(tags), coef=coef, h=h, origin=p["origin"])
+        loc["gidx"] = p["gidx"]
+        loc["peers"], loc["ex"] = halos_from_global_ids(gids, r)
+        out.append(loc)
+    return out if rank is None else out[rank]
 
 
 def kuhn_tets(nx, ny, nz):
@@ -165,7 +238,7 @@ def poisson3d_kuhn_assembled(nx, ny=None, nz=None):
     return A, rhs
 
 
-def elasticity3d_kuhn(nx, ny, nz, lx=None, E=1e3, nu=0.15, jump=None, clamp=("x0",)):
+def elasticity3d_kuhn(nx, ny, nz, lx=None, E=1e3, nu=0.15, jump=None, clamp=("x0",), h=None, origin=(0, 0, 0)):
     """P1 linear elasticity (3x3 blocks) on the beam [0,lx]x[0,1]^2 with Kuhn tets, element assembly.
 
     lam/mu as examples/elasticity/amg_utils.py:150-153; clamp at x=0, body force (0,x,0)
@@ -174,12 +247,12 @@ def elasticity3d_kuhn(nx, ny, nz, lx=None, E=1e3, nu=0.15, jump=None, clamp=("x0
     Returns dict(n, b=3, rowptr, col, val (blocks row-major), free, rhs, xyz).
     """
     import scipy.sparse as sp
-    h = 1.0 / (min(ny, nz) - 1)
+    h = 1.0 / (min(ny, nz) - 1) if h is None else float(h)   # h / origin: sub-box of a larger mesh (see partition_elasticity3d)
     lx = h * (nx - 1) if lx is None else lx
     n = nx * ny * nz
     T = kuhn_tets(nx, ny, nz)
     ids = np.arange(n)
-    X = np.stack([(ids % nx) * (lx / (nx - 1)), ((ids // nx) % ny) * h, (ids // (nx * ny)) * h], axis=1)
+    X = np.stack([(ids % nx) * (lx / (nx - 1)) + origin[0] * h, ((ids // nx) % ny + origin[1]) * h, (ids // (nx * ny) + origin[2]) * h], axis=1)
     P = X[T]
     M = np.concatenate([np.ones((len(T), 4, 1)), P], axis=2)
     Minv = np.linalg.inv(M)
@@ -292,3 +365,20 @@ def elasticity3d_kuhn_stencil(nx, ny, nz, E=1e3, nu=0.15, clamp=("x0",)):
     rhs = np.zeros((n, 3))
     rhs[:, 1] = (hs ** 3 / 24.0) * ntet * X[:, 0]
     return dict(n=n, b=3, rowptr=rowptr, col=col, val=val.reshape(-1), free=free, rhs=rhs.reshape(-1), xyz=X)
+
+
+def partition_elasticity3d(nx, ny, nz, nparts=2, rank=None, **kw):
+    """z-slab partition of elasticity3d_kuhn(nx, ny, nz): per rank the sub-assembled local problem + halo (see partition_poisson3d)"""
+    h = 1.0 / (min(ny, nz) - 1)
+    parts = box_partition((nx, ny, nz), (1, 1, nparts))
+    gids = [p["gidx"] for p in parts]
+    out = []
+    for r, p in enumerate(parts):
+        if rank is not None and r != rank:
+            out.append(None)
+            continue
+        loc = elasticity3d_kuhn(*p["dims"], h=h, origin=p["origin"], **kw)
+        loc["gidx"] = p["gidx"]
+        loc["peers"], loc["ex"] = halos_from_global_ids(gids, r)
+        out.append(loc)
+    return out if rank is None else out[rank]

@@ -1,0 +1,376 @@
+"""Multi-rank CPU oracle: the reference's MPI-parallel preconditioner apply restated for R simulated ranks in ONE process.
+
+TEST INFRASTRUCTURE ONLY (like oracle.py): imported by tests/ and the cpu_baseline / --impl reference legs of bench.py.
+
+PARITY UNPINNED (see ngsamg_oracle.c): restated from the reference sources, which cannot be built here.
+
+What is restated (reference paths relative to /root/reference):
+  * BasicDCCMap::CalcDOFMasters            src/base/linalg/dcc_map.cpp:494-543   -> dcc_lists
+  * DCCMap DIS2CO / CO2CU                  src/base/linalg/dcc_map.cpp:76-302    -> dis2co / co2cu
+  * DecomposeSparseMatrixHybrid            src/base/linalg/hybrid_matrix.cpp:17-307 -> hybrid_split
+  * CalcHybridSmootherRDGItGeneric         src/base/smoothers/hybrid_smoother_utils.hpp:11-143 -> mod_diag
+  * HybridGSSmoother::Finalize / stages    src/base/smoothers/gssmoother.cpp:616-861 -> HybridLevel.stage_masks
+  * HybridBaseSmoother::SmoothImplRES/RHS, CallStageKernelsImpl  src/base/smoothers/hybrid_base_smoother.cpp:294-574
+  * AMGMatrix::SmoothV on parallel vectors src/base/solve/amg_matrix.cpp:160-307
+  * CtrMap transfers + matrix contraction  src/base/coarsening/dof_contract.cpp:49-228, 557-727
+  * CGSolver with all-reduced inner products (ngsolve.krylovspace.CGSolver on ParallelVectors)
+The sequential Gauss-Seidel sweeps themselves run in the C oracle (GSS3 / GSS4 arithmetic, gssmoother.cpp:195-315, 406-570).
+The hierarchy (local prolongations, coarse sharing lists, contraction maps) is an INPUT -- it is read back from the product,
+exactly like the single-rank parity tests inject the product's prolongations into OracleAMG.
+"""
+import numpy as np
+import scipy.sparse as sp
+
+from . import oracle as O
+
+
+def _expand(A):
+    """Bsr -> scipy csr on scalar dofs, keeping structural zeros out of the way (values only matter here)"""
+    return A.to_scipy().tocsr()
+
+
+def dcc_lists(rank, n, peers, ex):
+    """master flags + m_ex / g_ex per neighbour.  master of a shared dof = lowest rank sharing it (dps[0] < rank -> ghost)."""
+    sharers = [[] for _ in range(n)]
+    for kp, p in enumerate(peers):
+        for d in ex[kp]:
+            sharers[d].append(p)
+    master = np.ones(n, bool)
+    master_rank = np.full(n, rank, np.int64)
+    for d in range(n):
+        if sharers[d] and min(sharers[d]) < rank:
+            master[d] = False
+            master_rank[d] = min(sharers[d])
+    m_ex, g_ex = [], []
+    for kp, p in enumerate(peers):
+        e = np.asarray(ex[kp], np.int64)
+        m_ex.append(e[master[e]] if len(e) else e)
+        g_ex.append(e[master_rank[e] == p] if len(e) else e)
+    nshare = np.array([len(s) for s in sharers])
+    return master, m_ex, g_ex, nshare
+
+
+class HybridLevel:
+    """one distributed level: all ranks' local matrices + sharing lists; builds M, G, mod diag, stage masks, dinv per rank"""
+
+    def __init__(self, A_loc, free, peers, ex, pinv=False):
+        self.R = len(A_loc)
+        self.A = A_loc
+        self.b = A_loc[0].bh
+        self.n = [a.nrows for a in A_loc]
+        self.free = [None if f is None else np.asarray(f, np.uint8) for f in free]
+        self.peers, self.ex = peers, ex
+        self.pinv = pinv
+        R, b = self.R, self.b
+        self.master, self.m_ex, self.g_ex, self.nshare = [], [], [], []
+        for r in range(R):
+            m, me, ge, ns = dcc_lists(r, self.n[r], peers[r], ex[r])
+            self.master.append(m); self.m_ex.append(me); self.g_ex.append(ge); self.nshare.append(ns)
+        self._split()
+        self._mod_diag()
+        self._smoothers()
+
+    def _sdofs(self, dofs):
+        d = np.asarray(dofs, np.int64)
+        return (d[:, None] * self.b + np.arange(self.b)[None, :]).ravel()
+
+    # ---- DecomposeSparseMatrixHybrid -------------------------------------------------------------------
+    def _split(self):
+        R, b = self.R, self.b
+        S = [_expand(a) for a in self.A]
+        self.S = S
+        # every rank ships the diagonal block on the ghost dofs of neighbour kp (master = that neighbour) to it
+        shipped = {}
+        for r in range(R):
+            for kp, p in enumerate(self.peers[r]):
+                g = self.g_ex[r][kp]
+                if len(g):
+                    sd = self._sdofs(g)
+                    shipped[(r, p)] = S[r][sd][:, sd].tocoo()
+        self.M, self.G = [], []
+        for r in range(R):
+            n = self.n[r] * b
+            msk = np.repeat(self.master[r], b)
+            D = sp.diags(msk.astype(float))
+            M = (D @ S[r] @ D).tocsr()       # master x master part of the own matrix
+            for kp, p in enumerate(self.peers[r]):   # ascending neighbour order, like the reference's merge
+                if (p, r) in shipped:
+                    blk = shipped[(p, r)]
+                    sd = self._sdofs(self.m_ex[r][kp])
+                    M = M + sp.coo_matrix((blk.data, (sd[blk.row], sd[blk.col])), shape=(n, n)).tocsr()
+            # G: entries whose row- and column-masters differ
+            mr = np.full(self.n[r], -1, np.int64)
+            for kp, p in enumerate(self.peers[r]):
+                if len(self.g_ex[r][kp]):
+                    mr[self.g_ex[r][kp]] = kp
+            mrs = np.repeat(mr, b)
+            C = S[r].tocoo()
+            keep = mrs[C.row] != mrs[C.col]
+            G = sp.coo_matrix((C.data[keep], (C.row[keep], C.col[keep])), shape=(n, n)).tocsr()
+            self.M.append(M); self.G.append(G)
+
+    # ---- CalcHybridSmootherRDGItGeneric ----------------------------------------------------------------
+    def _allreduce_dofdata(self, data):
+        """MyAllReduceDofData: every sharer ends up with the sum over all sharers (data[r]: n_r x k)"""
+        out = [d.copy() for d in data]
+        for r in range(self.R):
+            for kp, p in enumerate(self.peers[r]):
+                e = np.asarray(self.ex[r][kp], np.int64)
+                kq = list(self.peers[p]).index(r)
+                eo = np.asarray(self.ex[p][kq], np.int64)
+                if len(e):
+                    out[r][e] += data[p][eo]
+        return out
+
+    def _mod_diag(self):
+        R, b = self.R, self.b
+        od = []
+        for r in range(R):
+            d = np.zeros((self.n[r], b, b))
+            Md = self.M[r]
+            for i in range(b):
+                for j in range(b):
+                    d[:, i, j] = np.asarray(Md[np.arange(self.n[r]) * b + i, np.arange(self.n[r]) * b + j]).ravel()
+            od.append(d.reshape(self.n[r], b * b))
+        od = self._allreduce_dofdata(od)
+        self.orig_diag = od
+        ad = []
+        for r in range(R):
+            dd = od[r].reshape(self.n[r], b, b)
+            sq = np.sqrt(np.abs(np.einsum("kii->ki", dd))).reshape(-1)
+            G = self.G[r].tocoo()
+            with np.errstate(divide="ignore", invalid="ignore"):
+                w = np.abs(G.data) / (sq[G.row] * sq[G.col])
+            a = np.bincount(G.row, weights=w, minlength=self.n[r] * b).astype(np.float64).reshape(self.n[r], b)
+            if self.free[r] is not None:
+                a[self.free[r] == 0] = 0.0
+            ad.append(a)
+        ad = self._allreduce_dofdata(ad)
+        self.md = []
+        for r in range(R):
+            fac = np.maximum(1.0, 0.51 * (1.0 + ad[r])).max(axis=1)
+            md = od[r] * fac[:, None]
+            dead = ~self.master[r]
+            if self.free[r] is not None:
+                dead |= self.free[r] == 0
+            md[dead] = 0.0
+            self.md.append(md)
+
+    # ---- HybridGSSmoother::Finalize: loc / ex subsets, split index, GSS3(M, mod_diag, loc), GSS4(M, mod_diag, ex) ----
+    def _smoothers(self):
+        R = self.R
+        self.Mb, self.Gb, self.dinv, self.masks = [], [], [], []
+        for r in range(R):
+            n = self.n[r]
+            loc = self.master[r] & (self.nshare[r] == 0)
+            exm = self.master[r] & (self.nshare[r] > 0)
+            if self.free[r] is not None:
+                loc &= self.free[r] != 0
+                exm &= self.free[r] != 0
+                cnt, half, split = 0, int(loc.sum()) // 2, 0
+                idx = np.flatnonzero(loc)
+                if len(idx) > half:
+                    split = int(idx[half])
+            else:
+                split = n // 2
+            ar = np.arange(n)
+            m1 = (loc & (ar < split)).astype(np.uint8)
+            m2 = (loc & (ar >= split)).astype(np.uint8)
+            Mb = O.Bsr.from_scipy(self.M[r], self.b, self.b) if self.M[r].nnz else O.Bsr(n, n, self.b, self.b, np.zeros(n + 1, np.int64), np.zeros(0, np.int32), np.zeros(0))
+            if Mb.nrows != n:
+                raise RuntimeError("block conversion changed the size")
+            Gb = O.Bsr.from_scipy(self.G[r], self.b, self.b) if self.G[r].nnz else O.Bsr(n, n, self.b, self.b, np.zeros(n + 1, np.int64), np.zeros(0, np.int32), np.zeros(0))
+            sm = (loc | exm).astype(np.uint8)
+            dinv = O.calc_dinv(Mb, sm, self.pinv, self.md[r].reshape(-1))
+            self.Mb.append(Mb); self.Gb.append(Gb); self.dinv.append(dinv)
+            self.masks.append((m1, exm.astype(np.uint8), m2))
+
+    # ---- DCCMap ----------------------------------------------------------------------------------------
+    def dis2co(self, vec):
+        """BufferG (pack + zero the ghosts), send to the master, ApplyM (master adds, neighbours ascending)"""
+        b = self.b
+        buf = {}
+        for r in range(self.R):
+            v = vec[r].reshape(-1, b)
+            for kp, p in enumerate(self.peers[r]):
+                g = self.g_ex[r][kp]
+                if len(g):
+                    buf[(r, p)] = v[g].copy()
+                    v[g] = 0.0
+        for r in range(self.R):
+            v = vec[r].reshape(-1, b)
+            for kp, p in enumerate(self.peers[r]):
+                m = self.m_ex[r][kp]
+                if len(m):
+                    v[m] += buf[(p, r)]
+
+    def co2cu(self, vec):
+        """BufferM, send to the ghosts, ApplyG (ghost values are overwritten)"""
+        b = self.b
+        buf = {}
+        for r in range(self.R):
+            v = vec[r].reshape(-1, b)
+            for kp, p in enumerate(self.peers[r]):
+                m = self.m_ex[r][kp]
+                if len(m):
+                    buf[(r, p)] = v[m].copy()
+        for r in range(self.R):
+            v = vec[r].reshape(-1, b)
+            for kp, p in enumerate(self.peers[r]):
+                g = self.g_ex[r][kp]
+                if len(g):
+                    v[g] = buf[(p, r)]
+
+    # ---- HybridBaseSmoother::SmoothImplRES / SmoothImplRHS with CallStageKernelsImpl --------------------
+    def _stages(self, r, backward):
+        m1, mex, m2 = self.masks[r]
+        return (m2, mex, m1) if backward else (m1, mex, m2)
+
+    def smooth_res(self, x, res, backward, x_zero):
+        """x CUMULATED, res DISTRIBUTED (b - A x); afterwards x CUMULATED (new), res DISTRIBUTED"""
+        R = self.R
+        gx = None
+        if not x_zero:
+            gx = [O.spmv_add(self.Gb[r], 1.0, x[r], np.zeros_like(x[r])) for r in range(R)]
+        self.dis2co(res)                                   # StartDIS2CO ... FinishDIS2CO (overlap does not change values)
+        for r in range(R):
+            p1, pe, p2 = self._stages(r, backward)
+            for mask in (p1, pe):
+                O.gs_res(self.Mb[r], self.dinv[r], mask, x[r], res[r], backward)
+        # StartCO2CU happens before the last local stage; the last stage only touches local rows
+        for r in range(R):
+            p1, pe, p2 = self._stages(r, backward)
+            O.gs_res(self.Mb[r], self.dinv[r], p2, x[r], res[r], backward)
+        self.co2cu(x)
+        for r in range(R):
+            if gx is not None:
+                res[r] += gx[r]
+            O.spmv_add(self.Gb[r], -1.0, x[r], res[r])
+
+    def smooth_rhs(self, x, rhs, backward, x_zero):
+        """x CUMULATED, rhs DISTRIBUTED (not modified); afterwards x CUMULATED"""
+        R = self.R
+        t = [rhs[r].copy() for r in range(R)]
+        if not x_zero:
+            for r in range(R):
+                O.spmv_add(self.Gb[r], -1.0, x[r], t[r])
+        self.dis2co(t)
+        for r in range(R):
+            for mask in self._stages(r, backward):
+                O.gs_rhs(self.Mb[r], self.dinv[r], mask, x[r], t[r], backward)
+        self.co2cu(x)
+
+    def mult(self, x):
+        """HybridBaseMatrix::Mult: y = (M + G) x, x CUMULATED, y DISTRIBUTED"""
+        out = []
+        for r in range(self.R):
+            y = np.zeros_like(x[r])
+            O.spmv_add(self.Mb[r], 1.0, x[r], y)
+            O.spmv_add(self.Gb[r], 1.0, x[r], y)
+            out.append(y)
+        return out
+
+
+class OracleParAMG:
+    """AMGMatrix on a distributed hierarchy.
+    levels[l] = dict(A=[Bsr per rank], free=[mask or None per rank], peers=[...], ex=[...], P=[Bsr per rank]) for l < npar
+    ctr       = dict(maps=[local -> merged dof per rank]) for the contracted level npar
+    nested    = dict(prols=[Bsr ...], sm kwargs) : the serial hierarchy on the merged level (OracleAMG)"""
+
+    def __init__(self, A0, free0, peers0, ex0, prols, halos, ctr_maps, nested_prols, pinv=False, nested_free=None):
+        self.R = len(A0)
+        self.npar = len(prols)
+        self.levels = []
+        A, free, peers, ex = A0, free0, peers0, ex0
+        self.P, self.PT = [], []
+        for l in range(self.npar):
+            self.levels.append(HybridLevel(A, free, peers, ex, pinv))
+            Pl = prols[l]
+            PTl = [O.transpose(p) for p in Pl]
+            self.P.append(Pl); self.PT.append(PTl)
+            A = [O.restrict_matrix(PTl[r], A[r], Pl[r]) for r in range(self.R)]     # local Galerkin products (DISTRIBUTED sum)
+            free = [None] * self.R
+            peers, ex = halos[l + 1]
+        self.A_ctr = A
+        self.b_ctr = A[0].bh
+        # CtrMap::DoAssembleMatrix: the master sums the members' local matrices through the dof maps
+        self.maps = [np.asarray(m, np.int64) for m in ctr_maps]
+        N = int(max(int(m.max()) for m in self.maps if len(m)) + 1)
+        b = self.b_ctr
+        acc = sp.csr_matrix((N * b, N * b))
+        for r in range(self.R):
+            C = _expand(A[r]).tocoo()
+            sd = (self.maps[r][:, None] * b + np.arange(b)[None, :]).ravel()
+            acc = acc + sp.coo_matrix((C.data, (sd[C.row], sd[C.col])), shape=(N * b, N * b)).tocsr()
+        self.A_merged = O.Bsr.from_scipy(acc, b, b)
+        self.N = N
+        self.nested = O.OracleAMG(self.A_merged, nested_free, nested_prols, pinv=pinv)
+
+    def contracted_solve(self, rhs):
+        b = self.b_ctr
+        g = np.zeros(self.N * b)
+        for r in range(self.R):                                       # CtrMap::TransferF2C: master adds the members' values
+            np.add.at(g.reshape(-1, b), self.maps[r], rhs[r].reshape(-1, b))
+        xg = self.nested.apply(g)
+        return [xg.reshape(-1, b)[self.maps[r]].reshape(-1).copy() for r in range(self.R)]   # TransferC2F: CUMULATED values
+
+    def apply(self, b0):
+        """x = C b : b0[r] DISTRIBUTED local vectors -> CUMULATED x per rank; keeps the level vectors for inspection"""
+        R = self.R
+        rhs = [[np.ascontiguousarray(v, np.float64).copy() for v in b0]]
+        xs, ress = [], []
+        for l in range(self.npar):
+            L = self.levels[l]
+            x = [np.zeros_like(v) for v in rhs[l]]
+            res = [v.copy() for v in rhs[l]]
+            L.smooth_res(x, res, False, True)
+            xs.append(x); ress.append(res)
+            nxt = []
+            for r in range(R):
+                PT = self.PT[l][r]
+                nxt.append(O.spmv_add(PT, 1.0, res[r], np.zeros(PT.nrows * PT.bh)))
+            rhs.append(nxt)
+        xc = self.contracted_solve(rhs[self.npar])
+        self.level_x = [None] * self.npar + [xc]
+        for l in range(self.npar - 1, -1, -1):
+            L = self.levels[l]
+            x = xs[l]
+            for r in range(R):
+                O.spmv_add(self.P[l][r], 1.0, xc[r], x[r])
+            L.smooth_rhs(x, rhs[l], True, False)
+            xc = x
+            self.level_x[l] = x
+        self.level_rhs, self.level_res = rhs, ress
+        return xc
+
+    def pcg(self, rhs, tol=1e-8, maxsteps=200):
+        """CGSolver on parallel vectors: d DISTRIBUTED, w/s/u CUMULATED; inner products all-reduced"""
+        R = self.R
+        L0 = self.levels[0]
+        dot = lambda a, b: float(sum(np.dot(a[r], b[r]) for r in range(R)))
+        d = [np.ascontiguousarray(v, np.float64).copy() for v in rhs]
+        u = [np.zeros_like(v) for v in d]
+        w = self.apply(d)
+        s = [v.copy() for v in w]
+        wdn = dot(w, d)
+        err0 = np.sqrt(abs(wdn))
+        errs = [err0]
+        it = 0
+        if wdn != 0.0:
+            for it in range(1, maxsteps + 1):
+                q = L0.mult(s)
+                wd = wdn
+                alpha = wd / dot(s, q)
+                for r in range(R):
+                    u[r] += alpha * s[r]
+                    d[r] -= alpha * q[r]
+                w = self.apply(d)
+                wdn = dot(w, d)
+                beta = wdn / wd
+                for r in range(R):
+                    s[r] = w[r] + beta * s[r]
+                err = np.sqrt(abs(wd))
+                errs.append(err)
+                if err < tol * err0:
+                    break
+        return u, it, np.array(errs)

@@ -1,0 +1,159 @@
+"""GPU parity tests of the MULTI-RANK path (`-m gpu`): R ranks = R threads sharing ONE GPU (ThreadComm; the halo exchange is
+staged through host memory, the NCCL transport is exercised by bench.py --gpus N and tests/run_nccl_check.py).
+The CUDA path of every rank is compared with the multi-rank CPU oracle (oracle/oracle_par.py) fed the SAME hierarchy
+(local prolongations, coarse sharing lists, contraction maps): V-cycle vectors <= 1e-10 relative, identical PCG iteration
+counts, and -- independently of the oracle -- the PCG solution against the single-rank solve of the assembled problem."""
+import numpy as np
+import pytest
+
+import ngsamg_b200 as ng
+from helpers import rand, rel, to_oracle
+from ngsamg_b200 import parallel as par
+from ngsamg_b200 import synthetic as S
+from oracle import oracle as O
+from oracle import oracle_par as OP
+
+pytestmark = pytest.mark.gpu
+
+TOL_VCYCLE = 1e-10
+
+
+def _build_ranks(parts, cls, b, **flags):
+    R = len(parts)
+
+    def fn(r, comm):
+        p = parts[r]
+        A = ng.SparseMatrix(p["n"], p["n"], b, b, p["rowptr"], p["col"], p["val"])
+        xyz = p["xyz"] if b > 1 else None
+        pc = cls(A, par.Halo(p["peers"], p["ex"]), comm, p["free"], vertex_xyz=xyz, **flags)
+        return pc
+
+    return par.run_ranks(R, fn)
+
+
+def _oracle_for(parts, pcs, b, pinv=False):
+    R = len(parts)
+    npar = pcs[0].GetNParallelLevels()
+    assert all(pc.GetNParallelLevels() == npar for pc in pcs)
+    prols = [[to_oracle(pcs[r].GetProlongation(l)) for r in range(R)] for l in range(npar)]
+    halos = []
+    for l in range(npar + 1):
+        hs = [pcs[r].GetHalo(l) for r in range(R)]
+        halos.append(([list(h.peers) for h in hs], [[np.asarray(e) for e in h.ex] for h in hs]))
+    maps = [pcs[0].GetContractionMap(r) for r in range(R)]
+    nested = pcs[0].GetContracted()
+    nprols = [to_oracle(P) for P in nested.GetMap()]
+    A0 = [O.Bsr(p["n"], p["n"], b, b, p["rowptr"], p["col"], p["val"]) for p in parts]
+    return OP.OracleParAMG(A0, [p["free"] for p in parts], halos[0][0], halos[0][1], prols, halos, maps, nprols, pinv=pinv), npar
+
+
+def _collective(pcs, fn):
+    return par.run_ranks(len(pcs), lambda r, comm: fn(r, pcs[r]))
+
+
+@pytest.mark.parametrize("grid", [(1, 1, 2), (1, 2, 2), (1, 1, 3), (2, 2, 2)])
+def test_parallel_vcycle_and_pcg_match_oracle(grid):
+    dims = (13, 11, 15)
+    parts = S.partition_poisson3d(*dims, grid=grid)
+    R = len(parts)
+    pcs = _build_ranks(parts, par.h1_scal_par, 1, ngs_amg_max_coarse_size=15, ngs_amg_b200_ctr_nv=150)
+    amg, npar = _oracle_for(parts, pcs, 1)
+    assert npar >= 1, "the test must exercise at least one distributed level"
+    # the hybrid split itself
+    for r in range(R):
+        M, G, md = pcs[r].GetHybrid(0)
+        assert abs(M.to_scipy() - amg.levels[0].M[r]).max() < 1e-13
+        assert abs(G.to_scipy() - amg.levels[0].G[r]).max() == 0
+        assert np.allclose(md, amg.levels[0].md[r].ravel(), rtol=1e-13, atol=0)
+    # V-cycle: DISTRIBUTED random rhs per rank
+    b = [rand(40 + r, p["n"]) * p["free"] for r, p in enumerate(parts)]
+    xo = amg.apply(b)
+
+    def ap(r, pc):
+        x = np.zeros(parts[r]["n"])
+        pc.Mult(b[r], x)
+        return x, [pc.GetLevelVector("x", l) for l in range(npar + 1)], [pc.GetLevelVector("rhs", l) for l in range(npar + 1)]
+
+    got = _collective(pcs, ap)
+    for r in range(R):
+        assert rel(got[r][0], xo[r]) < TOL_VCYCLE, (r, rel(got[r][0], xo[r]))
+        for l in range(npar + 1):
+            assert rel(got[r][2][l], amg.level_rhs[l][r]) < TOL_VCYCLE, ("rhs", r, l)
+            assert rel(got[r][1][l], amg.level_x[l][r]) < TOL_VCYCLE, ("x", r, l)
+    # the result is CUMULATED: shared dofs agree on all sharers
+    for r in range(R):
+        for kp, q in enumerate(parts[r]["peers"]):
+            kq = list(parts[q]["peers"]).index(r)
+            assert np.allclose(got[r][0][parts[r]["ex"][kp]], got[q][0][parts[q]["ex"][kq]], rtol=0, atol=1e-14 * np.abs(xo[r]).max())
+    # PCG
+    rhs = [p["rhs"] * p["free"] for p in parts]
+    uo, ito, erro = amg.pcg(rhs, tol=1e-8, maxsteps=100)
+
+    def solve(r, pc):
+        x = np.zeros(parts[r]["n"])
+        it, errs = pc._pcg(rhs[r], x, 1e-8, 100)
+        return x, it, errs
+
+    sol = _collective(pcs, solve)
+    for r in range(R):
+        assert sol[r][1] == ito, (sol[r][1], ito)
+        assert rel(sol[r][0], uo[r]) < 1e-8
+        assert np.allclose(sol[r][2], erro, rtol=1e-7)
+    # independent check: the assembled global problem solved by the single-rank path
+    g = S.poisson3d_kuhn(*dims)
+    Ag = ng.SparseMatrix(g["n"], g["n"], 1, 1, g["rowptr"], g["col"], g["val"])
+    pcg = ng.h1_scal(Ag, g["free"], ngs_amg_max_coarse_size=15)
+    xg = ng.CGSolver(Ag, pcg, maxsteps=200, tol=1e-12).Solve(g["rhs"] * g["free"])
+    for r in range(R):
+        assert rel(sol[r][0], xg[parts[r]["gidx"]]) < 1e-6
+
+
+def test_parallel_elasticity_matches_oracle():
+    parts = S.partition_elasticity3d(9, 5, 9, 2)
+    pcs = _build_ranks(parts, par.elast_3d_par, 3, ngs_amg_max_coarse_size=10, ngs_amg_b200_ctr_nv=60)
+    amg, npar = _oracle_for(parts, pcs, 3, pinv=True)
+    assert npar >= 1
+    R = len(parts)
+    b = [rand(60 + r, 3 * p["n"]) * np.repeat(p["free"], 3) for r, p in enumerate(parts)]
+    xo = amg.apply(b)
+
+    def ap(r, pc):
+        x = np.zeros(3 * parts[r]["n"])
+        pc.Mult(b[r], x)
+        return x
+
+    got = _collective(pcs, ap)
+    for r in range(R):
+        assert rel(got[r], xo[r]) < TOL_VCYCLE, (r, rel(got[r], xo[r]))
+    rhs = [p["rhs"] * np.repeat(p["free"], 3) for p in parts]
+    uo, ito, _ = amg.pcg(rhs, tol=1e-6, maxsteps=100)
+
+    def solve(r, pc):
+        x = np.zeros(3 * parts[r]["n"])
+        it, errs = pc._pcg(rhs[r], x, 1e-6, 100)
+        return x, it
+
+    sol = _collective(pcs, solve)
+    for r in range(R):
+        assert sol[r][1] == ito
+        assert rel(sol[r][0], uo[r]) < 1e-7
+
+
+def test_parallel_apply_is_symmetric():
+    """(C b1, b2) == (b1, C b2) for the multi-rank operator (global inner products of CUMULATED x DISTRIBUTED)"""
+    parts = S.partition_poisson3d(11, 11, 13, grid=(1, 1, 2))
+    pcs = _build_ranks(parts, par.h1_scal_par, 1, ngs_amg_max_coarse_size=15, ngs_amg_b200_ctr_nv=150)
+    b1 = [rand(70 + r, p["n"]) * p["free"] for r, p in enumerate(parts)]
+    b2 = [rand(80 + r, p["n"]) * p["free"] for r, p in enumerate(parts)]
+
+    def ap(bb):
+        def f(r, pc):
+            x = np.zeros(parts[r]["n"])
+            pc.Mult(bb[r], x)
+            return x
+        return _collective(pcs, f)
+
+    x1, x2 = ap(b1), ap(b2)
+    s12 = sum(np.dot(x1[r], b2[r]) for r in range(2))
+    s21 = sum(np.dot(b1[r], x2[r]) for r in range(2))
+    assert abs(s12 - s21) < 1e-10 * abs(s12)

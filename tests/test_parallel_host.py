@@ -1,0 +1,107 @@
+"""CPU tests (`-m "not gpu"`) of the multi-rank HOST logic: DCC master/ghost lists, hybrid M/G split, modified diagonal and the
+stage order of the hybrid smoother (ngsamg_b200/csrc/par.cpp through the C ABI) against the multi-rank oracle -- with the ranks as
+threads (ThreadComm) and as world_size-2 gloo processes (TorchDistComm) -- plus the partitioned problem generator."""
+import os
+import socket
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+import ngsamg_b200 as ng
+from ngsamg_b200 import parallel as par
+from ngsamg_b200 import synthetic as S
+from oracle import oracle as O
+from oracle import oracle_par as OP
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.mark.parametrize("grid", [(1, 1, 2), (1, 2, 2), (2, 2, 2)])
+def test_partition_sums_to_global(grid):
+    g = S.poisson3d_kuhn(7, 6, 9)
+    A = sp.csr_matrix((g["val"], g["col"], g["rowptr"]), shape=(g["n"], g["n"]))
+    B = sp.csr_matrix(A.shape)
+    rhs = np.zeros(g["n"])
+    parts = S.partition_poisson3d(7, 6, 9, grid=grid)
+    for r, p in enumerate(parts):
+        Al = sp.csr_matrix((p["val"], p["col"], p["rowptr"]), shape=(p["n"], p["n"])).tocoo()
+        B = B + sp.coo_matrix((Al.data, (p["gidx"][Al.row], p["gidx"][Al.col])), shape=A.shape).tocsr()
+        rhs += np.bincount(p["gidx"], weights=p["rhs"], minlength=g["n"])
+        assert (p["free"] == g["free"][p["gidx"]]).all()
+        # halo lists are pairwise consistent: k-th shared dof here == k-th shared dof there
+        for kp, q in enumerate(p["peers"]):
+            kq = list(parts[q]["peers"]).index(r)
+            assert np.array_equal(p["gidx"][p["ex"][kp]], parts[q]["gidx"][parts[q]["ex"][kq]])
+    assert abs(A - B).max() < 1e-15 and abs(rhs - g["rhs"]).max() < 1e-18
+
+
+@pytest.mark.parametrize("grid", [(1, 1, 2), (1, 1, 3), (1, 2, 2), (2, 2, 2)])
+def test_hybrid_split_threads(grid):
+    parts = S.partition_poisson3d(7, 6, 9, grid=grid)
+    R = len(parts)
+
+    def fn(r, comm):
+        p = parts[r]
+        A = ng.SparseMatrix(p["n"], p["n"], 1, 1, p["rowptr"], p["col"], p["val"])
+        return par.hybrid_host(A, par.Halo(p["peers"], p["ex"]), comm, p["free"])
+
+    res = par.run_ranks(R, fn)
+    HL = OP.HybridLevel([O.Bsr(p["n"], p["n"], 1, 1, p["rowptr"], p["col"], p["val"]) for p in parts], [p["free"] for p in parts],
+                        [p["peers"] for p in parts], [p["ex"] for p in parts])
+    for r in range(R):
+        assert abs(res[r]["M"].to_scipy() - HL.M[r]).max() < 1e-14
+        assert abs(res[r]["G"].to_scipy() - HL.G[r]).max() == 0
+        assert np.allclose(res[r]["mod_diag"], HL.md[r].ravel(), rtol=1e-13, atol=0)
+        assert (res[r]["master"].astype(bool) == HL.master[r]).all()
+        m1, mex, m2 = HL.masks[r]
+        exp = np.concatenate([np.flatnonzero(m1), np.flatnonzero(mex), np.flatnonzero(m2)])
+        assert np.array_equal(np.argsort(res[r]["sweep_rank"])[:len(exp)], exp), "stage order LOC_PART_1 | EX_PART | LOC_PART_2"
+
+
+def test_hybrid_split_blocks_threads():
+    parts = S.partition_elasticity3d(5, 4, 7, 2)
+
+    def fn(r, comm):
+        p = parts[r]
+        A = ng.SparseMatrix(p["n"], p["n"], 3, 3, p["rowptr"], p["col"], p["val"])
+        return par.hybrid_host(A, par.Halo(p["peers"], p["ex"]), comm, p["free"])
+
+    res = par.run_ranks(2, fn)
+    HL = OP.HybridLevel([O.Bsr(p["n"], p["n"], 3, 3, p["rowptr"], p["col"], p["val"]) for p in parts], [p["free"] for p in parts],
+                        [p["peers"] for p in parts], [p["ex"] for p in parts])
+    for r in range(2):
+        scale = abs(HL.M[r]).max()
+        assert abs(res[r]["M"].to_scipy() - HL.M[r]).max() < 1e-14 * scale
+        assert abs(res[r]["G"].to_scipy() - HL.G[r]).max() == 0
+        assert np.allclose(res[r]["mod_diag"], HL.md[r].ravel(), rtol=1e-12, atol=1e-14 * scale)
+
+
+def test_hybrid_operator_is_the_global_operator():
+    """sum over ranks of (M_r + G_r) x_r == A x for a consistent (CUMULATED) x  -- HybridBaseMatrix::Mult, hybrid_matrix.cpp:433-453"""
+    g = S.poisson3d_kuhn(7, 6, 9)
+    A = sp.csr_matrix((g["val"], g["col"], g["rowptr"]), shape=(g["n"], g["n"]))
+    parts = S.partition_poisson3d(7, 6, 9, grid=(1, 2, 2))
+    HL = OP.HybridLevel([O.Bsr(p["n"], p["n"], 1, 1, p["rowptr"], p["col"], p["val"]) for p in parts], [p["free"] for p in parts],
+                        [p["peers"] for p in parts], [p["ex"] for p in parts])
+    x = np.random.default_rng(3).standard_normal(g["n"])
+    y = HL.mult([x[p["gidx"]].copy() for p in parts])
+    tot = np.zeros(g["n"])
+    for p, yr in zip(parts, y):
+        tot += np.bincount(p["gidx"], weights=yr, minlength=g["n"])
+    assert np.allclose(tot, A @ x, rtol=1e-12, atol=1e-13)
+
+
+def test_hybrid_split_over_gloo():
+    """world_size-2 torch.distributed (gloo) run of the same host path: the communicator callbacks are backed by isend/irecv"""
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", str(port), os.path.join(ROOT, "tests", "_gloo_worker.py")]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-4000:]
+    assert "rank 0 ok" in out.stdout and "rank 1 ok" in out.stdout
