@@ -138,7 +138,7 @@ int64_t ngsamg_b200_launch_count(ngsamg_b200_t *h);
  *   ex_dofs[ex_ptr[k] .. ex_ptr[k+1]), ascending, and the k-th DOF shared with rank p here is the k-th DOF shared with this
  *   rank on p (NGSolve's convention).  peers ascending.
  * ngsamg_comm  == the communicator.  Setup-phase (host) traffic goes through two caller-supplied callbacks -- an NGSolve
- *   adapter implements them with its NgMPI_Comm, the test harness with torch.distributed / threads:
+ *   adapter implements them with its NgMPI_Comm, the test harness with a process group (gloo) or plain threads:
  *     exchange      : post sendbuf[k] (sendbytes[k] bytes) to peers[k] and receive recvbytes[k] bytes from it into recvbuf[k],
  *                     for all k, then return (MPI_Isend/Irecv + Waitall); sizes are known to both sides.
  *     allreduce_sum : in-place sum over all ranks of n doubles (every rank receives the result).
@@ -174,7 +174,7 @@ int ngsamg_b200_create_parallel(const char *type, const ngsamg_csr *A, const uin
                                 const ngsamg_halo *halo, const ngsamg_comm *comm, const char *const *flag_keys,
                                 const char *const *flag_vals, int nflags, int device, ngsamg_b200_t **out);
 
-/* NCCL plumbing for the device data path (the library dlopens libnccl.so.2; no torch types): rank 0 creates the 128-byte
+/* NCCL plumbing for the device data path (the library dlopens libnccl.so.2; plain pointers only): rank 0 creates the 128-byte
  * unique id, the host application broadcasts it, every rank calls comm_init with its device.  comm_destroy frees it. */
 int ngsamg_b200_nccl_unique_id(char id[128]);
 int ngsamg_b200_nccl_comm_init(const char id[128], int rank, int size, int device, void **nccl_comm);
