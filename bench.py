@@ -33,8 +33,9 @@ TOL = 1e-8
 
 
 def rank_workload(n, rank, world):
-    """grid size of the subdomain problem a rank solves.  The multi-GPU path of this round runs independent subdomain
-    problems of identical size on every rank (weak scaling, no data-path collective yet)."""
+    """grid size of the subdomain a rank owns: n^3 vertices per GPU (weak scaling).  At N > 1 the ranks solve ONE global problem:
+    the n x n x ((n-1)N+1) mesh cut into N z-slabs, interface planes shared (NGSolve-style duplicated DOFs), hybrid smoothers + NCCL
+    halo exchange per sweep, coarse levels contracted onto rank 0."""
     return n
 
 
@@ -191,16 +192,28 @@ def main():
     torch.cuda.set_device(local_rank)
     if world > 1:
         import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        # torch.distributed is plumbing only: gloo carries the setup-phase host callbacks and the unique-id broadcast, the
+        # library opens its own NCCL communicator for the halo exchange / dot products / coarse gather
+        dist.init_process_group("cpu:gloo,cuda:nccl")
 
     def barrier():
         if world > 1:
-            dist.barrier()
+            dist.all_reduce(torch.zeros(1, device="cuda"))   # NCCL all-reduce as the barrier (the group mixes gloo and nccl)
         torch.cuda.synchronize()
 
     n = rank_workload(args.n, rank, world)
     t0 = time.time()
-    p, A = make_problem(n, args.problem)
+    comm = None
+    if world > 1:
+        if args.problem != "poisson":
+            raise SystemExit("bench.py: the multi-GPU bench runs the Poisson workload")
+        from ngsamg_b200 import parallel as par
+        from ngsamg_b200 import synthetic as S
+        p = S.slab_poisson3d(n, n, n, world, rank)
+        A = ng.SparseMatrix(p["n"], p["n"], 1, 1, p["rowptr"], p["col"], p["val"])
+        comm = par.TorchDistComm(use_nccl=os.environ.get("NGSAMG_BENCH_TRANSPORT", "nccl") == "nccl", device=local_rank)
+    else:
+        p, A = make_problem(n, args.problem)
     gen_s = time.time() - t0
     elast = args.problem == "elasticity"
     if elast:
@@ -213,7 +226,10 @@ def main():
             k, v = kv.split("=", 1)
             extra["ngs_amg_" + k.strip()] = v.strip()
     tol = 1e-6 if elast else TOL       # the reference's elasticity tests solve to 1e-6 (tests/elasticity/amg_utils.py:439)
-    if elast:
+    if world > 1:
+        args.no_multicolor = True
+        pc = par.h1_scal_par(A, par.Halo(p["peers"], p["ex"]), comm, p["free"], device=local_rank, **extra)
+    elif elast:
         pc = ng.elast_3d(A, p["free"], vertex_xyz=p["xyz"], device=local_rank, **extra)
     else:
         pc = ng.h1_scal(A, p["free"], device=local_rank, **extra)
@@ -269,6 +285,15 @@ def main():
     clocks = sampler.stop()
     vcycle_ms = float(np.mean(vms))
     vbytes = pc.VCycleBytes()
+    ndof_global = ndof
+    if world > 1:
+        # whole-job figures: bytes of all ranks, V-cycle time = max over ranks, global DOF count = master DOFs
+        agg = torch.tensor([vbytes, float(ndof - (len(p["ex"][0]) if rank > 0 else 0))], dtype=torch.float64, device="cuda")
+        dist.all_reduce(agg)
+        vt = torch.tensor([vcycle_ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(vt, op=dist.ReduceOp.MAX)
+        vbytes, ndof_global, vcycle_ms = agg[0].item(), int(agg[1].item()), vt.item()
+    peak_scale = world
     peak, peak_src = measured_peak()
     kern = {}
     for name in ("gs_tri_fwd", "gs_upass", "gs_lpass", "gs_tri_bwd", "spmv", "restrict", "prolong"):
@@ -298,6 +323,20 @@ def main():
     for l in range(pc.GetNLevels()):
         i = pc.level_info(l)
         levels.append({"n": int(i.n), "b": int(i.b), "nnz": int(i.nnz), "gs_depth": int(i.gs_depth)})
+    par_info = None
+    if world > 1:
+        npar = pc.GetNParallelLevels()
+        for l in range(len(levels)):
+            levels[l]["distributed"] = l < npar
+            levels[l]["rank0_local"] = True
+        nested = pc.GetContracted()
+        if nested is not None:
+            for l in range(nested.GetNLevels()):
+                i = nested.level_info(l)
+                levels.append({"n": int(i.n), "b": int(i.b), "nnz": int(i.nnz), "gs_depth": int(i.gs_depth), "contracted_on_rank0": True})
+        par_info = {"distributed_levels": npar, "transport": "nccl p2p" if comm.nccl else "host-staged (gloo callbacks)",
+                    "host_exchanges_setup": comm.n_exchange, "halo_dofs_per_interface": int(len(p["ex"][0])),
+                    "global_dims": list(p["global_dims"])}
 
     # ---- optional variant, reported separately: multicolour Gauss-Seidel on the fine level ------------------------------
     variant = None
@@ -334,25 +373,30 @@ def main():
 
     if rank == 0:
         line = {
-            "metric": "pcg_amg_solve_dofs_per_s", "value": world * ndof / solve_s, "unit": "DOF/s", "n_gpus": world,
+            "metric": "pcg_amg_solve_dofs_per_s", "value": ndof_global / solve_s, "unit": "DOF/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": solve_s * 1e3, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": ("3D Poisson P1 unit cube (Kuhn tets), %d^3 = %d DOFs per GPU, h1_scal + CG to 1e-8" % (n, ndof)) if not elast else
+            "config": {"workload": ("3D Poisson P1 (Kuhn tets), ONE global problem of %d x %d x %d = %d DOFs cut into %d z-slabs of %d^3 vertices (one per GPU, "
+                                    "interface planes shared), h1_scal + CG to 1e-8, hybrid Gauss-Seidel + NCCL halo exchange" % (tuple(p["global_dims"]) + (ndof_global, world, n))) if world > 1 else
+                                   ("3D Poisson P1 unit cube (Kuhn tets), %d^3 = %d DOFs per GPU, h1_scal + CG to 1e-8" % (n, ndof)) if not elast else
                                    ("3D linear elasticity P1 beam (Kuhn tets), %d vertices = %d DOFs per GPU, elast_3d (3x3 fine / 6x6 coarse blocks) + CG to 1e-6" % (p["n"], ndof)),
                        "tol": tol, "levels": levels, "operator_complexity": pc.GetOC(),
-                       "parallelism": "1 GPU" if world == 1 else "%d independent subdomain replicas (no halo exchange yet)" % world,
+                       "parallelism": "1 GPU" if world == 1 else "%d subdomains, one per GPU; DIS2CO/CO2CU halo exchange per sweep, all-reduced CG dot products, coarse levels contracted onto rank 0" % world,
+                       "multi_gpu": par_info,
                        "l2": "inputs larger than L2 (level-0 matrix %.1f GB)" % (levels[0]["nnz"] * (8 * levels[0]["b"] ** 2 + 4) / 1e9)},
             "solve_s": solve_s, "iterations": iters, "setup_s": setup_s, "setup_rap_ms": pc.LastMs("rap"),
             "setup_host_ms": pc.LastMs("host"), "gen_s": gen_s, "wall_s_timed_region": wall_s,
             "vcycle_ms": vcycle_ms, "vcycle_bytes": vbytes, "vcycle_gbs": vbytes / vcycle_ms / 1e6,
-            "vcycle_frac_of_peak": vbytes / vcycle_ms / 1e6 / peak,
+            "vcycle_frac_of_peak": vbytes / vcycle_ms / 1e6 / (peak * peak_scale),
             "kernels_level0": kern, "kernel_ms_by_level": by_level, "roofline": roof, "variant_multicolor": variant, "cpu_baseline": cpu,
-            "e2e": {"value": world * ndof / e2e_s, "unit": "DOF/s", "h2d_bytes_per_step": 8 * ndof, "d2h_bytes_per_step": 8 * ndof,
+            "e2e": {"value": ndof_global / e2e_s, "unit": "DOF/s", "h2d_bytes_per_step": 8 * ndof, "d2h_bytes_per_step": 8 * ndof,
                     "solve_s": e2e_s},
             "gpu_launches": int(launches), "clocks": clocks, "flags": extra,
         }
         print(json.dumps(line))
     if world > 1:
+        del cg, pc
+        comm.close()
         dist.destroy_process_group()
 
 

@@ -1112,7 +1112,7 @@ void Amg::finalize_parallel()
   copt.omega = flags.num("sp_omega", 1.0);
   copt.smooth = flags.str("prol_type", "semi_aux_smoothed") != "piecewise";
   copt.rounds = (int)flags.num("spw_rounds", 3);
-  use_graph = flags.flag("b200_cuda_graph_par", false) && nccl;   // halo exchanges inside a captured graph: opt-in
+  use_graph = flags.flag("b200_cuda_graph_par", nccl != nullptr) && nccl;   // NCCL halo exchanges are captured into the V-cycle graph
 
   d_err = dev_alloc<int>(1);
   NGB_CUDA(cudaMemsetAsync(d_err, 0, sizeof(int), st));
@@ -2209,7 +2209,7 @@ int ngsamg_b200_num_levels(ngsamg_b200_t *h) { return (h && h->amg.finalized) ? 
 
 static void level_bytes(const Level &L, i64 &m, i64 &p, i64 &v)
 {
-  m = L.nnz * (8 * (i64)L.b * L.b + 4) + 4 * (L.n + 1);
+  m = (L.par ? L.nnz_m + L.nnz_g : L.nnz) * (8 * (i64)L.b * L.b + 4) + 4 * (L.n + 1);   // hybrid level: M and G are each read once per sweep
   p = L.hP.nnz() ? L.hP.nnz() * (8 * (i64)L.b * L.bc + 4) + 4 * (L.n + 1) : 0;
   v = 8 * L.n * L.b;
 }
@@ -2291,6 +2291,18 @@ double ngsamg_b200_vcycle_bytes(ngsamg_b200_t *h)
   // B_V = sum_{l<L} [ 2(M_l + D_l) + 2 P_l + 9 v_l + 2 v_{l+1} ] + B_coarse        
   auto &lev = h->amg.lev;
   double B = 0;
+  if (h->amg.par) {
+    // this rank's share: its distributed levels (+ the contracted serial hierarchy on rank 0)
+    for (int l = 0; l < h->amg.npar; l++) {
+      i64 m, p, v, m2, p2, v2;
+      level_bytes(*lev[l], m, p, v);
+      level_bytes(*lev[l + 1], m2, p2, v2);
+      const double D = 8.0 * lev[l]->n * lev[l]->b * lev[l]->b;
+      B += 2.0 * (m + D) + 2.0 * p + 9.0 * v + 2.0 * v2;
+    }
+    if (h->amg.nested) B += ngsamg_b200_vcycle_bytes(reinterpret_cast<ngsamg_b200_t *>(h->amg.nested.get()));
+    return B;
+  }
   for (size_t l = 0; l + 1 < lev.size(); l++) {
     i64 m, p, v, m2, p2, v2;
     level_bytes(*lev[l], m, p, v);

@@ -382,3 +382,22 @@ def partition_elasticity3d(nx, ny, nz, nparts=2, rank=None, **kw):
         loc["peers"], loc["ex"] = halos_from_global_ids(gids, r)
         out.append(loc)
     return out if rank is None else out[rank]
+
+
+def slab_poisson3d(nx, ny, nz_per_rank, world, rank, dirichlet=("x0", "y1")):
+    """rank's local problem of a z-slab partition of the nx x ny x ((nz_per_rank-1)*world+1) mesh -- partition_poisson3d without the
+    global index arrays (bench sizes): every rank owns nz_per_rank vertex planes, the first / last plane is shared with rank-1 / rank+1."""
+    nzg = (nz_per_rank - 1) * world + 1
+    h = 1.0 / (max(nx, ny, nzg) - 1)
+    loc = poisson3d_kuhn(nx, ny, nz_per_rank, dirichlet=tuple(t for t in dirichlet if t[0] != "z"), h=h,
+                         origin=(0, 0, rank * (nz_per_rank - 1)))
+    plane = nx * ny
+    peers, ex = [], []
+    if rank > 0:
+        peers.append(rank - 1)
+        ex.append(np.arange(plane, dtype=np.int32))
+    if rank < world - 1:
+        peers.append(rank + 1)
+        ex.append(np.arange(plane * (nz_per_rank - 1), plane * nz_per_rank, dtype=np.int32))
+    loc["peers"], loc["ex"], loc["global_dims"] = peers, ex, (nx, ny, nzg)
+    return loc
