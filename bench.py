@@ -161,7 +161,7 @@ def run_reference(args):
                                    "NGSolve/MPI)" % (n, r["ndof"])},
         "e2e": {"value": val, "unit": "DOF/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line))
+    print(json.dumps(line), flush=True)
 
 
 def main():
@@ -181,8 +181,17 @@ def main():
         run_reference(args)
         return
 
+    import faulthandler
     import torch
     import ngsamg_b200 as ng
+
+    # a stuck collective must not burn the whole job: dump the Python stacks and exit after NGSAMG_BENCH_WATCHDOG_S seconds
+    faulthandler.dump_traceback_later(int(os.environ.get("NGSAMG_BENCH_WATCHDOG_S", "1500")), exit=True)
+    t_start = time.time()
+
+    def progress(msg):
+        if os.environ.get("NGSAMG_BENCH_VERBOSE"):
+            print("[bench r%s %.1fs] %s" % (os.environ.get("RANK", "0"), time.time() - t_start, msg), file=sys.stderr, flush=True)
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -215,6 +224,7 @@ def main():
     else:
         p, A = make_problem(n, args.problem)
     gen_s = time.time() - t0
+    progress("problem generated")
     elast = args.problem == "elasticity"
     if elast:
         args.no_cpu_baseline = True
@@ -234,6 +244,7 @@ def main():
     else:
         pc = ng.h1_scal(A, p["free"], device=local_rank, **extra)
     setup_s = time.time() - t0
+    progress("hierarchy built")
     ndof = p["n"] * A.bh
     rhs_h = np.ascontiguousarray(p["rhs"])
     x_h = np.zeros(ndof)
@@ -244,6 +255,7 @@ def main():
     # ---- device-resident solve (value) ---------------------------------------------------------------
     for _ in range(args.warmup):
         cg.Solve(rhs_d, x_d)
+        progress("warm-up solve done (%d iterations)" % cg.iterations)
     sampler = ClockSampler(local_rank)
     barrier()
     sampler.start()
@@ -264,6 +276,7 @@ def main():
     solve_s = dev_s / args.steps
 
     # ---- end-to-end through the C ABI with host buffers (e2e) ----------------------------------------
+    progress("timed solves done")
     cg.Solve(rhs_h, x_h)
     barrier()
     e0 = time.time()
@@ -276,6 +289,7 @@ def main():
     e2e_s = e2e.item() / args.steps
 
     # ---- V-cycle alone + per-kernel roofline (level 0) -------------------------------------------------
+    progress("e2e solves done")
     for _ in range(3):
         pc.Mult(rhs_d, x_d)
     vms = []
@@ -393,11 +407,16 @@ def main():
                     "solve_s": e2e_s},
             "gpu_launches": int(launches), "clocks": clocks, "flags": extra,
         }
-        print(json.dumps(line))
+        print(json.dumps(line), flush=True)
     if world > 1:
+        # the captured V-cycle graph pins the NCCL communicator: destroy the hierarchy first, then the communicator
+        nested = None
+        pc.close()
         del cg, pc
+        barrier()
         comm.close()
         dist.destroy_process_group()
+    faulthandler.cancel_dump_traceback_later()
 
 
 if __name__ == "__main__":

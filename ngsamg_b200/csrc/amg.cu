@@ -712,6 +712,24 @@ void Amg::build_transfer_layout(Level &F, Level &C)
     for (i64 c = 0; c < C.n; c++) bucket[PT.rowptr[c + 1] - PT.rowptr[c] + 1]++;
     for (i64 l = 0; l <= maxlen; l++) bucket[l + 1] += bucket[l];
     std::vector<i32> spos(C.n), rowmap(npt, -1);
+    if (flags.flag("b200_pt_locality", true)) {
+      // inside a length class, order the rows by the first fine row they read: consecutive restriction rows then gather from the
+      // same sectors of the fine residual (the coarse numbering is colour-major, i.e. spatially incoherent with the fine one)
+      std::vector<i32> key(C.n, 0);
+      parallel_for(C.n, [&](i64 lo, i64 hi) {
+        for (i64 c = lo; c < hi; c++) {
+          i32 m = std::numeric_limits<i32>::max();
+          for (i64 k = PT.rowptr[c]; k < PT.rowptr[c + 1]; k++) m = std::min(m, F.perm[PT.col[k]]);
+          key[c] = m;
+        }
+      });
+      for (i64 c = 0; c < C.n; c++) order[c] = (i32)c;
+      std::sort(order.begin(), order.end(), [&](i32 a, i32 b) {
+        const i64 la = PT.rowptr[a + 1] - PT.rowptr[a], lb = PT.rowptr[b + 1] - PT.rowptr[b];
+        return la < lb || (la == lb && (key[a] < key[b] || (key[a] == key[b] && a < b)));
+      });
+      for (i64 s2 = 0; s2 < C.n; s2++) { spos[order[s2]] = (i32)s2; rowmap[s2] = C.perm[order[s2]]; }
+    } else
     for (i64 pc = 0; pc < C.npad; pc++) {
       const i32 c = inv[pc];
       if (c < 0) continue;

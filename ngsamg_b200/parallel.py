@@ -234,6 +234,12 @@ class ParallelPreconditioner(Preconditioner):
                 msg += " [callback: %r]" % (self.comm.error,)
             raise NgsAMGError(msg)
 
+    def close(self):
+        """destroy the device hierarchy now (a captured V-cycle graph pins the NCCL communicator until it is gone)"""
+        if self._h:
+            self._lib.ngsamg_b200_destroy(self._h)
+            self._h = None
+
     def Mult(self, b, x):
         self._check(self._lib.ngsamg_b200_apply(self._h, _lib.ptr(b), _lib.ptr(x)))
 
