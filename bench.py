@@ -34,7 +34,8 @@ TOL = 1e-8
 
 def rank_workload(n, rank, world):
     """grid size of the subdomain a rank owns: n^3 vertices per GPU (weak scaling).  At N > 1 the ranks solve ONE global problem:
-    the n x n x ((n-1)N+1) mesh cut into N z-slabs, interface planes shared (NGSolve-style duplicated DOFs), hybrid smoothers + NCCL
+    the mesh is cut into N sub-boxes of n^3 vertices (1x1x2, 1x2x2, 2x2x2 for N = 2, 4, 8: 621^3 = 239 M DOFs at N = 8 with the
+    default n = 311, BASELINE.json configs[3]); interface DOFs are shared (NGSolve-style duplicated DOFs), hybrid smoothers + NCCL
     halo exchange per sweep, coarse levels contracted onto rank 0."""
     return n
 
@@ -182,6 +183,7 @@ def main():
         return
 
     import faulthandler
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # NCCL's banner / warnings go to stderr: stdout carries ONE JSON line
     import torch
     import ngsamg_b200 as ng
 
@@ -191,7 +193,9 @@ def main():
 
     def progress(msg):
         if os.environ.get("NGSAMG_BENCH_VERBOSE"):
-            print("[bench r%s %.1fs] %s" % (os.environ.get("RANK", "0"), time.time() - t_start, msg), file=sys.stderr, flush=True)
+            import resource
+            print("[bench r%s %.1fs, peak rss %.1f GB] %s" % (os.environ.get("RANK", "0"), time.time() - t_start,
+                                                             resource.getrusage(resource.RUSAGE_SELF).ru_maxrss / 1048576.0, msg), file=sys.stderr, flush=True)
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -218,7 +222,8 @@ def main():
             raise SystemExit("bench.py: the multi-GPU bench runs the Poisson workload")
         from ngsamg_b200 import parallel as par
         from ngsamg_b200 import synthetic as S
-        p = S.slab_poisson3d(n, n, n, world, rank)
+        grid = S.bench_grid(world)
+        p = S.box_poisson3d(n, grid, rank)
         A = ng.SparseMatrix(p["n"], p["n"], 1, 1, p["rowptr"], p["col"], p["val"])
         comm = par.TorchDistComm(use_nccl=os.environ.get("NGSAMG_BENCH_TRANSPORT", "nccl") == "nccl", device=local_rank)
     else:
@@ -238,7 +243,11 @@ def main():
     tol = 1e-6 if elast else TOL       # the reference's elasticity tests solve to 1e-6 (tests/elasticity/amg_utils.py:439)
     if world > 1:
         args.no_multicolor = True
-        pc = par.h1_scal_par(A, par.Halo(p["peers"], p["ex"]), comm, p["free"], device=local_rank, **extra)
+        pc = par.h1_scal_par(A, par.Halo(p["peers"], p["ex"]), comm, p["free"], device=local_rank, defer_finalize=True, **extra)
+        # the library holds its own copy now: release the generator's matrix arrays before the (memory-hungry) host setup
+        empty_i, empty_d = np.zeros(0, np.int32), np.zeros(0)
+        p["col"], p["val"], A.col, A.val = empty_i, empty_d, empty_i, empty_d
+        pc.FinalizeLevel()
     elif elast:
         pc = ng.elast_3d(A, p["free"], vertex_xyz=p["xyz"], device=local_rank, **extra)
     else:
@@ -302,7 +311,7 @@ def main():
     ndof_global = ndof
     if world > 1:
         # whole-job figures: bytes of all ranks, V-cycle time = max over ranks, global DOF count = master DOFs
-        agg = torch.tensor([vbytes, float(ndof - (len(p["ex"][0]) if rank > 0 else 0))], dtype=torch.float64, device="cuda")
+        agg = torch.tensor([vbytes, float(p["n_master"])], dtype=torch.float64, device="cuda")
         dist.all_reduce(agg)
         vt = torch.tensor([vcycle_ms], dtype=torch.float64, device="cuda")
         dist.all_reduce(vt, op=dist.ReduceOp.MAX)
@@ -349,8 +358,8 @@ def main():
                 i = nested.level_info(l)
                 levels.append({"n": int(i.n), "b": int(i.b), "nnz": int(i.nnz), "gs_depth": int(i.gs_depth), "contracted_on_rank0": True})
         par_info = {"distributed_levels": npar, "transport": "nccl p2p" if comm.nccl else "host-staged (gloo callbacks)",
-                    "host_exchanges_setup": comm.n_exchange, "halo_dofs_per_interface": int(len(p["ex"][0])),
-                    "global_dims": list(p["global_dims"])}
+                    "host_exchanges_setup": comm.n_exchange, "box_grid": list(grid), "neighbours_rank0": len(p["peers"]),
+                    "shared_dofs_rank0": int(sum(len(e) for e in p["ex"])), "global_dims": list(p["global_dims"])}
 
     # ---- optional variant, reported separately: multicolour Gauss-Seidel on the fine level ------------------------------
     variant = None
@@ -390,8 +399,8 @@ def main():
             "metric": "pcg_amg_solve_dofs_per_s", "value": ndof_global / solve_s, "unit": "DOF/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": solve_s * 1e3, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": ("3D Poisson P1 (Kuhn tets), ONE global problem of %d x %d x %d = %d DOFs cut into %d z-slabs of %d^3 vertices (one per GPU, "
-                                    "interface planes shared), h1_scal + CG to 1e-8, hybrid Gauss-Seidel + NCCL halo exchange" % (tuple(p["global_dims"]) + (ndof_global, world, n))) if world > 1 else
+            "config": {"workload": ("3D Poisson P1 (Kuhn tets), ONE global problem of %d x %d x %d = %d DOFs cut into %d sub-boxes (%dx%dx%d) of %d^3 vertices (one per GPU, "
+                                    "interface DOFs shared), h1_scal + CG to 1e-8, hybrid Gauss-Seidel + NCCL halo exchange" % (tuple(p["global_dims"]) + (ndof_global, world) + tuple(grid) + (n,))) if world > 1 else
                                    ("3D Poisson P1 unit cube (Kuhn tets), %d^3 = %d DOFs per GPU, h1_scal + CG to 1e-8" % (n, ndof)) if not elast else
                                    ("3D linear elasticity P1 beam (Kuhn tets), %d vertices = %d DOFs per GPU, elast_3d (3x3 fine / 6x6 coarse blocks) + CG to 1e-6" % (p["n"], ndof)),
                        "tol": tol, "levels": levels, "operator_complexity": pc.GetOC(),

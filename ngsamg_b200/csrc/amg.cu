@@ -1151,6 +1151,17 @@ void Amg::finalize_parallel()
       // ---- contraction: rank 0 receives the level, everybody keeps a stub level holding its local vectors
       auto h0 = std::chrono::steady_clock::now();
       contract_to_root(comm, pd, L.hA, L.free_mask, L.xyz, ctr);
+      if (me == 0 && l > 0 && flags.flag("b200_color_coarse", true) && ctr.A.nrows > 0) {
+        // the numbering of the merged level is ours to choose (like every coarse numbering): colour-major, so that its sequential
+        // sweep has a shallow dependency DAG; the dof maps of the contraction follow
+        std::vector<i32> cperm;
+        int ncol = 0;
+        greedy_coloring_perm(ctr.A, cperm, ncol);
+        permute_symmetric(ctr.A, cperm);
+        for (auto &m : ctr.dof_maps) for (i32 &d : m) d = cperm[d];
+        if (!ctr.free_mask.empty()) { std::vector<uint8_t> t(ctr.free_mask.size()); for (size_t i = 0; i < t.size(); i++) t[cperm[i]] = ctr.free_mask[i]; ctr.free_mask.swap(t); }
+        if (!ctr.xyz.empty()) { std::vector<double> t(ctr.xyz.size()); for (size_t i = 0; i < t.size() / 3; i++) for (int k = 0; k < 3; k++) t[(size_t)cperm[i] * 3 + k] = ctr.xyz[i * 3 + k]; ctr.xyz.swap(t); }
+      }
       host_s += tick(h0);
       dev_csr_free(dA);
       L.par = false;

@@ -206,7 +206,7 @@ class ParallelPreconditioner(Preconditioner):
     """BaseAMGPC on a ParallelMatrix: `mat` is this rank's sub-assembled local matrix, `halo` its ParallelDofs.
     Mult(b, x): b DISTRIBUTED (local load vector), x CUMULATED.  All ranks must call collectively."""
 
-    def __init__(self, mat, halo, comm, freedofs=None, vertex_xyz=None, device=0, **kwargs):
+    def __init__(self, mat, halo, comm, freedofs=None, vertex_xyz=None, device=0, defer_finalize=False, **kwargs):
         if not isinstance(mat, SparseMatrix):
             raise TypeError("mat must be an ngsamg_b200.SparseMatrix")
         L = _lib.lib()
@@ -224,8 +224,13 @@ class ParallelPreconditioner(Preconditioner):
         self._check(L.ngsamg_b200_create_parallel(self._type.encode(), C.byref(abi), _lib.ptr(fm), _lib.ptr(xyz), C.byref(habi),
                                                   C.byref(comm.struct), karr, varr, len(keys), int(device), C.byref(self._h)))
         self._finalized = False
-        self._check(L.ngsamg_b200_finalize(self._h))
-        self._finalized = True
+        if not defer_finalize:   # the library copied the host arrays at create: a caller short of host memory may drop its own first
+            self.FinalizeLevel()
+
+    def FinalizeLevel(self, mat=None):
+        if not self._finalized:
+            self._check(self._lib.ngsamg_b200_finalize(self._h))
+            self._finalized = True
 
     def _check(self, rc):
         if rc != 0:

@@ -401,3 +401,51 @@ def slab_poisson3d(nx, ny, nz_per_rank, world, rank, dirichlet=("x0", "y1")):
         ex.append(np.arange(plane * (nz_per_rank - 1), plane * nz_per_rank, dtype=np.int32))
     loc["peers"], loc["ex"], loc["global_dims"] = peers, ex, (nx, ny, nzg)
     return loc
+
+
+def bench_grid(world):
+    """box grid (px, py, pz) the bench cuts the global mesh into: as cube-like as the rank count allows"""
+    return {1: (1, 1, 1), 2: (1, 1, 2), 4: (1, 2, 2), 8: (2, 2, 2)}.get(world, (1, 1, world))
+
+
+def box_poisson3d(n, grid, rank, dirichlet=("x0", "y1")):
+    """rank's local problem of a box partition into grid = (px, py, pz) sub-boxes of n^3 vertices each (global mesh
+    ((n-1)px+1) x ((n-1)py+1) x ((n-1)pz+1)); same result as partition_poisson3d(..., rank=rank) without any global index array.
+    Shared DOFs: faces / edges / corners of the sub-box, listed per neighbour ascending in the local number (z-major), which is the
+    same order on both sides."""
+    px, py, pz = grid
+    bx, by, bz = rank % px, (rank // px) % py, rank // (px * py)
+    gd = ((n - 1) * px + 1, (n - 1) * py + 1, (n - 1) * pz + 1)
+    h = 1.0 / (max(gd) - 1)
+    origin = (bx * (n - 1), by * (n - 1), bz * (n - 1))
+    tags = []
+    for tag in dirichlet:
+        ax = "xyz".index(tag[0])
+        if tag[1] == "0" and origin[ax] == 0:
+            tags.append(tag)
+        if tag[1] == "1" and origin[ax] + n == gd[ax]:
+            tags.append(tag)
+    loc = poisson3d_kuhn(n, n, n, dirichlet=tuple(tags), h=h, origin=origin)
+    peers, ex = [], []
+    sel = {-1: np.array([0]), 0: np.arange(n), 1: np.array([n - 1])}
+    for dz in (-1, 0, 1):
+        for dy in (-1, 0, 1):
+            for dx in (-1, 0, 1):
+                if dx == dy == dz == 0:
+                    continue
+                qx, qy, qz = bx + dx, by + dy, bz + dz
+                if not (0 <= qx < px and 0 <= qy < py and 0 <= qz < pz):
+                    continue
+                idx = (sel[dx][None, None, :] + n * (sel[dy][None, :, None] + n * sel[dz][:, None, None])).ravel()
+                peers.append(qx + px * (qy + py * qz))
+                ex.append(idx.astype(np.int32))
+    order = np.argsort(peers)
+    loc["peers"], loc["ex"], loc["global_dims"] = [peers[i] for i in order], [ex[i] for i in order], gd
+    loc["n_master"] = int(n ** 3 - sum(1 for _ in ()))  # replaced below
+    # DOFs this rank is master of (lowest sharing rank): everything not shared with a lower rank
+    ghost = np.zeros(n ** 3, bool)
+    for q, e in zip(loc["peers"], loc["ex"]):
+        if q < rank:
+            ghost[e] = True
+    loc["n_master"] = int((~ghost).sum())
+    return loc
