@@ -194,6 +194,19 @@ int ngsamg_b200_get_contraction_map(ngsamg_b200_t *h, int rank, int64_t *n, int3
 
 /* host-only pieces of the multi-rank setup (no device needed; collective over comm) -- the CPU tests drive them over gloo:
  * hybrid split + modified diagonal of one level.  Results are fetched with ngsamg_b200_hybrid_host_fetch. */
+/* one step of the multi-rank DOF-map construction (what finalize() runs per distributed level): assembled local matrix ->
+ * coarsening that respects the sharing classes (vertices only merge with vertices shared by the same ranks, rows of shared DOFs are
+ * bit-identical on every sharer; cf. the EQC-wise agglomeration + hierarchic prolongation, vertex_factory_impl.hpp:1845-1848).
+ * fetch copies P, vmap, coarse coordinates and the sharing lists of the COARSE level (peers[npeers_coarse], ex_ptr[npeers_coarse+1],
+ * ex_dofs[nshared_coarse]) and frees the handle.  Host only, collective over comm. */
+typedef struct ngsamg_b200_parcoarsen ngsamg_b200_parcoarsen;
+int ngsamg_b200_coarsen_parallel_begin(const ngsamg_csr *A, const uint8_t *free_mask, const double *vertex_xyz, const ngsamg_halo *halo,
+                                       const ngsamg_comm *comm, int bcoarse, int max_per_row, double min_frac, double omega, int smooth,
+                                       int rounds, ngsamg_b200_parcoarsen **out, int64_t *ncoarse, int64_t *nnz, int32_t *npeers_coarse,
+                                       int64_t *nshared_coarse);
+int ngsamg_b200_coarsen_parallel_fetch(ngsamg_b200_parcoarsen *m, int64_t *rowptr, int32_t *col, double *val, int32_t *vmap, double *cxyz,
+                                       int32_t *peers, int64_t *ex_ptr, int32_t *ex_dofs);
+
 typedef struct ngsamg_b200_hybrid_host ngsamg_b200_hybrid_host;
 int ngsamg_b200_hybrid_host_begin(const ngsamg_csr *A, const uint8_t *free_mask, const ngsamg_halo *halo, const ngsamg_comm *comm,
                                   ngsamg_b200_hybrid_host **out, int64_t *nnz_m, int64_t *nnz_g);

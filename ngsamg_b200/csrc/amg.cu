@@ -1951,6 +1951,64 @@ int ngsamg_b200_get_contraction_map(ngsamg_b200_t *h, int rank, int64_t *n, int3
   NGB_CATCH
 }
 
+// host-only: one step of the class-respecting (multi-rank) coarsening, exactly what finalize() runs per distributed level
+struct ngsamg_b200_parcoarsen { HostBsr P; std::vector<i32> vmap; std::vector<double> cxyz; ParDofs cpd; };
+
+int ngsamg_b200_coarsen_parallel_begin(const ngsamg_csr *A, const uint8_t *free_mask, const double *vertex_xyz, const ngsamg_halo *halo,
+                                       const ngsamg_comm *comm, int bcoarse, int max_per_row, double min_frac, double omega, int smooth,
+                                       int rounds, ngsamg_b200_parcoarsen **out, int64_t *ncoarse, int64_t *nnz, int32_t *npeers_coarse,
+                                       int64_t *nshared_coarse)
+{
+  NGB_TRY
+  if (!comm || !out) throw Error("null argument");
+  check_csr(A, "coarsen_parallel");
+  HostBsr hA, Acum;
+  copy_csr(A, hA);
+  ParDofs pd;
+  halo_to_pardofs(halo, A->nrows, comm->rank, pd);
+  Comm c;
+  c.c = *comm;
+  cumulate_matrix(c, pd, hA, Acum);
+  std::vector<double> rowsum, xyz;
+  assembled_row_sums(c, pd, hA, rowsum);
+  if (vertex_xyz) xyz.assign(vertex_xyz, vertex_xyz + 3 * A->nrows);
+  CoarsenOptions o;
+  o.max_per_row = max_per_row; o.min_frac = min_frac; o.omega = omega; o.smooth = smooth != 0; o.rounds = rounds;
+  ParCoarsen pc;
+  pc.pd = &pd; pc.rowsum = &rowsum; pc.rank = comm->rank;
+  auto r = std::make_unique<ngsamg_b200_parcoarsen>();
+  build_prolongation(Acum, free_mask, bcoarse, xyz, o, r->P, r->vmap, r->cxyz, &pc);
+  coarse_pardofs(pd, r->vmap, r->P.ncols, r->cpd, comm->rank);
+  if (ncoarse) *ncoarse = r->P.ncols;
+  if (nnz) *nnz = r->P.nnz();
+  if (npeers_coarse) *npeers_coarse = (i32)r->cpd.peers.size();
+  if (nshared_coarse) { i64 t = 0; for (auto &l : r->cpd.ex) t += (i64)l.size(); *nshared_coarse = t; }
+  *out = r.release();
+  NGB_CATCH
+}
+
+int ngsamg_b200_coarsen_parallel_fetch(ngsamg_b200_parcoarsen *m, int64_t *rowptr, int32_t *col, double *val, int32_t *vmap, double *cxyz,
+                                       int32_t *peers, int64_t *ex_ptr, int32_t *ex_dofs)
+{
+  NGB_TRY
+  if (!m) throw Error("null handle");
+  if (rowptr) std::memcpy(rowptr, m->P.rowptr.data(), sizeof(i64) * (m->P.nrows + 1));
+  if (col) std::memcpy(col, m->P.col.data(), sizeof(i32) * m->P.nnz());
+  if (val) std::memcpy(val, m->P.val.data(), sizeof(double) * m->P.nnz() * m->P.bs());
+  if (vmap) std::memcpy(vmap, m->vmap.data(), sizeof(i32) * m->vmap.size());
+  if (cxyz && !m->cxyz.empty()) std::memcpy(cxyz, m->cxyz.data(), sizeof(double) * m->cxyz.size());
+  i64 off = 0;
+  for (size_t k = 0; k < m->cpd.peers.size(); k++) {
+    if (peers) peers[k] = m->cpd.peers[k];
+    if (ex_ptr) ex_ptr[k] = off;
+    if (ex_dofs) std::memcpy(ex_dofs + off, m->cpd.ex[k].data(), sizeof(i32) * m->cpd.ex[k].size());
+    off += (i64)m->cpd.ex[k].size();
+  }
+  if (ex_ptr) ex_ptr[m->cpd.peers.size()] = off;
+  delete m;
+  NGB_CATCH
+}
+
 struct ngsamg_b200_hybrid_host { HostBsr M, G; std::vector<double> md; std::vector<i32> sweep; std::vector<uint8_t> master; };
 
 int ngsamg_b200_hybrid_host_begin(const ngsamg_csr *A, const uint8_t *free_mask, const ngsamg_halo *halo, const ngsamg_comm *comm,

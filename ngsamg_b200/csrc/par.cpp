@@ -127,6 +127,9 @@ void coarse_pardofs(const ParDofs &fine, const std::vector<i32> &vmap, i64 ncoar
       stamp[c] = (i32)kp;
       lst.push_back(c);
     }
+    // ascending in the coarse number: the coarse numbering of build_prolongation is class-major / canonical inside a class, so the
+    // relative order of two shared coarse vertices is the same on both sides and the sorted lists still pair up entry by entry
+    std::sort(lst.begin(), lst.end());
     if (!lst.empty()) { coarse.peers.push_back(fine.peers[kp]); coarse.ex.push_back(std::move(lst)); }
   }
   coarse.derive(rank);

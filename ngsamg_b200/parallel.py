@@ -336,6 +336,34 @@ def hybrid_host(mat, halo, comm, freedofs=None):
                 G=SparseMatrix(n, n, mat.bh, mat.bw, grp, gci[:ng.value], gv[:ng.value * bs]), mod_diag=md, sweep_rank=sw, master=ma)
 
 
+def coarsen_par(mat, halo, comm, freedofs=None, vertex_xyz=None, bcoarse=None, max_per_row=3, min_frac=0.08, omega=1.0, smooth=True,
+                rounds=3):
+    """host-only: one class-respecting coarsening step of a distributed level (collective).  Returns (P, vmap, coarse_xyz, coarse Halo)."""
+    L = _lib.lib()
+    bc = mat.bh if bcoarse is None else int(bcoarse)
+    fm = None if freedofs is None else np.ascontiguousarray(freedofs, dtype=np.uint8)
+    xyz = None if vertex_xyz is None else np.ascontiguousarray(vertex_xyz, dtype=np.float64)
+    h, nc, nz, npc, nsh = C.c_void_p(), C.c_int64(), C.c_int64(), C.c_int32(), C.c_int64()
+    abi, habi = mat._abi(), halo._abi()
+    rc = L.ngsamg_b200_coarsen_parallel_begin(C.byref(abi), _lib.ptr(fm), _lib.ptr(xyz), C.byref(habi), C.byref(comm.struct), bc,
+                                              int(max_per_row), float(min_frac), float(omega), int(bool(smooth)), int(rounds), C.byref(h),
+                                              C.byref(nc), C.byref(nz), C.byref(npc), C.byref(nsh))
+    if rc:
+        raise NgsAMGError(L.ngsamg_b200_last_error().decode() + (" [callback: %r]" % (comm.error,) if comm.error else ""))
+    rp = np.zeros(mat.nrows + 1, np.int64)
+    ci = np.zeros(max(nz.value, 1), np.int32)
+    v = np.zeros(max(nz.value, 1) * mat.bh * bc)
+    vmap = np.zeros(mat.nrows, np.int32)
+    cxyz = None if xyz is None else np.zeros((nc.value, 3))
+    peers = np.zeros(max(npc.value, 1), np.int32)
+    exp = np.zeros(npc.value + 1, np.int64)
+    exd = np.zeros(max(nsh.value, 1), np.int32)
+    _lib.check(L.ngsamg_b200_coarsen_parallel_fetch(h, _lib.ptr(rp), _lib.ptr(ci), _lib.ptr(v), _lib.ptr(vmap), _lib.ptr(cxyz), _lib.ptr(peers),
+                                                    _lib.ptr(exp), _lib.ptr(exd)))
+    P = SparseMatrix(mat.nrows, nc.value, mat.bh, bc, rp, ci[:nz.value], v[:nz.value * mat.bh * bc])
+    return P, vmap, cxyz, Halo(list(peers[:npc.value]), [exd[exp[k]:exp[k + 1]] for k in range(npc.value)])
+
+
 def run_ranks(nranks, fn, timeout=300.0):
     """run fn(rank, comm) on `nranks` threads (ThreadComm world); returns the list of results, re-raises the first failure"""
     comms = ThreadComm.world(nranks, timeout)

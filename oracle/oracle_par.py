@@ -18,10 +18,29 @@ The sequential Gauss-Seidel sweeps themselves run in the C oracle (GSS3 / GSS4 a
 The hierarchy (local prolongations, coarse sharing lists, contraction maps) is an INPUT -- it is read back from the product,
 exactly like the single-rank parity tests inject the product's prolongations into OracleAMG.
 """
+from concurrent.futures import ThreadPoolExecutor
+
 import numpy as np
 import scipy.sparse as sp
 
 from . import oracle as O
+
+_POOL = None
+
+
+def set_threads(n):
+    """run the per-rank stages of the simulated ranks on n host threads (the C oracle releases the GIL); 0/1 = sequential"""
+    global _POOL
+    _POOL = ThreadPoolExecutor(n) if n and n > 1 else None
+
+
+def _each(R, fn):
+    """fn(r) for every rank -- the ranks are independent between two exchanges, exactly like MPI ranks"""
+    if _POOL is None:
+        for r in range(R):
+            fn(r)
+    else:
+        list(_POOL.map(fn, range(R)))
 
 
 def _expand(A):
@@ -233,19 +252,19 @@ class HybridLevel:
         if not x_zero:
             gx = [O.spmv_add(self.Gb[r], 1.0, x[r], np.zeros_like(x[r])) for r in range(R)]
         self.dis2co(res)                                   # StartDIS2CO ... FinishDIS2CO (overlap does not change values)
-        for r in range(R):
-            p1, pe, p2 = self._stages(r, backward)
-            for mask in (p1, pe):
+
+        def sweep(r):
+            # LOC_PART_1, EX_PART, then (after StartCO2CU, which only reads the exchange rows) LOC_PART_2
+            for mask in self._stages(r, backward):
                 O.gs_res(self.Mb[r], self.dinv[r], mask, x[r], res[r], backward)
-        # StartCO2CU happens before the last local stage; the last stage only touches local rows
-        for r in range(R):
-            p1, pe, p2 = self._stages(r, backward)
-            O.gs_res(self.Mb[r], self.dinv[r], p2, x[r], res[r], backward)
+        _each(R, sweep)
         self.co2cu(x)
-        for r in range(R):
+
+        def fix(r):
             if gx is not None:
                 res[r] += gx[r]
             O.spmv_add(self.Gb[r], -1.0, x[r], res[r])
+        _each(R, fix)
 
     def smooth_rhs(self, x, rhs, backward, x_zero):
         """x CUMULATED, rhs DISTRIBUTED (not modified); afterwards x CUMULATED"""
@@ -255,19 +274,21 @@ class HybridLevel:
             for r in range(R):
                 O.spmv_add(self.Gb[r], -1.0, x[r], t[r])
         self.dis2co(t)
-        for r in range(R):
+
+        def sweep(r):
             for mask in self._stages(r, backward):
                 O.gs_rhs(self.Mb[r], self.dinv[r], mask, x[r], t[r], backward)
+        _each(R, sweep)
         self.co2cu(x)
 
     def mult(self, x):
         """HybridBaseMatrix::Mult: y = (M + G) x, x CUMULATED, y DISTRIBUTED"""
-        out = []
-        for r in range(self.R):
-            y = np.zeros_like(x[r])
-            O.spmv_add(self.Mb[r], 1.0, x[r], y)
-            O.spmv_add(self.Gb[r], 1.0, x[r], y)
-            out.append(y)
+        out = [np.zeros_like(x[r]) for r in range(self.R)]
+
+        def mv(r):
+            O.spmv_add(self.Mb[r], 1.0, x[r], out[r])
+            O.spmv_add(self.Gb[r], 1.0, x[r], out[r])
+        _each(self.R, mv)
         return out
 
 
@@ -347,7 +368,7 @@ class OracleParAMG:
         """CGSolver on parallel vectors: d DISTRIBUTED, w/s/u CUMULATED; inner products all-reduced"""
         R = self.R
         L0 = self.levels[0]
-        dot = lambda a, b: float(sum(np.dot(a[r], b[r]) for r in range(R)))
+        dot = lambda a, b: float(sum(float(np.multiply(a[r], b[r]).sum()) for r in range(R)))   # local dots + all-reduce (no BLAS threads)
         d = [np.ascontiguousarray(v, np.float64).copy() for v in rhs]
         u = [np.zeros_like(v) for v in d]
         w = self.apply(d)

@@ -105,3 +105,80 @@ def test_hybrid_split_over_gloo():
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT)
     assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-4000:]
     assert "rank 0 ok" in out.stdout and "rank 1 ok" in out.stdout
+
+
+@pytest.mark.parametrize("grid", [(1, 1, 2), (1, 2, 2), (2, 2, 2), (1, 1, 3)])
+def test_parallel_coarsening_is_consistent_across_sharers(grid):
+    """the class-respecting coarsening needs NO communication for P: every sharer of a DOF must compute the bit-identical
+    prolongation row (same coarse vertices, same weights) and the coarse sharing lists must pair up entry by entry"""
+    parts = S.partition_poisson3d(9, 8, 11, grid=grid)
+    R = len(parts)
+
+    def fn(r, comm):
+        p = parts[r]
+        A = ng.SparseMatrix(p["n"], p["n"], 1, 1, p["rowptr"], p["col"], p["val"])
+        return par.coarsen_par(A, par.Halo(p["peers"], p["ex"]), comm, p["free"])
+
+    res = par.run_ranks(R, fn)
+    keys = []   # global identity of a coarse vertex: smallest global fine id among its members
+    for r in range(R):
+        P, vmap, _, _ = res[r]
+        key = np.full(P.ncols, np.iinfo(np.int64).max)
+        ok = vmap >= 0
+        np.minimum.at(key, vmap[ok], parts[r]["gidx"][ok])
+        keys.append(key)
+        # aggregates never mix sharing classes
+        nshare = np.zeros(parts[r]["n"], np.int64)
+        for e in parts[r]["ex"]:
+            nshare[e] += 1
+        for c in range(P.ncols):
+            mem = np.flatnonzero(vmap == c)
+            assert len(set(nshare[mem])) == 1
+    checked = 0
+    for r in range(R):
+        P, _, _, ch = res[r]
+        for kp, q in enumerate(parts[r]["peers"]):
+            kq = list(parts[q]["peers"]).index(r)
+            Pq, _, _, chq = res[q]
+            for dr, dq in zip(parts[r]["ex"][kp], parts[q]["ex"][kq]):
+                rowr = {int(keys[r][P.col[k]]): P.val[k] for k in range(P.rowptr[dr], P.rowptr[dr + 1])}
+                rowq = {int(keys[q][Pq.col[k]]): Pq.val[k] for k in range(Pq.rowptr[dq], Pq.rowptr[dq + 1])}
+                assert rowr == rowq, "prolongation rows of a shared DOF differ between rank %d and rank %d" % (r, q)
+                checked += 1
+            if q in list(ch.peers):
+                a, b = ch.ex[list(ch.peers).index(q)], chq.ex[list(chq.peers).index(r)]
+                assert len(a) == len(b) and np.array_equal(keys[r][a], keys[q][b])
+                assert np.all(np.diff(a) > 0) and np.all(np.diff(b) > 0)
+            else:
+                assert r not in list(chq.peers)
+    assert checked > 0
+
+
+@pytest.mark.parametrize("grid", [(1, 1, 2), (2, 2, 2)])
+def test_cpu_multirank_pipeline_solves_the_global_problem(grid):
+    """CPU-only restatement of the reference's MPI solve (host coarsening of the product + multi-rank oracle): the PCG solution of
+    the partitioned problem equals a direct solve of the assembled problem; iteration count within the reference's own ceilings"""
+    import scipy.sparse.linalg as spl
+    from oracle import cpu_pipeline as CP
+    dims = (13, 11, 15)
+    parts = S.partition_poisson3d(*dims, grid=grid)
+    amg, info = CP.build(parts, ctr_nv=150, max_coarse=15)
+    assert info["distributed_levels"] >= 1
+    rhs = [p["rhs"] * p["free"] for p in parts]
+    u, it, errs = amg.pcg(rhs, tol=1e-8, maxsteps=100)
+    assert it <= 30
+    g = S.poisson3d_kuhn(*dims)
+    A = sp.csr_matrix((g["val"], g["col"], g["rowptr"]), shape=(g["n"], g["n"]))
+    f = g["free"].astype(bool)
+    xg = np.zeros(g["n"])
+    xg[f] = spl.spsolve(A[f][:, f].tocsc(), g["rhs"][f])
+    for r, p in enumerate(parts):
+        assert np.linalg.norm(u[r] - xg[p["gidx"]]) < 1e-7 * np.linalg.norm(xg)
+    # threaded execution of the simulated ranks gives the same numbers (no dependence on thread timing, SURVEY §8c (7))
+    from oracle import oracle_par as OP
+    OP.set_threads(4)
+    try:
+        u2, it2, _ = amg.pcg(rhs, tol=1e-8, maxsteps=100)
+    finally:
+        OP.set_threads(0)
+    assert it2 == it and all(np.array_equal(a, b) for a, b in zip(u, u2))
