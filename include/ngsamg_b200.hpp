@@ -9,6 +9,8 @@
 //   pc.FinalizeLevel();                                             // amg_pc.cpp:413-434
 //   pc.Mult(b, x);  pc.MultAdd(s, b, x);                            // amg_matrix.cpp:377-393
 //   amg::CGSolver cg(A, pc, 100, 1e-8);  cg.Solve(rhs, sol);        // ngsolve.krylovspace.CGSolver, tests/h1/amg_utils.py:346
+//   amg::ParallelAMGPC ppc("NgsAMG.h1_scal", Aloc, pardofs, comm, freedofs);                // the same on a ParallelMatrix (one rank = one GPU)
+//   auto H = amg::DecomposeHybrid(Aloc, pardofs, comm);              // HybridMatrix: M, G, modified diagonal (host only)
 //
 // Header-only; link with -lngsamg_b200.  No torch, no NGSolve.
 #pragma once
@@ -110,6 +112,9 @@ class BaseAMGPC {
   ngsamg_b200_t *h = nullptr;
   int64_t n = 0;
   bool finalized = false;
+protected:
+  BaseAMGPC() = default;                                   // for ParallelAMGPC, which creates the handle itself
+  void adopt(ngsamg_b200_t *ah, int64_t an) { h = ah; n = an; }
 public:
   BaseAMGPC(const std::string &type, const SparseMat &A, const std::vector<uint8_t> *freedofs = nullptr, const Flags &flags = {},
             const std::vector<double> *vertex_xyz = nullptr, int device = 0)
@@ -176,6 +181,117 @@ public:
   void TransferF2C(int level, const double *x_fine, double *x_coarse) const { check(ngsamg_b200_restrict(h, level, x_fine, x_coarse)); }
   void AddC2F(int level, double fac, double *x_fine, const double *x_coarse) const { check(ngsamg_b200_prolong_add(h, level, fac, x_coarse, x_fine)); }
   ngsamg_b200_t *handle() const { return h; }
+};
+
+// ---- multi-rank (MPI) mirror ---------------------------------------------------------------------------------------
+// ngla::ParallelDofs as the path uses it (dcc_map.cpp:494-543, hybrid_matrix.cpp:27-33): neighbour ranks + shared DOFs
+class ParallelDofs {
+public:
+  int64_t ndof = 0;
+  std::vector<int32_t> procs;                  // GetDistantProcs(), ascending
+  std::vector<std::vector<int32_t>> exdofs;    // GetExchangeDofs(procs[k]), ascending, pairwise consistent
+  ParallelDofs() = default;
+  ParallelDofs(int64_t n, std::vector<int32_t> p, std::vector<std::vector<int32_t>> e) : ndof(n), procs(std::move(p)), exdofs(std::move(e))
+  {
+    if (procs.size() != exdofs.size()) throw Exception("ParallelDofs: one exchange list per distant proc");
+  }
+  const std::vector<int32_t> &GetDistantProcs() const { return procs; }
+  const std::vector<int32_t> &GetExchangeDofs(int proc) const
+  {
+    for (size_t k = 0; k < procs.size(); k++) if (procs[k] == proc) return exdofs[k];
+    throw Exception("ParallelDofs: not a distant proc");
+  }
+  int64_t GetNDofLocal() const { return ndof; }
+};
+
+// NgMPI_Comm stand-in: the two host callbacks of ngsamg_comm behind a C++ interface (an NGSolve adapter implements them with
+// ISend/IRecv/WaitAll and AllReduce) + the optional NCCL communicator for the device data path
+class Communicator {
+public:
+  virtual ~Communicator() = default;
+  virtual int Rank() const = 0;
+  virtual int Size() const = 0;
+  virtual void Exchange(int npeers, const int32_t *peers, const void *const *sendbuf, const int64_t *sendbytes, void *const *recvbuf,
+                        const int64_t *recvbytes) = 0;
+  virtual void AllReduceSum(double *vals, int n) = 0;
+  void *nccl = nullptr;
+  ngsamg_comm abi()
+  {
+    ngsamg_comm c;
+    c.rank = Rank(); c.size = Size(); c.ctx = this; c.nccl = nccl;
+    c.exchange = [](void *ctx, int32_t np, const int32_t *pr, const void *const *sb, const int64_t *sn, void *const *rb, const int64_t *rn) -> int {
+      try { static_cast<Communicator *>(ctx)->Exchange(np, pr, sb, sn, rb, rn); return 0; } catch (...) { return 1; }
+    };
+    c.allreduce_sum = [](void *ctx, double *v, int32_t n) -> int {
+      try { static_cast<Communicator *>(ctx)->AllReduceSum(v, n); return 0; } catch (...) { return 1; }
+    };
+    return c;
+  }
+};
+
+namespace detail {
+struct HaloArrays {
+  std::vector<int64_t> ptr{0};
+  std::vector<int32_t> dofs;
+  ngsamg_halo halo;
+  explicit HaloArrays(const ParallelDofs &pd)
+  {
+    for (auto &l : pd.exdofs) { dofs.insert(dofs.end(), l.begin(), l.end()); ptr.push_back((int64_t)dofs.size()); }
+    halo = ngsamg_halo{(int32_t)pd.procs.size(), pd.procs.data(), ptr.data(), dofs.data()};
+  }
+};
+}  // namespace detail
+
+// HybridMatrix (src/base/linalg/hybrid_matrix.hpp): A = M + G, plus what HybridGSSmoother::Finalize derives from it.
+// Host only (DecomposeSparseMatrixHybrid hybrid_matrix.cpp:17-307, CalcHybridSmootherRDG hybrid_smoother_utils.hpp:146-176).
+struct HybridMatrix {
+  SparseMat M, G;
+  std::vector<double> mod_diag;      // replacement diagonal of the hybrid smoother
+  std::vector<int32_t> sweep_rank;   // position of every row in the stage order LOC_PART_1 | EX_PART | LOC_PART_2
+  std::vector<uint8_t> master;       // DCCMap::GetMasterDOFs
+  const SparseMat &GetM() const { return M; }
+  const SparseMat &GetG() const { return G; }
+};
+inline HybridMatrix DecomposeHybrid(const SparseMat &A, const ParallelDofs &pd, Communicator &comm, const std::vector<uint8_t> *freedofs = nullptr)
+{
+  detail::HaloArrays ha(pd);
+  ngsamg_comm c = comm.abi();
+  ngsamg_csr a = A.abi();
+  ngsamg_b200_hybrid_host *h = nullptr;
+  int64_t nm = 0, ng = 0;
+  check(ngsamg_b200_hybrid_host_begin(&a, freedofs ? freedofs->data() : nullptr, &ha.halo, &c, &h, &nm, &ng));
+  HybridMatrix H;
+  const size_t bs = (size_t)A.bh * A.bw;
+  for (SparseMat *m : {&H.M, &H.G}) { m->nrows = m->ncols = A.nrows; m->bh = A.bh; m->bw = A.bw; m->rowptr.resize(A.nrows + 1); }
+  H.M.col.resize(nm); H.M.val.resize(nm * bs); H.G.col.resize(ng); H.G.val.resize(ng * bs);
+  H.mod_diag.resize(A.nrows * bs); H.sweep_rank.resize(A.nrows); H.master.resize(A.nrows);
+  check(ngsamg_b200_hybrid_host_fetch(h, H.M.rowptr.data(), H.M.col.data(), H.M.val.data(), H.G.rowptr.data(), H.G.col.data(), H.G.val.data(),
+                                      H.mod_diag.data(), H.sweep_rank.data(), H.master.data()));
+  return H;
+}
+
+// BaseAMGPC on a ParallelMatrix: A = the rank's sub-assembled local matrix, pd = its ParallelDofs.  Mult / CGSolver::Solve are
+// collective; b is DISTRIBUTED, x CUMULATED (amg_matrix.cpp:160-307).
+class ParallelAMGPC : public BaseAMGPC {
+public:
+  ParallelAMGPC(const std::string &type, const SparseMat &A, const ParallelDofs &pd, Communicator &comm,
+                const std::vector<uint8_t> *freedofs = nullptr, const Flags &flags = {}, const std::vector<double> *vertex_xyz = nullptr,
+                int device = 0)
+    : BaseAMGPC()
+  {
+    std::vector<const char *> k, v;
+    for (auto &kv : flags) { k.push_back(kv.first.c_str()); v.push_back(kv.second.c_str()); }
+    detail::HaloArrays ha(pd);
+    cabi = comm.abi();      // must outlive the handle
+    ngsamg_csr a = A.abi();
+    ngsamg_b200_t *hh = nullptr;
+    check(ngsamg_b200_create_parallel(type.c_str(), &a, freedofs ? freedofs->data() : nullptr, vertex_xyz ? vertex_xyz->data() : nullptr,
+                                      &ha.halo, &cabi, k.data(), v.data(), (int)k.size(), device, &hh));
+    adopt(hh, A.nrows * A.bh);
+  }
+  int GetNParallelLevels() const { return ngsamg_b200_num_parallel_levels(handle()); }
+private:
+  ngsamg_comm cabi;
 };
 
 // ngsolve.krylovspace.CGSolver(mat, pre, maxsteps, tol) as the reference's tests use it (tests/h1/amg_utils.py:346-362)

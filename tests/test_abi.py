@@ -138,6 +138,19 @@ def _build_cpp_test(tmp_path):
     return exe
 
 
+def test_cpp_parallel_host_mirror(tmp_path):
+    """tests/cpp/test_hpp_parallel.cpp: the multi-rank host path (amg::ParallelDofs, amg::Communicator, amg::DecomposeHybrid) driven from
+    C++ with two std::thread ranks -- master lists, M/G split, assembled interface block, operator identity, stage order"""
+    import subprocess
+    exe = os.path.join(str(tmp_path), "test_hpp_parallel")
+    libdir = os.path.dirname(_lib.LIB_PATH)
+    subprocess.check_call(["g++", "-std=c++17", "-O1", "-I", os.path.join(ROOT, "include"), os.path.join(ROOT, "tests", "cpp", "test_hpp_parallel.cpp"),
+                           "-o", exe, "-L", libdir, "-lngsamg_b200", "-Wl,-rpath," + libdir, "-pthread"])
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, (r.returncode, r.stdout, r.stderr)
+    assert "bad=0" in r.stdout
+
+
 @pytest.mark.skipif(_has_gpu(), reason="checks the no-device failure mode of the C++ host mirror")
 def test_cpp_host_mirror_compiles_and_fails_loudly(tmp_path):
     """include/ngsamg_b200.hpp (C++ mirror of BaseAMGPC / CGSolver / RestrictMatrix) links against the C ABI; without a
