@@ -187,6 +187,9 @@ struct Amg {
   void co2cu(Level &L, double *v);    // DCCMap::StartCO2CU + ApplyCO2CU: master values overwrite the ghosts
   void contracted_solve(Level &L);
   void allreduce_scalars(double *h, int n);
+  void hybrid_smooth_res(Level &L, bool backward, double *x, double *res, bool x_zero);
+  void hybrid_smooth_rhs(Level &L, bool backward, double *x, const double *b, double *work, bool x_zero);
+  void hybrid_smooth(Level &L, double *x, const double *b, double *res, bool ru, bool ur, bool xz, bool backward);
 
   ~Amg();
   void finalize();
@@ -1517,6 +1520,54 @@ void Amg::smooth_once(Level &L, double *x, const double *b, double *res, bool ru
   }
 }
 
+// HybridBaseSmoother::SmoothImplRES (hybrid_base_smoother.cpp:294-404): x CUMULATED, res DISTRIBUTED = b - A x_old.
+// The local sweep only sees M, so G x_old is stashed and the residual is corrected with res += G x_old - G x_new.
+void Amg::hybrid_smooth_res(Level &L, bool backward, double *x, double *res, bool x_zero)
+{
+  const bool stash = !x_zero && L.G.nnz;
+  double *gx = L.y;
+  if (stash) transfer(L.G, x, nullptr, gx, 1.0, 0.0);
+  dis2co(L, res);
+  gs_res(L, backward, x, res, x_zero);
+  co2cu(L, x);
+  if (L.G.nnz) {
+    if (stash) { k_axpby<<<nblk(L.npad * L.b), TB, 0, st>>>(L.npad * L.b, 1.0, gx, 1.0, res); launches++; }
+    transfer(L.G, x, res, res, -1.0, 1.0);
+  }
+}
+
+// HybridBaseSmoother::SmoothImplRHS (hybrid_base_smoother.cpp:407-446): the local sweep runs against b - G x (DISTRIBUTED -> DIS2CO);
+// `work` holds that right-hand side (the reference uses its stashed vector / res as work space)
+void Amg::hybrid_smooth_rhs(Level &L, bool backward, double *x, const double *b, double *work, bool x_zero)
+{
+  const size_t bytes = sizeof(double) * L.npad * L.b;
+  if (x_zero) NGB_CUDA(cudaMemsetAsync(x, 0, bytes, st));
+  if (!x_zero && L.G.nnz) transfer(L.G, x, b, work, -1.0, 1.0);
+  else NGB_CUDA(cudaMemcpyAsync(work, b, bytes, cudaMemcpyDeviceToDevice, st));
+  dis2co(L, work);
+  gs_rhs(L, backward, x, work, L.y);
+  NGB_CUDA(cudaMemcpyAsync(x, L.y, bytes, cudaMemcpyDeviceToDevice, st));
+  co2cu(L, x);
+}
+
+// HybridBaseSmoother::SmoothImpl (hybrid_base_smoother.cpp:242-290): the cost heuristic that picks the RES or the RHS form
+void Amg::hybrid_smooth(Level &L, double *x, const double *b, double *res, bool ru, bool ur, bool xz, bool backward)
+{
+  if (L.sm_symm || L.sm_steps != 1) throw Error("multi-rank levels support one non-symmetric Gauss-Seidel step per smoothing call");
+  if (ur) {
+    if (!ru) {
+      if (!xz) {
+        hybrid_smooth_rhs(L, backward, x, b, res, false);
+        spmv_part(L, 4, x, b, res, -1.0, 1.0, nullptr);                 // res = b - (M + G) x   (HybridBaseMatrix, DISTRIBUTED)
+        if (L.G.nnz) transfer(L.G, x, res, res, -1.0, 1.0);
+      } else {
+        NGB_CUDA(cudaMemcpyAsync(res, b, sizeof(double) * L.npad * L.b, cudaMemcpyDeviceToDevice, st));
+        hybrid_smooth_res(L, backward, x, res, true);
+      }
+    } else hybrid_smooth_res(L, backward, x, res, xz);
+  } else hybrid_smooth_rhs(L, backward, x, b, res, xz);
+}
+
 // ProxySmoother (base_smoother.hpp:169-229) + SmoothK / SmoothBackK / SmoothSymmK (:79-112)
 void Amg::level_smooth(Level &L, double *x, const double *b, double *res, bool ru, bool ur, bool xz, bool backward)
 {
@@ -2156,6 +2207,7 @@ int ngsamg_b200_spmv_add(ngsamg_b200_t *h, int level, double s, const double *x,
   const double *xd = a.to_device(x, n, a.io_a);
   k_permute_in<<<nblk(L.n), TB, 0, a.st>>>(L.n, L.b, L.d_perm, xd, L.wa);
   a.spmv_part(L, 4, L.wa, nullptr, L.wb, 1.0, 0.0, nullptr);
+  if (a.par && L.par && L.G.nnz) a.transfer(L.G, L.wa, L.wb, L.wb, 1.0, 1.0);   // HybridBaseMatrix::MultAdd: (M + G) x, x CUMULATED -> y DISTRIBUTED
   const bool ydev = a.is_device_ptr(y);
   double *yd = ydev ? y : a.io_b;
   if (!ydev) a.to_device(y, n, a.io_b);
@@ -2183,7 +2235,9 @@ int ngsamg_b200_smooth(ngsamg_b200_t *h, int level, double *x, const double *b, 
     const double *rd = a.to_device(res, n, a.io_a);
     k_permute_in<<<nblk(L.n), TB, 0, a.st>>>(L.n, L.b, L.d_perm, rd, L.res);
   }
-  a.level_smooth(L, L.x, L.rhs, L.res, res_updated != 0, update_res != 0, x_zero != 0, backwards != 0);
+  // multi-rank level: HybridBaseSmoother::Smooth / SmoothBack -- collective; x CUMULATED, b and res DISTRIBUTED
+  if (a.par && L.par) a.hybrid_smooth(L, L.x, L.rhs, L.res, res_updated != 0, update_res != 0, x_zero != 0, backwards != 0);
+  else a.level_smooth(L, L.x, L.rhs, L.res, res_updated != 0, update_res != 0, x_zero != 0, backwards != 0);
   k_permute_out<<<nblk(L.n), TB, 0, a.st>>>(L.n, L.b, L.d_perm, L.x, a.io_b, 1.0, 0);
   a.from_device(x, a.io_b, n);
   if (res) {

@@ -281,6 +281,25 @@ class HybridLevel:
         _each(R, sweep)
         self.co2cu(x)
 
+    def smooth(self, x, b, res, res_updated, update_res, x_zero, backward):
+        """HybridBaseSmoother::SmoothImpl (hybrid_base_smoother.cpp:242-290): picks the RES or the RHS form by cost"""
+        R = self.R
+        if update_res:
+            if not res_updated:
+                if not x_zero:
+                    self.smooth_rhs(x, b, backward, False)
+                    y = self.mult(x)
+                    for r in range(R):
+                        res[r][:] = b[r] - y[r]
+                else:
+                    for r in range(R):
+                        res[r][:] = b[r]
+                    self.smooth_res(x, res, backward, True)
+            else:
+                self.smooth_res(x, res, backward, x_zero)
+        else:
+            self.smooth_rhs(x, b, backward, x_zero)
+
     def mult(self, x):
         """HybridBaseMatrix::Mult: y = (M + G) x, x CUMULATED, y DISTRIBUTED"""
         out = [np.zeros_like(x[r]) for r in range(self.R)]

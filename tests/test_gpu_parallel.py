@@ -157,3 +157,51 @@ def test_parallel_apply_is_symmetric():
     s12 = sum(np.dot(x1[r], b2[r]) for r in range(2))
     s21 = sum(np.dot(b1[r], x2[r]) for r in range(2))
     assert abs(s12 - s21) < 1e-10 * abs(s12)
+
+
+@pytest.mark.parametrize("grid", [(1, 1, 2), (1, 2, 2)])
+def test_parallel_smoother_flag_protocol(grid):
+    """HybridBaseSmoother::Smooth / SmoothBack through the smoother-only entry with every (res_updated, update_res, x_zero)
+    combination (base_smoother.hpp:68-112, hybrid_base_smoother.cpp:242-290) and HybridBaseMatrix::MultAdd, against the oracle"""
+    dims = (11, 9, 13)
+    parts = S.partition_poisson3d(*dims, grid=grid)
+    R = len(parts)
+    pcs = _build_ranks(parts, par.h1_scal_par, 1, ngs_amg_max_coarse_size=15, ngs_amg_b200_ctr_nv=150)
+    amg, npar = _oracle_for(parts, pcs, 1)
+    L = amg.levels[0]
+    ntot = dims[0] * dims[1] * dims[2]
+    gx = rand(90, ntot)
+    x0 = [gx[p["gidx"]].copy() for p in parts]                        # CUMULATED: consistent on shared dofs
+    b = [rand(91 + r, p["n"]) * p["free"] for r, p in enumerate(parts)]   # DISTRIBUTED
+    # (M + G) x
+    yo = L.mult(x0)
+
+    def mv(r, pc):
+        y = np.ones(parts[r]["n"])
+        pc.LevelMultAdd(0, 2.0, x0[r], y)
+        return y
+
+    for r, y in enumerate(_collective(pcs, mv)):
+        assert rel(y, 1.0 + 2.0 * yo[r]) < 1e-13
+    for (ru, ur, xz) in [(False, True, False), (True, True, False), (False, False, False), (False, True, True), (True, True, True),
+                         (False, False, True)]:
+        for back in (False, True):
+            xs = [np.zeros_like(v) if xz else v.copy() for v in x0]
+            if ru:
+                res = [b[r] - (0.0 if xz else yo[r]) for r in range(R)]
+            else:
+                res = [np.zeros_like(v) for v in b]
+            xo, ro = [v.copy() for v in xs], [v.copy() for v in res]
+            L.smooth(xo, b, ro, ru, ur, xz, back)
+
+            def sm(r, pc):
+                x, rr = xs[r].copy(), res[r].copy()
+                s = pc.GetSmoother(0)
+                (s.SmoothBack if back else s.Smooth)(x, b[r], rr, res_updated=ru, update_res=ur, x_zero=xz)
+                return x, rr
+
+            got = _collective(pcs, sm)
+            for r in range(R):
+                assert rel(got[r][0], xo[r]) < TOL_VCYCLE, ("x", ru, ur, xz, back, r, rel(got[r][0], xo[r]))
+                if ur:
+                    assert rel(got[r][1], ro[r]) < TOL_VCYCLE, ("res", ru, ur, xz, back, r, rel(got[r][1], ro[r]))
