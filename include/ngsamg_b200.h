@@ -92,7 +92,10 @@ int ngsamg_b200_spmv_add(ngsamg_b200_t *h, int level, double s, const double *x,
 
 /* BaseSmoother::Smooth / SmoothBack of the smoother of `level` with the reference flag protocol
  * (base_smoother.hpp:68-112; GSS3::Smooth/SmoothBack gssmoother.cpp:349-398; ProxySmoother :181-196).
- * Smoother-only entry == NgsAMG.CreateHybridGSS(...).Smooth, src/base/smoothers/python_smoothers.cpp:144-194. */
+ * Smoother-only entry == NgsAMG.CreateHybridGSS(...).Smooth, src/base/smoothers/python_smoothers.cpp:144-194.
+ * On a distributed level of a multi-rank handle this is HybridBaseSmoother::Smooth / SmoothBack (hybrid_base_smoother.cpp:214-574):
+ * collective, x CUMULATED, b and res DISTRIBUTED, RES or RHS form picked by SmoothImpl's cost heuristic (:242-290); spmv_add is then
+ * HybridBaseMatrix::MultAdd, y(DISTRIBUTED) += s (M + G) x(CUMULATED) (hybrid_matrix.cpp:393-411). */
 int ngsamg_b200_smooth(ngsamg_b200_t *h, int level, double *x, const double *b, double *res, int res_updated,
                        int update_res, int x_zero, int backwards);
 
