@@ -47,6 +47,31 @@ def make_elasticity():
     print("elast_5x3x3: n=%d nc=%d nnz(Ac)=%d" % (p["n"], P.ncols, Ac.nnz))
 
 
+def make_poisson_multirank():
+    """2 ranks, 9 x 8 x 11 Poisson cut in z: hierarchy from the product's host-side class-respecting coarsening, everything else from the
+    multi-rank oracle (hybrid split, modified diagonal, stage sweeps, DCC exchange, contraction, all-reduced CG)"""
+    from ngsamg_b200 import synthetic as S
+    from oracle import cpu_pipeline as CP
+    parts = S.partition_poisson3d(9, 8, 11, grid=(1, 1, 2))
+    amg, info = CP.build(parts, ctr_nv=100, max_coarse=15)
+    b = [rand(777 + r, p["n"]) * p["free"] for r, p in enumerate(parts)]
+    x = amg.apply(b)
+    rhs = [p["rhs"] * p["free"] for p in parts]
+    u, it, errs = amg.pcg(rhs, tol=1e-8, maxsteps=50)
+    out = dict(pcg_iters=it, pcg_errors=errs, distributed_levels=info["distributed_levels"])
+    for r in range(2):
+        L0 = amg.levels[0]
+        M, G = L0.M[r].tocsr(), L0.G[r].tocsr()
+        M.sort_indices(); G.sort_indices()
+        out.update({"b%d" % r: b[r], "vcycle_x%d" % r: x[r], "pcg_u%d" % r: u[r], "mod_diag%d" % r: L0.md[r].ravel(),
+                    "m_indptr%d" % r: M.indptr, "m_indices%d" % r: M.indices, "m_data%d" % r: M.data,
+                    "g_indptr%d" % r: G.indptr, "g_indices%d" % r: G.indices, "g_data%d" % r: G.data,
+                    "master%d" % r: L0.master[r].astype(np.uint8)})
+    np.savez_compressed(os.path.join(HERE, "poisson_2ranks_9x8x11.npz"), **out)
+    print("poisson_2ranks_9x8x11: distributed levels=%d pcg iters=%d" % (info["distributed_levels"], it))
+
+
 if __name__ == "__main__":
     make_poisson()
     make_elasticity()
+    make_poisson_multirank()
