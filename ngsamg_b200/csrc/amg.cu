@@ -4,6 +4,7 @@
 
 #include <chrono>
 #include <memory>
+#include <mutex>
 
 #include <dlfcn.h>
 #include <nccl.h>   // types only: the library is dlopen'ed (libnccl.so.2), nothing links against it
@@ -103,6 +104,8 @@ NcclApi &nccl_api()
 {
   static NcclApi api;
   static bool loaded = false;
+  static std::mutex mu;
+  std::lock_guard<std::mutex> guard(mu);
   if (loaded) return api;
   void *h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD | RTLD_GLOBAL);   // the copy the host application already loaded, if any
   if (!h) h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);

@@ -481,24 +481,43 @@ void build_prolongation(const HostBsr &A_in, const uint8_t *free_mask, int bc, c
     std::iota(cord.begin(), cord.end(), 0);
     std::sort(cord.begin(), cord.end(), [&](i32 a, i32 b) { return full[a] < full[b]; });
     for (size_t q = 0; q < ncls; q++) cls_order[cord[q]] = (i32)q;
-    // canonical labels: class-major, canonical key inside a class
+    // canonical labels: class-major (unshared vertices first -- nobody else sees them --, then the shared classes in their consistent
+    // order), canonical key inside a class.  Counting sort by class; a class is only sorted by key when the keys are not already
+    // ascending in the local number (they are on the fine level).
     std::vector<i32> order(n), lab(n);
-    std::iota(order.begin(), order.end(), 0);
-    std::sort(order.begin(), order.end(), [&](i32 a, i32 b) {
-      const i32 ca = cls_order[pd.eqc[a]], cb = cls_order[pd.eqc[b]];
-      return ca < cb || (ca == cb && pd.canon[a] < pd.canon[b]);
-    });
+    {
+      std::vector<i32> slot(ncls);
+      for (size_t c = 0; c < ncls; c++) slot[c] = (c == 0) ? 0 : 1 + cls_order[c] - (cls_order[c] > cls_order[0] ? 1 : 0);
+      std::vector<i64> start(ncls + 1, 0);
+      for (i64 v = 0; v < n; v++) start[slot[pd.eqc[v]] + 1]++;
+      for (size_t c = 0; c < ncls; c++) start[c + 1] += start[c];
+      std::vector<i64> pos(start.begin(), start.end() - 1);
+      for (i64 v = 0; v < n; v++) order[pos[slot[pd.eqc[v]]]++] = (i32)v;
+      for (size_t c = 0; c < ncls; c++) {
+        bool sorted = true;
+        for (i64 q = start[c] + 1; q < start[c + 1] && sorted; q++) sorted = pd.canon[order[q - 1]] < pd.canon[order[q]];
+        if (!sorted) std::sort(order.begin() + start[c], order.begin() + start[c + 1], [&](i32 a, i32 b) { return pd.canon[a] < pd.canon[b]; });
+      }
+    }
     for (i64 q = 0; q < n; q++) lab[order[q]] = (i32)q;
+    // class a may use couplings to class b: table instead of a set comparison per matrix entry
+    std::vector<uint8_t> fe(ncls * ncls);
+    for (size_t a = 0; a < ncls; a++) for (size_t b = 0; b < ncls; b++) fe[a * ncls + b] = pd.finer_or_equal((i32)a, (i32)b) ? 1 : 0;
+    auto usable = [&](i64 i, i32 j) { return fe[(size_t)pd.eqc[i] * ncls + pd.eqc[j]] != 0; };
     // relabelled matrix restricted to the couplings a vertex may use: columns of a class that is shared by at least the row's ranks
     HostBsr B;
     B.nrows = n; B.ncols = n; B.bh = A_in.bh; B.bw = A_in.bw;
     B.rowptr.assign(n + 1, 0);
-    for (i64 q = 0; q < n; q++) {
-      const i64 i = order[q];
-      i64 c = 0;
-      for (i64 e = A_in.rowptr[i]; e < A_in.rowptr[i + 1]; e++) c += pd.finer_or_equal(pd.eqc[i], pd.eqc[A_in.col[e]]) ? 1 : 0;
-      B.rowptr[q + 1] = B.rowptr[q] + c;
-    }
+    parallel_for(n, [&](i64 lo, i64 hi) {
+      for (i64 q = lo; q < hi; q++) {
+        const i64 i = order[q];
+        i64 c = 0;
+        if (pd.eqc[i] == 0) c = A_in.rowptr[i + 1] - A_in.rowptr[i];   // an unshared vertex may use all its couplings
+        else for (i64 e = A_in.rowptr[i]; e < A_in.rowptr[i + 1]; e++) c += usable(i, A_in.col[e]) ? 1 : 0;
+        B.rowptr[q + 1] = c;
+      }
+    });
+    for (i64 q = 0; q < n; q++) B.rowptr[q + 1] += B.rowptr[q];
     B.col.resize(B.rowptr[n]);
     B.val.resize((size_t)B.rowptr[n] * bs);
     parallel_for(n, [&](i64 lo, i64 hi) {
@@ -507,7 +526,7 @@ void build_prolongation(const HostBsr &A_in, const uint8_t *free_mask, int bc, c
         const i64 i = order[q];
         ent.clear();
         for (i64 e = A_in.rowptr[i]; e < A_in.rowptr[i + 1]; e++)
-          if (pd.finer_or_equal(pd.eqc[i], pd.eqc[A_in.col[e]])) ent.emplace_back(lab[A_in.col[e]], e);
+          if (pd.eqc[i] == 0 || usable(i, A_in.col[e])) ent.emplace_back(lab[A_in.col[e]], e);
         std::sort(ent.begin(), ent.end());
         i64 p = B.rowptr[q];
         for (auto &x : ent) { B.col[p] = x.first; std::memcpy(&B.val[p * bs], &A_in.val[x.second * bs], sizeof(double) * bs); p++; }

@@ -205,3 +205,26 @@ def test_parallel_smoother_flag_protocol(grid):
                 assert rel(got[r][0], xo[r]) < TOL_VCYCLE, ("x", ru, ur, xz, back, r, rel(got[r][0], xo[r]))
                 if ur:
                     assert rel(got[r][1], ro[r]) < TOL_VCYCLE, ("res", ru, ur, xz, back, r, rel(got[r][1], ro[r]))
+
+
+def test_nccl_transport_two_gpus():
+    """tests/run_nccl_check.py under torch.distributed.run on 2 GPUs: one rank per GPU, the library's own NCCL communicator carries
+    the halo exchange / dot products / coarse gather (also inside the captured V-cycle graph); parity against the multi-rank oracle.
+    Skipped on a single-GPU box (the same ranks then run as threads in the tests above)."""
+    import os
+    import socket
+    import subprocess
+    import sys
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", str(port), os.path.join(root, "tests", "run_nccl_check.py")]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=root)
+    assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
+    assert "FAIL" not in out.stdout
