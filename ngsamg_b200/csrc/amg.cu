@@ -217,6 +217,13 @@ struct Amg {
   void level_smooth(Level &L, double *x, const double *b, double *res, bool ru, bool ur, bool xz, bool backward);
   void vcycle_record();
   void vcycle();  // rhs = lev[0].rhs -> x = lev[0].x
+  enum { CYCLE_V = 0, CYCLE_W = 1, CYCLE_BS = 2 };
+  int cycle = CYCLE_V;
+  void coarse_solve_record();
+  void restrict_record(int l, const double *res);
+  void w_visit(int l);
+  void v_from_level(int s, bool ru, bool ur, bool xz);
+  void bs_record();
   double dot(i64 n, const double *a, const double *b);
   // io helpers
   void ensure_io(i64 n);
@@ -807,8 +814,13 @@ void Amg::finalize()
   auto tick = [](std::chrono::steady_clock::time_point t) { return std::chrono::duration<double>(std::chrono::steady_clock::now() - t).count(); };
   const int max_levels = (int)flags.num("max_levels", 10);            // base_factory.hpp:88-152
   const i64 max_coarse = (i64)flags.num("max_coarse_size", 50);
-  const std::string cycle = flags.str("mg_cycle", "V");
-  if (cycle != "V" && cycle != "v") throw Error("mg_cycle=" + cycle + " is not supported by the B200 path (V only)");
+  {
+    const std::string cyc = flags.str("mg_cycle", "V");       // AMGMatrix::SetCycle, amg_pc.cpp:578-586
+    if (cyc == "V" || cyc == "v") cycle = CYCLE_V;
+    else if (cyc == "W" || cyc == "w") cycle = CYCLE_W;
+    else if (cyc == "BS" || cyc == "bs") cycle = CYCLE_BS;
+    else throw Error("mg_cycle=" + cyc + " is not supported (V | W | BS)");
+  }
   const std::string clev = flags.str("clev", "inv");
   const bool elast = type.find("elast") != std::string::npos;
   const int dim = (type.find("2d") != std::string::npos) ? 2 : 3;
@@ -1124,8 +1136,10 @@ void Amg::finalize_parallel()
   const bool verbose = flags.str("log_level", "none") != "none";
   const int me = comm.rank(), R = comm.size();
   const int max_levels = (int)flags.num("max_levels", 10);
-  const std::string cycle = flags.str("mg_cycle", "V");
-  if (cycle != "V" && cycle != "v") throw Error("mg_cycle=" + cycle + " is not supported by the B200 path (V only)");
+  {
+    const std::string cyc = flags.str("mg_cycle", "V");
+    if (cyc != "V" && cyc != "v") throw Error("mg_cycle=" + cyc + ": the multi-rank path runs V-cycles only");
+  }
   const bool elast = type.find("elast") != std::string::npos;
   const int dim = (type.find("2d") != std::string::npos) ? 2 : 3;
   const bool regularize = flags.flag("regularize_cmats", elast);
@@ -1194,6 +1208,7 @@ void Amg::finalize_parallel()
         Amg &N = *nested;
         N.type = type; N.device = device; N.flags = flags;
         N.flags.set("max_levels", std::to_string(std::max(1, max_levels - l)));
+        N.flags.set("mg_cycle", "V");
         N.st = st; N.owns_stream = false;
         NGB_CUDA(cudaEventCreate(&N.ev0));
         NGB_CUDA(cudaEventCreate(&N.ev1));
@@ -1622,6 +1637,8 @@ void Amg::vcycle_record()
     }
     return;
   }
+  if (cycle == CYCLE_W) { w_visit(0); return; }
+  if (cycle == CYCLE_BS) { bs_record(); return; }
   const int NL = (int)lev.size();
   for (int l = 0; l + 1 < NL; l++) {
     Level &L = *lev[l];
@@ -1659,6 +1676,92 @@ void Amg::vcycle_record()
       level_smooth(L, L.x, L.rhs, L.res, false, false, false, true);
       L.result = L.x;
     }
+  }
+}
+
+// ---- W and BS cycles (AMGMatrix::SmoothW / SmoothBS / SmoothVFromLevel, amg_matrix.cpp:37-157, 310-374), single rank.
+// Everything goes through the general smoother protocol (level_smooth); iterates live in L.x, residuals in L.res.
+void Amg::coarse_solve_record()
+{
+  Level &L = *lev.back();
+  if (has_cinv) { k_dense_gemv<<<nblk((i64)cinv_n * 32), TB, 0, st>>>(cinv_n, d_cinv, L.rhs, L.x); launches++; }
+  else NGB_CUDA(cudaMemsetAsync(L.x, 0, sizeof(double) * L.npad * L.b, st));
+  L.result = L.x;
+}
+
+void Amg::restrict_record(int l, const double *res)
+{
+  Level &L = *lev[l];
+  transfer(L.PT, res, nullptr, lev[l + 1]->rhs, 1.0, 0.0, L.d_pt_rowmap);
+}
+
+// the recursion of SmoothW (:46-104).  On level 0 the reference first runs a V-type visit and then the W-type visit below, which
+// restarts from x = 0, res = b: the first visit leaves no trace in the result and is not run.
+void Amg::w_visit(int l)
+{
+  const int NL = (int)lev.size();
+  if (l + 1 >= NL) { coarse_solve_record(); return; }
+  Level &L = *lev[l];
+  Level &C = *lev[l + 1];
+  const size_t bytes = sizeof(double) * L.npad * L.b;
+  NGB_CUDA(cudaMemsetAsync(L.x, 0, bytes, st));
+  NGB_CUDA(cudaMemcpyAsync(L.res, L.rhs, bytes, cudaMemcpyDeviceToDevice, st));
+  level_smooth(L, L.x, L.rhs, L.res, true, true, true, false);
+  restrict_record(l, L.res);
+  w_visit(l + 1);
+  transfer(L.P, C.x, L.x, L.x, 1.0, 1.0);
+  level_smooth(L, L.x, L.rhs, L.res, false, true, false, true);    // SmoothBack(x, b, res, false, true, false)   :82
+  level_smooth(L, L.x, L.rhs, L.res, true, true, false, false);    // Smooth(x, b, res, true, true, false)        :83
+  restrict_record(l, L.res);
+  w_visit(l + 1);
+  transfer(L.P, C.x, L.x, L.x, 1.0, 1.0);
+  level_smooth(L, L.x, L.rhs, L.res, false, false, false, true);   // :89
+  L.result = L.x;
+}
+
+// SmoothVFromLevel (:310-374) on the work vectors of level s
+void Amg::v_from_level(int s, bool ru, bool ur, bool xz)
+{
+  const int NL = (int)lev.size();
+  Level &S = *lev[s];
+  level_smooth(S, S.x, S.rhs, S.res, ru, true, xz, false);
+  restrict_record(s, S.res);
+  for (int l = s + 1; l + 1 < NL; l++) {
+    Level &L = *lev[l];
+    const size_t bytes = sizeof(double) * L.npad * L.b;
+    NGB_CUDA(cudaMemsetAsync(L.x, 0, bytes, st));
+    NGB_CUDA(cudaMemcpyAsync(L.res, L.rhs, bytes, cudaMemcpyDeviceToDevice, st));
+    level_smooth(L, L.x, L.rhs, L.res, true, true, true, false);
+    restrict_record(l, L.res);
+  }
+  coarse_solve_record();
+  for (int l = NL - 2; l > s; l--) {
+    Level &L = *lev[l];
+    transfer(L.P, lev[l + 1]->x, L.x, L.x, 1.0, 1.0);
+    level_smooth(L, L.x, L.rhs, L.res, false, false, false, true);
+  }
+  transfer(S.P, lev[s + 1]->x, S.x, S.x, 1.0, 1.0);
+  level_smooth(S, S.x, S.rhs, S.res, false, ur, false, true);
+}
+
+// SmoothBS (:107-157): every level is smoothed by a V-cycle that starts there
+void Amg::bs_record()
+{
+  const int NL = (int)lev.size();
+  for (int l = 0; l + 1 < NL; l++) {
+    Level &L = *lev[l];
+    const size_t bytes = sizeof(double) * L.npad * L.b;
+    NGB_CUDA(cudaMemsetAsync(L.x, 0, bytes, st));
+    NGB_CUDA(cudaMemcpyAsync(L.res, L.rhs, bytes, cudaMemcpyDeviceToDevice, st));
+    v_from_level(l, true, true, true);
+    restrict_record(l, L.res);
+  }
+  coarse_solve_record();
+  for (int l = NL - 2; l >= 0; l--) {
+    Level &L = *lev[l];
+    transfer(L.P, lev[l + 1]->x, L.x, L.x, 1.0, 1.0);
+    v_from_level(l, false, false, false);
+    L.result = L.x;
   }
 }
 

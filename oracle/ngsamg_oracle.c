@@ -761,6 +761,93 @@ void orc_amg_apply(orc_amg *a, const double *b, double *x)
   }
 }
 
+/* ---- W and BS cycles (amg_matrix.cpp:37-157, 307-374) ---------------------------------------------------- */
+static void restrict_res(orc_amg *a, int l, const double *res)
+{
+  orc_level *L = &a->lev[l], *C = &a->lev[l + 1];
+  memset(C->rhs, 0, sizeof(double) * (size_t)(C->n * C->b));
+  orc_spmv_add(L->nc, L->bc, L->b, L->pt_rp, L->pt_ci, L->pt_v, 1.0, res, C->rhs);
+}
+static void prolong_add(orc_amg *a, int l, double *x)
+{
+  orc_level *L = &a->lev[l], *C = &a->lev[l + 1];
+  orc_spmv_add(L->n, L->b, L->bc, L->p_rp, L->p_ci, L->p_v, 1.0, C->x, x);
+}
+
+/* the recursion of AMGMatrix::SmoothW (:46-104).  On level 0 the reference first runs a V-type visit and then the W-type visit
+   below, which starts from x = 0 and res = b again: the first visit leaves no trace in the result, so only the second is run. */
+static void w_visit(orc_amg *a, int l, double *xl, const double *bl)
+{
+  const int NL = a->nlevels;
+  if (l + 1 >= NL) { coarse_solve(a, bl, xl); return; }
+  orc_level *L = &a->lev[l], *C = &a->lev[l + 1];
+  i64 nb = L->n * L->b;
+  memset(xl, 0, sizeof(double) * (size_t)nb);
+  memcpy(L->res, bl, sizeof(double) * (size_t)nb);
+  level_smooth(L, xl, bl, L->res, 1, 1, 1, 0);
+  restrict_res(a, l, L->res);
+  w_visit(a, l + 1, C->x, C->rhs);
+  prolong_add(a, l, xl);
+  level_smooth(L, xl, bl, L->res, 0, 1, 0, 1);   /* SmoothBack(x, b, res, false, true, false)  :82 */
+  level_smooth(L, xl, bl, L->res, 1, 1, 0, 0);   /* Smooth(x, b, res, true, true, false)       :83 */
+  restrict_res(a, l, L->res);
+  w_visit(a, l + 1, C->x, C->rhs);
+  prolong_add(a, l, xl);
+  level_smooth(L, xl, bl, L->res, 0, 0, 0, 1);   /* :89 */
+}
+void orc_amg_apply_w(orc_amg *a, const double *b, double *x) { w_visit(a, 0, x, b); }
+
+/* AMGMatrix::SmoothVFromLevel (:310-374) */
+static void v_from_level(orc_amg *a, int s, double *x, const double *b, double *res, int ru, int ur, int xz)
+{
+  const int NL = a->nlevels;
+  level_smooth(&a->lev[s], x, b, res, ru, 1, xz, 0);
+  restrict_res(a, s, res);
+  for (int l = s + 1; l + 1 < NL; l++) {
+    orc_level *L = &a->lev[l];
+    i64 nb = L->n * L->b;
+    memset(L->x, 0, sizeof(double) * (size_t)nb);
+    memcpy(L->res, L->rhs, sizeof(double) * (size_t)nb);
+    level_smooth(L, L->x, L->rhs, L->res, 1, 1, 1, 0);
+    restrict_res(a, l, L->res);
+  }
+  coarse_solve(a, a->lev[NL - 1].rhs, a->lev[NL - 1].x);
+  for (int l = NL - 2; l > s; l--) {
+    orc_level *L = &a->lev[l];
+    prolong_add(a, l, L->x);
+    level_smooth(L, L->x, L->rhs, L->res, 0, 0, 0, 1);
+  }
+  prolong_add(a, s, x);
+  level_smooth(&a->lev[s], x, b, res, 0, ur, 0, 1);
+}
+
+/* AMGMatrix::SmoothBS (:107-157): every level is "smoothed" by a V-cycle that starts there */
+void orc_amg_apply_bs(orc_amg *a, const double *b, double *x)
+{
+  const int NL = a->nlevels;
+  for (int l = 0; l + 1 < NL; l++) {
+    orc_level *L = &a->lev[l];
+    double *xl = (l == 0) ? x : L->x;
+    const double *bl = (l == 0) ? b : L->rhs;
+    i64 nb = L->n * L->b;
+    memset(xl, 0, sizeof(double) * (size_t)nb);
+    memcpy(L->res, bl, sizeof(double) * (size_t)nb);
+    v_from_level(a, l, xl, bl, L->res, 1, 1, 1);
+    restrict_res(a, l, L->res);
+  }
+  {
+    orc_level *L = &a->lev[NL - 1];
+    coarse_solve(a, (NL == 1) ? b : L->rhs, (NL == 1) ? x : L->x);
+  }
+  for (int l = NL - 2; l >= 0; l--) {
+    orc_level *L = &a->lev[l];
+    double *xl = (l == 0) ? x : L->x;
+    const double *bl = (l == 0) ? b : L->rhs;
+    prolong_add(a, l, xl);
+    v_from_level(a, l, xl, bl, L->res, 0, 0, 0);
+  }
+}
+
 /* AMGMatrix::MultAdd, amg_matrix.cpp:385-389: x += s * V(b) */
 void orc_amg_apply_add(orc_amg *a, double s, const double *b, double *x)
 {

@@ -62,6 +62,8 @@ def lib():
     L.orc_amg_set_coarse_inv.restype = ci
     L.orc_amg_smooth.argtypes = [vp, ci, f64p, f64p, f64p, ci, ci, ci, ci]
     L.orc_amg_apply.argtypes = [vp, f64p, f64p]
+    L.orc_amg_apply_w.argtypes = [vp, f64p, f64p]
+    L.orc_amg_apply_bs.argtypes = [vp, f64p, f64p]
     L.orc_amg_apply_add.argtypes = [vp, dbl, f64p, f64p]
     L.orc_amg_pcg.argtypes = [vp, f64p, f64p, dbl, ci, f64p]
     L.orc_amg_pcg.restype = ci
@@ -227,10 +229,11 @@ class OracleAMG:
     def smooth(self, l, x, b, res, res_updated=False, update_res=True, x_zero=False, backwards=False):
         lib().orc_amg_smooth(self.h, l, x, b, res, int(res_updated), int(update_res), int(x_zero), int(backwards))
 
-    def apply(self, b):
-        """AMGMatrix::Mult"""
+    def apply(self, b, cycle="V"):
+        """AMGMatrix::Mult -> SmoothV / SmoothW / SmoothBS (amg_matrix.cpp:37-307)"""
         x = np.zeros(self.n0)
-        lib().orc_amg_apply(self.h, np.ascontiguousarray(b, np.float64), x)
+        fn = {"V": lib().orc_amg_apply, "W": lib().orc_amg_apply_w, "BS": lib().orc_amg_apply_bs}[cycle]
+        fn(self.h, np.ascontiguousarray(b, np.float64), x)
         return x
 
     def apply_add(self, s, b, x):

@@ -415,3 +415,37 @@ def test_multicolor_fine_level_option():
     bp = np.zeros(n); bp[rank] = b
     xo = amg.apply(bp)[rank]
     assert rel(pc * b, xo) < TOL_VCYCLE
+
+
+@pytest.mark.parametrize("cycle", ["W", "BS"])
+@pytest.mark.parametrize("problem", ["poisson", "elasticity"])
+def test_w_and_bs_cycles(cycle, problem):
+    """ngs_amg_mg_cycle = W | BS (Options::MG_CYCLE, amg_pc.cpp:293; AMGMatrix::SmoothW / SmoothBS / SmoothVFromLevel,
+    amg_matrix.cpp:37-157, 310-374): same hierarchy, other cycle -- every call goes through the general smoother protocol"""
+    if problem == "poisson":
+        p, A = poisson(12)
+        pc = ng.h1_scal(A, p["free"], ngs_amg_max_coarse_size=12, ngs_amg_mg_cycle=cycle)
+        amg = O.OracleAMG(to_oracle(A), p["free"], [to_oracle(P) for P in pc.GetMap()])
+        n = p["n"]
+        fr = p["free"]
+    else:
+        p, A = elasticity(7, 4, 4)
+        pc = ng.elast_3d(A, p["free"], vertex_xyz=p["xyz"], ngs_amg_max_coarse_size=6, ngs_amg_mg_cycle=cycle)
+        amg = O.OracleAMG(to_oracle(A), p["free"], [to_oracle(P) for P in pc.GetMap()], pinv=True)
+        n = 3 * p["n"]
+        fr = np.repeat(p["free"], 3)
+    assert pc.GetNLevels() >= 3, "needs at least three levels to tell the cycles apart"
+    b = rand(17, n) * fr
+    x = np.zeros(n)
+    pc.Mult(b, x)
+    xo = amg.apply(b, cycle)
+    assert rel(x, xo) < TOL_VCYCLE, rel(x, xo)
+    assert rel(x, amg.apply(b, "V")) > 1e-3, "the cycle must differ from the V-cycle"
+    # MultAdd and the symmetric-operator property hold for every cycle
+    y = np.ones(n)
+    pc.MultAdd(-0.5, b, y)
+    assert rel(y, 1.0 - 0.5 * xo) < TOL_VCYCLE
+    b2 = rand(18, n) * fr
+    x2 = np.zeros(n)
+    pc.Mult(b2, x2)
+    assert abs(np.dot(x, b2) - np.dot(b, x2)) < 1e-10 * abs(np.dot(x, b2))
