@@ -193,6 +193,7 @@ struct Amg {
   void hybrid_smooth_res(Level &L, bool backward, double *x, double *res, bool x_zero);
   void hybrid_smooth_rhs(Level &L, bool backward, double *x, const double *b, double *work, bool x_zero);
   void hybrid_smooth(Level &L, double *x, const double *b, double *res, bool ru, bool ur, bool xz, bool backward);
+  void hybrid_level_smooth(Level &L, double *x, const double *b, double *res, bool ru, bool ur, bool xz, bool backward);
 
   ~Amg();
   void finalize();
@@ -1571,7 +1572,6 @@ void Amg::hybrid_smooth_rhs(Level &L, bool backward, double *x, const double *b,
 // HybridBaseSmoother::SmoothImpl (hybrid_base_smoother.cpp:242-290): the cost heuristic that picks the RES or the RHS form
 void Amg::hybrid_smooth(Level &L, double *x, const double *b, double *res, bool ru, bool ur, bool xz, bool backward)
 {
-  if (L.sm_symm || L.sm_steps != 1) throw Error("multi-rank levels support one non-symmetric Gauss-Seidel step per smoothing call");
   if (ur) {
     if (!ru) {
       if (!xz) {
@@ -1584,6 +1584,23 @@ void Amg::hybrid_smooth(Level &L, double *x, const double *b, double *res, bool 
       }
     } else hybrid_smooth_res(L, backward, x, res, xz);
   } else hybrid_smooth_rhs(L, backward, x, b, res, xz);
+}
+
+// ProxySmoother around the hybrid smoother (sm_steps > 1 or sm_symm, amg_pc.cpp:1079-1082)
+void Amg::hybrid_level_smooth(Level &L, double *x, const double *b, double *res, bool ru, bool ur, bool xz, bool backward)
+{
+  const int k = std::max(1, L.sm_steps);
+  if (L.sm_symm) {
+    hybrid_smooth(L, x, b, res, ru, ur, xz, false);
+    hybrid_smooth(L, x, b, res, ur, ur, false, true);
+    for (int j = 0; j < k - 1; j++) {
+      hybrid_smooth(L, x, b, res, ur, ur, false, false);
+      hybrid_smooth(L, x, b, res, ur, ur, false, true);
+    }
+  } else {
+    hybrid_smooth(L, x, b, res, ru, ur, xz, backward);
+    for (int j = 0; j < k - 1; j++) hybrid_smooth(L, x, b, res, ur, ur, false, backward);
+  }
 }
 
 // ProxySmoother (base_smoother.hpp:169-229) + SmoothK / SmoothBackK / SmoothSymmK (:79-112)
@@ -1614,7 +1631,14 @@ void Amg::vcycle_record()
     for (int l = 0; l < npar; l++) {
       Level &L = *lev[l];
       Level &C = *lev[l + 1];
-      if (L.sm_symm || L.sm_steps != 1) throw Error("multi-rank levels support one non-symmetric Gauss-Seidel step per smoothing call");
+      if (L.sm_symm || L.sm_steps != 1) {
+        // general protocol (ProxySmoother): x = 0, res = b, Smooth(x, b, res, true, true, true)
+        NGB_CUDA(cudaMemsetAsync(L.x, 0, sizeof(double) * L.npad * L.b, st));
+        NGB_CUDA(cudaMemcpyAsync(L.res, L.rhs, sizeof(double) * L.npad * L.b, cudaMemcpyDeviceToDevice, st));
+        hybrid_level_smooth(L, L.x, L.rhs, L.res, true, true, true, false);
+        transfer(L.PT, L.res, nullptr, C.rhs, 1.0, 0.0, L.d_pt_rowmap);
+        continue;
+      }
       NGB_CUDA(cudaMemcpyAsync(L.res, L.rhs, sizeof(double) * L.npad * L.b, cudaMemcpyDeviceToDevice, st));
       dis2co(L, L.res);
       tri_dispatch(L, false, false, true, L.res, nullptr, L.x, L.res);
@@ -1628,6 +1652,11 @@ void Amg::vcycle_record()
       Level &L = *lev[l];
       Level &C = *lev[l + 1];
       transfer(L.P, C.result, L.x, L.x, 1.0, 1.0);
+      if (L.sm_symm || L.sm_steps != 1) {
+        hybrid_level_smooth(L, L.x, L.rhs, L.res, false, false, false, true);
+        L.result = L.x;
+        continue;
+      }
       if (L.G.nnz) transfer(L.G, L.x, L.rhs, L.res, -1.0, 1.0);
       else NGB_CUDA(cudaMemcpyAsync(L.res, L.rhs, sizeof(double) * L.npad * L.b, cudaMemcpyDeviceToDevice, st));
       dis2co(L, L.res);
@@ -2342,7 +2371,7 @@ int ngsamg_b200_smooth(ngsamg_b200_t *h, int level, double *x, const double *b, 
     k_permute_in<<<nblk(L.n), TB, 0, a.st>>>(L.n, L.b, L.d_perm, rd, L.res);
   }
   // multi-rank level: HybridBaseSmoother::Smooth / SmoothBack -- collective; x CUMULATED, b and res DISTRIBUTED
-  if (a.par && L.par) a.hybrid_smooth(L, L.x, L.rhs, L.res, res_updated != 0, update_res != 0, x_zero != 0, backwards != 0);
+  if (a.par && L.par) a.hybrid_level_smooth(L, L.x, L.rhs, L.res, res_updated != 0, update_res != 0, x_zero != 0, backwards != 0);
   else a.level_smooth(L, L.x, L.rhs, L.res, res_updated != 0, update_res != 0, x_zero != 0, backwards != 0);
   k_permute_out<<<nblk(L.n), TB, 0, a.st>>>(L.n, L.b, L.d_perm, L.x, a.io_b, 1.0, 0);
   a.from_device(x, a.io_b, n);

@@ -72,7 +72,8 @@ def dcc_lists(rank, n, peers, ex):
 class HybridLevel:
     """one distributed level: all ranks' local matrices + sharing lists; builds M, G, mod diag, stage masks, dinv per rank"""
 
-    def __init__(self, A_loc, free, peers, ex, pinv=False):
+    def __init__(self, A_loc, free, peers, ex, pinv=False, sm_steps=1, sm_symm=False):
+        self.sm_steps, self.sm_symm = int(sm_steps), bool(sm_symm)
         self.R = len(A_loc)
         self.A = A_loc
         self.b = A_loc[0].bh
@@ -300,6 +301,20 @@ class HybridLevel:
         else:
             self.smooth_rhs(x, b, backward, x_zero)
 
+    def level_smooth(self, x, b, res, ru, ur, xz, backward):
+        """ProxySmoother around the hybrid smoother: SmoothK / SmoothBackK / SmoothSymmK (base_smoother.hpp:79-112, 169-229)"""
+        k = max(1, self.sm_steps)
+        if self.sm_symm:
+            self.smooth(x, b, res, ru, ur, xz, False)
+            self.smooth(x, b, res, ur, ur, False, True)
+            for _ in range(k - 1):
+                self.smooth(x, b, res, ur, ur, False, False)
+                self.smooth(x, b, res, ur, ur, False, True)
+        else:
+            self.smooth(x, b, res, ru, ur, xz, backward)
+            for _ in range(k - 1):
+                self.smooth(x, b, res, ur, ur, False, backward)
+
     def mult(self, x):
         """HybridBaseMatrix::Mult: y = (M + G) x, x CUMULATED, y DISTRIBUTED"""
         out = [np.zeros_like(x[r]) for r in range(self.R)]
@@ -317,14 +332,15 @@ class OracleParAMG:
     ctr       = dict(maps=[local -> merged dof per rank]) for the contracted level npar
     nested    = dict(prols=[Bsr ...], sm kwargs) : the serial hierarchy on the merged level (OracleAMG)"""
 
-    def __init__(self, A0, free0, peers0, ex0, prols, halos, ctr_maps, nested_prols, pinv=False, nested_free=None):
+    def __init__(self, A0, free0, peers0, ex0, prols, halos, ctr_maps, nested_prols, pinv=False, nested_free=None, sm_steps=1,
+                 sm_symm=False):
         self.R = len(A0)
         self.npar = len(prols)
         self.levels = []
         A, free, peers, ex = A0, free0, peers0, ex0
         self.P, self.PT = [], []
         for l in range(self.npar):
-            self.levels.append(HybridLevel(A, free, peers, ex, pinv))
+            self.levels.append(HybridLevel(A, free, peers, ex, pinv, sm_steps, sm_symm))
             Pl = prols[l]
             PTl = [O.transpose(p) for p in Pl]
             self.P.append(Pl); self.PT.append(PTl)
@@ -344,7 +360,7 @@ class OracleParAMG:
             acc = acc + sp.coo_matrix((C.data, (sd[C.row], sd[C.col])), shape=(N * b, N * b)).tocsr()
         self.A_merged = O.Bsr.from_scipy(acc, b, b)
         self.N = N
-        self.nested = O.OracleAMG(self.A_merged, nested_free, nested_prols, pinv=pinv)
+        self.nested = O.OracleAMG(self.A_merged, nested_free, nested_prols, pinv=pinv, sm_steps=sm_steps, sm_symm=sm_symm)
 
     def contracted_solve(self, rhs):
         b = self.b_ctr
@@ -363,7 +379,7 @@ class OracleParAMG:
             L = self.levels[l]
             x = [np.zeros_like(v) for v in rhs[l]]
             res = [v.copy() for v in rhs[l]]
-            L.smooth_res(x, res, False, True)
+            L.level_smooth(x, rhs[l], res, True, True, True, False)
             xs.append(x); ress.append(res)
             nxt = []
             for r in range(R):
@@ -377,7 +393,7 @@ class OracleParAMG:
             x = xs[l]
             for r in range(R):
                 O.spmv_add(self.P[l][r], 1.0, xc[r], x[r])
-            L.smooth_rhs(x, rhs[l], True, False)
+            L.level_smooth(x, rhs[l], [np.zeros_like(v) for v in x], False, False, False, True)
             xc = x
             self.level_x[l] = x
         self.level_rhs, self.level_res = rhs, ress

@@ -31,7 +31,7 @@ def _build_ranks(parts, cls, b, **flags):
     return par.run_ranks(R, fn)
 
 
-def _oracle_for(parts, pcs, b, pinv=False):
+def _oracle_for(parts, pcs, b, pinv=False, **sm):
     R = len(parts)
     npar = pcs[0].GetNParallelLevels()
     assert all(pc.GetNParallelLevels() == npar for pc in pcs)
@@ -44,7 +44,7 @@ def _oracle_for(parts, pcs, b, pinv=False):
     nested = pcs[0].GetContracted()
     nprols = [to_oracle(P) for P in nested.GetMap()]
     A0 = [O.Bsr(p["n"], p["n"], b, b, p["rowptr"], p["col"], p["val"]) for p in parts]
-    return OP.OracleParAMG(A0, [p["free"] for p in parts], halos[0][0], halos[0][1], prols, halos, maps, nprols, pinv=pinv), npar
+    return OP.OracleParAMG(A0, [p["free"] for p in parts], halos[0][0], halos[0][1], prols, halos, maps, nprols, pinv=pinv, **sm), npar
 
 
 def _collective(pcs, fn):
@@ -228,3 +228,33 @@ def test_nccl_transport_two_gpus():
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=root)
     assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
     assert "FAIL" not in out.stdout
+
+
+@pytest.mark.parametrize("sm", [dict(sm_steps=2), dict(sm_symm=True), dict(sm_steps=2, sm_symm=True)])
+def test_parallel_proxy_smoothers(sm):
+    """sm_steps > 1 / sm_symm on distributed levels: ProxySmoother around the hybrid Gauss-Seidel (amg_pc.cpp:1079-1082,
+    base_smoother.hpp:169-229) -- V-cycle and PCG against the multi-rank oracle"""
+    parts = S.partition_poisson3d(11, 9, 13, grid=(1, 1, 2))
+    flags = {"ngs_amg_" + k: v for k, v in sm.items()}
+    pcs = _build_ranks(parts, par.h1_scal_par, 1, ngs_amg_max_coarse_size=15, ngs_amg_b200_ctr_nv=150, **flags)
+    amg, npar = _oracle_for(parts, pcs, 1, **sm)
+    assert npar >= 1
+    b = [rand(50 + r, p["n"]) * p["free"] for r, p in enumerate(parts)]
+    xo = amg.apply(b)
+
+    def ap(r, pc):
+        x = np.zeros(parts[r]["n"])
+        pc.Mult(b[r], x)
+        return x
+
+    got = _collective(pcs, ap)
+    for r in range(2):
+        assert rel(got[r], xo[r]) < TOL_VCYCLE, (sm, r, rel(got[r], xo[r]))
+    rhs = [p["rhs"] * p["free"] for p in parts]
+    _, ito, _ = amg.pcg(rhs, tol=1e-8, maxsteps=100)
+
+    def solve(r, pc):
+        x = np.zeros(parts[r]["n"])
+        return pc._pcg(rhs[r], x, 1e-8, 100)[0]
+
+    assert _collective(pcs, solve) == [ito, ito]
