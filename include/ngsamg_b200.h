@@ -58,7 +58,9 @@ typedef struct ngsamg_level_info {
  * `A`         : the assembled fine matrix (host arrays, copied)
  * `free_mask` : freedofs BitArray as bytes, one per block row (NULL = all free)
  * `vertex_xyz`: nrows x 3 vertex coordinates (elasticity: rigid-body modes; NULL for H1)
- * `flags`     : nflags (key, value) string pairs, keys as in the reference with the "ngs_amg_" prefix
+ * `flags`     : nflags (key, value) string pairs, keys as in the reference with the "ngs_amg_" prefix -- max_levels, max_coarse_size,
+ *               mg_cycle (V | W | BS, Options::MG_CYCLE amg_pc.cpp:293), clev, sm_type, sm_steps, sm_symm (+ "_spec" per-level lists),
+ *               regularize_cmats, sp_max_per_row, sp_min_frac, sp_omega, prol_type, log_level; B200-specific ones carry a "b200_" infix
  *               (amg_pc.hpp:168-172, Options::SetFromFlags amg_pc.cpp:270-339); unknown keys are ignored like
  *               NGSolve Flags does.  Lists (`*_spec`) are comma separated.
  * The hierarchy is not built yet; call ngsamg_b200_set_prolongations (optional) then ngsamg_b200_finalize. */
