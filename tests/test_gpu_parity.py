@@ -264,7 +264,7 @@ def test_edge_cases():
     assert rel(pc3 * b3, amg3.apply(b3)) < TOL_VCYCLE
     # errors are reported, not swallowed
     with pytest.raises(ng.NgsAMGError):
-        ng.h1_scal(A3, p3["free"], ngs_amg_mg_cycle="W")
+        ng.h1_scal(A3, p3["free"], ngs_amg_mg_cycle="F")      # V | W | BS are the reference's cycles (amg_pc.cpp:293)
     with pytest.raises(ng.NgsAMGError):
         ng.h1_scal(A3, p3["free"], ngs_amg_sm_type="bgs")
 
