@@ -251,6 +251,21 @@ int ngsamg_b200_coarsen_begin(const ngsamg_csr *A, const uint8_t *free_mask, con
 int ngsamg_b200_coarsen_fetch(ngsamg_b200_hostspm *m, int64_t *rowptr, int32_t *col, double *val, int32_t *vmap,
                               double *cxyz);
 
+/* ---- two-level (tile) schedule of the sequential Gauss-Seidel sweep (host only; ngsamg_b200/csrc/tiles.hpp) ---------------
+ * Groups the smoothed rows of a level matrix into compact tiles of <= max_rows graph-neighbouring rows, orders the tiles by the levels of
+ * the tile dependency DAG and the rows of a tile by their tile-local dependency levels.  Executing tile after tile, level after level, is
+ * a topological order of the row DAG of GSS3's sweep (gssmoother.cpp:195-315), i.e. it reproduces the reference's result while the number
+ * of cross-SM hops on the critical path falls from the row-DAG depth to the tile-DAG depth.  The device kernel consuming the schedule is
+ * experimental (flag ngs_amg_b200_tile_sweep); these entry points let tests validate the schedule without a device.
+ * info[9] = { ok, ntiles, npad, nonfree_pad, tile_depth, max_local_levels, merged_tiles, violations (self-check), npred }.
+ * fetch copies perm[n], tile_slice[ntiles+1], tile_nlev[ntiles], row_lvl[npad], pred_ptr[ntiles+1], pred[npred] and frees the handle. */
+typedef struct ngsamg_b200_tiles ngsamg_b200_tiles;
+int ngsamg_b200_tile_schedule_begin(const ngsamg_csr *A, const uint8_t *smoothed_mask, const int32_t *sweep_rank, int rounds, int max_rows,
+                                    ngsamg_b200_tiles **out, int64_t *info);
+int ngsamg_b200_tile_schedule_fetch(ngsamg_b200_tiles *m, int32_t *perm, int32_t *tile_slice, int32_t *tile_nlev, uint8_t *row_lvl,
+                                    int64_t *pred_ptr, int32_t *pred);
+const char *ngsamg_b200_tiles_last_error(void);
+
 #ifdef __cplusplus
 }
 #endif

@@ -12,7 +12,9 @@
 #include "../../include/ngsamg_b200.h"
 #include "device.hpp"
 #include "kernels.cuh"
+#include "kernels_tile.cuh"
 #include "par.hpp"
+#include "tiles.hpp"
 
 namespace ngb {
 
@@ -86,6 +88,14 @@ struct Level {
   i64 n_mu = 0;
   double *sendbuf = nullptr, *recvbuf = nullptr, *h_send = nullptr, *h_recv = nullptr;
   const std::vector<uint8_t> &mask() const { return par ? gs_mask : free_mask; }
+  // ---- experimental two-level (tile) schedule of the triangular sweeps (flag b200_tile_sweep, tiles.hpp / kernels_tile.cuh)
+  bool tiled = false;
+  i64 ntiles = 0;
+  int tile_maxs = 1;
+  i32 *d_tile_slice = nullptr, *d_tile_nlev = nullptr, *d_tile_pred = nullptr, *d_tile_succ = nullptr;
+  uint8_t *d_row_lvl = nullptr;
+  i64 *d_tile_pred_ptr = nullptr, *d_tile_succ_ptr = nullptr;
+  int *d_tile_done = nullptr;
 };
 
 // libnccl.so.2 entry points, resolved at run time
@@ -545,6 +555,8 @@ Amg::~Amg()
   for (auto &lp : lev) {
     Level &L = *lp;
     L.G.release();
+    dev_free(L.d_tile_slice); dev_free(L.d_tile_nlev); dev_free(L.d_tile_pred); dev_free(L.d_tile_succ); dev_free(L.d_row_lvl);
+    dev_free(L.d_tile_pred_ptr); dev_free(L.d_tile_succ_ptr); dev_free(L.d_tile_done);
     dev_free(L.d_m_idx); dev_free(L.d_g_idx); dev_free(L.d_mu_dof); dev_free(L.d_mu_ptr); dev_free(L.d_mu_pos);
     dev_free(L.sendbuf); dev_free(L.recvbuf);
     if (L.h_send) cudaFreeHost(L.h_send);
@@ -923,7 +935,25 @@ void Amg::finalize()
         int ncol = 0;
         greedy_coloring_perm(L.hA, L.sweep_rank, ncol);
       }
-      level_schedule(L.hA, L.mask(), !coarsest, L, st);
+      // EXPERIMENTAL (off by default): tile-major numbering + two-level schedule for big scalar levels
+      if (!coarsest && L.b == 1 && flags.flag("b200_tile_sweep", false) && L.n >= (i64)flags.num("b200_tile_min_rows", 200000)) {
+        TileSchedule ts;
+        const int cap = (int)flags.num("b200_tile_rows", 32);
+        build_tile_schedule(L.hA, L.mask(), L.sweep_rank, (int)flags.num("b200_tile_rounds", cap <= 32 ? 5 : 6), cap, ts);
+        if (ts.ok) {
+          L.perm = ts.perm; L.npad = ts.npad; L.nonfree_pad = ts.nonfree_pad; L.depth = ts.tile_depth;
+          L.level_start.clear();
+          L.ntiles = ts.ntiles; L.tile_maxs = cap / 32;
+          L.d_tile_slice = upload_vec(ts.tile_slice, st); L.d_tile_nlev = upload_vec(ts.tile_nlev, st);
+          L.d_row_lvl = upload_vec(ts.row_lvl, st);
+          L.d_tile_pred_ptr = upload_vec(ts.pred_ptr, st); L.d_tile_pred = upload_vec(ts.pred, st);
+          L.d_tile_succ_ptr = upload_vec(ts.succ_ptr, st); L.d_tile_succ = upload_vec(ts.succ, st);
+          L.d_tile_done = dev_alloc<int>((size_t)ts.ntiles);
+          L.tiled = true;
+          if (verbose) std::fprintf(stderr, "[ngsamg_b200] level %d: tile schedule: %lld tiles, tile DAG depth %d, <= %d local levels\n", l, (long long)ts.ntiles, ts.tile_depth, ts.max_local_levels);
+        }
+      }
+      if (!L.tiled) level_schedule(L.hA, L.mask(), !coarsest, L, st);
       L.d_err = d_err;
       host_s += tick(h0);
       if (verbose) std::fprintf(stderr, "[ngsamg_b200] level %d: level schedule %.2f s (depth %d)\n", l, tick(h0), L.depth);
@@ -1356,6 +1386,33 @@ template <int B>
 void Amg::tri(Level &L, bool backward, bool add_self, bool write_r, const double *rin, const double *self, double *out, double *rout)
 {
   const Sell &T = backward ? L.U : L.L;
+  if constexpr (B == 1) {
+    if (L.tiled) {
+      // EXPERIMENTAL two-level sweep: one warp per tile, flags between tiles (kernels_tile.cuh)
+      if (!add_self && !write_r) throw Error("tri: unsupported mode");
+      NGB_CUDA(cudaMemsetAsync(out, 0, sizeof(double) * L.npad, st));
+      NGB_CUDA(cudaMemsetAsync(L.d_tile_done, 0, sizeof(int) * (size_t)L.ntiles, st));
+      TileParams prm{(i32)L.ntiles, backward ? 1 : 0, L.d_tile_slice, L.d_tile_nlev, L.d_row_lvl,
+                     backward ? L.d_tile_succ_ptr : L.d_tile_pred_ptr, backward ? L.d_tile_succ : L.d_tile_pred, L.d_tile_done, tri_sleep_ns, d_err};
+      auto launch_tile = [&](auto kern, auto pre) {
+        int occ = 0;
+        NGB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 256, 0));
+        const int cap = std::max(1, occ) * num_sms;          // the whole grid must be resident (tiles wait for each other)
+        const int grid = (int)std::max<i64>(1, std::min<i64>((L.ntiles + 7) / 8, cap));
+        if (L.nonfree_pad) pre<<<nblk(L.nonfree_pad), TB, 0, st>>>(L.nonfree_pad, rin, self, out, rout);
+        kern<<<grid, 256, 0, st>>>(T.view(), L.diag, L.dinv, rin, self, out, rout, prm);
+      };
+      if (L.tile_maxs <= 1) {
+        if (add_self) launch_tile(k_gs_tile<1, true, false>, k_gs_tile_prefix<true, false>);
+        else launch_tile(k_gs_tile<1, false, true>, k_gs_tile_prefix<false, true>);
+      } else {
+        if (add_self) launch_tile(k_gs_tile<2, true, false>, k_gs_tile_prefix<true, false>);
+        else launch_tile(k_gs_tile<2, false, true>, k_gs_tile_prefix<false, true>);
+      }
+      launches += 2;
+      return;
+    }
+  }
   // sentinel-fill the output: a row is "published" once its entry is no longer the all-ones NaN
   NGB_CUDA(cudaMemsetAsync(out, 0xFF, sizeof(double) * L.npad * L.b, st));
   if (L.depth <= tri_level_launch_depth && L.npad > tri_level_launch_rows && (int)L.level_start.size() == L.depth + 1) {

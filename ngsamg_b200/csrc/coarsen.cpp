@@ -567,4 +567,34 @@ void build_prolongation(const HostBsr &A_in, const uint8_t *free_mask, int bc, c
   build_prolongation_canonical(A_in, free_mask, bc, xyz_in, opt, P, vmap, cxyz, nullptr);
 }
 
+// Clustering only (no orphan round, no prolongation): `rounds` pairwise matching rounds on the strength graph of the rows with
+// keep[i] != 0 -> cluster id per row (-1 for the others; isolated kept rows become singleton clusters), clusters hold at most 2^rounds
+// rows.  Used to tile a level for the two-level scheduled Gauss-Seidel sweep (tiles.cpp).
+i64 cluster_rows(const HostBsr &A, const uint8_t *keep, int rounds, double soc_thresh, std::vector<i32> &cluster)
+{
+  const i64 n = A.nrows;
+  std::vector<uint8_t> drop(n, 0);
+  if (keep) for (i64 i = 0; i < n; i++) drop[i] = keep[i] ? 0 : 1;
+  Graph G0;
+  graph_from_matrix(A, drop, G0);
+  cluster.assign(n, -1);
+  std::vector<i32> cmap;
+  Graph Gc, Gn;
+  const Graph *cur = &G0;
+  std::vector<uint8_t> nodrop;
+  i64 nc = 0;
+  for (int r = 0; r < rounds; r++) {
+    if (r > 0) nodrop.assign(cur->n, 0);
+    nc = pairing_round(*cur, (r == 0) ? drop : nodrop, soc_thresh, cmap);
+    if (r == 0) { for (i64 v = 0; v < n; v++) cluster[v] = cmap[v]; }
+    else { for (i64 v = 0; v < n; v++) if (cluster[v] >= 0) cluster[v] = cmap[cluster[v]]; }
+    if (r + 1 < rounds) {
+      coarsen_graph(*cur, cmap, nc, Gn);
+      std::swap(Gc, Gn);
+      cur = &Gc;
+    }
+  }
+  return nc;
+}
+
 }  // namespace ngb

@@ -1,0 +1,134 @@
+"""CPU tests of the two-level (tile) Gauss-Seidel schedule (ngsamg_b200/csrc/tiles.cpp through the host-only C entry points):
+the schedule must be a topological order of the row DAG of the reference's sequential sweep (gssmoother.cpp:195-315) -- checked by the
+library's own verifier AND by emulating the tile kernel's data flow (kernels_tile.cuh: out-of-tile couplings first, then the tile-local
+levels, tiles in schedule order) in numpy and comparing with the oracle's sequential sweep on the original matrix."""
+import ctypes as C
+
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+import ngsamg_b200 as ng
+from ngsamg_b200 import _lib
+from ngsamg_b200 import synthetic as S
+from helpers import rand, rel, to_oracle
+from oracle import oracle as O
+
+KEYS = ["ok", "ntiles", "npad", "nonfree_pad", "tile_depth", "max_local_levels", "merged", "violations", "npred"]
+
+
+def tile_schedule(A, mask=None, rank=None, rounds=5, max_rows=32):
+    L = _lib.lib()
+    info = np.zeros(9, np.int64)
+    h = C.c_void_p()
+    m = None if mask is None else np.ascontiguousarray(mask, np.uint8)
+    r = None if rank is None else np.ascontiguousarray(rank, np.int32)
+    abi = A._abi()
+    rc = L.ngsamg_b200_tile_schedule_begin(C.byref(abi), _lib.ptr(m), _lib.ptr(r), rounds, max_rows, C.byref(h), _lib.ptr(info))
+    assert rc == 0, L.ngsamg_b200_tiles_last_error()
+    d = dict(zip(KEYS, [int(v) for v in info]))
+    perm = np.zeros(A.nrows, np.int32)
+    ts = np.zeros(d["ntiles"] + 1, np.int32)
+    nl = np.zeros(max(d["ntiles"], 1), np.int32)
+    rl = np.zeros(max(d["npad"], 1), np.uint8)
+    pp = np.zeros(d["ntiles"] + 1, np.int64)
+    pr = np.zeros(max(d["npred"], 1), np.int32)
+    L.ngsamg_b200_tile_schedule_fetch(h, _lib.ptr(perm), _lib.ptr(ts), _lib.ptr(nl), _lib.ptr(rl), _lib.ptr(pp), _lib.ptr(pr))
+    d.update(perm=perm, tile_slice=ts, tile_nlev=nl, row_lvl=rl, pred_ptr=pp, pred=pr)
+    return d
+
+
+def emulate_forward(A, free, d, res):
+    """forward triangular half-sweep on the tile schedule, data flow as in k_gs_tile<.., ADD_SELF=false, WRITE_R=true>:
+    delta = (L + D)^-1 res in the sweep order, rout = res - (L + D) delta;  returns (delta, rout) in the ORIGINAL numbering"""
+    n = A.shape[0]
+    perm = d["perm"].astype(np.int64)
+    inv = np.full(d["npad"], -1, np.int64)
+    inv[perm] = np.arange(n)
+    Ap = A.tocsr()
+    diag = Ap.diagonal()
+    out = np.zeros(n)
+    rout = res.copy()
+    done = np.zeros(d["ntiles"], bool)
+    for t in range(d["ntiles"]):
+        for q in d["pred"][d["pred_ptr"][t]:d["pred_ptr"][t + 1]]:
+            assert done[q], "a tile runs before a tile it waits for"
+        r0, r1 = d["tile_slice"][t] * 32, d["tile_slice"][t + 1] * 32
+        rows = [r for r in range(r0, r1) if d["row_lvl"][r] != 255]
+        acc = {}
+        for r in rows:                                   # out-of-tile couplings: lower rows of OTHER tiles (final values)
+            i = inv[r]
+            a = res[i]
+            for k in range(Ap.indptr[i], Ap.indptr[i + 1]):
+                j = Ap.indices[k]
+                pj = perm[j]
+                if j != i and free[j] and pj < r and not (r0 <= pj < r1):
+                    a -= Ap.data[k] * out[j]
+            acc[r] = a
+        for s in range(d["tile_nlev"][t]):               # tile-local levels
+            for r in rows:
+                if d["row_lvl"][r] != s:
+                    continue
+                i = inv[r]
+                a = acc[r]
+                for k in range(Ap.indptr[i], Ap.indptr[i + 1]):
+                    j = Ap.indices[k]
+                    pj = perm[j]
+                    if j != i and free[j] and pj < r and r0 <= pj < r1:
+                        assert d["row_lvl"][pj] < s, "in-tile dependency on the same or a later local level"
+                        a -= Ap.data[k] * out[j]
+                out[i] = a / diag[i]
+                rout[i] = a - diag[i] * out[i]
+        done[t] = True
+    return out, rout
+
+
+@pytest.mark.parametrize("cfg", [dict(rounds=5, max_rows=32), dict(rounds=6, max_rows=64), dict(rounds=3, max_rows=32)])
+def test_tile_schedule_is_a_valid_sweep_order(cfg):
+    p = S.poisson3d_kuhn(13, 11, 9)
+    A = ng.SparseMatrix(p["n"], p["n"], 1, 1, p["rowptr"], p["col"], p["val"])
+    d = tile_schedule(A, p["free"], None, **cfg)
+    assert d["ok"] == 1 and d["violations"] == 0
+    assert d["nonfree_pad"] >= int((p["free"] == 0).sum()) and d["npad"] % 32 == 0
+    # the tile DAG is much shallower than the row DAG of the natural ordering (13 + 11 + 9 wavefronts)
+    if cfg["rounds"] >= 5:
+        assert d["tile_depth"] < 25
+    # emulated tile sweep == sequential sweep of the oracle (GSS3::SmoothRESInternal with x = 0)
+    As = to_oracle(A).to_scipy()
+    free = p["free"].astype(bool)
+    res = rand(3, p["n"]) * p["free"]
+    delta, rout = emulate_forward(As, free, d, res)
+    x = np.zeros(p["n"])
+    r2 = res.copy()
+    dinv = O.calc_dinv(to_oracle(A), p["free"])
+    O.gs_res(to_oracle(A), dinv, p["free"], x, r2, False)
+    assert rel(delta[free], x[free]) < 1e-13
+    # the oracle's residual holds res - A delta; ours only the (L + D) part: add the U part
+    U = sp.triu(As, 1).tocsr()
+    full = rout - U @ delta
+    assert rel(full[free], r2[free]) < 1e-12
+
+
+def test_tile_schedule_with_a_custom_sweep_order():
+    """non-natural sweep orders (multicolour option, hybrid stage order LOC_PART_1 | EX_PART | LOC_PART_2): still valid"""
+    p = S.poisson3d_kuhn(9, 9, 9)
+    A = ng.SparseMatrix(p["n"], p["n"], 1, 1, p["rowptr"], p["col"], p["val"])
+    rng = np.random.default_rng(5)
+    rank = rng.permutation(p["n"]).astype(np.int32)
+    d = tile_schedule(A, p["free"], rank)
+    assert d["ok"] == 1 and d["violations"] == 0
+    # stage-like order: second half of the rows first
+    n = p["n"]
+    rank2 = np.concatenate([np.arange(n // 2, n), np.arange(0, n // 2)]).astype(np.int32)
+    inv = np.zeros(n, np.int32)
+    inv[rank2] = np.arange(n, dtype=np.int32)
+    d2 = tile_schedule(A, p["free"], inv)
+    assert d2["ok"] == 1 and d2["violations"] == 0
+
+
+def test_tile_schedule_all_rows_smoothed_and_tiny():
+    p = S.poisson3d_kuhn(5, 4, 3, dirichlet=())
+    A = ng.SparseMatrix(p["n"], p["n"], 1, 1, p["rowptr"], p["col"], p["val"])
+    d = tile_schedule(A, None, None)
+    assert d["ok"] == 1 and d["violations"] == 0 and d["nonfree_pad"] == 0
+    assert sorted(d["perm"]) == sorted(set(d["perm"])) and d["perm"].max() < d["npad"]
