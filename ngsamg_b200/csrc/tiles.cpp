@@ -137,7 +137,7 @@ void build_tile_schedule(const HostBsr &A, const std::vector<uint8_t> &mask, con
     if (ext[a] == 0 && aptr[a + 1] > aptr[a]) full.emplace(rank_of(amem[aptr[a]]), (i32)a);
   for (i64 i = 0; i < n; i++)
     if (smoothed(i) && indeg[i] == 0) { heap.emplace(rank_of(i), (i32)i); ready[agg[i]].push_back((i32)i); }
-  const int min_fill = 24;          // a tile is closed once it holds at least this many rows and its cluster is exhausted
+  const int min_fill = 1;           // every emission closes its tile: sharing a tile between unrelated fragments would chain distant regions
   std::vector<i64> mptr{0};
   std::vector<i32> mem;
   mem.reserve(n);
