@@ -5,14 +5,24 @@
  * include, link or call this file; only tests/, __graft_entry__.smoke() and bench.py's
  * cpu_baseline / --impl reference legs use it, and there only as the checker / CPU baseline.
  *
- * PARITY UNPINNED: the reference (LukasKogler/NgsAMG) is an NGSolve add-on; NGSolve, netgen,
- * MPI, METIS and LAPACK are absent from this image, so neither the reference nor any of its
- * source files can be compiled here, and its tests hold no golden vectors (only CG iteration
- * ceilings).  This file therefore restates the algorithm from the reference sources, function
- * by function, and is cross-checked against scipy / pure-python loops (tests/test_oracle.py).
- * The arithmetic that lives in NGSolve (SparseMatrix::RowTimesVector, AddRowTransToVector,
- * MultAdd, CalcInverse, SparseCholesky, krylovspace.CGSolver; NGSolve is only lower-bounded,
- * `ngsolve>=6.2.2403.post68.dev0`, pyproject.toml:2) is restated from its published semantics.
+ * PARITY: PINNED IN PART.  The reference (LukasKogler/NgsAMG) is an NGSolve add-on; NGSolve, netgen,
+ * MPI, METIS and LAPACK are absent from this image, so the reference as a whole cannot be built
+ * or run here and its tests hold no golden vectors (only CG iteration ceilings).  What IS pinned:
+ * the bodies of the reference's own functions for the single-rank path -- TransposeSPMImpl,
+ * MatMultABImpl, RestrictMatrix, GSS3::SetUp/CalcDiags/SmoothRHSInternal/SmoothRESInternal/
+ * Smooth/SmoothBack, BaseSmoother::SmoothSymm/SmoothK/SmoothBackK/SmoothSymmK/CalcResiduum,
+ * ProxySmoother::Smooth/SmoothBack, ProlMap::TransferF2C/AddC2F, AMGMatrix::SmoothV/SmoothW/
+ * SmoothBS/SmoothVFromLevel -- are cut out of /root/reference at build time and compiled verbatim
+ * against a stand-in for the NGSolve containers (oracle/ref_pin/ -> oracle/_ref/libngsamg_ref.so);
+ * tests/test_ref_pin.py compares this file with that library bit for bit (patterns, values, sweeps,
+ * level vectors) and against fixtures it wrote (tests/golden/refpin_*.npz).
+ * STILL UNPINNED: the arithmetic that lives inside NGSolve and is therefore restated on both
+ * sides (SparseMatrix::RowTimesVector / AddRowTransToVector / MultAdd summation order, Mat*Vec
+ * evaluation order, CalcInverse, MergeArrays, SparseCholesky, krylovspace.CGSolver; NGSolve is only
+ * lower-bounded, `ngsolve>=6.2.2403.post68.dev0`, pyproject.toml:2), the pseudo-inverse
+ * (utils_denseLA.hpp, LAPACK), the Jacobi smoother, and the whole multi-rank path
+ * (oracle_par.py: hybrid smoother, DCC maps, contraction), which is cross-checked against the
+ * assembled global operator instead (tests/test_parallel_host.py).
  *
  * Citations are relative to /root/reference/.
  *
@@ -188,8 +198,11 @@ void orc_spmv_add(i64 n, int bh, int bw, const i64 *rp, const i32 *ci, const dou
     for (i64 k = rp[i]; k < rp[i + 1]; k++) {
       const double *blk = v + k * bh * bw;
       const double *xj = x + (i64)ci[k] * bw;
-      for (int r = 0; r < bh; r++)
-        for (int c = 0; c < bw; c++) acc[r] += blk[r * bw + c] * xj[c];
+      for (int r = 0; r < bh; r++) { /* sum += data[j] * x(col[j]): the block product is evaluated first, then added */
+        double t = blk[r * bw] * xj[0];
+        for (int c = 1; c < bw; c++) t += blk[r * bw + c] * xj[c];
+        acc[r] += t;
+      }
     }
     for (int r = 0; r < bh; r++) y[i * bh + r] += s * acc[r];
   }
@@ -381,8 +394,11 @@ static inline void gss3_row_rhs(const gss3 *g, i64 i, double *x, const double *r
   for (i64 k = g->rp[i]; k < g->rp[i + 1]; k++) {
     const double *blk = g->v + k * bb;
     const double *xj = x + (i64)g->ci[k] * b;
-    for (int p = 0; p < b; p++)
-      for (int q = 0; q < b; q++) r[p] += blk[p * b + q] * xj[q];
+    for (int p = 0; p < b; p++) { /* sum += A(row,col) * x(col): the block product is evaluated first, then added */
+      double t = blk[p * b] * xj[0];
+      for (int q = 1; q < b; q++) t += blk[p * b + q] * xj[q];
+      r[p] += t;
+    }
   }
   double d[ORC_MAXB];
   for (int p = 0; p < b; p++) d[p] = rhs[i * b + p] - r[p];

@@ -3,9 +3,12 @@
 TEST INFRASTRUCTURE ONLY -- imported by tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
 --impl reference legs.  The product package (ngsamg_b200/) never imports this module.
 
-PARITY UNPINNED (see the header of ngsamg_oracle.c): the reference cannot be compiled or run in this
-image and its tests carry no golden vectors; the oracle restates the reference sources and is
-cross-checked against scipy / pure-python loops in tests/test_oracle.py.
+PARITY PINNED IN PART (see the header of ngsamg_oracle.c): the reference as a whole cannot be built or run in
+this image and its tests carry no golden vectors, but the bodies of its functions for the single-rank path are
+compiled verbatim against a stand-in for the NGSolve containers (oracle/ref_pin/ -> oracle/_ref/) and this oracle
+agrees with them bit for bit (tests/test_ref_pin.py, tests/golden/refpin_*.npz).  The NGSolve-internal arithmetic,
+the pseudo-inverse, Jacobi, CG and the multi-rank path stay cross-checked only against scipy / pure-python loops /
+the assembled operator (tests/test_oracle.py, tests/test_parallel_host.py).
 """
 import ctypes as C
 import os

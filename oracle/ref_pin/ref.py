@@ -1,0 +1,194 @@
+"""ctypes front-end of oracle/_ref/libngsamg_ref.so: the reference's OWN hot-path functions (cut from /root/reference at
+build time, compiled verbatim against a stand-in for the NGSolve containers, see ref_harness.cpp / README.md).
+
+TEST INFRASTRUCTURE ONLY -- used by tests/test_ref_pin.py and tests/golden/make_ref_golden.py to pin the oracle.
+The library can only be BUILT where /root/reference exists; the built file travels with the repository snapshot.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+from oracle.oracle import Bsr
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_ORACLE = os.path.dirname(_HERE)
+_SO = os.path.join(_ORACLE, "_ref", "libngsamg_ref.so")
+REFERENCE = os.environ.get("NGSAMG_REFERENCE", "/root/reference")
+
+i64p = np.ctypeslib.ndpointer(np.int64, flags="C_CONTIGUOUS")
+i32p = np.ctypeslib.ndpointer(np.int32, flags="C_CONTIGUOUS")
+f64p = np.ctypeslib.ndpointer(np.float64, flags="C_CONTIGUOUS")
+
+
+def available():
+    """True if the library exists or can be built here (the reference tree is present)"""
+    return os.path.exists(_SO) or os.path.isdir(os.path.join(REFERENCE, "src", "base"))
+
+
+def build():
+    if os.path.isdir(os.path.join(REFERENCE, "src", "base")):
+        subprocess.check_call(["make", "-C", _ORACLE, "REFERENCE=" + REFERENCE, "_ref/libngsamg_ref.so"], stdout=subprocess.DEVNULL)
+    if not os.path.exists(_SO):
+        raise RuntimeError("oracle/_ref/libngsamg_ref.so is missing and %s is not present to build it from" % REFERENCE)
+    return _SO
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is not None:
+        return _lib
+    build()
+    L = C.CDLL(_SO)
+    vp, i64, ci = C.c_void_p, C.c_int64, C.c_int
+    L.ref_last_error.restype = C.c_char_p
+    L.ref_fragment_index.restype = C.c_char_p
+    L.ref_mat_new.argtypes = [i64, i64, ci, ci, i64p, i32p, f64p]
+    L.ref_mat_new.restype = vp
+    L.ref_mat_free.argtypes = [vp]
+    L.ref_mat_info.argtypes = [vp] + [C.POINTER(i64)] * 2 + [C.POINTER(ci)] * 2 + [C.POINTER(i64)]
+    L.ref_mat_fetch.argtypes = [vp, i64p, i32p, f64p]
+    L.ref_mat_transpose.argtypes = [vp]
+    L.ref_mat_transpose.restype = vp
+    L.ref_mat_mult.argtypes = [vp, vp]
+    L.ref_mat_mult.restype = vp
+    L.ref_mat_restrict.argtypes = [vp, vp, vp]
+    L.ref_mat_restrict.restype = vp
+    L.ref_amg_new.argtypes = [ci]
+    L.ref_amg_new.restype = vp
+    L.ref_amg_free.argtypes = [vp]
+    L.ref_amg_set_matrix.argtypes = [vp, i64, ci, i64p, i32p, f64p, vp]
+    L.ref_amg_set_prol.argtypes = [vp, ci, i64, ci, i64p, i32p, f64p]
+    L.ref_amg_finalize.argtypes = [vp, ci, ci, vp]
+    L.ref_amg_level_matrix.argtypes = [vp, ci]
+    L.ref_amg_level_matrix.restype = vp
+    L.ref_amg_level_pt.argtypes = [vp, ci]
+    L.ref_amg_level_pt.restype = vp
+    L.ref_amg_level_dinv.argtypes = [vp, ci, f64p]
+    L.ref_amg_level_vec.argtypes = [vp, ci, ci, f64p]
+    L.ref_amg_smooth.argtypes = [vp, ci, f64p, f64p, f64p, ci, ci, ci, ci, ci]
+    L.ref_amg_apply.argtypes = [vp, ci, f64p, f64p]
+    _lib = L
+    return L
+
+
+def fragment_index():
+    """the reference file:line ranges the library was built from"""
+    return lib().ref_fragment_index().decode()
+
+
+def _check(rc):
+    if rc:
+        raise RuntimeError("reference: " + lib().ref_last_error().decode())
+
+
+def _ptr(h):
+    if not h:
+        raise RuntimeError("reference: " + lib().ref_last_error().decode())
+    return h
+
+
+class RefMat:
+    """a SparseMatrix<Mat<bh,bw>> living in the reference library"""
+
+    def __init__(self, handle, owned=True):
+        self.h, self.owned = _ptr(handle), owned
+
+    @staticmethod
+    def from_bsr(M):
+        return RefMat(lib().ref_mat_new(M.nrows, M.ncols, M.bh, M.bw, M.rowptr, M.col if M.nnz else np.zeros(1, np.int32),
+                                        M.val if M.nnz else np.zeros(1, np.float64)))
+
+    def __del__(self):
+        try:
+            if self.owned:
+                lib().ref_mat_free(self.h)
+        except Exception:
+            pass
+
+    def to_bsr(self):
+        nr, nc, nnz, bh, bw = C.c_int64(), C.c_int64(), C.c_int64(), C.c_int(), C.c_int()
+        _check(lib().ref_mat_info(self.h, C.byref(nr), C.byref(nc), C.byref(bh), C.byref(bw), C.byref(nnz)))
+        rp = np.zeros(nr.value + 1, np.int64)
+        ci = np.zeros(max(nnz.value, 1), np.int32)
+        v = np.zeros(max(nnz.value, 1) * bh.value * bw.value, np.float64)
+        _check(lib().ref_mat_fetch(self.h, rp, ci, v))
+        return Bsr(nr.value, nc.value, bh.value, bw.value, rp, ci[:nnz.value], v[:nnz.value * bh.value * bw.value])
+
+
+def transpose(A):
+    """TransposeSPMImpl (utils_sparseMM.cpp:54-93)"""
+    a = RefMat.from_bsr(A)
+    return RefMat(lib().ref_mat_transpose(a.h)).to_bsr()
+
+
+def matmul(A, B):
+    """MatMultABImpl (utils_sparseMM.cpp:107-238)"""
+    a, b = RefMat.from_bsr(A), RefMat.from_bsr(B)
+    return RefMat(lib().ref_mat_mult(a.h, b.h)).to_bsr()
+
+
+def restrict_matrix(PT, A, P):
+    """RestrictMatrix (utils_sparseMM.hpp:93-109)"""
+    pt, a, p = RefMat.from_bsr(PT), RefMat.from_bsr(A), RefMat.from_bsr(P)
+    return RefMat(lib().ref_mat_restrict(pt.h, a.h, p.h)).to_bsr()
+
+
+class RefAMG:
+    """AMGMatrix of the reference: coarse matrices by TransposeSPMImpl + RestrictMatrix from injected prolongations, GSS3 per
+    level (ProxySmoother around it for sm_steps > 1 / sm_symm), cycles by AMGMatrix::SmoothV / SmoothW / SmoothBS.  The exact
+    coarse solve is a dense inverse handed in by the caller (the reference calls NGSolve's sparse Cholesky here)."""
+
+    def __init__(self, A, free, prols, sm_steps=1, sm_symm=False, coarse_inv=True):
+        L = lib()
+        self.nlevels = len(prols) + 1
+        self.h = _ptr(L.ref_amg_new(self.nlevels))
+        fm = None if free is None else np.ascontiguousarray(free, np.uint8)
+        _check(L.ref_amg_set_matrix(self.h, A.nrows, A.bh, A.rowptr, A.col, A.val, None if fm is None else fm.ctypes.data_as(C.c_void_p)))
+        self.bs = [A.bh]
+        for l, P in enumerate(prols):
+            _check(L.ref_amg_set_prol(self.h, l, P.ncols, P.bw, P.rowptr, P.col, P.val))
+            self.bs.append(P.bw)
+        cinv = None
+        if coarse_inv:
+            Ac = self.level_matrix(self.nlevels - 1).to_scipy().toarray()
+            cinv = np.ascontiguousarray(np.linalg.inv(Ac))
+        _check(L.ref_amg_finalize(self.h, int(sm_steps), int(bool(sm_symm)), None if cinv is None else cinv.ctypes.data_as(C.c_void_p)))
+        self.n0 = A.nrows * A.bh
+
+    def __del__(self):
+        try:
+            lib().ref_amg_free(self.h)
+        except Exception:
+            pass
+
+    def level_matrix(self, l):
+        return RefMat(lib().ref_amg_level_matrix(self.h, l), owned=False).to_bsr()
+
+    def level_pt(self, l):
+        return RefMat(lib().ref_amg_level_pt(self.h, l), owned=False).to_bsr()
+
+    def level_dinv(self, l):
+        A = self.level_matrix(l)
+        out = np.zeros(A.nrows * A.bh * A.bh)
+        _check(lib().ref_amg_level_dinv(self.h, l, out))
+        return out
+
+    def level_vec(self, which, l):
+        A = self.level_matrix(l)
+        out = np.zeros(A.nrows * A.bh)
+        _check(lib().ref_amg_level_vec(self.h, {"x": 0, "rhs": 1, "res": 2}[which], l, out))
+        return out
+
+    def smooth(self, l, x, b, res, res_updated=False, update_res=True, x_zero=False, backwards=False, bare=False):
+        _check(lib().ref_amg_smooth(self.h, l, x, np.ascontiguousarray(b, np.float64), res, int(res_updated), int(update_res),
+                                    int(x_zero), int(backwards), int(bare)))
+
+    def apply(self, b, cycle="V"):
+        x = np.zeros(self.n0)
+        _check(lib().ref_amg_apply(self.h, {"V": 0, "W": 1, "BS": 2}[cycle], np.ascontiguousarray(b, np.float64), x))
+        return x

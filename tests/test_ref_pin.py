@@ -1,0 +1,248 @@
+"""Pins the oracle (oracle/ngsamg_oracle.c) against the REFERENCE'S OWN CODE for the hot path (`-m "not gpu"`).
+
+oracle/_ref/libngsamg_ref.so holds the bodies of TransposeSPMImpl, MatMultABImpl, RestrictMatrix, GSS3::*, BaseSmoother /
+ProxySmoother, ProlMap transfers and AMGMatrix::SmoothV/W/BS cut out of /root/reference at build time and compiled verbatim
+against a stand-in for the NGSolve containers they call (oracle/ref_pin/README.md says exactly what that covers).
+ * live tests: oracle vs that library on seeded inputs -- bit for bit for the integer patterns and for every floating-point
+   result that does not pass through the exact coarse solve (the reference uses NGSolve's sparse Cholesky there, the harness a
+   dense inverse: <= 1e-13 after it).  Skipped where the library is neither present nor buildable.
+ * fixture test: the same comparisons against tests/golden/refpin_*.npz, which tests/golden/make_ref_golden.py wrote from
+   that library -- runs on any machine.
+"""
+import os
+
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+from helpers import poisson, elasticity, rand, rel, to_oracle, host_hierarchy
+from oracle import oracle as O
+from oracle.ref_pin import ref as R
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+needs_ref = pytest.mark.skipif(not R.available(), reason="oracle/_ref/libngsamg_ref.so not built and /root/reference not present")
+FLAGS = [(ru, ur, xz, bw) for ru in (0, 1) for ur in (0, 1) for xz in (0, 1) for bw in (0, 1)]
+
+
+def random_bsr(seed, n, m, bh, bw, density=0.2):
+    rng = np.random.default_rng(seed)
+    pat = sp.random(n, m, density=density, random_state=rng, format="csr")
+    pat.sort_indices()
+    return O.Bsr(n, m, bh, bw, pat.indptr, pat.indices, rng.standard_normal((pat.nnz, bh, bw)))
+
+
+def same(M1, M2):
+    assert (M1.nrows, M1.ncols, M1.bh, M1.bw) == (M2.nrows, M2.ncols, M2.bh, M2.bw)
+    assert np.array_equal(M1.rowptr, M2.rowptr) and np.array_equal(M1.col, M2.col), "patterns differ"
+    assert np.array_equal(M1.val, M2.val), "values differ (max %.3e)" % np.abs(M1.val - M2.val).max()
+
+
+@needs_ref
+def test_library_is_built_from_the_reference_sources():
+    idx = R.fragment_index()
+    for name, where in [("transpose", "utils_sparseMM.cpp"), ("matmult", "utils_sparseMM.cpp"), ("restrict", "utils_sparseMM.hpp"),
+                        ("gss3_rhs", "gssmoother.cpp"), ("gss3_res", "gssmoother.cpp"), ("gss3_calcdiags", "gssmoother.cpp"),
+                        ("proxy_smooth", "base_smoother.hpp"), ("prol_f2c", "dof_map.cpp"), ("prol_addc2f", "dof_map.cpp"),
+                        ("amg_smoothv", "amg_matrix.cpp"), ("amg_smoothw", "amg_matrix.cpp"), ("amg_smoothbs", "amg_matrix.cpp")]:
+        line = [ln for ln in idx.splitlines() if ln.split()[0] == name]
+        assert line and where in line[0], (name, idx)
+    # the cut-out text never enters the repository
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    assert "oracle/_ref/" in open(os.path.join(root, ".gitignore")).read().split()
+
+
+@needs_ref
+@pytest.mark.parametrize("bh,bw", [(1, 1), (2, 3), (3, 2), (3, 3), (3, 6), (6, 3), (6, 6)])
+def test_transpose_bit_exact(bh, bw):
+    for seed, n, m, dens in [(1, 17, 11, 0.2), (2, 40, 3, 0.5), (3, 5, 60, 0.05)]:   # incl. empty rows and columns
+        A = random_bsr(seed, n, m, bh, bw, dens)
+        same(O.transpose(A), R.transpose(A))
+
+
+@needs_ref
+@pytest.mark.parametrize("a,b,c", [(1, 1, 1), (2, 2, 3), (3, 2, 3), (3, 3, 3), (3, 3, 6), (6, 3, 3), (6, 3, 6), (3, 6, 6), (6, 6, 3), (6, 6, 6)])
+def test_matmult_bit_exact(a, b, c):
+    A, B = random_bsr(2, 23, 19, a, b), random_bsr(3, 19, 13, b, c)
+    same(O.matmul(A, B), R.matmul(A, B))
+    A, B = random_bsr(4, 9, 30, a, b, 0.7), random_bsr(5, 30, 21, b, c, 0.02)     # > 16 merged lists, many empty rows of B
+    same(O.matmul(A, B), R.matmul(A, B))
+
+
+@needs_ref
+def test_matmult_hash_collisions_take_the_search_branch():
+    """product rows that hold columns c and c + 2048 (same slot of the 2048-entry hash, utils_sparseMM.cpp:183-216)"""
+    rng = np.random.default_rng(7)
+    n, k, m = 12, 40, 9000
+    A = random_bsr(8, n, k, 1, 1, 0.6)
+    rows, cols = [], []
+    for r in range(k):
+        base = rng.choice(2048, size=6, replace=False)
+        cs = np.unique(np.concatenate([base, base[:4] + 2048, base[:2] + 4096]))
+        rows += [r] * len(cs)
+        cols += list(cs)
+    pat = sp.csr_matrix((np.ones(len(rows)), (rows, cols)), shape=(k, m))
+    pat.sort_indices()
+    B = O.Bsr(k, m, 1, 1, pat.indptr, pat.indices, rng.standard_normal(pat.nnz))
+    Co, Cr = O.matmul(A, B), R.matmul(A, B)
+    row_cols = Cr.col[Cr.rowptr[0]:Cr.rowptr[1]]
+    assert len(set(row_cols % 2048)) < len(row_cols)          # there ARE collisions in the row
+    same(Co, Cr)
+    assert np.abs(Cr.to_scipy() - A.to_scipy() @ B.to_scipy()).max() < 1e-12
+
+
+@needs_ref
+def test_matmult_rows_wider_than_the_hash():
+    """a product row with more than 1024 entries makes the reference grow its hash (utils_sparseMM.cpp:187-188)"""
+    A = random_bsr(9, 6, 50, 1, 1, 0.9)
+    B = random_bsr(10, 50, 3000, 1, 1, 0.05)
+    Co, Cr = O.matmul(A, B), R.matmul(A, B)
+    assert np.diff(Cr.rowptr).max() > 1024
+    same(Co, Cr)
+
+
+@needs_ref
+@pytest.mark.parametrize("h,w", [(1, 1), (3, 3), (3, 6), (6, 6), (2, 3)])
+def test_restrict_matrix_bit_exact(h, w):
+    A = random_bsr(11, 30, 30, h, h, 0.15)
+    P = random_bsr(12, 30, 8, h, w, 0.12)
+    PT = O.transpose(P)
+    same(O.restrict_matrix(PT, A, P), R.restrict_matrix(PT, A, P))
+
+
+def hierarchy(kind):
+    if kind == "poisson":
+        p, A = poisson(9)
+        prols = host_hierarchy(A, p["free"], max_coarse=30)
+    else:
+        p, A = elasticity(5, 4, 4)
+        prols = host_hierarchy(A, p["free"], p["xyz"], elast=True, max_coarse=4, max_per_row=4)
+    return p, to_oracle(A), [to_oracle(P) for P in prols]
+
+
+def check_hierarchy(oa, get_mat, get_dinv, nlevels):
+    for l in range(nlevels):
+        same(oa.level_matrix(l), get_mat(l))
+        if l + 1 < nlevels:
+            assert np.array_equal(oa.level_dinv(l), get_dinv(l)), "dinv differs on level %d" % l
+
+
+@needs_ref
+@pytest.mark.parametrize("kind", ["poisson", "elasticity"])
+def test_galerkin_hierarchy_and_diagonal_inverses_bit_exact(kind):
+    p, A, prols = hierarchy(kind)
+    oa, ra = O.OracleAMG(A, p["free"], prols), R.RefAMG(A, p["free"], prols)
+    assert oa.nlevels == ra.nlevels >= 3
+    check_hierarchy(oa, ra.level_matrix, ra.level_dinv, oa.nlevels)
+
+
+def sweep_inputs(A, ru, xz):
+    nb = A.nrows * A.bh
+    x0, b0 = rand(11, nb), rand(12, nb)
+    x = np.zeros(nb) if xz else x0.copy()
+    res = (b0.copy() if xz else b0 - A.to_scipy() @ x0) if ru else rand(13, nb)
+    return x, b0, res
+
+
+@needs_ref
+@pytest.mark.parametrize("kind", ["poisson", "elasticity"])
+@pytest.mark.parametrize("freemask", ["given", "all", "none_set", "null"])
+def test_gss3_sweeps_bit_exact_for_all_protocol_flags(kind, freemask):
+    """GSS3::Smooth / SmoothBack -> SmoothRESInternal / SmoothRHSInternal (gssmoother.cpp:195-398) incl. first_free / next_free"""
+    p, A, prols = hierarchy(kind)
+    free = {"given": p["free"], "all": np.ones(A.nrows, np.uint8), "none_set": np.zeros(A.nrows, np.uint8), "null": None}[freemask]
+    if freemask == "given":
+        free = np.array(free, np.uint8)
+        free[:3] = 0            # first_free > 0
+        free[-5:] = 0           # next_free < n
+    oa, ra = O.OracleAMG(A, free, prols[:1], clev="none"), R.RefAMG(A, free, prols[:1], coarse_inv=False)
+    for ru, ur, xz, bw in FLAGS:
+        x1, b, r1 = sweep_inputs(A, ru, xz)
+        x2, r2 = x1.copy(), r1.copy()
+        oa.smooth(0, x1, b, r1, ru, ur, xz, bw)
+        ra.smooth(0, x2, b, r2, ru, ur, xz, bw, bare=True)
+        assert np.array_equal(x1, x2), (ru, ur, xz, bw, rel(x1, x2))
+        if ur:
+            assert np.array_equal(r1, r2), (ru, ur, xz, bw, rel(r1, r2))
+
+
+@needs_ref
+@pytest.mark.parametrize("steps,symm", [(1, True), (2, False), (3, True)])
+def test_proxy_smoother_bit_exact(steps, symm):
+    p, A, prols = hierarchy("poisson")
+    oa = O.OracleAMG(A, p["free"], prols[:1], sm_steps=steps, sm_symm=symm, clev="none")
+    ra = R.RefAMG(A, p["free"], prols[:1], sm_steps=steps, sm_symm=symm, coarse_inv=False)
+    for ru, ur, xz, bw in FLAGS:
+        x1, b, r1 = sweep_inputs(A, ru, xz)
+        x2, r2 = x1.copy(), r1.copy()
+        oa.smooth(0, x1, b, r1, ru, ur, xz, bw)
+        ra.smooth(0, x2, b, r2, ru, ur, xz, bw)
+        assert np.array_equal(x1, x2), (ru, ur, xz, bw, rel(x1, x2))
+        if ur:
+            assert np.array_equal(r1, r2), (ru, ur, xz, bw)
+
+
+def check_cycles(oa, apply_ref, level_vec_ref, b, nlevels):
+    x = oa.apply(b, "V")
+    # everything before the exact coarse solve is bit-identical ...
+    assert np.array_equal(oa.level_vec("res", 0), level_vec_ref("res", 0))
+    for l in range(1, nlevels):
+        assert np.array_equal(oa.level_vec("rhs", l), level_vec_ref("rhs", l)), "rhs on level %d" % l
+        if l + 1 < nlevels:
+            assert np.array_equal(oa.level_vec("res", l), level_vec_ref("res", l)), "res on level %d" % l
+    # ... after it the two coarse solvers (Cholesky here, dense inverse there) differ in the last bits
+    for l in range(1, nlevels):
+        assert rel(oa.level_vec("x", l), level_vec_ref("x", l)) < 1e-13
+    assert rel(x, apply_ref("V")) < 1e-13
+    assert rel(oa.apply(b, "W"), apply_ref("W")) < 1e-13
+    assert rel(oa.apply(b, "BS"), apply_ref("BS")) < 1e-13
+
+
+@needs_ref
+@pytest.mark.parametrize("kind,steps,symm", [("poisson", 1, False), ("poisson", 2, True), ("elasticity", 1, False)])
+def test_v_w_bs_cycles_against_the_reference_code(kind, steps, symm):
+    """AMGMatrix::SmoothV / SmoothW / SmoothBS / SmoothVFromLevel (amg_matrix.cpp:37-374) with ProlMap transfers"""
+    p, A, prols = hierarchy(kind)
+    oa = O.OracleAMG(A, p["free"], prols, sm_steps=steps, sm_symm=symm)
+    ra = R.RefAMG(A, p["free"], prols, sm_steps=steps, sm_symm=symm)
+    b = rand(14, A.nrows * A.bh)
+    xs = {c: ra.apply(b, c) for c in ("W", "BS", "V")}          # V last: the level vectors read below are the V-cycle's
+    check_cycles(oa, lambda c: xs[c], ra.level_vec, b, oa.nlevels)
+
+
+@needs_ref
+def test_cycles_without_coarse_inverse_are_bit_exact():
+    """clev = none: no dense solve anywhere, so the whole cycle must agree bit for bit"""
+    p, A, prols = hierarchy("poisson")
+    oa, ra = O.OracleAMG(A, p["free"], prols, clev="none"), R.RefAMG(A, p["free"], prols, coarse_inv=False)
+    b = rand(15, A.nrows)
+    for cyc in ("V", "W", "BS"):
+        assert np.array_equal(oa.apply(b, cyc), ra.apply(b, cyc)), cyc
+
+
+# ---- the same pins against the fixtures the reference library wrote (no library needed) --------------------------------
+def unpack(g, prefix):
+    nr, nc, bh, bw = (int(v) for v in g[prefix + "_shape"])
+    return O.Bsr(nr, nc, bh, bw, g[prefix + "_rowptr"], g[prefix + "_col"], g[prefix + "_val"])
+
+
+@pytest.mark.parametrize("name", ["refpin_poisson_n7", "refpin_poisson_n7_symm2", "refpin_elast_5x3x3"])
+def test_oracle_against_reference_made_fixtures(name):
+    g = np.load(os.path.join(GOLD, name + ".npz"))
+    nlev = int(g["nlevels"])
+    assert "amg_matrix.cpp" in str(g["fragments"]) and "gssmoother.cpp" in str(g["fragments"])
+    A, free = unpack(g, "A0"), g["free"]
+    prols = [unpack(g, "P%d" % l) for l in range(nlev - 1)]
+    for l, P in enumerate(prols):
+        same(O.transpose(P), unpack(g, "PT%d" % l))
+    oa = O.OracleAMG(A, free, prols, sm_steps=int(g["sm_steps"]), sm_symm=bool(g["sm_symm"]))
+    check_hierarchy(oa, lambda l: unpack(g, "A%d" % l), lambda l: g["dinv%d" % l], nlev)
+    bare = O.OracleAMG(A, free, prols[:1], clev="none")
+    for ru, ur, xz, bw in FLAGS:
+        x = np.zeros_like(g["sm_x_in"]) if xz else g["sm_x_in"].copy()
+        res = (g["sm_b"].copy() if xz else g["sm_res_in_true"].copy()) if ru else g["sm_res_in_junk"].copy()
+        bare.smooth(0, x, g["sm_b"], res, ru, ur, xz, bw)
+        key = "%d%d%d%d" % (ru, ur, xz, bw)
+        assert np.array_equal(x, g["sm_x_" + key]), key
+        if ur:
+            assert np.array_equal(res, g["sm_res_" + key]), key
+    check_cycles(oa, lambda c: g["x_" + c], lambda w, l: g["V_%s%d" % (w, l)], g["b"], nlev)
