@@ -7,7 +7,7 @@ the individual functions of the path, against a small stand-in for the NGSolve c
 (oracle/ref_pin/ngs_standin.hpp, written for this repository).  This script locates each function in the tree under
 /root/reference by an anchor pattern, cuts it out with a brace matcher that understands comments and literals, and
 writes it to oracle/_ref/frag/<name>.inc.  Nothing of the reference is stored in this repository: oracle/_ref/ is
-git-ignored, the fragments exist only next to the library built from them.
+git-ignored, and oracle/Makefile deletes the fragments again once the library is compiled.
 
 usage: extract_ref.py <reference root> <output dir>
 """
