@@ -2,7 +2,7 @@
 """bench.py -- PCG+AMG solve throughput and V-cycle HBM bandwidth on B200 (BASELINE.json metric).
 
   python bench.py --gpus N --steps K --warmup W            # our CUDA path, one rank per GPU
-  python bench.py --impl reference --gpus N --steps K ...  # CPU arm: the oracle port of the reference algorithm
+  python bench.py --impl reference --gpus N --steps K ...  # CPU arm: the reference's own functions (oracle/_ref), else the oracle port
 
 A "step" is one complete PCG+AMG solve (tol 1e-8, V(1,1)-cycle preconditioner) of the synthetic 3D Poisson P1 problem
 (Kuhn tets on the unit cube, Dirichlet on x=0 and y=1, f=1).  N=1 workload = BASELINE.json configs[1]: 311^3 = 30.1 M DOFs.
@@ -109,24 +109,40 @@ def make_problem(n, problem="poisson"):
 
 
 def cpu_reference_run(n, steps, warmup, tol=TOL):
-    """the oracle (CPU port of the reference algorithm, single thread like one MPI rank of the reference)"""
+    """the CPU arm, single thread like one MPI rank of the reference.
+    kind "reference": oracle/_ref/libngsamg_ref.so -- the reference's OWN code for the path (RestrictMatrix / MatMultABImpl /
+    TransposeSPMImpl for the Galerkin products, GSS3 sweeps, ProlMap transfers, AMGMatrix::SmoothV; cut out of the reference at build
+    time and compiled against a stand-in for the NGSolve containers, oracle/ref_pin/README.md) under a CG loop; used whenever that
+    library is present.  kind "port": the oracle's C restatement of the same functions (bit-identical results, tests/test_ref_pin.py).
+    The hierarchy (prolongations) comes from the product's host-side coarsening in both cases."""
     import ngsamg_b200 as ng
     from oracle import oracle as O
+    from oracle.ref_pin import ref as R
     O.build()
+    kind = "port"
+    if R.available():
+        try:
+            R.lib()
+            kind = "reference"
+        except Exception as e:            # no compiler / stale tree: fall back to the port, say so
+            sys.stderr.write("[bench] oracle/_ref unusable (%s): CPU arm runs the oracle port\n" % e)
     p, A = make_problem(n)
+    to_o = lambda M: O.Bsr(M.nrows, M.ncols, M.bh, M.bw, M.rowptr, M.col, M.val)
     t0 = time.time()
-    # hierarchy: the product's host-side coarsening, Galerkin products by the oracle
     prols, cur, fm = [], A, p["free"]
+    amg = R.RefAMG(to_o(A), p["free"]) if kind == "reference" else None
     while cur.nrows > 50 and len(prols) + 1 < 10:
         P, _, _ = ng.coarsen(cur, fm)
         if P.ncols == 0 or P.ncols > 0.8 * cur.nrows:
             break
         prols.append(P)
-        Po = O.Bsr(P.nrows, P.ncols, 1, 1, P.rowptr, P.col, P.val)
-        Ac = O.restrict_matrix(O.transpose(Po), O.Bsr(cur.nrows, cur.ncols, 1, 1, cur.rowptr, cur.col, cur.val), Po)
+        Po = to_o(P)
+        Ac = amg.add_prol(Po) if kind == "reference" else O.restrict_matrix(O.transpose(Po), to_o(cur), Po)
         cur, fm = ng.SparseMatrix(Ac.nrows, Ac.ncols, 1, 1, Ac.rowptr, Ac.col, Ac.val), None
-    amg = O.OracleAMG(O.Bsr(A.nrows, A.ncols, 1, 1, A.rowptr, A.col, A.val), p["free"],
-                      [O.Bsr(P.nrows, P.ncols, 1, 1, P.rowptr, P.col, P.val) for P in prols])
+    if kind == "reference":
+        amg.finalize()
+    else:
+        amg = O.OracleAMG(to_o(A), p["free"], [to_o(P) for P in prols])
     setup_s = time.time() - t0
     for _ in range(warmup):
         amg.apply(p["rhs"])
@@ -140,7 +156,12 @@ def cpu_reference_run(n, steps, warmup, tol=TOL):
         amg.apply(p["rhs"])
     vcycle_s = (time.time() - tv) / 3
     return dict(ndof=p["n"], solve_s=float(np.mean(times)), iterations=int(its), setup_s=setup_s, vcycle_s=vcycle_s,
-                levels=amg.nlevels)
+                levels=amg.nlevels, kind=kind)
+
+
+CPU_KIND_TEXT = {"reference": "the reference's own functions (oracle/_ref: RestrictMatrix, GSS3, ProlMap, AMGMatrix::SmoothV compiled against "
+                              "an NGSolve container stand-in) under a CG loop",
+                 "port": "the oracle port of the reference algorithm (oracle/_ref not present)"}
 
 
 def cpu_reference_run_parallel(n, world, steps, warmup, tol=TOL):
@@ -210,9 +231,9 @@ def run_reference(args):
         "config": {"workload": "3D Poisson P1 unit cube (Kuhn tets), h1_scal + CG to 1e-8; CPU sample %d^3 = %d DOFs of the "
                                "%d^3 workload" % (n, r["ndof"], args.n), "tol": TOL, "levels": r["levels"]},
         "solve_s": r["solve_s"], "iterations": r["iterations"], "vcycle_ms": r["vcycle_s"] * 1e3,
-        "cpu_baseline": {"value": val, "unit": "DOF/s", "cores": 1, "kind": "port",
-                         "sample": "oracle PCG+AMG solve, %d^3 = %d DOFs, 1 thread (the reference cannot be built here: needs "
-                                   "NGSolve/MPI)" % (n, r["ndof"])},
+        "cpu_baseline": {"value": val, "unit": "DOF/s", "cores": 1, "kind": r["kind"],
+                         "sample": "PCG+AMG solve by %s, %d^3 = %d DOFs, 1 thread (the reference as a whole needs NGSolve/MPI and cannot be "
+                                   "built here)" % (CPU_KIND_TEXT[r["kind"]], n, r["ndof"])},
         "e2e": {"value": val, "unit": "DOF/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
@@ -449,9 +470,9 @@ def main():
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         r = cpu_reference_run(args.cpu_n, 1, 0)
-        cpu = {"value": r["ndof"] / r["solve_s"], "unit": "DOF/s", "cores": 1, "kind": "port",
-               "sample": "oracle PCG+AMG solve of the same problem at %d^3 = %d DOFs (1 thread, %d its, %.2f s; V-cycle %.1f ms)"
-                         % (args.cpu_n, r["ndof"], r["iterations"], r["solve_s"], r["vcycle_s"] * 1e3)}
+        cpu = {"value": r["ndof"] / r["solve_s"], "unit": "DOF/s", "cores": 1, "kind": r["kind"],
+               "sample": "PCG+AMG solve of the same problem at %d^3 = %d DOFs by %s (1 thread, %d its, %.2f s; V-cycle %.1f ms)"
+                         % (args.cpu_n, r["ndof"], CPU_KIND_TEXT[r["kind"]], r["iterations"], r["solve_s"], r["vcycle_s"] * 1e3)}
 
     if rank == 0:
         line = {

@@ -72,6 +72,7 @@ def lib():
     L.ref_amg_level_vec.argtypes = [vp, ci, ci, f64p]
     L.ref_amg_smooth.argtypes = [vp, ci, f64p, f64p, f64p, ci, ci, ci, ci, ci]
     L.ref_amg_apply.argtypes = [vp, ci, f64p, f64p]
+    L.ref_amg_pcg.argtypes = [vp, ci, f64p, f64p, C.c_double, ci, f64p, C.POINTER(ci)]
     _lib = L
     return L
 
@@ -143,22 +144,34 @@ class RefAMG:
     level (ProxySmoother around it for sm_steps > 1 / sm_symm), cycles by AMGMatrix::SmoothV / SmoothW / SmoothBS.  The exact
     coarse solve is a dense inverse handed in by the caller (the reference calls NGSolve's sparse Cholesky here)."""
 
-    def __init__(self, A, free, prols, sm_steps=1, sm_symm=False, coarse_inv=True):
+    def __init__(self, A, free, prols=None, sm_steps=1, sm_symm=False, coarse_inv=True, max_levels=32):
+        """with prols: the whole hierarchy at once.  prols=None: level by level -- add_prol(P) returns the Galerkin matrix the
+        reference's RestrictMatrix produced (input of the next coarsening step), finalize() ends the set-up."""
         L = lib()
-        self.nlevels = len(prols) + 1
-        self.h = _ptr(L.ref_amg_new(self.nlevels))
+        self.nlevels = 1
+        self.h = _ptr(L.ref_amg_new(max_levels if prols is None else len(prols) + 1))
         fm = None if free is None else np.ascontiguousarray(free, np.uint8)
         _check(L.ref_amg_set_matrix(self.h, A.nrows, A.bh, A.rowptr, A.col, A.val, None if fm is None else fm.ctypes.data_as(C.c_void_p)))
-        self.bs = [A.bh]
-        for l, P in enumerate(prols):
-            _check(L.ref_amg_set_prol(self.h, l, P.ncols, P.bw, P.rowptr, P.col, P.val))
-            self.bs.append(P.bw)
+        self.n0 = A.nrows * A.bh
+        self._opts = (int(sm_steps), int(bool(sm_symm)), bool(coarse_inv))
+        if prols is not None:
+            for P in prols:
+                self.add_prol(P, fetch=False)
+            self.finalize()
+
+    def add_prol(self, P, fetch=True):
+        """prolongation of the current coarsest level: TransposeSPMImpl + RestrictMatrix build the next level matrix"""
+        _check(lib().ref_amg_set_prol(self.h, self.nlevels - 1, P.ncols, P.bw, P.rowptr, P.col, P.val))
+        self.nlevels += 1
+        return self.level_matrix(self.nlevels - 1) if fetch else None
+
+    def finalize(self):
+        sm_steps, sm_symm, coarse_inv = self._opts
         cinv = None
         if coarse_inv:
             Ac = self.level_matrix(self.nlevels - 1).to_scipy().toarray()
             cinv = np.ascontiguousarray(np.linalg.inv(Ac))
-        _check(L.ref_amg_finalize(self.h, int(sm_steps), int(bool(sm_symm)), None if cinv is None else cinv.ctypes.data_as(C.c_void_p)))
-        self.n0 = A.nrows * A.bh
+        _check(lib().ref_amg_finalize(self.h, sm_steps, sm_symm, None if cinv is None else cinv.ctypes.data_as(C.c_void_p)))
 
     def __del__(self):
         try:
@@ -192,3 +205,10 @@ class RefAMG:
         x = np.zeros(self.n0)
         _check(lib().ref_amg_apply(self.h, {"V": 0, "W": 1, "BS": 2}[cycle], np.ascontiguousarray(b, np.float64), x))
         return x
+
+    def pcg(self, rhs, tol=1e-8, maxsteps=200, cycle="V"):
+        """CG (harness glue, NGSolve's CGSolver restated like the oracle's) preconditioned with the reference's cycle"""
+        u, errs, it = np.zeros(self.n0), np.zeros(maxsteps + 2), C.c_int(0)
+        _check(lib().ref_amg_pcg(self.h, {"V": 0, "W": 1, "BS": 2}[cycle], np.ascontiguousarray(rhs, np.float64), u, float(tol),
+                                 int(maxsteps), errs, C.byref(it)))
+        return u, it.value, errs[: it.value + 1].copy()

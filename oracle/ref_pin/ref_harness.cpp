@@ -377,11 +377,12 @@ void *ref_mat_restrict(const void *ptv, const void *av, const void *pv) {
 
 // ---- hierarchy: level matrices by the reference's RAP, GSS3 (+ProxySmoother) per level, cycles by AMGMatrix ------------
 void *ref_amg_new(int nlevels) {
+  // nlevels is an upper bound: the hierarchy ends with the last level ref_amg_set_prol produced
   AmgH *a = new AmgH;
-  a->nlevels = nlevels;
+  a->nlevels = 1;
   a->lev.resize(nlevels);
   a->amg.map = make_shared<DOFMap>();
-  a->amg.n_levels = nlevels;
+  a->amg.n_levels = 1;
   return a;
 }
 
@@ -409,6 +410,7 @@ int ref_amg_set_matrix(void *hv, i64 n, int b, const i64 *rp, const i32 *ci, con
 int ref_amg_set_prol(void *hv, int l, i64 nc, int bc, const i64 *rp, const i32 *ci, const double *v) {
   AmgH *a = (AmgH *)hv;
   return guarded([&] {
+    if (l + 1 != a->nlevels || l + 1 >= (int)a->lev.size()) throw Exception("ref_amg_set_prol: levels must be added in order, below the bound given to ref_amg_new");
     LevelH &L = a->lev[l], &C = a->lev[l + 1];
     L.P = (MatH *)ref_mat_new((i64)L.A->m->Height(), nc, L.b, bc, rp, ci, v);
     if (!L.P) throw Exception(g_err);
@@ -419,6 +421,7 @@ int ref_amg_set_prol(void *hv, int l, i64 nc, int bc, const i64 *rp, const i32 *
     if (!ac) throw Exception("ref_amg_set_prol: unsupported block shapes");
     C.b = bc;
     C.A = ac;
+    a->nlevels = a->amg.n_levels = l + 2;
   });
 }
 
@@ -506,6 +509,47 @@ int ref_amg_apply(void *hv, int cycle, const double *b, double *x) {
     else if (cycle == 2) a->amg.SmoothBS(vx, vb);
     else throw Exception("ref_amg_apply: unknown cycle");
     std::memcpy(x, vx.FVDouble().Data(), sizeof(double) * nb);
+  });
+}
+
+// PCG around the reference's cycle.  GLUE, not reference code: ngsolve.krylovspace.CGSolver lives in NGSolve; the loop is the same
+// restatement as orc_amg_pcg (oracle/ngsamg_oracle.c): the preconditioner C is AMGMatrix::SmoothV/W/BS, A*s is SparseMatrix::MultAdd.
+int ref_amg_pcg(void *hv, int cycle, const double *rhs, double *u, double tol, int maxsteps, double *errors, int *iterations) {
+  AmgH *a = (AmgH *)hv;
+  return guarded([&] {
+    LevelH &L = a->lev[0];
+    const size_t n = L.A->m->Height(), nb = n * (size_t)L.b;
+    BaseVector vd(n, L.b), vw(n, L.b), vs(n, L.b);
+    auto d = vd.FVDouble(), w = vw.FVDouble(), sv = vs.FVDouble();
+    auto precond = [&](const BaseVector &in, BaseVector &out) {
+      if (cycle == 0) a->amg.SmoothV(out, in);
+      else if (cycle == 1) a->amg.SmoothW(out, in);
+      else a->amg.SmoothBS(out, in);
+    };
+    auto dot = [&](FlatVector<double> p, FlatVector<double> q) { double t = 0; for (size_t i = 0; i < nb; i++) t += p(i) * q(i); return t; };
+    for (size_t i = 0; i < nb; i++) { u[i] = 0.0; d(i) = rhs[i]; }
+    precond(vd, vw);
+    for (size_t i = 0; i < nb; i++) sv(i) = w(i);
+    double wdn = dot(w, d);
+    const double err0 = std::sqrt(std::fabs(wdn));
+    if (errors) errors[0] = err0;
+    int it = 0;
+    if (wdn != 0.0)
+      for (it = 1; it <= maxsteps; it++) {
+        L.A->m->Mult(vs, vw);
+        const double wd = wdn, alpha = wd / dot(sv, w);
+        for (size_t i = 0; i < nb; i++) u[i] += alpha * sv(i);
+        for (size_t i = 0; i < nb; i++) d(i) -= alpha * w(i);
+        precond(vd, vw);
+        wdn = dot(w, d);
+        const double beta = wdn / wd;
+        for (size_t i = 0; i < nb; i++) sv(i) = beta * sv(i) + w(i);
+        const double err = std::sqrt(std::fabs(wd));
+        if (errors) errors[it] = err;
+        if (err < tol * err0) break;
+      }
+    if (it > maxsteps) it = maxsteps;
+    *iterations = it;
   });
 }
 }  // extern "C"

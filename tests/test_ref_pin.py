@@ -246,3 +246,30 @@ def test_oracle_against_reference_made_fixtures(name):
         if ur:
             assert np.array_equal(res, g["sm_res_" + key]), key
     check_cycles(oa, lambda c: g["x_" + c], lambda w, l: g["V_%s%d" % (w, l)], g["b"], nlev)
+
+
+@needs_ref
+def test_pcg_around_the_reference_cycle_matches_the_oracle():
+    """same CG restatement on both sides, the reference's SmoothV vs the oracle's as preconditioner: identical iteration counts and
+    error histories (this is what bench.py's CPU arm runs, kind "reference")"""
+    p, A, _ = hierarchy("poisson")
+    ra = R.RefAMG(A, p["free"])                 # level by level, like bench.py builds it
+    prols, cur, fm = [], A, p["free"]
+    import ngsamg_b200 as ng
+    while cur.nrows > 30:
+        P, _, _ = ng.coarsen(ng.SparseMatrix(cur.nrows, cur.ncols, 1, 1, cur.rowptr, cur.col, cur.val), fm)
+        prols.append(to_oracle(P))
+        cur, fm = ra.add_prol(prols[-1]), None
+    ra.finalize()
+    oa = O.OracleAMG(A, p["free"], prols)
+    assert ra.nlevels == oa.nlevels
+    u1, it1, e1 = oa.pcg(p["rhs"], tol=1e-8, maxsteps=50)
+    u2, it2, e2 = ra.pcg(p["rhs"], tol=1e-8, maxsteps=50)
+    assert it1 == it2 and rel(e1, e2) < 1e-12 and rel(u1, u2) < 1e-12
+
+
+@needs_ref
+def test_bench_cpu_arm_runs_the_reference_library():
+    import bench
+    r = bench.cpu_reference_run(15, 1, 0)
+    assert r["kind"] == "reference" and r["iterations"] > 0 and r["ndof"] == 15 ** 3
