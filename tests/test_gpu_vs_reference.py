@@ -1,0 +1,82 @@
+"""GPU parity against the REFERENCE'S OWN CODE (`-m gpu`): the CUDA path through the C ABI vs oracle/_ref/libngsamg_ref.so (the
+reference's function bodies compiled against an NGSolve container stand-in, oracle/ref_pin/README.md), no oracle in between.
+The library is built where /root/reference exists and travels with the snapshot; without it these tests skip (the same checks
+then run against the oracle, which tests/test_ref_pin.py pins to the library bit for bit)."""
+import numpy as np
+import pytest
+
+import ngsamg_b200 as ng
+from helpers import assert_same_pattern, elasticity, poisson, rand, rel, to_oracle, to_product
+from oracle.ref_pin import ref as R
+
+pytestmark = [pytest.mark.gpu, pytest.mark.skipif(not R.available(), reason="oracle/_ref/libngsamg_ref.so not present")]
+
+TOL_VCYCLE = 1e-10   # north_star: residual-vector agreement <= 1e-10 relative per V-cycle in fp64
+
+
+@pytest.fixture(scope="module")
+def pois():
+    p, A = poisson(13)
+    pc = ng.h1_scal(A, p["free"], ngs_amg_max_coarse_size=20)
+    ra = R.RefAMG(to_oracle(A), p["free"], [to_oracle(P) for P in pc.GetMap()])
+    return p, A, pc, ra
+
+
+def test_spgemm_and_transpose_bit_exact_vs_reference_code():
+    import scipy.sparse as sp
+    from oracle import oracle as O
+    rng = np.random.default_rng(21)
+    for ah, aw, bw in [(1, 1, 1), (6, 3, 6), (6, 6, 6)]:
+        def rnd(n, m, h, w, dens):
+            pat = sp.random(n, m, density=dens, random_state=rng, format="csr")
+            pat.sort_indices()
+            return O.Bsr(n, m, h, w, pat.indptr, pat.indices, rng.standard_normal((pat.nnz, h, w)))
+        A, B = rnd(200, 150, ah, aw, 0.05), rnd(150, 180, aw, bw, 0.06)
+        Cg, Cr = ng.matmul(to_product(A), to_product(B)), R.matmul(A, B)          # MatMultABImpl
+        assert_same_pattern(Cg, Cr)
+        assert np.array_equal(Cg.val, Cr.val)
+        Tg, Tr = ng.transpose(to_product(A)), R.transpose(A)                       # TransposeSPMImpl
+        assert_same_pattern(Tg, Tr)
+        assert np.array_equal(Tg.val, Tr.val)
+
+
+def test_galerkin_hierarchy_vs_reference_code(pois):
+    p, A, pc, ra = pois
+    assert pc.GetNLevels() == ra.nlevels >= 3
+    for l in range(pc.GetNLevels()):
+        Ag, Ar = pc.GetLevelMatrix(l), ra.level_matrix(l)                           # RestrictMatrix
+        assert_same_pattern(Ag, Ar)
+        assert rel(Ag.val, Ar.val) < 1e-12
+
+
+@pytest.mark.parametrize("cycle", ["V", "W", "BS"])
+def test_cycles_vs_reference_code(pois, cycle):
+    """AMGMatrix::SmoothV / SmoothW / SmoothBS of the reference vs the CUDA cycle"""
+    p, A, pc, ra = pois
+    pcc = pc if cycle == "V" else ng.h1_scal(A, p["free"], ngs_amg_max_coarse_size=20, ngs_amg_mg_cycle=cycle)
+    rac = ra if cycle == "V" else R.RefAMG(to_oracle(A), p["free"], [to_oracle(P) for P in pcc.GetMap()])
+    for seed in (1, 2):
+        b = rand(seed, p["n"])
+        x = np.zeros(p["n"])
+        pcc.Mult(b, x)
+        assert rel(x, rac.apply(b, cycle)) < TOL_VCYCLE
+
+
+def test_pcg_iterations_vs_reference_code(pois):
+    p, A, pc, ra = pois
+    cg = ng.CGSolver(mat=A, pre=pc, maxsteps=50, tol=1e-8)
+    u = cg.Solve(p["rhs"])
+    ur, itr, _ = ra.pcg(p["rhs"], tol=1e-8, maxsteps=50)
+    assert cg.iterations == itr
+    assert rel(np.asarray(u), ur) < 1e-8
+
+
+def test_elasticity_3_to_6_vs_reference_code():
+    p, A = elasticity(6, 4, 4)
+    pc = ng.elast_3d(A, p["free"], vertex_xyz=p["xyz"], ngs_amg_max_coarse_size=4, ngs_amg_max_levels=2)
+    assert pc.GetNLevels() == 2                    # one smoothed level (3x3 blocks: regular, pinv == inverse), exact solve on 6x6 blocks
+    ra = R.RefAMG(to_oracle(A), p["free"], [to_oracle(P) for P in pc.GetMap()])     # GSS3<Mat<3,3>>, ProlMap<Mat<3,6>>
+    b = rand(3, p["n"] * 3)
+    x = np.zeros(p["n"] * 3)
+    pc.Mult(b, x)
+    assert rel(x, ra.apply(b)) < 1e-9              # same bar as test_gpu_parity.py::test_elasticity_3d (dense coarse solves differ)
