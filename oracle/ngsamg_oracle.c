@@ -20,9 +20,9 @@
  * sides (SparseMatrix::RowTimesVector / AddRowTransToVector / MultAdd summation order, Mat*Vec
  * evaluation order, CalcInverse, MergeArrays, SparseCholesky, krylovspace.CGSolver; NGSolve is only
  * lower-bounded, `ngsolve>=6.2.2403.post68.dev0`, pyproject.toml:2), the pseudo-inverse
- * (utils_denseLA.hpp, LAPACK), the Jacobi smoother, and the whole multi-rank path
- * (oracle_par.py: hybrid smoother, DCC maps, contraction), which is cross-checked against the
- * assembled global operator instead (tests/test_parallel_host.py).
+ * (utils_denseLA.hpp, LAPACK), the Jacobi smoother.  The multi-rank oracle (oracle_par.py) is pinned
+ * the same way for the hybrid smoother level (tests/test_ref_pin_par.py); its contraction step and
+ * V-cycle / CG drivers are cross-checked against the assembled global operator only.
  *
  * Citations are relative to /root/reference/.
  *

@@ -2,7 +2,12 @@
 
 TEST INFRASTRUCTURE ONLY (like oracle.py): imported by tests/ and the cpu_baseline / --impl reference legs of bench.py.
 
-PARITY UNPINNED (see ngsamg_oracle.c): restated from the reference sources, which cannot be built here.
+PARITY PINNED for the hybrid smoother level (HybridLevel): the reference's own functions -- BasicDCCMap, DecomposeSparseMatrixHybrid,
+MyAllReduceDofData, CalcHybridSmootherRDG*, GSS3/GSS4, HybridGSSmoother, HybridBaseSmoother -- are cut out of /root/reference at build
+time and compiled against a threaded MPI stand-in (oracle/ref_pin/ -> oracle/_ref/libngsamg_ref.so); tests/test_ref_pin_par.py compares
+M, G, master flags, DCC lists, the inverted modified diagonal and x / res of every smoother call bit for bit.  UNPINNED: CtrMap /
+contraction, the parallel V-cycle driver and CG around it (restated from the sources; checked against the assembled global
+operator in tests/test_parallel_host.py).
 
 What is restated (reference paths relative to /root/reference):
   * BasicDCCMap::CalcDOFMasters            src/base/linalg/dcc_map.cpp:494-543   -> dcc_lists
@@ -206,8 +211,8 @@ class HybridLevel:
             self.masks.append((m1, exm.astype(np.uint8), m2))
 
     # ---- DCCMap ----------------------------------------------------------------------------------------
-    def dis2co(self, vec):
-        """BufferG (pack + zero the ghosts), send to the master, ApplyM (master adds, neighbours ascending)"""
+    def dis2co_start(self, vec):
+        """StartDIS2CO: BufferG (pack + zero the ghosts) and send to the master; returns the messages in flight"""
         b = self.b
         buf = {}
         for r in range(self.R):
@@ -217,12 +222,21 @@ class HybridLevel:
                 if len(g):
                     buf[(r, p)] = v[g].copy()
                     v[g] = 0.0
+        return buf
+
+    def dis2co_finish(self, vec, buf):
+        """FinishDIS2CO: ApplyM (the master adds what it received, neighbours ascending)"""
+        b = self.b
         for r in range(self.R):
             v = vec[r].reshape(-1, b)
             for kp, p in enumerate(self.peers[r]):
                 m = self.m_ex[r][kp]
                 if len(m):
                     v[m] += buf[(p, r)]
+
+    def dis2co(self, vec):
+        """DISTRIBUTED -> CONCENTRATED in one go (DCCMap::StartDIS2CO, ApplyDIS2CO, FinishDIS2CO)"""
+        self.dis2co_finish(vec, self.dis2co_start(vec))
 
     def co2cu(self, vec):
         """BufferM, send to the ghosts, ApplyG (ghost values are overwritten)"""
@@ -252,11 +266,17 @@ class HybridLevel:
         gx = None
         if not x_zero:
             gx = [O.spmv_add(self.Gb[r], 1.0, x[r], np.zeros_like(x[r])) for r in range(R)]
-        self.dis2co(res)                                   # StartDIS2CO ... FinishDIS2CO (overlap does not change values)
+        # CallStageKernelsImpl (hybrid_base_smoother.cpp:498-574): StartDIS2CO | first local part | FinishDIS2CO (ApplyM: the received
+        # values are added AFTER the first local part has already scattered into the master rows) | EX_PART | StartCO2CU | second
+        # local part | FinishCO2CU.  With or without overlap the order of these additions is the same.
+        inflight = self.dis2co_start(res)
+        st = [self._stages(r, backward) for r in range(R)]
+        _each(R, lambda r: O.gs_res(self.Mb[r], self.dinv[r], st[r][0], x[r], res[r], backward))
+        self.dis2co_finish(res, inflight)
 
         def sweep(r):
-            # LOC_PART_1, EX_PART, then (after StartCO2CU, which only reads the exchange rows) LOC_PART_2
-            for mask in self._stages(r, backward):
+            # EX_PART, then (after StartCO2CU, which only reads the exchange rows) the second local part
+            for mask in st[r][1:]:
                 O.gs_res(self.Mb[r], self.dinv[r], mask, x[r], res[r], backward)
         _each(R, sweep)
         self.co2cu(x)
@@ -289,9 +309,12 @@ class HybridLevel:
             if not res_updated:
                 if not x_zero:
                     self.smooth_rhs(x, b, backward, False)
-                    y = self.mult(x)
-                    for r in range(R):
-                        res[r][:] = b[r] - y[r]
+
+                    def residual(r):        # res = b; res -= A x  ->  HybridBaseMatrix::MultAdd(-1): M first, then G
+                        res[r][:] = b[r]
+                        O.spmv_add(self.Mb[r], -1.0, x[r], res[r])
+                        O.spmv_add(self.Gb[r], -1.0, x[r], res[r])
+                    _each(R, residual)
                 else:
                     for r in range(R):
                         res[r][:] = b[r]

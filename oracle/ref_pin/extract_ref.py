@@ -52,6 +52,64 @@ FRAGMENTS = [
     ("amg_smoothbs", "src/base/solve/amg_matrix.cpp", r"^\s*void AMGMatrix :: SmoothBS \(", "line", None),
     ("amg_smoothv", "src/base/solve/amg_matrix.cpp", r"^\s*void AMGMatrix :: SmoothV \(", "line", None),
     ("amg_smoothvfrom", "src/base/solve/amg_matrix.cpp", r"^\s*void AMGMatrix :: SmoothVFromLevel \(", "line", None),
+    # ===== multi-rank path (compiled against the threaded MPI stand-in, ngs_standin_mpi.hpp) =======================
+    # --- small utilities of the reference's own tree ---------------------------------------------------------------
+    ("u_find_sorted", "src/base/utils/utils_arrays_tables.hpp", r"^INLINE size_t find_in_sorted_array \(const T & elem, FlatArray<T> a\)$", "template", None),
+    ("u_merge3", "src/base/utils/utils_arrays_tables.hpp", r"^INLINE void merge_arrays \(T1& tab_in, Array<T2> & out, T3 lam_comp\)", "template", None),
+    ("u_tabtrait", "src/base/utils/utils_arrays_tables.hpp", r"^template<class T> struct tab_scal_trait", "line", None),
+    ("u_merge2", "src/base/utils/utils_arrays_tables.hpp", r"^INLINE Array<typename tab_scal_trait<T1>::type> merge_arrays \(T1& tab_in, T3 lam_comp\)", "template", None),
+    ("u_allreduce_dofdata", "src/base/distributed/mpiwrap_extension.hpp", r"^void MyAllReduceDofData \(const ParallelDofs", "template", None),
+    # --- DCCMap: DISTRIBUTED -> CONCENTRATED -> CUMULATED ----------------------------------------------------------
+    ("dcc_alloc", "src/base/linalg/dcc_map.cpp", r"^AllocMPIStuff \(\)", "template", None),
+    ("dcc_start_d2c", "src/base/linalg/dcc_map.cpp", r"^StartDIS2CO \(BaseVector & vec\) const", "template", None),
+    ("dcc_apply_d2c", "src/base/linalg/dcc_map.cpp", r"^ApplyDIS2CO \(BaseVector & vec\) const", "template", None),
+    ("dcc_finish_d2c", "src/base/linalg/dcc_map.cpp", r"^FinishDIS2CO \(\) const", "template", None),
+    ("dcc_start_c2c", "src/base/linalg/dcc_map.cpp", r"^StartCO2CU \(BaseVector & vec\) const", "template", None),
+    ("dcc_apply_c2c", "src/base/linalg/dcc_map.cpp", r"^ApplyCO2CU \(BaseVector & vec\) const", "template", None),
+    ("dcc_finish_c2c", "src/base/linalg/dcc_map.cpp", r"^FinishCO2CU \(\) const", "template", None),
+    ("dcc_wait_d2c", "src/base/linalg/dcc_map.cpp", r"^WaitD2C \(\) const", "template", None),
+    ("dcc_iterate", "src/base/linalg/dcc_map.cpp", r"^iterate_buf_vec \(int block_size", "template", None),
+    ("dcc_buffer_g", "src/base/linalg/dcc_map.cpp", r"^BufferG \(BaseVector & vec\) const", "template", None),
+    ("dcc_apply_m", "src/base/linalg/dcc_map.cpp", r"^ApplyM \(BaseVector & vec\) const", "template", None),
+    ("dcc_buffer_m", "src/base/linalg/dcc_map.cpp", r"^BufferM \(BaseVector & vec\) const", "template", None),
+    ("dcc_apply_g", "src/base/linalg/dcc_map.cpp", r"^ApplyG \(BaseVector & vec\) const", "template", None),
+    ("dcc_masters", "src/base/linalg/dcc_map.cpp", r"^CalcDOFMasters \(\)$", "template", r"^BasicDCCMap<TSCAL>::"),
+    # --- hybrid matrix: A = M + G ----------------------------------------------------------------------------------
+    ("hyb_decompose", "src/base/linalg/hybrid_matrix.cpp", r"^DecomposeSparseMatrixHybrid \(shared_ptr<SparseMatrix<TM>> anA,", "template", None),
+    ("hyb_multadd", "src/base/linalg/hybrid_matrix.cpp", r"^MultAdd \(double s, const BaseVector & x, BaseVector & y\) const", "template", None),
+    ("hyb_mult", "src/base/linalg/hybrid_matrix.cpp", r"^Mult \(const BaseVector & x, BaseVector & y\) const", "template", None),
+    # --- modified diagonal ------------------------------------------------------------------------------------------
+    ("rdg_generic", "src/base/smoothers/hybrid_smoother_utils.hpp", r"^CalcHybridSmootherRDGItGeneric\(size_t", "template", None),
+    ("rdg", "src/base/smoothers/hybrid_smoother_utils.hpp", r"^CalcHybridSmootherRDG\(size_t", "template", None),
+    ("hyb_calcmoddiag", "src/base/smoothers/hybrid_smoother.cpp", r"^CalcModDiag \(shared_ptr<BitArray> free\)", "template", None),
+    # --- GSS3 range sweeps (in-class), GSS4, HybridGSSmoother --------------------------------------------------------
+    ("gss3_r_smooth", "src/base/smoothers/gssmoother.hpp", r"^\s*virtual void Smooth \(size_t first, size_t next, BaseVector &x, const BaseVector &b\) const", "line", None),
+    ("gss3_r_smoothback", "src/base/smoothers/gssmoother.hpp", r"^\s*virtual void SmoothBack \(size_t first, size_t next, BaseVector &x, const BaseVector &b\) const", "line", None),
+    ("gss3_r_smoothres", "src/base/smoothers/gssmoother.hpp", r"^\s*virtual void SmoothRES \(size_t first, size_t next, BaseVector &x, BaseVector &res\) const", "line", None),
+    ("gss3_r_smoothbackres", "src/base/smoothers/gssmoother.hpp", r"^\s*virtual void SmoothBackRES \(size_t first, size_t next, BaseVector &x, BaseVector &res\) const", "line", None),
+    ("gss4_smooth", "src/base/smoothers/gssmoother.hpp", r"^\s*INLINE void Smooth \(BaseVector &x, const BaseVector &b\) const", "line", None),
+    ("gss4_smoothback", "src/base/smoothers/gssmoother.hpp", r"^\s*INLINE void SmoothBack \(BaseVector &x, const BaseVector &b\) const", "line", None),
+    ("gss4_smoothres", "src/base/smoothers/gssmoother.hpp", r"^\s*INLINE void SmoothRES \(BaseVector &x, BaseVector &res\) const", "line", None),
+    ("gss4_smoothbackres", "src/base/smoothers/gssmoother.hpp", r"^\s*INLINE void SmoothBackRES \(BaseVector &x, BaseVector &res\) const", "line", None),
+    ("gss4_ctor_repl", "src/base/smoothers/gssmoother.cpp", r"^GSS4<TM> :: GSS4 \(shared_ptr<SparseMatrix<TM>> A, FlatArray<TM> repl_diag", "template", None),
+    ("gss4_iterate", "src/base/smoothers/gssmoother.cpp", r"^INLINE void GSS4<TM> :: iterate_rows", "template", None),
+    ("gss4_setup", "src/base/smoothers/gssmoother.cpp", r"^void GSS4<TM> :: SetUp \(", "template", None),
+    ("gss4_res", "src/base/smoothers/gssmoother.cpp", r"^void GSS4<TM> :: SmoothRESInternal \(", "template", None),
+    ("gss4_rhs", "src/base/smoothers/gssmoother.cpp", r"^void GSS4<TM> :: SmoothRHSInternal \(", "template", None),
+    ("hgs_finalize", "src/base/smoothers/gssmoother.cpp", r"^Finalize \(\)", "template", r"^/\*\* HybridGSSmoother \*\*/"),
+    ("hgs_stage_rhs", "src/base/smoothers/gssmoother.cpp", r"^SmoothStageRHS \(SMOOTH_STAGE        const &stage,", "template", r"^/\*\* HybridGSSmoother \*\*/"),
+    ("hgs_stage_res", "src/base/smoothers/gssmoother.cpp", r"^SmoothStageRes \(SMOOTH_STAGE        const &stage,", "template", r"^/\*\* HybridGSSmoother \*\*/"),
+    # --- HybridBaseSmoother: the stage protocol around the exchanges -----------------------------------------------
+    ("hbs_start_d2c", "src/base/smoothers/hybrid_base_smoother.cpp", r"^StartDIS2CO \(BaseVector &vec\) const", "template", None),
+    ("hbs_finish_d2c", "src/base/smoothers/hybrid_base_smoother.cpp", r"^FinishDIS2CO \(BaseVector &vec\) const", "template", None),
+    ("hbs_start_c2c", "src/base/smoothers/hybrid_base_smoother.cpp", r"^StartCO2CU \(BaseVector &vec\) const", "template", None),
+    ("hbs_finish_c2c", "src/base/smoothers/hybrid_base_smoother.cpp", r"^FinishCO2CU \(BaseVector &vec\) const", "template", None),
+    ("hbs_smooth", "src/base/smoothers/hybrid_base_smoother.cpp", r"^Smooth \(BaseVector       &x,", "template", None),
+    ("hbs_smoothback", "src/base/smoothers/hybrid_base_smoother.cpp", r"^SmoothBack \(BaseVector       &x,", "template", None),
+    ("hbs_impl", "src/base/smoothers/hybrid_base_smoother.cpp", r"^SmoothImpl \(BaseVector       &x,", "template", None),
+    ("hbs_impl_res", "src/base/smoothers/hybrid_base_smoother.cpp", r"^SmoothImplRES \(BaseVector       &x,", "template", None),
+    ("hbs_impl_rhs", "src/base/smoothers/hybrid_base_smoother.cpp", r"^SmoothImplRHS \(BaseVector       &x,", "template", None),
+    ("hbs_stages", "src/base/smoothers/hybrid_base_smoother.cpp", r"^CallStageKernelsImpl\(BaseVector       &x,", "template", None),
 ]
 
 
@@ -98,6 +156,8 @@ def extract(root, name, rel, anchor, start, after):
             s -= 1
             if a - s > 6:
                 raise ValueError("%s: no template header above %s:%d" % (name, rel, a + 1))
+        while s > 0 and re.match(r"\s*template\s*<", lines[s - 1]):     # member templates of class templates: two headers
+            s -= 1
     text = "\n".join(lines)
     off = sum(len(ln) + 1 for ln in lines[:s])
     aoff = sum(len(ln) + 1 for ln in lines[:a])

@@ -95,6 +95,13 @@ public:
     for (size_t i = 0; i < size; i++) data[i] = v;
     return *this;
   }
+  // assignment copies the ELEMENTS (a FlatArray is a view); Assign re-seats the view
+  FlatArray(const FlatArray &) = default;
+  const FlatArray &operator=(const FlatArray &o) const {
+    for (size_t i = 0; i < size; i++) data[i] = o.data[i];
+    return *this;
+  }
+  void Assign(const FlatArray &o) { size = o.size; data = o.data; }
 };
 template <class T> INLINE IntRange Range(const FlatArray<T> &a) { return IntRange(0, a.Size()); }
 
@@ -112,6 +119,7 @@ public:
   Array &operator=(Array &&o) noexcept { store = std::move(o.store); sync(); o.sync(); return *this; }
   Array &operator=(const T &v) { for (auto &e : store) e = v; return *this; }
   void SetSize(size_t n) { store.resize(n); sync(); }
+  void SetSize0() { store.clear(); sync(); }
   void Append(const T &v) { store.push_back(v); sync(); }
 };
 template <class T, int N> class ArrayMem : public Array<T> {
@@ -129,6 +137,8 @@ public:
   bool Test(size_t i) const { return bits[i] != 0; }
   void SetBit(size_t i) { bits[i] = 1; }
   void Clear(size_t i) { bits[i] = 0; }
+  void Clear() { for (auto &b : bits) b = 0; }
+  void And(const BitArray &o) { for (size_t i = 0; i < bits.size(); i++) bits[i] = bits[i] && o.bits[i]; }
   size_t NumSet() const { size_t c = 0; for (auto b : bits) c += b; return c; }
 };
 
@@ -175,6 +185,8 @@ template <int N, class T = double> struct Vec {
   Vec(T s) { for (int i = 0; i < N; i++) v[i] = s; }
   T &operator()(int i) { return v[i]; }
   const T &operator()(int i) const { return v[i]; }
+  T &operator[](int i) { return v[i]; }
+  const T &operator[](int i) const { return v[i]; }
   Vec &operator=(T s) { for (int i = 0; i < N; i++) v[i] = s; return *this; }
   Vec &operator+=(const Vec &o) { for (int i = 0; i < N; i++) v[i] += o.v[i]; return *this; }
   Vec &operator-=(const Vec &o) { for (int i = 0; i < N; i++) v[i] -= o.v[i]; return *this; }
@@ -211,7 +223,10 @@ template <int H, int W> INLINE Mat<W, H> Trans(const Mat<H, W> &a) {
 }
 INLINE double Trans(double a) { return a; }
 
-template <class T> struct mat_traits { typedef double TSCAL; };
+template <class T> struct mat_traits { typedef double TSCAL; typedef Vec<T::HEIGHT> TV_COL; };
+template <> struct mat_traits<double> { typedef double TSCAL; typedef double TV_COL; };
+template <int I> struct IC { static constexpr int value = I; constexpr operator int() const { return I; } };
+template <int N, int I = 0, class F> INLINE void Iterate(F f) { if constexpr (I < N) { f(IC<I>()); Iterate<N, I + 1>(f); } }
 template <class T> constexpr int Height() { return T::HEIGHT; }
 template <> constexpr int Height<double>() { return 1; }
 template <class T> constexpr int Width() { return T::WIDTH; }
@@ -279,12 +294,22 @@ public:
   template <class TV> FlatVector<TV> FV() const {
     return FlatVector<TV>(store.size() * sizeof(double) / sizeof(TV), reinterpret_cast<TV *>(const_cast<double *>(store.data())));
   }
-  void Cumulate() const { if (stat == DISTRIBUTED) stat = CUMULATED; }
-  void Distribute() const { if (stat == CUMULATED) stat = DISTRIBUTED; }
+  // single rank: only the status flips.  Vectors of the multi-rank harness are marked `parallel`: a status change that would need
+  // communication (or zeroing of ghost entries) is an error there -- the hybrid smoother must be handed the right status
+  bool parallel = false;
+  void Cumulate() const {
+    if (stat == DISTRIBUTED) { if (parallel) throw Exception("BaseVector::Cumulate would need communication"); stat = CUMULATED; }
+  }
+  void Distribute() const {
+    if (stat == CUMULATED) { if (parallel) throw Exception("BaseVector::Distribute on a cumulated parallel vector"); stat = DISTRIBUTED; }
+  }
+  BaseVector *GetLocalVector() const { return const_cast<BaseVector *>(this); }
+  BaseVector &operator+=(const BaseVector &o) { for (size_t i = 0; i < store.size(); i++) store[i] += o.store[i]; return *this; }
   void SetParallelStatus(PARALLEL_STATUS s) const { stat = s; }
   PARALLEL_STATUS GetParallelStatus() const { return stat; }
   BaseVector &operator=(double s) { for (auto &e : store) e = s; return *this; }
   BaseVector &operator=(const BaseVector &o) { store = o.store; stat = o.stat; return *this; }
+  BaseVector(const BaseVector &) = default;
   BaseVector &operator-=(const MatVecExpr &e);
   BaseVector &operator+=(const MatVecExpr &e);
   BaseVector &operator+=(const ScaledVecExpr &e) { for (size_t i = 0; i < store.size(); i++) store[i] += e.s * e.x->store[i]; return *this; }
@@ -326,6 +351,7 @@ public:
     colnr.assign(firsti[h], 0);
     data.resize(firsti[h]);
   }
+  explicit SparseMatrix(const FlatArray<int> &elsperrow) : SparseMatrix(elsperrow, elsperrow.Size()) {}
   int VHeight() const override { return int(h); }
   int VWidth() const override { return int(w); }
   size_t NZE() const { return firsti[h]; }
@@ -339,7 +365,13 @@ public:
     return size_t(it - colnr.begin());
   }
   TM &operator()(size_t i, int c) { return data[GetPosition(i, c)]; }
-  const TM &operator()(size_t i, int c) const { return data[GetPosition(i, c)]; }
+  // const access to an entry outside the pattern reads as zero (GetPositionTest)
+  const TM &operator()(size_t i, int c) const {
+    static const TM nul = TM(0.0);
+    auto b = colnr.begin() + firsti[i], e = colnr.begin() + firsti[i + 1];
+    auto it = std::lower_bound(b, e, c);
+    return (it == e || *it != c) ? nul : data[size_t(it - colnr.begin())];
+  }
   FlatVector<TM> AsVector() { return FlatVector<TM>(data.size(), data.data()); }
   void PrefetchRow(size_t) const {}
   // sum over the stored entries of the row in storage (= ascending column) order, starting from zero
@@ -376,6 +408,7 @@ template <class F> INLINE void MergeArrays(FlatArray<int *> ptrs, FlatArray<int>
 }
 
 // sort keys ascending, move vals along
+template <class T> INLINE void QuickSort(FlatArray<T> a) { std::sort(a.begin(), a.end()); }
 template <class T, class S> INLINE void BubbleSort(FlatArray<T> keys, FlatArray<S> vals) {
   for (size_t i = 0; i + 1 < keys.Size(); i++)
     for (size_t j = i + 1; j < keys.Size(); j++)

@@ -212,3 +212,96 @@ class RefAMG:
         _check(lib().ref_amg_pcg(self.h, {"V": 0, "W": 1, "BS": 2}[cycle], np.ascontiguousarray(rhs, np.float64), u, float(tol),
                                  int(maxsteps), errs, C.byref(it)))
         return u, it.value, errs[: it.value + 1].copy()
+
+
+class RefHybridLevel:
+    """one distributed level in the reference library: R ranks = R host threads around the reference's BasicDCCMap, HybridMatrix
+    (DecomposeSparseMatrixHybrid), HybridGSSmoother (CalcModDiag, GSS3 + GSS4, stage protocol of HybridBaseSmoother).
+    Same inputs as oracle_par.HybridLevel: per rank the sub-assembled matrix, free mask, ascending peers and exchange dofs."""
+
+    def __init__(self, A_loc, free, peers, ex, overlap=True, symm_loc=False, nsteps_loc=1):
+        L = lib()
+        vp, ci, i64 = C.c_void_p, C.c_int, C.c_int64
+        L.ref_par_new.argtypes, L.ref_par_new.restype = [ci], vp
+        L.ref_par_free.argtypes = [vp]
+        L.ref_par_set_rank.argtypes = [vp, ci, i64, ci, i64p, i32p, f64p, vp, ci, i32p, i64p, i32p]
+        L.ref_par_setup.argtypes = [vp, ci, ci, ci]
+        L.ref_par_M.argtypes, L.ref_par_M.restype = [vp, ci], vp
+        L.ref_par_G.argtypes, L.ref_par_G.restype = [vp, ci], vp
+        L.ref_par_info.argtypes = [vp, ci, C.POINTER(i64), vp, f64p]
+        L.ref_par_dcc_lists.argtypes = [vp, ci, ci, C.POINTER(i64), vp, C.POINTER(i64), vp]
+        pp = C.POINTER(C.c_void_p)
+        L.ref_par_smooth.argtypes = [vp, pp, pp, pp, ci, ci, ci, ci, ci, ci]
+        L.ref_par_mult.argtypes = [vp, pp, pp]
+        L.ref_par_exchange.argtypes = [vp, ci, pp]
+        self.R = len(A_loc)
+        self.n = [a.nrows for a in A_loc]
+        self.b = A_loc[0].bh
+        self.peers = peers
+        self.h = _ptr(L.ref_par_new(self.R))
+        for r, A in enumerate(A_loc):
+            fm = None if free[r] is None else np.ascontiguousarray(free[r], np.uint8)
+            pr = np.ascontiguousarray(peers[r], np.int32)
+            ptr = np.zeros(len(pr) + 1, np.int64)
+            for k in range(len(pr)):
+                ptr[k + 1] = ptr[k] + len(ex[r][k])
+            exd = np.ascontiguousarray(np.concatenate([np.asarray(e, np.int32) for e in ex[r]] + [np.zeros(0, np.int32)]), np.int32)
+            _check(L.ref_par_set_rank(self.h, r, A.nrows, A.bh, A.rowptr, A.col, A.val, None if fm is None else fm.ctypes.data_as(vp),
+                                      len(pr), pr if len(pr) else np.zeros(1, np.int32), ptr, exd if len(exd) else np.zeros(1, np.int32)))
+        _check(L.ref_par_setup(self.h, int(overlap), int(symm_loc), int(nsteps_loc)))
+
+    def __del__(self):
+        try:
+            lib().ref_par_free(self.h)
+        except Exception:
+            pass
+
+    def M(self, r):
+        return RefMat(lib().ref_par_M(self.h, r), owned=False).to_bsr()
+
+    def G(self, r):
+        g = lib().ref_par_G(self.h, r)
+        return None if not g else RefMat(g, owned=False).to_bsr()
+
+    def info(self, r):
+        """(split_ind, master flags, inverted modified diagonal blocks held by the local smoothers)"""
+        split = C.c_int64()
+        master = np.zeros(self.n[r], np.uint8)
+        dinv = np.zeros(self.n[r] * self.b * self.b)
+        _check(lib().ref_par_info(self.h, r, C.byref(split), master.ctypes.data_as(C.c_void_p), dinv))
+        return split.value, master, dinv
+
+    def dcc_lists(self, r):
+        """m_ex / g_ex of BasicDCCMap::CalcDOFMasters per neighbour"""
+        m_ex, g_ex = [], []
+        for k in range(len(self.peers[r])):
+            nm, ng = C.c_int64(), C.c_int64()
+            _check(lib().ref_par_dcc_lists(self.h, r, k, C.byref(nm), None, C.byref(ng), None))
+            m, g = np.zeros(max(nm.value, 1), np.int32), np.zeros(max(ng.value, 1), np.int32)
+            _check(lib().ref_par_dcc_lists(self.h, r, k, C.byref(nm), m.ctypes.data_as(C.c_void_p), C.byref(ng), g.ctypes.data_as(C.c_void_p)))
+            m_ex.append(m[:nm.value].astype(np.int64))
+            g_ex.append(g[:ng.value].astype(np.int64))
+        return m_ex, g_ex
+
+    def _pp(self, vecs):
+        arr = (C.c_void_p * self.R)()
+        for r in range(self.R):
+            assert vecs[r].dtype == np.float64 and vecs[r].flags["C_CONTIGUOUS"]
+            arr[r] = vecs[r].ctypes.data
+        return arr
+
+    def smooth(self, x, b, res, res_updated, update_res, x_zero, backward, status_b=0, status_res=0):
+        """HybridBaseSmoother::Smooth / SmoothBack on all ranks; x CUMULATED, b / res DISTRIBUTED by default; x, res updated in place"""
+        _check(lib().ref_par_smooth(self.h, self._pp(x), self._pp(b), self._pp(res), status_b, status_res, int(res_updated), int(update_res),
+                                    int(x_zero), int(backward)))
+
+    def mult(self, x):
+        y = [np.zeros_like(v) for v in x]
+        _check(lib().ref_par_mult(self.h, self._pp(x), self._pp(y)))
+        return y
+
+    def dis2co(self, vec):
+        _check(lib().ref_par_exchange(self.h, 0, self._pp(vec)))
+
+    def co2cu(self, vec):
+        _check(lib().ref_par_exchange(self.h, 1, self._pp(vec)))

@@ -12,7 +12,8 @@
 //   BaseSmoother::SmoothSymm/SmoothK/SmoothBackK/SmoothSymmK/CalcResiduum, ProxySmoother::Smooth/SmoothBack  base_smoother.hpp:79-197
 //   ProlMap::TransferF2C/AddC2F                                   dof_map.cpp:633-709
 //   AMGMatrix::SmoothV/SmoothW/SmoothBS/SmoothVFromLevel          amg_matrix.cpp:37-374
-#include "ngs_standin.hpp"
+#define PARALLEL 1
+#include "ngs_standin_mpi.hpp"
 
 #include <cstdint>
 #include <cstring>
@@ -92,6 +93,14 @@ public:
     SetUp(mat, subset);
     CalcDiags(Array<TM>());
   }
+  GSS3(shared_ptr<SparseMatrix<TM>> mat, FlatArray<TM> repl_diag, shared_ptr<BitArray> subset, bool _pinv) : BaseSmoother(mat), pinv(_pinv) {
+    SetUp(mat, subset);
+    CalcDiags(repl_diag);
+  }
+#include "../_ref/frag/gss3_r_smooth.inc"
+#include "../_ref/frag/gss3_r_smoothback.inc"
+#include "../_ref/frag/gss3_r_smoothres.inc"
+#include "../_ref/frag/gss3_r_smoothbackres.inc"
   void SetUp(shared_ptr<SparseMatrix<TM>> mat, shared_ptr<BitArray> subset);
   virtual void CalcDiags(FlatArray<TM> repl_diag);
   void Smooth(BaseVector &x, const BaseVector &b, BaseVector &res, bool res_updated, bool update_res, bool x_zero) const override;
@@ -190,6 +199,8 @@ public:
   }
 };
 }  // namespace amg
+
+#include "ref_par.hpp"   // the multi-rank path: class shells + fragments, C ABI ref_par_*
 
 // =====================================================================================================================
 // C ABI
@@ -553,3 +564,5 @@ int ref_amg_pcg(void *hv, int cycle, const double *rhs, double *u, double tol, i
   });
 }
 }  // extern "C"
+
+#include "ref_par_abi.hpp"

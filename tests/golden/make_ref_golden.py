@@ -66,9 +66,60 @@ def make(name, p, A, elast, sm_steps, sm_symm, **copt):
     print("%s: levels %s, %d arrays" % (name, [ra.level_matrix(l).nrows for l in range(ra.nlevels)], len(out)))
 
 
+
+
+def make_hybrid():
+    """2 x 2 x 2 ranks (dofs shared by up to 8 ranks): the reference's hybrid split, modified diagonal and every smoother call"""
+    from ngsamg_b200 import synthetic as S
+    from oracle import oracle as O
+    from oracle import oracle_par as OP
+    parts = S.partition_poisson3d(6, 5, 7, grid=(2, 2, 2))
+    Rn = len(parts)
+    A = [O.Bsr(p["n"], p["n"], 1, 1, p["rowptr"], p["col"], p["val"]) for p in parts]
+    args = (A, [p["free"] for p in parts], [p["peers"] for p in parts], [p["ex"] for p in parts])
+    RL = R.RefHybridLevel(*args)
+    HL = OP.HybridLevel(*args)          # only used to produce a consistent residual input (b - A x); outputs come from RL
+    out = {"R": Rn, "fragments": np.array(R.fragment_index())}
+    for r, p in enumerate(parts):
+        out["n%d" % r] = p["n"]
+        out["rowptr%d" % r], out["col%d" % r], out["val%d" % r] = A[r].rowptr, A[r].col, A[r].val
+        out["free%d" % r] = np.asarray(p["free"], np.uint8)
+        out["peers%d" % r] = np.asarray(p["peers"], np.int32)
+        ptr = np.zeros(len(p["peers"]) + 1, np.int64)
+        for k in range(len(p["peers"])):
+            ptr[k + 1] = ptr[k] + len(p["ex"][k])
+        out["exptr%d" % r] = ptr
+        out["exdofs%d" % r] = np.concatenate([np.asarray(e, np.int32) for e in p["ex"]])
+        pack("M%d" % r, RL.M(r), out)
+        G = RL.G(r)
+        pack("G%d" % r, G if G is not None else O.Bsr(p["n"], p["n"], 1, 1, np.zeros(p["n"] + 1, np.int64), np.zeros(0, np.int32), np.zeros(0)), out)
+        _, master, dinv = RL.info(r)
+        out["master%d" % r], out["dinv%d" % r] = master, dinv
+    nglob = 1 + max(int(p["gidx"].max()) for p in parts)
+    for k, (ru, ur, xz, bw) in enumerate(FLAGS):
+        rng = np.random.default_rng(300 + k)
+        xg = rng.standard_normal(nglob)
+        x = [np.zeros(p["n"]) if xz else xg[p["gidx"]].copy() for p in parts]
+        rhs = [rng.standard_normal(p["n"]) for p in parts]
+        if ru:
+            y = RL.mult(x)
+            res = [rhs[r] - y[r] for r in range(Rn)]
+        else:
+            res = [rng.standard_normal(p["n"]) for p in parts]
+        key = "%d%d%d%d" % (ru, ur, xz, bw)
+        for r in range(Rn):
+            out["in_x_%s_%d" % (key, r)], out["in_b_%s_%d" % (key, r)], out["in_res_%s_%d" % (key, r)] = x[r].copy(), rhs[r].copy(), res[r].copy()
+        RL.smooth(x, rhs, res, ru, ur, xz, bw)
+        for r in range(Rn):
+            out["out_x_%s_%d" % (key, r)], out["out_res_%s_%d" % (key, r)] = x[r], res[r]
+    np.savez_compressed(os.path.join(HERE, "refpin_hybrid_2x2x2.npz"), **out)
+    print("refpin_hybrid_2x2x2: %d ranks, %s dofs, %d arrays" % (Rn, [p["n"] for p in parts], len(out)))
+
+
 if __name__ == "__main__":
     p, A = poisson(7)
     make("refpin_poisson_n7", p, A, False, 1, False, max_coarse=20)
     make("refpin_poisson_n7_symm2", p, A, False, 2, True, max_coarse=20)
     p, A = elasticity(5, 3, 3)
     make("refpin_elast_5x3x3", p, A, True, 1, False, max_coarse=4, max_per_row=4)
+    make_hybrid()
