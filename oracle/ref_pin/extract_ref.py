@@ -43,6 +43,10 @@ FRAGMENTS = [
      r"^class ProxySmoother"),
     ("proxy_smoothback", "src/base/smoothers/base_smoother.hpp", r"^\s*virtual void SmoothBack \(BaseVector &x, const BaseVector &b,", "line",
      r"^class ProxySmoother"),
+    ("rich_ctor", "src/base/smoothers/base_smoother.cpp", r"^RichardsonSmoother :: RichardsonSmoother \(", "line", None),
+    ("rich_smooth", "src/base/smoothers/base_smoother.cpp", r"^void RichardsonSmoother :: Smooth \(", "line", None),
+    ("rich_smoothback", "src/base/smoothers/base_smoother.cpp", r"^void RichardsonSmoother :: SmoothBack \(", "line", None),
+    ("jacobi_ctor", "src/base/smoothers/base_smoother.cpp", r"^JacobiSmoother<TM>::JacobiSmoother \(", "template", None),
     # --- grid transfer -----------------------------------------------------------------------------------------
     ("prol_f2c", "src/base/coarsening/dof_map.cpp", r"^TransferF2C \(BaseVector const \*x_fine,", "template", r"^timer_hack_prol_c2f"),
     ("prol_addc2f", "src/base/coarsening/dof_map.cpp", r"^AddC2F \(double fac, BaseVector \*x_fine, BaseVector const \*x_coarse\) const", "template",

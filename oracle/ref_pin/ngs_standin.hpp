@@ -277,7 +277,11 @@ enum PARALLEL_STATUS { DISTRIBUTED, CUMULATED, NOT_PARALLEL };
 
 class BaseMatrix;
 class BaseVector;
-struct MatVecExpr { const BaseMatrix *m; const BaseVector *x; };
+// the few vector expressions the smoothers write:  A * x,  s * A * x,  b - A * x,  s * x.  Evaluated like NGSolve does:
+// `v += s*A*x` is A.MultAdd(s, x, v);  `v = b - A*x` is v = b followed by A.MultAdd(-1, x, v)
+struct MatVecExpr { const BaseMatrix *m; const BaseVector *x; double s = 1.0; };
+struct ScaledMatExpr { double s; const BaseMatrix *m; };
+struct VecMinusMatVecExpr { const BaseVector *b; MatVecExpr e; };
 struct ScaledVecExpr { double s; const BaseVector *x; };
 
 // vector of n entries of `es` doubles each (es = block size); strictly single-rank: Cumulate/Distribute only flip the status
@@ -312,6 +316,7 @@ public:
   BaseVector(const BaseVector &) = default;
   BaseVector &operator-=(const MatVecExpr &e);
   BaseVector &operator+=(const MatVecExpr &e);
+  BaseVector &operator=(const VecMinusMatVecExpr &e);
   BaseVector &operator+=(const ScaledVecExpr &e) { for (size_t i = 0; i < store.size(); i++) store[i] += e.s * e.x->store[i]; return *this; }
 };
 INLINE ScaledVecExpr operator*(double s, const BaseVector &x) { return ScaledVecExpr{s, &x}; }
@@ -325,15 +330,42 @@ public:
   size_t Width() const { return VWidth(); }
   virtual void Mult(const BaseVector &x, BaseVector &y) const { y = 0.0; MultAdd(1.0, x, y); }
   virtual void MultAdd(double s, const BaseVector &x, BaseVector &y) const = 0;
-  MatVecExpr operator*(const BaseVector &x) const { return MatVecExpr{this, &x}; }
+  MatVecExpr operator*(const BaseVector &x) const { return MatVecExpr{this, &x, 1.0}; }
 };
-INLINE BaseVector &BaseVector::operator-=(const MatVecExpr &e) { e.m->MultAdd(-1.0, *e.x, *this); return *this; }
-INLINE BaseVector &BaseVector::operator+=(const MatVecExpr &e) { e.m->MultAdd(1.0, *e.x, *this); return *this; }
+INLINE ScaledMatExpr operator*(double s, const BaseMatrix &m) { return ScaledMatExpr{s, &m}; }
+INLINE MatVecExpr operator*(const ScaledMatExpr &sm, const BaseVector &x) { return MatVecExpr{sm.m, &x, sm.s}; }
+INLINE VecMinusMatVecExpr operator-(const BaseVector &b, const MatVecExpr &e) { return VecMinusMatVecExpr{&b, e}; }
+INLINE BaseVector &BaseVector::operator-=(const MatVecExpr &e) { e.m->MultAdd(-e.s, *e.x, *this); return *this; }
+INLINE BaseVector &BaseVector::operator+=(const MatVecExpr &e) { e.m->MultAdd(e.s, *e.x, *this); return *this; }
+INLINE BaseVector &BaseVector::operator=(const VecMinusMatVecExpr &e) {
+  if (this != e.b) *this = *e.b;
+  e.e.m->MultAdd(-e.e.s, *e.e.x, *this);
+  return *this;
+}
+
+// y(i) += s * d(i) * x(i)
+template <class TM> class DiagonalMatrix : public BaseMatrix {
+  std::vector<TM> d;
+
+public:
+  explicit DiagonalMatrix(size_t n) : d(n) {}
+  int VHeight() const override { return int(d.size()); }
+  int VWidth() const override { return int(d.size()); }
+  TM &operator()(size_t i) { return d[i]; }
+  const TM &operator()(size_t i) const { return d[i]; }
+  void MultAdd(double s, const BaseVector &x, BaseVector &y) const override;
+};
 
 template <class TM> struct vec_of_rows { typedef Vec<TM::HEIGHT> type; };
 template <> struct vec_of_rows<double> { typedef double type; };
 template <class TM> struct vec_of_cols { typedef Vec<TM::WIDTH> type; };
 template <> struct vec_of_cols<double> { typedef double type; };
+
+template <class TM> void DiagonalMatrix<TM>::MultAdd(double s, const BaseVector &x, BaseVector &y) const {
+  auto fx = x.FV<typename vec_of_cols<TM>::type>();
+  auto fy = y.FV<typename vec_of_rows<TM>::type>();
+  for (size_t i = 0; i < d.size(); i++) fy(i) += (s * d[i]) * fx(i);
+}
 
 // CSR with block entries, columns ascending inside a row
 template <class TM> class SparseMatrix : public BaseMatrix {

@@ -159,6 +159,12 @@ class RefAMG:
                 self.add_prol(P, fetch=False)
             self.finalize()
 
+    def use_jacobi(self, omega=0.9, sm_steps=1, sm_symm=False):
+        """replace the Gauss-Seidel smoothers by the reference's JacobiSmoother (RichardsonSmoother with prec = diag^-1)"""
+        L = lib()
+        L.ref_amg_use_jacobi.argtypes = [C.c_void_p, C.c_double, C.c_int, C.c_int]
+        _check(L.ref_amg_use_jacobi(self.h, float(omega), int(sm_steps), int(bool(sm_symm))))
+
     def add_prol(self, P, fetch=True):
         """prolongation of the current coarsest level: TransposeSPMImpl + RestrictMatrix build the next level matrix"""
         _check(lib().ref_amg_set_prol(self.h, self.nlevels - 1, P.ncols, P.bw, P.rowptr, P.col, P.val))

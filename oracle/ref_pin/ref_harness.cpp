@@ -74,6 +74,33 @@ public:
 #include "../_ref/frag/proxy_smoothback.inc"
 };
 
+// Richardson / Jacobi (base_smoother.hpp:250-285, base_smoother.cpp:52-114)
+template <class TM> INLINE shared_ptr<SparseMatrix<TM>> GetLocalTMM(shared_ptr<BaseMatrix> A) { return dynamic_pointer_cast<SparseMatrix<TM>>(A); }
+class RichardsonSmoother : public BaseSmoother {
+public:
+  RichardsonSmoother(shared_ptr<BaseMatrix> _mat, shared_ptr<BaseMatrix> _prec, double _omega = 1.0);
+  void Smooth(BaseVector &x, const BaseVector &b, BaseVector &res, bool res_updated, bool update_res, bool x_zero) const override;
+  void SmoothBack(BaseVector &x, const BaseVector &b, BaseVector &res, bool res_updated, bool update_res, bool x_zero) const override;
+
+protected:
+  shared_ptr<BaseMatrix> prec;
+  double omega;
+};
+#include "../_ref/frag/rich_ctor.inc"
+#include "../_ref/frag/rich_smooth.inc"
+#include "../_ref/frag/rich_smoothback.inc"
+template <class TMAT> class JacobiSmoother : public RichardsonSmoother {
+public:
+  using TM = TMAT;
+  JacobiSmoother(shared_ptr<BaseMatrix> _mat, shared_ptr<BitArray> _freedofs, double _omega = 0.9);
+  shared_ptr<DiagonalMatrix<TMAT>> DiagInv() const { return diagInv; }
+
+protected:
+  shared_ptr<DiagonalMatrix<TMAT>> diagInv;
+  shared_ptr<BitArray> freedofs;
+};
+#include "../_ref/frag/jacobi_ctor.inc"
+
 template <class TM> class GSS3 : public BaseSmoother {
 protected:
   size_t H;
@@ -278,6 +305,10 @@ struct AmgH {
 template <int B> shared_ptr<BaseSmoother> make_gss3(LevelH &L) {
   return make_shared<GSS3<typename spm_entry<B, B>::type>>(as<B, B>(L.A), L.free, false);
 }
+template <int B> shared_ptr<BaseSmoother> make_jacobi(LevelH &L, double omega) {
+  return make_shared<JacobiSmoother<typename spm_entry<B, B>::type>>(as<B, B>(L.A), L.free, omega);
+}
+
 template <int B> void dinv_out(LevelH &L, double *out) {
   auto g = dynamic_pointer_cast<GSS3<typename spm_entry<B, B>::type>>(L.gs);
   auto d = g->DiagInverses();
@@ -437,6 +468,22 @@ int ref_amg_set_prol(void *hv, int l, i64 nc, int bc, const i64 *rp, const i32 *
 }
 
 // smoothers (GSS3, wrapped into a ProxySmoother when sm_steps > 1 or sm_symm), level vectors, optional dense coarse inverse
+// Jacobi instead of Gauss-Seidel on every level (call after ref_amg_finalize): JacobiSmoother(A, free, omega)
+int ref_amg_use_jacobi(void *hv, double omega, int sm_steps, int sm_symm) {
+  AmgH *a = (AmgH *)hv;
+  return guarded([&] {
+    for (int l = 0; l + 1 < a->nlevels; l++) {
+      LevelH &L = a->lev[l];
+      if (L.b == 1) L.gs = make_jacobi<1>(L, omega);
+      else if (L.b == 2) L.gs = make_jacobi<2>(L, omega);
+      else if (L.b == 3) L.gs = make_jacobi<3>(L, omega);
+      else if (L.b == 6) L.gs = make_jacobi<6>(L, omega);
+      else throw Exception("ref_amg_use_jacobi: unsupported block size");
+      a->amg.smoothers[l] = (sm_steps > 1 || sm_symm) ? shared_ptr<BaseSmoother>(make_shared<ProxySmoother>(L.gs, sm_steps, sm_symm != 0)) : L.gs;
+    }
+  });
+}
+
 int ref_amg_finalize(void *hv, int sm_steps, int sm_symm, const double *coarse_inv) {
   AmgH *a = (AmgH *)hv;
   return guarded([&] {

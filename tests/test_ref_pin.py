@@ -273,3 +273,27 @@ def test_bench_cpu_arm_runs_the_reference_library():
     import bench
     r = bench.cpu_reference_run(15, 1, 0)
     assert r["kind"] == "reference" and r["iterations"] > 0 and r["ndof"] == 15 ** 3
+
+
+@needs_ref
+@pytest.mark.parametrize("kind", ["poisson", "elasticity"])
+@pytest.mark.parametrize("steps,symm", [(1, False), (2, True)])
+def test_jacobi_smoother_protocol_vs_reference_code(kind, steps, symm):
+    """JacobiSmoother ctor + RichardsonSmoother::Smooth / SmoothBack (base_smoother.cpp:52-114): which vector feeds the update and when
+    the residual is recomputed, for all 16 flag combinations.  The update itself is NGSolve's DiagonalMatrix::MultAdd; its
+    association (omega * d) * r vs omega * (d * r) is not in the reference tree, so the comparison is to 1e-14, not bit for bit."""
+    p, A, prols = hierarchy(kind)
+    oa = O.OracleAMG(A, p["free"], prols, sm_type="jacobi", sm_steps=steps, sm_symm=symm)
+    ra = R.RefAMG(A, p["free"], prols, sm_steps=steps, sm_symm=symm)
+    ra.use_jacobi(0.9, steps, symm)
+    for ru, ur, xz, bw in FLAGS:
+        x1, b, r1 = sweep_inputs(A, ru, xz)
+        x2, r2 = x1.copy(), r1.copy()
+        oa.smooth(0, x1, b, r1, ru, ur, xz, bw)
+        ra.smooth(0, x2, b, r2, ru, ur, xz, bw)
+        assert rel(x1, x2) < 1e-14, (ru, ur, xz, bw)
+        if ur:
+            assert rel(r1, r2) < 1e-14, (ru, ur, xz, bw)
+    b = rand(16, A.nrows * A.bh)
+    for cyc in ("V", "W", "BS"):
+        assert rel(oa.apply(b, cyc), ra.apply(b, cyc)) < 1e-13
