@@ -251,6 +251,13 @@ int ngsamg_b200_coarsen_begin(const ngsamg_csr *A, const uint8_t *free_mask, con
 int ngsamg_b200_coarsen_fetch(ngsamg_b200_hostspm *m, int64_t *rowptr, int32_t *col, double *val, int32_t *vmap,
                               double *cxyz);
 
+/* ---- pseudo-inverse of one diagonal block (host only; ngsamg_b200/csrc/dense.cpp) ---------------------------------------------
+ * What the smoother set-up applies to every diagonal block when ngs_amg_regularize_cmats asks for pinv smoothers: the reference's
+ * CalcPseudoInverseTryNormal(Mat<N,N>&) (src/base/utils/utils_denseLA.hpp:1549-1562) with its zero-row detection (:1237-1405), the direct
+ * inverse attempt TryDirectInverse_simple (utils_denseLA.cpp:458-555) and the eigenvalue fall-back (:1474-1519).  m: n x n, row-major, in
+ * place.  Exposed so that the CPU tests can compare it with the reference's own code without a device.  Returns non-zero on bad arguments. */
+int ngsamg_b200_block_pinv(int n, double *m);
+
 /* ---- two-level (tile) schedule of the sequential Gauss-Seidel sweep (host only; ngsamg_b200/csrc/tiles.hpp) ---------------
  * Groups the smoothed rows of a level matrix into compact tiles of <= max_rows graph-neighbouring rows, orders the tiles by the levels of
  * the tile dependency DAG and the rows of a tile by their tile-local dependency levels.  Executing tile after tile, level after level, is

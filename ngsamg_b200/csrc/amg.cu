@@ -398,62 +398,7 @@ bool dense_invert(int n, std::vector<double> &a)
   return true;
 }
 
-// host pseudo-inverse of one small symmetric block (CalcPseudoInverseTryNormal, utils_denseLA.hpp:1474-1569)
-void block_pinv(int n, double *m)
-{
-  if (n == 1) { m[0] = std::fabs(m[0]) > 1e-20 ? 1.0 / m[0] : 0.0; return; }
-  std::vector<int> idx;
-  for (int i = 0; i < n; i++) if (std::fabs(m[i * n + i]) > 1e-20) idx.push_back(i);
-  const int k = (int)idx.size();
-  std::vector<double> sub((size_t)k * k), keep;
-  for (int i = 0; i < k; i++) for (int j = 0; j < k; j++) sub[i * k + j] = m[idx[i] * n + idx[j]];
-  keep = sub;
-  bool ok = false;
-  if (k > 0) {
-    std::vector<double> t = sub;
-    if (dense_invert(k, t)) {
-      double err = 0;
-      for (int i = 0; i < k; i++) for (int j = 0; j < k; j++) {
-        double s = 0;
-        for (int l = 0; l < k; l++) s += keep[i * k + l] * t[l * k + j];
-        const double d = s - (i == j ? 1.0 : 0.0);
-        err += d * d;
-      }
-      ok = std::sqrt(err / (k * k)) < 1e-8;
-      if (ok) sub = t;
-    }
-    if (!ok) {
-      // cyclic Jacobi eigen-decomposition, eigenvalues <= 1e-12 * mean are treated as kernel
-      std::vector<double> a = keep, V((size_t)k * k, 0.0);
-      for (int i = 0; i < k; i++) V[i * k + i] = 1.0;
-      for (int sweep = 0; sweep < 100; sweep++) {
-        double off = 0;
-        for (int i = 0; i < k; i++) for (int j = i + 1; j < k; j++) off += a[i * k + j] * a[i * k + j];
-        if (off < 1e-300) break;
-        for (int p = 0; p < k; p++) for (int q = p + 1; q < k; q++) {
-          const double apq = a[p * k + q];
-          if (std::fabs(apq) < 1e-300) continue;
-          const double theta = (a[q * k + q] - a[p * k + p]) / (2.0 * apq);
-          const double tt = (theta >= 0 ? 1.0 : -1.0) / (std::fabs(theta) + std::sqrt(theta * theta + 1.0));
-          const double c = 1.0 / std::sqrt(tt * tt + 1.0), s = tt * c;
-          for (int r = 0; r < k; r++) { double x = a[r * k + p], y = a[r * k + q]; a[r * k + p] = c * x - s * y; a[r * k + q] = s * x + c * y; }
-          for (int r = 0; r < k; r++) { double x = a[p * k + r], y = a[q * k + r]; a[p * k + r] = c * x - s * y; a[q * k + r] = s * x + c * y; }
-          for (int r = 0; r < k; r++) { double x = V[p * k + r], y = V[q * k + r]; V[p * k + r] = c * x - s * y; V[q * k + r] = s * x + c * y; }
-        }
-      }
-      double tol = 0;
-      for (int i = 0; i < k; i++) tol += a[i * k + i];
-      tol = std::max(1e-12 * tol / k, 1e-20);
-      for (int i = 0; i < k; i++) for (int j = 0; j < k; j++) {
-        double s = 0;
-        for (int e = 0; e < k; e++) { const double ev = a[e * k + e]; if (ev > tol) s += V[e * k + i] * V[e * k + j] / ev; }
-        sub[i * k + j] = s;
-      }
-    }
-  }
-  for (int i = 0; i < n * n; i++) m[i] = 0.0;
-  for (int i = 0; i < k; i++) for (int j = 0; j < k; j++) m[idx[i] * n + idx[j]] = sub[i * k + j];
-}
+// block_pinv (pseudo-inverse of a diagonal block): dense.cpp, declared in common.hpp
 
 // ---- coarse-level numbering -------------------------------------------------------------------------
 // The numbering of a COARSE level is an output of the hierarchy builder (the reference's comes from its agglomeration

@@ -126,4 +126,7 @@ void build_prolongation(const HostBsr &A, const uint8_t *free_mask, int bc, cons
 
 void host_transpose(const HostBsr &A, HostBsr &T);
 
+// dense.cpp: CalcPseudoInverseTryNormal(Mat<N,N>&) of the reference restated (utils_denseLA.hpp:1237-1569, utils_denseLA.cpp:458-555); m: n x n row-major, in place
+void block_pinv(int n, double *m);
+
 }  // namespace ngb

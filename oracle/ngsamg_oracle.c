@@ -10,7 +10,8 @@
  * or run here and its tests hold no golden vectors (only CG iteration ceilings).  What IS pinned:
  * the bodies of the reference's own functions for the single-rank path -- TransposeSPMImpl,
  * MatMultABImpl, RestrictMatrix, GSS3::SetUp/CalcDiags/SmoothRHSInternal/SmoothRESInternal/
- * Smooth/SmoothBack, BaseSmoother::SmoothSymm/SmoothK/SmoothBackK/SmoothSymmK/CalcResiduum,
+ * Smooth/SmoothBack, CalcPseudoInverseTryNormal (with CallOnNonZeroDiagonalBlock, TryDirectInverse_simple),
+ * RichardsonSmoother/JacobiSmoother, BaseSmoother::SmoothSymm/SmoothK/SmoothBackK/SmoothSymmK/CalcResiduum,
  * ProxySmoother::Smooth/SmoothBack, ProlMap::TransferF2C/AddC2F, AMGMatrix::SmoothV/SmoothW/
  * SmoothBS/SmoothVFromLevel -- are cut out of /root/reference at build time and compiled verbatim
  * against a stand-in for the NGSolve containers (oracle/ref_pin/ -> oracle/_ref/libngsamg_ref.so);
@@ -19,8 +20,8 @@
  * STILL UNPINNED: the arithmetic that lives inside NGSolve and is therefore restated on both
  * sides (SparseMatrix::RowTimesVector / AddRowTransToVector / MultAdd summation order, Mat*Vec
  * evaluation order, CalcInverse, MergeArrays, SparseCholesky, krylovspace.CGSolver; NGSolve is only
- * lower-bounded, `ngsolve>=6.2.2403.post68.dev0`, pyproject.toml:2), the pseudo-inverse
- * (utils_denseLA.hpp, LAPACK), the Jacobi smoother.  The multi-rank oracle (oracle_par.py) is pinned
+ * lower-bounded, `ngsolve>=6.2.2403.post68.dev0`, pyproject.toml:2), the LAPACK eigen-solver
+ * inside the pseudo-inverse fall-back, DiagonalMatrix::MultAdd (Jacobi update).  The multi-rank oracle (oracle_par.py) is pinned
  * the same way for the hybrid smoother level (tests/test_ref_pin_par.py); its contraction step and
  * V-cycle / CG drivers are cross-checked against the assembled global operator only.
  *
@@ -151,43 +152,74 @@ static void dense_pinv_tol(int n, double *m, double reltol)
     }
 }
 
-/* CalcPseudoInverseTryNormal (utils_denseLA.hpp:1549-1562): operate on the block spanned by the
-   non-zero diagonal entries; try a direct inverse there, otherwise the eigenvalue pseudo inverse. */
+/* TryDirectInverse_simple (utils_denseLA.cpp:458-555): in-place Gauss-Jordan with COLUMN pivoting (the pivot of step j is
+   searched along row j).  Fails -- a untouched, returns 0 -- when a pivot is smaller than max(AbsZeroTol * rest, eps) with
+   eps = RelZeroTol * max_j a(j,j), rest = sum_{i>j} |inv(r,i)|.  RelZeroTol = 1e-12, AbsZeroTol = 1e-20 (utils_denseLA.hpp:93-117). */
+static int try_direct_inverse_simple(int n, double *a)
+{
+  if (n == 0) return 0;
+  double eps = 0;
+  for (int j = 0; j < n; j++) if (a[j * n + j] > eps) eps = a[j * n + j];
+  eps = 1e-12 * eps;
+  double inv[ORC_MAXB * ORC_MAXB], hv[ORC_MAXB];
+  int p[ORC_MAXB];
+  memcpy(inv, a, sizeof(double) * n * n);
+  for (int j = 0; j < n; j++) p[j] = j;
+  for (int j = 0; j < n; j++) {
+    double maxval = fabs(inv[j * n + j]);
+    int r = j;
+    for (int i = j + 1; i < n; i++)
+      if (fabs(inv[j * n + i]) > maxval) { r = i; maxval = fabs(inv[j * n + i]); }
+    double rest = 0.0;
+    for (int i = j + 1; i < n; i++) rest += fabs(inv[r * n + i]);
+    double lim = 1e-20 * rest;
+    if (eps > lim) lim = eps;
+    if (maxval < lim) return 0;
+    if (r > j) {
+      for (int k = 0; k < n; k++) { double t = inv[k * n + j]; inv[k * n + j] = inv[k * n + r]; inv[k * n + r] = t; }
+      int t = p[j]; p[j] = p[r]; p[r] = t;
+    }
+    double hr = 1.0 / inv[j * n + j];
+    for (int i = 0; i < n; i++) inv[j * n + i] = hr * inv[j * n + i];
+    inv[j * n + j] = hr;
+    for (int k = 0; k < n; k++)
+      if (k != j) {
+        double help = inv[k * n + j];
+        double h = help * hr;
+        for (int i = 0; i < n; i++) inv[k * n + i] -= help * inv[j * n + i];
+        inv[k * n + j] = -h;
+      }
+  }
+  for (int i = 0; i < n; i++) { /* row exchange */
+    for (int k = 0; k < n; k++) hv[p[k]] = inv[k * n + i];
+    for (int k = 0; k < n; k++) inv[k * n + i] = hv[k];
+  }
+  memcpy(a, inv, sizeof(double) * n * n);
+  return 1;
+}
+
+/* CalcPseudoInverseTryNormal(Mat<N,N>&) (utils_denseLA.hpp:1549-1562) through CallOnNonZeroDiagonalBlock<1> (:1237-1405):
+   rows whose diagonal entry is not above max(AbsZeroTol, RelZeroTol * max diagonal) are dropped (and come back as zero rows /
+   columns); on the remaining block the direct inverse is tried, the eigenvalue pseudo inverse is the fall-back.
+   Scalar overload (:1564-1569): 1/x if |x| > AbsZeroTol, else 0. */
 static void dense_pinv_try_normal(int n, double *m)
 {
   if (n == 1) { m[0] = (fabs(m[0]) > 1e-20) ? 1.0 / m[0] : 0.0; return; }
+  double maxd = 0.0;
+  for (int i = 0; i < n; i++) if (m[i * n + i] > maxd) maxd = m[i * n + i];
+  double thresh = 1e-12 * maxd;
+  if (thresh < 1e-20) thresh = 1e-20;
   int idx[ORC_MAXB], k = 0;
   for (int i = 0; i < n; i++)
-    if (fabs(m[i * n + i]) > 1e-20) idx[k++] = i;
-  double sub[ORC_MAXB * ORC_MAXB], keep[ORC_MAXB * ORC_MAXB];
+    if (m[i * n + i] > thresh) idx[k++] = i;
+  double sub[ORC_MAXB * ORC_MAXB];
   for (int i = 0; i < k; i++)
     for (int j = 0; j < k; j++) sub[i * k + j] = m[idx[i] * n + idx[j]];
-  memcpy(keep, sub, sizeof(double) * k * k);
-  int ok = 0;
-  if (k > 0) {
-    /* TryDirectInverse: accept the plain inverse iff it is a good inverse (well conditioned) */
-    if (dense_inverse(k, sub) == 0) {
-      double err = 0, nrm = 0;
-      for (int i = 0; i < k; i++)
-        for (int j = 0; j < k; j++) {
-          double s = 0;
-          for (int l = 0; l < k; l++) s += keep[i * k + l] * sub[l * k + j];
-          double d = s - (i == j ? 1.0 : 0.0);
-          err += d * d;
-          nrm += 1.0;
-        }
-      ok = (sqrt(err / nrm) < 1e-8);
-    }
-    if (!ok) { memcpy(sub, keep, sizeof(double) * k * k); dense_pinv_tol(k, sub, 1e-12); }
-  }
+  if (k > 0 && !try_direct_inverse_simple(k, sub)) dense_pinv_tol(k, sub, 1e-12);
   for (int i = 0; i < n * n; i++) m[i] = 0.0;
   for (int i = 0; i < k; i++)
     for (int j = 0; j < k; j++) m[idx[i] * n + idx[j]] = sub[i * k + j];
 }
-
-/* ------------------------------------------------------------------------------------------
- * sparse primitives (NGSolve SparseMatrix<TM> semantics)
- * ---------------------------------------------------------------------------------------- */
 
 /* y += s * A * x  (SparseMatrix::MultAdd; used by base_smoother.hpp:140, dof_map.cpp:651,708) */
 void orc_spmv_add(i64 n, int bh, int bw, const i64 *rp, const i32 *ci, const double *v,

@@ -33,6 +33,16 @@ FRAGMENTS = [
     ("gss3_res", "src/base/smoothers/gssmoother.cpp", r"^void GSS3<TM> :: SmoothRESInternal \(", "template", None),
     ("gss3_smooth", "src/base/smoothers/gssmoother.cpp", r"^void GSS3<TM> :: Smooth \(BaseVector", "template", None),
     ("gss3_smoothback", "src/base/smoothers/gssmoother.cpp", r"^void GSS3<TM> :: SmoothBack \(BaseVector", "template", None),
+    # --- pseudo inverse of a diagonal block ----------------------------------------------------------------------
+    ("la_reltol", "src/base/utils/utils_denseLA.hpp", r"^constexpr T RelZeroTol\(\)", "template", None),
+    ("la_abstol", "src/base/utils/utils_denseLA.hpp", r"^constexpr T AbsZeroTol\(\)", "template", None),
+    ("la_nzblock", "src/base/utils/utils_denseLA.hpp", r"^CallOnNonZeroDiagonalBlock \(int const &n, TGETETR mat,", "template", None),
+    ("la_nzblock_mat", "src/base/utils/utils_denseLA.hpp", r"^CallOnNonZeroDiagonalBlock \(Mat<N, N, TSCAL> &mat,", "template", None),
+    ("la_trydirect_simple", "src/base/utils/utils_denseLA.cpp", r"^TryDirectInverse_simple \(FlatMatrix<TSCAL> A, LocalHeap & lh\)", "template", None),
+    ("la_trydirect", "src/base/utils/utils_denseLA.hpp", r"^TryDirectInverse \(FlatMatrix<TSCAL> A, LocalHeap & lh\)", "template", None),
+    ("la_pinv_tol", "src/base/utils/utils_denseLA.hpp", r"^CalcPseudoInverseWithTolNonZeroBlock \(FlatMatrix<TSCAL>  M,", "template", None),
+    ("la_pinv_mat", "src/base/utils/utils_denseLA.hpp", r"^CalcPseudoInverseTryNormal \(Mat<N, N, TSCAL>       &mat,", "template", None),
+    ("la_pinv_scal", "src/base/utils/utils_denseLA.hpp", r"^CalcPseudoInverseTryNormal \(TSCAL &mat, LocalHeap &lh,", "template", None),
     # --- smoother protocol (in-class definitions of BaseSmoother / ProxySmoother) ------------------------------
     ("bs_smoothsymm", "src/base/smoothers/base_smoother.hpp", r"^\s*virtual void SmoothSymm \(BaseVector", "line", None),
     ("bs_smoothk", "src/base/smoothers/base_smoother.hpp", r"^\s*virtual void SmoothK \(int k", "line", None),

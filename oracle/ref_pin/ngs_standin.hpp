@@ -75,6 +75,7 @@ template <class T, class = std::enable_if_t<std::is_integral<T>::value>> INLINE 
 template <class T, class = std::enable_if_t<std::is_integral<T>::value>> INLINE T_Range<T> Range(T a, T b) { return T_Range<T>(a, b); }
 
 // ---- arrays --------------------------------------------------------------------------------------------------
+struct LocalHeap;
 template <class T> class FlatArray {
 protected:
   size_t size = 0;
@@ -83,6 +84,8 @@ protected:
 public:
   FlatArray() = default;
   FlatArray(size_t n, T *p) : size(n), data(p) {}
+  FlatArray(size_t n, LocalHeap &lh);
+  FlatArray Range(size_t a, size_t b) const { return FlatArray(b - a, data + a); }
   size_t Size() const { return size; }
   T *Data() const { return data; }
   T *Addr(size_t i) const { return data + i; }
@@ -153,11 +156,25 @@ template <class F> INLINE void ParallelForRange(IntRange r, F f, TasksPerThread 
 }
 template <class F> INLINE void ParallelForRange(size_t n, F f, TasksPerThread tpt = TasksPerThread(1)) { ParallelForRange(IntRange(0, n), f, tpt); }
 
-struct LocalHeap {
-  LocalHeap(size_t, const char *) {}
+struct HeapStore;
+struct LocalHeap {   // hands out memory that lives until a HeapReset taken earlier goes out of scope, or the heap (and its splits) dies
+  std::shared_ptr<HeapStore> store;
+  LocalHeap(size_t, const char *);
   LocalHeap Split() { return *this; }
 };
-struct HeapReset { explicit HeapReset(LocalHeap &) {} };
+struct HeapStore { std::vector<std::unique_ptr<char[]>> chunks; };
+struct HeapReset {   // everything allocated after construction is released on destruction
+  LocalHeap &lh;
+  size_t mark;
+  explicit HeapReset(LocalHeap &alh) : lh(alh), mark(alh.store->chunks.size()) {}
+  ~HeapReset() { lh.store->chunks.resize(mark); }
+};
+inline LocalHeap::LocalHeap(size_t, const char *) : store(std::make_shared<HeapStore>()) {}
+INLINE void *heap_alloc(LocalHeap &lh, size_t bytes) {
+  lh.store->chunks.emplace_back(new char[bytes ? bytes : 1]());
+  return lh.store->chunks.back().get();
+}
+template <class T> FlatArray<T>::FlatArray(size_t n, LocalHeap &lh) : size(n), data((T *)heap_alloc(lh, sizeof(T) * n)) {}
 }  // namespace ngcore
 
 namespace ngbla {
@@ -257,6 +274,7 @@ template <class T> class FlatVector {
 public:
   FlatVector() = default;
   FlatVector(size_t an, T *p) : n(an), d(p) {}
+  FlatVector(size_t an, ngcore::LocalHeap &lh) : n(an), d((T *)ngcore::heap_alloc(lh, sizeof(T) * an)) {}
   FlatVector(const FlatVector &) = default;
   size_t Size() const { return n; }
   T *Data() const { return d; }

@@ -139,12 +139,21 @@ def restrict_matrix(PT, A, P):
     return RefMat(lib().ref_mat_restrict(pt.h, a.h, p.h)).to_bsr()
 
 
+def pinv_block(m):
+    """CalcPseudoInverseTryNormal(Mat<N,N>&) (utils_denseLA.hpp:1549-1562) on one block"""
+    L = lib()
+    L.ref_pinv.argtypes = [C.c_int, f64p]
+    a = np.ascontiguousarray(m, np.float64).copy()
+    _check(L.ref_pinv(a.shape[0], a.reshape(-1)))
+    return a
+
+
 class RefAMG:
     """AMGMatrix of the reference: coarse matrices by TransposeSPMImpl + RestrictMatrix from injected prolongations, GSS3 per
     level (ProxySmoother around it for sm_steps > 1 / sm_symm), cycles by AMGMatrix::SmoothV / SmoothW / SmoothBS.  The exact
     coarse solve is a dense inverse handed in by the caller (the reference calls NGSolve's sparse Cholesky here)."""
 
-    def __init__(self, A, free, prols=None, sm_steps=1, sm_symm=False, coarse_inv=True, max_levels=32):
+    def __init__(self, A, free, prols=None, sm_steps=1, sm_symm=False, coarse_inv=True, max_levels=32, pinv=False):
         """with prols: the whole hierarchy at once.  prols=None: level by level -- add_prol(P) returns the Galerkin matrix the
         reference's RestrictMatrix produced (input of the next coarsening step), finalize() ends the set-up."""
         L = lib()
@@ -153,6 +162,8 @@ class RefAMG:
         fm = None if free is None else np.ascontiguousarray(free, np.uint8)
         _check(L.ref_amg_set_matrix(self.h, A.nrows, A.bh, A.rowptr, A.col, A.val, None if fm is None else fm.ctypes.data_as(C.c_void_p)))
         self.n0 = A.nrows * A.bh
+        L.ref_amg_set_pinv.argtypes = [C.c_void_p, C.c_int]
+        L.ref_amg_set_pinv(self.h, int(bool(pinv)))
         self._opts = (int(sm_steps), int(bool(sm_symm)), bool(coarse_inv))
         if prols is not None:
             for P in prols:

@@ -14,6 +14,7 @@
 //   AMGMatrix::SmoothV/SmoothW/SmoothBS/SmoothVFromLevel          amg_matrix.cpp:37-374
 #define PARALLEL 1
 #include "ngs_standin_mpi.hpp"
+#include "ngs_standin_dense.hpp"
 
 #include <cstdint>
 #include <cstring>
@@ -31,8 +32,18 @@ template <class SPM> struct TM_OF_SPM { typedef typename SPM::TENTRY type; };
 template <class V> struct strip_vec { typedef V type; };
 template <> struct strip_vec<Vec<1, double>> { typedef double type; };
 
-INLINE void CalcPseudoInverseTryNormal(double &, LocalHeap &) { throw Exception("ref harness: pinv is not part of the pin"); }
-template <int N> INLINE void CalcPseudoInverseTryNormal(Mat<N, N> &, LocalHeap &) { throw Exception("ref harness: pinv is not part of the pin"); }
+// ---- pseudo inverse of a diagonal block (utils_denseLA.hpp:93-117, 1237-1569, utils_denseLA.cpp:458-555) --------------
+#include "../_ref/frag/la_reltol.inc"
+#include "../_ref/frag/la_abstol.inc"
+#include "../_ref/frag/la_nzblock.inc"
+#include "../_ref/frag/la_nzblock_mat.inc"
+template <class TSCAL> bool TryDirectInverse_Lapack(FlatMatrix<TSCAL>, LocalHeap &) { throw Exception("ref harness: blocks of 50+ rows need LAPACK"); }
+template <class TSCAL> bool TryDirectInverse_simple(FlatMatrix<TSCAL> A, LocalHeap &lh);
+#include "../_ref/frag/la_trydirect.inc"
+#include "../_ref/frag/la_trydirect_simple.inc"
+#include "../_ref/frag/la_pinv_tol.inc"
+#include "../_ref/frag/la_pinv_mat.inc"
+#include "../_ref/frag/la_pinv_scal.inc"
 
 // ---- sparse products ---------------------------------------------------------------------------------------------
 #include "../_ref/frag/timer_transpose.inc"
@@ -297,13 +308,21 @@ struct LevelH {
 };
 
 struct AmgH {
+  bool pinv = false;
   int nlevels;
   std::vector<LevelH> lev;
   AMGMatrix amg;
 };
 
-template <int B> shared_ptr<BaseSmoother> make_gss3(LevelH &L) {
-  return make_shared<GSS3<typename spm_entry<B, B>::type>>(as<B, B>(L.A), L.free, false);
+template <int B> shared_ptr<BaseSmoother> make_gss3(LevelH &L, bool pinv) {
+  return make_shared<GSS3<typename spm_entry<B, B>::type>>(as<B, B>(L.A), L.free, pinv);
+}
+template <int N> void pinv_block(double *m) {
+  typename spm_entry<N, N>::type blk;
+  std::memcpy((void *)&blk, m, sizeof(double) * N * N);
+  LocalHeap lh(1024 * 1024, "pinv");
+  CalcPseudoInverseTryNormal(blk, lh);
+  std::memcpy(m, (const void *)&blk, sizeof(double) * N * N);
 }
 template <int B> shared_ptr<BaseSmoother> make_jacobi(LevelH &L, double omega) {
   return make_shared<JacobiSmoother<typename spm_entry<B, B>::type>>(as<B, B>(L.A), L.free, omega);
@@ -467,6 +486,20 @@ int ref_amg_set_prol(void *hv, int l, i64 nc, int bc, const i64 *rp, const i32 *
   });
 }
 
+// CalcPseudoInverseTryNormal on one n x n block (row-major, in place); n in {1, 2, 3, 6}
+int ref_pinv(int n, double *m) {
+  return guarded([&] {
+    if (n == 1) pinv_block<1>(m);
+    else if (n == 2) pinv_block<2>(m);
+    else if (n == 3) pinv_block<3>(m);
+    else if (n == 6) pinv_block<6>(m);
+    else throw Exception("ref_pinv: unsupported block size");
+  });
+}
+
+// GSS3(..., pinv): pseudo-inverted diagonal blocks (ngs_amg_regularize_cmats); call before ref_amg_finalize
+void ref_amg_set_pinv(void *hv, int pinv) { ((AmgH *)hv)->pinv = pinv != 0; }
+
 // smoothers (GSS3, wrapped into a ProxySmoother when sm_steps > 1 or sm_symm), level vectors, optional dense coarse inverse
 // Jacobi instead of Gauss-Seidel on every level (call after ref_amg_finalize): JacobiSmoother(A, free, omega)
 int ref_amg_use_jacobi(void *hv, double omega, int sm_steps, int sm_symm) {
@@ -497,10 +530,10 @@ int ref_amg_finalize(void *hv, int sm_steps, int sm_symm, const double *coarse_i
       M.rhs_level[l] = make_shared<BaseVector>(n, L.b);
       M.res_level[l] = make_shared<BaseVector>(n, L.b);
       if (l + 1 == a->nlevels) break;
-      if (L.b == 1) L.gs = make_gss3<1>(L);
-      else if (L.b == 2) L.gs = make_gss3<2>(L);
-      else if (L.b == 3) L.gs = make_gss3<3>(L);
-      else if (L.b == 6) L.gs = make_gss3<6>(L);
+      if (L.b == 1) L.gs = make_gss3<1>(L, a->pinv);
+      else if (L.b == 2) L.gs = make_gss3<2>(L, a->pinv);
+      else if (L.b == 3) L.gs = make_gss3<3>(L, a->pinv);
+      else if (L.b == 6) L.gs = make_gss3<6>(L, a->pinv);
       else throw Exception("ref_amg_finalize: unsupported block size");
       M.smoothers[l] = (sm_steps > 1 || sm_symm) ? shared_ptr<BaseSmoother>(make_shared<ProxySmoother>(L.gs, sm_steps, sm_symm != 0)) : L.gs;
     }

@@ -297,3 +297,71 @@ def test_jacobi_smoother_protocol_vs_reference_code(kind, steps, symm):
     b = rand(16, A.nrows * A.bh)
     for cyc in ("V", "W", "BS"):
         assert rel(oa.apply(b, cyc), ra.apply(b, cyc)) < 1e-13
+
+
+def pinv_cases(n, seed=0):
+    rng = np.random.default_rng(seed)
+    X = rng.standard_normal((n, n))
+    spd = X @ X.T + n * np.eye(n)
+    yield "spd", spd, True
+    z = spd.copy(); z[1, :] = 0; z[:, 1] = 0
+    yield "zero row and column", z, True
+    v = rng.standard_normal((n, n - 1))
+    yield "rank n-1 (eigenvalue fall-back)", v @ v.T, False
+    tiny = spd.copy(); tiny[0, :] *= 1e-8; tiny[:, 0] *= 1e-8
+    yield "diagonal entry below RelZeroTol * max", tiny, True
+    yield "zero block", np.zeros((n, n)), True
+    one = np.zeros((n, n)); one[0, 0] = 2.0
+    yield "single entry", one, True
+    neg = spd.copy(); neg[0, 0] = -1.0
+    yield "negative diagonal entry is dropped", neg, True
+    if n == 6:
+        e = np.zeros((6, 6)); e[:3, :3] = spd[:3, :3]
+        yield "translations only (rotational dofs without stiffness)", e, True
+        w = spd.copy(); w[3:, 3:] *= 1e-14; w[:3, 3:] *= 1e-7; w[3:, :3] *= 1e-7
+        yield "nearly uncoupled weak rotations", w, True
+
+
+def oracle_pinv(M):
+    n = M.shape[0]
+    return O.calc_dinv(O.Bsr(1, 1, n, n, [0, 1], [0], M.reshape(1, n, n)), None, pinv=True).reshape(n, n)
+
+
+def product_pinv(M):
+    import ctypes as C
+    from ngsamg_b200 import _lib
+    a = np.ascontiguousarray(M, np.float64).copy()
+    L = _lib.lib()
+    L.ngsamg_b200_block_pinv.argtypes = [C.c_int, C.c_void_p]
+    assert L.ngsamg_b200_block_pinv(a.shape[0], a.ctypes.data_as(C.c_void_p)) == 0
+    return a
+
+
+@needs_ref
+@pytest.mark.parametrize("n", [2, 3, 6])
+def test_pseudo_inverse_vs_reference_code(n):
+    """CalcPseudoInverseTryNormal(Mat<N,N>&): CallOnNonZeroDiagonalBlock + TryDirectInverse_simple + the eigenvalue fall-back
+    (utils_denseLA.hpp:1237-1569, utils_denseLA.cpp:458-555) vs the oracle AND vs the product's host routine (dense.cpp):
+    bit for bit wherever the direct inverse is taken, 1e-12 on the fall-back (LAPACK in NGSolve, Jacobi rotations everywhere here)."""
+    for name, M, direct in pinv_cases(n):
+        ref = R.pinv_block(M)
+        for who, got in (("oracle", oracle_pinv(M)), ("product", product_pinv(M))):
+            if direct:
+                assert np.array_equal(ref, got), (who, n, name)
+            else:
+                assert np.abs(ref - got).max() <= 1e-12 * np.abs(ref).max(), (who, n, name)
+        if name.startswith("spd"):
+            assert np.abs(ref @ M - np.eye(n)).max() < 1e-12
+    assert R.pinv_block(np.array([[1e-21]]))[0, 0] == 0.0 == oracle_pinv(np.array([[1e-21]]))[0, 0] == product_pinv(np.array([[1e-21]]))[0, 0]
+    assert R.pinv_block(np.array([[4.0]]))[0, 0] == 0.25 == oracle_pinv(np.array([[4.0]]))[0, 0] == product_pinv(np.array([[4.0]]))[0, 0]
+
+
+@needs_ref
+def test_pinv_smoothers_through_the_hierarchy():
+    """GSS3(..., pinv = true) on an elasticity hierarchy (what ngs_amg_regularize_cmats switches on): dinv and the V-cycle"""
+    p, A, prols = hierarchy("elasticity")
+    oa, ra = O.OracleAMG(A, p["free"], prols, pinv=True), R.RefAMG(A, p["free"], prols, pinv=True)
+    for l in range(oa.nlevels - 1):
+        assert np.array_equal(oa.level_dinv(l), ra.level_dinv(l)), l
+    b = rand(21, A.nrows * A.bh)
+    assert rel(oa.apply(b), ra.apply(b)) < 1e-13
