@@ -171,11 +171,21 @@ def cpu_reference_run_parallel(n, world, steps, warmup, tol=TOL):
     from oracle import cpu_pipeline as CP
     from oracle import oracle as O
     from oracle import oracle_par as OP
+    from oracle.ref_pin import ref as R
     O.build()
+    kind = "port"
+    if R.available():
+        try:
+            R.lib()
+            kind = "reference"
+        except Exception as e:
+            sys.stderr.write("[bench] oracle/_ref unusable (%s): CPU arm runs the oracle port\n" % e)
     grid = S.bench_grid(world)
     parts = [S.box_poisson3d(n, grid, r) for r in range(world)]
     t0 = time.time()
-    amg, info = CP.build(parts, ctr_nv=20000)
+    # kind "reference": the hierarchy runs inside oracle/_ref -- the reference's OWN HybridGSSmoother / DCCMap / ProlMap /
+    # AMGMatrix::SmoothV per rank, `world` ranks = `world` host threads over an in-process MPI stand-in (oracle/ref_pin/README.md)
+    amg, info = CP.build(parts, ctr_nv=20000, engine="reference" if kind == "reference" else "oracle")
     setup_s = time.time() - t0
     OP.set_threads(world)
     rhs = [p["rhs"] * p["free"] for p in parts]
@@ -192,7 +202,7 @@ def cpu_reference_run_parallel(n, world, steps, warmup, tol=TOL):
     vcycle_s = (time.time() - tv) / 3
     ndof = int(sum(p["n_master"] for p in parts))
     return dict(ndof=ndof, solve_s=float(np.mean(times)), iterations=int(its), setup_s=setup_s, vcycle_s=vcycle_s,
-                levels=info["distributed_levels"] + info["nested_levels"], grid=grid, info=info)
+                levels=info["distributed_levels"] + info["nested_levels"], grid=grid, info=info, kind=kind)
 
 
 def run_reference(args):
@@ -213,10 +223,13 @@ def run_reference(args):
                                    % ((world,) + tuple(r["grid"]) + (n, r["ndof"], args.n)), "tol": TOL, "levels": r["levels"],
                        "multi_rank": r["info"]},
             "solve_s": r["solve_s"], "iterations": r["iterations"], "vcycle_ms": r["vcycle_s"] * 1e3, "setup_s": r["setup_s"],
-            "cpu_baseline": {"value": val, "unit": "DOF/s", "cores": world, "kind": "port",
-                             "sample": "multi-rank oracle (restated MPI path: hybrid smoothers, DCC exchange, CtrMap), %d ranks on %d host "
-                                       "threads, %d^3 vertices per rank = %d DOFs (the reference itself needs NGSolve/MPI and cannot be built "
-                                       "here)" % (world, world, n, r["ndof"])},
+            "cpu_baseline": {"value": val, "unit": "DOF/s", "cores": world, "kind": r["kind"],
+                             "sample": ("the reference's own multi-rank functions (oracle/_ref: HybridGSSmoother, DCCMap exchange, ProlMap, "
+                                        "AMGMatrix::SmoothV per rank over an in-process MPI stand-in; contraction and CG are glue)"
+                                        if r["kind"] == "reference" else
+                                        "multi-rank oracle (restated MPI path: hybrid smoothers, DCC exchange, CtrMap)") +
+                                       ", %d ranks on %d host threads, %d^3 vertices per rank = %d DOFs (the reference as a whole needs "
+                                       "NGSolve/MPI and cannot be built here)" % (world, world, n, r["ndof"])},
             "e2e": {"value": val, "unit": "DOF/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         }
         print(json.dumps(line), flush=True)

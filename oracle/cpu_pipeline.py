@@ -57,8 +57,9 @@ def contraction_maps(ns, peers, ex):
     return [np.array([offs[mrank[r][d]] + ordinal[mrank[r][d]][mindex[r][d]] for d in range(ns[r])], np.int64) for r in range(R)]
 
 
-def build(parts, b=1, elast=False, ctr_nv=2000, max_coarse=50, max_levels=10, pinv=False):
-    """parts[r]: dict(n, rowptr, col, val, free, peers, ex[, xyz]).  Returns (OracleParAMG, info)."""
+def build(parts, b=1, elast=False, ctr_nv=2000, max_coarse=50, max_levels=10, pinv=False, engine="oracle"):
+    """parts[r]: dict(n, rowptr, col, val, free, peers, ex[, xyz]).  Returns (OracleParAMG, info); engine="reference" returns the same
+    hierarchy inside the reference library (RefParAMG), engine="both" returns the pair."""
     R = len(parts)
     A = [ng.SparseMatrix(p["n"], p["n"], b, b, p["rowptr"], p["col"], p["val"]) for p in parts]
     free = [p["free"] for p in parts]
@@ -116,5 +117,16 @@ def build(parts, b=1, elast=False, ctr_nv=2000, max_coarse=50, max_levels=10, pi
         nested.append(_to_o(P))
         curm = _to_p(O.restrict_matrix(O.transpose(nested[-1]), _to_o(curm), nested[-1]))
         cx = cxn
-    amg = OP.OracleParAMG(A0, free, peers, ex, prols, halos, maps, nested, pinv=pinv)
-    return amg, dict(distributed_levels=len(prols), nested_levels=len(nested) + 1, n_contracted=N, n_global=nglob)
+    args = (A0, free, peers, ex, prols, halos, maps, nested)
+    info = dict(distributed_levels=len(prols), nested_levels=len(nested) + 1, n_contracted=N, n_global=nglob)
+    if engine == "args":           # only the hierarchy: (A0, free, peers, ex, prols, halos, ctr_maps, nested_prols) for OracleParAMG / RefParAMG
+        return args, info
+    if engine == "reference":
+        # the same hierarchy run by the reference's OWN smoothers / transfers / cycle (oracle/_ref, oracle/ref_pin/README.md)
+        from oracle.ref_pin import ref as RP
+        return RP.RefParAMG(*args, pinv=pinv), info
+    amg = OP.OracleParAMG(*args, pinv=pinv)
+    if engine == "both":
+        from oracle.ref_pin import ref as RP
+        return (amg, RP.RefParAMG(*args, pinv=pinv)), info
+    return amg, info

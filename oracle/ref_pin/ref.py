@@ -322,3 +322,134 @@ class RefHybridLevel:
 
     def co2cu(self, vec):
         _check(lib().ref_par_exchange(self.h, 1, self._pp(vec)))
+
+
+class RefParAMG:
+    """The multi-rank preconditioner run by the reference's own code: per rank an AMGMatrix (SmoothV) over distributed levels with
+    HybridGSSmoother and ProlMap, R ranks = R host threads.  Same arguments as oracle_par.OracleParAMG.  Glue (not reference
+    code): the local Galerkin products are the reference's RestrictMatrix, but the merged matrix of the contracted level is
+    assembled like the oracle does (CtrMap::DoAssembleMatrix restated), the gather / scatter around the serial coarse hierarchy
+    restates CtrMap::TransferF2C / TransferC2F for one group, and the CG loop restates NGSolve's CGSolver."""
+
+    def __init__(self, A0, free0, peers0, ex0, prols, halos, ctr_maps, nested_prols, pinv=False, nested_free=None, sm_steps=1,
+                 sm_symm=False, overlap=True):
+        import scipy.sparse as sp
+        L = lib()
+        vp, ci, i64 = C.c_void_p, C.c_int, C.c_int64
+        pp = C.POINTER(C.c_void_p)
+        L.ref_paramg_new.argtypes, L.ref_paramg_new.restype = [ci, ci], vp
+        L.ref_paramg_free.argtypes = [vp]
+        L.ref_paramg_set_matrix.argtypes = [vp, ci, i64, ci, i64p, i32p, f64p, vp]
+        L.ref_paramg_set_halo.argtypes = [vp, ci, ci, ci, i32p, i64p, i32p]
+        L.ref_paramg_set_prol.argtypes = [vp, ci, ci, i64, ci, i64p, i32p, f64p]
+        L.ref_paramg_set_contraction.argtypes = [vp, ci, i64, i64p, i64, vp]
+        L.ref_paramg_setup.argtypes = [vp, ci, ci, ci]
+        L.ref_paramg_apply.argtypes = [vp, pp, pp]
+        L.ref_paramg_mult.argtypes = [vp, pp, pp]
+        L.ref_paramg_level_vec.argtypes = [vp, ci, ci, ci, f64p]
+        L.ref_paramg_level_size.argtypes, L.ref_paramg_level_size.restype = [vp, ci, ci], i64
+        assert not pinv, "pinv smoothers on distributed levels are not wired into the harness"
+        self.R, self.npar = len(A0), len(prols)
+        self.h = _ptr(L.ref_paramg_new(self.R, self.npar + 1))
+        self.b0 = A0[0].bh
+        self.n0 = [a.nrows * a.bh for a in A0]
+        for r in range(self.R):
+            fm = None if free0[r] is None else np.ascontiguousarray(free0[r], np.uint8)
+            A = A0[r]
+            _check(L.ref_paramg_set_matrix(self.h, r, A.nrows, A.bh, A.rowptr, A.col, A.val, None if fm is None else fm.ctypes.data_as(vp)))
+        for l in range(self.npar):
+            peers, ex = (peers0, ex0) if l == 0 else halos[l]
+            for r in range(self.R):
+                pr = np.ascontiguousarray(peers[r], np.int32)
+                ptr = np.zeros(len(pr) + 1, np.int64)
+                for k in range(len(pr)):
+                    ptr[k + 1] = ptr[k] + len(ex[r][k])
+                exd = np.ascontiguousarray(np.concatenate([np.asarray(e, np.int32) for e in ex[r]] + [np.zeros(0, np.int32)]), np.int32)
+                _check(L.ref_paramg_set_halo(self.h, r, l, len(pr), pr if len(pr) else np.zeros(1, np.int32), ptr,
+                                             exd if len(exd) else np.zeros(1, np.int32)))
+                P = prols[l][r]
+                _check(L.ref_paramg_set_prol(self.h, r, l, P.ncols, P.bw, P.rowptr, P.col if P.nnz else np.zeros(1, np.int32),
+                                             P.val if P.nnz else np.zeros(1)))
+        # contracted level: merged matrix (glue, like OracleParAMG), serial hierarchy by the reference's code
+        self.nested = None
+        if ctr_maps is not None:
+            maps = [np.ascontiguousarray(m, np.int64) for m in ctr_maps]
+            N = int(max(int(m.max()) for m in maps if len(m)) + 1)
+            b = prols[-1][0].bw if self.npar else self.b0
+            acc = sp.csr_matrix((N * b, N * b))
+            for r in range(self.R):
+                Cm = self._coarsest_matrix(r).to_scipy().tocoo()
+                sd = (maps[r][:, None] * b + np.arange(b)[None, :]).ravel()
+                acc = acc + sp.coo_matrix((Cm.data, (sd[Cm.row], sd[Cm.col])), shape=(N * b, N * b)).tocsr()
+            self.A_merged = Bsr.from_scipy(acc, b, b)
+            self.nested = RefAMG(self.A_merged, nested_free, nested_prols, sm_steps=sm_steps, sm_symm=sm_symm)
+            for r in range(self.R):
+                _check(L.ref_paramg_set_contraction(self.h, r, len(maps[r]), maps[r] if len(maps[r]) else np.zeros(1, np.int64), N, self.nested.h))
+        _check(L.ref_paramg_setup(self.h, int(sm_steps), int(bool(sm_symm)), int(bool(overlap))))
+
+    def _coarsest_matrix(self, r):
+        """local matrix of the contracted level (RestrictMatrix of the reference), fetched through a one-level-deeper handle trick:
+        recomputed in python from the prolongations is avoided by asking the library"""
+        L = lib()
+        L.ref_paramg_level_matrix.argtypes, L.ref_paramg_level_matrix.restype = [C.c_void_p, C.c_int, C.c_int], C.c_void_p
+        return RefMat(L.ref_paramg_level_matrix(self.h, r, self.npar), owned=False).to_bsr()
+
+    def __del__(self):
+        try:
+            lib().ref_paramg_free(self.h)
+        except Exception:
+            pass
+
+    def _pp(self, vecs):
+        arr = (C.c_void_p * self.R)()
+        for r in range(self.R):
+            assert vecs[r].dtype == np.float64 and vecs[r].flags["C_CONTIGUOUS"]
+            arr[r] = vecs[r].ctypes.data
+        return arr
+
+    def apply(self, b0):
+        b = [np.ascontiguousarray(v, np.float64) for v in b0]
+        x = [np.zeros_like(v) for v in b]
+        _check(lib().ref_paramg_apply(self.h, self._pp(b), self._pp(x)))
+        return x
+
+    def mult(self, x):
+        y = [np.zeros_like(v) for v in x]
+        _check(lib().ref_paramg_mult(self.h, self._pp(x), self._pp(y)))
+        return y
+
+    def level_vec(self, which, l, r):
+        n = lib().ref_paramg_level_size(self.h, r, l)
+        out = np.zeros(n)
+        _check(lib().ref_paramg_level_vec(self.h, r, {"x": 0, "rhs": 1, "res": 2}[which], l, out))
+        return out
+
+    def pcg(self, rhs, tol=1e-8, maxsteps=200):
+        """CGSolver on parallel vectors (glue, same restatement as OracleParAMG.pcg): d DISTRIBUTED, w/s/u CUMULATED"""
+        R = self.R
+        dot = lambda a, b: float(sum(float(np.multiply(a[r], b[r]).sum()) for r in range(R)))
+        d = [np.ascontiguousarray(v, np.float64).copy() for v in rhs]
+        u = [np.zeros_like(v) for v in d]
+        w = self.apply(d)
+        s = [v.copy() for v in w]
+        wdn = dot(w, d)
+        err0 = np.sqrt(abs(wdn))
+        errs, it = [err0], 0
+        if wdn != 0.0:
+            for it in range(1, maxsteps + 1):
+                q = self.mult(s)
+                wd = wdn
+                alpha = wd / dot(s, q)
+                for r in range(R):
+                    u[r] += alpha * s[r]
+                    d[r] -= alpha * q[r]
+                w = self.apply(d)
+                wdn = dot(w, d)
+                beta = wdn / wd
+                for r in range(R):
+                    s[r] = w[r] + beta * s[r]
+                err = np.sqrt(abs(wd))
+                errs.append(err)
+                if err < tol * err0:
+                    break
+        return u, it, np.array(errs)

@@ -206,3 +206,276 @@ int ref_par_exchange(void *hv, int which, double **v) {
   });
 }
 }  // extern "C"
+
+// =====================================================================================================================
+// the whole multi-rank preconditioner: AMGMatrix::SmoothV (reference code) over distributed levels with the reference's hybrid
+// smoothers and ProlMap transfers, one AMGMatrix per rank, R ranks = R host threads.  The step onto the coarsest, contracted
+// level is GLUE (CtrCoarse below restates CtrMap::TransferF2C / TransferC2F, dof_contract.cpp:49-228, for ONE group whose master
+// is rank 0; members are added in rank order): the reference makes it a DOFMap step and lets ranks drop out of the cycle.
+// =====================================================================================================================
+namespace {
+struct ParLevel {
+  int b = 1;
+  MatH *A = nullptr, *P = nullptr, *PT = nullptr;
+  shared_ptr<BitArray> free;
+  std::vector<int> peers;
+  std::vector<std::vector<int>> ex;
+  shared_ptr<ParallelDofs> pds;
+  shared_ptr<BasicDCCMap<double>> dcc;
+  shared_ptr<BaseMatrix> hyb;
+  shared_ptr<BaseSmoother> sm;
+};
+struct ParAmgH;
+struct ParAmgRank {
+  int rank = 0;
+  std::vector<ParLevel> lev;
+  AMGMatrix amg;
+  std::vector<i64> ctr_map;   // local coarsest dof -> dof of the merged level
+};
+struct ParAmgH {
+  int R = 0, nlev = 0;
+  std::unique_ptr<World> world;
+  std::vector<ParAmgRank> rk;
+  AmgH *nested = nullptr;     // serial hierarchy on the merged level (owned by the caller), used by rank 0
+  i64 n_merged = 0;
+};
+
+// coarsest level: gather on rank 0 (members added in rank order), serial V-cycle of the nested hierarchy, scatter
+class CtrCoarse : public BaseMatrix {
+  ParAmgH *h;
+  int rank, b;
+
+public:
+  CtrCoarse(ParAmgH *ah, int r, int ab) : h(ah), rank(r), b(ab) {}
+  int VHeight() const override { return 0; }
+  int VWidth() const override { return 0; }
+  void MultAdd(double, const BaseVector &, BaseVector &) const override { throw Exception("CtrCoarse: MultAdd"); }
+  void Mult(const BaseVector &rhs, BaseVector &x) const override {
+    World &w = *h->world;
+    const auto &map = h->rk[rank].ctr_map;
+    auto fr = rhs.FVDouble(), fx = x.FVDouble();
+    const int TAG_UP = 7001, TAG_DOWN = 7002;
+    if (rank != 0) {
+      w.put(rank, 0, TAG_UP, fr.Data(), sizeof(double) * fr.Size());
+      w.get(0, rank, TAG_DOWN, fx.Data(), sizeof(double) * fx.Size());
+    } else {
+      const size_t N = (size_t)h->n_merged;
+      BaseVector g(N, b), xg(N, b);
+      auto fg = g.FVDouble(), fxg = xg.FVDouble();
+      for (size_t j = 0; j < map.size(); j++) for (int c = 0; c < b; c++) fg(map[j] * b + c) += fr(j * b + c);
+      for (int r = 1; r < h->R; r++) {
+        const auto &mr = h->rk[r].ctr_map;
+        std::vector<double> buf(mr.size() * b);
+        w.get(r, 0, TAG_UP, buf.data(), sizeof(double) * buf.size());
+        for (size_t j = 0; j < mr.size(); j++) for (int c = 0; c < b; c++) fg(mr[j] * b + c) += buf[j * b + c];
+      }
+      h->nested->amg.SmoothV(xg, g);                       // the reference's serial cycle on the merged level
+      for (int r = 1; r < h->R; r++) {
+        const auto &mr = h->rk[r].ctr_map;
+        std::vector<double> buf(mr.size() * b);
+        for (size_t j = 0; j < mr.size(); j++) for (int c = 0; c < b; c++) buf[j * b + c] = fxg(mr[j] * b + c);
+        w.put(0, r, TAG_DOWN, buf.data(), sizeof(double) * buf.size());
+      }
+      for (size_t j = 0; j < map.size(); j++) for (int c = 0; c < b; c++) fx(j * b + c) = fxg(map[j] * b + c);
+    }
+    x.SetParallelStatus(CUMULATED);
+  }
+};
+
+template <class F> int run_amg_ranks(ParAmgH *h, F f) {
+  std::vector<std::string> errs(h->R);
+  std::vector<std::thread> th;
+  for (int r = 0; r < h->R; r++)
+    th.emplace_back([&, r] {
+      try {
+        f(h->rk[r]);
+      } catch (const std::exception &e) {
+        errs[r] = e.what();
+        h->world->abort();
+      }
+    });
+  for (auto &t : th) t.join();
+  for (int pass = 0; pass < 2; pass++)
+    for (int r = 0; r < h->R; r++)
+      if (!errs[r].empty() && (pass == 1 || errs[r].find("another rank failed") == std::string::npos)) { g_err = "rank " + std::to_string(r) + ": " + errs[r]; return 1; }
+  return 0;
+}
+
+template <int B> void paramg_level_setup(ParAmgH *h, ParAmgRank &K, int l, int sm_steps, bool sm_symm, bool overlap) {
+  typedef typename spm_entry<B, B>::type TM;
+  ParLevel &L = K.lev[l];
+  NgMPI_Comm comm(h->world.get(), K.rank);
+  Array<int> cnt(L.peers.size()), peers(L.peers.size());
+  for (size_t k = 0; k < L.peers.size(); k++) { cnt[k] = int(L.ex[k].size()); peers[k] = L.peers[k]; }
+  Table<int> ext(cnt);
+  for (size_t k = 0; k < L.peers.size(); k++) for (size_t j = 0; j < L.ex[k].size(); j++) ext[k][j] = L.ex[k][j];
+  L.pds = make_shared<ParallelDofs>(comm, L.A->m->Height(), B, peers, ext);
+  L.dcc = make_shared<BasicDCCMap<double>>(L.pds);
+  auto hm = make_shared<HybridMatrix<TM>>(as<B, B>(L.A), L.pds, L.dcc);
+  auto sm = make_shared<HybridGSSmoother<TM>>(hm, L.free, false, overlap, false, false, 1);
+  sm->Finalize();
+  L.hyb = hm;
+  L.sm = (sm_steps > 1 || sm_symm) ? shared_ptr<BaseSmoother>(make_shared<ProxySmoother>(sm, sm_steps, sm_symm)) : shared_ptr<BaseSmoother>(sm);
+}
+
+template <int BF, int BC> void paramg_rap(ParAmgRank &K, int l) {
+  ParLevel &L = K.lev[l];
+  auto pt = TransposeSPMImpl<BF, BC>(*as<BF, BC>(L.P));
+  L.PT = new MatH{BC, BF, pt};
+  K.lev[l + 1].A = new MatH{BC, BC, RestrictMatrix<BF, BC>(*pt, *as<BF, BF>(L.A), *as<BF, BC>(L.P))};   // local Galerkin product (DISTRIBUTED sum)
+  K.lev[l + 1].b = BC;
+  K.amg.map->AddStep(make_shared<ProlMap<typename spm_entry<BF, BC>::type>>(as<BF, BC>(L.P), as<BC, BF>(L.PT)));
+}
+}  // namespace
+
+extern "C" {
+
+// nlev levels per rank: 0 .. nlev-2 distributed (hybrid smoothers), nlev-1 the contracted coarsest level
+void *ref_paramg_new(int R, int nlev) {
+  ParAmgH *h = new ParAmgH;
+  h->R = R;
+  h->nlev = nlev;
+  h->world.reset(new World(R));
+  h->rk.resize(R);
+  for (int r = 0; r < R; r++) {
+    h->rk[r].rank = r;
+    h->rk[r].lev.resize(nlev);
+    h->rk[r].amg.map = make_shared<DOFMap>();
+    h->rk[r].amg.n_levels = nlev;
+  }
+  return h;
+}
+
+void ref_paramg_free(void *hv) {
+  ParAmgH *h = (ParAmgH *)hv;
+  for (auto &K : h->rk) for (auto &L : K.lev) { delete L.A; delete L.P; delete L.PT; }
+  delete h;
+}
+
+int ref_paramg_set_matrix(void *hv, int r, i64 n, int b, const i64 *rp, const i32 *ci, const double *v, const uint8_t *freed) {
+  ParAmgH *h = (ParAmgH *)hv;
+  return guarded([&] {
+    ParLevel &L = h->rk[r].lev[0];
+    L.b = b;
+    L.A = (MatH *)ref_mat_new(n, n, b, b, rp, ci, v);
+    if (!L.A) throw Exception(g_err);
+    if (freed) {
+      L.free = make_shared<BitArray>((size_t)n);
+      for (i64 i = 0; i < n; i++) if (freed[i]) L.free->SetBit(i);
+    }
+  });
+}
+
+int ref_paramg_set_halo(void *hv, int r, int l, int npeers, const i32 *peers, const i64 *ex_ptr, const i32 *ex_dofs) {
+  ParAmgH *h = (ParAmgH *)hv;
+  return guarded([&] {
+    ParLevel &L = h->rk[r].lev[l];
+    L.peers.assign(peers, peers + npeers);
+    L.ex.assign(npeers, {});
+    for (int k = 0; k < npeers; k++) L.ex[k].assign(ex_dofs + ex_ptr[k], ex_dofs + ex_ptr[k + 1]);
+  });
+}
+
+// local prolongation of level l on rank r (levels in order); the local coarse matrix comes from the reference's RestrictMatrix
+int ref_paramg_set_prol(void *hv, int r, int l, i64 nc, int bc, const i64 *rp, const i32 *ci, const double *v) {
+  ParAmgH *h = (ParAmgH *)hv;
+  return guarded([&] {
+    ParAmgRank &K = h->rk[r];
+    ParLevel &L = K.lev[l];
+    if (!L.A || l + 1 >= h->nlev) throw Exception("ref_paramg_set_prol: levels must be added in order");
+    L.P = (MatH *)ref_mat_new((i64)L.A->m->Height(), nc, L.b, bc, rp, ci, v);
+    if (!L.P) throw Exception(g_err);
+    bool done = false;
+#define X(H, W) if (!done && L.b == H && bc == W) { paramg_rap<H, W>(K, l); done = true; }
+    REF_FOR_SHAPES(X)
+#undef X
+    if (!done) throw Exception("ref_paramg_set_prol: unsupported block shapes");
+  });
+}
+
+// contraction onto rank 0: map[r] = local coarsest dof -> merged dof; nested = handle of a finalized ref_amg_* hierarchy on the merged level
+int ref_paramg_set_contraction(void *hv, int r, i64 n, const i64 *map, i64 n_merged, void *nested) {
+  ParAmgH *h = (ParAmgH *)hv;
+  return guarded([&] {
+    h->rk[r].ctr_map.assign(map, map + n);
+    h->n_merged = n_merged;
+    h->nested = (AmgH *)nested;
+  });
+}
+
+int ref_paramg_setup(void *hv, int sm_steps, int sm_symm, int overlap) {
+  ParAmgH *h = (ParAmgH *)hv;
+  return run_amg_ranks(h, [&](ParAmgRank &K) {
+    AMGMatrix &M = K.amg;
+    M.smoothers.SetSize(h->nlev - 1);
+    M.x_level.SetSize(h->nlev); M.rhs_level.SetSize(h->nlev); M.res_level.SetSize(h->nlev);
+    for (int l = 0; l < h->nlev; l++) {
+      ParLevel &L = K.lev[l];
+      if (!L.A) throw Exception("ref_paramg_setup: level matrix missing");
+      const size_t n = L.A->m->Height();
+      for (auto *arr : {&M.x_level, &M.rhs_level, &M.res_level}) {
+        (*arr)[l] = make_shared<BaseVector>(n, L.b);
+        (*arr)[l]->parallel = true;
+      }
+      if (l + 1 == h->nlev) break;
+      if (L.b == 1) paramg_level_setup<1>(h, K, l, sm_steps, sm_symm != 0, overlap != 0);
+      else if (L.b == 3) paramg_level_setup<3>(h, K, l, sm_steps, sm_symm != 0, overlap != 0);
+      else if (L.b == 6) paramg_level_setup<6>(h, K, l, sm_steps, sm_symm != 0, overlap != 0);
+      else throw Exception("ref_paramg_setup: unsupported block size");
+      M.smoothers[l] = L.sm;
+    }
+    if (h->nested) {
+      M.crs_inv = make_shared<CtrCoarse>(h, K.rank, K.lev[h->nlev - 1].b);
+      M.has_crs_inv = true;
+    }
+  });
+}
+
+// x = C b: b[r] DISTRIBUTED local vectors, x[r] CUMULATED on return (AMGMatrix::SmoothV on every rank)
+int ref_paramg_apply(void *hv, double **b, double **x) {
+  ParAmgH *h = (ParAmgH *)hv;
+  return run_amg_ranks(h, [&](ParAmgRank &K) {
+    ParLevel &L = K.lev[0];
+    const size_t n = L.A->m->Height();
+    BaseVector vx(n, L.b), vb(n, L.b);
+    vx.parallel = true;
+    load(vb, b[K.rank], 0);
+    K.amg.SmoothV(vx, vb);
+    if (vx.GetParallelStatus() != CUMULATED) throw Exception("ref_paramg_apply: x is not CUMULATED on return");
+    store(vx, x[K.rank]);
+  });
+}
+
+// y = (M + G) x on level 0 (HybridBaseMatrix::Mult), for the CG around the cycle
+int ref_paramg_mult(void *hv, double **x, double **y) {
+  ParAmgH *h = (ParAmgH *)hv;
+  return run_amg_ranks(h, [&](ParAmgRank &K) {
+    ParLevel &L = K.lev[0];
+    const size_t n = L.A->m->Height();
+    BaseVector vx(n, L.b), vy(n, L.b);
+    load(vx, x[K.rank], 1);
+    vy.parallel = true;
+    L.hyb->Mult(vx, vy);
+    store(vy, y[K.rank]);
+  });
+}
+
+// which: 0 = x_level, 1 = rhs_level, 2 = res_level of the last cycle
+int ref_paramg_level_vec(void *hv, int r, int which, int l, double *out) {
+  ParAmgH *h = (ParAmgH *)hv;
+  return guarded([&] {
+    const AMGMatrix &M = h->rk[r].amg;
+    const auto &arr = which == 0 ? M.x_level : which == 1 ? M.rhs_level : M.res_level;
+    auto fv = arr[l]->FVDouble();
+    std::memcpy(out, fv.Data(), sizeof(double) * fv.Size());
+  });
+}
+
+const void *ref_paramg_level_matrix(void *hv, int r, int l) { return ((ParAmgH *)hv)->rk[r].lev[l].A; }
+
+i64 ref_paramg_level_size(void *hv, int r, int l) {
+  ParAmgH *h = (ParAmgH *)hv;
+  ParLevel &L = h->rk[r].lev[l];
+  return L.A ? (i64)L.A->m->Height() * L.b : -1;
+}
+}  // extern "C"

@@ -190,3 +190,34 @@ def test_multirank_oracle_against_reference_made_fixture():
             assert np.array_equal(x[r], g["out_x_%s_%d" % (key, r)]), key
             if ur:
                 assert np.array_equal(res[r], g["out_res_%s_%d" % (key, r)]), key
+
+
+@needs_ref
+@pytest.mark.parametrize("grid,steps,symm", [((1, 1, 2), 1, False), ((2, 2, 2), 1, False), ((1, 2, 2), 2, True)])
+def test_parallel_vcycle_and_pcg_vs_reference_code(grid, steps, symm):
+    """the whole multi-rank preconditioner: AMGMatrix::SmoothV of the reference over distributed levels with its HybridGSSmoother
+    (+ProxySmoother) and ProlMap, contraction onto rank 0 and the reference's serial cycle below (RefParAMG) vs OracleParAMG on
+    the same hierarchy.  Everything before the exact coarse solve is bit-identical on every level and rank; after it the two
+    dense coarse solvers differ in the last bits; identical PCG iteration counts."""
+    from oracle import cpu_pipeline as CP
+    from helpers import rand, rel
+    parts = S.partition_poisson3d(13, 11, 15, grid=grid)
+    Rn = len(parts)
+    hier, info = CP.build(parts, ctr_nv=150, max_coarse=15, engine="args")
+    oa = OP.OracleParAMG(*hier, sm_steps=steps, sm_symm=symm)
+    ra = R.RefParAMG(*hier, sm_steps=steps, sm_symm=symm)
+    assert info["distributed_levels"] >= 2
+    b = [rand(7 + r, p["n"]) * p["free"] for r, p in enumerate(parts)]
+    xo, xr = oa.apply(b), ra.apply(b)
+    for l in range(oa.npar):
+        for r in range(Rn):
+            assert np.array_equal(ra.level_vec("res", l, r), oa.level_res[l][r]), ("res", l, r)
+            assert np.array_equal(ra.level_vec("rhs", l + 1, r), oa.level_rhs[l + 1][r]), ("rhs", l + 1, r)
+    for r in range(Rn):
+        assert rel(xr[r], xo[r]) < 1e-13
+        for l in range(1, oa.npar + 1):
+            assert rel(ra.level_vec("x", l, r), oa.level_x[l][r]) < 1e-13
+    rhs = [p["rhs"] * p["free"] for p in parts]
+    u1, it1, e1 = oa.pcg(rhs, tol=1e-8, maxsteps=60)
+    u2, it2, e2 = ra.pcg(rhs, tol=1e-8, maxsteps=60)
+    assert it1 == it2 and rel(e1, e2) < 1e-10
