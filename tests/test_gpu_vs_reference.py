@@ -80,3 +80,55 @@ def test_elasticity_3_to_6_vs_reference_code():
     x = np.zeros(p["n"] * 3)
     pc.Mult(b, x)
     assert rel(x, ra.apply(b)) < 1e-9              # same bar as test_gpu_parity.py::test_elasticity_3d (dense coarse solves differ)
+
+
+@pytest.mark.parametrize("grid", [(1, 1, 2), (2, 2, 2)])
+def test_multirank_vcycle_and_pcg_vs_reference_code(grid):
+    """R ranks (threads) sharing the GPU vs RefParAMG: the reference's AMGMatrix::SmoothV per rank over its HybridGSSmoother, DCCMap
+    exchanges and ProlMap (in-process MPI stand-in), fed the hierarchy read back from the product"""
+    from ngsamg_b200 import parallel as par
+    from ngsamg_b200 import synthetic as S
+    from oracle import oracle as O
+    parts = S.partition_poisson3d(13, 11, 15, grid=grid)
+    Rn = len(parts)
+
+    def build(r, comm):
+        p = parts[r]
+        A = ng.SparseMatrix(p["n"], p["n"], 1, 1, p["rowptr"], p["col"], p["val"])
+        return par.h1_scal_par(A, par.Halo(p["peers"], p["ex"]), comm, p["free"], ngs_amg_max_coarse_size=15, ngs_amg_b200_ctr_nv=150)
+
+    pcs = par.run_ranks(Rn, build)
+    npar = pcs[0].GetNParallelLevels()
+    assert npar >= 1
+    prols = [[to_oracle(pcs[r].GetProlongation(l)) for r in range(Rn)] for l in range(npar)]
+    halos = []
+    for l in range(npar + 1):
+        hs = [pcs[r].GetHalo(l) for r in range(Rn)]
+        halos.append(([list(h.peers) for h in hs], [[np.asarray(e) for e in h.ex] for h in hs]))
+    maps = [pcs[0].GetContractionMap(r) for r in range(Rn)]
+    nprols = [to_oracle(P) for P in pcs[0].GetContracted().GetMap()]
+    A0 = [O.Bsr(p["n"], p["n"], 1, 1, p["rowptr"], p["col"], p["val"]) for p in parts]
+    ra = R.RefParAMG(A0, [p["free"] for p in parts], halos[0][0], halos[0][1], prols, halos, maps, nprols)
+    b = [rand(40 + r, p["n"]) * p["free"] for r, p in enumerate(parts)]
+    xr = ra.apply(b)
+
+    def ap(r, comm):
+        x = np.zeros(parts[r]["n"])
+        pcs[r].Mult(b[r], x)
+        return x
+
+    got = par.run_ranks(Rn, ap)
+    for r in range(Rn):
+        assert rel(got[r], xr[r]) < TOL_VCYCLE, (r, rel(got[r], xr[r]))
+    rhs = [p["rhs"] * p["free"] for p in parts]
+    ur, itr, _ = ra.pcg(rhs, tol=1e-8, maxsteps=100)
+
+    def solve(r, comm):
+        x = np.zeros(parts[r]["n"])
+        it, errs = pcs[r]._pcg(rhs[r], x, 1e-8, 100)
+        return x, it
+
+    sol = par.run_ranks(Rn, solve)
+    for r in range(Rn):
+        assert sol[r][1] == itr
+        assert rel(sol[r][0], ur[r]) < 1e-8
