@@ -249,7 +249,9 @@ template <class TM> class HybridGSSmoother : public HybridSmoother<TM> {
 public:
   using TSCAL = double;
   HybridGSSmoother(shared_ptr<HybridMatrix<TM>> _A, shared_ptr<BitArray> _subset, bool _pinv, bool _overlap, bool _in_thread, bool _symm_loc, int _nsteps_loc)
-      : HybridSmoother<TM>(_A, _nsteps_loc, _in_thread, _overlap), subset(_subset), pinv(_pinv), symm_loc(_symm_loc) {}
+      // argument order as in the reference's ctor (gssmoother.cpp:603-617): (_overlap, _in_thread, _nsteps_loc) land in
+      // (numLocSteps, commInThread, overlapComm) -- so there is one local pass and the exchange always overlaps
+      : HybridSmoother<TM>(_A, _overlap, _in_thread, _nsteps_loc), subset(_subset), pinv(_pinv), symm_loc(_symm_loc) {}
   virtual void Finalize();
   size_t SplitInd() const { return split_ind; }
   shared_ptr<GSS3<TM>> Loc() const { return jac_loc; }
