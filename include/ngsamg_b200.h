@@ -257,6 +257,10 @@ int ngsamg_b200_coarsen_fetch(ngsamg_b200_hostspm *m, int64_t *rowptr, int32_t *
  * inverse attempt TryDirectInverse_simple (utils_denseLA.cpp:458-555) and the eigenvalue fall-back (:1474-1519).  m: n x n, row-major, in
  * place.  Exposed so that the CPU tests can compare it with the reference's own code without a device.  Returns non-zero on bad arguments. */
 int ngsamg_b200_block_pinv(int n, double *m);
+/* RegularizeMatrix of the elasticity preconditioners (src/elasticity/elasticity_pc_impl.hpp:711-763, local branch), one diagonal block of the
+ * coarsest matrix: dim 3 / n 6 = RegTM<0,6,6> (utils_denseLA.hpp:1198-1234), dim 2 / n 3 = unit rotational entry when |m(2,2)| < 1e-8; other
+ * shapes are left alone.  Applied by finalize() before the coarsest matrix is inverted when ngs_amg_regularize_cmats is set (amg_pc.cpp:861). */
+int ngsamg_b200_block_regularize(int n, double *m, int dim);
 
 /* ---- two-level (tile) schedule of the sequential Gauss-Seidel sweep (host only; ngsamg_b200/csrc/tiles.hpp) ---------------
  * Groups the smoothed rows of a level matrix into compact tiles of <= max_rows graph-neighbouring rows, orders the tiles by the levels of

@@ -27,7 +27,7 @@ EXPORTS = [
     "ngsamg_b200_get_halo", "ngsamg_b200_get_hybrid", "ngsamg_b200_num_parallel_levels", "ngsamg_b200_get_contracted",
     "ngsamg_b200_get_contraction_map", "ngsamg_b200_hybrid_host_begin", "ngsamg_b200_hybrid_host_fetch",
     "ngsamg_b200_coarsen_parallel_begin", "ngsamg_b200_coarsen_parallel_fetch",
-    "ngsamg_b200_tile_schedule_begin", "ngsamg_b200_tile_schedule_fetch", "ngsamg_b200_tiles_last_error", "ngsamg_b200_block_pinv",
+    "ngsamg_b200_tile_schedule_begin", "ngsamg_b200_tile_schedule_fetch", "ngsamg_b200_tiles_last_error", "ngsamg_b200_block_pinv", "ngsamg_b200_block_regularize",
 ]
 
 

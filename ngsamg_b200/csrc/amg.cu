@@ -155,6 +155,7 @@ struct Amg {
   double *d_cinv = nullptr;
   int cinv_n = 0;
   bool has_cinv = false;
+  int regularize_coarse_dim = 0;   // 2 / 3: RegularizeMatrix on the coarsest diagonal blocks (elasticity + regularize_cmats), 0: off
   // V-cycle graph
   cudaGraphExec_t vgraph = nullptr;
   i64 vgraph_launches = 0;
@@ -748,6 +749,21 @@ void Amg::build_coarse_inverse(Level &L)
           const i64 r = g2l[i * b + p], c = g2l[(i64)A.col[k] * b + q];
           if (r >= 0 && c >= 0) M[(size_t)r * cn + c] = A.val[k * b * b + p * b + q];
         }
+  if (regularize_coarse_dim) {
+    // RegularizeMatrix on the diagonal blocks (amg_pc.cpp:861-862, elasticity_pc_impl.hpp:711-763) before the inverse
+    std::vector<double> blk((size_t)b * b);
+    for (i64 i = 0; i < L.n; i++)
+      for (i64 k = A.rowptr[i]; k < A.rowptr[i + 1]; k++) {
+        if (A.col[k] != i) continue;
+        std::copy(A.val.begin() + k * b * b, A.val.begin() + (k + 1) * b * b, blk.begin());
+        block_regularize(b, blk.data(), regularize_coarse_dim);
+        for (int p = 0; p < b; p++)
+          for (int q = 0; q < b; q++) {
+            const i64 r = g2l[i * b + p], c = g2l[i * b + q];
+            if (r >= 0 && c >= 0) M[(size_t)r * cn + c] = blk[p * b + q];
+          }
+      }
+  }
   if (cn > 0 && !dense_invert(cn, M)) throw Error("coarsest level matrix is singular");
   // embed into the padded level numbering (identity permutation on the coarsest level)
   const i64 NP = L.npad * b;
@@ -783,6 +799,7 @@ void Amg::finalize()
   const bool elast = type.find("elast") != std::string::npos;
   const int dim = (type.find("2d") != std::string::npos) ? 2 : 3;
   const bool regularize = flags.flag("regularize_cmats", elast);        // elasticity_pc_impl.hpp:139, h1_impl.hpp:275-279
+  regularize_coarse_dim = (regularize && elast) ? (type.find("2d") != std::string::npos ? 2 : 3) : 0;
   CoarsenOptions copt;
   copt.max_per_row = (int)flags.num("sp_max_per_row", elast ? 1 + dim : 3);
   copt.min_frac = flags.num("sp_min_frac", dim == 3 ? 0.08 : 0.1);
@@ -1119,6 +1136,7 @@ void Amg::finalize_parallel()
   const bool elast = type.find("elast") != std::string::npos;
   const int dim = (type.find("2d") != std::string::npos) ? 2 : 3;
   const bool regularize = flags.flag("regularize_cmats", elast);
+  regularize_coarse_dim = (regularize && elast) ? (type.find("2d") != std::string::npos ? 2 : 3) : 0;
   const i64 ctr_nv = (i64)flags.num("b200_ctr_nv", 1000000);   // contract onto rank 0 once the GLOBAL level has at most this many vertices
   CoarsenOptions copt;
   copt.max_per_row = (int)flags.num("sp_max_per_row", elast ? 1 + dim : 3);

@@ -128,5 +128,7 @@ void host_transpose(const HostBsr &A, HostBsr &T);
 
 // dense.cpp: CalcPseudoInverseTryNormal(Mat<N,N>&) of the reference restated (utils_denseLA.hpp:1237-1569, utils_denseLA.cpp:458-555); m: n x n row-major, in place
 void block_pinv(int n, double *m);
+// dense.cpp: RegularizeMatrix of the elasticity preconditioners on one diagonal block of the coarsest matrix (elasticity_pc_impl.hpp:711-763)
+void block_regularize(int n, double *m, int dim);
 
 }  // namespace ngb

@@ -5,6 +5,7 @@
 //   CalcPseudoInverseWithTolNonZeroBlock  utils_denseLA.hpp:1474-1519               eigenvalues <= max(1e-12 * mean, 1e-20) are kernel
 // tests/test_ref_pin.py compares ngsamg_b200_block_pinv with the reference's own code (oracle/_ref) on regular, rank-deficient and
 // zero-row blocks: bit for bit where the direct inverse is taken, 1e-12 on the eigenvalue fall-back (LAPACK there, Jacobi rotations here).
+#include <algorithm>
 #include <cmath>
 #include <cstring>
 #include <vector>
@@ -105,7 +106,66 @@ void block_pinv(int n, double *m)
   for (int i = 0; i < k; i++) for (int j = 0; j < k; j++) m[idx[i] * n + idx[j]] = sub[i * k + j];
 }
 
+// RegularizeMatrix of the elasticity preconditioners, local branch (src/elasticity/elasticity_pc_impl.hpp:711-763), applied to every
+// diagonal block of the COARSEST matrix before it is inverted (amg_pc.cpp:861-862) when ngs_amg_regularize_cmats is set:
+//   3D, 6x6 blocks: RegTM<0,6,6> (utils_denseLA.hpp:1198-1234) -- eigenvalues <= max(1e-15, 1e-12 * largest) count as zero; the smallest
+//                   non-zero eigenvalue is added along every zero eigenvector; an entirely zero block becomes the identity
+//   2D, 3x3 blocks: a rotational diagonal entry with |m(2,2)| < 1e-8 is set to 1
+void block_regularize(int n, double *m, int dim)
+{
+  if (dim == 2) {
+    if (n == 3 && std::fabs(m[2 * 3 + 2]) < 1e-8) m[2 * 3 + 2] = 1.0;
+    return;
+  }
+  if (dim != 3 || n != 6) return;
+  // eigen-decomposition (cyclic Jacobi rotations; LAPACK in the reference), eigenvalues ascending, V rows = eigenvectors
+  std::vector<double> a(m, m + n * n), V((size_t)n * n, 0.0);
+  for (int i = 0; i < n; i++) V[i * n + i] = 1.0;
+  for (int sweep = 0; sweep < 100; sweep++) {
+    double off = 0;
+    for (int i = 0; i < n; i++) for (int j = i + 1; j < n; j++) off += a[i * n + j] * a[i * n + j];
+    if (off < 1e-300) break;
+    for (int p = 0; p < n; p++) for (int q = p + 1; q < n; q++) {
+      const double apq = a[p * n + q];
+      if (std::fabs(apq) < 1e-300) continue;
+      const double theta = (a[q * n + q] - a[p * n + p]) / (2.0 * apq);
+      const double tt = (theta >= 0 ? 1.0 : -1.0) / (std::fabs(theta) + std::sqrt(theta * theta + 1.0));
+      const double c = 1.0 / std::sqrt(tt * tt + 1.0), s = tt * c;
+      for (int r = 0; r < n; r++) { double x = a[r * n + p], y = a[r * n + q]; a[r * n + p] = c * x - s * y; a[r * n + q] = s * x + c * y; }
+      for (int r = 0; r < n; r++) { double x = a[p * n + r], y = a[q * n + r]; a[p * n + r] = c * x - s * y; a[q * n + r] = s * x + c * y; }
+      for (int r = 0; r < n; r++) { double x = V[p * n + r], y = V[q * n + r]; V[p * n + r] = c * x - s * y; V[q * n + r] = s * x + c * y; }
+    }
+  }
+  std::vector<int> order(n);
+  for (int i = 0; i < n; i++) order[i] = i;
+  std::sort(order.begin(), order.end(), [&](int x, int y) { return a[x * n + x] < a[y * n + y]; });
+  const double evmax = a[order[n - 1] * n + order[n - 1]];
+  const double eps = std::max(1e-15, 1e-12 * evmax);
+  double min_nzev = 0.0;
+  int nzero = 0;
+  for (int k = 0; k < n; k++) {
+    const double ev = a[order[k] * n + order[k]];
+    if (ev > eps) { min_nzev = ev; break; }
+    nzero++;
+  }
+  if (nzero < n) {
+    for (int l = 0; l < nzero; l++) {
+      const double *v = &V[(size_t)order[l] * n];
+      for (int i = 0; i < n; i++) for (int j = 0; j < n; j++) m[i * n + j] += min_nzev * v[i] * v[j];
+    }
+  } else {
+    for (int i = 0; i < n; i++) for (int j = 0; j < n; j++) m[i * n + j] = (i == j) ? 1.0 : 0.0;
+  }
+}
+
 }  // namespace ngb
+
+extern "C" int ngsamg_b200_block_regularize(int n, double *m, int dim)
+{
+  if (!m || n < 1 || n > 64) return 1;
+  ngb::block_regularize(n, m, dim);
+  return 0;
+}
 
 extern "C" int ngsamg_b200_block_pinv(int n, double *m)
 {

@@ -644,6 +644,55 @@ void orc_amg_galerkin(orc_amg *a, int l)
 /* coarsest level exact solve, amg_pc.cpp:843-928: cspm->InverseMatrix(free) with SPARSECHOLESKY
    (serial).  Restated as a dense Cholesky of the scalar-expanded free sub-matrix (exact up to
    rounding, like any direct solver).  returns 0 ok, 1 not positive definite */
+/* RegTM<0,6,6> (utils_denseLA.hpp:1198-1234): eigenvalues <= max(1e-15, 1e-12 * largest) count as zero, the smallest non-zero
+   eigenvalue is added along every zero eigenvector, an all-zero block becomes the identity. */
+static void reg_tm6(double *m)
+{
+  const int n = 6;
+  double a[36], ev[6], V[36];
+  memcpy(a, m, sizeof(a));
+  sym_eig(n, a, ev, V);
+  int order[6];
+  for (int i = 0; i < n; i++) order[i] = i;
+  for (int i = 0; i < n; i++)
+    for (int j = i + 1; j < n; j++)
+      if (ev[order[j]] < ev[order[i]]) { int t = order[i]; order[i] = order[j]; order[j] = t; }
+  double eps = 1e-12 * ev[order[n - 1]];
+  if (eps < 1e-15) eps = 1e-15;
+  double min_nzev = 0.0;
+  int nzero = 0;
+  for (int k = 0; k < n; k++) {
+    if (ev[order[k]] > eps) { min_nzev = ev[order[k]]; break; }
+    nzero++;
+  }
+  if (nzero < n) {
+    for (int l = 0; l < nzero; l++) {
+      const double *v = V + order[l] * n;
+      for (int i = 0; i < n; i++)
+        for (int j = 0; j < n; j++) m[i * n + j] += min_nzev * v[i] * v[j];
+    }
+  } else
+    for (int i = 0; i < n; i++)
+      for (int j = 0; j < n; j++) m[i * n + j] = (i == j) ? 1.0 : 0.0;
+}
+
+/* one diagonal block, VertexAMGPC<ElasticityAMGFactory<DIM>>::RegularizeMatrix, local branch (elasticity_pc_impl.hpp:711-763) */
+void orc_regularize_block(int n, double *m, int dim)
+{
+  if (dim == 2) { if (n == 3 && fabs(m[8]) < 1e-8) m[8] = 1.0; }
+  else if (dim == 3 && n == 6) reg_tm6(m);
+}
+
+/* RegularizeMatrix on the coarsest matrix before it is inverted (amg_pc.cpp:861-862), O.regularize_cmats */
+void orc_amg_regularize_coarse(orc_amg *a, int dim)
+{
+  orc_level *L = &a->lev[a->nlevels - 1];
+  const int bb = L->b * L->b;
+  for (i64 i = 0; i < L->n; i++)
+    for (i64 k = L->rp[i]; k < L->rp[i + 1]; k++)
+      if (L->ci[k] == i) orc_regularize_block(L->b, L->v + k * bb, dim);
+}
+
 int orc_amg_set_coarse_inv(orc_amg *a)
 {
   orc_level *L = &a->lev[a->nlevels - 1];

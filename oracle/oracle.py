@@ -61,6 +61,8 @@ def lib():
     L.orc_amg_set_smoother.restype = ci
     L.orc_amg_set_prol.argtypes = [vp, ci, i64, ci, i64p, i32p, f64p]
     L.orc_amg_galerkin.argtypes = [vp, ci]
+    L.orc_amg_regularize_coarse.argtypes = [vp, ci]
+    L.orc_regularize_block.argtypes = [ci, f64p, ci]
     L.orc_amg_set_coarse_inv.argtypes = [vp]
     L.orc_amg_set_coarse_inv.restype = ci
     L.orc_amg_smooth.argtypes = [vp, ci, f64p, f64p, f64p, ci, ci, ci, ci]
@@ -158,6 +160,13 @@ def calc_dinv(A, free=None, pinv=False, repl_diag=None):
     return d
 
 
+def regularize_block(m, dim):
+    """RegularizeMatrix on one diagonal block (elasticity_pc_impl.hpp:711-763): dim 3 -> RegTM<0,6,6>, dim 2 -> unit rotational entry"""
+    a = np.ascontiguousarray(m, np.float64).copy()
+    lib().orc_regularize_block(a.shape[0], a.reshape(-1), int(dim))
+    return a
+
+
 def gs_rhs(A, dinv, free, x, rhs, backwards):
     fm = None if free is None else np.ascontiguousarray(free, np.uint8)
     lib().orc_gs_rhs(A.nrows, A.bh, A.rowptr, A.col, A.val, dinv, _ptr(fm), x, rhs, int(backwards))
@@ -180,7 +189,9 @@ class OracleAMG:
     one smoother per level (the last level only has the exact coarse solve)."""
 
     def __init__(self, A, free, prols, sm_type="gs", sm_steps=1, sm_symm=False, pinv=False, omega=None,
-                 clev="inv"):
+                 clev="inv", regularize=None):
+        """pinv models ngs_amg_regularize_cmats for the smoothers; regularize (default: pinv on elasticity block sizes) is the other
+        half of that flag, RegularizeMatrix on the coarsest diagonal blocks before the inverse (amg_pc.cpp:861-862)"""
         L = lib()
         self.nlevels = len(prols) + 1
         self.h = L.orc_amg_new(self.nlevels)
@@ -199,6 +210,11 @@ class OracleAMG:
             if rc:
                 raise RuntimeError("oracle: singular diagonal block on level %d (rc=%d)" % (l, rc))
         self.has_cinv = False
+        cb = prols[-1].bw if len(prols) else A.bh
+        if regularize is None:
+            regularize = bool(pinv) and (cb == 6 or (cb == 3 and A.bh == 2))   # elast_3d: 6x6 coarse blocks; elast_2d: 2 -> 3
+        if regularize and clev == "inv":
+            L.orc_amg_regularize_coarse(self.h, 3 if cb == 6 else 2)     # 6x6 coarse blocks: 3D, 3x3: 2D
         if clev == "inv":
             rc = L.orc_amg_set_coarse_inv(self.h)
             if rc:

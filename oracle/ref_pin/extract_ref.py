@@ -36,6 +36,7 @@ FRAGMENTS = [
     # --- pseudo inverse of a diagonal block ----------------------------------------------------------------------
     ("la_reltol", "src/base/utils/utils_denseLA.hpp", r"^constexpr T RelZeroTol\(\)", "template", None),
     ("la_abstol", "src/base/utils/utils_denseLA.hpp", r"^constexpr T AbsZeroTol\(\)", "template", None),
+    ("la_regtm", "src/base/utils/utils_denseLA.hpp", r"^template<int IMIN, int N, int NN> INLINE void RegTM \(Mat<NN,NN,double> & m, double maxadd = -1\)", "line", None),
     ("la_nzblock", "src/base/utils/utils_denseLA.hpp", r"^CallOnNonZeroDiagonalBlock \(int const &n, TGETETR mat,", "template", None),
     ("la_nzblock_mat", "src/base/utils/utils_denseLA.hpp", r"^CallOnNonZeroDiagonalBlock \(Mat<N, N, TSCAL> &mat,", "template", None),
     ("la_trydirect_simple", "src/base/utils/utils_denseLA.cpp", r"^TryDirectInverse_simple \(FlatMatrix<TSCAL> A, LocalHeap & lh\)", "template", None),

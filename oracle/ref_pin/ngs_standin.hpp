@@ -276,6 +276,7 @@ public:
   FlatVector(size_t an, T *p) : n(an), d(p) {}
   FlatVector(size_t an, ngcore::LocalHeap &lh) : n(an), d((T *)ngcore::heap_alloc(lh, sizeof(T) * an)) {}
   FlatVector(const FlatVector &) = default;
+  void AssignMemory(size_t an, T *p) { n = an; d = p; }
   size_t Size() const { return n; }
   T *Data() const { return d; }
   T &operator()(size_t i) const { return d[i]; }

@@ -97,6 +97,25 @@ INLINE void LapackEigenValuesSymmetricLH(ngcore::LocalHeap &, FlatMatrix<double>
     for (int k = 0; k < n; k++) evecs(i, k) = V[order[i] * n + k];
   }
 }
+// owning dense matrix / vector (RegTM keeps static work arrays of these)
+template <class T> class Matrix : public FlatMatrix<T> {
+  std::vector<T> store;
+
+public:
+  Matrix(size_t h, size_t w) : FlatMatrix<T>(), store(h * w) { this->Assign(FlatMatrix<T>(h, w, store.data())); }
+};
+template <class T> class Vector : public FlatVector<T> {
+  std::vector<T> store;
+
+public:
+  explicit Vector(size_t n) : FlatVector<T>(), store(n) { this->AssignMemory(n, store.data()); }
+};
+INLINE void TimedLapackEigenValuesSymmetric(FlatMatrix<double> M, FlatVector<double> evals, FlatMatrix<double> evecs) {
+  ngcore::LocalHeap lh(0, "eig");
+  LapackEigenValuesSymmetricLH(lh, M, evals, evecs);
+}
+template <int N> INLINE void SetIdentity(Mat<N, N> &m) { for (int i = 0; i < N; i++) for (int j = 0; j < N; j++) m(i, j) = (i == j) ? 1.0 : 0.0; }
+template <int H, int W> INLINE Mat<H, W> &operator*=(Mat<H, W> &m, double s) { for (int i = 0; i < H * W; i++) m.v[i] *= s; return m; }
 }  // namespace ngbla
 
 namespace ngstd {

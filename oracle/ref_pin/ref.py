@@ -148,6 +148,15 @@ def pinv_block(m):
     return a
 
 
+def regularize_block6(m):
+    """RegTM<0,6,6> (utils_denseLA.hpp:1198-1234) on one block"""
+    L = lib()
+    L.ref_regularize6.argtypes = [f64p]
+    a = np.ascontiguousarray(m, np.float64).copy()
+    _check(L.ref_regularize6(a.reshape(-1)))
+    return a
+
+
 class RefAMG:
     """AMGMatrix of the reference: coarse matrices by TransposeSPMImpl + RestrictMatrix from injected prolongations, GSS3 per
     level (ProxySmoother around it for sm_steps > 1 / sm_symm), cycles by AMGMatrix::SmoothV / SmoothW / SmoothBS.  The exact

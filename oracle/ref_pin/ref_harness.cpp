@@ -35,6 +35,7 @@ template <> struct strip_vec<Vec<1, double>> { typedef double type; };
 // ---- pseudo inverse of a diagonal block (utils_denseLA.hpp:93-117, 1237-1569, utils_denseLA.cpp:458-555) --------------
 #include "../_ref/frag/la_reltol.inc"
 #include "../_ref/frag/la_abstol.inc"
+#include "../_ref/frag/la_regtm.inc"
 #include "../_ref/frag/la_nzblock.inc"
 #include "../_ref/frag/la_nzblock_mat.inc"
 template <class TSCAL> bool TryDirectInverse_Lapack(FlatMatrix<TSCAL>, LocalHeap &) { throw Exception("ref harness: blocks of 50+ rows need LAPACK"); }
@@ -494,6 +495,16 @@ int ref_pinv(int n, double *m) {
     else if (n == 3) pinv_block<3>(m);
     else if (n == 6) pinv_block<6>(m);
     else throw Exception("ref_pinv: unsupported block size");
+  });
+}
+
+// RegTM<0,6,6> on one 6 x 6 block: what RegularizeMatrix (elasticity_pc_impl.hpp:734-763) applies to the coarsest diagonal blocks
+int ref_regularize6(double *m) {
+  return guarded([&] {
+    Mat<6, 6> blk;
+    std::memcpy((void *)&blk, m, sizeof(double) * 36);
+    RegTM<0, 6, 6>(blk);
+    std::memcpy(m, (const void *)&blk, sizeof(double) * 36);
   });
 }
 

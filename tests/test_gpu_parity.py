@@ -449,3 +449,20 @@ def test_w_and_bs_cycles(cycle, problem):
     x2 = np.zeros(n)
     pc.Mult(b2, x2)
     assert abs(np.dot(x, b2) - np.dot(b, x2)) < 1e-10 * abs(np.dot(x, b2))
+
+
+def test_regularised_coarse_solve_with_a_lone_vertex():
+    """ngs_amg_regularize_cmats (default for elast_3d): RegularizeMatrix on the coarsest diagonal blocks (elasticity_pc_impl.hpp:734-763)
+    before the exact coarse solve.  One coarse vertex is stripped of its rotational stiffness, so the coarsest matrix is singular
+    without the regularisation; with it the V-cycle must match the oracle, and switching the flag off must fail loudly."""
+    p, A = elasticity(5, 4, 4)
+    P = host_hierarchy(A, p["free"], p["xyz"], elast=True, max_coarse=4, max_per_row=4)[0]
+    v = P.val.reshape(-1, 3, 6).copy()
+    v[P.col == 0, :, 3:] = 0.0
+    P0 = ng.SparseMatrix(P.nrows, P.ncols, 3, 6, P.rowptr, P.col, v.reshape(-1))
+    pc = ng.elast_3d(A, p["free"], vertex_xyz=p["xyz"], prolongations=[P0])
+    amg = O.OracleAMG(to_oracle(A), p["free"], [to_oracle(P0)], pinv=True)
+    b = rand(77, p["n"] * 3)
+    assert rel(pc * b, amg.apply(b)) < 1e-9
+    with pytest.raises(Exception):
+        ng.elast_3d(A, p["free"], vertex_xyz=p["xyz"], prolongations=[P0], ngs_amg_regularize_cmats=False)

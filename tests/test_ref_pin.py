@@ -365,3 +365,56 @@ def test_pinv_smoothers_through_the_hierarchy():
         assert np.array_equal(oa.level_dinv(l), ra.level_dinv(l)), l
     b = rand(21, A.nrows * A.bh)
     assert rel(oa.apply(b), ra.apply(b)) < 1e-13
+
+
+def product_regularize(M, dim):
+    import ctypes as C
+    from ngsamg_b200 import _lib
+    a = np.ascontiguousarray(M, np.float64).copy()
+    L = _lib.lib()
+    L.ngsamg_b200_block_regularize.argtypes = [C.c_int, C.c_void_p, C.c_int]
+    assert L.ngsamg_b200_block_regularize(a.shape[0], a.ctypes.data_as(C.c_void_p), dim) == 0
+    return a
+
+
+@needs_ref
+def test_coarse_regularisation_vs_reference_code():
+    """RegularizeMatrix on the coarsest diagonal blocks (ngs_amg_regularize_cmats, elasticity_pc_impl.hpp:734-763 -> RegTM<0,6,6>,
+    utils_denseLA.hpp:1198-1234): oracle and product (csrc/dense.cpp) vs the reference's own code"""
+    rng = np.random.default_rng(3)
+    Q, _ = np.linalg.qr(rng.standard_normal((6, 6)))
+    X = rng.standard_normal((6, 6))
+    cases = {"regular (left alone)": X @ X.T + 6 * np.eye(6),
+             "three zero eigenvalues (a lone vertex: no rotational stiffness)": Q @ np.diag([0, 0, 0, 1.5, 2.0, 7.0]) @ Q.T,
+             "translations only": np.diag([3.0, 2.0, 5.0, 0, 0, 0]),
+             "one tiny eigenvalue": Q @ np.diag([1e-14, 1.0, 2.0, 3.0, 4.0, 5.0]) @ Q.T,
+             "zero block becomes the identity": np.zeros((6, 6))}
+    for name, M in cases.items():
+        ref = R.regularize_block6(M)
+        for who, got in (("oracle", O.regularize_block(M, 3)), ("product", product_regularize(M, 3))):
+            assert np.abs(ref - got).max() <= 1e-12 * max(np.abs(ref).max(), 1.0), (who, name)
+        if name.startswith("regular"):
+            assert np.array_equal(ref, M)
+        if name.startswith("translations"):
+            assert np.allclose(ref, np.diag([3.0, 2.0, 5.0, 2.0, 2.0, 2.0]), atol=1e-12)     # smallest non-zero eigenvalue on the kernel
+    # 2D: unit rotational entry (elasticity_pc_impl.hpp:721-728); no reference fragment needed for a one-liner, oracle == product
+    M2 = np.diag([2.0, 3.0, 1e-9])
+    assert O.regularize_block(M2, 2)[2, 2] == 1.0 == product_regularize(M2, 2)[2, 2]
+    M3 = np.diag([2.0, 3.0, 1e-3])
+    assert np.array_equal(O.regularize_block(M3, 2), M3) and np.array_equal(product_regularize(M3, 2), M3)
+
+
+def test_regularised_coarse_solve_handles_lone_vertices():
+    """an elasticity hierarchy whose coarsest level has a vertex without rotational stiffness: singular without RegularizeMatrix,
+    solvable with it (what ngs_amg_regularize_cmats is for)"""
+    p, A, prols = hierarchy("elasticity")
+    P = prols[0]
+    # cut the rotational columns of one coarse vertex out of the first prolongation -> its 6x6 diagonal block loses rank 3
+    v = P.val.reshape(-1, 3, 6).copy()
+    v[P.col == 0, :, 3:] = 0.0
+    P0 = O.Bsr(P.nrows, P.ncols, 3, 6, P.rowptr, P.col, v)
+    with pytest.raises(RuntimeError):
+        O.OracleAMG(A, p["free"], [P0], pinv=True, regularize=False)
+    oa = O.OracleAMG(A, p["free"], [P0], pinv=True)                     # regularize defaults to on with pinv on 6x6 coarse blocks
+    x = oa.apply(rand(31, A.nrows * 3))
+    assert np.isfinite(x).all() and np.abs(x).max() > 0
