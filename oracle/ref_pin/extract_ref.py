@@ -67,6 +67,11 @@ FRAGMENTS = [
     ("amg_smoothbs", "src/base/solve/amg_matrix.cpp", r"^\s*void AMGMatrix :: SmoothBS \(", "line", None),
     ("amg_smoothv", "src/base/solve/amg_matrix.cpp", r"^\s*void AMGMatrix :: SmoothV \(", "line", None),
     ("amg_smoothvfrom", "src/base/solve/amg_matrix.cpp", r"^\s*void AMGMatrix :: SmoothVFromLevel \(", "line", None),
+    ("amg_smooth", "src/base/solve/amg_matrix.hpp", r"^\s*INLINE void Smooth \(BaseVector & x, const BaseVector & b\) const", "line", None),
+    ("amg_mult", "src/base/solve/amg_matrix.cpp", r"^\s*void AMGMatrix :: Mult \(const BaseVector & b, BaseVector & x\) const", "line", None),
+    ("amg_multtrans", "src/base/solve/amg_matrix.cpp", r"^\s*void AMGMatrix :: MultTrans \(const BaseVector & b, BaseVector & x\) const", "line", None),
+    ("amg_multadd", "src/base/solve/amg_matrix.cpp", r"^\s*void AMGMatrix :: MultAdd \(double s, const BaseVector & b, BaseVector & x\) const", "line", None),
+    ("amg_multtransadd", "src/base/solve/amg_matrix.cpp", r"^\s*void AMGMatrix :: MultTransAdd \(double s, const BaseVector & b, BaseVector & x\) const", "line", None),
     # ===== multi-rank path (compiled against the threaded MPI stand-in, ngs_standin_mpi.hpp) =======================
     # --- small utilities of the reference's own tree ---------------------------------------------------------------
     ("u_find_sorted", "src/base/utils/utils_arrays_tables.hpp", r"^INLINE size_t find_in_sorted_array \(const T & elem, FlatArray<T> a\)$", "template", None),

@@ -232,6 +232,20 @@ class RefAMG:
         _check(lib().ref_amg_apply(self.h, {"V": 0, "W": 1, "BS": 2}[cycle], np.ascontiguousarray(b, np.float64), x))
         return x
 
+    def mult(self, b, x, cycle="V", trans=False):
+        """AMGMatrix::Mult / MultTrans: x = C b (x is overwritten)"""
+        L = lib()
+        L.ref_amg_mult.argtypes = [C.c_void_p, C.c_int, C.c_int, f64p, f64p]
+        _check(L.ref_amg_mult(self.h, {"V": 0, "W": 1, "BS": 2}[cycle], int(trans), np.ascontiguousarray(b, np.float64), x))
+        return x
+
+    def mult_add(self, s, b, x, cycle="V", trans=False):
+        """AMGMatrix::MultAdd / MultTransAdd: x += s * C b"""
+        L = lib()
+        L.ref_amg_mult_add.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_double, f64p, f64p]
+        _check(L.ref_amg_mult_add(self.h, {"V": 0, "W": 1, "BS": 2}[cycle], int(trans), float(s), np.ascontiguousarray(b, np.float64), x))
+        return x
+
     def pcg(self, rhs, tol=1e-8, maxsteps=200, cycle="V"):
         """CG (harness glue, NGSolve's CGSolver restated like the oracle's) preconditioned with the reference's cycle"""
         u, errs, it = np.zeros(self.n0), np.zeros(maxsteps + 2), C.c_int(0)

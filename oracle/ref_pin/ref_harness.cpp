@@ -201,6 +201,12 @@ public:
   int n_levels = 0;
   bool drops_out = false, has_crs_inv = false;
   shared_ptr<BaseMatrix> crs_inv, crs_mat;
+  int vwb = 0;
+#include "../_ref/frag/amg_smooth.inc"
+  void Mult(const BaseVector &b, BaseVector &x) const;
+  void MultTrans(const BaseVector &b, BaseVector &x) const;
+  void MultAdd(double s, const BaseVector &b, BaseVector &x) const;
+  void MultTransAdd(double s, const BaseVector &b, BaseVector &x) const;
   void SmoothV(BaseVector &x, const BaseVector &b) const;
   void SmoothW(BaseVector &x, const BaseVector &b) const;
   void SmoothBS(BaseVector &x, const BaseVector &b) const;
@@ -210,6 +216,10 @@ public:
 #include "../_ref/frag/amg_smoothbs.inc"
 #include "../_ref/frag/amg_smoothv.inc"
 #include "../_ref/frag/amg_smoothvfrom.inc"
+#include "../_ref/frag/amg_mult.inc"
+#include "../_ref/frag/amg_multtrans.inc"
+#include "../_ref/frag/amg_multadd.inc"
+#include "../_ref/frag/amg_multtransadd.inc"
 
 // dense coarse inverse handed in by the caller (the reference uses NGSolve's sparse Cholesky, which is not in its tree)
 class DenseInverse : public BaseMatrix {
@@ -595,6 +605,40 @@ int ref_amg_smooth(void *hv, int l, double *x, const double *b, double *res, int
     else S.Smooth(vx, vb, vr, res_updated != 0, update_res != 0, x_zero != 0);
     std::memcpy(x, vx.FVDouble().Data(), sizeof(double) * nb);
     std::memcpy(res, vr.FVDouble().Data(), sizeof(double) * nb);
+  });
+}
+
+// AMGMatrix::MultAdd / MultTransAdd (amg_matrix.cpp:385-393) with SetVWB(cycle): x += s * C b; trans != 0 takes the Trans entry
+int ref_amg_mult_add(void *hv, int cycle, int trans, double s, const double *b, double *x) {
+  AmgH *a = (AmgH *)hv;
+  return guarded([&] {
+    LevelH &L = a->lev[0];
+    const size_t n = L.A->m->Height(), nb = n * (size_t)L.b;
+    BaseVector vx(n, L.b), vb(n, L.b);
+    std::memcpy(vb.FVDouble().Data(), b, sizeof(double) * nb);
+    std::memcpy(vx.FVDouble().Data(), x, sizeof(double) * nb);
+    a->amg.vwb = cycle;
+    if (trans) a->amg.MultTransAdd(s, vb, vx);
+    else a->amg.MultAdd(s, vb, vx);
+    a->amg.vwb = 0;
+    std::memcpy(x, vx.FVDouble().Data(), sizeof(double) * nb);
+  });
+}
+
+// AMGMatrix::Mult / MultTrans (amg_matrix.cpp:377-383)
+int ref_amg_mult(void *hv, int cycle, int trans, const double *b, double *x) {
+  AmgH *a = (AmgH *)hv;
+  return guarded([&] {
+    LevelH &L = a->lev[0];
+    const size_t n = L.A->m->Height(), nb = n * (size_t)L.b;
+    BaseVector vx(n, L.b), vb(n, L.b);
+    std::memcpy(vb.FVDouble().Data(), b, sizeof(double) * nb);
+    std::memcpy(vx.FVDouble().Data(), x, sizeof(double) * nb);       // Mult must overwrite whatever is in x
+    a->amg.vwb = cycle;
+    if (trans) a->amg.MultTrans(vb, vx);
+    else a->amg.Mult(vb, vx);
+    a->amg.vwb = 0;
+    std::memcpy(x, vx.FVDouble().Data(), sizeof(double) * nb);
   });
 }
 

@@ -418,3 +418,18 @@ def test_regularised_coarse_solve_handles_lone_vertices():
     oa = O.OracleAMG(A, p["free"], [P0], pinv=True)                     # regularize defaults to on with pinv on 6x6 coarse blocks
     x = oa.apply(rand(31, A.nrows * 3))
     assert np.isfinite(x).all() and np.abs(x).max() > 0
+
+
+@needs_ref
+def test_mult_quartet_vs_reference_code():
+    """AMGMatrix::Mult / MultTrans / MultAdd / MultTransAdd and the Smooth dispatch on the cycle type (amg_matrix.hpp:37-43,
+    amg_matrix.cpp:377-393): Mult overwrites x, MultAdd adds s * C b to x WITHOUT zeroing it, the Trans variants are aliases"""
+    p, A, prols = hierarchy("poisson")
+    oa, ra = O.OracleAMG(A, p["free"], prols, clev="none"), R.RefAMG(A, p["free"], prols, coarse_inv=False)
+    b, x0 = rand(41, A.nrows), rand(42, A.nrows)
+    for cyc in ("V", "W", "BS"):
+        ref = oa.apply(b, cyc)
+        for trans in (False, True):
+            assert np.array_equal(ra.mult(b, x0.copy(), cyc, trans), ref)
+            assert np.array_equal(ra.mult_add(-0.7, b, x0.copy(), cyc, trans), x0 + (-0.7) * ref)
+    assert np.array_equal(oa.apply_add(-0.7, b, x0.copy()), ra.mult_add(-0.7, b, x0.copy()))
