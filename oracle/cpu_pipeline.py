@@ -98,17 +98,13 @@ def build(parts, b=1, elast=False, ctr_nv=2000, max_coarse=50, max_levels=10, pi
     import scipy.sparse as sp
     bb = cur[0].bh
     N = int(max(int(m.max()) for m in maps if len(m)) + 1)
-    acc = sp.csr_matrix((N * bb, N * bb))
     mxyz = None
     for r in range(R):
-        C = _to_o(cur[r]).to_scipy().tocoo()
-        sd = (maps[r][:, None] * bb + np.arange(bb)[None, :]).ravel()
-        acc = acc + sp.coo_matrix((C.data, (sd[C.row], sd[C.col])), shape=(N * bb, N * bb)).tocsr()
         if elast and cxyz[r] is not None:
             if mxyz is None:
                 mxyz = np.zeros((N, 3))
             mxyz[maps[r]] = cxyz[r]
-    merged = O.Bsr.from_scipy(acc, bb, bb)
+    merged = OP.merge_contracted([_to_o(c) for c in cur], [np.asarray(m, np.int64) for m in maps], N, bb)
     nested, curm, cx = [], _to_p(merged), mxyz
     while curm.nrows > max_coarse and len(nested) + len(prols) + 2 < max_levels + 1:
         P, vmap, cxn = ng.coarsen(curm, None, cx, bcoarse=curm.bh, max_per_row=(4 if elast else 3))

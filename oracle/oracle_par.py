@@ -349,6 +349,36 @@ class HybridLevel:
         return out
 
 
+def merge_contracted(A, maps, N, b):
+    """CtrMap::DoAssembleMatrix (dof_contract.cpp:557-727): the master remaps the members' rows through the dof maps, merges the
+    (sorted) column lists -- a STRUCTURAL union, entries that cancel to zero stay in the pattern -- and sums coinciding entries,
+    members in group order.  (scipy's csr + csr would drop the cancelled entries, hence the single COO pass.)"""
+    rows, cols, vals = [], [], []
+    for r in range(len(A)):
+        C = A[r].to_scipy().tocoo() if A[r].nnz else None
+        if C is None:
+            continue
+        # to_scipy keeps every stored scalar of every stored block, explicit zeros included
+        rp, ci, bb = A[r].rowptr, A[r].col, A[r].bh
+        br = np.repeat(np.arange(A[r].nrows), np.diff(rp))
+        sd_r = (maps[r][br][:, None, None] * bb + np.arange(bb)[None, :, None])
+        sd_c = (maps[r][ci][:, None, None] * bb + np.arange(bb)[None, None, :])
+        rows.append(np.broadcast_to(sd_r, (len(ci), bb, bb)).ravel())
+        cols.append(np.broadcast_to(sd_c, (len(ci), bb, bb)).ravel())
+        vals.append(A[r].val.reshape(-1))
+    if not rows:
+        return O.Bsr(N, N, b, b, np.zeros(N + 1, np.int64), np.zeros(0, np.int32), np.zeros(0))
+    nb = N * b
+    keys = [rw.astype(np.int64) * nb + cl for rw, cl in zip(rows, cols)]
+    ukeys = np.unique(np.concatenate(keys))                     # the merged pattern: sorted union, nothing dropped
+    acc = np.zeros(len(ukeys))
+    for k, v in zip(keys, vals):                                # rvs = 0; rvs[pos] += member values, members in group (= rank) order
+        acc[np.searchsorted(ukeys, k)] += v                     # a member's dof map is injective: no duplicate positions inside one member
+    m = sp.csr_matrix((acc, (ukeys // nb, ukeys % nb)), shape=(nb, nb))
+    m.sort_indices()
+    return O.Bsr.from_scipy(m, b, b)
+
+
 class OracleParAMG:
     """AMGMatrix on a distributed hierarchy.
     levels[l] = dict(A=[Bsr per rank], free=[mask or None per rank], peers=[...], ex=[...], P=[Bsr per rank]) for l < npar
@@ -376,12 +406,7 @@ class OracleParAMG:
         self.maps = [np.asarray(m, np.int64) for m in ctr_maps]
         N = int(max(int(m.max()) for m in self.maps if len(m)) + 1)
         b = self.b_ctr
-        acc = sp.csr_matrix((N * b, N * b))
-        for r in range(self.R):
-            C = _expand(A[r]).tocoo()
-            sd = (self.maps[r][:, None] * b + np.arange(b)[None, :]).ravel()
-            acc = acc + sp.coo_matrix((C.data, (sd[C.row], sd[C.col])), shape=(N * b, N * b)).tocsr()
-        self.A_merged = O.Bsr.from_scipy(acc, b, b)
+        self.A_merged = merge_contracted(A, self.maps, N, b)
         self.N = N
         self.nested = O.OracleAMG(self.A_merged, nested_free, nested_prols, pinv=pinv, sm_steps=sm_steps, sm_symm=sm_symm)
 

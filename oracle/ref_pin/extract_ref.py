@@ -94,6 +94,16 @@ FRAGMENTS = [
     ("dcc_buffer_m", "src/base/linalg/dcc_map.cpp", r"^BufferM \(BaseVector & vec\) const", "template", None),
     ("dcc_apply_g", "src/base/linalg/dcc_map.cpp", r"^ApplyG \(BaseVector & vec\) const", "template", None),
     ("dcc_masters", "src/base/linalg/dcc_map.cpp", r"^CalcDOFMasters \(\)$", "template", r"^BasicDCCMap<TSCAL>::"),
+    # --- CtrMap: contraction of a distributed level onto the group master ---------------------------------------------
+    ("ctr_timer_f2c", "src/base/coarsening/dof_contract.cpp", r"timer_hack_ctr_f2c \(\)", "line", None),
+    ("ctr_timer_c2f", "src/base/coarsening/dof_contract.cpp", r"timer_hack_ctr_c2f \(\)", "line", None),
+    ("ctr_f2c", "src/base/coarsening/dof_contract.cpp", r"^void CtrMap<TV> :: TransferF2C \(", "template", None),
+    ("ctr_addf2c", "src/base/coarsening/dof_contract.cpp", r"^void CtrMap<TV> :: AddF2C \(", "template", None),
+    ("ctr_c2f", "src/base/coarsening/dof_contract.cpp", r"^void CtrMap<TV> :: TransferC2F \(", "template", None),
+    ("ctr_addc2f", "src/base/coarsening/dof_contract.cpp", r"^void CtrMap<TV> :: AddC2F \(", "template", None),
+    ("ctr_setup_mpi", "src/base/coarsening/dof_contract.cpp", r"^void CtrMap<TV> :: SetUpMPIStuff \(\)", "template", None),
+    ("ctr_timer_mat", "src/base/coarsening/dof_contract.cpp", r"timer_hack_ctrmat \(int nr\)", "line", None),
+    ("ctr_assemble", "src/base/coarsening/dof_contract.cpp", r"^CtrMap<TV> :: DoAssembleMatrix \(", "template", None),
     # --- hybrid matrix: A = M + G ----------------------------------------------------------------------------------
     ("hyb_decompose", "src/base/linalg/hybrid_matrix.cpp", r"^DecomposeSparseMatrixHybrid \(shared_ptr<SparseMatrix<TM>> anA,", "template", None),
     ("hyb_multadd", "src/base/linalg/hybrid_matrix.cpp", r"^MultAdd \(double s, const BaseVector & x, BaseVector & y\) const", "template", None),

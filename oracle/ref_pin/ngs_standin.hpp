@@ -125,6 +125,13 @@ public:
   void SetSize0() { store.clear(); sync(); }
   void Append(const T &v) { store.push_back(v); sync(); }
 };
+template <int N, class T = int> struct IVec {
+  T v[N];
+  IVec() {}
+  IVec(std::initializer_list<T> l) { int i = 0; for (auto e : l) v[i++] = e; }
+  T &operator[](int i) { return v[i]; }
+  const T &operator[](int i) const { return v[i]; }
+};
 template <class T, int N> class ArrayMem : public Array<T> {
 public:
   ArrayMem() = default;
@@ -327,6 +334,7 @@ public:
     if (stat == CUMULATED) { if (parallel) throw Exception("BaseVector::Distribute on a cumulated parallel vector"); stat = DISTRIBUTED; }
   }
   BaseVector *GetLocalVector() const { return const_cast<BaseVector *>(this); }
+  void *Memory() const { return const_cast<double *>(store.data()); }
   BaseVector &operator+=(const BaseVector &o) { for (size_t i = 0; i < store.size(); i++) store[i] += o.store[i]; return *this; }
   void SetParallelStatus(PARALLEL_STATUS s) const { stat = s; }
   PARALLEL_STATUS GetParallelStatus() const { return stat; }
@@ -460,6 +468,8 @@ template <class F> INLINE void MergeArrays(FlatArray<int *> ptrs, FlatArray<int>
 
 // sort keys ascending, move vals along
 template <class T> INLINE void QuickSort(FlatArray<T> a) { std::sort(a.begin(), a.end()); }
+// index sort: afterwards a[idx[0]] <= a[idx[1]] <= ... (a itself is untouched)
+template <class T> INLINE void QuickSortI(FlatArray<T> a, FlatArray<int> idx) { std::stable_sort(idx.begin(), idx.end(), [&](int x, int y) { return a[x] < a[y]; }); }
 template <class T, class S> INLINE void BubbleSort(FlatArray<T> keys, FlatArray<S> vals) {
   for (size_t i = 0; i + 1 < keys.Size(); i++)
     for (size_t j = i + 1; j < keys.Size(); j++)

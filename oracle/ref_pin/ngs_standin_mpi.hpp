@@ -77,8 +77,21 @@ public:
 };
 
 enum NG_MPI_Op { NG_MPI_SUM };
-struct NG_MPI_Datatype { size_t bytes; };
-template <class T> INLINE NG_MPI_Datatype GetMPIType() { return NG_MPI_Datatype{sizeof(T)}; }
+// element size, plus (for NG_MPI_Type_indexed with unit block lengths) the element displacements of a gather type
+struct NG_MPI_Datatype {
+  size_t bytes = 0;
+  std::shared_ptr<std::vector<int>> displs;
+};
+template <class T> INLINE NG_MPI_Datatype GetMPIType() { return NG_MPI_Datatype{sizeof(T), nullptr}; }
+INLINE void NG_MPI_Type_indexed(size_t count, const int *blocklens, const int *displs, NG_MPI_Datatype old, NG_MPI_Datatype *out) {
+  for (size_t i = 0; i < count; i++) if (blocklens[i] != 1) throw Exception("MPI stand-in: indexed types with unit blocks only");
+  out->bytes = old.bytes;
+  out->displs = std::make_shared<std::vector<int>>(displs, displs + count);
+}
+INLINE void NG_MPI_Type_commit(NG_MPI_Datatype *) {}
+INLINE void NG_MPI_Type_free(NG_MPI_Datatype *) {}
+struct NG_MPI_Status {};
+#define NG_MPI_STATUS_IGNORE ((ngcore::NG_MPI_Status *) nullptr)
 constexpr int NG_MPI_TAG_AMG = 1120;
 
 struct MPIRequest {
@@ -128,6 +141,8 @@ public:
     return NG_MPI_REQUEST_NULL;
   }
   template <class OBJ> void Recv(std::shared_ptr<OBJ> &o, int src, int tag) const { o = std::static_pointer_cast<OBJ>(w->get_obj(src, rank, tag)); }
+  template <class OBJ> void Send(const OBJ &o, int dest, int tag) const { w->put_obj(rank, dest, tag, std::make_shared<OBJ>(o)); }
+  template <class T> void Recv(FlatArray<T> a, int src, int tag) const { w->get(src, rank, tag, a.Data(), a.Size() * sizeof(T)); }
 };
 typedef NgMPI_Comm NgsAMG_Comm;
 
@@ -138,6 +153,34 @@ INLINE void NG_MPI_Recv_init(void *buf, size_t count, NG_MPI_Datatype t, int src
   *req = new MPIRequest{MPIRequest::RECV, buf, count * t.bytes, src, tag, c.rank, c.w, false, true};
 }
 INLINE void NG_MPI_Startall(size_t n, NG_MPI_Request *reqs) { for (size_t i = 0; i < n; i++) start_request(reqs[i]); }
+
+// blocking / immediate raw sends and receives; a send with an indexed type gathers `count` x (the listed elements) first
+INLINE std::vector<char> pack_typed(const void *buf, size_t count, const NG_MPI_Datatype &t) {
+  if (!t.displs) return std::vector<char>((const char *)buf, (const char *)buf + count * t.bytes);
+  std::vector<char> out;
+  out.reserve(count * t.displs->size() * t.bytes);
+  for (size_t c = 0; c < count; c++)
+    for (int d : *t.displs) out.insert(out.end(), (const char *)buf + size_t(d) * t.bytes, (const char *)buf + size_t(d + 1) * t.bytes);
+  return out;
+}
+INLINE void NG_MPI_Send(const void *buf, size_t count, NG_MPI_Datatype t, int dest, int tag, const NgMPI_Comm &c) {
+  auto msg = pack_typed(buf, count, t);
+  c.w->put(c.rank, dest, tag, msg.data(), msg.size());
+}
+INLINE void NG_MPI_Isend(const void *buf, size_t count, NG_MPI_Datatype t, int dest, int tag, const NgMPI_Comm &c, NG_MPI_Request *req) {
+  NG_MPI_Send(buf, count, t, dest, tag, c);      // eager
+  *req = NG_MPI_REQUEST_NULL;
+}
+INLINE void NG_MPI_Recv(void *buf, size_t count, NG_MPI_Datatype t, int src, int tag, const NgMPI_Comm &c, NG_MPI_Status *) {
+  if (t.displs) throw Exception("MPI stand-in: receive into an indexed type");
+  c.w->get(src, c.rank, tag, buf, count * t.bytes);
+}
+// completes the active request with the LOWEST index (real MPI: whichever arrives first -- the stand-in is deterministic)
+INLINE void NG_MPI_Waitany(int n, NG_MPI_Request *reqs, int *index, NG_MPI_Status *) {
+  for (int i = 0; i < n; i++)
+    if (reqs[i]) { wait_request(reqs[i]); *index = i; return; }
+  *index = -1;
+}
 
 // ---- tables ---------------------------------------------------------------------------------------------------------
 template <class T> class Table {

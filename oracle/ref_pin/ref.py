@@ -349,10 +349,11 @@ class RefHybridLevel:
 
 class RefParAMG:
     """The multi-rank preconditioner run by the reference's own code: per rank an AMGMatrix (SmoothV) over distributed levels with
-    HybridGSSmoother and ProlMap, R ranks = R host threads.  Same arguments as oracle_par.OracleParAMG.  Glue (not reference
-    code): the local Galerkin products are the reference's RestrictMatrix, but the merged matrix of the contracted level is
-    assembled like the oracle does (CtrMap::DoAssembleMatrix restated), the gather / scatter around the serial coarse hierarchy
-    restates CtrMap::TransferF2C / TransferC2F for one group, and the CG loop restates NGSolve's CGSolver."""
+    HybridGSSmoother and ProlMap, R ranks = R host threads.  Same arguments as oracle_par.OracleParAMG.  The local Galerkin
+    products are the reference's RestrictMatrix, the merged matrix of the contracted level its CtrMap::DoAssembleMatrix, the
+    gather / scatter around the serial coarse hierarchy its CtrMap::TransferF2C / TransferC2F (one group, master rank 0).
+    Glue (not reference code): where the contraction sits (plugged in as the coarse solve instead of being a DOFMap step with
+    ranks dropping out) and the CG loop (NGSolve's CGSolver restated)."""
 
     def __init__(self, A0, free0, peers0, ex0, prols, halos, ctr_maps, nested_prols, pinv=False, nested_free=None, sm_steps=1,
                  sm_symm=False, overlap=True):
@@ -365,7 +366,9 @@ class RefParAMG:
         L.ref_paramg_set_matrix.argtypes = [vp, ci, i64, ci, i64p, i32p, f64p, vp]
         L.ref_paramg_set_halo.argtypes = [vp, ci, ci, ci, i32p, i64p, i32p]
         L.ref_paramg_set_prol.argtypes = [vp, ci, ci, i64, ci, i64p, i32p, f64p]
-        L.ref_paramg_set_contraction.argtypes = [vp, ci, i64, i64p, i64, vp]
+        L.ref_paramg_set_contraction.argtypes = [vp, ci, i64, i64p, i64]
+        L.ref_paramg_merged_matrix.argtypes, L.ref_paramg_merged_matrix.restype = [vp], vp
+        L.ref_paramg_set_nested.argtypes = [vp, vp]
         L.ref_paramg_setup.argtypes = [vp, ci, ci, ci]
         L.ref_paramg_apply.argtypes = [vp, pp, pp]
         L.ref_paramg_mult.argtypes = [vp, pp, pp]
@@ -380,7 +383,7 @@ class RefParAMG:
             fm = None if free0[r] is None else np.ascontiguousarray(free0[r], np.uint8)
             A = A0[r]
             _check(L.ref_paramg_set_matrix(self.h, r, A.nrows, A.bh, A.rowptr, A.col, A.val, None if fm is None else fm.ctypes.data_as(vp)))
-        for l in range(self.npar):
+        for l in range(self.npar + 1):
             peers, ex = (peers0, ex0) if l == 0 else halos[l]
             for r in range(self.R):
                 pr = np.ascontiguousarray(peers[r], np.int32)
@@ -390,25 +393,23 @@ class RefParAMG:
                 exd = np.ascontiguousarray(np.concatenate([np.asarray(e, np.int32) for e in ex[r]] + [np.zeros(0, np.int32)]), np.int32)
                 _check(L.ref_paramg_set_halo(self.h, r, l, len(pr), pr if len(pr) else np.zeros(1, np.int32), ptr,
                                              exd if len(exd) else np.zeros(1, np.int32)))
+                if l == self.npar:
+                    continue
                 P = prols[l][r]
                 _check(L.ref_paramg_set_prol(self.h, r, l, P.ncols, P.bw, P.rowptr, P.col if P.nnz else np.zeros(1, np.int32),
                                              P.val if P.nnz else np.zeros(1)))
-        # contracted level: merged matrix (glue, like OracleParAMG), serial hierarchy by the reference's code
+        # contracted level: CtrMap of the reference (group = all ranks, master 0) merges the local matrices; serial hierarchy below
         self.nested = None
         if ctr_maps is not None:
             maps = [np.ascontiguousarray(m, np.int64) for m in ctr_maps]
             N = int(max(int(m.max()) for m in maps if len(m)) + 1)
-            b = prols[-1][0].bw if self.npar else self.b0
-            acc = sp.csr_matrix((N * b, N * b))
             for r in range(self.R):
-                Cm = self._coarsest_matrix(r).to_scipy().tocoo()
-                sd = (maps[r][:, None] * b + np.arange(b)[None, :]).ravel()
-                acc = acc + sp.coo_matrix((Cm.data, (sd[Cm.row], sd[Cm.col])), shape=(N * b, N * b)).tocsr()
-            self.A_merged = Bsr.from_scipy(acc, b, b)
-            self.nested = RefAMG(self.A_merged, nested_free, nested_prols, sm_steps=sm_steps, sm_symm=sm_symm)
-            for r in range(self.R):
-                _check(L.ref_paramg_set_contraction(self.h, r, len(maps[r]), maps[r] if len(maps[r]) else np.zeros(1, np.int64), N, self.nested.h))
+                _check(L.ref_paramg_set_contraction(self.h, r, len(maps[r]), maps[r] if len(maps[r]) else np.zeros(1, np.int64), N))
         _check(L.ref_paramg_setup(self.h, int(sm_steps), int(bool(sm_symm)), int(bool(overlap))))
+        if ctr_maps is not None:
+            self.A_merged = RefMat(L.ref_paramg_merged_matrix(self.h), owned=False).to_bsr()     # CtrMap::DoAssembleMatrix
+            self.nested = RefAMG(self.A_merged, nested_free, nested_prols, sm_steps=sm_steps, sm_symm=sm_symm)
+            _check(L.ref_paramg_set_nested(self.h, self.nested.h))
 
     def _coarsest_matrix(self, r):
         """local matrix of the contracted level (RestrictMatrix of the reference), fetched through a one-level-deeper handle trick:

@@ -272,4 +272,52 @@ protected:
 #include "../_ref/frag/hgs_stage_rhs.inc"
 #include "../_ref/frag/hgs_stage_res.inc"
 
+// ---- CtrMap: contraction of a distributed level onto its group master (dof_contract.cpp) -------------------------------------
+template <class TV> constexpr int VecHeight() { return TV::HEIGHT; }
+template <> constexpr int VecHeight<double>() { return 1; }
+struct UDofsView {
+  shared_ptr<ParallelDofs> pd;
+  const NgMPI_Comm &GetCommunicator() const { return pd->GetCommunicator(); }
+};
+template <class TV> class CtrMap : public BaseDOFMapStep {
+public:
+  using TM = typename spm_entry<VecHeight<TV>(), VecHeight<TV>()>::type;
+  using TSPM = SparseMatrix<TM>;
+  using TSPM_TM = SparseMatrix<TM>;
+  // group[0] is the master; dof_maps[k][j] = contracted dof of local dof j of group member k (master only)
+  CtrMap(shared_ptr<ParallelDofs> originalDofs, shared_ptr<ParallelDofs> mappedDofs, Array<int> &&_group, Table<int> &&_dof_maps)
+      : _orig(originalDofs), _mapped(mappedDofs), group(std::move(_group)), master(group[0]), dof_maps(std::move(_dof_maps)) {
+    is_gm = (GetUDofs().GetCommunicator().Rank() == master);
+  }
+  void TransferF2C(const BaseVector *x_fine, BaseVector *x_coarse) const override;
+  void AddF2C(double fac, const BaseVector *x_fine, BaseVector *x_coarse) const;
+  void TransferC2F(BaseVector *x_fine, const BaseVector *x_coarse) const;
+  void AddC2F(double fac, BaseVector *x_fine, const BaseVector *x_coarse) const override;
+  bool IsMaster() const { return is_gm; }
+  void SetUpMPIStuff();
+  shared_ptr<TSPM> DoAssembleMatrix(shared_ptr<TSPM> mat) const;
+  UDofsView GetUDofs() const { return UDofsView{_orig}; }
+  shared_ptr<ParallelDofs> GetParallelDofs() const { return _orig; }
+  shared_ptr<ParallelDofs> GetMappedParDofs() const { return _mapped; }
+
+protected:
+  shared_ptr<ParallelDofs> _orig, _mapped;
+  Array<int> group;
+  int master;
+  bool is_gm;
+  Table<int> dof_maps;
+  mutable Array<NG_MPI_Request> reqs;
+  Array<NG_MPI_Datatype> NG_MPI_types;
+  mutable Table<TV> buffers;
+};
+#include "../_ref/frag/ctr_timer_f2c.inc"
+#include "../_ref/frag/ctr_timer_c2f.inc"
+#include "../_ref/frag/ctr_f2c.inc"
+#include "../_ref/frag/ctr_addf2c.inc"
+#include "../_ref/frag/ctr_c2f.inc"
+#include "../_ref/frag/ctr_addc2f.inc"
+#include "../_ref/frag/ctr_setup_mpi.inc"
+#include "../_ref/frag/ctr_timer_mat.inc"
+#include "../_ref/frag/ctr_assemble.inc"
+
 }  // namespace amg

@@ -210,8 +210,10 @@ int ref_par_exchange(void *hv, int which, double **v) {
 // =====================================================================================================================
 // the whole multi-rank preconditioner: AMGMatrix::SmoothV (reference code) over distributed levels with the reference's hybrid
 // smoothers and ProlMap transfers, one AMGMatrix per rank, R ranks = R host threads.  The step onto the coarsest, contracted
-// level is GLUE (CtrCoarse below restates CtrMap::TransferF2C / TransferC2F, dof_contract.cpp:49-228, for ONE group whose master
-// is rank 0; members are added in rank order): the reference makes it a DOFMap step and lets ranks drop out of the cycle.
+// level uses the reference's CtrMap (TransferF2C / TransferC2F / DoAssembleMatrix, dof_contract.cpp:49-228, 503-727) for ONE group
+// whose master is rank 0; what is GLUE is only where it sits: CtrCoarse below plugs "contract, serial cycle of the nested
+// hierarchy on the master, expand" in as the coarse solve, where the reference makes the CtrMap a DOFMap step and lets the other
+// ranks drop out of the cycle.
 // =====================================================================================================================
 namespace {
 struct ParLevel {
@@ -231,6 +233,8 @@ struct ParAmgRank {
   std::vector<ParLevel> lev;
   AMGMatrix amg;
   std::vector<i64> ctr_map;   // local coarsest dof -> dof of the merged level
+  shared_ptr<BaseDOFMapStep> ctr;                                   // CtrMap<TV> of the reference
+  std::function<void(const BaseVector *, BaseVector *)> ctr_c2f;    // its TransferC2F (not part of BaseDOFMapStep here)
 };
 struct ParAmgH {
   int R = 0, nlev = 0;
@@ -238,6 +242,7 @@ struct ParAmgH {
   std::vector<ParAmgRank> rk;
   AmgH *nested = nullptr;     // serial hierarchy on the merged level (owned by the caller), used by rank 0
   i64 n_merged = 0;
+  MatH *merged = nullptr;     // CtrMap::DoAssembleMatrix on the master
 };
 
 // coarsest level: gather on rank 0 (members added in rank order), serial V-cycle of the nested hierarchy, scatter
@@ -251,34 +256,18 @@ public:
   int VWidth() const override { return 0; }
   void MultAdd(double, const BaseVector &, BaseVector &) const override { throw Exception("CtrCoarse: MultAdd"); }
   void Mult(const BaseVector &rhs, BaseVector &x) const override {
-    World &w = *h->world;
-    const auto &map = h->rk[rank].ctr_map;
-    auto fr = rhs.FVDouble(), fx = x.FVDouble();
-    const int TAG_UP = 7001, TAG_DOWN = 7002;
+    ParAmgRank &K = h->rk[rank];
     if (rank != 0) {
-      w.put(rank, 0, TAG_UP, fr.Data(), sizeof(double) * fr.Size());
-      w.get(0, rank, TAG_DOWN, fx.Data(), sizeof(double) * fx.Size());
+      K.ctr->TransferF2C(&rhs, nullptr);                   // members send their DISTRIBUTED values to the master ...
+      K.ctr_c2f(&x, nullptr);                              // ... and receive the CUMULATED correction
     } else {
       const size_t N = (size_t)h->n_merged;
       BaseVector g(N, b), xg(N, b);
-      auto fg = g.FVDouble(), fxg = xg.FVDouble();
-      for (size_t j = 0; j < map.size(); j++) for (int c = 0; c < b; c++) fg(map[j] * b + c) += fr(j * b + c);
-      for (int r = 1; r < h->R; r++) {
-        const auto &mr = h->rk[r].ctr_map;
-        std::vector<double> buf(mr.size() * b);
-        w.get(r, 0, TAG_UP, buf.data(), sizeof(double) * buf.size());
-        for (size_t j = 0; j < mr.size(); j++) for (int c = 0; c < b; c++) fg(mr[j] * b + c) += buf[j * b + c];
-      }
+      K.ctr->TransferF2C(&rhs, &g);                        // master: zero, add own, add the members' through dof_maps
       h->nested->amg.SmoothV(xg, g);                       // the reference's serial cycle on the merged level
-      for (int r = 1; r < h->R; r++) {
-        const auto &mr = h->rk[r].ctr_map;
-        std::vector<double> buf(mr.size() * b);
-        for (size_t j = 0; j < mr.size(); j++) for (int c = 0; c < b; c++) buf[j * b + c] = fxg(mr[j] * b + c);
-        w.put(0, r, TAG_DOWN, buf.data(), sizeof(double) * buf.size());
-      }
-      for (size_t j = 0; j < map.size(); j++) for (int c = 0; c < b; c++) fx(j * b + c) = fxg(map[j] * b + c);
+      K.ctr_c2f(&x, &xg);
     }
-    x.SetParallelStatus(CUMULATED);
+    if (x.GetParallelStatus() != CUMULATED) throw Exception("CtrCoarse: x is not CUMULATED after TransferC2F");
   }
 };
 
@@ -318,6 +307,37 @@ template <int B> void paramg_level_setup(ParAmgH *h, ParAmgRank &K, int l, int s
   L.sm = (sm_steps > 1 || sm_symm) ? shared_ptr<BaseSmoother>(make_shared<ProxySmoother>(sm, sm_steps, sm_symm)) : shared_ptr<BaseSmoother>(sm);
 }
 
+// CtrMap for the coarsest distributed level: group = all ranks, master = rank 0; DoAssembleMatrix gives the merged matrix there
+template <int B> void paramg_ctr_setup(ParAmgH *h, ParAmgRank &K) {
+  typedef typename std::conditional<B == 1, double, Vec<B>>::type TV;
+  ParLevel &L = K.lev[h->nlev - 1];
+  NgMPI_Comm comm(h->world.get(), K.rank);
+  Array<int> cnt(L.peers.size()), peers(L.peers.size());
+  for (size_t k = 0; k < L.peers.size(); k++) { cnt[k] = int(L.ex[k].size()); peers[k] = L.peers[k]; }
+  Table<int> ext(cnt);
+  for (size_t k = 0; k < L.peers.size(); k++) for (size_t j = 0; j < L.ex[k].size(); j++) ext[k][j] = L.ex[k][j];
+  auto orig = make_shared<ParallelDofs>(comm, L.A->m->Height(), B, peers, ext);
+  Array<int> group(h->R);
+  for (int r = 0; r < h->R; r++) group[r] = r;
+  shared_ptr<ParallelDofs> mapped;
+  Table<int> maps;
+  if (K.rank == 0) {
+    Array<int> none(0);
+    Table<int> noex(none);
+    mapped = make_shared<ParallelDofs>(comm, (size_t)h->n_merged, B, none, noex);
+    Array<int> per(h->R);
+    for (int r = 0; r < h->R; r++) per[r] = int(h->rk[r].ctr_map.size());
+    maps = Table<int>(per);
+    for (int r = 0; r < h->R; r++) for (size_t j = 0; j < h->rk[r].ctr_map.size(); j++) maps[r][j] = int(h->rk[r].ctr_map[j]);
+  }
+  auto ctr = make_shared<CtrMap<TV>>(orig, mapped, std::move(group), std::move(maps));
+  ctr->SetUpMPIStuff();
+  auto merged = ctr->DoAssembleMatrix(as<B, B>(L.A));           // collective: members send, the master merges
+  if (K.rank == 0) h->merged = new MatH{B, B, merged};
+  K.ctr = ctr;
+  K.ctr_c2f = [ctr](const BaseVector *xf, BaseVector *xc) { ctr->TransferC2F(const_cast<BaseVector *>(xf), xc); };
+}
+
 template <int BF, int BC> void paramg_rap(ParAmgRank &K, int l) {
   ParLevel &L = K.lev[l];
   auto pt = TransposeSPMImpl<BF, BC>(*as<BF, BC>(L.P));
@@ -349,6 +369,7 @@ void *ref_paramg_new(int R, int nlev) {
 void ref_paramg_free(void *hv) {
   ParAmgH *h = (ParAmgH *)hv;
   for (auto &K : h->rk) for (auto &L : K.lev) { delete L.A; delete L.P; delete L.PT; }
+  delete h->merged;
   delete h;
 }
 
@@ -393,13 +414,13 @@ int ref_paramg_set_prol(void *hv, int r, int l, i64 nc, int bc, const i64 *rp, c
   });
 }
 
-// contraction onto rank 0: map[r] = local coarsest dof -> merged dof; nested = handle of a finalized ref_amg_* hierarchy on the merged level
-int ref_paramg_set_contraction(void *hv, int r, i64 n, const i64 *map, i64 n_merged, void *nested) {
+// contraction onto rank 0: map = local coarsest dof -> merged dof of rank r (call for every rank before ref_paramg_setup; the sharing
+// lists of the coarsest level must have been given with ref_paramg_set_halo too)
+int ref_paramg_set_contraction(void *hv, int r, i64 n, const i64 *map, i64 n_merged) {
   ParAmgH *h = (ParAmgH *)hv;
   return guarded([&] {
     h->rk[r].ctr_map.assign(map, map + n);
     h->n_merged = n_merged;
-    h->nested = (AmgH *)nested;
   });
 }
 
@@ -424,9 +445,29 @@ int ref_paramg_setup(void *hv, int sm_steps, int sm_symm, int overlap) {
       else throw Exception("ref_paramg_setup: unsupported block size");
       M.smoothers[l] = L.sm;
     }
-    if (h->nested) {
-      M.crs_inv = make_shared<CtrCoarse>(h, K.rank, K.lev[h->nlev - 1].b);
-      M.has_crs_inv = true;
+    if (h->n_merged > 0) {
+      const int bc = K.lev[h->nlev - 1].b;
+      if (bc == 1) paramg_ctr_setup<1>(h, K);
+      else if (bc == 3) paramg_ctr_setup<3>(h, K);
+      else if (bc == 6) paramg_ctr_setup<6>(h, K);
+      else throw Exception("ref_paramg_setup: unsupported block size on the contracted level");
+    }
+  });
+}
+
+// CtrMap::DoAssembleMatrix result (valid after ref_paramg_setup; lives on the master)
+const void *ref_paramg_merged_matrix(void *hv) { return ((ParAmgH *)hv)->merged; }
+
+// the serial hierarchy on the merged level (a finalized ref_amg_* handle, owned by the caller): "contract, V-cycle there, expand" becomes
+// the coarse solve of every rank's AMGMatrix
+int ref_paramg_set_nested(void *hv, void *nested) {
+  ParAmgH *h = (ParAmgH *)hv;
+  return guarded([&] {
+    if (!h->merged) throw Exception("ref_paramg_set_nested: no contraction was set up");
+    h->nested = (AmgH *)nested;
+    for (auto &K : h->rk) {
+      K.amg.crs_inv = make_shared<CtrCoarse>(h, K.rank, K.lev[h->nlev - 1].b);
+      K.amg.has_crs_inv = true;
     }
   });
 }

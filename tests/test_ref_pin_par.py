@@ -193,11 +193,11 @@ def test_multirank_oracle_against_reference_made_fixture():
 
 
 @needs_ref
-@pytest.mark.parametrize("grid,steps,symm", [((1, 1, 2), 1, False), ((2, 2, 2), 1, False), ((1, 2, 2), 2, True)])
+@pytest.mark.parametrize("grid,steps,symm", [((1, 1, 2), 1, False), ((2, 2, 2), 1, False), ((1, 2, 2), 2, True), ((1, 1, 3), 1, False)])
 def test_parallel_vcycle_and_pcg_vs_reference_code(grid, steps, symm):
     """the whole multi-rank preconditioner: AMGMatrix::SmoothV of the reference over distributed levels with its HybridGSSmoother
-    (+ProxySmoother) and ProlMap, contraction onto rank 0 and the reference's serial cycle below (RefParAMG) vs OracleParAMG on
-    the same hierarchy.  Everything before the exact coarse solve is bit-identical on every level and rank; after it the two
+    (+ProxySmoother) and ProlMap, its CtrMap (DoAssembleMatrix, TransferF2C / TransferC2F) onto rank 0 and its serial cycle below
+    (RefParAMG) vs OracleParAMG on the same hierarchy.  Everything before the exact coarse solve is bit-identical on every level and rank; after it the two
     dense coarse solvers differ in the last bits; identical PCG iteration counts."""
     from oracle import cpu_pipeline as CP
     from helpers import rand, rel
@@ -207,6 +207,10 @@ def test_parallel_vcycle_and_pcg_vs_reference_code(grid, steps, symm):
     oa = OP.OracleParAMG(*hier, sm_steps=steps, sm_symm=symm)
     ra = R.RefParAMG(*hier, sm_steps=steps, sm_symm=symm)
     assert info["distributed_levels"] >= 2
+    # CtrMap::DoAssembleMatrix: the contracted matrix is a structural union (entries that cancel across ranks stay) summed in group order
+    Am, Ao = ra.A_merged, oa.A_merged
+    assert np.array_equal(Am.rowptr, Ao.rowptr) and np.array_equal(Am.col, Ao.col), "contracted pattern"
+    assert np.array_equal(Am.val, Ao.val), "contracted values"
     b = [rand(7 + r, p["n"]) * p["free"] for r, p in enumerate(parts)]
     xo, xr = oa.apply(b), ra.apply(b)
     for l in range(oa.npar):
