@@ -273,6 +273,10 @@ int ngsamg_b200_block_regularize(int n, double *m, int dim);
 typedef struct ngsamg_b200_tiles ngsamg_b200_tiles;
 int ngsamg_b200_tile_schedule_begin(const ngsamg_csr *A, const uint8_t *smoothed_mask, const int32_t *sweep_rank, int rounds, int max_rows,
                                     ngsamg_b200_tiles **out, int64_t *info);
+/* the same with caller-supplied clusters (cluster[i] >= 0 for every smoothed row) instead of the built-in pairwise clustering, e.g. the boxes
+ * of a structured grid: the clusters are a hint, the scheduler still splits whatever is not executable as one piece */
+int ngsamg_b200_tile_schedule_hinted(const ngsamg_csr *A, const uint8_t *smoothed_mask, const int32_t *sweep_rank, const int32_t *cluster, int max_rows,
+                                     ngsamg_b200_tiles **out, int64_t *info);
 int ngsamg_b200_tile_schedule_fetch(ngsamg_b200_tiles *m, int32_t *perm, int32_t *tile_slice, int32_t *tile_nlev, uint8_t *row_lvl,
                                     int64_t *pred_ptr, int32_t *pred);
 const char *ngsamg_b200_tiles_last_error(void);

@@ -27,7 +27,7 @@ EXPORTS = [
     "ngsamg_b200_get_halo", "ngsamg_b200_get_hybrid", "ngsamg_b200_num_parallel_levels", "ngsamg_b200_get_contracted",
     "ngsamg_b200_get_contraction_map", "ngsamg_b200_hybrid_host_begin", "ngsamg_b200_hybrid_host_fetch",
     "ngsamg_b200_coarsen_parallel_begin", "ngsamg_b200_coarsen_parallel_fetch",
-    "ngsamg_b200_tile_schedule_begin", "ngsamg_b200_tile_schedule_fetch", "ngsamg_b200_tiles_last_error", "ngsamg_b200_block_pinv", "ngsamg_b200_block_regularize",
+    "ngsamg_b200_tile_schedule_begin", "ngsamg_b200_tile_schedule_hinted", "ngsamg_b200_tile_schedule_fetch", "ngsamg_b200_tiles_last_error", "ngsamg_b200_block_pinv", "ngsamg_b200_block_regularize",
 ]
 
 
@@ -118,6 +118,7 @@ def lib():
                                                      C.POINTER(i64), C.POINTER(C.c_int32), C.POINTER(i64)]
     L.ngsamg_b200_coarsen_parallel_fetch.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, vp]
     L.ngsamg_b200_tile_schedule_begin.argtypes = [C.POINTER(Csr), vp, vp, ci, ci, C.POINTER(vp), vp]
+    L.ngsamg_b200_tile_schedule_hinted.argtypes = [C.POINTER(Csr), vp, vp, vp, ci, C.POINTER(vp), vp]
     L.ngsamg_b200_tile_schedule_fetch.argtypes = [vp, vp, vp, vp, vp, vp, vp]
     L.ngsamg_b200_tiles_last_error.restype = C.c_char_p
     _lib = L

@@ -70,7 +70,7 @@ void transpose_lists(i64 nt, const std::vector<i64> &pptr, const std::vector<i32
 }  // namespace
 
 void build_tile_schedule(const HostBsr &A, const std::vector<uint8_t> &mask, const std::vector<i32> &sweep_rank, int rounds, int max_rows,
-                         TileSchedule &ts)
+                         TileSchedule &ts, const std::vector<i32> *cluster_hint)
 {
   ts = TileSchedule();
   const i64 n = A.nrows;
@@ -83,7 +83,16 @@ void build_tile_schedule(const HostBsr &A, const std::vector<uint8_t> &mask, con
 
   // ---- 1. clusters of graph-neighbouring smoothed rows: only a HINT for which rows should share a tile
   std::vector<i32> agg;
-  const i64 nagg = cluster_rows(A, hm ? mask.data() : nullptr, rounds, 0.25, agg);
+  i64 nagg = 0;
+  if (cluster_hint && (i64)cluster_hint->size() == n) {
+    agg = *cluster_hint;
+    for (i64 i = 0; i < n; i++) {
+      if (!smoothed(i)) agg[i] = -1;
+      else if (agg[i] < 0) throw Error("tile schedule: a smoothed row has no cluster in the hint");
+      nagg = std::max<i64>(nagg, (i64)agg[i] + 1);
+    }
+  } else
+    nagg = cluster_rows(A, hm ? mask.data() : nullptr, rounds, 0.25, agg);
 
   // ---- 2. tiles = consecutive chunks of a topological order of the row DAG (=> the tile graph is acyclic by construction).
   // The order is produced by list scheduling that stays inside one cluster as long as that cluster has executable rows: a cluster

@@ -28,8 +28,9 @@ struct TileSchedule {
 
 // A: level matrix (original numbering); mask: rows that are smoothed (empty = all); sweep_rank: position of each row in the sweep
 // (empty = row number); max_rows: capacity of a tile (multiple of 32, <= 128); rounds: pairwise clustering rounds (tiles of <= 2^rounds rows).
+// cluster_hint (optional): caller-supplied cluster id per row (-1 = not smoothed) instead of the pairwise clustering -- e.g. boxes of a structured grid.
 void build_tile_schedule(const HostBsr &A, const std::vector<uint8_t> &mask, const std::vector<i32> &sweep_rank, int rounds, int max_rows,
-                         TileSchedule &out);
+                         TileSchedule &out, const std::vector<i32> *cluster_hint = nullptr);
 
 // self-check: every dependency of every row is scheduled before the row (other tile listed as predecessor and earlier in the order, or
 // same tile and lower local level).  Returns the number of violations.

@@ -12,8 +12,24 @@ extern "C" {
 
 const char *ngsamg_b200_tiles_last_error(void) { return g_tile_err.c_str(); }
 
+static int tile_schedule_impl(const ngsamg_csr *A, const uint8_t *smoothed_mask, const int32_t *sweep_rank, const int32_t *cluster_hint, int rounds,
+                              int max_rows, ngsamg_b200_tiles **out, int64_t *info);
+
 int ngsamg_b200_tile_schedule_begin(const ngsamg_csr *A, const uint8_t *smoothed_mask, const int32_t *sweep_rank, int rounds, int max_rows,
                                     ngsamg_b200_tiles **out, int64_t *info /* 9 values, see header */)
+{
+  return tile_schedule_impl(A, smoothed_mask, sweep_rank, nullptr, rounds, max_rows, out, info);
+}
+
+int ngsamg_b200_tile_schedule_hinted(const ngsamg_csr *A, const uint8_t *smoothed_mask, const int32_t *sweep_rank, const int32_t *cluster, int max_rows,
+                                     ngsamg_b200_tiles **out, int64_t *info)
+{
+  if (!cluster) { g_tile_err = "null cluster hint"; return 1; }
+  return tile_schedule_impl(A, smoothed_mask, sweep_rank, cluster, 0, max_rows, out, info);
+}
+
+static int tile_schedule_impl(const ngsamg_csr *A, const uint8_t *smoothed_mask, const int32_t *sweep_rank, const int32_t *cluster_hint, int rounds,
+                              int max_rows, ngsamg_b200_tiles **out, int64_t *info)
 {
   try {
     if (!A || !out || !A->rowptr) throw Error("null argument");
@@ -28,7 +44,9 @@ int ngsamg_b200_tile_schedule_begin(const ngsamg_csr *A, const uint8_t *smoothed
     std::vector<i32> rank;
     if (sweep_rank) rank.assign(sweep_rank, sweep_rank + A->nrows);
     auto r = std::make_unique<ngsamg_b200_tiles>();
-    build_tile_schedule(h, mask, rank, rounds, max_rows, r->ts);
+    std::vector<i32> hint;
+    if (cluster_hint) hint.assign(cluster_hint, cluster_hint + A->nrows);
+    build_tile_schedule(h, mask, rank, rounds, max_rows, r->ts, cluster_hint ? &hint : nullptr);
     if (r->ts.ok) r->violations = check_tile_schedule(h, mask, rank, r->ts);
     if (info) {
       const TileSchedule &t = r->ts;

@@ -11,7 +11,7 @@ import scipy.sparse as sp
 import ngsamg_b200 as ng
 from ngsamg_b200 import _lib
 from ngsamg_b200 import synthetic as S
-from helpers import rand, rel, to_oracle
+from helpers import poisson, rand, rel, to_oracle
 from oracle import oracle as O
 
 KEYS = ["ok", "ntiles", "npad", "nonfree_pad", "tile_depth", "max_local_levels", "merged", "violations", "npred"]
@@ -132,3 +132,28 @@ def test_tile_schedule_all_rows_smoothed_and_tiny():
     d = tile_schedule(A, None, None)
     assert d["ok"] == 1 and d["violations"] == 0 and d["nonfree_pad"] == 0
     assert sorted(d["perm"]) == sorted(set(d["perm"])) and d["perm"].max() < d["npad"]
+
+
+def test_tile_schedule_with_cluster_hints_reaches_the_box_bound():
+    """caller-supplied clusters (ngsamg_b200_tile_schedule_hinted): axis-aligned 4x4x2 boxes of the structured grid give the ideal tile-DAG
+    depth sum_d ceil(n_d / e_d) - 2 (every lower neighbour of a box member lies in a box with smaller-or-equal box coordinates), and the
+    schedule is still a valid sweep order; the built-in pairwise clustering stays within 1.6x of that bound"""
+    n = 21
+    p, A = poisson(n)
+    idx = np.arange(n ** 3)
+    x, y, z = idx % n, (idx // n) % n, idx // (n * n)
+    bx, by, bz = -(-n // 4), -(-n // 4), -(-n // 2)
+    cl = np.ascontiguousarray((x // 4) + bx * ((y // 4) + by * (z // 2)), np.int32)
+    L = _lib.lib()
+    abi = A._abi()
+    h = C.c_void_p()
+    info = np.zeros(9, np.int64)
+    m = np.ascontiguousarray(p["free"], np.uint8)
+    rc = L.ngsamg_b200_tile_schedule_hinted(C.byref(abi), _lib.ptr(m), None, _lib.ptr(cl), 32, C.byref(h), _lib.ptr(info))
+    assert rc == 0, L.ngsamg_b200_tiles_last_error()
+    d = dict(zip(KEYS, [int(v) for v in info]))
+    L.ngsamg_b200_tile_schedule_fetch(h, None, None, None, None, None, None)
+    assert d["ok"] == 1 and d["violations"] == 0
+    assert d["tile_depth"] <= bx + by + bz - 2
+    d2 = tile_schedule(A, p["free"], None)
+    assert d2["tile_depth"] <= 1.6 * d["tile_depth"]
