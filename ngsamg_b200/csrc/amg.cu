@@ -900,7 +900,7 @@ void Amg::finalize()
       // EXPERIMENTAL (off by default): tile-major numbering + two-level schedule for big scalar levels
       if (!coarsest && L.b == 1 && flags.flag("b200_tile_sweep", false) && L.n >= (i64)flags.num("b200_tile_min_rows", 200000)) {
         TileSchedule ts;
-        const int cap = (int)flags.num("b200_tile_rows", 32);
+        const int cap = (int)flags.num("b200_tile_rows", 64);     // 64-row tiles (6 pairing rounds): about half the tile-DAG depth of 32-row tiles
         build_tile_schedule(L.hA, L.mask(), L.sweep_rank, (int)flags.num("b200_tile_rounds", cap <= 32 ? 5 : 6), cap, ts);
         if (ts.ok) {
           L.perm = ts.perm; L.npad = ts.npad; L.nonfree_pad = ts.nonfree_pad; L.depth = ts.tile_depth;

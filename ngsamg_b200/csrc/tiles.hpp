@@ -36,6 +36,6 @@ void build_tile_schedule(const HostBsr &A, const std::vector<uint8_t> &mask, con
 // same tile and lower local level).  Returns the number of violations.
 i64 check_tile_schedule(const HostBsr &A, const std::vector<uint8_t> &mask, const std::vector<i32> &sweep_rank, const TileSchedule &ts);
 
-i64 cluster_rows(const HostBsr &A, const uint8_t *keep, int rounds, double soc_thresh, std::vector<i32> &cluster);
+i64 cluster_rows(const HostBsr &A, const uint8_t *keep, int rounds, double soc_thresh, std::vector<i32> &cluster, bool forward = false);
 
 }  // namespace ngb
