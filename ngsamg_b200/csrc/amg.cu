@@ -901,6 +901,7 @@ void Amg::finalize()
       if (!coarsest && L.b == 1 && flags.flag("b200_tile_sweep", false) && L.n >= (i64)flags.num("b200_tile_min_rows", 200000)) {
         TileSchedule ts;
         const int cap = (int)flags.num("b200_tile_rows", 64);     // 64-row tiles (6 pairing rounds): about half the tile-DAG depth of 32-row tiles
+        if (cap != 32 && cap != 64) throw Error("ngs_amg_b200_tile_rows must be 32 or 64 (the warp-per-tile kernel holds at most two slices per lane)");
         build_tile_schedule(L.hA, L.mask(), L.sweep_rank, (int)flags.num("b200_tile_rounds", cap <= 32 ? 5 : 6), cap, ts);
         if (ts.ok) {
           L.perm = ts.perm; L.npad = ts.npad; L.nonfree_pad = ts.nonfree_pad; L.depth = ts.tile_depth;

@@ -79,7 +79,7 @@ void build_tile_schedule(const HostBsr &A, const std::vector<uint8_t> &mask, con
   const bool natural = sweep_rank.empty();
   auto smoothed = [&](i64 i) { return !hm || mask[i]; };
   auto rank_of = [&](i64 i) -> i64 { return natural ? i : (i64)sweep_rank[i]; };
-  if (max_rows % 32 || max_rows < 32 || max_rows > 128) throw Error("tile capacity must be 32, 64, 96 or 128 rows");
+  if (max_rows % 32 || max_rows < 32 || max_rows > 1024) throw Error("tile capacity must be a multiple of 32 rows, at most 1024");   // the warp kernel takes <= 64, a CTA-per-tile kernel more
 
   // ---- 1. clusters of graph-neighbouring smoothed rows: only a HINT for which rows should share a tile
   std::vector<i32> agg;

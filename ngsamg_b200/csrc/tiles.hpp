@@ -27,7 +27,7 @@ struct TileSchedule {
 };
 
 // A: level matrix (original numbering); mask: rows that are smoothed (empty = all); sweep_rank: position of each row in the sweep
-// (empty = row number); max_rows: capacity of a tile (multiple of 32, <= 128); rounds: pairwise clustering rounds (tiles of <= 2^rounds rows).
+// (empty = row number); max_rows: capacity of a tile (multiple of 32, <= 1024; the warp-per-tile kernel handles <= 64); rounds: pairwise clustering rounds (tiles of <= 2^rounds rows).
 // cluster_hint (optional): caller-supplied cluster id per row (-1 = not smoothed) instead of the pairwise clustering -- e.g. boxes of a structured grid.
 void build_tile_schedule(const HostBsr &A, const std::vector<uint8_t> &mask, const std::vector<i32> &sweep_rank, int rounds, int max_rows,
                          TileSchedule &out, const std::vector<i32> *cluster_hint = nullptr);
