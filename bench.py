@@ -496,7 +496,7 @@ def main():
                                     "interface DOFs shared), h1_scal + CG to 1e-8, hybrid Gauss-Seidel + NCCL halo exchange" % (tuple(p["global_dims"]) + (ndof_global, world) + tuple(grid) + (n,))) if world > 1 else
                                    ("3D Poisson P1 unit cube (Kuhn tets), %d^3 = %d DOFs per GPU, h1_scal + CG to 1e-8" % (n, ndof)) if not elast else
                                    ("3D linear elasticity P1 beam (Kuhn tets), %d vertices = %d DOFs per GPU, elast_3d (3x3 fine / 6x6 coarse blocks) + CG to 1e-6" % (p["n"], ndof)),
-                       "tol": tol, "levels": levels, "operator_complexity": pc.GetOC(),
+                       "tol": tol, "levels": levels, "operator_complexity": pc.GetOC()[0],
                        "parallelism": "1 GPU" if world == 1 else "%d subdomains, one per GPU; DIS2CO/CO2CU halo exchange per sweep, all-reduced CG dot products, coarse levels contracted onto rank 0" % world,
                        "multi_gpu": par_info,
                        "l2": "inputs larger than L2 (level-0 matrix %.1f GB)" % (levels[0]["nnz"] * (8 * levels[0]["b"] ** 2 + 4) / 1e9)},

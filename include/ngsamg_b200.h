@@ -125,7 +125,11 @@ int ngsamg_b200_get_level_vector(ngsamg_b200_t *h, int level, int which, double 
 /* position of every row of `level` in the Gauss-Seidel sweep: rank[i] == i (the reference's order, gssmoother.cpp:195-315)
  * unless the optional multicolour smoother was requested for the fine level (flag ngs_amg_b200_sm_order=multicolor). */
 int ngsamg_b200_get_sweep_order(ngsamg_b200_t *h, int level, int32_t *rank);
-/* operator complexity sum_l nnz_l*b_l^2 / (nnz_0*b_0^2) (AMGMatrix::GetOC) */
+/* AMGMatrix::GetOC (src/base/solve/amg_matrix.cpp:551-582): occs = [OC, OC_0, OC_1, ...], OC_l = cycle factor * nops_l / nze_0 for the
+ * levels that carry a smoother (nze = scalar non-zeros, nops = nze times nsteps * (symm ? 2 : 1) under a ProxySmoother; factor 1 / 2^l / 2(1+l)
+ * for V / W / BS), 0 for the exactly solved coarsest level, OC = their sum.  Returns the number of entries (pass occs = NULL to query it). */
+int ngsamg_b200_operator_complexities(ngsamg_b200_t *h, double *occs, int cap);
+/* occs[0] of the above */
 double ngsamg_b200_operator_complexity(ngsamg_b200_t *h);
 /* algorithmic bytes of one V(1,1)-cycle, SURVEY.md §8d formula B_V, from the actual level sizes */
 double ngsamg_b200_vcycle_bytes(ngsamg_b200_t *h);

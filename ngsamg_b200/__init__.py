@@ -218,7 +218,11 @@ class Preconditioner:
         return int(i.n), int(i.b)
 
     def GetOC(self):
-        return float(self._lib.ngsamg_b200_operator_complexity(self._h))
+        """AMGMatrix::GetOC (amg_matrix.cpp:551-582): [OC, OC_l0, OC_l1, ...]"""
+        n = self._lib.ngsamg_b200_operator_complexities(self._h, None, 0)
+        occs = np.zeros(max(n, 1))
+        self._lib.ngsamg_b200_operator_complexities(self._h, occs.ctypes.data_as(C.c_void_p), n)
+        return [float(v) for v in occs[:n]]
 
     def GetAMGMatrix(self):
         return AMGMatrix(self)

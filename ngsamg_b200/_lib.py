@@ -18,7 +18,7 @@ EXPORTS = [
     "ngsamg_b200_last_error", "ngsamg_b200_apply", "ngsamg_b200_apply_add", "ngsamg_b200_spmv_add",
     "ngsamg_b200_smooth", "ngsamg_b200_restrict", "ngsamg_b200_prolong_add", "ngsamg_b200_pcg",
     "ngsamg_b200_num_levels", "ngsamg_b200_level_info", "ngsamg_b200_get_level_matrix",
-    "ngsamg_b200_get_prolongation", "ngsamg_b200_get_level_vector", "ngsamg_b200_operator_complexity",
+    "ngsamg_b200_get_prolongation", "ngsamg_b200_get_level_vector", "ngsamg_b200_operator_complexity", "ngsamg_b200_operator_complexities",
     "ngsamg_b200_vcycle_bytes", "ngsamg_b200_last_ms", "ngsamg_b200_launch_count", "ngsamg_b200_rap_begin",
     "ngsamg_b200_matmul_begin", "ngsamg_b200_transpose_begin", "ngsamg_b200_spm_fetch",
     "ngsamg_b200_coarsen_begin", "ngsamg_b200_coarsen_fetch", "ngsamg_b200_profile_kernel",
@@ -84,6 +84,7 @@ def lib():
     L.ngsamg_b200_get_level_vector.argtypes = [vp, ci, ci, vp]
     L.ngsamg_b200_operator_complexity.argtypes = [vp]
     L.ngsamg_b200_operator_complexity.restype = dbl
+    L.ngsamg_b200_operator_complexities.argtypes = [vp, vp, ci]
     L.ngsamg_b200_vcycle_bytes.argtypes = [vp]
     L.ngsamg_b200_vcycle_bytes.restype = dbl
     L.ngsamg_b200_last_ms.argtypes = [vp, ci]

@@ -2573,13 +2573,40 @@ int ngsamg_b200_get_sweep_order(ngsamg_b200_t *h, int level, int32_t *rank)
   NGB_CATCH
 }
 
+// AMGMatrix::GetOC (amg_matrix.cpp:551-582): occs[1 + l] = cycle factor * nops_l / nze_0 for the levels that carry a smoother, 0 for the
+// coarsest (exactly solved) level; occs[0] = their sum.  nze = scalar non-zeros (GetScalNZE: NZE * entry size, utils_sparseLA.cpp:324-342),
+// nops_l = nze_l, times nsteps * (symm ? 2 : 1) under a ProxySmoother (base_smoother.cpp:38-41); cycle factor 1 (V), 2^l (W), 2 (1 + l) (BS).
+int ngsamg_b200_operator_complexities(ngsamg_b200_t *h, double *occs, int cap)
+{
+  if (!h || !h->amg.finalized) return 0;
+  auto &lev = h->amg.lev;
+  const int nl = (int)lev.size();
+  const int nsm = std::max(0, nl - 1);
+  const int nout = 1 + nsm + (h->amg.has_cinv ? 1 : 0);
+  if (!occs || cap < nout) return nout;
+  const double nze0 = (double)lev[0]->nnz * lev[0]->b * lev[0]->b;
+  double sum = 0.0;
+  for (int l = 0; l < nout - 1; l++) {
+    double v = 0.0;
+    if (l < nsm) {
+      const Level &L = *lev[l];
+      double nops = (double)L.nnz * L.b * L.b;
+      if (L.sm_steps > 1 || L.sm_symm) nops *= (double)L.sm_steps * (L.sm_symm ? 2 : 1);
+      const double fac = h->amg.cycle == Amg::CYCLE_W ? std::pow(2.0, l) : h->amg.cycle == Amg::CYCLE_BS ? 2.0 * (1 + l) : 1.0;
+      v = fac * nops / nze0;
+    }
+    occs[1 + l] = v;
+    sum += v;
+  }
+  occs[0] = sum;
+  return nout;
+}
+
 double ngsamg_b200_operator_complexity(ngsamg_b200_t *h)
 {
-  if (!h || !h->amg.finalized) return 0.0;
-  double s = 0;
-  for (auto &lp : h->amg.lev) s += (double)lp->nnz * lp->b * lp->b;
-  const Level &L0 = *h->amg.lev[0];
-  return s / ((double)L0.nnz * L0.b * L0.b);
+  double occs[64];
+  const int n = ngsamg_b200_operator_complexities(h, occs, 64);
+  return (n > 0 && n <= 64) ? occs[0] : 0.0;
 }
 
 double ngsamg_b200_vcycle_bytes(ngsamg_b200_t *h)

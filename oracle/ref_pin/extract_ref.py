@@ -67,6 +67,11 @@ FRAGMENTS = [
     ("amg_smoothbs", "src/base/solve/amg_matrix.cpp", r"^\s*void AMGMatrix :: SmoothBS \(", "line", None),
     ("amg_smoothv", "src/base/solve/amg_matrix.cpp", r"^\s*void AMGMatrix :: SmoothV \(", "line", None),
     ("amg_smoothvfrom", "src/base/solve/amg_matrix.cpp", r"^\s*void AMGMatrix :: SmoothVFromLevel \(", "line", None),
+    ("amg_getoc", "src/base/solve/amg_matrix.cpp", r"^\s*Array<double> AMGMatrix :: GetOC \(\) const", "line", None),
+    ("bs_getnops", "src/base/smoothers/base_smoother.hpp", r"^\s*virtual size_t GetNOps \(\) const$", "line", None),
+    ("bs_getanze", "src/base/smoothers/base_smoother.hpp", r"^\s*virtual size_t GetANZE \(\) const$", "line", None),
+    ("proxy_getnops", "src/base/smoothers/base_smoother.cpp", r"^size_t ProxySmoother :: GetNOps \(\) const", "line", None),
+    ("proxy_getanze", "src/base/smoothers/base_smoother.cpp", r"^size_t ProxySmoother :: GetANZE \(\) const", "line", None),
     ("amg_smooth", "src/base/solve/amg_matrix.hpp", r"^\s*INLINE void Smooth \(BaseVector & x, const BaseVector & b\) const", "line", None),
     ("amg_mult", "src/base/solve/amg_matrix.cpp", r"^\s*void AMGMatrix :: Mult \(const BaseVector & b, BaseVector & x\) const", "line", None),
     ("amg_multtrans", "src/base/solve/amg_matrix.cpp", r"^\s*void AMGMatrix :: MultTrans \(const BaseVector & b, BaseVector & x\) const", "line", None),

@@ -17,6 +17,7 @@
 #include <iostream>
 #include <limits>
 #include <memory>
+#include <numeric>
 #include <stdexcept>
 #include <string>
 #include <tuple>
@@ -356,6 +357,7 @@ public:
   size_t Height() const { return VHeight(); }
   size_t Width() const { return VWidth(); }
   virtual void Mult(const BaseVector &x, BaseVector &y) const { y = 0.0; MultAdd(1.0, x, y); }
+  virtual size_t ScalNZE() const { return 0; }      // stored entries * entry size (what the reference's GetScalNZE reports for sparse matrices)
   virtual void MultAdd(double s, const BaseVector &x, BaseVector &y) const = 0;
   MatVecExpr operator*(const BaseVector &x) const { return MatVecExpr{this, &x, 1.0}; }
 };
@@ -414,6 +416,7 @@ public:
   int VHeight() const override { return int(h); }
   int VWidth() const override { return int(w); }
   size_t NZE() const { return firsti[h]; }
+  size_t ScalNZE() const override { return firsti[h] * (sizeof(TM) / sizeof(double)); }
   FlatArray<int> GetRowIndices(size_t i) const { return FlatArray<int>(firsti[i + 1] - firsti[i], const_cast<int *>(colnr.data()) + firsti[i]); }
   FlatVector<TM> GetRowValues(size_t i) const { return FlatVector<TM>(firsti[i + 1] - firsti[i], const_cast<TM *>(data.data()) + firsti[i]); }
   size_t First(size_t i) const { return firsti[i]; }

@@ -232,6 +232,16 @@ class RefAMG:
         _check(lib().ref_amg_apply(self.h, {"V": 0, "W": 1, "BS": 2}[cycle], np.ascontiguousarray(b, np.float64), x))
         return x
 
+    def get_oc(self, cycle="V"):
+        """AMGMatrix::GetOC (amg_matrix.cpp:551-582): [OC, OC_l0, OC_l1, ...]"""
+        L = lib()
+        L.ref_amg_get_oc.argtypes = [C.c_void_p, C.c_int, f64p, C.c_int]
+        out = np.zeros(64)
+        n = L.ref_amg_get_oc(self.h, {"V": 0, "W": 1, "BS": 2}[cycle], out, 64)
+        if n < 0:
+            _check(1)
+        return [float(v) for v in out[:n]]
+
     def mult(self, b, x, cycle="V", trans=False):
         """AMGMatrix::Mult / MultTrans: x = C b (x is overwritten)"""
         L = lib()

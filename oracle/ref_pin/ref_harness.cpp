@@ -54,6 +54,9 @@ template <class TSCAL> bool TryDirectInverse_simple(FlatMatrix<TSCAL> A, LocalHe
 #include "../_ref/frag/timer_restrict.inc"
 #include "../_ref/frag/restrict.inc"
 
+// GetScalNZE (utils_sparseLA.cpp:324-342) on one rank: NZE * entry size of the local sparse matrix
+INLINE size_t GetScalNZE(BaseMatrix const *m) { return m->ScalNZE(); }
+
 // ---- smoothers ---------------------------------------------------------------------------------------------------
 class BaseSmoother : public BaseMatrix {
 protected:
@@ -68,6 +71,8 @@ public:
 #include "../_ref/frag/bs_smoothbackk.inc"
 #include "../_ref/frag/bs_smoothsymmk.inc"
   virtual shared_ptr<BaseMatrix> GetAMatrix() const { return sysmat; }
+#include "../_ref/frag/bs_getnops.inc"
+#include "../_ref/frag/bs_getanze.inc"
   int VHeight() const override { return sysmat->VHeight(); }
   int VWidth() const override { return sysmat->VWidth(); }
   void MultAdd(double, const BaseVector &, BaseVector &) const override { throw Exception("BaseSmoother :: MultAdd not overloaded!"); }
@@ -84,7 +89,11 @@ public:
   ProxySmoother(shared_ptr<BaseSmoother> _sm, int _nsteps, bool _symm) : BaseSmoother(_sm->GetAMatrix()), sm(_sm), nsteps(_nsteps), symm(_symm) {}
 #include "../_ref/frag/proxy_smooth.inc"
 #include "../_ref/frag/proxy_smoothback.inc"
+  size_t GetNOps() const override;
+  size_t GetANZE() const override;
 };
+#include "../_ref/frag/proxy_getnops.inc"
+#include "../_ref/frag/proxy_getanze.inc"
 
 // Richardson / Jacobi (base_smoother.hpp:250-285, base_smoother.cpp:52-114)
 template <class TM> INLINE shared_ptr<SparseMatrix<TM>> GetLocalTMM(shared_ptr<BaseMatrix> A) { return dynamic_pointer_cast<SparseMatrix<TM>>(A); }
@@ -180,7 +189,12 @@ public:
 #include "../_ref/frag/prol_f2c.inc"
 #include "../_ref/frag/prol_addc2f.inc"
 
-struct DummyUDofs { int GetCommunicator() const { return 0; } };
+enum { NG_MPI_MAX = 1001 };
+struct OneRankComm {      // the communicator of a single-rank AMGMatrix: reductions are the identity
+  template <class T, class OP> T AllReduce(T v, OP) const { return v; }
+  template <class T> void AllReduceFA(FlatArray<T>) const {}
+};
+struct DummyUDofs { OneRankComm GetCommunicator() const { return OneRankComm(); } };
 class DOFMap {
   Array<shared_ptr<BaseDOFMapStep>> steps;
   DummyUDofs ud;
@@ -207,6 +221,7 @@ public:
   void MultTrans(const BaseVector &b, BaseVector &x) const;
   void MultAdd(double s, const BaseVector &b, BaseVector &x) const;
   void MultTransAdd(double s, const BaseVector &b, BaseVector &x) const;
+  Array<double> GetOC() const;
   void SmoothV(BaseVector &x, const BaseVector &b) const;
   void SmoothW(BaseVector &x, const BaseVector &b) const;
   void SmoothBS(BaseVector &x, const BaseVector &b) const;
@@ -220,6 +235,7 @@ public:
 #include "../_ref/frag/amg_multtrans.inc"
 #include "../_ref/frag/amg_multadd.inc"
 #include "../_ref/frag/amg_multtransadd.inc"
+#include "../_ref/frag/amg_getoc.inc"
 
 // dense coarse inverse handed in by the caller (the reference uses NGSolve's sparse Cholesky, which is not in its tree)
 class DenseInverse : public BaseMatrix {
@@ -623,6 +639,20 @@ int ref_amg_mult_add(void *hv, int cycle, int trans, double s, const double *b, 
     a->amg.vwb = 0;
     std::memcpy(x, vx.FVDouble().Data(), sizeof(double) * nb);
   });
+}
+
+// AMGMatrix::GetOC (amg_matrix.cpp:551-582) with SetVWB(cycle): [OC, OC_l0, ...]; returns the number of entries written (<= cap)
+int ref_amg_get_oc(void *hv, int cycle, double *out, int cap) {
+  AmgH *a = (AmgH *)hv;
+  int n = 0;
+  int rc = guarded([&] {
+    a->amg.vwb = cycle;
+    auto occs = a->amg.GetOC();
+    a->amg.vwb = 0;
+    n = (int)occs.Size();
+    for (int i = 0; i < n && i < cap; i++) out[i] = occs[i];
+  });
+  return rc ? -1 : n;
 }
 
 // AMGMatrix::Mult / MultTrans (amg_matrix.cpp:377-383)

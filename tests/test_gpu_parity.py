@@ -296,7 +296,7 @@ def test_config1_size_properties():
     fr = p["free"] == 1
     r = p["rhs"] - A.to_scipy() @ u
     assert np.linalg.norm(r[fr]) < 1e-6 * np.linalg.norm(p["rhs"][fr])
-    assert 1.0 < pc.GetOC() < 2.0
+    assert 1.0 < pc.GetOC()[0] < 2.0 and pc.GetOC()[1] == 1.0 and pc.GetOC()[-1] == 0.0   # [OC, OC_l0, ..., 0 for the exactly solved level]
 
 
 def test_elasticity_3d():

@@ -62,6 +62,15 @@ def test_cycles_vs_reference_code(pois, cycle):
         assert rel(x, rac.apply(b, cycle)) < TOL_VCYCLE
 
 
+@pytest.mark.parametrize("cycle,steps,symm", [("V", 1, False), ("W", 2, True), ("BS", 3, False)])
+def test_operator_complexity_vs_reference_code(pois, cycle, steps, symm):
+    """AMGMatrix::GetOC (amg_matrix.cpp:551-582) incl. the ProxySmoother and cycle factors"""
+    p, A, pc, ra = pois
+    pcc = ng.h1_scal(A, p["free"], ngs_amg_max_coarse_size=20, ngs_amg_mg_cycle=cycle, ngs_amg_sm_steps=steps, ngs_amg_sm_symm=symm)
+    rac = R.RefAMG(to_oracle(A), p["free"], [to_oracle(P) for P in pcc.GetMap()], sm_steps=steps, sm_symm=symm)
+    assert np.allclose(pcc.GetOC(), rac.get_oc(cycle), rtol=1e-14, atol=0)
+
+
 def test_pcg_iterations_vs_reference_code(pois):
     p, A, pc, ra = pois
     cg = ng.CGSolver(mat=A, pre=pc, maxsteps=50, tol=1e-8)

@@ -433,3 +433,17 @@ def test_mult_quartet_vs_reference_code():
             assert np.array_equal(ra.mult(b, x0.copy(), cyc, trans), ref)
             assert np.array_equal(ra.mult_add(-0.7, b, x0.copy(), cyc, trans), x0 + (-0.7) * ref)
     assert np.array_equal(oa.apply_add(-0.7, b, x0.copy()), ra.mult_add(-0.7, b, x0.copy()))
+
+
+@needs_ref
+def test_operator_complexity_accounting_of_the_reference():
+    """AMGMatrix::GetOC + BaseSmoother / ProxySmoother GetNOps / GetANZE (amg_matrix.cpp:551-582, base_smoother.hpp:145-150,
+    base_smoother.cpp:38-47): what the product's ngsamg_b200_operator_complexities restates (its GPU test compares the two)"""
+    p, A, prols = hierarchy("poisson")
+    ra = R.RefAMG(A, p["free"], prols, sm_steps=2, sm_symm=True)
+    nze = [ra.level_matrix(l).nnz for l in range(ra.nlevels)]
+    for cyc, fac in (("V", lambda l: 1.0), ("W", lambda l: 2.0 ** l), ("BS", lambda l: 2.0 * (1 + l))):
+        occ = ra.get_oc(cyc)
+        exp = [fac(l) * 2 * 2 * nze[l] / nze[0] for l in range(ra.nlevels - 1)] + [0.0]
+        assert np.allclose(occ[1:], exp, rtol=1e-15) and np.isclose(occ[0], sum(exp), rtol=1e-15)
+    assert len(R.RefAMG(A, p["free"], prols, coarse_inv=False).get_oc()) == ra.nlevels       # no entry for a level without inverse
