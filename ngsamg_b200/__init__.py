@@ -113,6 +113,9 @@ class AMGMatrix:
     def GetOC(self):
         return self._pc.GetOC()
 
+    def GetBF(self, vec, level, dof, comp=0, rank=0, onLevel=0):
+        return self._pc.GetBF(vec, level, dof, comp, rank, onLevel)
+
     def GetSmoother(self, level=0):
         return self._pc.GetSmoother(level)
 
@@ -301,6 +304,26 @@ class Preconditioner:
 
     def AddC2F(self, level, fac, xf, xc):
         _lib.check(self._lib.ngsamg_b200_prolong_add(self._h, int(level), float(fac), _lib.ptr(xc), _lib.ptr(xf)))
+
+    def GetBF(self, vec, level, dof, comp=0, rank=0, onLevel=0):
+        """AMGMatrix::GetBF (amg_matrix.cpp:438-510; python_amg.hpp:30-101): the coarse basis function of (level, dof, comp) prolongated down to
+        `onLevel` -- unit vector on `level`, then x_l = P_l x_{l+1} through the device transfers.  Single rank: rank must be 0."""
+        if rank != 0:
+            raise NgsAMGError("GetBF: rank %d does not exist (single-rank preconditioner)" % rank)
+        nl = self.GetNLevels()
+        if not (0 <= onLevel <= level < nl):
+            raise NgsAMGError("GetBF: invalid level %d (levels 0..%d, onLevel %d)" % (level, nl - 1, onLevel))
+        bs = self.GetBlockSize(level)
+        if not (0 <= comp < bs and 0 <= dof < self.GetNDof(level)):
+            raise NgsAMGError("GetBF: component %d / dof %d invalid on level %d" % (comp, dof, level))
+        x = np.zeros(self.GetNDof(level) * bs)
+        x[bs * dof + comp] = 1.0
+        for l in range(level - 1, onLevel - 1, -1):
+            xf = np.zeros(self.GetNDof(l) * self.GetBlockSize(l))
+            self.AddC2F(l, 1.0, xf, x)
+            x = xf
+        vec[:] = x
+        return vec
 
     def _pcg(self, rhs, x, tol, maxsteps):
         it = C.c_int(0)

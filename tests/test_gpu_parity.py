@@ -487,3 +487,21 @@ def test_tile_sweep_experimental(rows):
     cg.Solve(p["rhs"])
     _, ito, _ = amg.pcg(p["rhs"], tol=1e-8, maxsteps=50)
     assert cg.iterations == ito
+
+
+def test_get_bf_is_the_prolongation_chain(pois):
+    """AMGMatrix::GetBF (amg_matrix.cpp:438-510): a coarse basis function on the fine level = P_0 P_1 ... e_dof"""
+    p, A, pc, prols, amg = pois
+    lvl = pc.GetNLevels() - 1
+    dof = pc.GetNDof(lvl) // 2
+    vec = np.zeros(p["n"])
+    pc.GetBF(vec, lvl, dof)
+    e = np.zeros(pc.GetNDof(lvl)); e[dof] = 1.0
+    for P in reversed(prols[:lvl]):
+        e = P.to_scipy() @ e
+    assert rel(vec, e) < 1e-14
+    half = np.zeros(pc.GetNDof(1))
+    pc.GetBF(half, lvl, dof, onLevel=1)
+    assert rel(prols[0].to_scipy() @ half, e) < 1e-14
+    with pytest.raises(Exception):
+        pc.GetBF(vec, lvl, pc.GetNDof(lvl))
