@@ -105,6 +105,9 @@ int ngsamg_b200_smooth(ngsamg_b200_t *h, int level, double *x, const double *b, 
  *   restrict: xc = P_l^T xf ;  prolong_add: xf += fac * P_l xc */
 int ngsamg_b200_restrict(ngsamg_b200_t *h, int level, const double *xf, double *xc);
 int ngsamg_b200_prolong_add(ngsamg_b200_t *h, int level, double fac, const double *xc, double *xf);
+/* the exact coarsest-level solve alone: x = A_L^-1 rhs on the free dofs (crs_inv->Mult, amg_matrix.cpp:228-233; CoarseLevelInv,
+ * amg_pc.cpp:843-928); x = 0 if the hierarchy has no coarse inverse (clev=none).  Building block of AMGMatrix::CINV (amg_matrix.cpp:407-435). */
+int ngsamg_b200_coarse_solve(ngsamg_b200_t *h, const double *rhs, double *x);
 
 /* PCG with the V-cycle as preconditioner == ngsolve.krylovspace.CGSolver(mat, pre, maxsteps, tol) as the reference
  * tests call it (tests/h1/amg_utils.py:346-349).  errors has room for maxsteps+1 doubles (errors[0] = err0);

@@ -116,6 +116,9 @@ class AMGMatrix:
     def GetBF(self, vec, level, dof, comp=0, rank=0, onLevel=0):
         return self._pc.GetBF(vec, level, dof, comp, rank, onLevel)
 
+    def CINV(self, x, b):
+        return self._pc.CINV(x, b)
+
     def GetSmoother(self, level=0):
         return self._pc.GetSmoother(level)
 
@@ -304,6 +307,29 @@ class Preconditioner:
 
     def AddC2F(self, level, fac, xf, xc):
         _lib.check(self._lib.ngsamg_b200_prolong_add(self._h, int(level), float(fac), _lib.ptr(xc), _lib.ptr(xf)))
+
+    def CoarseSolve(self, rhs, x):
+        """crs_inv->Mult on the coarsest level (amg_matrix.cpp:228-233)"""
+        _lib.check(self._lib.ngsamg_b200_coarse_solve(self._h, _lib.ptr(rhs), _lib.ptr(x)))
+        return x
+
+    def CINV(self, x, b):
+        """AMGMatrix::CINV (amg_matrix.cpp:407-435): restrict b through all levels (TransferF2C), solve exactly on the coarsest level,
+        prolongate the result back (TransferC2F) -- the coarse-grid correction without any smoothing"""
+        nl = self.GetNLevels()
+        r = np.ascontiguousarray(b, np.float64)
+        for l in range(nl - 1):
+            rc = np.zeros(self.GetNDof(l + 1) * self.GetBlockSize(l + 1))
+            self.TransferF2C(l, r, rc)
+            r = rc
+        xc = np.zeros_like(r)
+        self.CoarseSolve(r, xc)
+        for l in range(nl - 2, -1, -1):
+            xf = np.zeros(self.GetNDof(l) * self.GetBlockSize(l))
+            self.AddC2F(l, 1.0, xf, xc)
+            xc = xf
+        x[:] = xc
+        return x
 
     def GetBF(self, vec, level, dof, comp=0, rank=0, onLevel=0):
         """AMGMatrix::GetBF (amg_matrix.cpp:438-510; python_amg.hpp:30-101): the coarse basis function of (level, dof, comp) prolongated down to

@@ -2424,6 +2424,25 @@ int ngsamg_b200_restrict(ngsamg_b200_t *h, int level, const double *xf, double *
   NGB_CATCH
 }
 
+// exact solve on the coarsest level (crs_inv->Mult, amg_matrix.cpp:228-233); x = 0 when the hierarchy was built with clev=none
+int ngsamg_b200_coarse_solve(ngsamg_b200_t *h, const double *rhs, double *x)
+{
+  NGB_TRY
+  Amg &a = ready(h);
+  Level &C = get_level(a, (int)a.lev.size() - 1);
+  const i64 nc = C.n * C.b;
+  a.ensure_io(nc);
+  const double *rd = a.to_device(rhs, nc, a.io_a);
+  k_permute_in<<<nblk(C.n), TB, 0, a.st>>>(C.n, C.b, C.d_perm, rd, C.rhs);
+  if (a.has_cinv) k_dense_gemv<<<nblk((i64)a.cinv_n * 32), TB, 0, a.st>>>(a.cinv_n, a.d_cinv, C.rhs, C.x);
+  else NGB_CUDA(cudaMemsetAsync(C.x, 0, sizeof(double) * C.npad * C.b, a.st));
+  k_permute_out<<<nblk(C.n), TB, 0, a.st>>>(C.n, C.b, C.d_perm, C.x, a.io_b, 1.0, 0);
+  a.from_device(x, a.io_b, nc);
+  a.launches += 3;
+  NGB_CUDA(cudaGetLastError());
+  NGB_CATCH
+}
+
 int ngsamg_b200_prolong_add(ngsamg_b200_t *h, int level, double fac, const double *xc, double *xf)
 {
   NGB_TRY

@@ -505,3 +505,19 @@ def test_get_bf_is_the_prolongation_chain(pois):
     assert rel(prols[0].to_scipy() @ half, e) < 1e-14
     with pytest.raises(Exception):
         pc.GetBF(vec, lvl, pc.GetNDof(lvl))
+
+
+def test_cinv_is_the_unsmoothed_coarse_grid_correction(pois):
+    """AMGMatrix::CINV (amg_matrix.cpp:407-435): x = P_0 .. P_{L-2} A_L^-1 P_{L-2}^T .. P_0^T b"""
+    p, A, pc, prols, amg = pois
+    b = rand(61, p["n"])
+    x = np.zeros(p["n"])
+    pc.CINV(x, b)
+    r = b.copy()
+    for P in prols:
+        r = P.to_scipy().T @ r
+    Ac = amg.level_matrix(pc.GetNLevels() - 1).to_scipy().toarray()
+    e = np.linalg.solve(Ac, r)
+    for P in reversed(prols):
+        e = P.to_scipy() @ e
+    assert rel(x, e) < 1e-10
