@@ -156,6 +156,12 @@ public:
     ngsamg_level_info i; check(ngsamg_b200_level_info(h, level, &i)); return {i.n, i.b};
   }
   double GetOC() const { return ngsamg_b200_operator_complexity(h); }
+  // AMGMatrix::GetOC (amg_matrix.cpp:551-582): [OC, OC_l0, OC_l1, ...]
+  std::vector<double> GetOCs() const {
+    std::vector<double> occs((size_t)ngsamg_b200_operator_complexities(h, nullptr, 0));
+    if (!occs.empty()) ngsamg_b200_operator_complexities(h, occs.data(), (int)occs.size());
+    return occs;
+  }
   BaseSmoother GetSmoother(int level) const
   {
     if (level + 1 >= (int)GetNLevels()) throw Exception("only have " + std::to_string(GetNLevels() - 1) + " smoothers");
