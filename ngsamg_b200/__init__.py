@@ -219,6 +219,32 @@ class Preconditioner:
     def GetBlockSize(self, level=0):
         return int(self.level_info(level).b)
 
+    def GetNProcs(self, level=0):
+        """number of ranks holding `level` (python_amg.hpp:36-48): 1 for the single-rank preconditioner"""
+        return 1
+
+    @staticmethod
+    def __flags_doc__():
+        return {}
+
+    def RegularizeMatrix(self, mat):
+        """VertexAMGPC::RegularizeMatrix (python_amg.hpp:86-91; elasticity_pc_impl.hpp:711-763), local branch: regularises the diagonal blocks
+        of `mat` in place (elast_3d: RegTM<0,6,6> on 6x6 blocks, elast_2d: unit rotational entry on 3x3 blocks; no-op for the H1 classes)"""
+        dim = {"elast_3d": 3, "elast_2d": 2}.get(self._type, 0)
+        if not dim or mat.bh != mat.bw or mat.bh != (6 if dim == 3 else 3):
+            return mat
+        bb = mat.bh * mat.bh
+        val = mat.val.reshape(-1, bb)
+        self._lib.ngsamg_b200_block_regularize.argtypes = [C.c_int, C.c_void_p, C.c_int]
+        for i in range(mat.nrows):
+            for k in range(mat.rowptr[i], mat.rowptr[i + 1]):
+                if mat.col[k] == i:
+                    blk = np.ascontiguousarray(val[k])
+                    _lib.check(self._lib.ngsamg_b200_block_regularize(mat.bh, blk.ctypes.data_as(C.c_void_p), dim))
+                    val[k] = blk
+        mat.val = np.ascontiguousarray(val.reshape(-1))
+        return mat
+
     def GetNDBS(self, level, rank=0):
         i = self.level_info(level)
         return int(i.n), int(i.b)

@@ -169,3 +169,26 @@ def test_cpp_host_mirror_on_gpu(tmp_path):
     r = subprocess.run([exe], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, (r.returncode, r.stdout, r.stderr)
     assert "rap_pattern_same=1" in r.stdout
+
+
+def test_regularize_matrix_method_is_host_only():
+    """RegularizeMatrix of the elasticity classes (python_amg.hpp:86-91) works on a matrix object without a device: it only needs the
+    host-side block routine"""
+    import ngsamg_b200 as ng
+    import numpy as np
+    rng = np.random.default_rng(0)
+    X = rng.standard_normal((6, 6))
+    spd = X @ X.T + 6 * np.eye(6)
+    lone = np.zeros((6, 6)); lone[:3, :3] = spd[:3, :3]
+    # 2 x 2 block matrix: diagonal blocks spd / lone, one off-diagonal block
+    M = ng.SparseMatrix(2, 2, 6, 6, [0, 2, 3], [0, 1, 1], np.stack([spd, spd, lone]).reshape(-1))
+    pc = object.__new__(ng.elast_3d)                       # no device: only the method and the library are needed
+    from ngsamg_b200 import _lib
+    pc._lib = _lib.lib()
+    out = ng.elast_3d.RegularizeMatrix(pc, M).val.reshape(3, 6, 6)
+    assert np.array_equal(out[0], spd) and np.array_equal(out[1], spd)            # regular diagonal block and the off-diagonal block: untouched
+    assert np.allclose(out[2][3:, 3:], np.eye(3) * np.linalg.eigvalsh(spd[:3, :3]).min())   # lone vertex: smallest non-zero eigenvalue on the rotations
+    h1 = object.__new__(ng.h1_scal)
+    h1._lib = pc._lib
+    before = M.val.copy()
+    assert h1.RegularizeMatrix(M) is M and np.array_equal(M.val, before) and pc.GetNProcs() == 1      # H1: nothing to regularise
