@@ -116,8 +116,6 @@ INLINE void wait_request(NG_MPI_Request &r) {
 }
 INLINE void MyMPI_WaitAll(FlatArray<NG_MPI_Request> reqs) { for (auto &r : reqs) wait_request(r); }
 
-template <class TM> class SparseMatrixShim;  // (unused; sparse matrices travel as shared copies, see NgMPI_Comm::ISend below)
-
 class NgMPI_Comm {
 public:
   World *w = nullptr;

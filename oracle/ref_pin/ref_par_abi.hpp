@@ -22,8 +22,8 @@ struct ParH {
   std::vector<ParRank> rk;
 };
 
-// f(rank) on R threads; the first failure aborts the world (nobody is left waiting for a message that never comes)
-template <class F> int run_ranks(ParH *h, F f) {
+// f(rank state) on R threads; the first failure aborts the world (nobody is left waiting for a message that never comes)
+template <class H, class F> int run_ranks(H *h, F f) {
   std::vector<std::string> errs(h->R);
   std::vector<std::thread> th;
   for (int r = 0; r < h->R; r++)
@@ -36,10 +36,9 @@ template <class F> int run_ranks(ParH *h, F f) {
       }
     });
   for (auto &t : th) t.join();
-  for (int r = 0; r < h->R; r++)
-    if (!errs[r].empty() && errs[r].find("another rank failed") == std::string::npos) { g_err = "rank " + std::to_string(r) + ": " + errs[r]; return 1; }
-  for (int r = 0; r < h->R; r++)
-    if (!errs[r].empty()) { g_err = errs[r]; return 1; }
+  for (int pass = 0; pass < 2; pass++)     // report the rank that failed first-hand, not the ones that were woken up by the abort
+    for (int r = 0; r < h->R; r++)
+      if (!errs[r].empty() && (pass == 1 || errs[r].find("another rank failed") == std::string::npos)) { g_err = "rank " + std::to_string(r) + ": " + errs[r]; return 1; }
   return 0;
 }
 
@@ -271,25 +270,6 @@ public:
   }
 };
 
-template <class F> int run_amg_ranks(ParAmgH *h, F f) {
-  std::vector<std::string> errs(h->R);
-  std::vector<std::thread> th;
-  for (int r = 0; r < h->R; r++)
-    th.emplace_back([&, r] {
-      try {
-        f(h->rk[r]);
-      } catch (const std::exception &e) {
-        errs[r] = e.what();
-        h->world->abort();
-      }
-    });
-  for (auto &t : th) t.join();
-  for (int pass = 0; pass < 2; pass++)
-    for (int r = 0; r < h->R; r++)
-      if (!errs[r].empty() && (pass == 1 || errs[r].find("another rank failed") == std::string::npos)) { g_err = "rank " + std::to_string(r) + ": " + errs[r]; return 1; }
-  return 0;
-}
-
 template <int B> void paramg_level_setup(ParAmgH *h, ParAmgRank &K, int l, int sm_steps, bool sm_symm, bool overlap) {
   typedef typename spm_entry<B, B>::type TM;
   ParLevel &L = K.lev[l];
@@ -426,7 +406,7 @@ int ref_paramg_set_contraction(void *hv, int r, i64 n, const i64 *map, i64 n_mer
 
 int ref_paramg_setup(void *hv, int sm_steps, int sm_symm, int overlap) {
   ParAmgH *h = (ParAmgH *)hv;
-  return run_amg_ranks(h, [&](ParAmgRank &K) {
+  return run_ranks(h, [&](ParAmgRank &K) {
     AMGMatrix &M = K.amg;
     M.smoothers.SetSize(h->nlev - 1);
     M.x_level.SetSize(h->nlev); M.rhs_level.SetSize(h->nlev); M.res_level.SetSize(h->nlev);
@@ -475,7 +455,7 @@ int ref_paramg_set_nested(void *hv, void *nested) {
 // x = C b: b[r] DISTRIBUTED local vectors, x[r] CUMULATED on return (AMGMatrix::SmoothV on every rank)
 int ref_paramg_apply(void *hv, double **b, double **x) {
   ParAmgH *h = (ParAmgH *)hv;
-  return run_amg_ranks(h, [&](ParAmgRank &K) {
+  return run_ranks(h, [&](ParAmgRank &K) {
     ParLevel &L = K.lev[0];
     const size_t n = L.A->m->Height();
     BaseVector vx(n, L.b), vb(n, L.b);
@@ -490,7 +470,7 @@ int ref_paramg_apply(void *hv, double **b, double **x) {
 // y = (M + G) x on level 0 (HybridBaseMatrix::Mult), for the CG around the cycle
 int ref_paramg_mult(void *hv, double **x, double **y) {
   ParAmgH *h = (ParAmgH *)hv;
-  return run_amg_ranks(h, [&](ParAmgRank &K) {
+  return run_ranks(h, [&](ParAmgRank &K) {
     ParLevel &L = K.lev[0];
     const size_t n = L.A->m->Height();
     BaseVector vx(n, L.b), vy(n, L.b);
