@@ -157,3 +157,75 @@ def test_tile_schedule_with_cluster_hints_reaches_the_box_bound():
     assert d["tile_depth"] <= bx + by + bz - 2
     d2 = tile_schedule(A, p["free"], None)
     assert d2["tile_depth"] <= 1.6 * d["tile_depth"]
+
+
+def emulate_backward(A, free, d, t_in, x_old):
+    """backward triangular half-sweep on the tile schedule, data flow as in k_gs_tile<.., ADD_SELF=true, WRITE_R=false> with backward = 1:
+    tiles in REVERSE schedule order waiting for their SUCCESSORS, tile-local levels descending;
+    x_new_i = x_old_i + (t_i - sum_{U} A_ik x_new_k) / d_i   (post-smoother: t = b - (L + D) x_old)"""
+    n = A.shape[0]
+    perm = d["perm"].astype(np.int64)
+    inv = np.full(d["npad"], -1, np.int64)
+    inv[perm] = np.arange(n)
+    Ap = A.tocsr()
+    diag = Ap.diagonal()
+    nt = d["ntiles"]
+    succ = [[] for _ in range(nt)]                       # the kernel gets these from the scheduler (transpose of the predecessor lists)
+    for t in range(nt):
+        for q in d["pred"][d["pred_ptr"][t]:d["pred_ptr"][t + 1]]:
+            succ[q].append(t)
+    out = x_old.copy()
+    done = np.zeros(nt, bool)
+    for t in range(nt - 1, -1, -1):
+        for q in succ[t]:
+            assert done[q], "a tile runs before a tile it waits for (backward)"
+        r0, r1 = d["tile_slice"][t] * 32, d["tile_slice"][t + 1] * 32
+        rows = [r for r in range(r0, r1) if d["row_lvl"][r] != 255]
+        acc = {}
+        for r in rows:                                   # couplings to HIGHER rows of other tiles: final values
+            i = inv[r]
+            a = t_in[i]
+            for k in range(Ap.indptr[i], Ap.indptr[i + 1]):
+                j = Ap.indices[k]
+                pj = perm[j]
+                if j != i and free[j] and pj > r and not (r0 <= pj < r1):
+                    a -= Ap.data[k] * out[j]
+            acc[r] = a
+        for s in range(d["tile_nlev"][t] - 1, -1, -1):   # tile-local levels, descending
+            for r in rows:
+                if d["row_lvl"][r] != s:
+                    continue
+                i = inv[r]
+                a = acc[r]
+                for k in range(Ap.indptr[i], Ap.indptr[i + 1]):
+                    j = Ap.indices[k]
+                    pj = perm[j]
+                    if j != i and free[j] and pj > r and r0 <= pj < r1:
+                        assert d["row_lvl"][pj] > s, "in-tile dependency on the same or an earlier local level (backward)"
+                        a -= Ap.data[k] * out[j]
+                out[i] = x_old[i] + a / diag[i]
+        done[t] = True
+    return out
+
+
+@pytest.mark.parametrize("cfg", [dict(rounds=5, max_rows=32), dict(rounds=6, max_rows=64)])
+def test_tile_schedule_backward_sweep(cfg):
+    """the same schedule run backwards (successor lists, descending local levels) == GSS3::SmoothRHSInternal(backwards) of the oracle"""
+    p = S.poisson3d_kuhn(11, 13, 9)
+    A = ng.SparseMatrix(p["n"], p["n"], 1, 1, p["rowptr"], p["col"], p["val"])
+    d = tile_schedule(A, p["free"], None, **cfg)
+    assert d["ok"] == 1 and d["violations"] == 0
+    As = to_oracle(A).to_scipy().tocsr()
+    free = p["free"].astype(bool)
+    # tile-major numbering keeps every dependency's orientation: perm is monotone along every edge of the sweep DAG
+    x_old, b = rand(5, p["n"]) * p["free"], rand(6, p["n"]) * p["free"]
+    LD = sp.tril(As, 0).tocsr()
+    t_in = b - LD @ x_old                                   # the parallel half of the post-smoother (one SpMV on the device)
+    # couplings to non-free columns do not enter the sweep (their x is fixed): move them to the right-hand side like the kernel's N part
+    nf = sp.diags((~free).astype(float))
+    t_in = t_in - sp.triu(As, 1).tocsr() @ (nf @ x_old)
+    x_new = emulate_backward(As, free, d, t_in, x_old)
+    xo = x_old.copy()
+    dinv = O.calc_dinv(to_oracle(A), p["free"])
+    O.gs_rhs(to_oracle(A), dinv, p["free"], xo, b, True)
+    assert rel(x_new[free], xo[free]) < 1e-13
