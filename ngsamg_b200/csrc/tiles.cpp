@@ -1,6 +1,7 @@
 // tiles.cpp -- host construction of the two-level (tile DAG x tile-local levels) Gauss-Seidel schedule, see tiles.hpp.
 #include "tiles.hpp"
 
+#include <cstdlib>
 #include <numeric>
 #include <queue>
 
@@ -92,7 +93,7 @@ void build_tile_schedule(const HostBsr &A, const std::vector<uint8_t> &mask, con
       nagg = std::max<i64>(nagg, (i64)agg[i] + 1);
     }
   } else
-    nagg = cluster_rows(A, hm ? mask.data() : nullptr, rounds, 0.25, agg, true);
+    nagg = cluster_rows(A, hm ? mask.data() : nullptr, rounds, 0.25, agg, true);   // stricter strength thresholds (0.6 .. 0.99) were tried: deeper tile DAGs
 
   // ---- 2. tiles = consecutive chunks of a topological order of the row DAG (=> the tile graph is acyclic by construction).
   // The order is produced by list scheduling that stays inside one cluster as long as that cluster has executable rows: a cluster
