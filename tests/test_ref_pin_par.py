@@ -225,3 +225,24 @@ def test_parallel_vcycle_and_pcg_vs_reference_code(grid, steps, symm):
     u1, it1, e1 = oa.pcg(rhs, tol=1e-8, maxsteps=60)
     u2, it2, e2 = ra.pcg(rhs, tol=1e-8, maxsteps=60)
     assert it1 == it2 and rel(e1, e2) < 1e-10
+
+
+@needs_ref
+def test_parallel_elasticity_hierarchy_vs_reference_code():
+    """3x3 fine / 6x6 coarse blocks on two distributed levels (HybridGSSmoother<Mat<3,3>> / <Mat<6,6>>, ProlMap<Mat<3,6>>, DCCMap with block
+    size 6, CtrMap<Vec<6>>): downward leg bit for bit, contracted matrix bit for bit"""
+    from oracle import cpu_pipeline as CP
+    from helpers import rand, rel
+    parts = S.partition_elasticity3d(13, 5, 5, 2)
+    hier, info = CP.build(parts, b=3, elast=True, ctr_nv=8, max_coarse=3, engine="args")
+    assert info["distributed_levels"] == 2
+    oa, ra = OP.OracleParAMG(*hier, pinv=False), R.RefParAMG(*hier)
+    Am, Ao = ra.A_merged, oa.A_merged
+    assert Am.bh == 6 and np.array_equal(Am.rowptr, Ao.rowptr) and np.array_equal(Am.col, Ao.col) and np.array_equal(Am.val, Ao.val)
+    b = [rand(7 + r, p["n"] * 3) * np.repeat(p["free"], 3) for r, p in enumerate(parts)]
+    xo, xr = oa.apply(b), ra.apply(b)
+    for l in range(oa.npar):
+        for r in range(2):
+            assert np.array_equal(ra.level_vec("res", l, r), oa.level_res[l][r])
+            assert np.array_equal(ra.level_vec("rhs", l + 1, r), oa.level_rhs[l + 1][r])
+    assert max(rel(xr[r], xo[r]) for r in range(2)) < 1e-12
