@@ -225,6 +225,16 @@ int ngsamg_b200_hybrid_host_begin(const ngsamg_csr *A, const uint8_t *free_mask,
 int ngsamg_b200_hybrid_host_fetch(ngsamg_b200_hybrid_host *m, int64_t *m_rowptr, int32_t *m_col, double *m_val, int64_t *g_rowptr,
                                   int32_t *g_col, double *g_val, double *mod_diag, int32_t *sweep_rank, uint8_t *master);
 
+/* host-only: contraction of one distributed level onto rank 0 -- CtrMap::DoAssembleMatrix (src/base/coarsening/dof_contract.cpp:557-727) for ONE
+ * group with master 0: the members' local (DISTRIBUTED) matrices are remapped through the dof maps, the column lists merged (structural union:
+ * entries that cancel stay) and coinciding entries summed in rank order.  Collective over the ranks of `comm`; rank 0 receives the merged matrix and
+ * the maps local dof -> merged dof of every rank (master dofs numbered rank by rank, a ghost takes its master's number).  Lets the CPU tests check
+ * the host contraction the multi-GPU path uses without a device.  map_total = length of the concatenated dof maps (rank 0). */
+typedef struct ngsamg_b200_contract_host ngsamg_b200_contract_host;
+int ngsamg_b200_contract_host_begin(const ngsamg_csr *A, const uint8_t *free_mask, const ngsamg_halo *halo, const ngsamg_comm *comm,
+                                    ngsamg_b200_contract_host **out, int64_t *n_merged, int64_t *nnz_merged, int64_t *map_total);
+int ngsamg_b200_contract_host_fetch(ngsamg_b200_contract_host *m, int64_t *rowptr, int32_t *col, double *val, int64_t *map_ptr, int32_t *dof_map);
+
 /* ---- standalone sparse kernels (setup path) ----------------------------------------------------
  * Galerkin product on the device: Ac = (P^T A) P.   RestrictMatrix<H,W>, utils_sparseMM.hpp:93-109;
  * MatMultABImpl utils_sparseMM.cpp:107-238; TransposeSPMImpl :54-93.

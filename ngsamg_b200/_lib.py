@@ -26,6 +26,7 @@ EXPORTS = [
     "ngsamg_b200_create_parallel", "ngsamg_b200_nccl_unique_id", "ngsamg_b200_nccl_comm_init", "ngsamg_b200_nccl_comm_destroy",
     "ngsamg_b200_get_halo", "ngsamg_b200_get_hybrid", "ngsamg_b200_num_parallel_levels", "ngsamg_b200_get_contracted",
     "ngsamg_b200_get_contraction_map", "ngsamg_b200_hybrid_host_begin", "ngsamg_b200_hybrid_host_fetch",
+    "ngsamg_b200_contract_host_begin", "ngsamg_b200_contract_host_fetch",
     "ngsamg_b200_coarsen_parallel_begin", "ngsamg_b200_coarsen_parallel_fetch",
     "ngsamg_b200_tile_schedule_begin", "ngsamg_b200_tile_schedule_hinted", "ngsamg_b200_tile_schedule_fetch", "ngsamg_b200_tiles_last_error", "ngsamg_b200_block_pinv", "ngsamg_b200_block_regularize",
 ]
@@ -116,6 +117,8 @@ def lib():
     L.ngsamg_b200_get_contraction_map.argtypes = [vp, ci, vp, vp]
     L.ngsamg_b200_hybrid_host_begin.argtypes = [C.POINTER(Csr), vp, vp, vp, C.POINTER(vp), C.POINTER(i64), C.POINTER(i64)]
     L.ngsamg_b200_hybrid_host_fetch.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]
+    L.ngsamg_b200_contract_host_begin.argtypes = [C.POINTER(Csr), vp, vp, vp, C.POINTER(vp), C.POINTER(i64), C.POINTER(i64), C.POINTER(i64)]
+    L.ngsamg_b200_contract_host_fetch.argtypes = [vp, vp, vp, vp, vp, vp]
     L.ngsamg_b200_coarsen_parallel_begin.argtypes = [C.POINTER(Csr), vp, vp, vp, vp, ci, ci, dbl, dbl, ci, ci, C.POINTER(vp), C.POINTER(i64),
                                                      C.POINTER(i64), C.POINTER(C.c_int32), C.POINTER(i64)]
     L.ngsamg_b200_coarsen_parallel_fetch.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, vp]

@@ -2263,6 +2263,56 @@ int ngsamg_b200_hybrid_host_fetch(ngsamg_b200_hybrid_host *m, int64_t *m_rowptr,
   NGB_CATCH
 }
 
+// host-only: contraction of one distributed level onto rank 0 (par.cpp: contract_to_root = CtrMap::DoAssembleMatrix + the dof maps).  Collective;
+// only rank 0 gets data: the merged matrix and, per rank, the map local dof -> merged dof.
+struct ngsamg_b200_contract_host { Contraction c; };
+
+int ngsamg_b200_contract_host_begin(const ngsamg_csr *A, const uint8_t *free_mask, const ngsamg_halo *halo, const ngsamg_comm *comm,
+                                    ngsamg_b200_contract_host **out, int64_t *n_merged, int64_t *nnz_merged, int64_t *map_total)
+{
+  NGB_TRY
+  if (!comm || !out) throw Error("null argument");
+  check_csr(A, "contract_host");
+  HostBsr hA;
+  copy_csr(A, hA);
+  ParDofs pd;
+  halo_to_pardofs(halo, A->nrows, comm->rank, pd);
+  Comm c;
+  c.c = *comm;
+  std::vector<uint8_t> fm;
+  if (free_mask) fm.assign(free_mask, free_mask + A->nrows);
+  auto r = std::make_unique<ngsamg_b200_contract_host>();
+  contract_to_root(c, pd, hA, fm, std::vector<double>(), r->c);
+  if (n_merged) *n_merged = r->c.A.nrows;
+  if (nnz_merged) *nnz_merged = r->c.A.nnz();
+  if (map_total) { *map_total = 0; for (auto &m : r->c.dof_maps) *map_total += (i64)m.size(); }
+  *out = r.release();
+  NGB_CATCH
+}
+
+// rank 0: rowptr[n_merged + 1], col, val of the merged matrix; dof_map: concatenation over the ranks of local -> merged (map_ptr[R + 1] offsets).
+// Other ranks: nothing is written.  Frees the handle.
+int ngsamg_b200_contract_host_fetch(ngsamg_b200_contract_host *m, int64_t *rowptr, int32_t *col, double *val, int64_t *map_ptr, int32_t *dof_map)
+{
+  NGB_TRY
+  if (!m) throw Error("null handle");
+  const HostBsr &H = m->c.A;
+  if (H.nrows > 0 || !m->c.dof_maps.empty()) {
+    if (rowptr) std::memcpy(rowptr, H.rowptr.data(), sizeof(i64) * (H.nrows + 1));
+    if (col) std::memcpy(col, H.col.data(), sizeof(i32) * H.nnz());
+    if (val) std::memcpy(val, H.val.data(), sizeof(double) * H.nnz() * H.bs());
+    i64 off = 0;
+    for (size_t r = 0; r < m->c.dof_maps.size(); r++) {
+      if (map_ptr) map_ptr[r] = off;
+      if (dof_map) std::memcpy(dof_map + off, m->c.dof_maps[r].data(), sizeof(i32) * m->c.dof_maps[r].size());
+      off += (i64)m->c.dof_maps[r].size();
+    }
+    if (map_ptr) map_ptr[m->c.dof_maps.size()] = off;
+  }
+  delete m;
+  NGB_CATCH
+}
+
 int ngsamg_b200_set_prolongations(ngsamg_b200_t *h, int nprol, const ngsamg_csr *P)
 {
   NGB_TRY

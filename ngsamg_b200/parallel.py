@@ -336,6 +336,28 @@ def hybrid_host(mat, halo, comm, freedofs=None):
                 G=SparseMatrix(n, n, mat.bh, mat.bw, grp, gci[:ng.value], gv[:ng.value * bs]), mod_diag=md, sweep_rank=sw, master=ma)
 
 
+def contract_host(mat, halo, comm, freedofs=None):
+    """host-only contraction of one distributed level onto rank 0 (collective): rank 0 gets (merged SparseMatrix, [dof map per rank]),
+    the other ranks (None, None)"""
+    L = _lib.lib()
+    fm = None if freedofs is None else np.ascontiguousarray(freedofs, dtype=np.uint8)
+    h, n, nz, nmap = C.c_void_p(), C.c_int64(), C.c_int64(), C.c_int64()
+    abi, habi = mat._abi(), halo._abi()
+    rc = L.ngsamg_b200_contract_host_begin(C.byref(abi), _lib.ptr(fm), C.byref(habi), C.byref(comm.struct), C.byref(h), C.byref(n), C.byref(nz),
+                                           C.byref(nmap))
+    if rc:
+        raise NgsAMGError(L.ngsamg_b200_last_error().decode() + (" [callback: %r]" % (comm.error,) if comm.error else ""))
+    if comm.rank != 0:
+        _lib.check(L.ngsamg_b200_contract_host_fetch(h, None, None, None, None, None))
+        return None, None
+    bs = mat.bh * mat.bw
+    rp, ci, v = np.zeros(n.value + 1, np.int64), np.zeros(max(nz.value, 1), np.int32), np.zeros(max(nz.value, 1) * bs)
+    mp, dm = np.zeros(comm.size + 1, np.int64), np.zeros(max(nmap.value, 1), np.int32)
+    _lib.check(L.ngsamg_b200_contract_host_fetch(h, _lib.ptr(rp), _lib.ptr(ci), _lib.ptr(v), _lib.ptr(mp), _lib.ptr(dm)))
+    maps = [dm[mp[r]:mp[r + 1]].astype(np.int64) for r in range(comm.size)]
+    return SparseMatrix(n.value, n.value, mat.bh, mat.bw, rp, ci[:nz.value], v[:nz.value * bs]), maps
+
+
 def coarsen_par(mat, halo, comm, freedofs=None, vertex_xyz=None, bcoarse=None, max_per_row=3, min_frac=0.08, omega=1.0, smooth=True,
                 rounds=3):
     """host-only: one class-respecting coarsening step of a distributed level (collective).  Returns (P, vmap, coarse_xyz, coarse Halo)."""

@@ -209,3 +209,39 @@ def test_multirank_golden_fixture():
     assert it == int(g["pcg_iters"]) and np.allclose(errs, g["pcg_errors"], rtol=1e-9)
     for r in range(2):
         assert np.linalg.norm(u[r] - g["pcg_u%d" % r]) <= 1e-10 * np.linalg.norm(g["pcg_u%d" % r])
+
+
+@pytest.mark.parametrize("grid", [(1, 1, 2), (1, 2, 2), (2, 2, 2)])
+def test_host_contraction_is_the_reference_ctrmap(grid):
+    """contract_to_root (par.cpp), the host contraction of the multi-GPU path, against oracle_par.merge_contracted -- which
+    tests/test_ref_pin_par.py pins bit for bit to the reference's CtrMap::DoAssembleMatrix (dof_contract.cpp:557-727): same pattern
+    (structural union: entries that cancel across ranks stay), same values (members summed in rank order)"""
+    parts = S.partition_poisson3d(7, 6, 9, grid=grid)
+    R = len(parts)
+
+    def fn(r, comm):
+        p = parts[r]
+        A = ng.SparseMatrix(p["n"], p["n"], 1, 1, p["rowptr"], p["col"], p["val"])
+        return par.contract_host(A, par.Halo(p["peers"], p["ex"]), comm, p["free"])
+
+    res = par.run_ranks(R, fn)
+    merged, maps = res[0]
+    assert all(res[r] == (None, None) for r in range(1, R))
+    N = merged.nrows
+    g = S.poisson3d_kuhn(7, 6, 9)
+    assert N == g["n"]                                              # every global dof has exactly one master
+    for r, p in enumerate(parts):                                   # shared dofs of different ranks map to the same merged dof
+        for kp, q in enumerate(p["peers"]):
+            kq = list(parts[q]["peers"]).index(r)
+            assert np.array_equal(maps[r][p["ex"][kp]], maps[q][parts[q]["ex"][kq]])
+    A_loc = [O.Bsr(p["n"], p["n"], 1, 1, p["rowptr"], p["col"], p["val"]) for p in parts]
+    ref = OP.merge_contracted(A_loc, maps, N, 1)
+    assert np.array_equal(merged.rowptr, ref.rowptr) and np.array_equal(merged.col, ref.col), "contracted pattern"
+    assert np.array_equal(merged.val, ref.val), "contracted values"
+    # and it is the assembled global operator up to the renumbering
+    G = sp.csr_matrix((g["val"], g["col"], g["rowptr"]), shape=(N, N))
+    perm = np.zeros(N, np.int64)
+    for r, p in enumerate(parts):
+        perm[p["gidx"]] = maps[r]
+    Pm = sp.csr_matrix((np.ones(N), (perm, np.arange(N))), shape=(N, N))
+    assert abs(merged.to_scipy() - Pm @ G @ Pm.T).max() < 1e-13
