@@ -58,6 +58,8 @@ FRAGMENTS = [
     ("rich_smooth", "src/base/smoothers/base_smoother.cpp", r"^void RichardsonSmoother :: Smooth \(", "line", None),
     ("rich_smoothback", "src/base/smoothers/base_smoother.cpp", r"^void RichardsonSmoother :: SmoothBack \(", "line", None),
     ("jacobi_ctor", "src/base/smoothers/base_smoother.cpp", r"^JacobiSmoother<TM>::JacobiSmoother \(", "template", None),
+    # --- rigid-body transport between vertices (elasticity prolongation blocks) ---------------------------------------
+    ("el_calcq", "src/elasticity/elasticity_energy_impl.hpp", r"^INLINE void EpsEpsEnergy<DIM, TVD, TED>::CalcQ\(const Vec<DIM>& t, TM& Q,", "template", None),
     # --- grid transfer -----------------------------------------------------------------------------------------
     ("prol_f2c", "src/base/coarsening/dof_map.cpp", r"^TransferF2C \(BaseVector const \*x_fine,", "template", r"^timer_hack_prol_c2f"),
     ("prol_addc2f", "src/base/coarsening/dof_map.cpp", r"^AddC2F \(double fac, BaseVector \*x_fine, BaseVector const \*x_coarse\) const", "template",

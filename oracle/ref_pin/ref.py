@@ -148,6 +148,17 @@ def pinv_block(m):
     return a
 
 
+def elast_calcq(t, si=1.0, sj=1.0):
+    """EpsEpsEnergy<DIM>::CalcQ (elasticity_energy_impl.hpp:8-29): the rigid-body transport block for the offset t (len 2 or 3)"""
+    L = lib()
+    L.ref_elast_calcq.argtypes = [C.c_int, f64p, C.c_double, C.c_double, f64p]
+    t = np.ascontiguousarray(t, np.float64)
+    n = 6 if len(t) == 3 else 3
+    q = np.zeros(n * n)
+    _check(L.ref_elast_calcq(len(t), t, float(si), float(sj), q))
+    return q.reshape(n, n)
+
+
 def regularize_block6(m):
     """RegTM<0,6,6> (utils_denseLA.hpp:1198-1234) on one block"""
     L = lib()

@@ -164,6 +164,17 @@ public:
 #include "../_ref/frag/gss3_smooth.inc"
 #include "../_ref/frag/gss3_smoothback.inc"
 
+// ---- rigid-body transport Q(t) of the elasticity energy (elasticity_energy.hpp:19-30, 823; elasticity_energy_impl.hpp:8-29) ----------
+template <int DIM, class TVD, class TED> class EpsEpsEnergy {
+public:
+  static constexpr int DISPPV = DIM;
+  static constexpr int ROTPV = (DIM == 2) ? 1 : 3;
+  static constexpr int DPV = DISPPV + ROTPV;
+  typedef Mat<DPV, DPV, double> TM;
+  static INLINE void CalcQ(const Vec<DIM> &t, TM &Q, double si, double sj);
+};
+#include "../_ref/frag/el_calcq.inc"
+
 // ---- grid transfer -------------------------------------------------------------------------------------------------
 INLINE Timer<> &timer_hack_prol_f2c() { static Timer t("ProlMap::TransferF2C"); return t; }
 INLINE Timer<> &timer_hack_prol_c2f() { static Timer t("ProlMap::TransferC2F"); return t; }
@@ -531,6 +542,23 @@ int ref_regularize6(double *m) {
     std::memcpy((void *)&blk, m, sizeof(double) * 36);
     RegTM<0, 6, 6>(blk);
     std::memcpy(m, (const void *)&blk, sizeof(double) * 36);
+  });
+}
+
+// EpsEpsEnergy<DIM>::CalcQ(t, Q, si, sj): dim 3 -> q is 6 x 6, dim 2 -> 3 x 3 (row-major)
+int ref_elast_calcq(int dim, const double *t, double si, double sj, double *q) {
+  return guarded([&] {
+    if (dim == 3) {
+      Vec<3> tv; for (int i = 0; i < 3; i++) tv(i) = t[i];
+      Mat<6, 6> Q;
+      EpsEpsEnergy<3, int, int>::CalcQ(tv, Q, si, sj);
+      std::memcpy(q, (const void *)&Q, sizeof(double) * 36);
+    } else if (dim == 2) {
+      Vec<2> tv; for (int i = 0; i < 2; i++) tv(i) = t[i];
+      Mat<3, 3> Q;
+      EpsEpsEnergy<2, int, int>::CalcQ(tv, Q, si, sj);
+      std::memcpy(q, (const void *)&Q, sizeof(double) * 9);
+    } else throw Exception("ref_elast_calcq: dim must be 2 or 3");
   });
 }
 

@@ -447,3 +447,33 @@ def test_operator_complexity_accounting_of_the_reference():
         exp = [fac(l) * 2 * 2 * nze[l] / nze[0] for l in range(ra.nlevels - 1)] + [0.0]
         assert np.allclose(occ[1:], exp, rtol=1e-15) and np.isclose(occ[0], sum(exp), rtol=1e-15)
     assert len(R.RefAMG(A, p["free"], prols, coarse_inv=False).get_oc()) == ra.nlevels       # no entry for a level without inverse
+
+
+@needs_ref
+def test_elasticity_prolongation_blocks_are_the_reference_rigid_body_transport():
+    """the piecewise prolongation of elast_3d: a fine vertex at x interpolates from its coarse vertex at c with the rigid-body transport
+    Q(x - c) of the reference (EpsEpsEnergy::CalcQ, elasticity_energy_impl.hpp:8-29; CalcQHh: t = fine - coarse) -- the top three rows
+    [I | -skew(t)] on the 3 -> 6 step (E_D = [I 0], elasticity_pc_impl.hpp:668-685), the full 6 x 6 block below.  Same sign convention,
+    bit for bit, so prolongations dumped by the reference can be injected as they are."""
+    import ngsamg_b200 as ng
+    Q = R.elast_calcq([1.0, 2.0, 3.0])
+    assert np.array_equal(Q[:3, 3:], -np.array([[0, -3.0, 2.0], [3.0, 0, -1.0], [-2.0, 1.0, 0]])) and np.array_equal(Q[3:, :3], np.zeros((3, 3)))
+    p, A = elasticity(5, 4, 4)
+    P, vmap, cxyz = ng.coarsen(A, p["free"], p["xyz"], bcoarse=6, max_per_row=4, smooth=False)
+    blocks = P.val.reshape(-1, 3, 6)
+    assert P.nnz > 0
+    for i in range(P.nrows):
+        for k in range(P.rowptr[i], P.rowptr[i + 1]):
+            assert np.array_equal(blocks[k], R.elast_calcq(p["xyz"][i] - cxyz[P.col[k]])[:3, :]), (i, k)
+    # 6 -> 6 step
+    Po = to_oracle(P)
+    A1 = O.restrict_matrix(O.transpose(Po), to_oracle(A), Po)
+    A1p = ng.SparseMatrix(A1.nrows, A1.ncols, 6, 6, A1.rowptr, A1.col, A1.val)
+    P1, _, cxyz1 = ng.coarsen(A1p, None, cxyz, bcoarse=6, max_per_row=4, smooth=False)
+    b1 = P1.val.reshape(-1, 6, 6)
+    assert P1.nnz > 0
+    for i in range(P1.nrows):
+        for k in range(P1.rowptr[i], P1.rowptr[i + 1]):
+            assert np.array_equal(b1[k], R.elast_calcq(cxyz[i] - cxyz1[P1.col[k]])), (i, k)
+    # 2D: rotation about the out-of-plane axis
+    assert np.array_equal(R.elast_calcq([2.0, 5.0]), np.array([[1.0, 0, -5.0], [0, 1.0, 2.0], [0, 0, 1.0]]))
