@@ -7,6 +7,7 @@ The library can only be BUILT where /root/reference exists; the built file trave
 import ctypes as C
 import os
 import subprocess
+import sys
 
 import numpy as np
 
@@ -22,9 +23,21 @@ i32p = np.ctypeslib.ndpointer(np.int32, flags="C_CONTIGUOUS")
 f64p = np.ctypeslib.ndpointer(np.float64, flags="C_CONTIGUOUS")
 
 
+_avail = None
+
+
 def available():
-    """True if the library exists or can be built here (the reference tree is present)"""
-    return os.path.exists(_SO) or os.path.isdir(os.path.join(REFERENCE, "src", "base"))
+    """True if the library can be used: it loads (building it first where the reference tree is present).  Never raises -- tests skip,
+    bench.py falls back to the oracle port, smoke() prints a note."""
+    global _avail
+    if _avail is None:
+        try:
+            lib()
+            _avail = True
+        except Exception as e:          # no reference tree and no prebuilt library, no compiler, or a library that does not load here
+            sys.stderr.write("[oracle/ref_pin] reference library unavailable: %s\n" % e)
+            _avail = False
+    return _avail
 
 
 def build():
