@@ -116,6 +116,31 @@ def make_hybrid():
     print("refpin_hybrid_2x2x2: %d ranks, %s dofs, %d arrays" % (Rn, [p["n"] for p in parts], len(out)))
 
 
+def make_dense():
+    """pseudo-inverse (CalcPseudoInverseTryNormal), coarse regularisation (RegTM<0,6,6>) and rigid-body transport (CalcQ) on seeded blocks"""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from test_ref_pin import pinv_cases
+    out = {"fragments": np.array(R.fragment_index())}
+    k = 0
+    for n in (2, 3, 6):
+        for name, M, direct in pinv_cases(n):
+            out["pinv_in_%d" % k], out["pinv_out_%d" % k], out["pinv_direct_%d" % k] = M, R.pinv_block(M), np.array(direct)
+            k += 1
+    out["pinv_count"] = k
+    rng = np.random.default_rng(3)
+    Q, _ = np.linalg.qr(rng.standard_normal((6, 6)))
+    X = rng.standard_normal((6, 6))
+    regs = [X @ X.T + 6 * np.eye(6), Q @ np.diag([0, 0, 0, 1.5, 2.0, 7.0]) @ Q.T, np.diag([3.0, 2.0, 5.0, 0, 0, 0]), np.zeros((6, 6))]
+    for i, M in enumerate(regs):
+        out["reg_in_%d" % i], out["reg_out_%d" % i] = M, R.regularize_block6(M)
+    out["reg_count"] = len(regs)
+    ts = rng.standard_normal((5, 3))
+    out["calcq_t"] = ts
+    out["calcq_q"] = np.stack([R.elast_calcq(t) for t in ts])
+    np.savez_compressed(os.path.join(HERE, "refpin_dense.npz"), **out)
+    print("refpin_dense: %d pinv cases, %d regularisation cases, %d transport blocks" % (k, len(regs), len(ts)))
+
+
 if __name__ == "__main__":
     p, A = poisson(7)
     make("refpin_poisson_n7", p, A, False, 1, False, max_coarse=20)
@@ -123,3 +148,4 @@ if __name__ == "__main__":
     p, A = elasticity(5, 3, 3)
     make("refpin_elast_5x3x3", p, A, True, 1, False, max_coarse=4, max_per_row=4)
     make_hybrid()
+    make_dense()

@@ -477,3 +477,24 @@ def test_elasticity_prolongation_blocks_are_the_reference_rigid_body_transport()
             assert np.array_equal(b1[k], R.elast_calcq(cxyz[i] - cxyz1[P1.col[k]])), (i, k)
     # 2D: rotation about the out-of-plane axis
     assert np.array_equal(R.elast_calcq([2.0, 5.0]), np.array([[1.0, 0, -5.0], [0, 1.0, 2.0], [0, 0, 1.0]]))
+
+
+def test_dense_block_routines_against_reference_made_fixture():
+    """pseudo-inverse, coarse regularisation and rigid-body transport against tests/golden/refpin_dense.npz (written by the reference library,
+    tests/golden/make_ref_golden.py): oracle and product host routines, no library needed"""
+    g = np.load(os.path.join(GOLD, "refpin_dense.npz"))
+    assert "utils_denseLA" in str(g["fragments"])
+    for k in range(int(g["pinv_count"])):
+        M, ref, direct = g["pinv_in_%d" % k], g["pinv_out_%d" % k], bool(g["pinv_direct_%d" % k])
+        for got in (oracle_pinv(M), product_pinv(M)):
+            if direct:
+                assert np.array_equal(ref, got), k
+            else:
+                assert np.abs(ref - got).max() <= 1e-12 * np.abs(ref).max(), k
+    for i in range(int(g["reg_count"])):
+        M, ref = g["reg_in_%d" % i], g["reg_out_%d" % i]
+        for got in (O.regularize_block(M, 3), product_regularize(M, 3)):
+            assert np.abs(ref - got).max() <= 1e-12 * max(np.abs(ref).max(), 1.0), i
+    for t, Q in zip(g["calcq_t"], g["calcq_q"]):
+        sk = np.array([[0, -t[2], t[1]], [t[2], 0, -t[0]], [-t[1], t[0], 0]])
+        assert np.array_equal(Q[:3, :3], np.eye(3)) and np.array_equal(Q[:3, 3:], -sk) and np.array_equal(Q[3:, 3:], np.eye(3))
