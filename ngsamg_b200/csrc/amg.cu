@@ -406,7 +406,10 @@ bool dense_invert(int n, std::vector<double> &a)
 // order).  We number coarse vertices colour-major from a greedy colouring of the Galerkin matrix graph, so that the
 // sequential Gauss-Seidel sweep in that numbering has a dependency depth equal to the number of colours instead of
 // O(n^(1/3)).  The sweep itself stays "rows in increasing number", exactly what GSS3 does.
-void greedy_coloring_perm(const HostBsr &A, std::vector<i32> &perm, int &ncolors)
+// `fixed` (optional): rows that keep their number (the shared dofs of a distributed level: their relative order must stay the
+// same on every sharer and the exchange lists ascending, the ParallelDofs contract of dcc_map.cpp:494-543); the other rows are dealt
+// colour-major into the remaining numbers.
+void greedy_coloring_perm(const HostBsr &A, std::vector<i32> &perm, int &ncolors, const std::vector<uint8_t> *fixed = nullptr)
 {
   const i64 n = A.nrows;
   std::vector<i32> color(n, -1);
@@ -437,7 +440,18 @@ void greedy_coloring_perm(const HostBsr &A, std::vector<i32> &perm, int &ncolors
   for (i64 i = 0; i < n; i++) order[i] = (i32)i;
   std::stable_sort(order.begin(), order.end(), [&](i32 a, i32 b) { return key[a] < key[b]; });
   perm.resize(n);
-  for (i64 q = 0; q < n; q++) perm[order[q]] = (i32)q;
+  if (!fixed) {
+    for (i64 q = 0; q < n; q++) perm[order[q]] = (i32)q;
+    return;
+  }
+  std::vector<i32> slots;
+  slots.reserve(n);
+  for (i64 i = 0; i < n; i++) if (!(*fixed)[i]) slots.push_back((i32)i);
+  size_t q = 0;
+  for (i32 o : order) {
+    if ((*fixed)[o]) perm[o] = o;
+    else perm[o] = slots[q++];
+  }
 }
 
 // B = Pi A Pi^T (rows and columns renumbered old -> perm[old]), columns re-sorted ascending
@@ -1294,10 +1308,16 @@ void Amg::finalize_parallel()
       auto h1 = std::chrono::steady_clock::now();
       std::vector<i32> cperm;
       int ncol = 0;
-      greedy_coloring_perm(C.hA, cperm, ncol);
+      // shared coarse dofs keep their (class-major, canonical) numbers: only the interior is recoloured
+      std::vector<uint8_t> keep(C.hA.nrows, 0);
+      for (i64 i = 0; i < C.hA.nrows; i++) keep[i] = C.pd.eqc[i] != 0;
+      greedy_coloring_perm(C.hA, cperm, ncol, &keep);
       permute_symmetric(C.hA, cperm);
       renumber_columns(L.hP, cperm);
       permute_pardofs(C.pd, cperm);
+      for (const auto &l : C.pd.ex)
+        for (size_t k = 1; k < l.size(); k++)
+          if (l[k] <= l[k - 1]) throw Error("coarse-level exchange dofs are not ascending after the renumbering");
       if (!C.xyz.empty()) {
         std::vector<double> nx(C.xyz.size());
         for (i64 i = 0; i < L.nc; i++) for (int k = 0; k < 3; k++) nx[(i64)cperm[i] * 3 + k] = C.xyz[i * 3 + k];
@@ -1346,6 +1366,26 @@ void Amg::finalize_parallel()
 // ------------------------------------------------------------------------------------------------
 // device primitives
 // ------------------------------------------------------------------------------------------------
+// The sync-free sweeps wait on rows/tiles computed by OTHER CTAs of the same launch: the whole grid has to be co-resident.  A
+// cooperative launch makes the driver guarantee that (it refuses grids that cannot be resident and never runs such a grid
+// half-resident next to another kernel) -- so two handles sharing a device, MPS neighbours or a host application's own kernels
+// cannot dead-lock a sweep.  One process per GPU remains the intended deployment (include/ngsamg_b200.h).
+template <class K, class... Args>
+static void launch_resident(K kern, int grid, int block, cudaStream_t st, Args... args)
+{
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3((unsigned)block);
+  cfg.dynamicSmemBytes = 0;
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeCooperative;
+  at[0].val.cooperative = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  NGB_CUDA(cudaLaunchKernelEx(&cfg, kern, args...));
+}
+
 template <int B>
 void Amg::tri(Level &L, bool backward, bool add_self, bool write_r, const double *rin, const double *self, double *out, double *rout)
 {
@@ -1364,7 +1404,7 @@ void Amg::tri(Level &L, bool backward, bool add_self, bool write_r, const double
         const int cap = std::max(1, occ) * num_sms;          // the whole grid must be resident (tiles wait for each other)
         const int grid = (int)std::max<i64>(1, std::min<i64>((L.ntiles + 7) / 8, cap));
         if (L.nonfree_pad) pre<<<nblk(L.nonfree_pad), TB, 0, st>>>(L.nonfree_pad, rin, self, out, rout);
-        kern<<<grid, 256, 0, st>>>(T.view(), L.diag, L.dinv, rin, self, out, rout, prm);
+        launch_resident(kern, grid, 256, st, T.view(), (const double *)L.diag, (const double *)L.dinv, rin, self, out, rout, prm);
       };
       if (L.tile_maxs <= 1) {
         if (add_self) launch_tile(k_gs_tile<1, true, false>, k_gs_tile_prefix<true, false>);
@@ -1405,7 +1445,7 @@ void Amg::tri(Level &L, bool backward, bool add_self, bool write_r, const double
       const i64 want = (L.npad + 8 * 16 - 1) / (8 * 16);   // >= 16 rows per warp
       const int grid = (int)std::max<i64>(1, std::min<i64>(want, tri_grid_cap[sidx]));
       TriParams prm{L.npad / 32, backward ? 1 : 0, tri_sleep_ns, tri_prepoll, tri_gate_all, 0, 0u, 0, L.nonfree_pad, d_err, nullptr, nullptr};
-      kern<<<grid, 256, 0, st>>>(T.view(), L.diag, L.dinv, rin, self, out, rout, prm);
+      launch_resident(kern, grid, 256, st, T.view(), (const double *)L.diag, (const double *)L.dinv, rin, self, out, rout, prm);
     };
     if (!add_self && !write_r) throw Error("tri: unsupported mode");
     if (add_self) launch_small(k_gs_tri_small<B, true, false>);
@@ -1428,7 +1468,7 @@ void Amg::tri(Level &L, bool backward, bool add_self, bool write_r, const double
     const int grid = (int)std::min<i64>((nslices + 7) / 8, tri_grid_cap[idx]);
     const i64 gap = tri_gate_gap_levels > 0 ? (i64)(tri_gate_gap_levels * (double)L.npad / std::max(1, L.depth)) : 0;
     TriParams prm{nslices, backward ? 1 : 0, tri_sleep_ns, tri_prepoll, tri_gate_all, gap, tri_repoll_ns, tri_regate, L.nonfree_pad, d_err, tri_split ? (backward ? L.d_bnd_bwd : L.d_bnd_fwd) : nullptr, tri_trace};
-    kern<<<grid, 256, 0, st>>>(T.view(), L.diag, L.dinv, rin, self, out, rout, prm);
+    launch_resident(kern, grid, 256, st, T.view(), (const double *)L.diag, (const double *)L.dinv, rin, self, out, rout, prm);
   };
   if (!add_self && !write_r) throw Error("tri: unsupported mode");
   if constexpr (B == 1) {

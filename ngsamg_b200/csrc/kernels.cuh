@@ -244,6 +244,14 @@ __device__ __forceinline__ double ld_poll(const double *p)
   return v;
 }
 __device__ __forceinline__ bool is_sentinel(double v) { return __double_as_longlong(v) == -1LL; }
+// watchdog of every spin loop: gives up after `limit` polls, or as soon as ANY waiter of the launch has given up (the flag is read
+// every 1024 polls), so one timeout bounds the whole kernel instead of every dependent row spinning to its own limit.
+__device__ __forceinline__ bool spin_fail(unsigned &spins, int *err, unsigned limit = (1u << 26))
+{
+  if ((++spins & 1023u) != 0) return false;
+  if (spins > limit || *(volatile int *)err != 0) { atomicExch(err, 1); return true; }
+  return false;
+}
 
 struct TriParams {
   i64 nslices;
@@ -354,7 +362,7 @@ __global__ void __launch_bounds__(256) k_gs_tri(SellView T, const double *__rest
         unsigned spins = 0;
         while (is_sentinel(ld_poll(out + (i64)f * B))) {
           if (prm.sleep_ns) __nanosleep(prm.sleep_ns);
-          if (++spins > (1u << 26)) { atomicExch(prm.err, 1); break; }
+          if (spin_fail(spins, prm.err)) break;
         }
       }
       __syncwarp();
@@ -404,13 +412,13 @@ __global__ void __launch_bounds__(256) k_gs_tri(SellView T, const double *__rest
             unsigned spins = 0;
             while (is_sentinel(ld_poll(out + u))) {
               if (prm.sleep_ns) __nanosleep(prm.sleep_ns);
-              if (++spins > (1u << 26)) { atomicExch(prm.err, 1); break; }
+              if (spin_fail(spins, prm.err)) break;
             }
           }
           __syncwarp();
 #pragma unroll
           for (int k = 0; k < PRE; k++) if (pc[k] >= 0 && is_sentinel(xk[k])) xk[k] = ld_poll(out + pc[k]);
-          if (round > (1u << 22)) { atomicExch(prm.err, 1); break; }
+          if (round > (1u << 22) || *(volatile int *)prm.err) { atomicExch(prm.err, 1); break; }
         }
       }
       if (split) {
@@ -420,7 +428,7 @@ __global__ void __launch_bounds__(256) k_gs_tri(SellView T, const double *__rest
           for (int k = 0; k < PRE; k++)
             if (pc[k] >= 0 && is_sentinel(xk[k])) { xk[k] = ld_poll(out + pc[k]); un |= is_sentinel(xk[k]); }
           if (!__any_sync(0xffffffffu, un)) break;
-          if (it > (1u << 26)) { atomicExch(prm.err, 1); break; }
+          if ((it & 1023u) == 1023u && (it > (1u << 26) || *(volatile int *)prm.err)) { atomicExch(prm.err, 1); break; }
         }
       }
 #pragma unroll
@@ -430,7 +438,7 @@ __global__ void __launch_bounds__(256) k_gs_tri(SellView T, const double *__rest
           while (is_sentinel(xk[k])) {
             if (prm.repoll_ns) __nanosleep(prm.repoll_ns);
             xk[k] = ld_poll(out + pc[k]);
-            if (++spins > (1u << 26)) { atomicExch(prm.err, 1); break; }
+            if (spin_fail(spins, prm.err)) break;
           }
           acc[0] = fma(-pv[k], xk[k], acc[0]);
         }
@@ -475,7 +483,7 @@ __global__ void __launch_bounds__(256) k_gs_tri(SellView T, const double *__rest
             while (is_sentinel(xv[j][q])) {
               if (prm.repoll_ns) __nanosleep(prm.repoll_ns);
               xv[j][q] = ld_poll(out + (i64)c[j] * B + q);
-              if (++spins > (1u << 26)) { atomicExch(prm.err, 1); break; }
+              if (spin_fail(spins, prm.err)) break;
             }
           }
 #pragma unroll
@@ -601,7 +609,7 @@ __global__ void __launch_bounds__(256) k_gs_tri_small(SellView T, const double *
         while (is_sentinel(v)) {
           if (prm.sleep_ns) __nanosleep(prm.sleep_ns);
           v = ld_poll(out + (i64)c * B + q);
-          if (++spins > (1u << 26)) { atomicExch(prm.err, 1); break; }
+          if (spin_fail(spins, prm.err)) break;
         }
         xv[q] = v;
       }

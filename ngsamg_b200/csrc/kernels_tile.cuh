@@ -83,7 +83,7 @@ __global__ void __launch_bounds__(256) k_gs_tile(SellView T, const double *__res
         unsigned spins = 0;
         while (ld_acquire_i32(f) == 0) {
           if (p.sleep_ns) __nanosleep(p.sleep_ns);
-          if (++spins > (1u << 24)) { atomicExch(p.err, 1); break; }
+          if (spin_fail(spins, p.err, 1u << 24)) break;
         }
       }
       __syncwarp();

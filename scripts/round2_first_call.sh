@@ -8,7 +8,7 @@ mkdir -p "$OUT"
 step() { local name=$1 secs=$2; shift 2; echo "=== $name" | tee -a "$OUT/steps.log"; timeout "$secs" "$@" > "$OUT/$name.log" 2>&1; echo "rc=$? ($name)" | tee -a "$OUT/steps.log"; }
 
 # 1. the regular GPU suite (incl. the tests added at the end of round 1 that have never run on hardware)
-step pytest_gpu 600 python -m pytest tests -m gpu -q -x
+step pytest_gpu 900 python -m pytest tests -m gpu -q
 # 2. the experimental tile sweep: parity first (opt-in test), hard 120 s limit
 NGSAMG_EXPERIMENTAL=1 step pytest_tile 120 python -m pytest tests/test_gpu_parity.py -k tile_sweep -q -x
 # 3. baseline bench, then the same with the tile sweep on level 0 (only if the parity test passed)
