@@ -13,6 +13,7 @@
 #include "device.hpp"
 #include "kernels.cuh"
 #include "kernels_tile.cuh"
+#include "kernels_ctile.cuh"
 #include "par.hpp"
 #include "tiles.hpp"
 
@@ -96,6 +97,11 @@ struct Level {
   uint8_t *d_row_lvl = nullptr;
   i64 *d_tile_pred_ptr = nullptr, *d_tile_succ_ptr = nullptr;
   int *d_tile_done = nullptr;
+  // CTA-per-tile sweep (kernels_ctile.cuh; tile capacity >= 128 rows): slab capacity, launch geometry
+  std::vector<i32> h_tile_slice;
+  int tile_cap_slots = 0;
+  int ctile_grid[2] = {0, 0};     // [add_self]
+  size_t ctile_smem = 0;
 };
 
 // libnccl.so.2 entry points, resolved at run time
@@ -209,6 +215,7 @@ struct Amg {
   ~Amg();
   void finalize();
   void build_level_layout(Level &L, const DevCsr &dA);
+  void prepare_ctile(Level &L);
   void build_transfer_layout(Level &F, Level &C);
   void build_coarse_inverse(Level &L);
   void alloc_vectors(Level &L);
@@ -347,6 +354,31 @@ void level_schedule(const HostBsr &A, const std::vector<uint8_t> &free_mask, boo
     L.d_bnd_bwd = upload_vec(bb, st);
   }
   (void)st;
+}
+
+// depth of the dependency DAG of the sequential sweep (what level_schedule would report), without building anything
+int sweep_depth(const HostBsr &A, const std::vector<uint8_t> &free_mask, const std::vector<i32> &sweep_rank)
+{
+  const i64 n = A.nrows;
+  std::vector<i32> lvl(n, 0);
+  const bool hf = !free_mask.empty(), natural = sweep_rank.empty();
+  std::vector<i32> inv;
+  if (!natural) { inv.resize(n); for (i64 i = 0; i < n; i++) inv[sweep_rank[i]] = (i32)i; }
+  i32 depth = 0;
+  for (i64 q = 0; q < n; q++) {
+    const i64 i = natural ? q : inv[q];
+    if (hf && !free_mask[i]) continue;
+    i32 m = 0;
+    for (i64 k = A.rowptr[i]; k < A.rowptr[i + 1]; k++) {
+      const i32 j = A.col[k];
+      if (natural && j >= i) break;
+      if (j == i || (!natural && sweep_rank[j] >= sweep_rank[i]) || (hf && !free_mask[j])) continue;
+      m = std::max(m, lvl[j]);
+    }
+    lvl[i] = m + 1;
+    depth = std::max(depth, m + 1);
+  }
+  return depth;
 }
 
 void build_sell(i64 nrows_pad, int bh, int bw, const i32 *d_len, Sell &S, cudaStream_t st, i64 *launches)
@@ -668,6 +700,52 @@ void Amg::build_level_layout(Level &L, const DevCsr &dA)
   dev_free(d_err);
 }
 
+// the four instantiations of the CTA-per-tile sweep: [maxs == 16][add_self]
+constexpr int CTILE_NT = 256;
+using CTileKernel = void (*)(SellView, const double *, const double *, const double *, const double *, double *, double *, CTileParams);
+static CTileKernel ctile_kernel(int maxs, bool add_self)
+{
+  if (maxs <= 8) return add_self ? (CTileKernel)k_gs_ctile<CTILE_NT, 8, true, false> : (CTileKernel)k_gs_ctile<CTILE_NT, 8, false, true>;
+  return add_self ? (CTileKernel)k_gs_ctile<CTILE_NT, 16, true, false> : (CTileKernel)k_gs_ctile<CTILE_NT, 16, false, true>;
+}
+
+// CTA-per-tile sweep: slab capacity (largest tile of L and U, in SELL slots), shared-memory opt-in, resident grid
+void Amg::prepare_ctile(Level &L)
+{
+  i64 cap = 1;
+  for (const Sell *S : {&L.L, &L.U}) {
+    std::vector<i64> sp(S->nslices + 1);
+    NGB_CUDA(cudaMemcpyAsync(sp.data(), S->slice_ptr, sizeof(i64) * (S->nslices + 1), cudaMemcpyDeviceToHost, st));
+    NGB_CUDA(cudaStreamSynchronize(st));
+    for (i64 t = 0; t < L.ntiles; t++) cap = std::max(cap, sp[L.h_tile_slice[t + 1]] - sp[L.h_tile_slice[t]]);
+  }
+  L.tile_cap_slots = (int)cap;
+  L.ctile_smem = ctile_smem_bytes(L.tile_maxs, L.tile_cap_slots);
+  int dev_max = 0;
+  NGB_CUDA(cudaDeviceGetAttribute(&dev_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
+  if (L.ctile_smem > (size_t)dev_max)
+    throw Error("tile sweep: a tile needs " + std::to_string(L.ctile_smem) + " bytes of shared memory (device limit " + std::to_string(dev_max) + "); use smaller tiles (ngs_amg_b200_tile_rows)");
+  for (int as = 0; as < 2; as++) {
+    CTileKernel k = ctile_kernel(L.tile_maxs, as == 1);
+    {
+      // the opt-in is per kernel, not per level: keep the largest request of any hierarchy of this process
+      static std::mutex mu;
+      static size_t granted[2][2] = {{0, 0}, {0, 0}};
+      std::lock_guard<std::mutex> guard(mu);
+      size_t &g = granted[L.tile_maxs <= 8 ? 0 : 1][as];
+      g = std::max(g, L.ctile_smem);
+      NGB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g));
+    }
+    int occ = 0;
+    NGB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k, CTILE_NT, L.ctile_smem));
+    occ = std::max(1, occ);
+    if (tri_ctas_per_sm > 0) occ = std::min(occ, tri_ctas_per_sm);
+    L.ctile_grid[as] = (int)std::max<i64>(1, std::min<i64>(L.ntiles, (i64)occ * num_sms));
+    if (flags.str("log_level", "none") != "none") std::fprintf(stderr, "[ngsamg_b200] tile sweep (%s): %lld tiles, slab %d slots, %zu B smem, %d CTAs/SM, grid %d\n", as ? "backward/rhs" : "forward/res",
+                              (long long)L.ntiles, L.tile_cap_slots, L.ctile_smem, occ, L.ctile_grid[as]);
+  }
+}
+
 void Amg::build_transfer_layout(Level &F, Level &C)
 {
   // P: rows = fine (level-scheduled), cols = coarse (level-scheduled); PT the other way round
@@ -912,20 +990,26 @@ void Amg::finalize()
         greedy_coloring_perm(L.hA, L.sweep_rank, ncol);
       }
       // EXPERIMENTAL (off by default): tile-major numbering + two-level schedule for big scalar levels
-      if (!coarsest && L.b == 1 && flags.flag("b200_tile_sweep", false) && L.n >= (i64)flags.num("b200_tile_min_rows", 200000)) {
+      // (only where the row DAG is deep: a colour-major coarse level has a shallower DAG than any tiling of it)
+      if (!coarsest && L.b == 1 && flags.flag("b200_tile_sweep", false) && L.n >= (i64)flags.num("b200_tile_min_rows", 200000) &&
+          sweep_depth(L.hA, L.mask(), L.sweep_rank) >= (int)flags.num("b200_tile_min_depth", 150)) {
         TileSchedule ts;
         const int cap = (int)flags.num("b200_tile_rows", 64);     // 64-row tiles (6 pairing rounds): about half the tile-DAG depth of 32-row tiles
-        if (cap != 32 && cap != 64) throw Error("ngs_amg_b200_tile_rows must be 32 or 64 (the warp-per-tile kernel holds at most two slices per lane)");
-        build_tile_schedule(L.hA, L.mask(), L.sweep_rank, (int)flags.num("b200_tile_rounds", cap <= 32 ? 5 : 6), cap, ts);
+        if (cap != 32 && cap != 64 && cap != 256 && cap != 512)
+          throw Error("ngs_amg_b200_tile_rows must be 32 or 64 (one warp per tile) or 256 or 512 (one CTA per tile)");
+        int rounds = 5;
+        while ((1 << rounds) < cap) rounds++;
+        build_tile_schedule(L.hA, L.mask(), L.sweep_rank, (int)flags.num("b200_tile_rounds", rounds), cap, ts);
         if (ts.ok) {
           L.perm = ts.perm; L.npad = ts.npad; L.nonfree_pad = ts.nonfree_pad; L.depth = ts.tile_depth;
           L.level_start.clear();
-          L.ntiles = ts.ntiles; L.tile_maxs = cap / 32;
+          L.ntiles = ts.ntiles; L.tile_maxs = cap / 32;   // 1, 2: warp per tile; 8, 16: CTA per tile
           L.d_tile_slice = upload_vec(ts.tile_slice, st); L.d_tile_nlev = upload_vec(ts.tile_nlev, st);
           L.d_row_lvl = upload_vec(ts.row_lvl, st);
           L.d_tile_pred_ptr = upload_vec(ts.pred_ptr, st); L.d_tile_pred = upload_vec(ts.pred, st);
           L.d_tile_succ_ptr = upload_vec(ts.succ_ptr, st); L.d_tile_succ = upload_vec(ts.succ, st);
           L.d_tile_done = dev_alloc<int>((size_t)ts.ntiles);
+          L.h_tile_slice = ts.tile_slice;
           L.tiled = true;
           if (verbose) std::fprintf(stderr, "[ngsamg_b200] level %d: tile schedule: %lld tiles, tile DAG depth %d, <= %d local levels\n", l, (long long)ts.ntiles, ts.tile_depth, ts.max_local_levels);
         }
@@ -935,7 +1019,7 @@ void Amg::finalize()
       host_s += tick(h0);
       if (verbose) std::fprintf(stderr, "[ngsamg_b200] level %d: level schedule %.2f s (depth %d)\n", l, tick(h0), L.depth);
     }
-    if (!coarsest) build_level_layout(L, dA);
+    if (!coarsest) { build_level_layout(L, dA); if (L.tiled && L.tile_maxs > 2) prepare_ctile(L); }
     else {
       L.d_perm = upload_vec(L.perm, st);
       if (clev == "inv") build_coarse_inverse(L);
@@ -1371,12 +1455,12 @@ void Amg::finalize_parallel()
 // half-resident next to another kernel) -- so two handles sharing a device, MPS neighbours or a host application's own kernels
 // cannot dead-lock a sweep.  One process per GPU remains the intended deployment (include/ngsamg_b200.h).
 template <class K, class... Args>
-static void launch_resident(K kern, int grid, int block, cudaStream_t st, Args... args)
+static void launch_resident_smem(K kern, int grid, int block, size_t smem, cudaStream_t st, Args... args)
 {
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3((unsigned)grid);
   cfg.blockDim = dim3((unsigned)block);
-  cfg.dynamicSmemBytes = 0;
+  cfg.dynamicSmemBytes = smem;
   cfg.stream = st;
   cudaLaunchAttribute at[1];
   at[0].id = cudaLaunchAttributeCooperative;
@@ -1385,12 +1469,34 @@ static void launch_resident(K kern, int grid, int block, cudaStream_t st, Args..
   cfg.numAttrs = 1;
   NGB_CUDA(cudaLaunchKernelEx(&cfg, kern, args...));
 }
+template <class K, class... Args>
+static void launch_resident(K kern, int grid, int block, cudaStream_t st, Args... args)
+{
+  launch_resident_smem(kern, grid, block, 0, st, args...);
+}
 
 template <int B>
 void Amg::tri(Level &L, bool backward, bool add_self, bool write_r, const double *rin, const double *self, double *out, double *rout)
 {
   const Sell &T = backward ? L.U : L.L;
   if constexpr (B == 1) {
+    if (L.tiled && L.tile_maxs > 2) {
+      // two-level sweep, one CTA per tile (kernels_ctile.cuh): sentinel-filled output, hint flags, slab fetched by bulk copies
+      if (!add_self && !write_r) throw Error("tri: unsupported mode");
+      NGB_CUDA(cudaMemsetAsync(out, 0xFF, sizeof(double) * L.npad, st));
+      NGB_CUDA(cudaMemsetAsync(L.d_tile_done, 0, sizeof(int) * (size_t)L.ntiles, st));
+      CTileParams prm{(i32)L.ntiles, backward ? 1 : 0, L.d_tile_slice, L.d_tile_nlev, L.d_row_lvl,
+                      backward ? L.d_tile_succ_ptr : L.d_tile_pred_ptr, backward ? L.d_tile_succ : L.d_tile_pred, L.d_tile_done,
+                      tri_sleep_ns, tri_repoll_ns, L.tile_cap_slots, d_err};
+      if (L.nonfree_pad) {
+        if (add_self) k_gs_tile_prefix<true, false><<<nblk(L.nonfree_pad), TB, 0, st>>>(L.nonfree_pad, rin, self, out, rout);
+        else k_gs_tile_prefix<false, true><<<nblk(L.nonfree_pad), TB, 0, st>>>(L.nonfree_pad, rin, self, out, rout);
+      }
+      launch_resident_smem(ctile_kernel(L.tile_maxs, add_self), L.ctile_grid[add_self ? 1 : 0], CTILE_NT, L.ctile_smem, st, T.view(),
+                           (const double *)L.diag, (const double *)L.dinv, rin, self, out, rout, prm);
+      launches += 2;
+      return;
+    }
     if (L.tiled) {
       // EXPERIMENTAL two-level sweep: one warp per tile, flags between tiles (kernels_tile.cuh)
       if (!add_self && !write_r) throw Error("tri: unsupported mode");

@@ -468,17 +468,16 @@ def test_regularised_coarse_solve_with_a_lone_vertex():
         ng.elast_3d(A, p["free"], vertex_xyz=p["xyz"], prolongations=[P0], ngs_amg_regularize_cmats=False)
 
 
-@pytest.mark.skipif(__import__("os").environ.get("NGSAMG_EXPERIMENTAL") != "1",
-                    reason="experimental two-level (tile) sweep: not validated on hardware yet; run with NGSAMG_EXPERIMENTAL=1")
-@pytest.mark.parametrize("rows", [32, 64])
-def test_tile_sweep_experimental(rows):
-    """ngs_amg_b200_tile_sweep: the triangular half-sweeps on the tile schedule (kernels_tile.cuh) must reproduce the sequential sweep
-    like the row-level kernels do -- same bars as everywhere else"""
-    p, A = poisson(21)
+@pytest.mark.parametrize("rows,n", [(32, 21), (64, 21), (256, 29), (512, 33)])
+def test_tile_sweep(rows, n):
+    """ngs_amg_b200_tile_sweep: the triangular half-sweeps on the two-level tile schedule -- one warp per tile (kernels_tile.cuh, 32/64
+    rows) or one CTA per tile with the matrix slab fetched by bulk copies (kernels_ctile.cuh, 256/512 rows) -- must reproduce the
+    reference's sequential sweep like the row-level kernels do: same bars as everywhere else, forward and backward (V-cycle + PCG)"""
+    p, A = poisson(n)
     base = dict(ngs_amg_max_coarse_size=20)
     pc0 = ng.h1_scal(A, p["free"], **base)
     pc = ng.h1_scal(A, p["free"], prolongations=pc0.GetMap(), ngs_amg_b200_tile_sweep=True, ngs_amg_b200_tile_min_rows=0,
-                    ngs_amg_b200_tile_rows=rows, **base)
+                    ngs_amg_b200_tile_min_depth=0, ngs_amg_b200_tile_rows=rows, **base)
     amg = O.OracleAMG(to_oracle(A), p["free"], [to_oracle(P) for P in pc0.GetMap()])
     for seed in (1, 2, 3):
         b = rand(seed, p["n"])
