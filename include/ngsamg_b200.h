@@ -285,6 +285,7 @@ int ngsamg_b200_block_regularize(int n, double *m, int dim);
  * a topological order of the row DAG of GSS3's sweep (gssmoother.cpp:195-315), i.e. it reproduces the reference's result while the number
  * of cross-SM hops on the critical path falls from the row-DAG depth to the tile-DAG depth.  The device kernel consuming the schedule is
  * experimental (flag ngs_amg_b200_tile_sweep); these entry points let tests validate the schedule without a device.
+ * rounds < 0: the setup default (box-shaped clusters when the matrix is numbered like a structured grid, else pairwise clustering).
  * info[9] = { ok, ntiles, npad, nonfree_pad, tile_depth, max_local_levels, merged_tiles, violations (self-check), npred }.
  * fetch copies perm[n], tile_slice[ntiles+1], tile_nlev[ntiles], row_lvl[npad], pred_ptr[ntiles+1], pred[npred] and frees the handle. */
 typedef struct ngsamg_b200_tiles ngsamg_b200_tiles;

@@ -177,10 +177,12 @@ class Preconditioner:
 
     # -- BaseMatrix quartet ----------------------------------------------------------------------
     def Mult(self, b, x):
-        _lib.check(self._lib.ngsamg_b200_apply(self._h, _lib.ptr(b), _lib.ptr(x)))
+        n = self.height
+        _lib.check(self._lib.ngsamg_b200_apply(self._h, _lib.vec(b, n, "Mult: b"), _lib.vec(x, n, "Mult: x")))
 
     def MultAdd(self, s, b, x):
-        _lib.check(self._lib.ngsamg_b200_apply_add(self._h, float(s), _lib.ptr(b), _lib.ptr(x)))
+        n = self.height
+        _lib.check(self._lib.ngsamg_b200_apply_add(self._h, float(s), _lib.vec(b, n, "MultAdd: b"), _lib.vec(x, n, "MultAdd: x")))
 
     MultTrans = Mult          # amg_matrix.cpp:381-382
     MultTransAdd = MultAdd    # amg_matrix.cpp:392-393
@@ -320,23 +322,33 @@ class Preconditioner:
         return ms.value, by.value
 
     # -- level operations ------------------------------------------------------------------------
+    def _level_len(self, level):
+        """scalar length of a vector of that level"""
+        return self.GetNDof(level) * self.GetBlockSize(level)
+
     def _smooth(self, level, x, b, res, ru, ur, xz, back):
-        _lib.check(self._lib.ngsamg_b200_smooth(self._h, int(level), _lib.ptr(x), _lib.ptr(b), _lib.ptr(res), int(ru), int(ur),
+        n = self._level_len(level)
+        _lib.check(self._lib.ngsamg_b200_smooth(self._h, int(level), _lib.vec(x, n, "smooth: x"), _lib.vec(b, n, "smooth: b"),
+                                                _lib.vec(res, n, "smooth: res"), int(ru), int(ur),
                                                 int(xz), int(back)))
 
     def LevelMultAdd(self, level, s, x, y):
         """y += s * A_level * x"""
-        _lib.check(self._lib.ngsamg_b200_spmv_add(self._h, int(level), float(s), _lib.ptr(x), _lib.ptr(y)))
+        n = self._level_len(level)
+        _lib.check(self._lib.ngsamg_b200_spmv_add(self._h, int(level), float(s), _lib.vec(x, n, "LevelMultAdd: x"), _lib.vec(y, n, "LevelMultAdd: y")))
 
     def TransferF2C(self, level, xf, xc):
-        _lib.check(self._lib.ngsamg_b200_restrict(self._h, int(level), _lib.ptr(xf), _lib.ptr(xc)))
+        _lib.check(self._lib.ngsamg_b200_restrict(self._h, int(level), _lib.vec(xf, self._level_len(level), "TransferF2C: fine"),
+                                                  _lib.vec(xc, self._level_len(level + 1), "TransferF2C: coarse")))
 
     def AddC2F(self, level, fac, xf, xc):
-        _lib.check(self._lib.ngsamg_b200_prolong_add(self._h, int(level), float(fac), _lib.ptr(xc), _lib.ptr(xf)))
+        _lib.check(self._lib.ngsamg_b200_prolong_add(self._h, int(level), float(fac), _lib.vec(xc, self._level_len(level + 1), "AddC2F: coarse"),
+                                                     _lib.vec(xf, self._level_len(level), "AddC2F: fine")))
 
     def CoarseSolve(self, rhs, x):
         """crs_inv->Mult on the coarsest level (amg_matrix.cpp:228-233)"""
-        _lib.check(self._lib.ngsamg_b200_coarse_solve(self._h, _lib.ptr(rhs), _lib.ptr(x)))
+        n = self._level_len(self.GetNLevels() - 1)
+        _lib.check(self._lib.ngsamg_b200_coarse_solve(self._h, _lib.vec(rhs, n, "CoarseSolve: rhs"), _lib.vec(x, n, "CoarseSolve: x")))
         return x
 
     def CINV(self, x, b):
@@ -380,7 +392,8 @@ class Preconditioner:
     def _pcg(self, rhs, x, tol, maxsteps):
         it = C.c_int(0)
         errs = np.zeros(maxsteps + 2)
-        _lib.check(self._lib.ngsamg_b200_pcg(self._h, _lib.ptr(rhs), _lib.ptr(x), float(tol), int(maxsteps), C.byref(it),
+        n = self.height
+        _lib.check(self._lib.ngsamg_b200_pcg(self._h, _lib.vec(rhs, n, "pcg: rhs"), _lib.vec(x, n, "pcg: x"), float(tol), int(maxsteps), C.byref(it),
                                              _lib.ptr(errs)))
         return it.value, errs[: it.value + 1].copy()
 

@@ -139,6 +139,30 @@ def check(rc):
         raise NgsAMGError(lib().ngsamg_b200_last_error().decode())
 
 
+def vec(a, n, what="vector"):
+    """a float64 vector of at least n entries -> void*.  The C ABI reads/writes n doubles through the pointer, so anything else
+    (float32, a strided slice, a short array) would silently give garbage or overrun memory: raise instead.  Nothing is copied:
+    output arrays must be written in place."""
+    if isinstance(a, np.ndarray):
+        if a.dtype != np.float64:
+            raise TypeError("%s: expected float64, got %s" % (what, a.dtype))
+        if not a.flags["C_CONTIGUOUS"]:
+            raise ValueError("%s: array must be C-contiguous" % what)
+        if a.size < n:
+            raise ValueError("%s: %d entries, at least %d expected" % (what, a.size, n))
+    elif hasattr(a, "data_ptr"):
+        import torch
+        if a.dtype != torch.float64:
+            raise TypeError("%s: expected a float64 tensor, got %s" % (what, a.dtype))
+        if not a.is_contiguous():
+            raise ValueError("%s: tensor must be contiguous" % what)
+        if a.numel() < n:
+            raise ValueError("%s: %d entries, at least %d expected" % (what, a.numel(), n))
+    elif a is not None and not isinstance(a, int):
+        raise TypeError("%s: unsupported buffer type %r" % (what, type(a)))
+    return ptr(a)
+
+
 def ptr(a):
     """numpy array / torch CUDA tensor / raw int -> void*"""
     if a is None:

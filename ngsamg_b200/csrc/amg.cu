@@ -2,6 +2,7 @@
 // V-cycle (AMGMatrix::SmoothV, src/base/solve/amg_matrix.cpp:160-307) and PCG on one B200.
 #include <cub/cub.cuh>
 
+#include <atomic>
 #include <chrono>
 #include <memory>
 #include <mutex>
@@ -182,6 +183,8 @@ struct Amg {
   i64 tri_level_launch_rows = 131072;
   double tri_gate_gap_levels = 0.0;
   unsigned tri_repoll_ns = 0;
+  int tri_pollmode = 0;
+  i64 spmv_small_rows = 200000;   // levels with fewer rows use the warp-per-row SpMV
   int tri_regate = 1;
   int tri_split = 0;
   unsigned long long *tri_trace = nullptr;  // debug tracing of the sync-free sweep (NGSAMG_B200_TRACE_FILE)
@@ -999,7 +1002,12 @@ void Amg::finalize()
           throw Error("ngs_amg_b200_tile_rows must be 32 or 64 (one warp per tile) or 256 or 512 (one CTA per tile)");
         int rounds = 5;
         while ((1 << rounds) < cap) rounds++;
-        build_tile_schedule(L.hA, L.mask(), L.sweep_rank, (int)flags.num("b200_tile_rounds", rounds), cap, ts);
+        // matrices numbered like a structured grid get near-cubic boxes as cluster hints (ideal tile DAG); everything else the pairwise clustering
+        std::vector<i32> hint;
+        i64 gd[3] = {0, 0, 0};
+        const bool grid = flags.flag("b200_tile_grid_hint", true) && grid_box_hint(L.hA, L.mask(), cap, hint, gd);
+        if (verbose && grid) std::fprintf(stderr, "[ngsamg_b200] level %d: numbered like a %lld x %lld x %lld grid: box-shaped tiles\n", l, (long long)gd[0], (long long)gd[1], (long long)gd[2]);
+        build_tile_schedule(L.hA, L.mask(), L.sweep_rank, (int)flags.num("b200_tile_rounds", rounds), cap, ts, grid ? &hint : nullptr);
         if (ts.ok) {
           L.perm = ts.perm; L.npad = ts.npad; L.nonfree_pad = ts.nonfree_pad; L.depth = ts.tile_depth;
           L.level_start.clear();
@@ -1487,7 +1495,7 @@ void Amg::tri(Level &L, bool backward, bool add_self, bool write_r, const double
       NGB_CUDA(cudaMemsetAsync(L.d_tile_done, 0, sizeof(int) * (size_t)L.ntiles, st));
       CTileParams prm{(i32)L.ntiles, backward ? 1 : 0, L.d_tile_slice, L.d_tile_nlev, L.d_row_lvl,
                       backward ? L.d_tile_succ_ptr : L.d_tile_pred_ptr, backward ? L.d_tile_succ : L.d_tile_pred, L.d_tile_done,
-                      tri_sleep_ns, tri_repoll_ns, L.tile_cap_slots, d_err};
+                      tri_sleep_ns, tri_repoll_ns, tri_pollmode, L.tile_cap_slots, d_err, tri_trace};
       if (L.nonfree_pad) {
         if (add_self) k_gs_tile_prefix<true, false><<<nblk(L.nonfree_pad), TB, 0, st>>>(L.nonfree_pad, rin, self, out, rout);
         else k_gs_tile_prefix<false, true><<<nblk(L.nonfree_pad), TB, 0, st>>>(L.nonfree_pad, rin, self, out, rout);
@@ -1550,7 +1558,7 @@ void Amg::tri(Level &L, bool backward, bool add_self, bool write_r, const double
       }
       const i64 want = (L.npad + 8 * 16 - 1) / (8 * 16);   // >= 16 rows per warp
       const int grid = (int)std::max<i64>(1, std::min<i64>(want, tri_grid_cap[sidx]));
-      TriParams prm{L.npad / 32, backward ? 1 : 0, tri_sleep_ns, tri_prepoll, tri_gate_all, 0, 0u, 0, L.nonfree_pad, d_err, nullptr, nullptr};
+      TriParams prm{L.npad / 32, backward ? 1 : 0, tri_sleep_ns, tri_prepoll, tri_gate_all, 0, 0u, 0, L.nonfree_pad, d_err, tri_pollmode, nullptr, nullptr};
       launch_resident(kern, grid, 256, st, T.view(), (const double *)L.diag, (const double *)L.dinv, rin, self, out, rout, prm);
     };
     if (!add_self && !write_r) throw Error("tri: unsupported mode");
@@ -1573,7 +1581,7 @@ void Amg::tri(Level &L, bool backward, bool add_self, bool write_r, const double
     const i64 nslices = L.npad / 32;
     const int grid = (int)std::min<i64>((nslices + 7) / 8, tri_grid_cap[idx]);
     const i64 gap = tri_gate_gap_levels > 0 ? (i64)(tri_gate_gap_levels * (double)L.npad / std::max(1, L.depth)) : 0;
-    TriParams prm{nslices, backward ? 1 : 0, tri_sleep_ns, tri_prepoll, tri_gate_all, gap, tri_repoll_ns, tri_regate, L.nonfree_pad, d_err, tri_split ? (backward ? L.d_bnd_bwd : L.d_bnd_fwd) : nullptr, tri_trace};
+    TriParams prm{nslices, backward ? 1 : 0, tri_sleep_ns, tri_prepoll, tri_gate_all, gap, tri_repoll_ns, tri_regate, L.nonfree_pad, d_err, tri_pollmode, tri_split ? (backward ? L.d_bnd_bwd : L.d_bnd_fwd) : nullptr, tri_trace};
     launch_resident(kern, grid, 256, st, T.view(), (const double *)L.diag, (const double *)L.dinv, rin, self, out, rout, prm);
   };
   if (!add_self && !write_r) throw Error("tri: unsupported mode");
@@ -1598,14 +1606,13 @@ void Amg::tri_dispatch(Level &L, bool backward, bool add_self, bool write_r, con
   }
 }
 
-static i64 g_spmv_small_rows = 200000;   // levels with fewer rows use the warp-per-row SpMV
 template <int BH, int BW, bool S2, bool D>
-static void launch_spmv(cudaStream_t st, i64 npad, const Sell &a, const Sell *b, const double *diag, const double *v, const double *y_in,
+static void launch_spmv(cudaStream_t st, i64 small_rows, i64 npad, const Sell &a, const Sell *b, const double *diag, const double *v, const double *y_in,
                         double *y_out, double alpha, double beta, double *xadd, const Sell *nfp = nullptr, const i32 *rowmap = nullptr)
 {
   const SellView none{nullptr, nullptr, nullptr};
   const SellView s3 = (nfp && nfp->slice_ptr) ? nfp->view() : none;
-  if (npad <= g_spmv_small_rows) {
+  if (npad <= small_rows) {
     const unsigned grid = (unsigned)std::max<i64>(1, std::min<i64>((npad + 7) / 8, 148 * 8));
     k_sell_spmv_small<BH, BW, S2, D><<<grid, TB, 0, st>>>(npad, a.view(), b ? b->view() : a.view(), diag, v, y_in, y_out, alpha, beta,
                                                          xadd, s3, rowmap);
@@ -1620,9 +1627,9 @@ void Amg::spmv_part(Level &L, int which, const double *v, const double *y_in, do
   const Sell &A1 = (which == 1 || which == 3) ? L.U : L.L;
   const bool s2 = (which == 4), d = (which >= 2);
 #define NGB_SPMV(B)                                                                                                     \
-  if (s2) launch_spmv<B, B, true, true>(st, L.npad, L.L, &L.U, L.diag, v, y_in, y_out, alpha, beta, xadd, &L.N);       \
-  else if (d) launch_spmv<B, B, false, true>(st, L.npad, A1, nullptr, L.diag, v, y_in, y_out, alpha, beta, xadd, &L.N); \
-  else launch_spmv<B, B, false, false>(st, L.npad, A1, nullptr, L.diag, v, y_in, y_out, alpha, beta, xadd);
+  if (s2) launch_spmv<B, B, true, true>(st, spmv_small_rows, L.npad, L.L, &L.U, L.diag, v, y_in, y_out, alpha, beta, xadd, &L.N);       \
+  else if (d) launch_spmv<B, B, false, true>(st, spmv_small_rows, L.npad, A1, nullptr, L.diag, v, y_in, y_out, alpha, beta, xadd, &L.N); \
+  else launch_spmv<B, B, false, false>(st, spmv_small_rows, L.npad, A1, nullptr, L.diag, v, y_in, y_out, alpha, beta, xadd);
   switch (L.b) {
     case 1: NGB_SPMV(1) break;
     case 2: NGB_SPMV(2) break;
@@ -1637,7 +1644,7 @@ void Amg::spmv_part(Level &L, int which, const double *v, const double *y_in, do
 void Amg::transfer(const Sell &S, const double *v, const double *y_in, double *y_out, double alpha, double beta, const i32 *rowmap)
 {
   const int key = S.bh * 10 + S.bw;
-#define NGB_TR(H, W) launch_spmv<H, W, false, false>(st, S.nrows_pad, S, nullptr, nullptr, v, y_in, y_out, alpha, beta, nullptr, nullptr, rowmap)
+#define NGB_TR(H, W) launch_spmv<H, W, false, false>(st, spmv_small_rows, S.nrows_pad, S, nullptr, nullptr, v, y_in, y_out, alpha, beta, nullptr, nullptr, rowmap)
   switch (key) {
     case 11: NGB_TR(1, 1); break;
     case 22: NGB_TR(2, 2); break;
@@ -2083,6 +2090,26 @@ static void check_csr(const ngsamg_csr *A, const char *what)
   if (!A || !A->rowptr || (A->rowptr[A->nrows] > 0 && (!A->col || !A->val))) throw Error(std::string(what) + ": null matrix arrays");
   if (A->bh < 1 || A->bw < 1 || A->bh > 6 || A->bw > 6) throw Error(std::string(what) + ": unsupported block shape");
   if (A->nrows >= (i64)2147483647 - 64 || A->ncols >= (i64)2147483647 - 64) throw Error(std::string(what) + ": more than 2^31 block rows per GPU");
+  if (A->nrows < 0 || A->ncols < 0 || A->rowptr[0] != 0) throw Error(std::string(what) + ": malformed matrix (negative size or rowptr[0] != 0)");
+  // NGSolve SparseMatrix invariants every consumer relies on (level schedule, L/D/U split, binary searches of the SpGEMM, device
+  // gathers): row pointers monotone, column numbers in range and strictly ascending inside a row.  One O(nnz) pass.
+  std::atomic<int> bad{0};
+  parallel_for(A->nrows, [&](i64 lo, i64 hi) {
+    for (i64 i = lo; i < hi && !bad.load(std::memory_order_relaxed); i++) {
+      const i64 b0 = A->rowptr[i], b1 = A->rowptr[i + 1];
+      if (b1 < b0) { bad = 1; return; }
+      i64 prev = -1;
+      for (i64 k = b0; k < b1; k++) {
+        const i64 c = A->col[k];
+        if (c < 0 || c >= A->ncols) { bad = 2; return; }
+        if (c <= prev) { bad = 3; return; }
+        prev = c;
+      }
+    }
+  }, 1 << 16);
+  if (bad == 1) throw Error(std::string(what) + ": row pointers are not monotone");
+  if (bad == 2) throw Error(std::string(what) + ": column index out of range");
+  if (bad == 3) throw Error(std::string(what) + ": column indices of a row must be strictly ascending (NGSolve SparseMatrix layout)");
 }
 
 static void copy_csr(const ngsamg_csr *A, HostBsr &h)
@@ -2148,11 +2175,8 @@ static void create_impl(const char *type, const ngsamg_csr *A, const uint8_t *fr
   a.tri_repoll_ns = (unsigned)a.flags.num("b200_tri_repoll_ns", 0);
   a.tri_regate = (int)a.flags.num("b200_tri_regate", 1);
   a.tri_split = (int)a.flags.num("b200_tri_split", 0);
-  g_spmv_small_rows = (i64)a.flags.num("b200_spmv_small_rows", 200000);
-  {
-    int pm = (int)a.flags.num("b200_tri_pollmode", 0);
-    NGB_CUDA(cudaMemcpyToSymbol(g_pollmode, &pm, sizeof(int)));
-  }
+  a.spmv_small_rows = (i64)a.flags.num("b200_spmv_small_rows", 200000);
+  a.tri_pollmode = (int)a.flags.num("b200_tri_pollmode", 0);
   auto L = std::make_unique<Level>();
   copy_csr(A, L->hA);
   if (free_mask) {
@@ -2986,7 +3010,32 @@ int ngsamg_b200_profile_kernel(ngsamg_b200_t *h, int level, int which, int reps,
   if (ms_avg) *ms_avg = ms / std::max(reps, 1);
   if (bytes) *bytes = B;
   if (const char *tf = std::getenv("NGSAMG_B200_TRACE_FILE")) {
-    if (which == 0 || which == 3) {
+    if ((which == 0 || which == 3) && L.tiled && L.tile_maxs > 2) {
+      // CTA-per-tile sweep: 8 words per tile + the tile DAG (predecessor lists) for the offline analysis (scripts/analyze_ctile_trace.py)
+      const i64 nt = L.ntiles;
+      a.tri_trace = dev_alloc<unsigned long long>(nt * 8);
+      NGB_CUDA(cudaMemsetAsync(a.tri_trace, 0, sizeof(unsigned long long) * nt * 8, a.st));
+      run();
+      NGB_CUDA(cudaStreamSynchronize(a.st));
+      std::vector<unsigned long long> ht(nt * 8);
+      NGB_CUDA(cudaMemcpy(ht.data(), a.tri_trace, sizeof(unsigned long long) * nt * 8, cudaMemcpyDeviceToHost));
+      dev_free(a.tri_trace);
+      a.tri_trace = nullptr;
+      std::vector<i64> pp(nt + 1);
+      NGB_CUDA(cudaMemcpy(pp.data(), which == 0 ? L.d_tile_pred_ptr : L.d_tile_succ_ptr, sizeof(i64) * (nt + 1), cudaMemcpyDeviceToHost));
+      std::vector<i32> pl(std::max<i64>(pp[nt], 1));
+      NGB_CUDA(cudaMemcpy(pl.data(), which == 0 ? L.d_tile_pred : L.d_tile_succ, sizeof(i32) * pp[nt], cudaMemcpyDeviceToHost));
+      std::string fn = std::string(tf) + (which == 0 ? ".ctile.fwd" : ".ctile.bwd");
+      if (FILE *f = std::fopen(fn.c_str(), "wb")) {
+        const i64 np = pp[nt];
+        std::fwrite(&nt, sizeof(i64), 1, f);
+        std::fwrite(&np, sizeof(i64), 1, f);
+        std::fwrite(pp.data(), sizeof(i64), nt + 1, f);
+        std::fwrite(pl.data(), sizeof(i32), np, f);
+        std::fwrite(ht.data(), sizeof(unsigned long long), ht.size(), f);
+        std::fclose(f);
+      }
+    } else if (which == 0 || which == 3) {
       const i64 ns = L.npad / 32;
       a.tri_trace = dev_alloc<unsigned long long>(ns * 3);
       NGB_CUDA(cudaMemsetAsync(a.tri_trace, 0, sizeof(unsigned long long) * ns * 3, a.st));

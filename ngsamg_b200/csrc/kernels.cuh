@@ -232,11 +232,10 @@ __global__ void __launch_bounds__(256) k_sell_spmv_small(i64 nrows_pad, SellView
 // is resident (the host sizes it from the occupancy calculator).  Each warp loads its matrix entries BEFORE it starts
 // polling, so HBM latency is off the dependency chain; the chain costs one L2 store->load hop per dependency level.
 // ------------------------------------------------------------------------------------------------
-__device__ int g_pollmode;  // experiment switch: flavour of the polling load
-__device__ __forceinline__ double ld_poll(const double *p)
+// m = flavour of the polling load (flag ngs_amg_b200_tri_pollmode; a per-handle kernel parameter)
+__device__ __forceinline__ double ld_poll(const double *p, int m)
 {
   double v;
-  const int m = g_pollmode;
   if (m == 0) asm volatile("ld.relaxed.gpu.global.f64 %0, [%1];" : "=d"(v) : "l"(p));
   else if (m == 1) asm volatile("ld.volatile.global.f64 %0, [%1];" : "=d"(v) : "l"(p));
   else if (m == 2) asm volatile("ld.acquire.gpu.global.f64 %0, [%1];" : "=d"(v) : "l"(p));
@@ -264,6 +263,7 @@ struct TriParams {
   int regate;         // 1: stragglers are waited for with a single polling lane (re-gate) instead of all lanes spinning
   i64 nonfree;        // rows [0, nonfree) are the non-free rows (dependency level 0)
   int *err;           // watchdog flag (set if a wait exceeds ~2^26 polls; never in a healthy run)
+  int pollmode;       // flavour of the polling load (ld_poll)
   const i32 *bnd;     // split gate: per slice, first row of the previous level (forward) / end row of the next level (backward)
   unsigned long long *trace;  // debug: per slice {pick-up, gate passed, published} globaltimer stamps (NULL = off)
 };
@@ -360,7 +360,7 @@ __global__ void __launch_bounds__(256) k_gs_tri(SellView T, const double *__rest
       }
       if (f >= 0 && lane == 0) {
         unsigned spins = 0;
-        while (is_sentinel(ld_poll(out + (i64)f * B))) {
+        while (is_sentinel(ld_poll(out + (i64)f * B, prm.pollmode))) {
           if (prm.sleep_ns) __nanosleep(prm.sleep_ns);
           if (spin_fail(spins, prm.err)) break;
         }
@@ -392,7 +392,7 @@ __global__ void __launch_bounds__(256) k_gs_tri(SellView T, const double *__rest
       if (prm.trace && lane == 0) prm.trace[slice * 3 + 1] = gtimer();
       double xk[PRE > 0 ? PRE : 1];
 #pragma unroll
-      for (int k = 0; k < PRE; k++) xk[k] = (pc[k] >= 0) ? ld_poll(out + pc[k]) : 0.0;
+      for (int k = 0; k < PRE; k++) xk[k] = (pc[k] >= 0) ? ld_poll(out + pc[k], prm.pollmode) : 0.0;
       if (prm.regate) {
         // stragglers (the wavefront is not perfectly ordered): instead of spinning with all lanes, gate again with one
         // lane on an entry that is still unpublished, then re-poll only the missing entries
@@ -410,14 +410,14 @@ __global__ void __launch_bounds__(256) k_gs_tri(SellView T, const double *__rest
           if (u < 0) break;
           if (lane == 0 && (u >> 5) != slice) {
             unsigned spins = 0;
-            while (is_sentinel(ld_poll(out + u))) {
+            while (is_sentinel(ld_poll(out + u, prm.pollmode))) {
               if (prm.sleep_ns) __nanosleep(prm.sleep_ns);
               if (spin_fail(spins, prm.err)) break;
             }
           }
           __syncwarp();
 #pragma unroll
-          for (int k = 0; k < PRE; k++) if (pc[k] >= 0 && is_sentinel(xk[k])) xk[k] = ld_poll(out + pc[k]);
+          for (int k = 0; k < PRE; k++) if (pc[k] >= 0 && is_sentinel(xk[k])) xk[k] = ld_poll(out + pc[k], prm.pollmode);
           if (round > (1u << 22) || *(volatile int *)prm.err) { atomicExch(prm.err, 1); break; }
         }
       }
@@ -426,7 +426,7 @@ __global__ void __launch_bounds__(256) k_gs_tri(SellView T, const double *__rest
           bool un = false;
 #pragma unroll
           for (int k = 0; k < PRE; k++)
-            if (pc[k] >= 0 && is_sentinel(xk[k])) { xk[k] = ld_poll(out + pc[k]); un |= is_sentinel(xk[k]); }
+            if (pc[k] >= 0 && is_sentinel(xk[k])) { xk[k] = ld_poll(out + pc[k], prm.pollmode); un |= is_sentinel(xk[k]); }
           if (!__any_sync(0xffffffffu, un)) break;
           if ((it & 1023u) == 1023u && (it > (1u << 26) || *(volatile int *)prm.err)) { atomicExch(prm.err, 1); break; }
         }
@@ -437,7 +437,7 @@ __global__ void __launch_bounds__(256) k_gs_tri(SellView T, const double *__rest
           unsigned spins = 0;
           while (is_sentinel(xk[k])) {
             if (prm.repoll_ns) __nanosleep(prm.repoll_ns);
-            xk[k] = ld_poll(out + pc[k]);
+            xk[k] = ld_poll(out + pc[k], prm.pollmode);
             if (spin_fail(spins, prm.err)) break;
           }
           acc[0] = fma(-pv[k], xk[k], acc[0]);
@@ -472,7 +472,7 @@ __global__ void __launch_bounds__(256) k_gs_tri(SellView T, const double *__rest
       for (int j = 0; j < CH; j++)
         if (c[j] >= 0) {
 #pragma unroll
-          for (int q = 0; q < B; q++) xv[j][q] = ld_poll(out + (i64)c[j] * B + q);
+          for (int q = 0; q < B; q++) xv[j][q] = ld_poll(out + (i64)c[j] * B + q, prm.pollmode);
         }
 #pragma unroll
       for (int j = 0; j < CH; j++)
@@ -482,7 +482,7 @@ __global__ void __launch_bounds__(256) k_gs_tri(SellView T, const double *__rest
             unsigned spins = 0;
             while (is_sentinel(xv[j][q])) {
               if (prm.repoll_ns) __nanosleep(prm.repoll_ns);
-              xv[j][q] = ld_poll(out + (i64)c[j] * B + q);
+              xv[j][q] = ld_poll(out + (i64)c[j] * B + q, prm.pollmode);
               if (spin_fail(spins, prm.err)) break;
             }
           }
@@ -604,11 +604,11 @@ __global__ void __launch_bounds__(256) k_gs_tri_small(SellView T, const double *
       double xv[B];
 #pragma unroll
       for (int q = 0; q < B; q++) {
-        double v = ld_poll(out + (i64)c * B + q);
+        double v = ld_poll(out + (i64)c * B + q, prm.pollmode);
         unsigned spins = 0;
         while (is_sentinel(v)) {
           if (prm.sleep_ns) __nanosleep(prm.sleep_ns);
-          v = ld_poll(out + (i64)c * B + q);
+          v = ld_poll(out + (i64)c * B + q, prm.pollmode);
           if (spin_fail(spins, prm.err)) break;
         }
         xv[q] = v;

@@ -35,8 +35,10 @@ struct CTileParams {
   int *done;                 // hint flag per tile, zeroed before the launch
   unsigned sleep_ns;         // back-off of the hint polls
   unsigned repoll_ns;        // back-off of the data re-polls (stragglers)
+  int pollmode;              // flavour of the polling load (ld_poll)
   int cap_slots;             // capacity of the shared-memory slab in SELL slots (a slot = 32 entries)
   int *err;                  // watchdog
+  unsigned long long *trace; // debug: 8 words per tile {begin, hints passed, slab landed, gathered, levels done, end, smid|cta<<32, nlev|slices<<16} (NULL = off)
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -100,6 +102,8 @@ __global__ void __launch_bounds__(NT, (MAXS >= 16 ? 3 : 4)) k_gs_ctile(SellView 
   uint32_t phase = 0;
   for (i32 q = blockIdx.x; q < p.ntiles; q += gridDim.x) {
     const i32 t = p.backward ? (p.ntiles - 1 - q) : q;
+    unsigned long long *tr = (p.trace && tid == 0) ? p.trace + (size_t)t * 8 : nullptr;
+    if (tr) tr[0] = gtimer();
     const i32 s0 = p.tile_slice[t];
     const int ns = p.tile_slice[t + 1] - s0;
     const i32 r0 = s0 * 32;
@@ -143,8 +147,10 @@ __global__ void __launch_bounds__(NT, (MAXS >= 16 ? 3 : 4)) k_gs_ctile(SellView 
         }
       }
     }
+    if (tr) tr[1] = gtimer();
     if (has) { mbar_wait(bar, phase); phase ^= 1u; }
     __syncthreads();
+    if (tr) tr[2] = gtimer();
     // ---- couplings to rows of other tiles: poll the data itself (sentinel), a round of CH slots per owned row at a time
     int maxw = 0;
 #pragma unroll
@@ -160,7 +166,7 @@ __global__ void __launch_bounds__(NT, (MAXS >= 16 ? 3 : 4)) k_gs_ctile(SellView 
           i32 c = (k < wd[j]) ? cols_s[(sb[j] + k) * 32 + lane] : -1;
           if (c >= 0 && (unsigned)(c - r0) < nrow) c = -1;       // in-tile: served from shared memory below
           cc[j][e] = c;
-          xv[j][e] = (c >= 0) ? ld_poll(out + c) : 0.0;
+          xv[j][e] = (c >= 0) ? ld_poll(out + c, p.pollmode) : 0.0;
         }
 #pragma unroll
       for (int j = 0; j < NR; j++)
@@ -170,12 +176,13 @@ __global__ void __launch_bounds__(NT, (MAXS >= 16 ? 3 : 4)) k_gs_ctile(SellView 
             unsigned spins = 0;
             while (is_sentinel(xv[j][e])) {
               if (p.repoll_ns) __nanosleep(p.repoll_ns);
-              xv[j][e] = ld_poll(out + cc[j][e]);
+              xv[j][e] = ld_poll(out + cc[j][e], p.pollmode);
               if (spin_fail(spins, p.err)) break;
             }
             acc[j] = fma(-vals_s[(sb[j] + k0 + e) * 32 + lane], xv[j][e], acc[j]);
           }
     }
+    if (tr) tr[3] = gtimer();
     // ---- the tile itself, local level by local level (ascending forward, descending backward)
     const int nlev = p.tile_nlev[t];
     for (int it = 0; it < nlev; it++) {
@@ -213,6 +220,7 @@ __global__ void __launch_bounds__(NT, (MAXS >= 16 ? 3 : 4)) k_gs_ctile(SellView 
       }
       __syncthreads();
     }
+    if (tr) tr[4] = gtimer();
     // padding rows of the tile (no level): never updated, but `out` must not keep the sentinel
 #pragma unroll
     for (int j = 0; j < NR; j++)
@@ -222,6 +230,13 @@ __global__ void __launch_bounds__(NT, (MAXS >= 16 ? 3 : 4)) k_gs_ctile(SellView 
         if (WRITE_R) rout[(i64)r0 + lr] = acc[j];
       }
     if (tid == 0) st_relaxed_i32(p.done + t, 1);
+    if (tr) {
+      unsigned smid;
+      asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+      tr[5] = gtimer();
+      tr[6] = (unsigned long long)smid | ((unsigned long long)blockIdx.x << 32);
+      tr[7] = (unsigned long long)nlev | ((unsigned long long)ns << 16);
+    }
     __syncthreads();     // the slab and xs are reused by the next tile
   }
 }

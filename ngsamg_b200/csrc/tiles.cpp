@@ -1,6 +1,7 @@
 // tiles.cpp -- host construction of the two-level (tile DAG x tile-local levels) Gauss-Seidel schedule, see tiles.hpp.
 #include "tiles.hpp"
 
+#include <atomic>
 #include <cstdlib>
 #include <numeric>
 #include <queue>
@@ -359,6 +360,84 @@ void build_tile_schedule(const HostBsr &A, const std::vector<uint8_t> &mask, con
     for (i64 k = 0; k < sptr[t + 1] - sptr[t]; k++) ts.succ[ts.succ_ptr[q] + k] = newid[sl[sptr[t] + k]];
   }
   ts.ok = true;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------------
+// Cluster hint for matrices numbered like a structured grid (lexicographic x-fastest numbering of an N1 x N2 x N3 box -- what a
+// structured mesher, NGSolve's MakeStructured3DMesh or any "i + N1 (j + N2 k)" assembly loop produces).  Purely algebraic: the line
+// length N1 is the period of the rows that have no entry at column i-1, the plane size N1*N2 the first row >= N1 without an entry at
+// column i-N1; both are verified on every row.  The hint groups the smoothed rows into near-cubic boxes (edges as equal as the free
+// extents allow); build_tile_schedule turns them into tiles and splits whatever is not convex in the sweep DAG, so a wrong guess costs
+// depth, never correctness.  Returns false if the pattern is not of that kind (the caller falls back to the pairwise clustering).
+// ---------------------------------------------------------------------------------------------------------------------------
+bool grid_box_hint(const HostBsr &A, const std::vector<uint8_t> &mask, int max_rows, std::vector<i32> &hint, i64 dims[3])
+{
+  const i64 n = A.nrows;
+  if (n < 64) return false;
+  auto has = [&](i64 i, i64 j) {
+    if (j < 0) return false;
+    const i32 *b = A.col.data() + A.rowptr[i], *e = A.col.data() + A.rowptr[i + 1];
+    const i32 *q = std::lower_bound(b, e, (i32)j);
+    return q != e && *q == (i32)j;
+  };
+  // line length: rows 1 .. N1-1 are coupled to their predecessor, row N1 is not
+  i64 n1 = 0;
+  for (i64 i = 1; i < n; i++) if (!has(i, i - 1)) { n1 = i; break; }
+  if (n1 < 2) n1 = n;                     // a single line (1D) -- or no x-coupling at all
+  if (n % n1) return false;
+  i64 n12 = 0;
+  for (i64 i = n1; i < n; i += n1) if (!has(i, i - n1)) { n12 = i; break; }
+  if (n12 == 0) n12 = n;                  // a single plane (2D)
+  if (n12 % n1 || n % n12) return false;
+  const i64 N1 = n1, N2 = n12 / n1, N3 = n / n12;
+  // verify on all rows: every entry is a grid neighbour (|dx|,|dy|,|dz| <= 1) and the line / plane starts are where they should be
+  std::atomic<int> bad{0};
+  parallel_for(n, [&](i64 lo, i64 hi) {
+    for (i64 i = lo; i < hi && !bad.load(std::memory_order_relaxed); i++) {
+      const i64 x = i % N1, y = (i / N1) % N2, z = i / n12;
+      for (i64 k = A.rowptr[i]; k < A.rowptr[i + 1]; k++) {
+        const i64 j = A.col[k];
+        const i64 dx = j % N1 - x, dy = (j / N1) % N2 - y, dz = j / n12 - z;
+        if (dx < -1 || dx > 1 || dy < -1 || dy > 1 || dz < -1 || dz > 1) { bad = 1; return; }
+      }
+    }
+  }, 1 << 16);
+  if (bad) return false;
+  dims[0] = N1; dims[1] = N2; dims[2] = N3;
+  // extents of the smoothed rows
+  const bool hm = !mask.empty();
+  i64 lo[3] = {N1, N2, N3}, hi[3] = {-1, -1, -1};
+  for (i64 i = 0; i < n; i++) {
+    if (hm && !mask[i]) continue;
+    const i64 c[3] = {i % N1, (i / N1) % N2, i / n12};
+    for (int d = 0; d < 3; d++) { lo[d] = std::min(lo[d], c[d]); hi[d] = std::max(hi[d], c[d]); }
+  }
+  if (hi[0] < 0) return false;
+  i64 ext[3], nb[3];
+  int nd = 0;
+  for (int d = 0; d < 3; d++) { ext[d] = hi[d] - lo[d] + 1; nd += ext[d] > 1; }
+  if (nd == 0) return false;
+  // box edge: the largest e with e^nd <= max_rows; extents are cut into ceil(ext / e) nearly equal parts
+  i64 e = 1;
+  for (;;) {
+    i64 v = 1;
+    for (int d = 0; d < nd; d++) v *= (e + 1);
+    if (v > max_rows) break;
+    e++;
+  }
+  for (int d = 0; d < 3; d++) nb[d] = ext[d] > 1 ? (ext[d] + e - 1) / e : 1;
+  if ((double)nb[0] * nb[1] * nb[2] > 2.0e9) return false;
+  hint.assign(n, -1);
+  parallel_for(n, [&](i64 a, i64 b) {
+    for (i64 i = a; i < b; i++) {
+      if (hm && !mask[i]) continue;
+      const i64 c[3] = {i % N1, (i / N1) % N2, i / n12};
+      i64 bx[3];
+      for (int d = 0; d < 3; d++) bx[d] = (c[d] - lo[d]) * nb[d] / ext[d];
+      hint[i] = (i32)((bx[2] * nb[1] + bx[1]) * nb[0] + bx[0]);
+    }
+  }, 1 << 16);
+  return true;
 }
 
 i64 check_tile_schedule(const HostBsr &A, const std::vector<uint8_t> &mask, const std::vector<i32> &sweep_rank, const TileSchedule &ts)

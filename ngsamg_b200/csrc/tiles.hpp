@@ -36,6 +36,9 @@ void build_tile_schedule(const HostBsr &A, const std::vector<uint8_t> &mask, con
 // same tile and lower local level).  Returns the number of violations.
 i64 check_tile_schedule(const HostBsr &A, const std::vector<uint8_t> &mask, const std::vector<i32> &sweep_rank, const TileSchedule &ts);
 
+// cluster hint for matrices numbered like a structured grid (algebraic detection of the line / plane strides); false = not such a matrix
+bool grid_box_hint(const HostBsr &A, const std::vector<uint8_t> &mask, int max_rows, std::vector<i32> &hint, i64 dims[3]);
+
 i64 cluster_rows(const HostBsr &A, const uint8_t *keep, int rounds, double soc_thresh, std::vector<i32> &cluster, bool forward = false);
 
 }  // namespace ngb

@@ -46,7 +46,16 @@ static int tile_schedule_impl(const ngsamg_csr *A, const uint8_t *smoothed_mask,
     auto r = std::make_unique<ngsamg_b200_tiles>();
     std::vector<i32> hint;
     if (cluster_hint) hint.assign(cluster_hint, cluster_hint + A->nrows);
-    build_tile_schedule(h, mask, rank, rounds, max_rows, r->ts, cluster_hint ? &hint : nullptr);
+    bool hinted = cluster_hint != nullptr;
+    if (!hinted && rounds < 0) {
+      // rounds < 0: what the library does at setup -- box-shaped clusters if the matrix is numbered like a structured grid, else the
+      // pairwise clustering with as many rounds as the capacity asks for
+      i64 dims[3];
+      hinted = grid_box_hint(h, mask, max_rows, hint, dims);
+      rounds = 5;
+      while ((1 << rounds) < max_rows) rounds++;
+    }
+    build_tile_schedule(h, mask, rank, rounds, max_rows, r->ts, hinted ? &hint : nullptr);
     if (r->ts.ok) r->violations = check_tile_schedule(h, mask, rank, r->ts);
     if (info) {
       const TileSchedule &t = r->ts;

@@ -192,3 +192,34 @@ def test_regularize_matrix_method_is_host_only():
     h1._lib = pc._lib
     before = M.val.copy()
     assert h1.RegularizeMatrix(M) is M and np.array_equal(M.val, before) and pc.GetNProcs() == 1      # H1: nothing to regularise
+
+
+def test_vector_arguments_are_checked_before_they_reach_the_c_abi():
+    """the C ABI reads n doubles through every vector pointer: float32 / strided / short arrays must raise, not corrupt memory"""
+    from ngsamg_b200 import _lib
+    ok = np.zeros(10)
+    assert _lib.vec(ok, 10).value == ok.ctypes.data
+    with pytest.raises(TypeError):
+        _lib.vec(np.zeros(10, np.float32), 10)
+    with pytest.raises(ValueError):
+        _lib.vec(np.zeros(20)[::2], 10)
+    with pytest.raises(ValueError):
+        _lib.vec(np.zeros(9), 10)
+    with pytest.raises(TypeError):
+        _lib.vec([0.0] * 10, 10)
+    assert _lib.vec(None, 10) is None
+
+
+def test_malformed_matrices_are_rejected():
+    """check_csr: row pointers monotone, columns in range and strictly ascending (host-only entry point, no device needed)"""
+    import ngsamg_b200 as ng
+    rp = np.array([0, 2, 4], np.int64)
+    good = ng.SparseMatrix(2, 2, 1, 1, rp, np.array([0, 1, 0, 1], np.int32), np.ones(4))
+    ng.coarsen(good, None)
+    for col in ([1, 0, 0, 1], [0, 0, 0, 1], [0, 2, 0, 1], [0, -1, 0, 1]):
+        bad = ng.SparseMatrix(2, 2, 1, 1, rp, np.array(col, np.int32), np.ones(4))
+        with pytest.raises(Exception):
+            ng.coarsen(bad, None)
+    bad = ng.SparseMatrix(2, 2, 1, 1, np.array([0, 3, 2], np.int64), np.array([0, 1, 0, 1], np.int32), np.ones(4))
+    with pytest.raises(Exception):
+        ng.coarsen(bad, None)

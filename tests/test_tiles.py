@@ -83,7 +83,8 @@ def emulate_forward(A, free, d, res):
     return out, rout
 
 
-@pytest.mark.parametrize("cfg", [dict(rounds=5, max_rows=32), dict(rounds=6, max_rows=64), dict(rounds=3, max_rows=32)])
+@pytest.mark.parametrize("cfg", [dict(rounds=5, max_rows=32), dict(rounds=6, max_rows=64), dict(rounds=3, max_rows=32),
+                                 dict(rounds=-1, max_rows=256), dict(rounds=9, max_rows=512)])
 def test_tile_schedule_is_a_valid_sweep_order(cfg):
     p = S.poisson3d_kuhn(13, 11, 9)
     A = ng.SparseMatrix(p["n"], p["n"], 1, 1, p["rowptr"], p["col"], p["val"])
@@ -208,7 +209,7 @@ def emulate_backward(A, free, d, t_in, x_old):
     return out
 
 
-@pytest.mark.parametrize("cfg", [dict(rounds=5, max_rows=32), dict(rounds=6, max_rows=64)])
+@pytest.mark.parametrize("cfg", [dict(rounds=5, max_rows=32), dict(rounds=6, max_rows=64), dict(rounds=-1, max_rows=512)])
 def test_tile_schedule_backward_sweep(cfg):
     """the same schedule run backwards (successor lists, descending local levels) == GSS3::SmoothRHSInternal(backwards) of the oracle"""
     p = S.poisson3d_kuhn(11, 13, 9)
@@ -229,3 +230,33 @@ def test_tile_schedule_backward_sweep(cfg):
     dinv = O.calc_dinv(to_oracle(A), p["free"])
     O.gs_rhs(to_oracle(A), dinv, p["free"], xo, b, True)
     assert rel(x_new[free], xo[free]) < 1e-13
+
+
+@pytest.mark.parametrize("dims", [(23, 23, 23), (17, 9, 26), (40, 33, 1)])
+def test_grid_numbered_matrices_get_box_tiles(dims):
+    """rounds < 0 (the setup default): a matrix numbered like a structured grid is detected from its pattern alone (line length = period
+    of the rows without a left neighbour, plane size likewise) and tiled into near-cubic boxes -> the ideal tile DAG sum_d ceil(ext_d / e) - 2"""
+    p = S.poisson3d_kuhn(*dims)
+    A = ng.SparseMatrix(p["n"], p["n"], 1, 1, p["rowptr"], p["col"], p["val"])
+    d = tile_schedule(A, p["free"], None, rounds=-1, max_rows=512)
+    assert d["ok"] == 1 and d["violations"] == 0
+    free = p["free"].astype(bool).reshape(dims[::-1])
+    ext = [int(np.any(free, axis=tuple(a for a in range(3) if a != ax)).sum()) for ax in (2, 1, 0)]
+    nd = sum(e > 1 for e in ext)
+    edge = int(np.floor(512 ** (1.0 / nd) + 1e-9))
+    ideal = sum(-(-e // edge) for e in ext if e > 1) - (nd - 1)
+    assert d["tile_depth"] == ideal, (d["tile_depth"], ideal, ext)
+    assert d["max_local_levels"] <= nd * edge - (nd - 1)
+
+
+def test_a_scrambled_numbering_falls_back_to_the_pairwise_clustering():
+    """the grid detector must refuse a matrix that is not numbered like a grid (the schedule is still valid, built from the matching)"""
+    p = S.poisson3d_kuhn(9, 9, 9)
+    rng = np.random.default_rng(5)
+    q = rng.permutation(p["n"])
+    M = sp.csr_matrix((p["val"], p["col"], p["rowptr"]), shape=(p["n"], p["n"]))
+    Mp = M[q][:, q].tocsr()
+    Mp.sort_indices()
+    A = ng.SparseMatrix(p["n"], p["n"], 1, 1, Mp.indptr.astype(np.int64), Mp.indices.astype(np.int32), Mp.data)
+    d = tile_schedule(A, p["free"][q], None, rounds=-1, max_rows=512)
+    assert d["ok"] == 1 and d["violations"] == 0
