@@ -137,7 +137,7 @@ double ngsamg_b200_operator_complexity(ngsamg_b200_t *h);
 /* algorithmic bytes of one V(1,1)-cycle, SURVEY.md §8d formula B_V, from the actual level sizes */
 double ngsamg_b200_vcycle_bytes(ngsamg_b200_t *h);
 /* device milliseconds (CUDA events on the library stream) of the last apply / pcg call, setup phases */
-double ngsamg_b200_last_ms(ngsamg_b200_t *h, int what); /* 0 apply, 1 pcg, 2 setup total, 3 setup RAP, 4 setup host */
+double ngsamg_b200_last_ms(ngsamg_b200_t *h, int what); /* 0 apply, 1 pcg, 2 setup total, 3 setup RAP (device transpose + both SpGEMMs of every level), 4 setup host, 5 = compulsory BYTES of those products (M_f + 2 P + M_c) */
 /* number of kernel launches issued by the library since create (bench.py's gpu_launches) */
 int64_t ngsamg_b200_launch_count(ngsamg_b200_t *h);
 

@@ -307,7 +307,7 @@ class Preconditioner:
         return float(self._lib.ngsamg_b200_vcycle_bytes(self._h))
 
     def LastMs(self, what="apply"):
-        return float(self._lib.ngsamg_b200_last_ms(self._h, {"apply": 0, "pcg": 1, "setup": 2, "rap": 3, "host": 4}[what]))
+        return float(self._lib.ngsamg_b200_last_ms(self._h, {"apply": 0, "pcg": 1, "setup": 2, "rap": 3, "host": 4, "rap_bytes": 5}[what]))
 
     def LaunchCount(self):
         return int(self._lib.ngsamg_b200_launch_count(self._h))

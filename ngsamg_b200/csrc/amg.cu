@@ -99,7 +99,10 @@ struct Level {
   i64 *d_tile_pred_ptr = nullptr, *d_tile_succ_ptr = nullptr;
   int *d_tile_done = nullptr;
   // CTA-per-tile sweep (kernels_ctile.cuh; tile capacity >= 128 rows): slab capacity, launch geometry
-  std::vector<i32> h_tile_slice;
+  std::vector<i32> h_tile_slice, h_tile_nlev;
+  std::vector<i64> h_pred_ptr, h_succ_ptr;
+  CTileMeta *d_meta_fwd = nullptr, *d_meta_bwd = nullptr;
+  int tile_nbuf = 1;
   int tile_cap_slots = 0;
   int ctile_grid[2] = {0, 0};     // [add_self]
   size_t ctile_smem = 0;
@@ -175,7 +178,7 @@ struct Amg {
   double *io_a = nullptr, *io_b = nullptr, *io_c = nullptr;  // device staging in original numbering
   i64 io_n = 0;
   i64 launches = 0;
-  double ms_apply = 0, ms_pcg = 0, ms_setup = 0, ms_rap = 0, ms_host = 0;
+  double ms_apply = 0, ms_pcg = 0, ms_setup = 0, ms_rap = 0, ms_host = 0, bytes_rap = 0;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   int tri_grid_cap[32] = {0};
   i64 tri_small_rows = 1000000;
@@ -551,7 +554,7 @@ Amg::~Amg()
     Level &L = *lp;
     L.G.release();
     dev_free(L.d_tile_slice); dev_free(L.d_tile_nlev); dev_free(L.d_tile_pred); dev_free(L.d_tile_succ); dev_free(L.d_row_lvl);
-    dev_free(L.d_tile_pred_ptr); dev_free(L.d_tile_succ_ptr); dev_free(L.d_tile_done);
+    dev_free(L.d_tile_pred_ptr); dev_free(L.d_tile_succ_ptr); dev_free(L.d_tile_done); dev_free(L.d_meta_fwd); dev_free(L.d_meta_bwd);
     dev_free(L.d_m_idx); dev_free(L.d_g_idx); dev_free(L.d_mu_dof); dev_free(L.d_mu_ptr); dev_free(L.d_mu_pos);
     dev_free(L.sendbuf); dev_free(L.recvbuf);
     if (L.h_send) cudaFreeHost(L.h_send);
@@ -703,39 +706,55 @@ void Amg::build_level_layout(Level &L, const DevCsr &dA)
   dev_free(d_err);
 }
 
-// the four instantiations of the CTA-per-tile sweep: [maxs == 16][add_self]
+// the instantiations of the CTA-per-tile sweep: [maxs == 16][nbuf == 2][add_self]
 constexpr int CTILE_NT = 256;
 using CTileKernel = void (*)(SellView, const double *, const double *, const double *, const double *, double *, double *, CTileParams);
-static CTileKernel ctile_kernel(int maxs, bool add_self)
+static CTileKernel ctile_kernel(int maxs, int nbuf, bool add_self)
 {
-  if (maxs <= 8) return add_self ? (CTileKernel)k_gs_ctile<CTILE_NT, 8, true, false> : (CTileKernel)k_gs_ctile<CTILE_NT, 8, false, true>;
-  return add_self ? (CTileKernel)k_gs_ctile<CTILE_NT, 16, true, false> : (CTileKernel)k_gs_ctile<CTILE_NT, 16, false, true>;
+  if (maxs <= 8) {
+    if (nbuf == 1) return add_self ? (CTileKernel)k_gs_ctile<CTILE_NT, 8, 1, true, false> : (CTileKernel)k_gs_ctile<CTILE_NT, 8, 1, false, true>;
+    return add_self ? (CTileKernel)k_gs_ctile<CTILE_NT, 8, 2, true, false> : (CTileKernel)k_gs_ctile<CTILE_NT, 8, 2, false, true>;
+  }
+  if (nbuf == 1) return add_self ? (CTileKernel)k_gs_ctile<CTILE_NT, 16, 1, true, false> : (CTileKernel)k_gs_ctile<CTILE_NT, 16, 1, false, true>;
+  return add_self ? (CTileKernel)k_gs_ctile<CTILE_NT, 16, 2, true, false> : (CTileKernel)k_gs_ctile<CTILE_NT, 16, 2, false, true>;
 }
-
 // CTA-per-tile sweep: slab capacity (largest tile of L and U, in SELL slots), shared-memory opt-in, resident grid
 void Amg::prepare_ctile(Level &L)
 {
   i64 cap = 1;
-  for (const Sell *S : {&L.L, &L.U}) {
+  const i64 nt = L.ntiles;
+  std::vector<CTileMeta> meta[2];
+  for (int dir = 0; dir < 2; dir++) {
+    const Sell *S = dir ? &L.U : &L.L;
+    const std::vector<i64> &dp = dir ? L.h_succ_ptr : L.h_pred_ptr;
     std::vector<i64> sp(S->nslices + 1);
     NGB_CUDA(cudaMemcpyAsync(sp.data(), S->slice_ptr, sizeof(i64) * (S->nslices + 1), cudaMemcpyDeviceToHost, st));
     NGB_CUDA(cudaStreamSynchronize(st));
-    for (i64 t = 0; t < L.ntiles; t++) cap = std::max(cap, sp[L.h_tile_slice[t + 1]] - sp[L.h_tile_slice[t]]);
+    meta[dir].resize(nt);
+    for (i64 t = 0; t < nt; t++) {
+      const i32 s0 = L.h_tile_slice[t], s1 = L.h_tile_slice[t + 1];
+      const i64 slots = sp[s1] - sp[s0];
+      cap = std::max(cap, slots);
+      if (dp[t] >= (i64)2147483647) throw Error("tile sweep: wait lists too long");
+      meta[dir][t] = CTileMeta{sp[s0], s0, s1 - s0, (i32)slots, L.h_tile_nlev[t], (i32)dp[t], (i32)(dp[t + 1] - dp[t])};
+    }
   }
+  L.d_meta_fwd = upload_vec(meta[0], st);
+  L.d_meta_bwd = upload_vec(meta[1], st);
   L.tile_cap_slots = (int)cap;
-  L.ctile_smem = ctile_smem_bytes(L.tile_maxs, L.tile_cap_slots);
+  L.ctile_smem = ctile_smem_bytes(L.tile_maxs, L.tile_cap_slots, L.tile_nbuf);
   int dev_max = 0;
   NGB_CUDA(cudaDeviceGetAttribute(&dev_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
   if (L.ctile_smem > (size_t)dev_max)
     throw Error("tile sweep: a tile needs " + std::to_string(L.ctile_smem) + " bytes of shared memory (device limit " + std::to_string(dev_max) + "); use smaller tiles (ngs_amg_b200_tile_rows)");
   for (int as = 0; as < 2; as++) {
-    CTileKernel k = ctile_kernel(L.tile_maxs, as == 1);
+    CTileKernel k = ctile_kernel(L.tile_maxs, L.tile_nbuf, as == 1);
     {
       // the opt-in is per kernel, not per level: keep the largest request of any hierarchy of this process
       static std::mutex mu;
-      static size_t granted[2][2] = {{0, 0}, {0, 0}};
+      static size_t granted[2][2][2] = {};
       std::lock_guard<std::mutex> guard(mu);
-      size_t &g = granted[L.tile_maxs <= 8 ? 0 : 1][as];
+      size_t &g = granted[L.tile_maxs <= 8 ? 0 : 1][L.tile_nbuf - 1][as];
       g = std::max(g, L.ctile_smem);
       NGB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g));
     }
@@ -744,19 +763,20 @@ void Amg::prepare_ctile(Level &L)
     occ = std::max(1, occ);
     if (tri_ctas_per_sm > 0) occ = std::min(occ, tri_ctas_per_sm);
     L.ctile_grid[as] = (int)std::max<i64>(1, std::min<i64>(L.ntiles, (i64)occ * num_sms));
-    if (flags.str("log_level", "none") != "none") std::fprintf(stderr, "[ngsamg_b200] tile sweep (%s): %lld tiles, slab %d slots, %zu B smem, %d CTAs/SM, grid %d\n", as ? "backward/rhs" : "forward/res",
-                              (long long)L.ntiles, L.tile_cap_slots, L.ctile_smem, occ, L.ctile_grid[as]);
+    if (flags.str("log_level", "none") != "none")
+      std::fprintf(stderr, "[ngsamg_b200] tile sweep (%s): %lld tiles, %d slab(s) of %d slots, %zu B smem, %d CTAs/SM, grid %d\n", as ? "backward/rhs" : "forward/res",
+                   (long long)L.ntiles, L.tile_nbuf, L.tile_cap_slots, L.ctile_smem, occ, L.ctile_grid[as]);
   }
 }
 
 void Amg::build_transfer_layout(Level &F, Level &C)
 {
   // P: rows = fine (level-scheduled), cols = coarse (level-scheduled); PT the other way round
-  HostBsr PT;
-  host_transpose(F.hP, PT);
   DevCsr dP, dPT;
   dev_csr_upload(F.hP, dP, st);
-  dev_csr_upload(PT, dPT, st);
+  dev_transpose(dP, dPT, st, &launches);
+  HostBsr PT;                                  // pattern only: the storage order of the restriction rows is decided on the host
+  dev_csr_download(dPT, PT, st, false);
   {
     i32 *len = dev_alloc<i32>(F.npad);
     NGB_CUDA(cudaMemsetAsync(len, 0, sizeof(i32) * F.npad, st));
@@ -878,7 +898,7 @@ void Amg::finalize()
   if (finalized) throw Error("finalize called twice");
   if (par) { finalize_parallel(); return; }
   auto t0 = std::chrono::steady_clock::now();
-  double host_s = 0, rap_ms = 0;
+  double host_s = 0, rap_ms = 0, rap_bytes = 0;
   const bool verbose = flags.str("log_level", "none") != "none";   // factory log levels, base_factory.cpp:83-199
   auto tick = [](std::chrono::steady_clock::time_point t) { return std::chrono::duration<double>(std::chrono::steady_clock::now() - t).count(); };
   const int max_levels = (int)flags.num("max_levels", 10);            // base_factory.hpp:88-152
@@ -948,20 +968,22 @@ void Amg::finalize()
     if (!coarsest) {
       // Galerkin product on the device: A_{l+1} = (P^T A_l) P
       if (injected.empty() == false && l + 1 >= (int)lev.size()) lev.push_back(std::make_unique<Level>());
-      cudaEventRecord(ev0, st);
-      HostBsr PT;
-      host_transpose(L.hP, PT);
+      // P travels to the device once; transpose (K12) and both products (K10/K11) run there and are timed alone
       DevCsr dP, dPT, dPTA;
       dev_csr_upload(L.hP, dP, st);
-      dev_csr_upload(PT, dPT, st);
+      cudaEventRecord(ev0, st);
+      dev_transpose(dP, dPT, st, &launches);
       dev_spgemm(dPT, dA, dPTA, st, &launches);
       dev_spgemm(dPTA, dP, dAc, st, &launches);
-      dev_csr_free(dPTA); dev_csr_free(dP); dev_csr_free(dPT);
       cudaEventRecord(ev1, st);
       cudaEventSynchronize(ev1);
       float ms = 0;
       cudaEventElapsedTime(&ms, ev0, ev1);
       rap_ms += ms;
+      // compulsory traffic of the triple product: read A_f, P and P^T once, write A_c once (M_f + 2 P + M_c)
+      rap_bytes += (double)dA.nnz * (8.0 * dA.bs() + 4) + 8.0 * (dA.nrows + 1) + 2.0 * ((double)dP.nnz * (8.0 * dP.bs() + 4) + 8.0 * (dP.nrows + 1)) +
+                   (double)dAc.nnz * (8.0 * dAc.bs() + 4) + 8.0 * (dAc.nrows + 1);
+      dev_csr_free(dPTA); dev_csr_free(dP); dev_csr_free(dPT);
       L.nc = L.hP.ncols; L.bc = L.hP.bw;
       dev_csr_download(dAc, lev[l + 1]->hA, st, true);
       if (injected.empty() && flags.flag("b200_color_coarse", true)) {
@@ -1017,7 +1039,9 @@ void Amg::finalize()
           L.d_tile_pred_ptr = upload_vec(ts.pred_ptr, st); L.d_tile_pred = upload_vec(ts.pred, st);
           L.d_tile_succ_ptr = upload_vec(ts.succ_ptr, st); L.d_tile_succ = upload_vec(ts.succ, st);
           L.d_tile_done = dev_alloc<int>((size_t)ts.ntiles);
-          L.h_tile_slice = ts.tile_slice;
+          L.h_tile_slice = ts.tile_slice; L.h_tile_nlev = ts.tile_nlev; L.h_pred_ptr = ts.pred_ptr; L.h_succ_ptr = ts.succ_ptr;
+          L.tile_nbuf = (int)flags.num("b200_tile_nbuf", 1);
+          if (L.tile_nbuf != 1 && L.tile_nbuf != 2) throw Error("ngs_amg_b200_tile_nbuf must be 1 or 2");
           L.tiled = true;
           if (verbose) std::fprintf(stderr, "[ngsamg_b200] level %d: tile schedule: %lld tiles, tile DAG depth %d, <= %d local levels\n", l, (long long)ts.ntiles, ts.tile_depth, ts.max_local_levels);
         }
@@ -1047,6 +1071,7 @@ void Amg::finalize()
   finalized = true;
   ms_setup = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
   ms_rap = rap_ms;
+  bytes_rap = rap_bytes;
   ms_host = host_s * 1e3;
 }
 
@@ -1231,7 +1256,7 @@ void Amg::contracted_solve(Level &L)
 void Amg::finalize_parallel()
 {
   auto t0 = std::chrono::steady_clock::now();
-  double host_s = 0, rap_ms = 0;
+  double host_s = 0, rap_ms = 0, rap_bytes = 0;
   auto tick = [](std::chrono::steady_clock::time_point t) { return std::chrono::duration<double>(std::chrono::steady_clock::now() - t).count(); };
   const bool verbose = flags.str("log_level", "none") != "none";
   const int me = comm.rank(), R = comm.size();
@@ -1328,6 +1353,7 @@ void Amg::finalize_parallel()
         N.finalize();
         launches += N.launches;
         rap_ms += N.ms_rap;
+        rap_bytes += N.bytes_rap;
         host_s += N.ms_host * 1e-3;
       }
       break;
@@ -1378,20 +1404,22 @@ void Amg::finalize_parallel()
     // Galerkin product of the DISTRIBUTED local matrix: A_{l+1}^loc = P^T A_l^loc P (P rows are identical on all sharers)
     DevCsr dAc;
     {
-      cudaEventRecord(ev0, st);
-      HostBsr PT;
-      host_transpose(L.hP, PT);
+      // P travels to the device once; transpose (K12) and both products (K10/K11) run there and are timed alone
       DevCsr dP, dPT, dPTA;
       dev_csr_upload(L.hP, dP, st);
-      dev_csr_upload(PT, dPT, st);
+      cudaEventRecord(ev0, st);
+      dev_transpose(dP, dPT, st, &launches);
       dev_spgemm(dPT, dA, dPTA, st, &launches);
       dev_spgemm(dPTA, dP, dAc, st, &launches);
-      dev_csr_free(dPTA); dev_csr_free(dP); dev_csr_free(dPT);
       cudaEventRecord(ev1, st);
       cudaEventSynchronize(ev1);
       float ms = 0;
       cudaEventElapsedTime(&ms, ev0, ev1);
       rap_ms += ms;
+      // compulsory traffic of the triple product: read A_f, P and P^T once, write A_c once (M_f + 2 P + M_c)
+      rap_bytes += (double)dA.nnz * (8.0 * dA.bs() + 4) + 8.0 * (dA.nrows + 1) + 2.0 * ((double)dP.nnz * (8.0 * dP.bs() + 4) + 8.0 * (dP.nrows + 1)) +
+                   (double)dAc.nnz * (8.0 * dAc.bs() + 4) + 8.0 * (dAc.nrows + 1);
+      dev_csr_free(dPTA); dev_csr_free(dP); dev_csr_free(dPT);
       L.nc = L.hP.ncols; L.bc = L.hP.bw;
       dev_csr_download(dAc, C.hA, st, true);
     }
@@ -1452,6 +1480,7 @@ void Amg::finalize_parallel()
   finalized = true;
   ms_setup = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
   ms_rap = rap_ms;
+  bytes_rap = rap_bytes;
   ms_host = host_s * 1e3;
 }
 
@@ -1493,14 +1522,13 @@ void Amg::tri(Level &L, bool backward, bool add_self, bool write_r, const double
       if (!add_self && !write_r) throw Error("tri: unsupported mode");
       NGB_CUDA(cudaMemsetAsync(out, 0xFF, sizeof(double) * L.npad, st));
       NGB_CUDA(cudaMemsetAsync(L.d_tile_done, 0, sizeof(int) * (size_t)L.ntiles, st));
-      CTileParams prm{(i32)L.ntiles, backward ? 1 : 0, L.d_tile_slice, L.d_tile_nlev, L.d_row_lvl,
-                      backward ? L.d_tile_succ_ptr : L.d_tile_pred_ptr, backward ? L.d_tile_succ : L.d_tile_pred, L.d_tile_done,
-                      tri_sleep_ns, tri_repoll_ns, tri_pollmode, L.tile_cap_slots, d_err, tri_trace};
+      CTileParams prm{(i32)L.ntiles, backward ? 1 : 0, backward ? L.d_meta_bwd : L.d_meta_fwd, L.d_row_lvl, backward ? L.d_tile_succ : L.d_tile_pred,
+                      L.d_tile_done, tri_sleep_ns, tri_repoll_ns, tri_pollmode, L.tile_cap_slots, d_err, tri_trace};
       if (L.nonfree_pad) {
         if (add_self) k_gs_tile_prefix<true, false><<<nblk(L.nonfree_pad), TB, 0, st>>>(L.nonfree_pad, rin, self, out, rout);
         else k_gs_tile_prefix<false, true><<<nblk(L.nonfree_pad), TB, 0, st>>>(L.nonfree_pad, rin, self, out, rout);
       }
-      launch_resident_smem(ctile_kernel(L.tile_maxs, add_self), L.ctile_grid[add_self ? 1 : 0], CTILE_NT, L.ctile_smem, st, T.view(),
+      launch_resident_smem(ctile_kernel(L.tile_maxs, L.tile_nbuf, add_self), L.ctile_grid[add_self ? 1 : 0], CTILE_NT, L.ctile_smem, st, T.view(),
                            (const double *)L.diag, (const double *)L.dinv, rin, self, out, rout, prm);
       launches += 2;
       return;
@@ -2888,6 +2916,7 @@ double ngsamg_b200_last_ms(ngsamg_b200_t *h, int what)
     case 2: return h->amg.ms_setup;
     case 3: return h->amg.ms_rap;
     case 4: return h->amg.ms_host;
+    case 5: return h->amg.bytes_rap;   // compulsory bytes of all Galerkin products (M_f + 2 P + M_c per level)
   }
   return 0.0;
 }
@@ -2923,13 +2952,10 @@ int ngsamg_b200_rap_begin(const ngsamg_csr *A, const ngsamg_csr *P, int device, 
   NGB_TRY
   require_device(device);
   check_csr(A, "rap"); check_csr(P, "rap");
-  HostBsr hP, hPT;
-  copy_csr(P, hP);
-  host_transpose(hP, hPT);
   DevCsr dA, dP, dPT, dPTA;
   upload_abi(A, dA, nullptr);
-  dev_csr_upload(hP, dP, nullptr);
-  dev_csr_upload(hPT, dPT, nullptr);
+  upload_abi(P, dP, nullptr);
+  dev_transpose(dP, dPT, nullptr, nullptr);
   auto r = std::make_unique<ngsamg_b200_spm>();
   r->st = nullptr;
   dev_spgemm(dPT, dA, dPTA, nullptr, nullptr);
@@ -2946,12 +2972,12 @@ int ngsamg_b200_transpose_begin(const ngsamg_csr *A, int device, ngsamg_b200_spm
   NGB_TRY
   require_device(device);
   check_csr(A, "transpose");
-  HostBsr hA, hT;
-  copy_csr(A, hA);
-  host_transpose(hA, hT);
+  DevCsr dA;
+  upload_abi(A, dA, nullptr);
   auto r = std::make_unique<ngsamg_b200_spm>();
   r->st = nullptr;
-  dev_csr_upload(hT, r->d, nullptr);
+  dev_transpose(dA, r->d, nullptr, nullptr);
+  dev_csr_free(dA);
   if (nrows) *nrows = r->d.nrows;
   if (nnz) *nnz = r->d.nnz;
   *out = r.release();

@@ -48,4 +48,7 @@ void dev_csr_free(DevCsr &d);
 // A-row order then B-row order without FMA contraction (MatMultABImpl, utils_sparseMM.cpp:107-238).
 void dev_spgemm(const DevCsr &A, const DevCsr &B, DevCsr &C, cudaStream_t st, i64 *launches);
 
+// T = A^T with every block transposed; rows of T ascending (TransposeSPMImpl, utils_sparseMM.cpp:54-93) -- bit-identical integers
+void dev_transpose(const DevCsr &A, DevCsr &T, cudaStream_t st, i64 *launches);
+
 }  // namespace ngb

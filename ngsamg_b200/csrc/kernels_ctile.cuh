@@ -24,19 +24,29 @@
 
 namespace ngb {
 
+// everything a CTA needs to know about a tile before it touches the matrix, in one 32-byte record (one broadcast load per warp);
+// one array per sweep direction (the slab of L or U, predecessors or successors)
+struct __align__(16) CTileMeta {
+  i64 base;      // first SELL slot of the tile's slab in this part (L forward, U backward)
+  i32 s0;        // first 32-row slice of the tile
+  i32 ns;        // slices
+  i32 nslots;    // slots of the slab
+  i32 nlev;      // tile-local dependency levels
+  i32 d0;        // first entry of the tile's wait list in `dep`
+  i32 nd;        // tiles to wait for
+};
+
 struct CTileParams {
   i32 ntiles;
   int backward;
-  const i32 *tile_slice;     // ntiles + 1: first slice of every tile (schedule order)
-  const i32 *tile_nlev;      // tile-local dependency levels
+  const CTileMeta *meta;     // per tile, this direction
   const uint8_t *row_lvl;    // per row: tile-local level, 255 = padding
-  const i64 *dep_ptr;        // tiles to wait for: predecessors (forward) / successors (backward)
-  const i32 *dep;
+  const i32 *dep;            // wait lists: predecessors (forward) / successors (backward)
   int *done;                 // hint flag per tile, zeroed before the launch
   unsigned sleep_ns;         // back-off of the hint polls
   unsigned repoll_ns;        // back-off of the data re-polls (stragglers)
   int pollmode;              // flavour of the polling load (ld_poll)
-  int cap_slots;             // capacity of the shared-memory slab in SELL slots (a slot = 32 entries)
+  int cap_slots;             // capacity of ONE shared-memory slab in SELL slots (a slot = 32 entries)
   int *err;                  // watchdog
   unsigned long long *trace; // debug: 8 words per tile {begin, hints passed, slab landed, gathered, levels done, end, smid|cta<<32, nlev|slices<<16} (NULL = off)
 };
@@ -79,54 +89,77 @@ __device__ __forceinline__ int ld_relaxed_i32(const int *p)
 }
 __device__ __forceinline__ void st_relaxed_i32(int *p, int v) { asm volatile("st.relaxed.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
 
-constexpr int CTILE_HDR = 128;   // bytes in front of the slab: the mbarrier
-__host__ __device__ inline size_t ctile_smem_bytes(int maxs, int cap_slots) { return (size_t)CTILE_HDR + (size_t)maxs * 32 * 8 + (size_t)cap_slots * 32 * 12; }
+constexpr int CTILE_HDR = 128;   // bytes in front of the slabs: the mbarriers
+__host__ __device__ inline size_t ctile_smem_bytes(int maxs, int cap_slots, int nbuf)
+{
+  return (size_t)CTILE_HDR + (size_t)maxs * 32 * 8 + (size_t)nbuf * (size_t)cap_slots * 32 * 12;
+}
 
-template <int NT, int MAXS, bool ADD_SELF, bool WRITE_R>
+// NBUF = slabs in shared memory: 1 = the next tile's slab is fetched when the current tile is finished, 2 = while the current tile is
+// being swept (HBM latency never exposed; twice the shared memory).
+template <int NT, int MAXS, int NBUF, bool ADD_SELF, bool WRITE_R>
 __global__ void __launch_bounds__(NT, (MAXS >= 16 ? 3 : 4)) k_gs_ctile(SellView T, const double *__restrict__ diag, const double *__restrict__ dinv,
-                                                const double *rin, const double *__restrict__ self, double *out, double *rout,
-                                                CTileParams p)
+                                                                      const double *rin, const double *__restrict__ self, double *out, double *rout,
+                                                                      CTileParams p)
 {
   constexpr int NW = NT / 32;
   static_assert(MAXS % NW == 0, "every warp owns the same number of slices");
   constexpr int NR = MAXS / NW;                 // rows per thread: tile-local rows tid, tid + NT, ...
-  constexpr int CH = (NR <= 1) ? 8 : 4;         // slots gathered per round and row
+  constexpr int CH = (NR <= 2) ? 8 : 4;         // slots gathered per round and row
   extern __shared__ __align__(128) unsigned char smem_raw[];
   double *xs = (double *)(smem_raw + CTILE_HDR);                      // the tile's part of `out`
-  double *vals_s = xs + MAXS * 32;                                    // slab: values, then column indices
-  i32 *cols_s = (i32 *)(vals_s + (size_t)p.cap_slots * 32);
+  unsigned char *slab0 = (unsigned char *)(xs + MAXS * 32);            // NBUF slabs: values, then column indices
+  const size_t slab_bytes = (size_t)p.cap_slots * 32 * 12;
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
-  const uint32_t bar = smem_u32(smem_raw);
-  if (tid == 0) { mbar_init(bar, 1); mbar_fence_init(); }
+  const uint32_t bar0 = smem_u32(smem_raw);                           // mbarrier b at bar0 + 8 b
+  if (tid == 0) {
+    for (int b = 0; b < NBUF; b++) mbar_init(bar0 + 8 * b, 1);
+    mbar_fence_init();
+  }
   __syncthreads();
-  uint32_t phase = 0;
-  for (i32 q = blockIdx.x; q < p.ntiles; q += gridDim.x) {
-    const i32 t = p.backward ? (p.ntiles - 1 - q) : q;
+  auto tile_of = [&](i32 q) { return p.backward ? (p.ntiles - 1 - q) : q; };
+  auto fetch = [&](const CTileMeta &m, int buf) {                     // one thread: both bulk copies of a tile's slab
+    if (m.nslots <= 0) return;
+    unsigned char *sl = slab0 + (size_t)buf * slab_bytes;
+    const uint32_t bar = bar0 + 8 * buf;
+    mbar_expect_tx(bar, (uint32_t)m.nslots * 32u * 12u);
+    bulk_g2s(smem_u32(sl), T.val + m.base * 32, (uint32_t)m.nslots * 256u, bar);
+    bulk_g2s(smem_u32(sl + (size_t)p.cap_slots * 256), T.col + m.base * 32, (uint32_t)m.nslots * 128u, bar);
+  };
+  const CTileMeta none{0, 0, 0, 0, 0, 0, 0};
+  uint32_t phases = 0;                                                // bit b: parity the next wait on mbarrier b expects
+  i32 q = blockIdx.x;
+  if (q >= p.ntiles) return;
+  // software pipeline: the record of the NEXT tile (and the first tile it waits for) is loaded while the current tile is swept
+  CTileMeta cur = p.meta[tile_of(q)];
+  i32 cur_dep = (tid < cur.nd) ? p.dep[cur.d0 + tid] : -1;
+  if (tid == 0) fetch(cur, 0);
+  int buf = 0;
+  for (; q < p.ntiles; q += gridDim.x) {
+    const i32 t = tile_of(q);
     unsigned long long *tr = (p.trace && tid == 0) ? p.trace + (size_t)t * 8 : nullptr;
     if (tr) tr[0] = gtimer();
-    const i32 s0 = p.tile_slice[t];
-    const int ns = p.tile_slice[t + 1] - s0;
+    const i32 qn = q + (i32)gridDim.x;
+    const bool more = qn < p.ntiles;
+    const CTileMeta nxt = more ? p.meta[tile_of(qn)] : none;          // in flight until the end of this iteration
+    if (NBUF == 2 && more && tid == 0) fetch(nxt, buf ^ 1);           // the other slab is free: its tile finished an iteration ago
+    const i32 s0 = cur.s0;
+    const int ns = cur.ns;
     const i32 r0 = s0 * 32;
     const unsigned nrow = (unsigned)ns * 32u;
-    const i64 base0 = T.slice_ptr[s0];
-    const int nslots = (int)(T.slice_ptr[s0 + ns] - base0);
-    const bool has = nslots > 0;
-    if (has && tid == 0) {
-      mbar_expect_tx(bar, (uint32_t)nslots * 32u * 12u);
-      bulk_g2s(smem_u32(vals_s), T.val + base0 * 32, (uint32_t)nslots * 256u, bar);
-      bulk_g2s(smem_u32(cols_s), T.col + base0 * 32, (uint32_t)nslots * 128u, bar);
-    }
+    const double *vals_s = (const double *)(slab0 + (size_t)buf * slab_bytes);
+    const i32 *cols_s = (const i32 *)(slab0 + (size_t)buf * slab_bytes + (size_t)p.cap_slots * 256);
     // ---- per-row data that does not depend on `out`
-    double acc[NR], dv[NR], sv[NR], dg[NR];
+    double acc[NR], dv[NR], sv[NR], dg[NR], rs[NR];
     int lv[NR], sb[NR], wd[NR];
 #pragma unroll
     for (int j = 0; j < NR; j++) {
       const int sl = w + j * NW;
-      lv[j] = 256; sb[j] = 0; wd[j] = 0; acc[j] = 0.0; dv[j] = 0.0; sv[j] = 0.0; dg[j] = 0.0;
+      lv[j] = 256; sb[j] = 0; wd[j] = 0; acc[j] = 0.0; dv[j] = 0.0; sv[j] = 0.0; dg[j] = 0.0; rs[j] = 0.0;
       if (sl < ns) {
         const i64 slice = (i64)s0 + sl, row = slice * 32 + lane;
         const i64 b = T.slice_ptr[slice];
-        sb[j] = (int)(b - base0);
+        sb[j] = (int)(b - cur.base);
         wd[j] = (int)(T.slice_ptr[slice + 1] - b);
         lv[j] = p.row_lvl[row];
         acc[j] = rin[row];
@@ -135,56 +168,59 @@ __global__ void __launch_bounds__(NT, (MAXS >= 16 ? 3 : 4)) k_gs_ctile(SellView 
         if (WRITE_R) dg[j] = diag[row];
       }
     }
-    // ---- hint flags of the tiles this one depends on (one thread per dependency), then the slab
-    {
-      const i64 d0 = p.dep_ptr[t], d1 = p.dep_ptr[t + 1];
-      for (i64 k = d0 + tid; k < d1; k += NT) {
-        const int *f = p.done + p.dep[k];
-        unsigned spins = 0;
-        while (ld_relaxed_i32(f) == 0) {
-          if (p.sleep_ns) __nanosleep(p.sleep_ns);
-          if (spin_fail(spins, p.err)) break;
-        }
+    // ---- hint flags of the tiles this one depends on (one thread per dependency; the first NT ids were prefetched)
+    for (int k = tid; k < cur.nd; k += NT) {
+      const i32 dt = (k < NT) ? cur_dep : p.dep[cur.d0 + k];
+      const int *f = p.done + dt;
+      unsigned spins = 0;
+      while (ld_relaxed_i32(f) == 0) {
+        if (p.sleep_ns) __nanosleep(p.sleep_ns);
+        if (spin_fail(spins, p.err)) break;
       }
     }
     if (tr) tr[1] = gtimer();
-    if (has) { mbar_wait(bar, phase); phase ^= 1u; }
+    if (cur.nslots > 0) { mbar_wait(bar0 + 8 * buf, (phases >> buf) & 1u); phases ^= 1u << buf; }
     __syncthreads();
     if (tr) tr[2] = gtimer();
-    // ---- couplings to rows of other tiles: poll the data itself (sentinel), a round of CH slots per owned row at a time
+    // ---- couplings to rows of other tiles: poll the data itself (sentinel); all polls of a round of CH slots per owned row are in flight together
     int maxw = 0;
 #pragma unroll
     for (int j = 0; j < NR; j++) maxw = max(maxw, wd[j]);
     for (int k0 = 0; k0 < maxw; k0 += CH) {
-      i32 cc[NR][CH];
       double xv[NR][CH];
 #pragma unroll
       for (int j = 0; j < NR; j++)
 #pragma unroll
         for (int e = 0; e < CH; e++) {
           const int k = k0 + e;
-          i32 c = (k < wd[j]) ? cols_s[(sb[j] + k) * 32 + lane] : -1;
-          if (c >= 0 && (unsigned)(c - r0) < nrow) c = -1;       // in-tile: served from shared memory below
-          cc[j][e] = c;
-          xv[j][e] = (c >= 0) ? ld_poll(out + c, p.pollmode) : 0.0;
+          const i32 c = (k < wd[j]) ? cols_s[(sb[j] + k) * 32 + lane] : -1;
+          xv[j][e] = (c >= 0 && (unsigned)(c - r0) >= nrow) ? ld_poll(out + c, p.pollmode) : 0.0;   // in-tile columns: shared memory, below
         }
 #pragma unroll
       for (int j = 0; j < NR; j++)
 #pragma unroll
-        for (int e = 0; e < CH; e++)
-          if (cc[j][e] >= 0) {
-            unsigned spins = 0;
-            while (is_sentinel(xv[j][e])) {
-              if (p.repoll_ns) __nanosleep(p.repoll_ns);
-              xv[j][e] = ld_poll(out + cc[j][e], p.pollmode);
-              if (spin_fail(spins, p.err)) break;
+        for (int e = 0; e < CH; e++) {
+          const int k = k0 + e;
+          if (k < wd[j]) {
+            const i32 c = cols_s[(sb[j] + k) * 32 + lane];
+            if (c >= 0 && (unsigned)(c - r0) >= nrow) {
+              unsigned spins = 0;
+              while (is_sentinel(xv[j][e])) {
+                if (p.repoll_ns) __nanosleep(p.repoll_ns);
+                xv[j][e] = ld_poll(out + c, p.pollmode);
+                if (spin_fail(spins, p.err)) break;
+              }
+              acc[j] = fma(-vals_s[(sb[j] + k) * 32 + lane], xv[j][e], acc[j]);
             }
-            acc[j] = fma(-vals_s[(sb[j] + k0 + e) * 32 + lane], xv[j][e], acc[j]);
           }
+        }
     }
     if (tr) tr[3] = gtimer();
-    // ---- the tile itself, local level by local level (ascending forward, descending backward)
-    const int nlev = p.tile_nlev[t];
+    // the next tile's first dependency ids: its record has arrived by now
+    const i32 nxt_dep = (more && tid < nxt.nd) ? p.dep[nxt.d0 + tid] : -1;
+    // ---- the tile itself, local level by local level (ascending forward, descending backward).  No global stores in here: a store
+    // in flight would be waited for by every __syncthreads (0.38 us per level measured); results go to shared memory and registers.
+    const int nlev = cur.nlev;
     for (int it = 0; it < nlev; it++) {
       const int s = p.backward ? (nlev - 1 - it) : it;
 #pragma unroll
@@ -211,23 +247,21 @@ __global__ void __launch_bounds__(NT, (MAXS >= 16 ? 3 : 4)) k_gs_ctile(SellView 
           }
           a += a2;
           const double d = dv[j] * a;
-          const double r = ADD_SELF ? sv[j] + d : d;
-          const int lr = tid + j * NT;
-          xs[lr] = r;
-          __stcg(out + (i64)r0 + lr, r);
-          if (WRITE_R) rout[(i64)r0 + lr] = fma(-dg[j], d, a);
+          rs[j] = ADD_SELF ? sv[j] + d : d;
+          xs[tid + j * NT] = rs[j];
+          if (WRITE_R) acc[j] = fma(-dg[j], d, a);      // the row's new residual (acc is not needed any more)
         }
       }
       __syncthreads();
     }
     if (tr) tr[4] = gtimer();
-    // padding rows of the tile (no level): never updated, but `out` must not keep the sentinel
+    // ---- publish the tile: coalesced stores (padding rows: never updated, but `out` must not keep the sentinel), then the hint flag
 #pragma unroll
     for (int j = 0; j < NR; j++)
-      if (lv[j] == 255) {
-        const int lr = tid + j * NT;
-        __stcg(out + (i64)r0 + lr, ADD_SELF ? sv[j] : 0.0);
-        if (WRITE_R) rout[(i64)r0 + lr] = acc[j];
+      if (lv[j] <= 255) {
+        const i64 row = (i64)r0 + tid + j * NT;
+        __stcg(out + row, lv[j] == 255 ? (ADD_SELF ? sv[j] : 0.0) : rs[j]);
+        if (WRITE_R) rout[row] = acc[j];
       }
     if (tid == 0) st_relaxed_i32(p.done + t, 1);
     if (tr) {
@@ -237,7 +271,11 @@ __global__ void __launch_bounds__(NT, (MAXS >= 16 ? 3 : 4)) k_gs_ctile(SellView 
       tr[6] = (unsigned long long)smid | ((unsigned long long)blockIdx.x << 32);
       tr[7] = (unsigned long long)nlev | ((unsigned long long)ns << 16);
     }
-    __syncthreads();     // the slab and xs are reused by the next tile
+    __syncthreads();     // slab and xs are free again
+    if (NBUF == 1) { if (more && tid == 0) fetch(nxt, 0); }
+    else buf ^= 1;
+    cur = nxt;
+    cur_dep = nxt_dep;
   }
 }
 

@@ -262,4 +262,73 @@ void dev_spgemm(const DevCsr &A, const DevCsr &B, DevCsr &C, cudaStream_t st, i6
   cudaFree(tmp);
 }
 
+// ------------------------------------------------------------------------------------------------
+// T = A^T on the device (TransposeSPMImpl, src/base/linalg/utils_sparseMM.cpp:54-93: counting sort by column, every block transposed,
+// rows of T ascending).  A stable radix sort of the entries by column number keeps the row-major order of A inside every column,
+// i.e. ascending row numbers -- the same integer arrays as the reference's counting sort + per-row BubbleSort, bit for bit.
+// ------------------------------------------------------------------------------------------------
+namespace {
+__global__ void k_tr_rows(i64 nrows, const i64 *__restrict__ rp, i32 *row_of, i32 *cnt, const i32 *__restrict__ ci)
+{
+  const i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nrows) return;
+  for (i64 k = rp[i]; k < rp[i + 1]; k++) { row_of[k] = (i32)i; atomicAdd(cnt + ci[k], 1); }
+}
+__global__ void k_tr_iota(i64 n, i32 *v)
+{
+  const i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) v[i] = (i32)i;
+}
+__global__ void k_tr_widen(i64 n, const i32 *__restrict__ in, i64 *out)
+{
+  const i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = in[i];
+}
+__global__ void k_tr_fill(i64 nnz, int bh, int bw, const i32 *__restrict__ src, const i32 *__restrict__ row_of, const double *__restrict__ aval,
+                          i32 *tcol, double *tval)
+{
+  const i64 p = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= nnz) return;
+  const i64 k = src[p];
+  tcol[p] = row_of[k];
+  const int bs = bh * bw;
+  for (int r = 0; r < bh; r++)
+    for (int c = 0; c < bw; c++) tval[p * bs + c * bh + r] = aval[k * bs + r * bw + c];
+}
+}  // namespace
+
+void dev_transpose(const DevCsr &A, DevCsr &T, cudaStream_t st, i64 *launches)
+{
+  if (A.nnz >= (i64)2147483647) throw Error("dev_transpose: more than 2^31 entries");
+  T.nrows = A.ncols; T.ncols = A.nrows; T.bh = A.bw; T.bw = A.bh; T.nnz = A.nnz;
+  T.rowptr = dev_alloc<i64>(T.nrows + 1);
+  T.col = dev_alloc<i32>(T.nnz);
+  T.val = dev_alloc<double>(T.nnz * T.bs());
+  const int TB = 256;
+  auto nb = [&](i64 n) { return (unsigned)((n + TB - 1) / TB); };
+  i32 *row_of = dev_alloc<i32>(A.nnz), *cnt = dev_alloc<i32>(T.nrows + 1), *idx = dev_alloc<i32>(A.nnz), *idx2 = dev_alloc<i32>(A.nnz),
+      *keys2 = dev_alloc<i32>(A.nnz);
+  i64 *cnt64 = dev_alloc<i64>(T.nrows + 1);
+  NGB_CUDA(cudaMemsetAsync(cnt, 0, sizeof(i32) * (T.nrows + 1), st));
+  if (A.nrows) k_tr_rows<<<nb(A.nrows), TB, 0, st>>>(A.nrows, A.rowptr, row_of, cnt, A.col);
+  if (A.nnz) k_tr_iota<<<nb(A.nnz), TB, 0, st>>>(A.nnz, idx);
+  k_tr_widen<<<nb(T.nrows + 1), TB, 0, st>>>(T.nrows + 1, cnt, cnt64);
+  size_t b1 = 0, b2 = 0;
+  int end_bit = 1;
+  while (end_bit < 31 && ((i64)1 << end_bit) < std::max<i64>(A.ncols, 2)) end_bit++;
+  cub::DeviceScan::ExclusiveSum(nullptr, b1, cnt64, T.rowptr, T.nrows + 1, st);
+  cub::DeviceRadixSort::SortPairs(nullptr, b2, A.col, keys2, idx, idx2, A.nnz, 0, end_bit, st);
+  void *tmp = dev_alloc<char>(std::max(b1, b2));
+  cub::DeviceScan::ExclusiveSum(tmp, b1, cnt64, T.rowptr, T.nrows + 1, st);
+  if (A.nnz) {
+    cub::DeviceRadixSort::SortPairs(tmp, b2, A.col, keys2, idx, idx2, A.nnz, 0, end_bit, st);
+    k_tr_fill<<<nb(A.nnz), TB, 0, st>>>(A.nnz, A.bh, A.bw, idx2, row_of, A.val, T.col, T.val);
+  }
+  NGB_CUDA(cudaStreamSynchronize(st));
+  NGB_CUDA(cudaGetLastError());
+  if (launches) *launches += 6;
+  dev_free(row_of); dev_free(cnt); dev_free(idx); dev_free(idx2); dev_free(keys2); dev_free(cnt64);
+  cudaFree(tmp);
+}
+
 }  // namespace ngb
