@@ -400,6 +400,14 @@ def main():
         vms.append(pc.LastMs("apply"))
     clocks = sampler.stop()
     vcycle_ms = float(np.mean(vms))
+    # where the cycle spends its device time: one eager V-cycle with events around every phase (max over ranks per phase)
+    pc.MultPhases(rhs_d, x_d)
+    ph = pc.MultPhases(rhs_d, x_d)
+    pht = torch.tensor([ph[k] for k in pc.PHASES], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(pht, op=dist.ReduceOp.MAX)
+    phases = {k: round(float(v), 4) for k, v in zip(pc.PHASES, pht.tolist())}
+    phases["note"] = "eager launch (no CUDA graph): launch gaps are exposed, compare shares"
     vbytes = pc.VCycleBytes()
     ndof_global = ndof
     if world > 1:
@@ -509,7 +517,7 @@ def main():
                     "frac": pc.LastMs("rap_bytes") / max(pc.LastMs("rap"), 1e-9) / 1e6 / peak}, "wall_s_timed_region": wall_s,
             "vcycle_ms": vcycle_ms, "vcycle_bytes": vbytes, "vcycle_gbs": vbytes / vcycle_ms / 1e6,
             "vcycle_frac_of_peak": vbytes / vcycle_ms / 1e6 / (peak * peak_scale),
-            "kernels_level0": kern, "kernel_ms_by_level": by_level, "roofline": roof, "variant_multicolor": variant, "cpu_baseline": cpu,
+            "vcycle_phases_ms": phases, "kernels_level0": kern, "kernel_ms_by_level": by_level, "roofline": roof, "variant_multicolor": variant, "cpu_baseline": cpu,
             "e2e": {"value": ndof_global / e2e_s, "unit": "DOF/s", "h2d_bytes_per_step": 8 * ndof, "d2h_bytes_per_step": 8 * ndof,
                     "solve_s": e2e_s},
             "gpu_launches": int(launches), "clocks": clocks, "flags": extra,

@@ -134,6 +134,10 @@ int ngsamg_b200_get_sweep_order(ngsamg_b200_t *h, int level, int32_t *rank);
 int ngsamg_b200_operator_complexities(ngsamg_b200_t *h, double *occs, int cap);
 /* occs[0] of the above */
 double ngsamg_b200_operator_complexity(ngsamg_b200_t *h);
+/* one V-cycle run eagerly with CUDA events around every phase (measurement aid; reference timers: "AMGMatrix::Mult", "GSSmoother", the
+ * hybrid smoother's comm timers hybrid_base_smoother.cpp:498-574).  ms[7] = { triangular sweeps, parallel halves (U / L+D passes), transfers,
+ * halo exchanges, G products, coarse part (contracted hierarchy or coarsest solve), other }.  Collective on a distributed hierarchy. */
+int ngsamg_b200_apply_phases(ngsamg_b200_t *h, const double *b, double *x, double *ms);
 /* algorithmic bytes of one V(1,1)-cycle, SURVEY.md §8d formula B_V, from the actual level sizes */
 double ngsamg_b200_vcycle_bytes(ngsamg_b200_t *h);
 /* device milliseconds (CUDA events on the library stream) of the last apply / pcg call, setup phases */

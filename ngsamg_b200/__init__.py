@@ -184,6 +184,15 @@ class Preconditioner:
         n = self.height
         _lib.check(self._lib.ngsamg_b200_apply_add(self._h, float(s), _lib.vec(b, n, "MultAdd: b"), _lib.vec(x, n, "MultAdd: x")))
 
+    PHASES = ("tri_sweeps", "parallel_halves", "transfers", "exchange", "g_spmv", "coarse", "other")
+
+    def MultPhases(self, b, x):
+        """one V-cycle run eagerly with CUDA events around every phase -> dict of device milliseconds per phase (measurement aid)"""
+        n = self.height
+        ms = np.zeros(8)
+        _lib.check(self._lib.ngsamg_b200_apply_phases(self._h, _lib.vec(b, n, "MultPhases: b"), _lib.vec(x, n, "MultPhases: x"), _lib.ptr(ms)))
+        return dict(zip(self.PHASES, [float(v) for v in ms[:7]]))
+
     MultTrans = Mult          # amg_matrix.cpp:381-382
     MultTransAdd = MultAdd    # amg_matrix.cpp:392-393
 

@@ -152,6 +152,39 @@ NcclApi &nccl_api()
 
 }  // namespace
 
+// per-phase device timing of ONE eagerly executed V-cycle (ngsamg_b200_apply_phases): event pairs around every call of a category
+enum { PH_TRI = 0, PH_PASS, PH_TRANSFER, PH_EXCHANGE, PH_GSPMV, PH_COARSE, PH_OTHER, PH_COUNT };
+struct PhaseTimer {
+  cudaStream_t st = nullptr;
+  std::vector<cudaEvent_t> ev;
+  std::vector<int> cat;
+  size_t used = 0;
+  int depth = 0;
+  void begin(int c)
+  {
+    if (depth++ > 0) return;                       // nested scopes belong to the outermost category
+    if (used + 2 > ev.size()) { ev.resize(used + 2); cudaEventCreate(&ev[used]); cudaEventCreate(&ev[used + 1]); }
+    cat.push_back(c);
+    cudaEventRecord(ev[used], st);
+  }
+  void end()
+  {
+    if (--depth > 0) return;
+    cudaEventRecord(ev[used + 1], st);
+    used += 2;
+  }
+  void collect(double *ms)
+  {
+    for (int c = 0; c < PH_COUNT; c++) ms[c] = 0.0;
+    for (size_t k = 0; k * 2 < used; k++) {
+      float t = 0;
+      cudaEventElapsedTime(&t, ev[2 * k], ev[2 * k + 1]);
+      ms[cat[k]] += t;
+    }
+  }
+  ~PhaseTimer() { for (auto e : ev) cudaEventDestroy(e); }
+};
+
 struct Amg {
   std::string type;
   Flags flags;
@@ -190,6 +223,7 @@ struct Amg {
   i64 spmv_small_rows = 200000;   // levels with fewer rows use the warp-per-row SpMV
   int tri_regate = 1;
   int tri_split = 0;
+  PhaseTimer *pt = nullptr;          // non-null only inside ngsamg_b200_apply_phases
   unsigned long long *tri_trace = nullptr;  // debug tracing of the sync-free sweep (NGSAMG_B200_TRACE_FILE)
   int *d_err = nullptr;
   void check_watchdog();
@@ -546,6 +580,13 @@ void renumber_columns(HostBsr &P, const std::vector<i32> &perm)
 }
 
 }  // namespace
+
+struct PhaseScope {
+  PhaseTimer *t;
+  PhaseScope(Amg &a, int cat) : t(a.pt) { if (t) t->begin(cat); }
+  ~PhaseScope() { if (t) t->end(); }
+};
+#define NGB_PHASE(cat) PhaseScope phase_scope_##cat(*this, cat)
 
 Amg::~Amg()
 {
@@ -1187,6 +1228,7 @@ static std::vector<i64> scaled(const std::vector<i64> &off, int b)
 
 void Amg::dis2co(Level &L, double *v)
 {
+  NGB_PHASE(PH_EXCHANGE);
   const size_t np = L.peers.size();
   if (np == 0) { exchanges++; if (!nccl) NGB_CUDA(cudaStreamSynchronize(st)); return; }
   const i64 ng = L.g_off[np], nm = L.m_off[np];
@@ -1197,6 +1239,7 @@ void Amg::dis2co(Level &L, double *v)
 
 void Amg::co2cu(Level &L, double *v)
 {
+  NGB_PHASE(PH_EXCHANGE);
   const size_t np = L.peers.size();
   if (np == 0) { exchanges++; if (!nccl) NGB_CUDA(cudaStreamSynchronize(st)); return; }
   const i64 ng = L.g_off[np], nm = L.m_off[np];
@@ -1216,6 +1259,7 @@ void Amg::allreduce_scalars(double *h, int n)
 // its CUMULATED values back)   -- dof_contract.cpp:49-228.
 void Amg::contracted_solve(Level &L)
 {
+  NGB_PHASE(PH_COARSE);
   const int R = comm.size(), me = comm.rank();
   const i64 nl = L.n * L.b;
   if (me != 0) {
@@ -1625,6 +1669,7 @@ void Amg::tri(Level &L, bool backward, bool add_self, bool write_r, const double
 
 void Amg::tri_dispatch(Level &L, bool backward, bool add_self, bool write_r, const double *rin, const double *self, double *out, double *rout)
 {
+  NGB_PHASE(PH_TRI);
   switch (L.b) {
     case 1: tri<1>(L, backward, add_self, write_r, rin, self, out, rout); break;
     case 2: tri<2>(L, backward, add_self, write_r, rin, self, out, rout); break;
@@ -1652,6 +1697,7 @@ static void launch_spmv(cudaStream_t st, i64 small_rows, i64 npad, const Sell &a
 
 void Amg::spmv_part(Level &L, int which, const double *v, const double *y_in, double *y_out, double alpha, double beta, double *xadd)
 {
+  NGB_PHASE(PH_PASS);
   const Sell &A1 = (which == 1 || which == 3) ? L.U : L.L;
   const bool s2 = (which == 4), d = (which >= 2);
 #define NGB_SPMV(B)                                                                                                     \
@@ -1671,6 +1717,7 @@ void Amg::spmv_part(Level &L, int which, const double *v, const double *y_in, do
 
 void Amg::transfer(const Sell &S, const double *v, const double *y_in, double *y_out, double alpha, double beta, const i32 *rowmap)
 {
+  NGB_PHASE(PH_TRANSFER);
   const int key = S.bh * 10 + S.bw;
 #define NGB_TR(H, W) launch_spmv<H, W, false, false>(st, spmv_small_rows, S.nrows_pad, S, nullptr, nullptr, v, y_in, y_out, alpha, beta, nullptr, nullptr, rowmap)
   switch (key) {
@@ -1841,12 +1888,12 @@ void Amg::vcycle_record()
         transfer(L.PT, L.res, nullptr, C.rhs, 1.0, 0.0, L.d_pt_rowmap);
         continue;
       }
-      NGB_CUDA(cudaMemcpyAsync(L.res, L.rhs, sizeof(double) * L.npad * L.b, cudaMemcpyDeviceToDevice, st));
+      { NGB_PHASE(PH_OTHER); NGB_CUDA(cudaMemcpyAsync(L.res, L.rhs, sizeof(double) * L.npad * L.b, cudaMemcpyDeviceToDevice, st)); }
       dis2co(L, L.res);
       tri_dispatch(L, false, false, true, L.res, nullptr, L.x, L.res);
       spmv_part(L, 1, L.x, L.res, L.res, -1.0, 1.0, nullptr);
       co2cu(L, L.x);
-      if (L.G.nnz) transfer(L.G, L.x, L.res, L.res, -1.0, 1.0);
+      if (L.G.nnz) { NGB_PHASE(PH_GSPMV); transfer(L.G, L.x, L.res, L.res, -1.0, 1.0); }
       transfer(L.PT, L.res, nullptr, C.rhs, 1.0, 0.0, L.d_pt_rowmap);
     }
     contracted_solve(*lev[npar]);
@@ -1859,8 +1906,8 @@ void Amg::vcycle_record()
         L.result = L.x;
         continue;
       }
-      if (L.G.nnz) transfer(L.G, L.x, L.rhs, L.res, -1.0, 1.0);
-      else NGB_CUDA(cudaMemcpyAsync(L.res, L.rhs, sizeof(double) * L.npad * L.b, cudaMemcpyDeviceToDevice, st));
+      if (L.G.nnz) { NGB_PHASE(PH_GSPMV); transfer(L.G, L.x, L.rhs, L.res, -1.0, 1.0); }
+      else { NGB_PHASE(PH_OTHER); NGB_CUDA(cudaMemcpyAsync(L.res, L.rhs, sizeof(double) * L.npad * L.b, cudaMemcpyDeviceToDevice, st)); }
       dis2co(L, L.res);
       gs_rhs(L, true, L.x, L.res, L.y);
       co2cu(L, L.y);
@@ -1888,6 +1935,7 @@ void Amg::vcycle_record()
   }
   {
     Level &L = *lev[NL - 1];
+    NGB_PHASE(PH_COARSE);
     if (has_cinv) {  // x_L = A_L^-1 rhs_L   (:217-247)
       k_dense_gemv<<<nblk((i64)cinv_n * 32), TB, 0, st>>>(cinv_n, d_cinv, L.rhs, L.x);
       launches++;
@@ -2585,6 +2633,28 @@ int ngsamg_b200_apply_add(ngsamg_b200_t *h, double s, const double *b, double *x
 {
   NGB_TRY
   apply_impl(ready(h), s, b, x, true);
+  NGB_CATCH
+}
+
+// one V-cycle executed EAGERLY (no CUDA graph) with an event pair around every phase: where the cycle spends its device time.
+// ms[7] = { triangular sweeps, parallel halves of the sweeps (U / L+D passes), restriction + prolongation, halo exchanges (DIS2CO / CO2CU:
+// pack + NCCL or host staging + unpack), G products of the hybrid smoother, coarse part (contracted hierarchy incl. gather/scatter, or the
+// coarsest solve), other (vector copies) }.  Collective on a distributed hierarchy.  The sum is larger than a graph-launched cycle
+// (launch gaps are exposed); the SHARES are what it is for.
+int ngsamg_b200_apply_phases(ngsamg_b200_t *h, const double *b, double *x, double *ms)
+{
+  NGB_TRY
+  Amg &a = ready(h);
+  if (!ms) throw Error("apply_phases: ms is null");
+  PhaseTimer pt;
+  pt.st = a.st;
+  const bool ug = a.use_graph;
+  a.use_graph = false;
+  a.pt = &pt;
+  struct Restore { Amg &a; bool ug; ~Restore() { a.pt = nullptr; a.use_graph = ug; } } restore{a, ug};
+  apply_impl(a, 1.0, b, x, false);
+  NGB_CUDA(cudaStreamSynchronize(a.st));
+  pt.collect(ms);
   NGB_CATCH
 }
 

@@ -48,7 +48,7 @@ struct CTileParams {
   int pollmode;              // flavour of the polling load (ld_poll)
   int cap_slots;             // capacity of ONE shared-memory slab in SELL slots (a slot = 32 entries)
   int *err;                  // watchdog
-  unsigned long long *trace; // debug: 8 words per tile {begin, hints passed, slab landed, gathered, levels done, end, smid|cta<<32, nlev|slices<<16} (NULL = off)
+  unsigned long long *trace; // debug: 8 words per tile {begin, hints passed, slab landed, gathered, levels done, end, smid|cta<<16|nlev<<40|slices<<52, first level done} (NULL = off)
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -89,6 +89,28 @@ __device__ __forceinline__ int ld_relaxed_i32(const int *p)
 }
 __device__ __forceinline__ void st_relaxed_i32(int *p, int v) { asm volatile("st.relaxed.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
 
+// shared-memory accesses by 32-bit shared-window address: keeps the address arithmetic in plain integer registers (through C++ pointers
+// the compiler re-derives the shared window base from SR_CgaCtaId in front of every access of the level loop -- S2R on the critical path)
+__device__ __forceinline__ double lds_f64(uint32_t a)
+{
+  double v;
+  asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(a) : "memory");
+  return v;
+}
+__device__ __forceinline__ i32 lds_i32(uint32_t a)
+{
+  i32 v;
+  asm volatile("ld.shared.s32 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
+  return v;
+}
+__device__ __forceinline__ void sts_f64(uint32_t a, double v) { asm volatile("st.shared.f64 [%0], %1;" ::"r"(a), "d"(v) : "memory"); }
+__device__ __forceinline__ double ld_poll_relaxed(const double *p)
+{
+  double v;
+  asm volatile("ld.relaxed.gpu.global.f64 %0, [%1];" : "=d"(v) : "l"(p));
+  return v;
+}
+
 constexpr int CTILE_HDR = 128;   // bytes in front of the slabs: the mbarriers
 __host__ __device__ inline size_t ctile_smem_bytes(int maxs, int cap_slots, int nbuf)
 {
@@ -107,11 +129,17 @@ __global__ void __launch_bounds__(NT, (MAXS >= 16 ? 3 : 4)) k_gs_ctile(SellView 
   constexpr int NR = MAXS / NW;                 // rows per thread: tile-local rows tid, tid + NT, ...
   constexpr int CH = (NR <= 2) ? 8 : 4;         // slots gathered per round and row
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  double *xs = (double *)(smem_raw + CTILE_HDR);                      // the tile's part of `out`
-  unsigned char *slab0 = (unsigned char *)(xs + MAXS * 32);            // NBUF slabs: values, then column indices
+  // layout: [mbarriers | xs: the tile's part of `out`, MAXS*32 doubles | NBUF slabs: values, then column indices]
   const size_t slab_bytes = (size_t)p.cap_slots * 32 * 12;
-  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
-  const uint32_t bar0 = smem_u32(smem_raw);                           // mbarrier b at bar0 + 8 b
+  int tid;                                                            // (opaque as well: S2R SR_TID.X would be re-issued inside the level loop)
+  asm volatile("mov.u32 %0, %%tid.x;" : "=r"(tid));
+  const int lane = tid & 31, w = tid >> 5;
+  // the shared-window base goes through an opaque move: otherwise the compiler re-derives it from SR_CgaCtaId (S2R, slow) in front of
+  // every shared-memory access instead of keeping it in a register
+  uint32_t smem_base;
+  asm volatile("mov.u32 %0, %1;" : "=r"(smem_base) : "r"(smem_u32(smem_raw)));
+  const uint32_t bar0 = smem_base;                                    // mbarrier b at bar0 + 8 b
+  const uint32_t xs_a = smem_base + CTILE_HDR, slab_a0 = xs_a + MAXS * 32 * 8;
   if (tid == 0) {
     for (int b = 0; b < NBUF; b++) mbar_init(bar0 + 8 * b, 1);
     mbar_fence_init();
@@ -120,11 +148,11 @@ __global__ void __launch_bounds__(NT, (MAXS >= 16 ? 3 : 4)) k_gs_ctile(SellView 
   auto tile_of = [&](i32 q) { return p.backward ? (p.ntiles - 1 - q) : q; };
   auto fetch = [&](const CTileMeta &m, int buf) {                     // one thread: both bulk copies of a tile's slab
     if (m.nslots <= 0) return;
-    unsigned char *sl = slab0 + (size_t)buf * slab_bytes;
+    const uint32_t sl = slab_a0 + (uint32_t)buf * (uint32_t)slab_bytes;
     const uint32_t bar = bar0 + 8 * buf;
     mbar_expect_tx(bar, (uint32_t)m.nslots * 32u * 12u);
-    bulk_g2s(smem_u32(sl), T.val + m.base * 32, (uint32_t)m.nslots * 256u, bar);
-    bulk_g2s(smem_u32(sl + (size_t)p.cap_slots * 256), T.col + m.base * 32, (uint32_t)m.nslots * 128u, bar);
+    bulk_g2s(sl, T.val + m.base * 32, (uint32_t)m.nslots * 256u, bar);
+    bulk_g2s(sl + (uint32_t)p.cap_slots * 256u, T.col + m.base * 32, (uint32_t)m.nslots * 128u, bar);
   };
   const CTileMeta none{0, 0, 0, 0, 0, 0, 0};
   uint32_t phases = 0;                                                // bit b: parity the next wait on mbarrier b expects
@@ -147,8 +175,8 @@ __global__ void __launch_bounds__(NT, (MAXS >= 16 ? 3 : 4)) k_gs_ctile(SellView 
     const int ns = cur.ns;
     const i32 r0 = s0 * 32;
     const unsigned nrow = (unsigned)ns * 32u;
-    const double *vals_s = (const double *)(slab0 + (size_t)buf * slab_bytes);
-    const i32 *cols_s = (const i32 *)(slab0 + (size_t)buf * slab_bytes + (size_t)p.cap_slots * 256);
+    const uint32_t vals_a = slab_a0 + (uint32_t)buf * (uint32_t)slab_bytes;      // values of the slab, then its column indices
+    const uint32_t cols_a = vals_a + (uint32_t)p.cap_slots * 256u;
     // ---- per-row data that does not depend on `out`
     double acc[NR], dv[NR], sv[NR], dg[NR], rs[NR];
     int lv[NR], sb[NR], wd[NR];
@@ -193,8 +221,8 @@ __global__ void __launch_bounds__(NT, (MAXS >= 16 ? 3 : 4)) k_gs_ctile(SellView 
 #pragma unroll
         for (int e = 0; e < CH; e++) {
           const int k = k0 + e;
-          const i32 c = (k < wd[j]) ? cols_s[(sb[j] + k) * 32 + lane] : -1;
-          xv[j][e] = (c >= 0 && (unsigned)(c - r0) >= nrow) ? ld_poll(out + c, p.pollmode) : 0.0;   // in-tile columns: shared memory, below
+          const i32 c = (k < wd[j]) ? lds_i32(cols_a + (uint32_t)((sb[j] + k) * 32 + lane) * 4u) : -1;
+          xv[j][e] = (c >= 0 && (unsigned)(c - r0) >= nrow) ? ld_poll_relaxed(out + c) : 0.0;   // in-tile columns: shared memory, below
         }
 #pragma unroll
       for (int j = 0; j < NR; j++)
@@ -202,15 +230,16 @@ __global__ void __launch_bounds__(NT, (MAXS >= 16 ? 3 : 4)) k_gs_ctile(SellView 
         for (int e = 0; e < CH; e++) {
           const int k = k0 + e;
           if (k < wd[j]) {
-            const i32 c = cols_s[(sb[j] + k) * 32 + lane];
+            const uint32_t slot = (uint32_t)((sb[j] + k) * 32 + lane);
+            const i32 c = lds_i32(cols_a + slot * 4u);
             if (c >= 0 && (unsigned)(c - r0) >= nrow) {
               unsigned spins = 0;
               while (is_sentinel(xv[j][e])) {
                 if (p.repoll_ns) __nanosleep(p.repoll_ns);
-                xv[j][e] = ld_poll(out + c, p.pollmode);
+                xv[j][e] = ld_poll_relaxed(out + c);
                 if (spin_fail(spins, p.err)) break;
               }
-              acc[j] = fma(-vals_s[(sb[j] + k) * 32 + lane], xv[j][e], acc[j]);
+              acc[j] = fma(-lds_f64(vals_a + slot * 8u), xv[j][e], acc[j]);
             }
           }
         }
@@ -234,13 +263,14 @@ __global__ void __launch_bounds__(NT, (MAXS >= 16 ? 3 : 4)) k_gs_ctile(SellView 
 #pragma unroll
             for (int e = 0; e < 8; e++) {
               const bool in = k0 + e < wd[j];
-              c[e] = in ? cols_s[(sb[j] + k0 + e) * 32 + lane] : -1;
-              v[e] = in ? vals_s[(sb[j] + k0 + e) * 32 + lane] : 0.0;
+              const uint32_t slot = (uint32_t)((sb[j] + k0 + e) * 32 + lane);
+              c[e] = in ? lds_i32(cols_a + slot * 4u) : -1;
+              v[e] = in ? lds_f64(vals_a + slot * 8u) : 0.0;
             }
 #pragma unroll
             for (int e = 0; e < 8; e++) {
               const unsigned lc = (unsigned)(c[e] - r0);
-              x[e] = (c[e] >= 0 && lc < nrow) ? xs[lc] : 0.0;
+              x[e] = (c[e] >= 0 && lc < nrow) ? lds_f64(xs_a + lc * 8u) : 0.0;
             }
 #pragma unroll
             for (int e = 0; e < 8; e += 2) { a = fma(-v[e], x[e], a); a2 = fma(-v[e + 1], x[e + 1], a2); }
@@ -248,11 +278,12 @@ __global__ void __launch_bounds__(NT, (MAXS >= 16 ? 3 : 4)) k_gs_ctile(SellView 
           a += a2;
           const double d = dv[j] * a;
           rs[j] = ADD_SELF ? sv[j] + d : d;
-          xs[tid + j * NT] = rs[j];
+          sts_f64(xs_a + (uint32_t)(tid + j * NT) * 8u, rs[j]);
           if (WRITE_R) acc[j] = fma(-dg[j], d, a);      // the row's new residual (acc is not needed any more)
         }
       }
       __syncthreads();
+      if (tr && it == 0) tr[7] = gtimer();              // the first barrier also absorbs the gather skew between the warps
     }
     if (tr) tr[4] = gtimer();
     // ---- publish the tile: coalesced stores (padding rows: never updated, but `out` must not keep the sentinel), then the hint flag
@@ -268,8 +299,7 @@ __global__ void __launch_bounds__(NT, (MAXS >= 16 ? 3 : 4)) k_gs_ctile(SellView 
       unsigned smid;
       asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
       tr[5] = gtimer();
-      tr[6] = (unsigned long long)smid | ((unsigned long long)blockIdx.x << 32);
-      tr[7] = (unsigned long long)nlev | ((unsigned long long)ns << 16);
+      tr[6] = (unsigned long long)smid | ((unsigned long long)blockIdx.x << 16) | ((unsigned long long)nlev << 40) | ((unsigned long long)ns << 52);
     }
     __syncthreads();     // slab and xs are free again
     if (NBUF == 1) { if (more && tid == 0) fetch(nxt, 0); }

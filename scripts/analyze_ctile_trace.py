@@ -20,10 +20,11 @@ def main(fn, backward=False):
     t = tr[:, :6].astype(np.int64)
     t0 = t[:, 0].min()
     t = (t - t0) / 1e3                                       # us
-    smid = (tr[:, 6] & np.uint64(0xffffffff)).astype(np.int64)
-    cta = (tr[:, 6] >> np.uint64(32)).astype(np.int64)
-    nlev = (tr[:, 7] & np.uint64(0xffff)).astype(np.int64)
-    ns = (tr[:, 7] >> np.uint64(16)).astype(np.int64)
+    smid = (tr[:, 6] & np.uint64(0xffff)).astype(np.int64)
+    cta = ((tr[:, 6] >> np.uint64(16)) & np.uint64(0xffffff)).astype(np.int64)
+    nlev = ((tr[:, 6] >> np.uint64(40)) & np.uint64(0xfff)).astype(np.int64)
+    ns = (tr[:, 6] >> np.uint64(52)).astype(np.int64)
+    t_first = (tr[:, 7].astype(np.int64) - t0) / 1e3
     span = t[:, 5].max()
     ph = {"hint wait": t[:, 1] - t[:, 0], "slab wait": t[:, 2] - t[:, 1], "gather": t[:, 3] - t[:, 2], "levels": t[:, 4] - t[:, 3],
           "tail": t[:, 5] - t[:, 4], "whole tile": t[:, 5] - t[:, 0]}
@@ -31,6 +32,8 @@ def main(fn, backward=False):
     for k, v in ph.items():
         print("  %-10s mean %7.2f  median %7.2f  p90 %7.2f  max %8.2f us   (sum/CTA-time %.2f)" % (k, v.mean(), np.median(v), np.percentile(v, 90), v.max(),
                                                                                                  v.sum() / (span * len(np.unique(cta)))))
+    ok = nlev > 1
+    print("  first level incl. gather skew: mean %.2f us; later levels: %.3f us each" % ((t_first - t[:, 3])[ok].mean(), ((t[:, 4] - t_first)[ok] / (nlev[ok] - 1)).mean()))
     print("  per local level: %.3f us (levels / nlev, mean nlev %.1f, mean slices %.1f)" % ((ph["levels"] / np.maximum(nlev, 1)).mean(), nlev.mean(), ns.mean()))
     # tile DAG levels and the dependency slack: when did the last dependency finish vs when did the tile pass its hint wait / gather
     lvl = np.zeros(nt, np.int64)
