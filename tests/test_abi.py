@@ -223,3 +223,40 @@ def test_malformed_matrices_are_rejected():
     bad = ng.SparseMatrix(2, 2, 1, 1, np.array([0, 3, 2], np.int64), np.array([0, 1, 0, 1], np.int32), np.ones(4))
     with pytest.raises(Exception):
         ng.coarsen(bad, None)
+
+
+def _build_adapter_test(tmp_path):
+    import subprocess
+    exe = os.path.join(str(tmp_path), "test_adapter")
+    libdir = os.path.dirname(_lib.LIB_PATH)
+    subprocess.check_call(["g++", "-std=c++17", "-O1", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), "-I", os.path.join(ROOT, "tests", "cpp"),
+                           os.path.join(ROOT, "tests", "cpp", "test_adapter.cpp"), "-o", exe, "-L", libdir, "-lngsamg_b200", "-Wl,-rpath," + libdir])
+    return exe
+
+
+def test_ngsolve_adapter_compiles_and_registers_the_reference_names(tmp_path):
+    """include/ngsamg_b200_ngsolve.hpp -- the reference-side adapter (B200AMGPC : ngcomp::Preconditioner, B200AMGMatrix : BaseMatrix,
+    RegisterPreconditioner) -- compiles against the NGSolve stand-in, links against the C ABI, and its static initialisers put
+    "NgsAMG.h1_scal" / "NgsAMG.elast_3d" (amg_register.hpp:79-98, elasticity.hpp:104-140) into the preconditioner registry"""
+    import subprocess
+    exe = _build_adapter_test(tmp_path)
+    r = subprocess.run([exe, "--list"], capture_output=True, text=True, timeout=60)
+    assert r.returncode == 0, (r.stdout, r.stderr)
+    assert set(r.stdout.split()) == {"NgsAMG.h1_scal", "NgsAMG.elast_3d"}
+
+
+@pytest.mark.skipif(_has_gpu(), reason="checks the no-device failure mode of the adapter")
+def test_ngsolve_adapter_fails_loudly_without_a_device(tmp_path):
+    import subprocess
+    r = subprocess.run([_build_adapter_test(tmp_path)], capture_output=True, text=True, timeout=60)
+    assert r.returncode == 2 and "no CUDA device" in r.stdout, (r.returncode, r.stdout, r.stderr)
+
+
+@pytest.mark.gpu
+def test_ngsolve_adapter_on_the_device(tmp_path):
+    """the adapter driven like NGSolve drives a registered preconditioner (registry lookup, InitLevel, FinalizeLevel, Mult / MultAdd /
+    MultTrans through BaseMatrix, PCG): identical to direct C-ABI calls, PCG converges, wrong entry type throws ngcore::Exception"""
+    import subprocess
+    r = subprocess.run([_build_adapter_test(tmp_path)], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, (r.returncode, r.stdout, r.stderr)
+    assert "adapter: levels=" in r.stdout
