@@ -210,38 +210,44 @@ __global__ void __launch_bounds__(NT, (MAXS >= 16 ? 3 : 4)) k_gs_ctile(SellView 
     if (cur.nslots > 0) { mbar_wait(bar0 + 8 * buf, (phases >> buf) & 1u); phases ^= 1u << buf; }
     __syncthreads();
     if (tr) tr[2] = gtimer();
-    // ---- couplings to rows of other tiles: poll the data itself (sentinel); all polls of a round of CH slots per owned row are in flight together
+    // ---- couplings to rows of other tiles: poll the data itself (sentinel).  All polls of a round (CH slots of every owned row) are in
+    // flight together; a round with a straggler is simply polled again as a whole.  (Kept compact on purpose: three CTAs in different
+    // phases share an SM, and a kernel that does not fit the instruction cache pays for it inside the latency-critical level loop.)
     int maxw = 0;
 #pragma unroll
     for (int j = 0; j < NR; j++) maxw = max(maxw, wd[j]);
+#pragma unroll 1
     for (int k0 = 0; k0 < maxw; k0 += CH) {
       double xv[NR][CH];
+      unsigned spins = 0;
+      bool missing;
+#pragma unroll 1
+      do {
+        missing = false;
 #pragma unroll
-      for (int j = 0; j < NR; j++)
+        for (int j = 0; j < NR; j++)
 #pragma unroll
-        for (int e = 0; e < CH; e++) {
-          const int k = k0 + e;
-          const i32 c = (k < wd[j]) ? lds_i32(cols_a + (uint32_t)((sb[j] + k) * 32 + lane) * 4u) : -1;
-          xv[j][e] = (c >= 0 && (unsigned)(c - r0) >= nrow) ? ld_poll_relaxed(out + c) : 0.0;   // in-tile columns: shared memory, below
-        }
-#pragma unroll
-      for (int j = 0; j < NR; j++)
-#pragma unroll
-        for (int e = 0; e < CH; e++) {
-          const int k = k0 + e;
-          if (k < wd[j]) {
-            const uint32_t slot = (uint32_t)((sb[j] + k) * 32 + lane);
-            const i32 c = lds_i32(cols_a + slot * 4u);
-            if (c >= 0 && (unsigned)(c - r0) >= nrow) {
-              unsigned spins = 0;
-              while (is_sentinel(xv[j][e])) {
-                if (p.repoll_ns) __nanosleep(p.repoll_ns);
-                xv[j][e] = ld_poll_relaxed(out + c);
-                if (spin_fail(spins, p.err)) break;
-              }
-              acc[j] = fma(-lds_f64(vals_a + slot * 8u), xv[j][e], acc[j]);
-            }
+          for (int e = 0; e < CH; e++) {
+            const int k = k0 + e;
+            const i32 c = (k < wd[j]) ? lds_i32(cols_a + (uint32_t)((sb[j] + k) * 32 + lane) * 4u) : -1;
+            xv[j][e] = (c >= 0 && (unsigned)(c - r0) >= nrow) ? ld_poll_relaxed(out + c) : 0.0;   // in-tile columns: shared memory, below
           }
+#pragma unroll
+        for (int j = 0; j < NR; j++)
+#pragma unroll
+          for (int e = 0; e < CH; e++) missing |= is_sentinel(xv[j][e]);
+        if (missing) {
+          if (p.repoll_ns) __nanosleep(p.repoll_ns);
+          if (spin_fail(spins, p.err)) break;
+        }
+      } while (missing);
+#pragma unroll
+      for (int j = 0; j < NR; j++)
+#pragma unroll
+        for (int e = 0; e < CH; e++) {
+          const int k = k0 + e;
+          // xv == 0 for in-tile / padding slots; the value slot is read only where the row has one
+          if (k < wd[j]) acc[j] = fma(-lds_f64(vals_a + (uint32_t)((sb[j] + k) * 32 + lane) * 8u), xv[j][e], acc[j]);
         }
     }
     if (tr) tr[3] = gtimer();
