@@ -99,7 +99,7 @@ struct Level {
   i64 *d_tile_pred_ptr = nullptr, *d_tile_succ_ptr = nullptr;
   int *d_tile_done = nullptr;
   // CTA-per-tile sweep (kernels_ctile.cuh; tile capacity >= 128 rows): slab capacity, launch geometry
-  std::vector<i32> h_tile_slice, h_tile_nlev;
+  std::vector<i32> h_tile_slice, h_tile_nlev, h_tile_nreal;   // nreal: rows of the tile that are not padding
   std::vector<i64> h_pred_ptr, h_succ_ptr;
   CTileMeta *d_meta_fwd = nullptr, *d_meta_bwd = nullptr;
   int tile_nbuf = 1;
@@ -256,6 +256,7 @@ struct Amg {
   void finalize();
   void build_level_layout(Level &L, const DevCsr &dA);
   void prepare_ctile(Level &L);
+  bool setup_tiles(Level &L, int l, const HostBsr &A);
   void build_transfer_layout(Level &F, Level &C);
   void build_coarse_inverse(Level &L);
   void alloc_vectors(Level &L);
@@ -759,6 +760,51 @@ static CTileKernel ctile_kernel(int maxs, int nbuf, bool add_self)
   if (nbuf == 1) return add_self ? (CTileKernel)k_gs_ctile<CTILE_NT, 16, 1, true, false> : (CTileKernel)k_gs_ctile<CTILE_NT, 16, 1, false, true>;
   return add_self ? (CTileKernel)k_gs_ctile<CTILE_NT, 16, 2, true, false> : (CTileKernel)k_gs_ctile<CTILE_NT, 16, 2, false, true>;
 }
+// Two-level (tile) schedule of the triangular sweeps of a level (tiles.hpp): only for scalar levels that are big and whose sweep DAG is
+// deep -- a colour-major coarse level has a shallower DAG than any tiling of it.  A = the matrix the sweep runs on (the level matrix, or
+// the master-master block M of a distributed level with the hybrid stage order in L.sweep_rank).
+bool Amg::setup_tiles(Level &L, int l, const HostBsr &A)
+{
+  const bool verbose = flags.str("log_level", "none") != "none";
+  if (L.b != 1 || !flags.flag("b200_tile_sweep", false) || L.n < (i64)flags.num("b200_tile_min_rows", 200000)) return false;
+  if (sweep_depth(A, L.mask(), L.sweep_rank) < (int)flags.num("b200_tile_min_depth", 150)) return false;
+  TileSchedule ts;
+  const int cap = (int)flags.num("b200_tile_rows", 64);
+  if (cap != 32 && cap != 64 && cap != 256 && cap != 512)
+    throw Error("ngs_amg_b200_tile_rows must be 32 or 64 (one warp per tile) or 256 or 512 (one CTA per tile)");
+  int rounds = 5;
+  while ((1 << rounds) < cap) rounds++;
+  // matrices numbered like a structured grid get near-cubic boxes as cluster hints (ideal tile DAG); everything else the pairwise clustering
+  std::vector<i32> hint;
+  i64 gd[3] = {0, 0, 0};
+  const bool grid = flags.flag("b200_tile_grid_hint", true) && grid_box_hint(A, L.mask(), cap, hint, gd);
+  if (verbose && grid) std::fprintf(stderr, "[ngsamg_b200] level %d: numbered like a %lld x %lld x %lld grid: box-shaped tiles\n", l, (long long)gd[0], (long long)gd[1], (long long)gd[2]);
+  build_tile_schedule(A, L.mask(), L.sweep_rank, (int)flags.num("b200_tile_rounds", rounds), cap, ts, grid ? &hint : nullptr);
+  if (!ts.ok) return false;
+  L.perm = ts.perm; L.npad = ts.npad; L.nonfree_pad = ts.nonfree_pad; L.depth = ts.tile_depth;
+  L.level_start.clear();
+  L.ntiles = ts.ntiles; L.tile_maxs = cap / 32;   // 1, 2: warp per tile; 8, 16: CTA per tile
+  L.d_tile_slice = upload_vec(ts.tile_slice, st); L.d_tile_nlev = upload_vec(ts.tile_nlev, st);
+  L.d_row_lvl = upload_vec(ts.row_lvl, st);
+  L.d_tile_pred_ptr = upload_vec(ts.pred_ptr, st); L.d_tile_pred = upload_vec(ts.pred, st);
+  L.d_tile_succ_ptr = upload_vec(ts.succ_ptr, st); L.d_tile_succ = upload_vec(ts.succ, st);
+  L.d_tile_done = dev_alloc<int>((size_t)ts.ntiles);
+  L.h_tile_slice = ts.tile_slice; L.h_tile_nlev = ts.tile_nlev; L.h_pred_ptr = ts.pred_ptr; L.h_succ_ptr = ts.succ_ptr;
+  L.h_tile_nreal.assign(ts.ntiles, 0);
+  parallel_for(ts.ntiles, [&](i64 lo, i64 hi) {
+    for (i64 t = lo; t < hi; t++) {
+      i32 c = 0;
+      for (i64 r = (i64)ts.tile_slice[t] * 32; r < (i64)ts.tile_slice[t + 1] * 32; r++) c += ts.row_lvl[r] != 255;
+      L.h_tile_nreal[t] = c;
+    }
+  }, 1024);
+  L.tile_nbuf = (int)flags.num("b200_tile_nbuf", 1);
+  if (L.tile_nbuf != 1 && L.tile_nbuf != 2) throw Error("ngs_amg_b200_tile_nbuf must be 1 or 2");
+  L.tiled = true;
+  if (verbose) std::fprintf(stderr, "[ngsamg_b200] level %d: tile schedule: %lld tiles, tile DAG depth %d, <= %d local levels\n", l, (long long)ts.ntiles, ts.tile_depth, ts.max_local_levels);
+  return true;
+}
+
 // CTA-per-tile sweep: slab capacity (largest tile of L and U, in SELL slots), shared-memory opt-in, resident grid
 void Amg::prepare_ctile(Level &L)
 {
@@ -777,7 +823,7 @@ void Amg::prepare_ctile(Level &L)
       const i64 slots = sp[s1] - sp[s0];
       cap = std::max(cap, slots);
       if (dp[t] >= (i64)2147483647) throw Error("tile sweep: wait lists too long");
-      meta[dir][t] = CTileMeta{sp[s0], s0, s1 - s0, (i32)slots, L.h_tile_nlev[t], (i32)dp[t], (i32)(dp[t + 1] - dp[t])};
+      meta[dir][t] = CTileMeta{sp[s0], s0, s1 - s0, (i32)slots, L.h_tile_nlev[t] | (L.h_tile_nreal[t] << 16), (i32)dp[t], (i32)(dp[t + 1] - dp[t])};
     }
   }
   L.d_meta_fwd = upload_vec(meta[0], st);
@@ -1055,38 +1101,8 @@ void Amg::finalize()
         int ncol = 0;
         greedy_coloring_perm(L.hA, L.sweep_rank, ncol);
       }
-      // EXPERIMENTAL (off by default): tile-major numbering + two-level schedule for big scalar levels
-      // (only where the row DAG is deep: a colour-major coarse level has a shallower DAG than any tiling of it)
-      if (!coarsest && L.b == 1 && flags.flag("b200_tile_sweep", false) && L.n >= (i64)flags.num("b200_tile_min_rows", 200000) &&
-          sweep_depth(L.hA, L.mask(), L.sweep_rank) >= (int)flags.num("b200_tile_min_depth", 150)) {
-        TileSchedule ts;
-        const int cap = (int)flags.num("b200_tile_rows", 64);     // 64-row tiles (6 pairing rounds): about half the tile-DAG depth of 32-row tiles
-        if (cap != 32 && cap != 64 && cap != 256 && cap != 512)
-          throw Error("ngs_amg_b200_tile_rows must be 32 or 64 (one warp per tile) or 256 or 512 (one CTA per tile)");
-        int rounds = 5;
-        while ((1 << rounds) < cap) rounds++;
-        // matrices numbered like a structured grid get near-cubic boxes as cluster hints (ideal tile DAG); everything else the pairwise clustering
-        std::vector<i32> hint;
-        i64 gd[3] = {0, 0, 0};
-        const bool grid = flags.flag("b200_tile_grid_hint", true) && grid_box_hint(L.hA, L.mask(), cap, hint, gd);
-        if (verbose && grid) std::fprintf(stderr, "[ngsamg_b200] level %d: numbered like a %lld x %lld x %lld grid: box-shaped tiles\n", l, (long long)gd[0], (long long)gd[1], (long long)gd[2]);
-        build_tile_schedule(L.hA, L.mask(), L.sweep_rank, (int)flags.num("b200_tile_rounds", rounds), cap, ts, grid ? &hint : nullptr);
-        if (ts.ok) {
-          L.perm = ts.perm; L.npad = ts.npad; L.nonfree_pad = ts.nonfree_pad; L.depth = ts.tile_depth;
-          L.level_start.clear();
-          L.ntiles = ts.ntiles; L.tile_maxs = cap / 32;   // 1, 2: warp per tile; 8, 16: CTA per tile
-          L.d_tile_slice = upload_vec(ts.tile_slice, st); L.d_tile_nlev = upload_vec(ts.tile_nlev, st);
-          L.d_row_lvl = upload_vec(ts.row_lvl, st);
-          L.d_tile_pred_ptr = upload_vec(ts.pred_ptr, st); L.d_tile_pred = upload_vec(ts.pred, st);
-          L.d_tile_succ_ptr = upload_vec(ts.succ_ptr, st); L.d_tile_succ = upload_vec(ts.succ, st);
-          L.d_tile_done = dev_alloc<int>((size_t)ts.ntiles);
-          L.h_tile_slice = ts.tile_slice; L.h_tile_nlev = ts.tile_nlev; L.h_pred_ptr = ts.pred_ptr; L.h_succ_ptr = ts.succ_ptr;
-          L.tile_nbuf = (int)flags.num("b200_tile_nbuf", 1);
-          if (L.tile_nbuf != 1 && L.tile_nbuf != 2) throw Error("ngs_amg_b200_tile_nbuf must be 1 or 2");
-          L.tiled = true;
-          if (verbose) std::fprintf(stderr, "[ngsamg_b200] level %d: tile schedule: %lld tiles, tile DAG depth %d, <= %d local levels\n", l, (long long)ts.ntiles, ts.tile_depth, ts.max_local_levels);
-        }
-      }
+      // tile-major numbering + two-level schedule for big scalar levels with a deep sweep DAG (setup_tiles)
+      if (!coarsest) setup_tiles(L, l, L.hA);
       if (!L.tiled) level_schedule(L.hA, L.mask(), !coarsest, L, st);
       L.d_err = d_err;
       host_s += tick(h0);
@@ -1493,7 +1509,7 @@ void Amg::finalize_parallel()
     }
     {
       auto h1 = std::chrono::steady_clock::now();
-      level_schedule(L.hM, L.gs_mask, true, L, st);
+      if (!setup_tiles(L, l, L.hM)) level_schedule(L.hM, L.gs_mask, true, L, st);
       L.d_err = d_err;
       host_s += tick(h1);
       if (verbose) std::fprintf(stderr, "[ngsamg_b200 r%d] level %d: hybrid level, nnz(M)=%lld nnz(G)=%lld, sweep depth %d\n", me, l, (long long)L.nnz_m, (long long)L.nnz_g, L.depth);
@@ -1502,6 +1518,7 @@ void Amg::finalize_parallel()
       DevCsr dM;
       dev_csr_upload(L.hM, dM, st);
       build_level_layout(L, dM);
+      if (L.tiled && L.tile_maxs > 2) prepare_ctile(L);
       dev_csr_free(dM);
     }
     build_plain_sell(L.hG, L.d_perm, L.d_perm, L.npad, L.G, st, &launches);
@@ -3109,12 +3126,12 @@ int ngsamg_b200_profile_kernel(ngsamg_b200_t *h, int level, int which, int reps,
     if ((which == 0 || which == 3) && L.tiled && L.tile_maxs > 2) {
       // CTA-per-tile sweep: 8 words per tile + the tile DAG (predecessor lists) for the offline analysis (scripts/analyze_ctile_trace.py)
       const i64 nt = L.ntiles;
-      a.tri_trace = dev_alloc<unsigned long long>(nt * 8);
-      NGB_CUDA(cudaMemsetAsync(a.tri_trace, 0, sizeof(unsigned long long) * nt * 8, a.st));
+      a.tri_trace = dev_alloc<unsigned long long>(nt * 16);
+      NGB_CUDA(cudaMemsetAsync(a.tri_trace, 0, sizeof(unsigned long long) * nt * 16, a.st));
       run();
       NGB_CUDA(cudaStreamSynchronize(a.st));
-      std::vector<unsigned long long> ht(nt * 8);
-      NGB_CUDA(cudaMemcpy(ht.data(), a.tri_trace, sizeof(unsigned long long) * nt * 8, cudaMemcpyDeviceToHost));
+      std::vector<unsigned long long> ht(nt * 16);
+      NGB_CUDA(cudaMemcpy(ht.data(), a.tri_trace, sizeof(unsigned long long) * nt * 16, cudaMemcpyDeviceToHost));
       dev_free(a.tri_trace);
       a.tri_trace = nullptr;
       std::vector<i64> pp(nt + 1);

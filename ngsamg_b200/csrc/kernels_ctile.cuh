@@ -31,7 +31,7 @@ struct __align__(16) CTileMeta {
   i32 s0;        // first 32-row slice of the tile
   i32 ns;        // slices
   i32 nslots;    // slots of the slab
-  i32 nlev;      // tile-local dependency levels
+  i32 nlev;      // tile-local dependency levels (low 16 bits) | rows of the tile that are not padding << 16
   i32 d0;        // first entry of the tile's wait list in `dep`
   i32 nd;        // tiles to wait for
 };
@@ -111,12 +111,31 @@ __device__ __forceinline__ double ld_poll_relaxed(const double *p)
   return v;
 }
 
-constexpr int CTILE_HDR = 128;   // bytes in front of the slabs: the mbarriers
+__device__ __forceinline__ unsigned lds_u16(uint32_t a)
+{
+  unsigned short v;
+  asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(a) : "memory");
+  return v;
+}
+__device__ __forceinline__ void sts_u16(uint32_t a, unsigned v) { asm volatile("st.shared.u16 [%0], %1;" ::"r"(a), "h"((unsigned short)v) : "memory"); }
+__device__ __forceinline__ void sts_i32(uint32_t a, i32 v) { asm volatile("st.shared.s32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
+
+// shared memory of a CTA: [ header | level starts | slice slot offsets | xs | acc | dinv | aux | NBUF slabs ]
+//   header      : the mbarriers (one per slab)
+//   level starts: first tile-local row of every tile-local level (+ end), u16
+//   slot offsets: first slot of every slice of the tile inside the slab (+ end), i32
+//   xs          : the tile's part of `out`;  acc: per row  rin - (couplings to other tiles);  dinv;  aux: self (ADD_SELF) or diag (WRITE_R)
+constexpr int CTILE_HDR = 128;
+constexpr int CTILE_MAXLEV = 256;                                   // tile-local levels fit a byte (tiles.cpp)
+__host__ __device__ inline size_t ctile_fixed_bytes(int maxs) { return (size_t)CTILE_HDR + (CTILE_MAXLEV + 8) * 2 + (size_t)(maxs + 8) * 4 + (size_t)4 * maxs * 32 * 8; }
 __host__ __device__ inline size_t ctile_smem_bytes(int maxs, int cap_slots, int nbuf)
 {
-  return (size_t)CTILE_HDR + (size_t)maxs * 32 * 8 + (size_t)nbuf * (size_t)cap_slots * 32 * 12;
+  return ((ctile_fixed_bytes(maxs) + 127) / 128) * 128 + (size_t)nbuf * (size_t)cap_slots * 32 * 12;
 }
 
+// One CTA per tile.  All warps fetch, wait and fold the couplings to other tiles; then ONE warp (the solver) walks the tile-local levels
+// with __syncwarp between them -- a CTA-wide barrier per level costs ~0.35 us with one late warp (measured, scripts/micro/), a warp walking
+// the levels alone ~0.1-0.15 us -- and all warps publish the result.
 // NBUF = slabs in shared memory: 1 = the next tile's slab is fetched when the current tile is finished, 2 = while the current tile is
 // being swept (HBM latency never exposed; twice the shared memory).
 template <int NT, int MAXS, int NBUF, bool ADD_SELF, bool WRITE_R>
@@ -129,9 +148,8 @@ __global__ void __launch_bounds__(NT, (MAXS >= 16 ? 3 : 4)) k_gs_ctile(SellView 
   constexpr int NR = MAXS / NW;                 // rows per thread: tile-local rows tid, tid + NT, ...
   constexpr int CH = (NR <= 2) ? 8 : 4;         // slots gathered per round and row
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  // layout: [mbarriers | xs: the tile's part of `out`, MAXS*32 doubles | NBUF slabs: values, then column indices]
   const size_t slab_bytes = (size_t)p.cap_slots * 32 * 12;
-  int tid;                                                            // (opaque as well: S2R SR_TID.X would be re-issued inside the level loop)
+  int tid;                                                            // (opaque: S2R SR_TID.X would be re-issued inside the loops)
   asm volatile("mov.u32 %0, %%tid.x;" : "=r"(tid));
   const int lane = tid & 31, w = tid >> 5;
   // the shared-window base goes through an opaque move: otherwise the compiler re-derives it from SR_CgaCtaId (S2R, slow) in front of
@@ -139,7 +157,11 @@ __global__ void __launch_bounds__(NT, (MAXS >= 16 ? 3 : 4)) k_gs_ctile(SellView 
   uint32_t smem_base;
   asm volatile("mov.u32 %0, %1;" : "=r"(smem_base) : "r"(smem_u32(smem_raw)));
   const uint32_t bar0 = smem_base;                                    // mbarrier b at bar0 + 8 b
-  const uint32_t xs_a = smem_base + CTILE_HDR, slab_a0 = xs_a + MAXS * 32 * 8;
+  const uint32_t ls_a = smem_base + CTILE_HDR;                        // level starts
+  const uint32_t so_a = ls_a + (CTILE_MAXLEV + 8) * 2;                // slice slot offsets
+  const uint32_t xs_a = so_a + (MAXS + 8) * 4;
+  const uint32_t acc_a = xs_a + MAXS * 32 * 8, dv_a = acc_a + MAXS * 32 * 8, aux_a = dv_a + MAXS * 32 * 8;
+  const uint32_t slab_a0 = smem_base + (uint32_t)(((ctile_fixed_bytes(MAXS) + 127) / 128) * 128);
   if (tid == 0) {
     for (int b = 0; b < NBUF; b++) mbar_init(bar0 + 8 * b, 1);
     mbar_fence_init();
@@ -158,14 +180,14 @@ __global__ void __launch_bounds__(NT, (MAXS >= 16 ? 3 : 4)) k_gs_ctile(SellView 
   uint32_t phases = 0;                                                // bit b: parity the next wait on mbarrier b expects
   i32 q = blockIdx.x;
   if (q >= p.ntiles) return;
-  // software pipeline: the record of the NEXT tile (and the first tile it waits for) is loaded while the current tile is swept
+  // software pipeline: the record of the NEXT tile (and the first tiles it waits for) is loaded while the current tile is swept
   CTileMeta cur = p.meta[tile_of(q)];
   i32 cur_dep = (tid < cur.nd) ? p.dep[cur.d0 + tid] : -1;
   if (tid == 0) fetch(cur, 0);
   int buf = 0;
   for (; q < p.ntiles; q += gridDim.x) {
     const i32 t = tile_of(q);
-    unsigned long long *tr = (p.trace && tid == 0) ? p.trace + (size_t)t * 8 : nullptr;
+    unsigned long long *tr = (p.trace && tid == 0) ? p.trace + (size_t)t * 16 : nullptr;
     if (tr) tr[0] = gtimer();
     const i32 qn = q + (i32)gridDim.x;
     const bool more = qn < p.ntiles;
@@ -175,35 +197,40 @@ __global__ void __launch_bounds__(NT, (MAXS >= 16 ? 3 : 4)) k_gs_ctile(SellView 
     const int ns = cur.ns;
     const i32 r0 = s0 * 32;
     const unsigned nrow = (unsigned)ns * 32u;
+    const int nlev = cur.nlev & 0xffff, nreal = cur.nlev >> 16;       // tile-local levels, rows that are not padding
     const uint32_t vals_a = slab_a0 + (uint32_t)buf * (uint32_t)slab_bytes;      // values of the slab, then its column indices
     const uint32_t cols_a = vals_a + (uint32_t)p.cap_slots * 256u;
+    // ---- the first hint flag is requested before anything else (one L2 round trip that everything below overlaps)
+    int flag0 = 1;
+    if (tid < cur.nd) flag0 = ld_relaxed_i32(p.done + cur_dep);
     // ---- per-row data that does not depend on `out`
-    double acc[NR], dv[NR], sv[NR], dg[NR], rs[NR];
-    int lv[NR], sb[NR], wd[NR];
+    double acc[NR], dv[NR], aux[NR];
+    int lv[NR], lvp[NR], sb[NR], wd[NR];
 #pragma unroll
     for (int j = 0; j < NR; j++) {
       const int sl = w + j * NW;
-      lv[j] = 256; sb[j] = 0; wd[j] = 0; acc[j] = 0.0; dv[j] = 0.0; sv[j] = 0.0; dg[j] = 0.0; rs[j] = 0.0;
+      lv[j] = 256; lvp[j] = 256; sb[j] = 0; wd[j] = 0; acc[j] = 0.0; dv[j] = 0.0; aux[j] = 0.0;
       if (sl < ns) {
         const i64 slice = (i64)s0 + sl, row = slice * 32 + lane;
         const i64 b = T.slice_ptr[slice];
         sb[j] = (int)(b - cur.base);
         wd[j] = (int)(T.slice_ptr[slice + 1] - b);
         lv[j] = p.row_lvl[row];
+        lvp[j] = (sl == 0 && lane == 0) ? -1 : (int)p.row_lvl[row - 1];
         acc[j] = rin[row];
         dv[j] = dinv[row];
-        if (ADD_SELF) sv[j] = self[row];
-        if (WRITE_R) dg[j] = diag[row];
+        aux[j] = ADD_SELF ? self[row] : (WRITE_R ? diag[row] : 0.0);
       }
     }
     // ---- hint flags of the tiles this one depends on (one thread per dependency; the first NT ids were prefetched)
     for (int k = tid; k < cur.nd; k += NT) {
-      const i32 dt = (k < NT) ? cur_dep : p.dep[cur.d0 + k];
-      const int *f = p.done + dt;
+      const int *f = p.done + ((k < NT) ? cur_dep : p.dep[cur.d0 + k]);
       unsigned spins = 0;
-      while (ld_relaxed_i32(f) == 0) {
+      int fl = (k < NT) ? flag0 : ld_relaxed_i32(f);
+      while (fl == 0) {
         if (p.sleep_ns) __nanosleep(p.sleep_ns);
         if (spin_fail(spins, p.err)) break;
+        fl = ld_relaxed_i32(f);
       }
     }
     if (tr) tr[1] = gtimer();
@@ -211,8 +238,7 @@ __global__ void __launch_bounds__(NT, (MAXS >= 16 ? 3 : 4)) k_gs_ctile(SellView 
     __syncthreads();
     if (tr) tr[2] = gtimer();
     // ---- couplings to rows of other tiles: poll the data itself (sentinel).  All polls of a round (CH slots of every owned row) are in
-    // flight together; a round with a straggler is simply polled again as a whole.  (Kept compact on purpose: three CTAs in different
-    // phases share an SM, and a kernel that does not fit the instruction cache pays for it inside the latency-critical level loop.)
+    // flight together; a round with a straggler is simply polled again as a whole.
     int maxw = 0;
 #pragma unroll
     for (int j = 0; j < NR; j++) maxw = max(maxw, wd[j]);
@@ -230,7 +256,7 @@ __global__ void __launch_bounds__(NT, (MAXS >= 16 ? 3 : 4)) k_gs_ctile(SellView 
           for (int e = 0; e < CH; e++) {
             const int k = k0 + e;
             const i32 c = (k < wd[j]) ? lds_i32(cols_a + (uint32_t)((sb[j] + k) * 32 + lane) * 4u) : -1;
-            xv[j][e] = (c >= 0 && (unsigned)(c - r0) >= nrow) ? ld_poll_relaxed(out + c) : 0.0;   // in-tile columns: shared memory, below
+            xv[j][e] = (c >= 0 && (unsigned)(c - r0) >= nrow) ? ld_poll_relaxed(out + c) : 0.0;   // in-tile columns: the solver's business
           }
 #pragma unroll
         for (int j = 0; j < NR; j++)
@@ -250,26 +276,46 @@ __global__ void __launch_bounds__(NT, (MAXS >= 16 ? 3 : 4)) k_gs_ctile(SellView 
           if (k < wd[j]) acc[j] = fma(-lds_f64(vals_a + (uint32_t)((sb[j] + k) * 32 + lane) * 8u), xv[j][e], acc[j]);
         }
     }
+    // ---- hand the rows to the solver: per-row scalars, slot offsets of the slices, first row of every level (rows are sorted by level)
+#pragma unroll
+    for (int j = 0; j < NR; j++) {
+      const int sl = w + j * NW;
+      if (sl < ns) {
+        const uint32_t lr = (uint32_t)(tid + j * NT);
+        sts_f64(acc_a + lr * 8u, acc[j]);
+        sts_f64(dv_a + lr * 8u, dv[j]);
+        sts_f64(aux_a + lr * 8u, aux[j]);
+        if (lane == 0) sts_i32(so_a + (uint32_t)sl * 4u, sb[j]);
+        if (lv[j] != lvp[j] && lv[j] < 255) sts_u16(ls_a + (uint32_t)lv[j] * 2u, lr);
+      }
+    }
+    if (tid == 0) { sts_i32(so_a + (uint32_t)ns * 4u, cur.nslots); sts_u16(ls_a + (uint32_t)nlev * 2u, (unsigned)nreal); }
     if (tr) tr[3] = gtimer();
     // the next tile's first dependency ids: its record has arrived by now
     const i32 nxt_dep = (more && tid < nxt.nd) ? p.dep[nxt.d0 + tid] : -1;
-    // ---- the tile itself, local level by local level (ascending forward, descending backward).  No global stores in here: a store
-    // in flight would be waited for by every __syncthreads (0.38 us per level measured); results go to shared memory and registers.
-    const int nlev = cur.nlev;
-    for (int it = 0; it < nlev; it++) {
-      const int s = p.backward ? (nlev - 1 - it) : it;
-#pragma unroll
-      for (int j = 0; j < NR; j++) {
-        if (lv[j] == s) {
-          double a = acc[j], a2 = 0.0;
-          // rounds of 8 slots: all shared-memory loads of a round are issued before the first FMA (two FMA chains)
-          for (int k0 = 0; k0 < wd[j]; k0 += 8) {
+    __syncthreads();
+    // ---- the tile itself: the solver warp walks the local levels (ascending forward, descending backward); in-tile couplings come from xs
+    if (w == 0) {
+      for (int it = 0; it < nlev; it++) {
+        const int s = p.backward ? (nlev - 1 - it) : it;
+        const int rb = (int)lds_u16(ls_a + (uint32_t)s * 2u), re = (int)lds_u16(ls_a + (uint32_t)(s + 1) * 2u);
+#pragma unroll 1
+        for (int rr = rb; rr < re; rr += 32) {
+          const int r = rr + lane;
+          const bool act = r < re;
+          const int rc = act ? r : rb;                                  // idle lanes shadow the first row (results discarded)
+          const uint32_t slc = (uint32_t)rc >> 5, ln = (uint32_t)rc & 31u;
+          const int base = lds_i32(so_a + slc * 4u), wdt = lds_i32(so_a + (slc + 1) * 4u) - base;
+          double a = lds_f64(acc_a + (uint32_t)rc * 8u), a2 = 0.0;
+          const double dvv = lds_f64(dv_a + (uint32_t)rc * 8u), ax = lds_f64(aux_a + (uint32_t)rc * 8u);
+          int k0 = 0;
+          do {
             i32 c[8];
             double v[8], x[8];
 #pragma unroll
             for (int e = 0; e < 8; e++) {
-              const bool in = k0 + e < wd[j];
-              const uint32_t slot = (uint32_t)((sb[j] + k0 + e) * 32 + lane);
+              const bool in = k0 + e < wdt;
+              const uint32_t slot = (uint32_t)(base + k0 + e) * 32u + ln;
               c[e] = in ? lds_i32(cols_a + slot * 4u) : -1;
               v[e] = in ? lds_f64(vals_a + slot * 8u) : 0.0;
             }
@@ -280,25 +326,33 @@ __global__ void __launch_bounds__(NT, (MAXS >= 16 ? 3 : 4)) k_gs_ctile(SellView 
             }
 #pragma unroll
             for (int e = 0; e < 8; e += 2) { a = fma(-v[e], x[e], a); a2 = fma(-v[e + 1], x[e + 1], a2); }
-          }
+            k0 += 8;
+          } while (__any_sync(0xffffffffu, k0 < wdt));
           a += a2;
-          const double d = dv[j] * a;
-          rs[j] = ADD_SELF ? sv[j] + d : d;
-          sts_f64(xs_a + (uint32_t)(tid + j * NT) * 8u, rs[j]);
-          if (WRITE_R) acc[j] = fma(-dg[j], d, a);      // the row's new residual (acc is not needed any more)
+          const double d = dvv * a;
+          if (act) {
+            sts_f64(xs_a + (uint32_t)r * 8u, ADD_SELF ? ax + d : d);
+            if (WRITE_R) sts_f64(acc_a + (uint32_t)r * 8u, fma(-ax, d, a));   // the row's new residual
+          }
         }
+        __syncwarp();
       }
-      __syncthreads();
-      if (tr && it == 0) tr[7] = gtimer();              // the first barrier also absorbs the gather skew between the warps
     }
+    __syncthreads();
     if (tr) tr[4] = gtimer();
     // ---- publish the tile: coalesced stores (padding rows: never updated, but `out` must not keep the sentinel), then the hint flag
 #pragma unroll
     for (int j = 0; j < NR; j++)
       if (lv[j] <= 255) {
-        const i64 row = (i64)r0 + tid + j * NT;
-        __stcg(out + row, lv[j] == 255 ? (ADD_SELF ? sv[j] : 0.0) : rs[j]);
-        if (WRITE_R) rout[row] = acc[j];
+        const uint32_t lr = (uint32_t)(tid + j * NT);
+        const i64 row = (i64)r0 + lr;
+        if (lv[j] == 255) {
+          __stcg(out + row, ADD_SELF ? aux[j] : 0.0);
+          if (WRITE_R) rout[row] = acc[j];
+        } else {
+          __stcg(out + row, lds_f64(xs_a + lr * 8u));
+          if (WRITE_R) rout[row] = lds_f64(acc_a + lr * 8u);
+        }
       }
     if (tid == 0) st_relaxed_i32(p.done + t, 1);
     if (tr) {
@@ -307,7 +361,7 @@ __global__ void __launch_bounds__(NT, (MAXS >= 16 ? 3 : 4)) k_gs_ctile(SellView 
       tr[5] = gtimer();
       tr[6] = (unsigned long long)smid | ((unsigned long long)blockIdx.x << 16) | ((unsigned long long)nlev << 40) | ((unsigned long long)ns << 52);
     }
-    __syncthreads();     // slab and xs are free again
+    __syncthreads();     // slab, xs and the per-row arrays are free again
     if (NBUF == 1) { if (more && tid == 0) fetch(nxt, 0); }
     else buf ^= 1;
     cur = nxt;

@@ -11,7 +11,7 @@ def load(fn):
     o = 16
     pp = np.frombuffer(raw[o:o + 8 * (nt + 1)], dtype=np.int64); o += 8 * (nt + 1)
     pl = np.frombuffer(raw[o:o + 4 * npred], dtype=np.int32); o += 4 * npred
-    tr = np.frombuffer(raw[o:o + 64 * nt], dtype=np.uint64).reshape(nt, 8)
+    tr = np.frombuffer(raw[o:o + 128 * nt], dtype=np.uint64).reshape(nt, 16)
     return int(nt), pp, pl, tr
 
 
@@ -32,8 +32,14 @@ def main(fn, backward=False):
     for k, v in ph.items():
         print("  %-10s mean %7.2f  median %7.2f  p90 %7.2f  max %8.2f us   (sum/CTA-time %.2f)" % (k, v.mean(), np.median(v), np.percentile(v, 90), v.max(),
                                                                                                  v.sum() / (span * len(np.unique(cta)))))
-    ok = nlev > 1
-    print("  first level incl. gather skew: mean %.2f us; later levels: %.3f us each" % ((t_first - t[:, 3])[ok].mean(), ((t[:, 4] - t_first)[ok] / (nlev[ok] - 1)).mean()))
+    ok = (nlev > 1) & (tr[:, 7] > 0)
+    if ok.any():
+      print("  first level incl. gather skew: mean %.2f us; later levels: %.3f us each" % ((t_first - t[:, 3])[ok].mean(), ((t[:, 4] - t_first)[ok] / (nlev[ok] - 1)).mean()))
+    cyc = tr[:, 8:12].astype(np.float64)
+    if cyc[:, 3].max() > 0:
+      print("  warp 0 cycle accounting per tile: loop %.0f cyc (%.2f us at 1.965 GHz) = active blocks %.0f (%.1f visits, %.0f cyc each) + barriers %.0f (%.0f cyc per level)"
+          % (cyc[:, 3].mean(), cyc[:, 3].mean() / 1965.0, cyc[:, 0].mean(), cyc[:, 1].mean(), cyc[:, 0].sum() / max(cyc[:, 1].sum(), 1), cyc[:, 2].mean(),
+             cyc[:, 2].sum() / max(nlev.sum(), 1)))
     print("  per local level: %.3f us (levels / nlev, mean nlev %.1f, mean slices %.1f)" % ((ph["levels"] / np.maximum(nlev, 1)).mean(), nlev.mean(), ns.mean()))
     # tile DAG levels and the dependency slack: when did the last dependency finish vs when did the tile pass its hint wait / gather
     lvl = np.zeros(nt, np.int64)
