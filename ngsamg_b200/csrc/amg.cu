@@ -748,17 +748,17 @@ void Amg::build_level_layout(Level &L, const DevCsr &dA)
   dev_free(d_err);
 }
 
-// the instantiations of the CTA-per-tile sweep: [maxs == 16][nbuf == 2][add_self]
-constexpr int CTILE_NT = 256;
+// the instantiations of the CTA-per-tile sweep: 256-row tiles run on 128-thread CTAs (6 per SM), 512-row tiles on 256-thread CTAs (3 per SM)
 using CTileKernel = void (*)(SellView, const double *, const double *, const double *, const double *, double *, double *, CTileParams);
+static int ctile_threads(int maxs) { return maxs <= 8 ? 128 : 256; }
 static CTileKernel ctile_kernel(int maxs, int nbuf, bool add_self)
 {
   if (maxs <= 8) {
-    if (nbuf == 1) return add_self ? (CTileKernel)k_gs_ctile<CTILE_NT, 8, 1, true, false> : (CTileKernel)k_gs_ctile<CTILE_NT, 8, 1, false, true>;
-    return add_self ? (CTileKernel)k_gs_ctile<CTILE_NT, 8, 2, true, false> : (CTileKernel)k_gs_ctile<CTILE_NT, 8, 2, false, true>;
+    if (nbuf == 1) return add_self ? (CTileKernel)k_gs_ctile<128, 8, 1, true, false, 6> : (CTileKernel)k_gs_ctile<128, 8, 1, false, true, 6>;
+    return add_self ? (CTileKernel)k_gs_ctile<128, 8, 2, true, false, 6> : (CTileKernel)k_gs_ctile<128, 8, 2, false, true, 6>;
   }
-  if (nbuf == 1) return add_self ? (CTileKernel)k_gs_ctile<CTILE_NT, 16, 1, true, false> : (CTileKernel)k_gs_ctile<CTILE_NT, 16, 1, false, true>;
-  return add_self ? (CTileKernel)k_gs_ctile<CTILE_NT, 16, 2, true, false> : (CTileKernel)k_gs_ctile<CTILE_NT, 16, 2, false, true>;
+  if (nbuf == 1) return add_self ? (CTileKernel)k_gs_ctile<256, 16, 1, true, false, 3> : (CTileKernel)k_gs_ctile<256, 16, 1, false, true, 3>;
+  return add_self ? (CTileKernel)k_gs_ctile<256, 16, 2, true, false, 3> : (CTileKernel)k_gs_ctile<256, 16, 2, false, true, 3>;
 }
 // Two-level (tile) schedule of the triangular sweeps of a level (tiles.hpp): only for scalar levels that are big and whose sweep DAG is
 // deep -- a colour-major coarse level has a shallower DAG than any tiling of it.  A = the matrix the sweep runs on (the level matrix, or
@@ -822,6 +822,8 @@ void Amg::prepare_ctile(Level &L)
       const i32 s0 = L.h_tile_slice[t], s1 = L.h_tile_slice[t + 1];
       const i64 slots = sp[s1] - sp[s0];
       cap = std::max(cap, slots);
+      for (i32 s2 = s0; s2 < s1; s2++)
+        if (sp[s2 + 1] - sp[s2] > 255) throw Error("tile sweep: a row with more than 255 entries in one triangle; disable ngs_amg_b200_tile_sweep for this matrix");
       if (dp[t] >= (i64)2147483647) throw Error("tile sweep: wait lists too long");
       meta[dir][t] = CTileMeta{sp[s0], s0, s1 - s0, (i32)slots, L.h_tile_nlev[t] | (L.h_tile_nreal[t] << 16), (i32)dp[t], (i32)(dp[t + 1] - dp[t])};
     }
@@ -846,7 +848,7 @@ void Amg::prepare_ctile(Level &L)
       NGB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g));
     }
     int occ = 0;
-    NGB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k, CTILE_NT, L.ctile_smem));
+    NGB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k, ctile_threads(L.tile_maxs), L.ctile_smem));
     occ = std::max(1, occ);
     if (tri_ctas_per_sm > 0) occ = std::min(occ, tri_ctas_per_sm);
     L.ctile_grid[as] = (int)std::max<i64>(1, std::min<i64>(L.ntiles, (i64)occ * num_sms));
@@ -1589,7 +1591,7 @@ void Amg::tri(Level &L, bool backward, bool add_self, bool write_r, const double
         if (add_self) k_gs_tile_prefix<true, false><<<nblk(L.nonfree_pad), TB, 0, st>>>(L.nonfree_pad, rin, self, out, rout);
         else k_gs_tile_prefix<false, true><<<nblk(L.nonfree_pad), TB, 0, st>>>(L.nonfree_pad, rin, self, out, rout);
       }
-      launch_resident_smem(ctile_kernel(L.tile_maxs, L.tile_nbuf, add_self), L.ctile_grid[add_self ? 1 : 0], CTILE_NT, L.ctile_smem, st, T.view(),
+      launch_resident_smem(ctile_kernel(L.tile_maxs, L.tile_nbuf, add_self), L.ctile_grid[add_self ? 1 : 0], ctile_threads(L.tile_maxs), L.ctile_smem, st, T.view(),
                            (const double *)L.diag, (const double *)L.dinv, rin, self, out, rout, prm);
       launches += 2;
       return;

@@ -120,33 +120,53 @@ __device__ __forceinline__ unsigned lds_u16(uint32_t a)
 __device__ __forceinline__ void sts_u16(uint32_t a, unsigned v) { asm volatile("st.shared.u16 [%0], %1;" ::"r"(a), "h"((unsigned short)v) : "memory"); }
 __device__ __forceinline__ void sts_i32(uint32_t a, i32 v) { asm volatile("st.shared.s32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
 
-// shared memory of a CTA: [ header | level starts | slice slot offsets | xs | acc | dinv | aux | NBUF slabs ]
-//   header      : the mbarriers (one per slab)
-//   level starts: first tile-local row of every tile-local level (+ end), u16
-//   slot offsets: first slot of every slice of the tile inside the slab (+ end), i32
-//   xs          : the tile's part of `out`;  acc: per row  rin - (couplings to other tiles);  dinv;  aux: self (ADD_SELF) or diag (WRITE_R)
+__device__ __forceinline__ uint4 lds_v4(uint32_t a)
+{
+  uint4 v;
+  asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a) : "memory");
+  return v;
+}
+__device__ __forceinline__ void sts_v4(uint32_t a, uint4 v)
+{
+  asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+
+// shared memory of a CTA: [ header | level starts | gather indices | row bases | xs (+ zero slot) | acc | dinv | aux | NBUF slabs ]
+//   header        : the mbarriers (one per slab)
+//   level starts  : first tile-local row of every tile-local level (+ end), u16
+//   gather indices: per row 8 x u16 (one 16-byte word): tile-local row of the in-tile column in slot e, or the zero slot
+//   row bases     : per row  (first slot of the row's slice in the slab) * 32 + lane  |  slice width << 24
+//   xs            : the tile's part of `out`, followed by a slot that always holds 0.0
+//   acc           : per row  rin - (couplings to other tiles);  dinv;  aux: self (ADD_SELF) or diag (WRITE_R)
 constexpr int CTILE_HDR = 128;
 constexpr int CTILE_MAXLEV = 256;                                   // tile-local levels fit a byte (tiles.cpp)
-__host__ __device__ inline size_t ctile_fixed_bytes(int maxs) { return (size_t)CTILE_HDR + (CTILE_MAXLEV + 8) * 2 + (size_t)(maxs + 8) * 4 + (size_t)4 * maxs * 32 * 8; }
+constexpr int CTILE_LS_BYTES = 640;                                 // (CTILE_MAXLEV + 8) u16, rounded to 128 bytes
+__host__ __device__ inline size_t ctile_fixed_bytes(int maxs)
+{
+  const size_t rows = (size_t)maxs * 32;
+  return (size_t)CTILE_HDR + CTILE_LS_BYTES + rows * 16 + rows * 4 + (rows + 16) * 8 + 3 * rows * 8;
+}
 __host__ __device__ inline size_t ctile_smem_bytes(int maxs, int cap_slots, int nbuf)
 {
   return ((ctile_fixed_bytes(maxs) + 127) / 128) * 128 + (size_t)nbuf * (size_t)cap_slots * 32 * 12;
 }
 
-// One CTA per tile.  All warps fetch, wait and fold the couplings to other tiles; then ONE warp (the solver) walks the tile-local levels
-// with __syncwarp between them -- a CTA-wide barrier per level costs ~0.35 us with one late warp (measured, scripts/micro/), a warp walking
-// the levels alone ~0.1-0.15 us -- and all warps publish the result.
+// One CTA per tile.  All warps fetch, wait, fold the couplings to other tiles into the rows' accumulators and PREPARE the solver's
+// operands; then ONE warp (the solver) walks the tile-local levels with __syncwarp between them -- a CTA-wide barrier per level costs
+// ~0.35 us with one late warp (measured, scripts/micro/), a warp walking the levels alone ~0.12 us per 32 rows -- and all warps publish.
+// Small CTAs (NT = 128 for 256-row tiles) so that 6+ tiles per SM are in flight: the phases of different tiles overlap.
 // NBUF = slabs in shared memory: 1 = the next tile's slab is fetched when the current tile is finished, 2 = while the current tile is
 // being swept (HBM latency never exposed; twice the shared memory).
-template <int NT, int MAXS, int NBUF, bool ADD_SELF, bool WRITE_R>
-__global__ void __launch_bounds__(NT, (MAXS >= 16 ? 3 : 4)) k_gs_ctile(SellView T, const double *__restrict__ diag, const double *__restrict__ dinv,
-                                                                      const double *rin, const double *__restrict__ self, double *out, double *rout,
-                                                                      CTileParams p)
+template <int NT, int MAXS, int NBUF, bool ADD_SELF, bool WRITE_R, int MINB>
+__global__ void __launch_bounds__(NT, MINB) k_gs_ctile(SellView T, const double *__restrict__ diag, const double *__restrict__ dinv,
+                                                       const double *rin, const double *__restrict__ self, double *out, double *rout,
+                                                       CTileParams p)
 {
   constexpr int NW = NT / 32;
   static_assert(MAXS % NW == 0, "every warp owns the same number of slices");
   constexpr int NR = MAXS / NW;                 // rows per thread: tile-local rows tid, tid + NT, ...
   constexpr int CH = (NR <= 2) ? 8 : 4;         // slots gathered per round and row
+  constexpr unsigned ZERO = MAXS * 32;          // gather index of the zero slot
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const size_t slab_bytes = (size_t)p.cap_slots * 32 * 12;
   int tid;                                                            // (opaque: S2R SR_TID.X would be re-issued inside the loops)
@@ -158,13 +178,15 @@ __global__ void __launch_bounds__(NT, (MAXS >= 16 ? 3 : 4)) k_gs_ctile(SellView 
   asm volatile("mov.u32 %0, %1;" : "=r"(smem_base) : "r"(smem_u32(smem_raw)));
   const uint32_t bar0 = smem_base;                                    // mbarrier b at bar0 + 8 b
   const uint32_t ls_a = smem_base + CTILE_HDR;                        // level starts
-  const uint32_t so_a = ls_a + (CTILE_MAXLEV + 8) * 2;                // slice slot offsets
-  const uint32_t xs_a = so_a + (MAXS + 8) * 4;
-  const uint32_t acc_a = xs_a + MAXS * 32 * 8, dv_a = acc_a + MAXS * 32 * 8, aux_a = dv_a + MAXS * 32 * 8;
+  const uint32_t ix_a = ls_a + CTILE_LS_BYTES;                        // gather indices
+  const uint32_t rb_a = ix_a + MAXS * 32 * 16;                        // row bases
+  const uint32_t xs_a = rb_a + MAXS * 32 * 4;
+  const uint32_t acc_a = xs_a + (MAXS * 32 + 16) * 8, dv_a = acc_a + MAXS * 32 * 8, aux_a = dv_a + MAXS * 32 * 8;
   const uint32_t slab_a0 = smem_base + (uint32_t)(((ctile_fixed_bytes(MAXS) + 127) / 128) * 128);
   if (tid == 0) {
     for (int b = 0; b < NBUF; b++) mbar_init(bar0 + 8 * b, 1);
     mbar_fence_init();
+    sts_f64(xs_a + ZERO * 8u, 0.0);
   }
   __syncthreads();
   auto tile_of = [&](i32 q) { return p.backward ? (p.ntiles - 1 - q) : q; };
@@ -276,7 +298,7 @@ __global__ void __launch_bounds__(NT, (MAXS >= 16 ? 3 : 4)) k_gs_ctile(SellView 
           if (k < wd[j]) acc[j] = fma(-lds_f64(vals_a + (uint32_t)((sb[j] + k) * 32 + lane) * 8u), xv[j][e], acc[j]);
         }
     }
-    // ---- hand the rows to the solver: per-row scalars, slot offsets of the slices, first row of every level (rows are sorted by level)
+    // ---- hand the rows to the solver: per-row scalars, gather indices of the first 8 slots, row base, first row of every level
 #pragma unroll
     for (int j = 0; j < NR; j++) {
       const int sl = w + j * NW;
@@ -285,17 +307,26 @@ __global__ void __launch_bounds__(NT, (MAXS >= 16 ? 3 : 4)) k_gs_ctile(SellView 
         sts_f64(acc_a + lr * 8u, acc[j]);
         sts_f64(dv_a + lr * 8u, dv[j]);
         sts_f64(aux_a + lr * 8u, aux[j]);
-        if (lane == 0) sts_i32(so_a + (uint32_t)sl * 4u, sb[j]);
+        unsigned h[8];
+#pragma unroll
+        for (int e = 0; e < 8; e++) {
+          const i32 c = (e < wd[j]) ? lds_i32(cols_a + (uint32_t)((sb[j] + e) * 32 + lane) * 4u) : -1;
+          const unsigned lc = (unsigned)(c - r0);
+          h[e] = (c >= 0 && lc < nrow) ? lc : ZERO;
+        }
+        sts_v4(ix_a + lr * 16u, make_uint4(h[0] | (h[1] << 16), h[2] | (h[3] << 16), h[4] | (h[5] << 16), h[6] | (h[7] << 16)));
+        sts_i32(rb_a + lr * 4u, (sb[j] * 32 + lane) | (min(wd[j], 255) << 24));
         if (lv[j] != lvp[j] && lv[j] < 255) sts_u16(ls_a + (uint32_t)lv[j] * 2u, lr);
       }
     }
-    if (tid == 0) { sts_i32(so_a + (uint32_t)ns * 4u, cur.nslots); sts_u16(ls_a + (uint32_t)nlev * 2u, (unsigned)nreal); }
+    if (tid == 0) sts_u16(ls_a + (uint32_t)nlev * 2u, (unsigned)nreal);
     if (tr) tr[3] = gtimer();
     // the next tile's first dependency ids: its record has arrived by now
     const i32 nxt_dep = (more && tid < nxt.nd) ? p.dep[nxt.d0 + tid] : -1;
-    __syncthreads();
+    const int wide = __syncthreads_or(maxw > 8);                      // rows with more than 8 slots: the solver's second round
     // ---- the tile itself: the solver warp walks the local levels (ascending forward, descending backward); in-tile couplings come from xs
     if (w == 0) {
+#pragma unroll 1
       for (int it = 0; it < nlev; it++) {
         const int s = p.backward ? (nlev - 1 - it) : it;
         const int rb = (int)lds_u16(ls_a + (uint32_t)s * 2u), re = (int)lds_u16(ls_a + (uint32_t)(s + 1) * 2u);
@@ -303,31 +334,30 @@ __global__ void __launch_bounds__(NT, (MAXS >= 16 ? 3 : 4)) k_gs_ctile(SellView 
         for (int rr = rb; rr < re; rr += 32) {
           const int r = rr + lane;
           const bool act = r < re;
-          const int rc = act ? r : rb;                                  // idle lanes shadow the first row (results discarded)
-          const uint32_t slc = (uint32_t)rc >> 5, ln = (uint32_t)rc & 31u;
-          const int base = lds_i32(so_a + slc * 4u), wdt = lds_i32(so_a + (slc + 1) * 4u) - base;
-          double a = lds_f64(acc_a + (uint32_t)rc * 8u), a2 = 0.0;
-          const double dvv = lds_f64(dv_a + (uint32_t)rc * 8u), ax = lds_f64(aux_a + (uint32_t)rc * 8u);
-          int k0 = 0;
-          do {
-            i32 c[8];
-            double v[8], x[8];
+          const uint32_t rc = (uint32_t)(act ? r : rb);                 // idle lanes shadow the first row (results discarded)
+          const uint4 iw = lds_v4(ix_a + rc * 16u);
+          const i32 rbw = lds_i32(rb_a + rc * 4u);
+          const uint32_t vb = vals_a + (uint32_t)(rbw & 0xffffff) * 8u;
+          const int wdt = (int)((unsigned)rbw >> 24);
+          double a = lds_f64(acc_a + rc * 8u), a2 = 0.0;
+          const double dvv = lds_f64(dv_a + rc * 8u), ax = lds_f64(aux_a + rc * 8u);
+          const unsigned ix[4] = {iw.x, iw.y, iw.z, iw.w};
+          double v[8], x[8];
 #pragma unroll
-            for (int e = 0; e < 8; e++) {
-              const bool in = k0 + e < wdt;
-              const uint32_t slot = (uint32_t)(base + k0 + e) * 32u + ln;
-              c[e] = in ? lds_i32(cols_a + slot * 4u) : -1;
-              v[e] = in ? lds_f64(vals_a + slot * 8u) : 0.0;
+          for (int e = 0; e < 8; e++) v[e] = (e < wdt) ? lds_f64(vb + (uint32_t)e * 256u) : 0.0;
+#pragma unroll
+          for (int e = 0; e < 8; e++) x[e] = lds_f64(xs_a + ((ix[e >> 1] >> ((e & 1) * 16)) & 0xffffu) * 8u);
+#pragma unroll
+          for (int e = 0; e < 8; e += 2) { a = fma(-v[e], x[e], a); a2 = fma(-v[e + 1], x[e + 1], a2); }
+          if (wide) {
+            // slots 8.. of wide rows: column indices straight from the slab (rare: coarse-like matrices)
+            const uint32_t cb = cols_a + (uint32_t)(rbw & 0xffffff) * 4u;
+            for (int k = 8; k < wdt; k++) {
+              const i32 c = lds_i32(cb + (uint32_t)k * 128u);
+              const unsigned lc = (unsigned)(c - r0);
+              if (c >= 0 && lc < nrow) a = fma(-lds_f64(vb + (uint32_t)k * 256u), lds_f64(xs_a + lc * 8u), a);
             }
-#pragma unroll
-            for (int e = 0; e < 8; e++) {
-              const unsigned lc = (unsigned)(c[e] - r0);
-              x[e] = (c[e] >= 0 && lc < nrow) ? lds_f64(xs_a + lc * 8u) : 0.0;
-            }
-#pragma unroll
-            for (int e = 0; e < 8; e += 2) { a = fma(-v[e], x[e], a); a2 = fma(-v[e + 1], x[e + 1], a2); }
-            k0 += 8;
-          } while (__any_sync(0xffffffffu, k0 < wdt));
+          }
           a += a2;
           const double d = dvv * a;
           if (act) {
