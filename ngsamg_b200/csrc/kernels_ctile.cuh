@@ -207,6 +207,7 @@ __global__ void __launch_bounds__(NT, MINB) k_gs_ctile(SellView T, const double 
   i32 cur_dep = (tid < cur.nd) ? p.dep[cur.d0 + tid] : -1;
   if (tid == 0) fetch(cur, 0);
   int buf = 0;
+  int solver = (int)(blockIdx.x % NW);
   for (; q < p.ntiles; q += gridDim.x) {
     const i32 t = tile_of(q);
     unsigned long long *tr = (p.trace && tid == 0) ? p.trace + (size_t)t * 16 : nullptr;
@@ -325,7 +326,9 @@ __global__ void __launch_bounds__(NT, MINB) k_gs_ctile(SellView T, const double 
     const i32 nxt_dep = (more && tid < nxt.nd) ? p.dep[nxt.d0 + tid] : -1;
     const int wide = __syncthreads_or(maxw > 8);                      // rows with more than 8 slots: the solver's second round
     // ---- the tile itself: the solver warp walks the local levels (ascending forward, descending backward); in-tile couplings come from xs
-    if (w == 0) {
+    // (the solver role rotates over the warps: warp w of every CTA sits on scheduler w % 4 -- a fixed solver warp would put the
+    // latency-critical chains of all resident CTAs on the same scheduler)
+    if (w == solver) {
 #pragma unroll 1
       for (int it = 0; it < nlev; it++) {
         const int s = p.backward ? (nlev - 1 - it) : it;
@@ -396,6 +399,7 @@ __global__ void __launch_bounds__(NT, MINB) k_gs_ctile(SellView T, const double 
     else buf ^= 1;
     cur = nxt;
     cur_dep = nxt_dep;
+    solver = (solver + 1) % NW;
   }
 }
 
