@@ -432,14 +432,16 @@ def main():
         by_level.append(row)
     dom = max(("gs_tri_fwd", "gs_tri_bwd", "gs_upass", "gs_lpass"), key=lambda k: kern[k]["ms"])
     traffic = None
+    tiled = extra.get("ngs_amg_b200_tile_sweep", "1") not in ("0", "false", "False")
     try:
-        with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as f:
+        # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full capture of the same kernel and size
+        with open(os.path.join(ROOT, "profiles", "r02_traffic.json" if tiled else "r01_traffic.json")) as f:
             tj = json.load(f)
         if tj.get("n") == n:
             traffic = tj.get(dom)
     except Exception:
         pass
-    roof = {"bound": "hbm", "kernel": "k_gs_tri (%s, level 0)" % dom, "achieved": kern[dom]["gbs"], "peak": peak,
+    roof = {"bound": "hbm", "kernel": "%s (%s, level 0)" % ("k_gs_ctile" if tiled else "k_gs_tri", dom), "achieved": kern[dom]["gbs"], "peak": peak,
             "unit": "GB/s", "frac": kern[dom]["gbs"] / peak, "traffic": traffic, "peak_source": peak_src,
             "ms_per_launch": kern[dom]["ms"], "algorithmic_bytes": kern[dom]["bytes"]}
 

@@ -766,10 +766,10 @@ static CTileKernel ctile_kernel(int maxs, int nbuf, bool add_self)
 bool Amg::setup_tiles(Level &L, int l, const HostBsr &A)
 {
   const bool verbose = flags.str("log_level", "none") != "none";
-  if (L.b != 1 || !flags.flag("b200_tile_sweep", false) || L.n < (i64)flags.num("b200_tile_min_rows", 200000)) return false;
+  if (L.b != 1 || !flags.flag("b200_tile_sweep", true) || L.n < (i64)flags.num("b200_tile_min_rows", 200000)) return false;
   if (sweep_depth(A, L.mask(), L.sweep_rank) < (int)flags.num("b200_tile_min_depth", 150)) return false;
   TileSchedule ts;
-  const int cap = (int)flags.num("b200_tile_rows", 64);
+  const int cap = (int)flags.num("b200_tile_rows", 256);
   if (cap != 32 && cap != 64 && cap != 256 && cap != 512)
     throw Error("ngs_amg_b200_tile_rows must be 32 or 64 (one warp per tile) or 256 or 512 (one CTA per tile)");
   int rounds = 5;
