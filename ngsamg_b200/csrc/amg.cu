@@ -15,6 +15,7 @@
 #include "kernels.cuh"
 #include "kernels_tile.cuh"
 #include "kernels_ctile.cuh"
+#include "kernels_itile.cuh"
 #include "par.hpp"
 #include "tiles.hpp"
 
@@ -102,6 +103,14 @@ struct Level {
   std::vector<i32> h_tile_slice, h_tile_nlev, h_tile_nreal;   // nreal: rows of the tile that are not padding
   std::vector<i64> h_pred_ptr, h_succ_ptr;
   CTileMeta *d_meta_fwd = nullptr, *d_meta_bwd = nullptr;
+  // prepared tile images (kernels_itile.cuh): the production path when no row has more than 7 entries per triangle
+  bool itile = false;
+  unsigned char *d_img[2] = {nullptr, nullptr};      // [forward (L, with diag), backward (U)]
+  ITileMeta *d_imeta[2] = {nullptr, nullptr};
+  int itile_cap = 0;
+  size_t itile_smem = 0;
+  int itile_grid[2] = {0, 0};
+  i64 img_bytes_total = 0;
   int tile_nbuf = 1;
   int tile_cap_slots = 0;
   int ctile_grid[2] = {0, 0};     // [add_self]
@@ -256,6 +265,7 @@ struct Amg {
   void finalize();
   void build_level_layout(Level &L, const DevCsr &dA);
   void prepare_ctile(Level &L);
+  bool prepare_itile(Level &L);
   bool setup_tiles(Level &L, int l, const HostBsr &A);
   void build_transfer_layout(Level &F, Level &C);
   void build_coarse_inverse(Level &L);
@@ -597,6 +607,7 @@ Amg::~Amg()
     L.G.release();
     dev_free(L.d_tile_slice); dev_free(L.d_tile_nlev); dev_free(L.d_tile_pred); dev_free(L.d_tile_succ); dev_free(L.d_row_lvl);
     dev_free(L.d_tile_pred_ptr); dev_free(L.d_tile_succ_ptr); dev_free(L.d_tile_done); dev_free(L.d_meta_fwd); dev_free(L.d_meta_bwd);
+    for (int d = 0; d < 2; d++) { dev_free(L.d_img[d]); dev_free(L.d_imeta[d]); }
     dev_free(L.d_m_idx); dev_free(L.d_g_idx); dev_free(L.d_mu_dof); dev_free(L.d_mu_ptr); dev_free(L.d_mu_pos);
     dev_free(L.sendbuf); dev_free(L.recvbuf);
     if (L.h_send) cudaFreeHost(L.h_send);
@@ -760,6 +771,13 @@ static CTileKernel ctile_kernel(int maxs, int nbuf, bool add_self)
   if (nbuf == 1) return add_self ? (CTileKernel)k_gs_ctile<256, 16, 1, true, false, 3> : (CTileKernel)k_gs_ctile<256, 16, 1, false, true, 3>;
   return add_self ? (CTileKernel)k_gs_ctile<256, 16, 2, true, false, 3> : (CTileKernel)k_gs_ctile<256, 16, 2, false, true, 3>;
 }
+using ITileKernel = void (*)(const double *, const double *, double *, double *, ITileParams);
+static ITileKernel itile_kernel(int maxs, bool add_self)
+{
+  if (maxs <= 8) return add_self ? (ITileKernel)k_gs_itile<128, 256, true, false, 6> : (ITileKernel)k_gs_itile<128, 256, false, true, 6>;
+  return add_self ? (ITileKernel)k_gs_itile<128, 512, true, false, 3> : (ITileKernel)k_gs_itile<128, 512, false, true, 3>;
+}
+
 // Two-level (tile) schedule of the triangular sweeps of a level (tiles.hpp): only for scalar levels that are big and whose sweep DAG is
 // deep -- a colour-major coarse level has a shallower DAG than any tiling of it.  A = the matrix the sweep runs on (the level matrix, or
 // the master-master block M of a distributed level with the hybrid stage order in L.sweep_rank).
@@ -856,6 +874,86 @@ void Amg::prepare_ctile(Level &L)
       std::fprintf(stderr, "[ngsamg_b200] tile sweep (%s): %lld tiles, %d slab(s) of %d slots, %zu B smem, %d CTAs/SM, grid %d\n", as ? "backward/rhs" : "forward/res",
                    (long long)L.ntiles, L.tile_nbuf, L.tile_cap_slots, L.ctile_smem, occ, L.ctile_grid[as]);
   }
+}
+
+// Prepared tile images (kernels_itile.cuh): built once per level and direction on the device; false = some row has more than 7 entries
+// in a triangle (the general kernel k_gs_ctile stays in charge).
+bool Amg::prepare_itile(Level &L)
+{
+  if (!flags.flag("b200_tile_image", true)) return false;
+  const i64 nt = L.ntiles;
+  const int maxrows = L.tile_maxs * 32;
+  i32 *d_nxr = dev_alloc<i32>(nt), *d_nx = dev_alloc<i32>(nt), *d_max = dev_alloc<i32>(1);
+  i32 *d_nreal = upload_vec(L.h_tile_nreal, st);
+  std::vector<i32> nxr(nt), nx(nt);
+  bool ok = true;
+  for (int dir = 0; dir < 2 && ok; dir++) {
+    const Sell &S = dir ? L.U : L.L;
+    const std::vector<i64> &dp = dir ? L.h_succ_ptr : L.h_pred_ptr;
+    NGB_CUDA(cudaMemsetAsync(d_max, 0, sizeof(i32), st));
+    k_img_count<<<(unsigned)nt, 128, 0, st>>>((i32)nt, L.d_tile_slice, S.view(), d_nxr, d_nx, d_max);
+    i32 mx = 0;
+    NGB_CUDA(cudaMemcpyAsync(&mx, d_max, sizeof(i32), cudaMemcpyDeviceToHost, st));
+    NGB_CUDA(cudaMemcpyAsync(nxr.data(), d_nxr, sizeof(i32) * nt, cudaMemcpyDeviceToHost, st));
+    NGB_CUDA(cudaMemcpyAsync(nx.data(), d_nx, sizeof(i32) * nt, cudaMemcpyDeviceToHost, st));
+    NGB_CUDA(cudaStreamSynchronize(st));
+    if (mx > IT_NV) { ok = false; break; }
+    std::vector<i64> off(nt + 1, 0);
+    std::vector<ITileMeta> meta(nt);
+    i64 cap = 0;
+    for (i64 t = 0; t < nt; t++) {
+      const int nrow = (L.h_tile_slice[t + 1] - L.h_tile_slice[t]) * 32;
+      const i64 b = itile_image_bytes(L.h_tile_nlev[t], nrow, nxr[t], nx[t], dir == 0);
+      if (nx[t] > 65535 || b > (i64)200 * 1024) { ok = false; break; }
+      off[t + 1] = off[t] + b;
+      cap = std::max(cap, b);
+      meta[t] = ITileMeta{off[t], L.h_tile_slice[t] * 32, nrow, (i32)b, 0, (i32)dp[t], (i32)(dp[t + 1] - dp[t])};
+    }
+    if (!ok) break;
+    L.itile_cap = std::max(L.itile_cap, (int)cap);
+    L.d_img[dir] = dev_alloc<unsigned char>((size_t)off[nt]);
+    L.img_bytes_total += off[nt];
+    i64 *d_off = upload_vec(off, st);
+    if (maxrows <= 256)
+      k_img_fill<256><<<(unsigned)nt, 128, 0, st>>>((i32)nt, L.d_tile_slice, L.d_tile_nlev, d_nreal, L.d_row_lvl, S.view(), L.dinv, L.diag, dir == 0 ? 1 : 0, d_off, d_nxr, d_nx, L.d_img[dir]);
+    else
+      k_img_fill<512><<<(unsigned)nt, 128, 0, st>>>((i32)nt, L.d_tile_slice, L.d_tile_nlev, d_nreal, L.d_row_lvl, S.view(), L.dinv, L.diag, dir == 0 ? 1 : 0, d_off, d_nxr, d_nx, L.d_img[dir]);
+    launches += 2;
+    L.d_imeta[dir] = upload_vec(meta, st);
+    NGB_CUDA(cudaStreamSynchronize(st));
+    NGB_CUDA(cudaGetLastError());
+    dev_free(d_off);
+  }
+  dev_free(d_nxr); dev_free(d_nx); dev_free(d_max); dev_free(d_nreal);
+  if (!ok) {
+    for (int d = 0; d < 2; d++) { dev_free(L.d_img[d]); dev_free(L.d_imeta[d]); }
+    return false;
+  }
+  L.itile_smem = itile_smem_bytes(maxrows, L.itile_cap);
+  int dev_max = 0;
+  NGB_CUDA(cudaDeviceGetAttribute(&dev_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
+  if (L.itile_smem > (size_t)dev_max) { for (int d = 0; d < 2; d++) { dev_free(L.d_img[d]); dev_free(L.d_imeta[d]); } return false; }
+  for (int as = 0; as < 2; as++) {
+    ITileKernel k = itile_kernel(L.tile_maxs, as == 1);
+    {
+      static std::mutex mu;
+      static size_t granted[2][2] = {};
+      std::lock_guard<std::mutex> guard(mu);
+      size_t &g = granted[L.tile_maxs <= 8 ? 0 : 1][as];
+      g = std::max(g, L.itile_smem);
+      NGB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g));
+    }
+    int occ = 0;
+    NGB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k, 128, L.itile_smem));
+    occ = std::max(1, occ);
+    if (tri_ctas_per_sm > 0) occ = std::min(occ, tri_ctas_per_sm);
+    L.itile_grid[as] = (int)std::max<i64>(1, std::min<i64>(L.ntiles, (i64)occ * num_sms));
+    if (flags.str("log_level", "none") != "none")
+      std::fprintf(stderr, "[ngsamg_b200] tile images (%s): %lld tiles, largest image %d B, %zu B smem, %d CTAs/SM, grid %d, %.2f GB of images\n", as ? "backward/rhs" : "forward/res",
+                   (long long)L.ntiles, L.itile_cap, L.itile_smem, occ, L.itile_grid[as], L.img_bytes_total / 1e9);
+  }
+  L.itile = true;
+  return true;
 }
 
 void Amg::build_transfer_layout(Level &F, Level &C)
@@ -1110,7 +1208,7 @@ void Amg::finalize()
       host_s += tick(h0);
       if (verbose) std::fprintf(stderr, "[ngsamg_b200] level %d: level schedule %.2f s (depth %d)\n", l, tick(h0), L.depth);
     }
-    if (!coarsest) { build_level_layout(L, dA); if (L.tiled && L.tile_maxs > 2) prepare_ctile(L); }
+    if (!coarsest) { build_level_layout(L, dA); if (L.tiled && L.tile_maxs > 2) { prepare_ctile(L); prepare_itile(L); } }
     else {
       L.d_perm = upload_vec(L.perm, st);
       if (clev == "inv") build_coarse_inverse(L);
@@ -1520,7 +1618,7 @@ void Amg::finalize_parallel()
       DevCsr dM;
       dev_csr_upload(L.hM, dM, st);
       build_level_layout(L, dM);
-      if (L.tiled && L.tile_maxs > 2) prepare_ctile(L);
+      if (L.tiled && L.tile_maxs > 2) { prepare_ctile(L); prepare_itile(L); }
       dev_csr_free(dM);
     }
     build_plain_sell(L.hG, L.d_perm, L.d_perm, L.npad, L.G, st, &launches);
@@ -1590,6 +1688,13 @@ void Amg::tri(Level &L, bool backward, bool add_self, bool write_r, const double
       if (L.nonfree_pad) {
         if (add_self) k_gs_tile_prefix<true, false><<<nblk(L.nonfree_pad), TB, 0, st>>>(L.nonfree_pad, rin, self, out, rout);
         else k_gs_tile_prefix<false, true><<<nblk(L.nonfree_pad), TB, 0, st>>>(L.nonfree_pad, rin, self, out, rout);
+      }
+      if (L.itile) {
+        ITileParams ip{(i32)L.ntiles, backward ? 1 : 0, L.d_imeta[backward ? 1 : 0], L.d_img[backward ? 1 : 0], backward ? L.d_tile_succ : L.d_tile_pred,
+                       L.d_tile_done, tri_sleep_ns, tri_repoll_ns, L.itile_cap, d_err, tri_trace};
+        launch_resident_smem(itile_kernel(L.tile_maxs, add_self), L.itile_grid[add_self ? 1 : 0], 128, L.itile_smem, st, rin, self, out, rout, ip);
+        launches += 2;
+        return;
       }
       launch_resident_smem(ctile_kernel(L.tile_maxs, L.tile_nbuf, add_self), L.ctile_grid[add_self ? 1 : 0], ctile_threads(L.tile_maxs), L.ctile_smem, st, T.view(),
                            (const double *)L.diag, (const double *)L.dinv, rin, self, out, rout, prm);

@@ -1,0 +1,343 @@
+// kernels_itile.cuh -- the CTA-per-tile Gauss-Seidel sweep on PREPARED TILE IMAGES (the production path for matrices with at most 7
+// entries per row and triangle, e.g. P1 tets; everything else runs k_gs_ctile, kernels_ctile.cuh).
+//
+// What k_gs_ctile does per sweep -- scanning column indices, turning them into tile-local gather indices, separating the couplings to
+// other tiles, loading dinv / diag / level numbers row by row -- does not depend on the vectors.  It is done ONCE at setup (k_img_count /
+// k_img_fill below): every tile gets a contiguous image in global memory, already in the layout the kernel wants in shared memory
+//
+//   header (16 B) | level starts (u16) | records: per row { 8 x u16 gather index | 7 values | dinv } = 80 B | [diag per row, forward only]
+//                 | external rows: { row, first entry, count } | external entries: { column, slot }
+//
+// so that a sweep fetches a tile with ONE bulk copy (+ one for the tile's rows of the right-hand side, + one for `self`), all on one
+// mbarrier, and no thread touches the matrix through the LSU.  Rows are sorted by tile-local level; a record is row-major (5 x LDS.128 per
+// row for the solver; 80 B stride = conflict-free quarter-warps); gather index 8*MAXS*... = ZERO addresses a slot that always holds 0.0
+// (padding slots and couplings to other tiles, which the gather phase folds into the accumulator).
+// HBM bytes per row: 80 + 8 (diag) + ~18 (external lists) = ~106 for the forward sweep against 100 of the plain SELL triangle.
+#pragma once
+#include "kernels_ctile.cuh"
+
+namespace ngb {
+
+constexpr int IT_NV = 7;            // value slots per record
+constexpr int IT_REC = 80;          // bytes per record
+
+struct __align__(16) ITileMeta {
+  i64 img;       // byte offset of the tile's image
+  i32 r0;        // first row of the tile
+  i32 nrow;      // rows incl. padding (multiple of 32)
+  i32 bytes;     // image size (multiple of 16)
+  i32 pad;
+  i32 d0;        // first entry of the tile's wait list in `dep`
+  i32 nd;        // tiles to wait for
+};
+
+struct ITileHeader {   // 16 bytes
+  unsigned short nlev, nreal, nrow, n_ext_rows;
+  unsigned short n_ext, ls_bytes, has_diag, pad;
+};
+
+__host__ __device__ inline i64 itile_image_bytes(int nlev, int nrow, int n_ext_rows, int n_ext, bool with_diag)
+{
+  const i64 ls = ((2 * (i64)(nlev + 1) + 15) / 16) * 16;
+  i64 b = 16 + ls + (i64)IT_REC * nrow + (with_diag ? 8 * (i64)nrow : 0) + 8 * (i64)n_ext_rows + 8 * (i64)n_ext;
+  return ((b + 127) / 128) * 128;
+}
+
+// ---- setup: pass 1 -- external rows / entries per tile ------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_img_count(i32 ntiles, const i32 *__restrict__ tile_slice, SellView T, i32 *n_ext_rows, i32 *n_ext, i32 *maxlen)
+{
+  __shared__ int s_rows, s_ent, s_max;
+  const i32 t = blockIdx.x;
+  if (t >= ntiles) return;
+  if (threadIdx.x == 0) { s_rows = 0; s_ent = 0; s_max = 0; }
+  __syncthreads();
+  const i32 s0 = tile_slice[t], s1 = tile_slice[t + 1];
+  const i32 r0 = s0 * 32;
+  const unsigned nrow = (unsigned)(s1 - s0) * 32u;
+  int rows = 0, ent = 0, mx = 0;
+  for (unsigned lr = threadIdx.x; lr < nrow; lr += blockDim.x) {
+    const i64 slice = s0 + (lr >> 5);
+    const int lane = lr & 31;
+    const i64 base = T.slice_ptr[slice];
+    const int wd = (int)(T.slice_ptr[slice + 1] - base);
+    int e = 0, len = 0;
+    for (int k = 0; k < wd; k++) {
+      const i32 c = T.col[(base + k) * 32 + lane];
+      if (c < 0) continue;
+      len++;
+      if ((unsigned)(c - r0) >= nrow) e++;
+    }
+    rows += e > 0; ent += e; mx = max(mx, len);
+  }
+  atomicAdd(&s_rows, rows); atomicAdd(&s_ent, ent); atomicMax(&s_max, mx);
+  __syncthreads();
+  if (threadIdx.x == 0) { n_ext_rows[t] = s_rows; n_ext[t] = s_ent; atomicMax(maxlen, s_max); }
+}
+
+// ---- setup: pass 2 -- write the images.  One CTA per tile, thread per row; external lists in (row, slot) order (deterministic). ------
+template <int MAXROWS>
+__global__ void __launch_bounds__(128) k_img_fill(i32 ntiles, const i32 *__restrict__ tile_slice, const i32 *__restrict__ tile_nlev,
+                                                 const i32 *__restrict__ tile_nreal, const uint8_t *__restrict__ row_lvl, SellView T,
+                                                 const double *__restrict__ dinv, const double *__restrict__ diag, int with_diag,
+                                                 const i64 *__restrict__ img_off, const i32 *__restrict__ n_ext_rows, const i32 *__restrict__ n_ext,
+                                                 unsigned char *img)
+{
+  constexpr int NT = 128, PER = MAXROWS / NT;
+  __shared__ int s_cnt[MAXROWS + 1];       // external entries per row -> exclusive prefix
+  __shared__ int s_rowid[MAXROWS + 1];     // external row flags -> exclusive prefix
+  const i32 t = blockIdx.x;
+  if (t >= ntiles) return;
+  const i32 s0 = tile_slice[t], s1 = tile_slice[t + 1];
+  const i32 r0 = s0 * 32;
+  const unsigned nrow = (unsigned)(s1 - s0) * 32u;
+  const int nlev = tile_nlev[t], nreal = tile_nreal[t];
+  unsigned char *base_p = img + img_off[t];
+  const i64 ls_bytes = ((2 * (i64)(nlev + 1) + 15) / 16) * 16;
+  unsigned short *ls = (unsigned short *)(base_p + 16);
+  unsigned char *recs = base_p + 16 + ls_bytes;
+  double *dg = (double *)(recs + (i64)IT_REC * nrow);
+  unsigned short *xrows = (unsigned short *)((unsigned char *)dg + (with_diag ? 8 * (i64)nrow : 0));
+  i32 *xent = (i32 *)((unsigned char *)xrows + 8 * (i64)n_ext_rows[t]);
+  if (threadIdx.x == 0) {
+    ITileHeader h;
+    h.nlev = (unsigned short)nlev; h.nreal = (unsigned short)nreal; h.nrow = (unsigned short)nrow; h.n_ext_rows = (unsigned short)n_ext_rows[t];
+    h.n_ext = (unsigned short)n_ext[t]; h.ls_bytes = (unsigned short)ls_bytes; h.has_diag = (unsigned short)with_diag; h.pad = 0;
+    *(ITileHeader *)base_p = h;
+    ls[nlev] = (unsigned short)nreal;
+  }
+  // records + per-row external counts
+#pragma unroll
+  for (int j = 0; j < PER; j++) {
+    const unsigned lr = threadIdx.x + j * NT;
+    int e = 0;
+    if (lr < nrow) {
+      const i64 slice = s0 + (lr >> 5), row = (i64)r0 + lr;
+      const int lane = lr & 31;
+      const i64 b = T.slice_ptr[slice];
+      const int wd = (int)(T.slice_ptr[slice + 1] - b);
+      unsigned short ix[8];
+      double v[IT_NV];
+#pragma unroll
+      for (int k = 0; k < 8; k++) ix[k] = (unsigned short)MAXROWS;
+#pragma unroll
+      for (int k = 0; k < IT_NV; k++) v[k] = 0.0;
+      int slot = 0;
+      for (int k = 0; k < wd && slot < IT_NV; k++) {
+        const i32 c = T.col[(b + k) * 32 + lane];
+        if (c < 0) continue;
+        v[slot] = T.val[(b + k) * 32 + lane];
+        const unsigned lc = (unsigned)(c - r0);
+        if (lc < nrow) ix[slot] = (unsigned short)lc; else e++;
+        slot++;
+      }
+      unsigned char *rec = recs + (i64)IT_REC * lr;
+      *(uint4 *)rec = make_uint4(ix[0] | (ix[1] << 16), ix[2] | (ix[3] << 16), ix[4] | (ix[5] << 16), ix[6] | (ix[7] << 16));
+      double *rv = (double *)(rec + 16);
+#pragma unroll
+      for (int k = 0; k < IT_NV; k++) rv[k] = v[k];
+      rv[IT_NV] = dinv[row];
+      if (with_diag) dg[lr] = diag[row];
+      const int lv = row_lvl[row], lvp = lr ? (int)row_lvl[row - 1] : -1;
+      if (lv != lvp && lv < 255) ls[lv] = (unsigned short)lr;
+    }
+    if (lr < MAXROWS) { s_cnt[lr] = e; s_rowid[lr] = e > 0; }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {   // tiles are small: a serial prefix is fine at setup
+    int a = 0, b2 = 0;
+    for (unsigned i = 0; i < nrow; i++) { const int c = s_cnt[i], f = s_rowid[i]; s_cnt[i] = a; s_rowid[i] = b2; a += c; b2 += f; }
+    s_cnt[nrow] = a; s_rowid[nrow] = b2;
+  }
+  __syncthreads();
+  // external lists
+#pragma unroll
+  for (int j = 0; j < PER; j++) {
+    const unsigned lr = threadIdx.x + j * NT;
+    if (lr >= nrow) continue;
+    const int first = s_cnt[lr], cnt = s_cnt[lr + 1] - first;
+    if (!cnt) continue;
+    const int xr = s_rowid[lr];
+    xrows[xr * 4 + 0] = (unsigned short)lr; xrows[xr * 4 + 1] = (unsigned short)first; xrows[xr * 4 + 2] = (unsigned short)cnt; xrows[xr * 4 + 3] = 0;
+    const i64 slice = s0 + (lr >> 5);
+    const int lane = lr & 31;
+    const i64 b = T.slice_ptr[slice];
+    const int wd = (int)(T.slice_ptr[slice + 1] - b);
+    int slot = 0, o = first;
+    for (int k = 0; k < wd && slot < IT_NV; k++) {
+      const i32 c = T.col[(b + k) * 32 + lane];
+      if (c < 0) continue;
+      if ((unsigned)(c - r0) >= nrow) { xent[2 * o] = c; xent[2 * o + 1] = slot; o++; }
+      slot++;
+    }
+  }
+}
+
+struct ITileParams {
+  i32 ntiles;
+  int backward;
+  const ITileMeta *meta;
+  const unsigned char *img;
+  const i32 *dep;
+  int *done;
+  unsigned sleep_ns, repoll_ns;
+  int cap_bytes;             // largest image (bytes)
+  int *err;
+  unsigned long long *trace;
+};
+
+// shared memory: [ header 128: mbarrier | xs (+ zero slot) | acc | aux | image ]
+__host__ __device__ inline size_t itile_smem_bytes(int maxrows, int cap_bytes) { return 128 + ((size_t)maxrows + 16) * 8 + 2 * (size_t)maxrows * 8 + (size_t)cap_bytes; }
+
+template <int NT, int MAXROWS, bool ADD_SELF, bool WRITE_R, int MINB>
+__global__ void __launch_bounds__(NT, MINB) k_gs_itile(const double *rin, const double *__restrict__ self, double *out, double *rout, ITileParams p)
+{
+  constexpr int NW = NT / 32;
+  constexpr unsigned ZERO = MAXROWS;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  int tid;
+  asm volatile("mov.u32 %0, %%tid.x;" : "=r"(tid));
+  const int lane = tid & 31, w = tid >> 5;
+  uint32_t smem_base;
+  asm volatile("mov.u32 %0, %1;" : "=r"(smem_base) : "r"(smem_u32(smem_raw)));
+  const uint32_t bar = smem_base;
+  const uint32_t xs_a = smem_base + 128, acc_a = xs_a + (MAXROWS + 16) * 8, aux_a = acc_a + MAXROWS * 8, img_a = aux_a + MAXROWS * 8;
+  if (tid == 0) { mbar_init(bar, 1); mbar_fence_init(); sts_f64(xs_a + ZERO * 8u, 0.0); }
+  __syncthreads();
+  auto tile_of = [&](i32 q) { return p.backward ? (p.ntiles - 1 - q) : q; };
+  auto fetch = [&](const ITileMeta &m) {   // one thread: the image, the tile's rows of rin (-> acc) and of self (-> aux)
+    const uint32_t vb = (uint32_t)m.nrow * 8u;
+    mbar_expect_tx(bar, (uint32_t)m.bytes + vb + (ADD_SELF ? vb : 0u));
+    bulk_g2s(img_a, p.img + m.img, (uint32_t)m.bytes, bar);
+    bulk_g2s(acc_a, rin + m.r0, vb, bar);
+    if (ADD_SELF) bulk_g2s(aux_a, self + m.r0, vb, bar);
+  };
+  const ITileMeta none{0, 0, 0, 0, 0, 0, 0};
+  uint32_t phase = 0;
+  i32 q = blockIdx.x;
+  if (q >= p.ntiles) return;
+  ITileMeta cur = p.meta[tile_of(q)];
+  i32 cur_dep = (tid < cur.nd) ? p.dep[cur.d0 + tid] : -1;
+  if (tid == 0) fetch(cur);
+  int solver = (int)(blockIdx.x % NW);
+  for (; q < p.ntiles; q += gridDim.x) {
+    const i32 t = tile_of(q);
+    unsigned long long *tr = (p.trace && tid == 0) ? p.trace + (size_t)t * 16 : nullptr;
+    if (tr) tr[0] = gtimer();
+    const i32 qn = q + (i32)gridDim.x;
+    const bool more = qn < p.ntiles;
+    const ITileMeta nxt = more ? p.meta[tile_of(qn)] : none;
+    const i32 r0 = cur.r0;
+    // ---- hint flags of the tiles this one depends on
+    for (int k = tid; k < cur.nd; k += NT) {
+      const int *f = p.done + ((k < NT) ? cur_dep : p.dep[cur.d0 + k]);
+      unsigned spins = 0;
+      while (ld_relaxed_i32(f) == 0) {
+        if (p.sleep_ns) __nanosleep(p.sleep_ns);
+        if (spin_fail(spins, p.err)) break;
+      }
+    }
+    if (tr) tr[1] = gtimer();
+    mbar_wait(bar, phase);
+    phase ^= 1u;
+    __syncthreads();
+    if (tr) tr[2] = gtimer();
+    // ---- the image
+    const uint4 hw = lds_v4(img_a);
+    const int nlev = hw.x & 0xffff, nreal = hw.x >> 16, nrow = hw.y & 0xffff, nxr = hw.y >> 16;
+    const uint32_t ls_a = img_a + 16, rec_a = ls_a + (hw.z >> 16);
+    const uint32_t dg_a = rec_a + (uint32_t)nrow * IT_REC;
+    const uint32_t xr_a = dg_a + (WRITE_R ? (uint32_t)nrow * 8u : 0u);
+    const uint32_t xe_a = xr_a + (uint32_t)nxr * 8u;
+    // ---- couplings to rows of other tiles: one thread per external row, all its polls in flight together; the data is the flag
+#pragma unroll 1
+    for (int er = tid; er < nxr; er += NT) {
+      const uint32_t e0 = lds_i32(xr_a + (uint32_t)er * 8u), e1 = lds_i32(xr_a + (uint32_t)er * 8u + 4u);
+      const uint32_t row = e0 & 0xffffu, first = e0 >> 16, cnt = e1 & 0xffffu;
+      i32 c[IT_NV], sl[IT_NV];
+      double x[IT_NV];
+#pragma unroll
+      for (int i = 0; i < IT_NV; i++) {
+        c[i] = (i < (int)cnt) ? lds_i32(xe_a + (first + i) * 8u) : -1;
+        sl[i] = (i < (int)cnt) ? lds_i32(xe_a + (first + i) * 8u + 4u) : 0;
+      }
+      unsigned spins = 0;
+      bool missing;
+#pragma unroll 1
+      do {
+        missing = false;
+#pragma unroll
+        for (int i = 0; i < IT_NV; i++) x[i] = (c[i] >= 0) ? ld_poll_relaxed(out + c[i]) : 0.0;
+#pragma unroll
+        for (int i = 0; i < IT_NV; i++) missing |= is_sentinel(x[i]);
+        if (missing) {
+          if (p.repoll_ns) __nanosleep(p.repoll_ns);
+          if (spin_fail(spins, p.err)) break;
+        }
+      } while (missing);
+      double a = lds_f64(acc_a + row * 8u);
+#pragma unroll
+      for (int i = 0; i < IT_NV; i++)
+        if (i < (int)cnt) a = fma(-lds_f64(rec_a + row * IT_REC + 16u + (uint32_t)sl[i] * 8u), x[i], a);
+      sts_f64(acc_a + row * 8u, a);
+    }
+    if (tr) tr[3] = gtimer();
+    const i32 nxt_dep = (more && tid < nxt.nd) ? p.dep[nxt.d0 + tid] : -1;
+    __syncthreads();
+    // ---- the tile itself: the solver warp (role rotates over the warps = schedulers) walks the local levels
+    if (w == solver) {
+#pragma unroll 1
+      for (int it = 0; it < nlev; it++) {
+        const int s = p.backward ? (nlev - 1 - it) : it;
+        const int rb = (int)lds_u16(ls_a + (uint32_t)s * 2u), re = (int)lds_u16(ls_a + (uint32_t)(s + 1) * 2u);
+#pragma unroll 1
+        for (int rr = rb; rr < re; rr += 32) {
+          const int r = rr + lane;
+          const bool act = r < re;
+          const uint32_t rc = (uint32_t)(act ? r : rb);
+          const uint32_t ra = rec_a + rc * IT_REC;
+          const uint4 iw = lds_v4(ra), q1 = lds_v4(ra + 16), q2 = lds_v4(ra + 32), q3 = lds_v4(ra + 48), q4 = lds_v4(ra + 64);
+          double a = lds_f64(acc_a + rc * 8u), a2 = 0.0;
+          const double ax = ADD_SELF ? lds_f64(aux_a + rc * 8u) : (WRITE_R ? lds_f64(dg_a + rc * 8u) : 0.0);
+          const double v0 = __hiloint2double(q1.y, q1.x), v1 = __hiloint2double(q1.w, q1.z), v2 = __hiloint2double(q2.y, q2.x),
+                       v3 = __hiloint2double(q2.w, q2.z), v4 = __hiloint2double(q3.y, q3.x), v5 = __hiloint2double(q3.w, q3.z),
+                       v6 = __hiloint2double(q4.y, q4.x), dvv = __hiloint2double(q4.w, q4.z);
+          const double x0 = lds_f64(xs_a + (iw.x & 0xffffu) * 8u), x1 = lds_f64(xs_a + (iw.x >> 16) * 8u), x2 = lds_f64(xs_a + (iw.y & 0xffffu) * 8u),
+                       x3 = lds_f64(xs_a + (iw.y >> 16) * 8u), x4 = lds_f64(xs_a + (iw.z & 0xffffu) * 8u), x5 = lds_f64(xs_a + (iw.z >> 16) * 8u),
+                       x6 = lds_f64(xs_a + (iw.w & 0xffffu) * 8u);
+          a = fma(-v0, x0, a); a2 = fma(-v1, x1, a2); a = fma(-v2, x2, a); a2 = fma(-v3, x3, a2);
+          a = fma(-v4, x4, a); a2 = fma(-v5, x5, a2); a = fma(-v6, x6, a);
+          a += a2;
+          const double d = dvv * a;
+          if (act) {
+            sts_f64(xs_a + (uint32_t)r * 8u, ADD_SELF ? ax + d : d);
+            if (WRITE_R) sts_f64(acc_a + (uint32_t)r * 8u, fma(-ax, d, a));
+          }
+        }
+        __syncwarp();
+      }
+    }
+    __syncthreads();
+    if (tr) tr[4] = gtimer();
+    // ---- publish: coalesced stores; padding rows are never updated, but `out` must not keep the sentinel
+    for (int lr = tid; lr < nrow; lr += NT) {
+      const i64 row = (i64)r0 + lr;
+      const bool real = lr < nreal;
+      __stcg(out + row, real ? lds_f64(xs_a + (uint32_t)lr * 8u) : (ADD_SELF ? lds_f64(aux_a + (uint32_t)lr * 8u) : 0.0));
+      if (WRITE_R) rout[row] = lds_f64(acc_a + (uint32_t)lr * 8u);
+    }
+    if (tid == 0) st_relaxed_i32(p.done + t, 1);
+    if (tr) {
+      unsigned smid;
+      asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+      tr[5] = gtimer();
+      tr[6] = (unsigned long long)smid | ((unsigned long long)blockIdx.x << 16) | ((unsigned long long)nlev << 40) | ((unsigned long long)(nrow / 32) << 52);
+    }
+    __syncthreads();     // image, xs, acc, aux are free again
+    if (more && tid == 0) fetch(nxt);
+    cur = nxt;
+    cur_dep = nxt_dep;
+    solver = (solver + 1) % NW;
+  }
+}
+
+}  // namespace ngb

@@ -468,16 +468,18 @@ def test_regularised_coarse_solve_with_a_lone_vertex():
         ng.elast_3d(A, p["free"], vertex_xyz=p["xyz"], prolongations=[P0], ngs_amg_regularize_cmats=False)
 
 
-@pytest.mark.parametrize("rows,n,nbuf", [(32, 21, 1), (64, 21, 1), (256, 29, 1), (512, 33, 1), (256, 31, 2), (512, 35, 2)])
-def test_tile_sweep(rows, n, nbuf):
+@pytest.mark.parametrize("rows,n,nbuf,image", [(32, 21, 1, 0), (64, 21, 1, 0), (256, 29, 1, 0), (512, 33, 1, 0), (256, 31, 2, 0), (512, 35, 2, 0),
+                                                (256, 33, 1, 1), (512, 37, 1, 1), (256, 24, 1, 1)])
+def test_tile_sweep(rows, n, nbuf, image):
     """ngs_amg_b200_tile_sweep: the triangular half-sweeps on the two-level tile schedule -- one warp per tile (kernels_tile.cuh, 32/64
-    rows) or one CTA per tile with the matrix slab fetched by bulk copies (kernels_ctile.cuh, 256/512 rows) -- must reproduce the
+    rows), one CTA per tile with the matrix slab fetched by bulk copies (kernels_ctile.cuh, 256/512 rows), or the same on tile images
+    prepared at setup (kernels_itile.cuh, image=1: the default for matrices with <= 7 entries per row and triangle) -- must reproduce the
     reference's sequential sweep like the row-level kernels do: same bars as everywhere else, forward and backward (V-cycle + PCG)"""
     p, A = poisson(n)
     base = dict(ngs_amg_max_coarse_size=20)
     pc0 = ng.h1_scal(A, p["free"], **base)
     pc = ng.h1_scal(A, p["free"], prolongations=pc0.GetMap(), ngs_amg_b200_tile_sweep=True, ngs_amg_b200_tile_min_rows=0,
-                    ngs_amg_b200_tile_min_depth=0, ngs_amg_b200_tile_rows=rows, ngs_amg_b200_tile_nbuf=nbuf, **base)
+                    ngs_amg_b200_tile_min_depth=0, ngs_amg_b200_tile_rows=rows, ngs_amg_b200_tile_nbuf=nbuf, ngs_amg_b200_tile_image=image, **base)
     amg = O.OracleAMG(to_oracle(A), p["free"], [to_oracle(P) for P in pc0.GetMap()])
     for seed in (1, 2, 3):
         b = rand(seed, p["n"])
