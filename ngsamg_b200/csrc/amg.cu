@@ -774,7 +774,7 @@ static CTileKernel ctile_kernel(int maxs, int nbuf, bool add_self)
 using ITileKernel = void (*)(const double *, const double *, double *, double *, ITileParams);
 static ITileKernel itile_kernel(int maxs, bool add_self)
 {
-  if (maxs <= 8) return add_self ? (ITileKernel)k_gs_itile<128, 256, true, false, 6> : (ITileKernel)k_gs_itile<128, 256, false, true, 6>;
+  if (maxs <= 8) return add_self ? (ITileKernel)k_gs_itile<128, 256, true, false, 7> : (ITileKernel)k_gs_itile<128, 256, false, true, 7>;
   return add_self ? (ITileKernel)k_gs_itile<128, 512, true, false, 3> : (ITileKernel)k_gs_itile<128, 512, false, true, 3>;
 }
 

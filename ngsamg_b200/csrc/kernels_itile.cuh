@@ -172,6 +172,12 @@ __global__ void __launch_bounds__(128) k_img_fill(i32 ntiles, const i32 *__restr
   }
 }
 
+// bulk L2 prefetch (no shared-memory destination): the next tile's image is on its way to L2 while the current tile is swept
+__device__ __forceinline__ void bulk_prefetch_l2(const void *src, uint32_t bytes)
+{
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
+}
+
 struct ITileParams {
   i32 ntiles;
   int backward;
@@ -227,6 +233,12 @@ __global__ void __launch_bounds__(NT, MINB) k_gs_itile(const double *rin, const 
     const bool more = qn < p.ntiles;
     const ITileMeta nxt = more ? p.meta[tile_of(qn)] : none;
     const i32 r0 = cur.r0;
+    if (more && tid == 0) {
+      // the slab in shared memory is busy until this tile is done: stage the next tile's bytes in L2 meanwhile
+      bulk_prefetch_l2(p.img + nxt.img, (uint32_t)nxt.bytes);
+      bulk_prefetch_l2(rin + nxt.r0, (uint32_t)nxt.nrow * 8u);
+      if (ADD_SELF) bulk_prefetch_l2(self + nxt.r0, (uint32_t)nxt.nrow * 8u);
+    }
     // ---- hint flags of the tiles this one depends on
     for (int k = tid; k < cur.nd; k += NT) {
       const int *f = p.done + ((k < NT) ? cur_dep : p.dep[cur.d0 + k]);
