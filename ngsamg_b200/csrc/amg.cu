@@ -229,6 +229,7 @@ struct Amg {
   double tri_gate_gap_levels = 0.0;
   unsigned tri_repoll_ns = 0;
   int tri_pollmode = 0;
+  int itile_minb = 6;             // CTAs per SM the 256-row tile-image kernel is compiled for (6: no spills, 7: 72 registers)
   i64 spmv_small_rows = 200000;   // levels with fewer rows use the warp-per-row SpMV
   int tri_regate = 1;
   int tri_split = 0;
@@ -772,9 +773,12 @@ static CTileKernel ctile_kernel(int maxs, int nbuf, bool add_self)
   return add_self ? (CTileKernel)k_gs_ctile<256, 16, 2, true, false, 3> : (CTileKernel)k_gs_ctile<256, 16, 2, false, true, 3>;
 }
 using ITileKernel = void (*)(const double *, const double *, double *, double *, ITileParams);
-static ITileKernel itile_kernel(int maxs, bool add_self)
+static ITileKernel itile_kernel(int maxs, bool add_self, int minb)
 {
-  if (maxs <= 8) return add_self ? (ITileKernel)k_gs_itile<128, 256, true, false, 7> : (ITileKernel)k_gs_itile<128, 256, false, true, 7>;
+  if (maxs <= 8) {
+    if (minb >= 7) return add_self ? (ITileKernel)k_gs_itile<128, 256, true, false, 7> : (ITileKernel)k_gs_itile<128, 256, false, true, 7>;
+    return add_self ? (ITileKernel)k_gs_itile<128, 256, true, false, 6> : (ITileKernel)k_gs_itile<128, 256, false, true, 6>;
+  }
   return add_self ? (ITileKernel)k_gs_itile<128, 512, true, false, 3> : (ITileKernel)k_gs_itile<128, 512, false, true, 3>;
 }
 
@@ -934,12 +938,12 @@ bool Amg::prepare_itile(Level &L)
   NGB_CUDA(cudaDeviceGetAttribute(&dev_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
   if (L.itile_smem > (size_t)dev_max) { for (int d = 0; d < 2; d++) { dev_free(L.d_img[d]); dev_free(L.d_imeta[d]); } return false; }
   for (int as = 0; as < 2; as++) {
-    ITileKernel k = itile_kernel(L.tile_maxs, as == 1);
+    ITileKernel k = itile_kernel(L.tile_maxs, as == 1, itile_minb);
     {
       static std::mutex mu;
-      static size_t granted[2][2] = {};
+      static size_t granted[3][2] = {};
       std::lock_guard<std::mutex> guard(mu);
-      size_t &g = granted[L.tile_maxs <= 8 ? 0 : 1][as];
+      size_t &g = granted[L.tile_maxs <= 8 ? (itile_minb >= 7 ? 2 : 0) : 1][as];
       g = std::max(g, L.itile_smem);
       NGB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g));
     }
@@ -1692,7 +1696,7 @@ void Amg::tri(Level &L, bool backward, bool add_self, bool write_r, const double
       if (L.itile) {
         ITileParams ip{(i32)L.ntiles, backward ? 1 : 0, L.d_imeta[backward ? 1 : 0], L.d_img[backward ? 1 : 0], backward ? L.d_tile_succ : L.d_tile_pred,
                        L.d_tile_done, tri_sleep_ns, tri_repoll_ns, L.itile_cap, d_err, tri_trace};
-        launch_resident_smem(itile_kernel(L.tile_maxs, add_self), L.itile_grid[add_self ? 1 : 0], 128, L.itile_smem, st, rin, self, out, rout, ip);
+        launch_resident_smem(itile_kernel(L.tile_maxs, add_self, itile_minb), L.itile_grid[add_self ? 1 : 0], 128, L.itile_smem, st, rin, self, out, rout, ip);
         launches += 2;
         return;
       }
@@ -2377,6 +2381,7 @@ static void create_impl(const char *type, const ngsamg_csr *A, const uint8_t *fr
   a.tri_split = (int)a.flags.num("b200_tri_split", 0);
   a.spmv_small_rows = (i64)a.flags.num("b200_spmv_small_rows", 200000);
   a.tri_pollmode = (int)a.flags.num("b200_tri_pollmode", 0);
+  a.itile_minb = (int)a.flags.num("b200_tile_minb", 6);
   auto L = std::make_unique<Level>();
   copy_csr(A, L->hA);
   if (free_mask) {
