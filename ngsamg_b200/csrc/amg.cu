@@ -229,7 +229,7 @@ struct Amg {
   double tri_gate_gap_levels = 0.0;
   unsigned tri_repoll_ns = 0;
   int tri_pollmode = 0;
-  int itile_minb = 6;             // CTAs per SM the 256-row tile-image kernel is compiled for (6: no spills, 7: 72 registers)
+  int itile_minb = 7;             // CTAs per SM the 256-row tile-image kernel is compiled for (6: no spills, 7: 72 registers)
   i64 spmv_small_rows = 200000;   // levels with fewer rows use the warp-per-row SpMV
   int tri_regate = 1;
   int tri_split = 0;
@@ -2381,7 +2381,7 @@ static void create_impl(const char *type, const ngsamg_csr *A, const uint8_t *fr
   a.tri_split = (int)a.flags.num("b200_tri_split", 0);
   a.spmv_small_rows = (i64)a.flags.num("b200_spmv_small_rows", 200000);
   a.tri_pollmode = (int)a.flags.num("b200_tri_pollmode", 0);
-  a.itile_minb = (int)a.flags.num("b200_tile_minb", 6);
+  a.itile_minb = (int)a.flags.num("b200_tile_minb", 7);
   auto L = std::make_unique<Level>();
   copy_csr(A, L->hA);
   if (free_mask) {

@@ -295,57 +295,38 @@ __global__ void __launch_bounds__(NT, MINB) k_gs_itile(const double *rin, const 
     if (tr) tr[3] = gtimer();
     const i32 nxt_dep = (more && tid < nxt.nd) ? p.dep[nxt.d0 + tid] : -1;
     __syncthreads();
-    // ---- the tile itself: the solver warp (role rotates over the warps = schedulers) walks the local levels.  Software pipeline: the
-    // record of the NEXT item (a level, or 32 rows of a wide level) is loaded while the current one waits for its gathers and FMA chain;
-    // only  xs gather -> FMAs -> store -> __syncwarp  is serial.
-    if (w == solver && nlev > 0) {
-      struct Item { int r, re_, s; bool act; uint4 iw, q1, q2, q3, q4; double a, ax; };
-      int s_it = 0;                                                    // levels consumed by the item generator
-      int lvl = p.backward ? nlev - 1 : 0;
-      int rb = (int)lds_u16(ls_a + (uint32_t)lvl * 2u), re = (int)lds_u16(ls_a + (uint32_t)(lvl + 1) * 2u), rr = rb;
-      auto load = [&](Item &o) -> bool {                               // next item in sweep order; false = no more
-        while (rr >= re) {
-          if (++s_it >= nlev) return false;
-          lvl = p.backward ? nlev - 1 - s_it : s_it;
-          rb = (int)lds_u16(ls_a + (uint32_t)lvl * 2u); re = (int)lds_u16(ls_a + (uint32_t)(lvl + 1) * 2u); rr = rb;
-        }
-        o.r = rr + lane; o.act = o.r < re; o.s = lvl; o.re_ = re;
-        const uint32_t rc = (uint32_t)(o.act ? o.r : rr);
-        const uint32_t ra = rec_a + rc * IT_REC;
-        o.iw = lds_v4(ra); o.q1 = lds_v4(ra + 16); o.q2 = lds_v4(ra + 32); o.q3 = lds_v4(ra + 48); o.q4 = lds_v4(ra + 64);
-        o.a = lds_f64(acc_a + rc * 8u);
-        o.ax = ADD_SELF ? lds_f64(aux_a + rc * 8u) : (WRITE_R ? lds_f64(dg_a + rc * 8u) : 0.0);
-        rr += 32;
-        return true;
-      };
-      auto compute = [&](const Item &o, bool last_of_level) {
-        const double x0 = lds_f64(xs_a + (o.iw.x & 0xffffu) * 8u), x1 = lds_f64(xs_a + (o.iw.x >> 16) * 8u), x2 = lds_f64(xs_a + (o.iw.y & 0xffffu) * 8u),
-                     x3 = lds_f64(xs_a + (o.iw.y >> 16) * 8u), x4 = lds_f64(xs_a + (o.iw.z & 0xffffu) * 8u), x5 = lds_f64(xs_a + (o.iw.z >> 16) * 8u),
-                     x6 = lds_f64(xs_a + (o.iw.w & 0xffffu) * 8u);
-        const double v0 = __hiloint2double(o.q1.y, o.q1.x), v1 = __hiloint2double(o.q1.w, o.q1.z), v2 = __hiloint2double(o.q2.y, o.q2.x),
-                     v3 = __hiloint2double(o.q2.w, o.q2.z), v4 = __hiloint2double(o.q3.y, o.q3.x), v5 = __hiloint2double(o.q3.w, o.q3.z),
-                     v6 = __hiloint2double(o.q4.y, o.q4.x), dvv = __hiloint2double(o.q4.w, o.q4.z);
-        double a = o.a, a2, a3;
-        a = fma(-v0, x0, a); a2 = -v1 * x1; a3 = -v2 * x2;
-        a = fma(-v3, x3, a); a2 = fma(-v4, x4, a2); a3 = fma(-v5, x5, a3);
-        a = fma(-v6, x6, a);
-        a += a2 + a3;
-        const double d = dvv * a;
-        if (o.act) {
-          sts_f64(xs_a + (uint32_t)o.r * 8u, ADD_SELF ? o.ax + d : d);
-          if (WRITE_R) sts_f64(acc_a + (uint32_t)o.r * 8u, fma(-o.ax, d, a));
-        }
-        if (last_of_level) __syncwarp();
-      };
-      Item A, B;
-      bool hasA = load(A), hasB;
+    // ---- the tile itself: the solver warp (role rotates over the warps = schedulers) walks the local levels
+    // (a software-pipelined variant -- next item's record loaded during the FMA chain -- was measured SLOWER: 1.60 vs 1.35 ms, registers)
+    if (w == solver) {
 #pragma unroll 1
-      while (hasA) {
-        hasB = load(B);
-        compute(A, !hasB || B.s != A.s);
-        if (!hasB) break;
-        hasA = load(A);
-        compute(B, !hasA || A.s != B.s);
+      for (int it = 0; it < nlev; it++) {
+        const int s = p.backward ? (nlev - 1 - it) : it;
+        const int rb = (int)lds_u16(ls_a + (uint32_t)s * 2u), re = (int)lds_u16(ls_a + (uint32_t)(s + 1) * 2u);
+#pragma unroll 1
+        for (int rr = rb; rr < re; rr += 32) {
+          const int r = rr + lane;
+          const bool act = r < re;
+          const uint32_t rc = (uint32_t)(act ? r : rb);
+          const uint32_t ra = rec_a + rc * IT_REC;
+          const uint4 iw = lds_v4(ra), q1 = lds_v4(ra + 16), q2 = lds_v4(ra + 32), q3 = lds_v4(ra + 48), q4 = lds_v4(ra + 64);
+          double a = lds_f64(acc_a + rc * 8u), a2 = 0.0;
+          const double ax = ADD_SELF ? lds_f64(aux_a + rc * 8u) : (WRITE_R ? lds_f64(dg_a + rc * 8u) : 0.0);
+          const double v0 = __hiloint2double(q1.y, q1.x), v1 = __hiloint2double(q1.w, q1.z), v2 = __hiloint2double(q2.y, q2.x),
+                       v3 = __hiloint2double(q2.w, q2.z), v4 = __hiloint2double(q3.y, q3.x), v5 = __hiloint2double(q3.w, q3.z),
+                       v6 = __hiloint2double(q4.y, q4.x), dvv = __hiloint2double(q4.w, q4.z);
+          const double x0 = lds_f64(xs_a + (iw.x & 0xffffu) * 8u), x1 = lds_f64(xs_a + (iw.x >> 16) * 8u), x2 = lds_f64(xs_a + (iw.y & 0xffffu) * 8u),
+                       x3 = lds_f64(xs_a + (iw.y >> 16) * 8u), x4 = lds_f64(xs_a + (iw.z & 0xffffu) * 8u), x5 = lds_f64(xs_a + (iw.z >> 16) * 8u),
+                       x6 = lds_f64(xs_a + (iw.w & 0xffffu) * 8u);
+          a = fma(-v0, x0, a); a2 = fma(-v1, x1, a2); a = fma(-v2, x2, a); a2 = fma(-v3, x3, a2);
+          a = fma(-v4, x4, a); a2 = fma(-v5, x5, a2); a = fma(-v6, x6, a);
+          a += a2;
+          const double d = dvv * a;
+          if (act) {
+            sts_f64(xs_a + (uint32_t)r * 8u, ADD_SELF ? ax + d : d);
+            if (WRITE_R) sts_f64(acc_a + (uint32_t)r * 8u, fma(-ax, d, a));
+          }
+        }
+        __syncwarp();
       }
     }
     __syncthreads();
