@@ -108,6 +108,39 @@ def test_parallel_vcycle_and_pcg_match_oracle(grid):
         assert rel(sol[r][0], xg[parts[r]["gidx"]]) < 1e-6
 
 
+@pytest.mark.parametrize("grid,rows,image", [((1, 1, 2), 256, 1), ((2, 2, 2), 256, 1), ((1, 2, 2), 512, 0)])
+def test_parallel_tiled_sweeps_match_oracle(grid, rows, image):
+    """the distributed levels swept on the two-level tile schedule (hybrid stage order LOC_PART_1 | EX_PART | LOC_PART_2 as the sweep order
+    of the tiles; CTA-per-tile kernels, with and without prepared tile images): same bars as the row-level sweeps"""
+    dims = (19, 17, 21)
+    parts = S.partition_poisson3d(*dims, grid=grid)
+    R = len(parts)
+    pcs = _build_ranks(parts, par.h1_scal_par, 1, ngs_amg_max_coarse_size=15, ngs_amg_b200_ctr_nv=300, ngs_amg_b200_tile_min_rows=0,
+                       ngs_amg_b200_tile_min_depth=0, ngs_amg_b200_tile_rows=rows, ngs_amg_b200_tile_image=image)
+    amg, npar = _oracle_for(parts, pcs, 1)
+    assert npar >= 1
+    b = [rand(70 + r, p["n"]) * p["free"] for r, p in enumerate(parts)]
+    xo = amg.apply(b)
+
+    def ap(r, pc):
+        x = np.zeros(parts[r]["n"])
+        pc.Mult(b[r], x)
+        return x
+
+    got = _collective(pcs, ap)
+    for r in range(R):
+        assert rel(got[r], xo[r]) < TOL_VCYCLE, (r, rel(got[r], xo[r]))
+    rhs = [p["rhs"] * p["free"] for p in parts]
+    _, ito, _ = amg.pcg(rhs, tol=1e-8, maxsteps=100)
+
+    def solve(r, pc):
+        x = np.zeros(parts[r]["n"])
+        it, _ = pc._pcg(rhs[r], x, 1e-8, 100)
+        return it
+
+    assert all(it == ito for it in _collective(pcs, solve))
+
+
 def test_parallel_elasticity_matches_oracle():
     parts = S.partition_elasticity3d(9, 5, 9, 2)
     pcs = _build_ranks(parts, par.elast_3d_par, 3, ngs_amg_max_coarse_size=10, ngs_amg_b200_ctr_nv=60)
