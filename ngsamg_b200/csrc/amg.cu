@@ -493,7 +493,8 @@ bool dense_invert(int n, std::vector<double> &a)
 // `fixed` (optional): rows that keep their number (the shared dofs of a distributed level: their relative order must stay the
 // same on every sharer and the exchange lists ascending, the ParallelDofs contract of dcc_map.cpp:494-543); the other rows are dealt
 // colour-major into the remaining numbers.
-void greedy_coloring_perm(const HostBsr &A, std::vector<i32> &perm, int &ncolors, const std::vector<uint8_t> *fixed = nullptr)
+void greedy_coloring_perm(const HostBsr &A, std::vector<i32> &perm, int &ncolors, const std::vector<uint8_t> *fixed = nullptr,
+                          std::vector<i32> *color_out = nullptr)
 {
   const i64 n = A.nrows;
   std::vector<i32> color(n, -1);
@@ -535,6 +536,35 @@ void greedy_coloring_perm(const HostBsr &A, std::vector<i32> &perm, int &ncolors
   for (i32 o : order) {
     if ((*fixed)[o]) perm[o] = o;
     else perm[o] = slots[q++];
+  }
+  if (color_out) color_out->swap(color);
+}
+
+// Numbering of a DISTRIBUTED coarse level.  Interior dofs: colour-major (as on one rank).  Shared dofs must keep the ParallelDofs contract
+// (dcc_map.cpp:494-543: exchange lists ascending, k-th entry here == k-th entry on the neighbour), so they stay inside the block of their
+// sharing class -- the blocks keep their places -- and are ordered INSIDE the block by the colour their MASTER gave them (sent to the
+// other sharers once at setup), ties by the old, canonical order: the same order on every sharer, and the master's EX stage
+// (hybrid_base_smoother.cpp:508-573) sweeps class after class, colour after colour instead of along the canonical numbering of a whole
+// interface (dependency depth ~800 on a 3.7 M-row level).
+void parallel_coloring_perm(const Comm &comm, const ParDofs &pd, const HostBsr &A, std::vector<i32> &perm, int &ncolors)
+{
+  const i64 n = A.nrows;
+  std::vector<uint8_t> keep(n, 0);
+  for (i64 i = 0; i < n; i++) keep[i] = pd.eqc[i] != 0;
+  std::vector<i32> color;
+  greedy_coloring_perm(A, perm, ncolors, &keep, &color);          // interior done; shared: identity so far
+  std::vector<double> mc(n, 0.0);
+  for (i64 i = 0; i < n; i++) if (keep[i] && pd.is_master(i)) mc[i] = (double)color[i];
+  allreduce_dof_data(comm, pd, 1, mc);                            // every sharer learns the master's colour (the others contribute 0)
+  // members of every class in old order = the slots of the class block
+  const size_t ncls = pd.sharers.size();
+  std::vector<std::vector<i32>> members(ncls);
+  for (i64 i = 0; i < n; i++) if (keep[i]) members[pd.eqc[i]].push_back((i32)i);
+  for (size_t c = 1; c < ncls; c++) {
+    const std::vector<i32> &slots = members[c];
+    std::vector<i32> ord(slots);
+    std::stable_sort(ord.begin(), ord.end(), [&](i32 x, i32 y) { return mc[x] < mc[y]; });
+    for (size_t k = 0; k < ord.size(); k++) perm[ord[k]] = slots[k];
   }
 }
 
@@ -1592,10 +1622,8 @@ void Amg::finalize_parallel()
       auto h1 = std::chrono::steady_clock::now();
       std::vector<i32> cperm;
       int ncol = 0;
-      // shared coarse dofs keep their (class-major, canonical) numbers: only the interior is recoloured
-      std::vector<uint8_t> keep(C.hA.nrows, 0);
-      for (i64 i = 0; i < C.hA.nrows; i++) keep[i] = C.pd.eqc[i] != 0;
-      greedy_coloring_perm(C.hA, cperm, ncol, &keep);
+      // interior colour-major; shared dofs inside their class block by the master's colour (same order on every sharer)
+      parallel_coloring_perm(comm, C.pd, C.hA, cperm, ncol);
       permute_symmetric(C.hA, cperm);
       renumber_columns(L.hP, cperm);
       permute_pardofs(C.pd, cperm);

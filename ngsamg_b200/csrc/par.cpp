@@ -97,9 +97,10 @@ bool ParDofs::finer_or_equal(i32 a, i32 b) const
 
 void permute_pardofs(ParDofs &pd, const std::vector<i32> &perm)
 {
-  for (auto &l : pd.ex) for (i32 &d : l) d = perm[d];
-  for (auto &l : pd.m_ex) for (i32 &d : l) d = perm[d];
-  for (auto &l : pd.g_ex) for (i32 &d : l) d = perm[d];
+  // lists stay ascending; the renumbering must keep the relative order of two shared dofs the same on every sharer, then the sorted
+  // lists still pair up entry by entry
+  for (auto *ll : {&pd.ex, &pd.m_ex, &pd.g_ex})
+    for (auto &l : *ll) { for (i32 &d : l) d = perm[d]; std::sort(l.begin(), l.end()); }
   auto mv = [&](auto &v) {
     auto t = v;
     for (i64 i = 0; i < pd.n; i++) t[perm[i]] = v[i];
