@@ -917,28 +917,29 @@ bool Amg::prepare_itile(Level &L)
   if (!flags.flag("b200_tile_image", true)) return false;
   const i64 nt = L.ntiles;
   const int maxrows = L.tile_maxs * 32;
-  i32 *d_nxr = dev_alloc<i32>(nt), *d_nx = dev_alloc<i32>(nt), *d_max = dev_alloc<i32>(1);
+  i32 *d_nxr = dev_alloc<i32>(nt), *d_nx = dev_alloc<i32>(nt), *d_nov = dev_alloc<i32>(nt), *d_max = dev_alloc<i32>(1);
   i32 *d_nreal = upload_vec(L.h_tile_nreal, st);
-  std::vector<i32> nxr(nt), nx(nt);
+  std::vector<i32> nxr(nt), nx(nt), nov(nt);
   bool ok = true;
   for (int dir = 0; dir < 2 && ok; dir++) {
     const Sell &S = dir ? L.U : L.L;
     const std::vector<i64> &dp = dir ? L.h_succ_ptr : L.h_pred_ptr;
     NGB_CUDA(cudaMemsetAsync(d_max, 0, sizeof(i32), st));
-    k_img_count<<<(unsigned)nt, 128, 0, st>>>((i32)nt, L.d_tile_slice, S.view(), d_nxr, d_nx, d_max);
+    k_img_count<<<(unsigned)nt, 128, 0, st>>>((i32)nt, L.d_tile_slice, S.view(), d_nxr, d_nx, d_nov, d_max);
     i32 mx = 0;
     NGB_CUDA(cudaMemcpyAsync(&mx, d_max, sizeof(i32), cudaMemcpyDeviceToHost, st));
     NGB_CUDA(cudaMemcpyAsync(nxr.data(), d_nxr, sizeof(i32) * nt, cudaMemcpyDeviceToHost, st));
     NGB_CUDA(cudaMemcpyAsync(nx.data(), d_nx, sizeof(i32) * nt, cudaMemcpyDeviceToHost, st));
+    NGB_CUDA(cudaMemcpyAsync(nov.data(), d_nov, sizeof(i32) * nt, cudaMemcpyDeviceToHost, st));
     NGB_CUDA(cudaStreamSynchronize(st));
-    if (mx > IT_NV) { ok = false; break; }
+    if (mx > IT_NV + IT_MAXOVF) { ok = false; break; }
     std::vector<i64> off(nt + 1, 0);
     std::vector<ITileMeta> meta(nt);
     i64 cap = 0;
     for (i64 t = 0; t < nt; t++) {
       const int nrow = (L.h_tile_slice[t + 1] - L.h_tile_slice[t]) * 32;
-      const i64 b = itile_image_bytes(L.h_tile_nlev[t], nrow, nxr[t], nx[t], dir == 0);
-      if (nx[t] > 65535 || b > (i64)200 * 1024) { ok = false; break; }
+      const i64 b = itile_image_bytes(L.h_tile_nlev[t], nrow, nxr[t], nx[t], nov[t], dir == 0);
+      if (nx[t] > 65535 || nov[t] > 4095 || b > (i64)200 * 1024) { ok = false; break; }
       off[t + 1] = off[t] + b;
       cap = std::max(cap, b);
       meta[t] = ITileMeta{off[t], L.h_tile_slice[t] * 32, nrow, (i32)b, 0, (i32)dp[t], (i32)(dp[t + 1] - dp[t])};
@@ -949,16 +950,16 @@ bool Amg::prepare_itile(Level &L)
     L.img_bytes_total += off[nt];
     i64 *d_off = upload_vec(off, st);
     if (maxrows <= 256)
-      k_img_fill<256><<<(unsigned)nt, 128, 0, st>>>((i32)nt, L.d_tile_slice, L.d_tile_nlev, d_nreal, L.d_row_lvl, S.view(), L.dinv, L.diag, dir == 0 ? 1 : 0, d_off, d_nxr, d_nx, L.d_img[dir]);
+      k_img_fill<256><<<(unsigned)nt, 128, 0, st>>>((i32)nt, L.d_tile_slice, L.d_tile_nlev, d_nreal, L.d_row_lvl, S.view(), L.dinv, L.diag, dir == 0 ? 1 : 0, d_off, d_nxr, d_nx, d_nov, L.d_img[dir]);
     else
-      k_img_fill<512><<<(unsigned)nt, 128, 0, st>>>((i32)nt, L.d_tile_slice, L.d_tile_nlev, d_nreal, L.d_row_lvl, S.view(), L.dinv, L.diag, dir == 0 ? 1 : 0, d_off, d_nxr, d_nx, L.d_img[dir]);
+      k_img_fill<512><<<(unsigned)nt, 128, 0, st>>>((i32)nt, L.d_tile_slice, L.d_tile_nlev, d_nreal, L.d_row_lvl, S.view(), L.dinv, L.diag, dir == 0 ? 1 : 0, d_off, d_nxr, d_nx, d_nov, L.d_img[dir]);
     launches += 2;
     L.d_imeta[dir] = upload_vec(meta, st);
     NGB_CUDA(cudaStreamSynchronize(st));
     NGB_CUDA(cudaGetLastError());
     dev_free(d_off);
   }
-  dev_free(d_nxr); dev_free(d_nx); dev_free(d_max); dev_free(d_nreal);
+  dev_free(d_nxr); dev_free(d_nx); dev_free(d_nov); dev_free(d_max); dev_free(d_nreal);
   if (!ok) {
     for (int d = 0; d < 2; d++) { dev_free(L.d_img[d]); dev_free(L.d_imeta[d]); }
     return false;

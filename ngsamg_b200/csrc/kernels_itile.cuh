@@ -6,7 +6,8 @@
 // k_img_fill below): every tile gets a contiguous image in global memory, already in the layout the kernel wants in shared memory
 //
 //   header (16 B) | level starts (u16) | records: per row { 8 x u16 gather index | 7 values | dinv } = 80 B | [diag per row, forward only]
-//                 | external rows: { row, first entry, count } | external entries: { column, slot }
+//                 | external rows: { row, first entry, count } | external entries: { column, byte offset of the value }
+//                 | overflow entries { gather index, value } of rows with 8 .. 22 entries (hybrid stage order: rows next to an interface)
 //
 // so that a sweep fetches a tile with ONE bulk copy (+ one for the tile's rows of the right-hand side, + one for `self`), all on one
 // mbarrier, and no thread touches the matrix through the LSU.  Rows are sorted by tile-local level; a record is row-major (5 x LDS.128 per
@@ -20,6 +21,7 @@ namespace ngb {
 
 constexpr int IT_NV = 7;            // value slots per record
 constexpr int IT_REC = 80;          // bytes per record
+constexpr int IT_MAXOVF = 15;       // overflow entries per row (slot 7 of the index word: first overflow entry << 4 | count, 0xffff = none)
 
 struct __align__(16) ITileMeta {
   i64 img;       // byte offset of the tile's image
@@ -33,28 +35,29 @@ struct __align__(16) ITileMeta {
 
 struct ITileHeader {   // 16 bytes
   unsigned short nlev, nreal, nrow, n_ext_rows;
-  unsigned short n_ext, ls_bytes, has_diag, pad;
+  unsigned short n_ext, ls_bytes, has_diag, n_ovf;
 };
 
-__host__ __device__ inline i64 itile_image_bytes(int nlev, int nrow, int n_ext_rows, int n_ext, bool with_diag)
+__host__ __device__ inline i64 itile_image_bytes(int nlev, int nrow, int n_ext_rows, int n_ext, int n_ovf, bool with_diag)
 {
   const i64 ls = ((2 * (i64)(nlev + 1) + 15) / 16) * 16;
   i64 b = 16 + ls + (i64)IT_REC * nrow + (with_diag ? 8 * (i64)nrow : 0) + 8 * (i64)n_ext_rows + 8 * (i64)n_ext;
+  b = ((b + 15) / 16) * 16 + 16 * (i64)n_ovf;
   return ((b + 127) / 128) * 128;
 }
 
 // ---- setup: pass 1 -- external rows / entries per tile ------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) k_img_count(i32 ntiles, const i32 *__restrict__ tile_slice, SellView T, i32 *n_ext_rows, i32 *n_ext, i32 *maxlen)
+__global__ void __launch_bounds__(128) k_img_count(i32 ntiles, const i32 *__restrict__ tile_slice, SellView T, i32 *n_ext_rows, i32 *n_ext, i32 *n_ovf, i32 *maxlen)
 {
-  __shared__ int s_rows, s_ent, s_max;
+  __shared__ int s_rows, s_ent, s_max, s_ovf;
   const i32 t = blockIdx.x;
   if (t >= ntiles) return;
-  if (threadIdx.x == 0) { s_rows = 0; s_ent = 0; s_max = 0; }
+  if (threadIdx.x == 0) { s_rows = 0; s_ent = 0; s_max = 0; s_ovf = 0; }
   __syncthreads();
   const i32 s0 = tile_slice[t], s1 = tile_slice[t + 1];
   const i32 r0 = s0 * 32;
   const unsigned nrow = (unsigned)(s1 - s0) * 32u;
-  int rows = 0, ent = 0, mx = 0;
+  int rows = 0, ent = 0, mx = 0, ov = 0;
   for (unsigned lr = threadIdx.x; lr < nrow; lr += blockDim.x) {
     const i64 slice = s0 + (lr >> 5);
     const int lane = lr & 31;
@@ -67,11 +70,11 @@ __global__ void __launch_bounds__(128) k_img_count(i32 ntiles, const i32 *__rest
       len++;
       if ((unsigned)(c - r0) >= nrow) e++;
     }
-    rows += e > 0; ent += e; mx = max(mx, len);
+    rows += e > 0; ent += e; mx = max(mx, len); ov += max(0, len - IT_NV);
   }
-  atomicAdd(&s_rows, rows); atomicAdd(&s_ent, ent); atomicMax(&s_max, mx);
+  atomicAdd(&s_rows, rows); atomicAdd(&s_ent, ent); atomicMax(&s_max, mx); atomicAdd(&s_ovf, ov);
   __syncthreads();
-  if (threadIdx.x == 0) { n_ext_rows[t] = s_rows; n_ext[t] = s_ent; atomicMax(maxlen, s_max); }
+  if (threadIdx.x == 0) { n_ext_rows[t] = s_rows; n_ext[t] = s_ent; n_ovf[t] = s_ovf; atomicMax(maxlen, s_max); }
 }
 
 // ---- setup: pass 2 -- write the images.  One CTA per tile, thread per row; external lists in (row, slot) order (deterministic). ------
@@ -80,11 +83,12 @@ __global__ void __launch_bounds__(128) k_img_fill(i32 ntiles, const i32 *__restr
                                                  const i32 *__restrict__ tile_nreal, const uint8_t *__restrict__ row_lvl, SellView T,
                                                  const double *__restrict__ dinv, const double *__restrict__ diag, int with_diag,
                                                  const i64 *__restrict__ img_off, const i32 *__restrict__ n_ext_rows, const i32 *__restrict__ n_ext,
-                                                 unsigned char *img)
+                                                 const i32 *__restrict__ n_ovf, unsigned char *img)
 {
   constexpr int NT = 128, PER = MAXROWS / NT;
   __shared__ int s_cnt[MAXROWS + 1];       // external entries per row -> exclusive prefix
   __shared__ int s_rowid[MAXROWS + 1];     // external row flags -> exclusive prefix
+  __shared__ int s_ovf[MAXROWS + 1];       // overflow entries per row -> exclusive prefix
   const i32 t = blockIdx.x;
   if (t >= ntiles) return;
   const i32 s0 = tile_slice[t], s1 = tile_slice[t + 1];
@@ -98,76 +102,99 @@ __global__ void __launch_bounds__(128) k_img_fill(i32 ntiles, const i32 *__restr
   double *dg = (double *)(recs + (i64)IT_REC * nrow);
   unsigned short *xrows = (unsigned short *)((unsigned char *)dg + (with_diag ? 8 * (i64)nrow : 0));
   i32 *xent = (i32 *)((unsigned char *)xrows + 8 * (i64)n_ext_rows[t]);
+  // overflow entries start at the next 16-byte boundary (counted from the image base, which is 128-byte aligned)
+  const i64 ovf_off = ((((unsigned char *)xent + 8 * (i64)n_ext[t]) - base_p + 15) / 16) * 16;
+  unsigned char *ovf = base_p + ovf_off;
+  const i64 ovf_from_rec = ovf - recs;
   if (threadIdx.x == 0) {
     ITileHeader h;
     h.nlev = (unsigned short)nlev; h.nreal = (unsigned short)nreal; h.nrow = (unsigned short)nrow; h.n_ext_rows = (unsigned short)n_ext_rows[t];
-    h.n_ext = (unsigned short)n_ext[t]; h.ls_bytes = (unsigned short)ls_bytes; h.has_diag = (unsigned short)with_diag; h.pad = 0;
+    h.n_ext = (unsigned short)n_ext[t]; h.ls_bytes = (unsigned short)ls_bytes; h.has_diag = (unsigned short)with_diag; h.n_ovf = (unsigned short)n_ovf[t];
     *(ITileHeader *)base_p = h;
     ls[nlev] = (unsigned short)nreal;
   }
-  // records + per-row external counts
+  // per-row external / overflow counts, level starts
 #pragma unroll
   for (int j = 0; j < PER; j++) {
     const unsigned lr = threadIdx.x + j * NT;
-    int e = 0;
+    int e = 0, len = 0;
     if (lr < nrow) {
       const i64 slice = s0 + (lr >> 5), row = (i64)r0 + lr;
       const int lane = lr & 31;
       const i64 b = T.slice_ptr[slice];
       const int wd = (int)(T.slice_ptr[slice + 1] - b);
-      unsigned short ix[8];
-      double v[IT_NV];
-#pragma unroll
-      for (int k = 0; k < 8; k++) ix[k] = (unsigned short)MAXROWS;
-#pragma unroll
-      for (int k = 0; k < IT_NV; k++) v[k] = 0.0;
-      int slot = 0;
-      for (int k = 0; k < wd && slot < IT_NV; k++) {
+      for (int k = 0; k < wd; k++) {
         const i32 c = T.col[(b + k) * 32 + lane];
         if (c < 0) continue;
-        v[slot] = T.val[(b + k) * 32 + lane];
-        const unsigned lc = (unsigned)(c - r0);
-        if (lc < nrow) ix[slot] = (unsigned short)lc; else e++;
-        slot++;
+        len++;
+        if ((unsigned)(c - r0) >= nrow) e++;
       }
-      unsigned char *rec = recs + (i64)IT_REC * lr;
-      *(uint4 *)rec = make_uint4(ix[0] | (ix[1] << 16), ix[2] | (ix[3] << 16), ix[4] | (ix[5] << 16), ix[6] | (ix[7] << 16));
-      double *rv = (double *)(rec + 16);
-#pragma unroll
-      for (int k = 0; k < IT_NV; k++) rv[k] = v[k];
-      rv[IT_NV] = dinv[row];
-      if (with_diag) dg[lr] = diag[row];
       const int lv = row_lvl[row], lvp = lr ? (int)row_lvl[row - 1] : -1;
       if (lv != lvp && lv < 255) ls[lv] = (unsigned short)lr;
     }
-    if (lr < MAXROWS) { s_cnt[lr] = e; s_rowid[lr] = e > 0; }
+    if (lr < MAXROWS) { s_cnt[lr] = e; s_rowid[lr] = e > 0; s_ovf[lr] = max(0, len - IT_NV); }
   }
   __syncthreads();
   if (threadIdx.x == 0) {   // tiles are small: a serial prefix is fine at setup
-    int a = 0, b2 = 0;
-    for (unsigned i = 0; i < nrow; i++) { const int c = s_cnt[i], f = s_rowid[i]; s_cnt[i] = a; s_rowid[i] = b2; a += c; b2 += f; }
-    s_cnt[nrow] = a; s_rowid[nrow] = b2;
+    int a = 0, b2 = 0, o2 = 0;
+    for (unsigned i = 0; i < nrow; i++) {
+      const int c = s_cnt[i], f = s_rowid[i], o = s_ovf[i];
+      s_cnt[i] = a; s_rowid[i] = b2; s_ovf[i] = o2;
+      a += c; b2 += f; o2 += o;
+    }
+    s_cnt[nrow] = a; s_rowid[nrow] = b2; s_ovf[nrow] = o2;
   }
   __syncthreads();
-  // external lists
+  // records, overflow entries, external lists
 #pragma unroll
   for (int j = 0; j < PER; j++) {
     const unsigned lr = threadIdx.x + j * NT;
     if (lr >= nrow) continue;
-    const int first = s_cnt[lr], cnt = s_cnt[lr + 1] - first;
-    if (!cnt) continue;
-    const int xr = s_rowid[lr];
-    xrows[xr * 4 + 0] = (unsigned short)lr; xrows[xr * 4 + 1] = (unsigned short)first; xrows[xr * 4 + 2] = (unsigned short)cnt; xrows[xr * 4 + 3] = 0;
-    const i64 slice = s0 + (lr >> 5);
+    const i64 slice = s0 + (lr >> 5), row = (i64)r0 + lr;
     const int lane = lr & 31;
     const i64 b = T.slice_ptr[slice];
     const int wd = (int)(T.slice_ptr[slice + 1] - b);
-    int slot = 0, o = first;
-    for (int k = 0; k < wd && slot < IT_NV; k++) {
+    const int xfirst = s_cnt[lr], xcnt = s_cnt[lr + 1] - xfirst;
+    const int ofirst = s_ovf[lr], ocnt = s_ovf[lr + 1] - ofirst;
+    unsigned short ix[8];
+    double v[IT_NV];
+#pragma unroll
+    for (int k = 0; k < 8; k++) ix[k] = (unsigned short)MAXROWS;
+#pragma unroll
+    for (int k = 0; k < IT_NV; k++) v[k] = 0.0;
+    ix[7] = ocnt ? (unsigned short)((ofirst << 4) | ocnt) : (unsigned short)0xffff;
+    int slot = 0, xo = xfirst;
+    for (int k = 0; k < wd; k++) {
       const i32 c = T.col[(b + k) * 32 + lane];
       if (c < 0) continue;
-      if ((unsigned)(c - r0) >= nrow) { xent[2 * o] = c; xent[2 * o + 1] = slot; o++; }
+      const double val = T.val[(b + k) * 32 + lane];
+      const unsigned lc = (unsigned)(c - r0);
+      const bool in = lc < nrow;
+      i64 voff;
+      if (slot < IT_NV) {
+        v[slot] = val;
+        if (in) ix[slot] = (unsigned short)lc;
+        voff = (i64)IT_REC * lr + 16 + 8 * slot;
+      } else {
+        unsigned char *oe = ovf + 16 * (i64)(ofirst + slot - IT_NV);
+        *(unsigned *)oe = in ? lc : (unsigned)MAXROWS;
+        *(unsigned *)(oe + 4) = 0u;
+        *(double *)(oe + 8) = val;
+        voff = ovf_from_rec + 16 * (i64)(ofirst + slot - IT_NV) + 8;
+      }
+      if (!in) { xent[2 * xo] = c; xent[2 * xo + 1] = (i32)voff; xo++; }
       slot++;
+    }
+    unsigned char *rec = recs + (i64)IT_REC * lr;
+    *(uint4 *)rec = make_uint4(ix[0] | (ix[1] << 16), ix[2] | (ix[3] << 16), ix[4] | (ix[5] << 16), ix[6] | (ix[7] << 16));
+    double *rv = (double *)(rec + 16);
+#pragma unroll
+    for (int k = 0; k < IT_NV; k++) rv[k] = v[k];
+    rv[IT_NV] = dinv[row];
+    if (with_diag) dg[lr] = diag[row];
+    if (xcnt) {
+      const int xr = s_rowid[lr];
+      xrows[xr * 4 + 0] = (unsigned short)lr; xrows[xr * 4 + 1] = (unsigned short)xfirst; xrows[xr * 4 + 2] = (unsigned short)xcnt; xrows[xr * 4 + 3] = 0;
     }
   }
 }
@@ -260,36 +287,41 @@ __global__ void __launch_bounds__(NT, MINB) k_gs_itile(const double *rin, const 
     const uint32_t dg_a = rec_a + (uint32_t)nrow * IT_REC;
     const uint32_t xr_a = dg_a + (WRITE_R ? (uint32_t)nrow * 8u : 0u);
     const uint32_t xe_a = xr_a + (uint32_t)nxr * 8u;
+    const uint32_t ov_a = img_a + (((xe_a - img_a) + (hw.z & 0xffffu) * 8u + 15u) & ~15u);        // overflow entries
     // ---- couplings to rows of other tiles: one thread per external row, all its polls in flight together; the data is the flag
 #pragma unroll 1
     for (int er = tid; er < nxr; er += NT) {
       const uint32_t e0 = lds_i32(xr_a + (uint32_t)er * 8u), e1 = lds_i32(xr_a + (uint32_t)er * 8u + 4u);
       const uint32_t row = e0 & 0xffffu, first = e0 >> 16, cnt = e1 & 0xffffu;
-      i32 c[IT_NV], sl[IT_NV];
-      double x[IT_NV];
-#pragma unroll
-      for (int i = 0; i < IT_NV; i++) {
-        c[i] = (i < (int)cnt) ? lds_i32(xe_a + (first + i) * 8u) : -1;
-        sl[i] = (i < (int)cnt) ? lds_i32(xe_a + (first + i) * 8u + 4u) : 0;
-      }
-      unsigned spins = 0;
-      bool missing;
-#pragma unroll 1
-      do {
-        missing = false;
-#pragma unroll
-        for (int i = 0; i < IT_NV; i++) x[i] = (c[i] >= 0) ? ld_poll_relaxed(out + c[i]) : 0.0;
-#pragma unroll
-        for (int i = 0; i < IT_NV; i++) missing |= is_sentinel(x[i]);
-        if (missing) {
-          if (p.repoll_ns) __nanosleep(p.repoll_ns);
-          if (spin_fail(spins, p.err)) break;
-        }
-      } while (missing);
       double a = lds_f64(acc_a + row * 8u);
+#pragma unroll 1
+      for (uint32_t b0 = 0; b0 < cnt; b0 += IT_NV) {
+        i32 c[IT_NV], vo[IT_NV];
+        double x[IT_NV];
 #pragma unroll
-      for (int i = 0; i < IT_NV; i++)
-        if (i < (int)cnt) a = fma(-lds_f64(rec_a + row * IT_REC + 16u + (uint32_t)sl[i] * 8u), x[i], a);
+        for (int i = 0; i < IT_NV; i++) {
+          const bool in = b0 + i < cnt;
+          c[i] = in ? lds_i32(xe_a + (first + b0 + i) * 8u) : -1;
+          vo[i] = in ? lds_i32(xe_a + (first + b0 + i) * 8u + 4u) : 0;
+        }
+        unsigned spins = 0;
+        bool missing;
+#pragma unroll 1
+        do {
+          missing = false;
+#pragma unroll
+          for (int i = 0; i < IT_NV; i++) x[i] = (c[i] >= 0) ? ld_poll_relaxed(out + c[i]) : 0.0;
+#pragma unroll
+          for (int i = 0; i < IT_NV; i++) missing |= is_sentinel(x[i]);
+          if (missing) {
+            if (p.repoll_ns) __nanosleep(p.repoll_ns);
+            if (spin_fail(spins, p.err)) break;
+          }
+        } while (missing);
+#pragma unroll
+        for (int i = 0; i < IT_NV; i++)
+          if (c[i] >= 0) a = fma(-lds_f64(rec_a + (uint32_t)vo[i]), x[i], a);
+      }
       sts_f64(acc_a + row * 8u, a);
     }
     if (tr) tr[3] = gtimer();
@@ -319,6 +351,14 @@ __global__ void __launch_bounds__(NT, MINB) k_gs_itile(const double *rin, const 
                        x6 = lds_f64(xs_a + (iw.w & 0xffffu) * 8u);
           a = fma(-v0, x0, a); a2 = fma(-v1, x1, a2); a = fma(-v2, x2, a); a2 = fma(-v3, x3, a2);
           a = fma(-v4, x4, a); a2 = fma(-v5, x5, a2); a = fma(-v6, x6, a);
+          const unsigned o7 = iw.w >> 16;
+          if (o7 != 0xffffu) {                         // rows with more than 7 entries (rare: next to an interface of a distributed level)
+            const uint32_t oa = ov_a + (o7 >> 4) * 16u;
+            for (unsigned k = 0; k < (o7 & 15u); k++) {
+              const uint4 oe = lds_v4(oa + k * 16u);
+              a = fma(-__hiloint2double(oe.w, oe.z), lds_f64(xs_a + oe.x * 8u), a);
+            }
+          }
           a += a2;
           const double d = dvv * a;
           if (act) {

@@ -1,0 +1,11 @@
+#!/usr/bin/env bash
+set -u
+OUT=gpurun_out/r02_2gpu_b
+mkdir -p "$OUT"
+timeout 1200 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus 2 --steps 5 --warmup 3 > $OUT/bench2.log 2>&1; echo "rc=$?"
+python - "$OUT/bench2.log" <<'PY'
+import json,sys
+for l in open(sys.argv[1]):
+    if l.startswith('{'):
+        d=json.loads(l); print('N=2', d['solve_s'], d['iterations'], 'setup', d['setup_s'], 'vcycle', d['vcycle_ms'], d['vcycle_frac_of_peak'], 'value', d['value'], 'e2e', d['e2e']['value']); print(d['vcycle_phases_ms']); print(d['kernel_ms_by_level'][:3]); print([ (l['n'], l['gs_depth']) for l in d['config']['levels']])
+PY
