@@ -227,6 +227,10 @@ class Preconditioner:
     def GetNDof(self, level, rank=0):
         return int(self.level_info(level).n)
 
+    def SweepKind(self, level=0):
+        """which kernel sweeps the level: 'rows' | 'warp_tiles' | 'cta_tiles' | 'tile_images'"""
+        return {0: "rows", 1: "warp_tiles", 2: "cta_tiles", 3: "tile_images"}[int(self._lib.ngsamg_b200_level_sweep_kind(self._h, int(level)))]
+
     def GetBlockSize(self, level=0):
         return int(self.level_info(level).b)
 

@@ -16,7 +16,7 @@ CSRC = os.path.join(_PKG, "csrc")
 EXPORTS = [
     "ngsamg_b200_create", "ngsamg_b200_set_prolongations", "ngsamg_b200_finalize", "ngsamg_b200_destroy",
     "ngsamg_b200_last_error", "ngsamg_b200_apply", "ngsamg_b200_apply_add", "ngsamg_b200_spmv_add",
-    "ngsamg_b200_apply_phases", "ngsamg_b200_smooth", "ngsamg_b200_restrict", "ngsamg_b200_prolong_add", "ngsamg_b200_coarse_solve", "ngsamg_b200_pcg",
+    "ngsamg_b200_apply_phases", "ngsamg_b200_level_sweep_kind", "ngsamg_b200_smooth", "ngsamg_b200_restrict", "ngsamg_b200_prolong_add", "ngsamg_b200_coarse_solve", "ngsamg_b200_pcg",
     "ngsamg_b200_num_levels", "ngsamg_b200_level_info", "ngsamg_b200_get_level_matrix",
     "ngsamg_b200_get_prolongation", "ngsamg_b200_get_level_vector", "ngsamg_b200_operator_complexity", "ngsamg_b200_operator_complexities",
     "ngsamg_b200_vcycle_bytes", "ngsamg_b200_last_ms", "ngsamg_b200_launch_count", "ngsamg_b200_rap_begin",
@@ -74,6 +74,7 @@ def lib():
     L.ngsamg_b200_apply.argtypes = [vp, vp, vp]
     L.ngsamg_b200_apply_add.argtypes = [vp, dbl, vp, vp]
     L.ngsamg_b200_spmv_add.argtypes = [vp, ci, dbl, vp, vp]
+    L.ngsamg_b200_level_sweep_kind.argtypes = [vp, ci]
     L.ngsamg_b200_apply_phases.argtypes = [vp, vp, vp, vp]
     L.ngsamg_b200_smooth.argtypes = [vp, ci, vp, vp, vp, ci, ci, ci, ci]
     L.ngsamg_b200_restrict.argtypes = [vp, ci, vp, vp]

@@ -2999,6 +2999,17 @@ int ngsamg_b200_pcg(ngsamg_b200_t *h, const double *rhs, double *x, double tol, 
 
 int ngsamg_b200_num_levels(ngsamg_b200_t *h) { return (h && h->amg.finalized) ? (int)h->amg.lev.size() : 0; }
 
+// which kernel sweeps the level: 0 row-level (k_gs_tri / k_gs_level / k_gs_tri_small), 1 warp per tile, 2 CTA per tile, 3 CTA per tile on
+// prepared tile images; -1 = no such level
+int ngsamg_b200_level_sweep_kind(ngsamg_b200_t *h, int level)
+{
+  if (!h || !h->amg.finalized || level < 0 || level >= (int)h->amg.lev.size()) return -1;
+  const Level &L = *h->amg.lev[level];
+  if (!L.tiled) return 0;
+  if (L.tile_maxs <= 2) return 1;
+  return L.itile ? 3 : 2;
+}
+
 static void level_bytes(const Level &L, i64 &m, i64 &p, i64 &v)
 {
   m = (L.par ? L.nnz_m + L.nnz_g : L.nnz) * (8 * (i64)L.b * L.b + 4) + 4 * (L.n + 1);   // hybrid level: M and G are each read once per sweep

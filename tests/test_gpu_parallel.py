@@ -119,6 +119,8 @@ def test_parallel_tiled_sweeps_match_oracle(grid, rows, image):
                        ngs_amg_b200_tile_min_depth=0, ngs_amg_b200_tile_rows=rows, ngs_amg_b200_tile_image=image)
     amg, npar = _oracle_for(parts, pcs, 1)
     assert npar >= 1
+    # rows next to an interface have up to 14 entries in a triangle of the stage order: the images carry them as overflow entries
+    assert all(pc.SweepKind(0) == ("tile_images" if image else "cta_tiles") for pc in pcs)
     b = [rand(70 + r, p["n"]) * p["free"] for r, p in enumerate(parts)]
     xo = amg.apply(b)
 

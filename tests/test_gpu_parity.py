@@ -480,6 +480,7 @@ def test_tile_sweep(rows, n, nbuf, image):
     pc0 = ng.h1_scal(A, p["free"], **base)
     pc = ng.h1_scal(A, p["free"], prolongations=pc0.GetMap(), ngs_amg_b200_tile_sweep=True, ngs_amg_b200_tile_min_rows=0,
                     ngs_amg_b200_tile_min_depth=0, ngs_amg_b200_tile_rows=rows, ngs_amg_b200_tile_nbuf=nbuf, ngs_amg_b200_tile_image=image, **base)
+    assert pc.SweepKind(0) == ("warp_tiles" if rows <= 64 else ("tile_images" if image else "cta_tiles"))
     amg = O.OracleAMG(to_oracle(A), p["free"], [to_oracle(P) for P in pc0.GetMap()])
     for seed in (1, 2, 3):
         b = rand(seed, p["n"])
