@@ -266,21 +266,13 @@ __global__ void __launch_bounds__(NT, MINB) k_gs_itile(const double *rin, const 
       bulk_prefetch_l2(rin + nxt.r0, (uint32_t)nxt.nrow * 8u);
       if (ADD_SELF) bulk_prefetch_l2(self + nxt.r0, (uint32_t)nxt.nrow * 8u);
     }
-    // ---- hint flags of the tiles this one depends on
-    for (int k = tid; k < cur.nd; k += NT) {
-      const int *f = p.done + ((k < NT) ? cur_dep : p.dep[cur.d0 + k]);
-      unsigned spins = 0;
-      while (ld_relaxed_i32(f) == 0) {
-        if (p.sleep_ns) __nanosleep(p.sleep_ns);
-        if (spin_fail(spins, p.err)) break;
-      }
-    }
-    if (tr) tr[1] = gtimer();
+    // ---- the first hint flag is requested right away; the image is usually there already: parse it and preload this thread's external
+    // row (columns, values) so that nothing but the data polls themselves follows the flags on the critical path
+    int flag0 = 1;
+    if (tid < cur.nd) flag0 = ld_relaxed_i32(p.done + cur_dep);
     mbar_wait(bar, phase);
     phase ^= 1u;
-    __syncthreads();
-    if (tr) tr[2] = gtimer();
-    // ---- the image
+    if (tr) tr[1] = gtimer();
     const uint4 hw = lds_v4(img_a);
     const int nlev = hw.x & 0xffff, nreal = hw.x >> 16, nrow = hw.y & 0xffff, nxr = hw.y >> 16;
     const uint32_t ls_a = img_a + 16, rec_a = ls_a + (hw.z >> 16);
@@ -288,39 +280,86 @@ __global__ void __launch_bounds__(NT, MINB) k_gs_itile(const double *rin, const 
     const uint32_t xr_a = dg_a + (WRITE_R ? (uint32_t)nrow * 8u : 0u);
     const uint32_t xe_a = xr_a + (uint32_t)nxr * 8u;
     const uint32_t ov_a = img_a + (((xe_a - img_a) + (hw.z & 0xffffu) * 8u + 15u) & ~15u);        // overflow entries
+    uint32_t row0 = 0, first0 = 0, cnt0 = 0;
+    i32 c0[IT_NV];
+    double v0[IT_NV], a0 = 0.0;
+#pragma unroll
+    for (int i = 0; i < IT_NV; i++) { c0[i] = -1; v0[i] = 0.0; }
+    if (tid < nxr) {
+      const uint32_t e0 = lds_i32(xr_a + (uint32_t)tid * 8u), e1 = lds_i32(xr_a + (uint32_t)tid * 8u + 4u);
+      row0 = e0 & 0xffffu; first0 = e0 >> 16; cnt0 = e1 & 0xffffu;
+      a0 = lds_f64(acc_a + row0 * 8u);
+#pragma unroll
+      for (int i = 0; i < IT_NV; i++)
+        if (i < (int)cnt0) { c0[i] = lds_i32(xe_a + (first0 + i) * 8u); v0[i] = lds_f64(rec_a + (uint32_t)lds_i32(xe_a + (first0 + i) * 8u + 4u)); }
+    }
+    // ---- hint flags of the tiles this one depends on
+    for (int k = tid; k < cur.nd; k += NT) {
+      const int *f = p.done + ((k < NT) ? cur_dep : p.dep[cur.d0 + k]);
+      unsigned spins = 0;
+      int fl = (k < NT) ? flag0 : ld_relaxed_i32(f);
+      while (fl == 0) {
+        if (p.sleep_ns) __nanosleep(p.sleep_ns);
+        if (spin_fail(spins, p.err)) break;
+        fl = ld_relaxed_i32(f);
+      }
+    }
+    __syncthreads();
+    if (tr) tr[2] = gtimer();
     // ---- couplings to rows of other tiles: one thread per external row, all its polls in flight together; the data is the flag
+    auto poll_row = [&](const i32 (&c)[IT_NV], const double (&v)[IT_NV], double a) {
+      double x[IT_NV];
+      unsigned spins = 0;
+      bool missing;
 #pragma unroll 1
-    for (int er = tid; er < nxr; er += NT) {
+      do {
+        missing = false;
+#pragma unroll
+        for (int i = 0; i < IT_NV; i++) x[i] = (c[i] >= 0) ? ld_poll_relaxed(out + c[i]) : 0.0;
+#pragma unroll
+        for (int i = 0; i < IT_NV; i++) missing |= is_sentinel(x[i]);
+        if (missing) {
+          if (p.repoll_ns) __nanosleep(p.repoll_ns);
+          if (spin_fail(spins, p.err)) break;
+        }
+      } while (missing);
+#pragma unroll
+      for (int i = 0; i < IT_NV; i++) a = fma(-v[i], x[i], a);      // v = 0 where there is no entry
+      return a;
+    };
+    if (tid < nxr) {
+      a0 = poll_row(c0, v0, a0);
+      // rows with more than IT_NV couplings to other tiles (rare), and further external rows of this thread (tiles with > NT of them)
+#pragma unroll 1
+      for (uint32_t b0 = IT_NV; b0 < cnt0; b0 += IT_NV) {
+        i32 c[IT_NV];
+        double v[IT_NV];
+#pragma unroll
+        for (int i = 0; i < IT_NV; i++) {
+          const bool in = b0 + i < cnt0;
+          c[i] = in ? lds_i32(xe_a + (first0 + b0 + i) * 8u) : -1;
+          v[i] = in ? lds_f64(rec_a + (uint32_t)lds_i32(xe_a + (first0 + b0 + i) * 8u + 4u)) : 0.0;
+        }
+        a0 = poll_row(c, v, a0);
+      }
+      sts_f64(acc_a + row0 * 8u, a0);
+    }
+#pragma unroll 1
+    for (int er = tid + NT; er < nxr; er += NT) {
       const uint32_t e0 = lds_i32(xr_a + (uint32_t)er * 8u), e1 = lds_i32(xr_a + (uint32_t)er * 8u + 4u);
       const uint32_t row = e0 & 0xffffu, first = e0 >> 16, cnt = e1 & 0xffffu;
       double a = lds_f64(acc_a + row * 8u);
 #pragma unroll 1
       for (uint32_t b0 = 0; b0 < cnt; b0 += IT_NV) {
-        i32 c[IT_NV], vo[IT_NV];
-        double x[IT_NV];
+        i32 c[IT_NV];
+        double v[IT_NV];
 #pragma unroll
         for (int i = 0; i < IT_NV; i++) {
           const bool in = b0 + i < cnt;
           c[i] = in ? lds_i32(xe_a + (first + b0 + i) * 8u) : -1;
-          vo[i] = in ? lds_i32(xe_a + (first + b0 + i) * 8u + 4u) : 0;
+          v[i] = in ? lds_f64(rec_a + (uint32_t)lds_i32(xe_a + (first + b0 + i) * 8u + 4u)) : 0.0;
         }
-        unsigned spins = 0;
-        bool missing;
-#pragma unroll 1
-        do {
-          missing = false;
-#pragma unroll
-          for (int i = 0; i < IT_NV; i++) x[i] = (c[i] >= 0) ? ld_poll_relaxed(out + c[i]) : 0.0;
-#pragma unroll
-          for (int i = 0; i < IT_NV; i++) missing |= is_sentinel(x[i]);
-          if (missing) {
-            if (p.repoll_ns) __nanosleep(p.repoll_ns);
-            if (spin_fail(spins, p.err)) break;
-          }
-        } while (missing);
-#pragma unroll
-        for (int i = 0; i < IT_NV; i++)
-          if (c[i] >= 0) a = fma(-lds_f64(rec_a + (uint32_t)vo[i]), x[i], a);
+        a = poll_row(c, v, a);
       }
       sts_f64(acc_a + row * 8u, a);
     }
@@ -362,23 +401,26 @@ __global__ void __launch_bounds__(NT, MINB) k_gs_itile(const double *rin, const 
           a += a2;
           const double d = dvv * a;
           if (act) {
-            sts_f64(xs_a + (uint32_t)r * 8u, ADD_SELF ? ax + d : d);
-            if (WRITE_R) sts_f64(acc_a + (uint32_t)r * 8u, fma(-ax, d, a));
+            // the solver publishes a row the moment it is computed (rows of a level are consecutive: coalesced); waiting tiles poll `out`
+            const double xn = ADD_SELF ? ax + d : d;
+            sts_f64(xs_a + (uint32_t)r * 8u, xn);
+            __stcg(out + (i64)r0 + r, xn);
+            if (WRITE_R) rout[(i64)r0 + r] = fma(-ax, d, a);
           }
         }
         __syncwarp();
       }
+      if (lane == 0) st_relaxed_i32(p.done + t, 1);                  // hint for the waiting tiles: worth polling now
+    } else {
+      // the other warps: padding rows are never updated, but `out` must not keep the sentinel
+      for (int lr = nreal + (tid - (w > solver ? 32 : 0)) ; lr < nrow; lr += NT - 32) {
+        const i64 row = (i64)r0 + lr;
+        __stcg(out + row, ADD_SELF ? lds_f64(aux_a + (uint32_t)lr * 8u) : 0.0);
+        if (WRITE_R) rout[row] = lds_f64(acc_a + (uint32_t)lr * 8u);
+      }
     }
     __syncthreads();
     if (tr) tr[4] = gtimer();
-    // ---- publish: coalesced stores; padding rows are never updated, but `out` must not keep the sentinel
-    for (int lr = tid; lr < nrow; lr += NT) {
-      const i64 row = (i64)r0 + lr;
-      const bool real = lr < nreal;
-      __stcg(out + row, real ? lds_f64(xs_a + (uint32_t)lr * 8u) : (ADD_SELF ? lds_f64(aux_a + (uint32_t)lr * 8u) : 0.0));
-      if (WRITE_R) rout[row] = lds_f64(acc_a + (uint32_t)lr * 8u);
-    }
-    if (tid == 0) st_relaxed_i32(p.done + t, 1);
     if (tr) {
       unsigned smid;
       asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
