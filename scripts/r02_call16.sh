@@ -1,7 +1,7 @@
 #!/usr/bin/env bash
 # GPU call 16: tile-image kernel (kernels_itile.cuh): parity, trace at 311^3 for 256/512-row tiles
 set -u
-OUT=gpurun_out/r02_c26
+OUT=gpurun_out/r02_c27
 mkdir -p "$OUT"
 step() { local name=$1 secs=$2; shift 2; echo "=== $name" | tee -a "$OUT/steps.log"; timeout "$secs" "$@" > "$OUT/$name.log" 2>&1; echo "rc=$? ($name)" | tee -a "$OUT/steps.log"; }
 step pytest_tile 300 python -m pytest tests/test_gpu_parity.py -k "tile_sweep" -q
