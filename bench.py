@@ -432,7 +432,9 @@ def main():
         by_level.append(row)
     dom = max(("gs_tri_fwd", "gs_tri_bwd", "gs_upass", "gs_lpass"), key=lambda k: kern[k]["ms"])
     traffic = None
-    tiled = extra.get("ngs_amg_b200_tile_sweep", "1") not in ("0", "false", "False")
+    sweep_kind = pc.SweepKind(0)
+    tiled = sweep_kind != "rows"
+    sweep_kernel = {"rows": "k_gs_tri", "warp_tiles": "k_gs_tile", "cta_tiles": "k_gs_ctile", "tile_images": "k_gs_itile"}[sweep_kind]
     try:
         # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full capture of the same kernel and size
         with open(os.path.join(ROOT, "profiles", "r02_traffic.json" if tiled else "r01_traffic.json")) as f:
@@ -441,7 +443,7 @@ def main():
             traffic = tj.get(dom)
     except Exception:
         pass
-    roof = {"bound": "hbm", "kernel": "%s (%s, level 0)" % ("k_gs_ctile" if tiled else "k_gs_tri", dom), "achieved": kern[dom]["gbs"], "peak": peak,
+    roof = {"bound": "hbm", "kernel": "%s (%s, level 0)" % (sweep_kernel, dom), "achieved": kern[dom]["gbs"], "peak": peak,
             "unit": "GB/s", "frac": kern[dom]["gbs"] / peak, "traffic": traffic, "peak_source": peak_src,
             "ms_per_launch": kern[dom]["ms"], "algorithmic_bytes": kern[dom]["bytes"]}
 
