@@ -433,8 +433,8 @@ def main():
     dom = max(("gs_tri_fwd", "gs_tri_bwd", "gs_upass", "gs_lpass"), key=lambda k: kern[k]["ms"])
     traffic = None
     sweep_kind = pc.SweepKind(0)
-    tiled = sweep_kind != "rows"
-    sweep_kernel = {"rows": "k_gs_tri", "warp_tiles": "k_gs_tile", "cta_tiles": "k_gs_ctile", "tile_images": "k_gs_itile"}[sweep_kind]
+    tiled = sweep_kind in ("warp_tiles", "cta_tiles", "tile_images")
+    sweep_kernel = {"rows": "k_gs_tri", "rows_rm": "k_gs_tri_rm", "warp_tiles": "k_gs_tile", "cta_tiles": "k_gs_ctile", "tile_images": "k_gs_itile"}[sweep_kind]
     try:
         # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full capture of the same kernel and size
         with open(os.path.join(ROOT, "profiles", "r02_traffic.json" if tiled else "r01_traffic.json")) as f:

@@ -118,8 +118,11 @@ int ngsamg_b200_pcg(ngsamg_b200_t *h, const double *rhs, double *x, double tol, 
 /* ---- introspection (AMGMatrix::GetNLevels/GetNDof amg_matrix.cpp:396-, GetOC :551-582) -------------- */
 int ngsamg_b200_num_levels(ngsamg_b200_t *h);
 /* which kernel sweeps the level (measurement / test aid): 0 row-level sync-free or per-colour launches, 1 warp per tile, 2 CTA per tile,
- * 3 CTA per tile on tile images prepared at setup; -1 = no such level */
+ * 3 CTA per tile on tile images prepared at setup, 4 warp per row on the row-major copy of a small level; -1 = no such level */
 int ngsamg_b200_level_sweep_kind(ngsamg_b200_t *h, int level);
+/* measurement aid: change a run-time tunable of the sweep kernels ("tri_sleep_ns", "tri_prepoll", "tri_rm", "tri_rm_rows_per_warp",
+ * "tri_small_rows", "tri_level_launch_depth", "tri_level_launch_rows", "spmv_small_rows", "use_graph", ...) on a finalized hierarchy */
+int ngsamg_b200_set_tunable(ngsamg_b200_t *h, const char *name, double value);
 int ngsamg_b200_level_info(ngsamg_b200_t *h, int level, ngsamg_level_info *info);
 /* copy the level matrix A_l / the prolongation P_l (original DOF numbering) into caller arrays sized from
  * level_info: rowptr[n+1], col[nnz], val[nnz*b*b] resp. val[nnz_prol*b*bcoarse].  Any pointer may be NULL.

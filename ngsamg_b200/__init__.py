@@ -229,7 +229,7 @@ class Preconditioner:
 
     def SweepKind(self, level=0):
         """which kernel sweeps the level: 'rows' | 'warp_tiles' | 'cta_tiles' | 'tile_images'"""
-        return {0: "rows", 1: "warp_tiles", 2: "cta_tiles", 3: "tile_images"}[int(self._lib.ngsamg_b200_level_sweep_kind(self._h, int(level)))]
+        return {0: "rows", 1: "warp_tiles", 2: "cta_tiles", 3: "tile_images", 4: "rows_rm"}[int(self._lib.ngsamg_b200_level_sweep_kind(self._h, int(level)))]
 
     def GetBlockSize(self, level=0):
         return int(self.level_info(level).b)
@@ -333,6 +333,10 @@ class Preconditioner:
         ms, by = C.c_double(), C.c_double()
         _lib.check(self._lib.ngsamg_b200_profile_kernel(self._h, int(level), self.KERNELS[which], int(reps), C.byref(ms), C.byref(by)))
         return ms.value, by.value
+
+    def SetTunable(self, name, value):
+        """measurement aid: change a run-time tunable of the sweep kernels on the finalized hierarchy (include/ngsamg_b200.h)"""
+        _lib.check(self._lib.ngsamg_b200_set_tunable(self._h, str(name).encode(), float(value)))
 
     # -- level operations ------------------------------------------------------------------------
     def _level_len(self, level):

@@ -16,6 +16,7 @@
 #include "kernels_tile.cuh"
 #include "kernels_ctile.cuh"
 #include "kernels_itile.cuh"
+#include "kernels_rm.cuh"
 #include "par.hpp"
 #include "tiles.hpp"
 
@@ -40,6 +41,16 @@ struct Sell {
   void release() { dev_free(slice_ptr); dev_free(col); dev_free(val); }
 };
 
+// row-major copy of a triangle (small levels, kernels_rm.cuh)
+struct Rm {
+  i64 *ptr = nullptr;
+  i32 *col = nullptr;
+  double *val = nullptr;
+  i32 *gate = nullptr;
+  RmView view() const { return RmView{ptr, col, val, gate}; }
+  void release() { dev_free(ptr); dev_free(col); dev_free(val); dev_free(gate); ptr = nullptr; col = nullptr; val = nullptr; gate = nullptr; }
+};
+
 enum { SM_GS = 0, SM_JACOBI = 1 };
 
 struct Level {
@@ -54,6 +65,7 @@ struct Level {
   i32 *d_perm = nullptr;
   uint8_t *d_freep = nullptr;
   Sell L, U, N;   // strictly lower / strictly upper / free-row couplings to non-free rows
+  Rm rmL, rmU;    // row-major copies of L / U for the warp-per-row sweep of small levels (empty otherwise)
   double *diag = nullptr, *dinv = nullptr;
   // Gauss-Seidel dependency structure
   int depth = 0;        // number of dependency levels (length of the critical path of a sweep)
@@ -222,8 +234,12 @@ struct Amg {
   i64 launches = 0;
   double ms_apply = 0, ms_pcg = 0, ms_setup = 0, ms_rap = 0, ms_host = 0, bytes_rap = 0;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-  int tri_grid_cap[32] = {0};
+  int tri_grid_cap[48] = {0};
   i64 tri_small_rows = 1000000;
+  int tri_rm_rows_per_warp = 8;   // grid of the row-major sweep: at least this many rows per warp
+  i64 tri_rm_max_rows = 100000;   // larger small levels keep the SELL warp-per-row sweep (measured: 0.22 vs 0.29 ms at 519 k rows)
+  i64 tri_rm_gate_rows = 4096;    // levels with more rows gate every row on its newest dependency before the per-lane polls
+  int tri_rm = 1;                 // small levels sweep a row-major copy of the triangle (k_gs_tri_rm) instead of the SELL layout
   int tri_level_launch_depth = 24;
   i64 tri_level_launch_rows = 131072;
   double tri_gate_gap_levels = 0.0;
@@ -265,6 +281,9 @@ struct Amg {
   ~Amg();
   void finalize();
   void build_level_layout(Level &L, const DevCsr &dA);
+  void build_rm(const Sell &S, Rm &R, bool upper, i64 nonfree);
+  // shallow dependency DAG with many rows per level: one plain launch per level (k_gs_level)
+  bool level_launch(const Level &L) const { return L.depth <= tri_level_launch_depth && L.npad > tri_level_launch_rows && (int)L.level_start.size() == L.depth + 1; }
   void prepare_ctile(Level &L);
   bool prepare_itile(Level &L);
   bool setup_tiles(Level &L, int l, const HostBsr &A);
@@ -644,7 +663,7 @@ Amg::~Amg()
     if (L.h_send) cudaFreeHost(L.h_send);
     if (L.h_recv) cudaFreeHost(L.h_recv);
     dev_free(L.d_perm); dev_free(L.d_freep); dev_free(L.d_pt_rowmap); dev_free(L.d_bnd_fwd); dev_free(L.d_bnd_bwd);
-    L.L.release(); L.U.release(); L.N.release(); L.P.release(); L.PT.release();
+    L.L.release(); L.U.release(); L.N.release(); L.P.release(); L.PT.release(); L.rmL.release(); L.rmU.release();
     dev_free(L.diag); dev_free(L.dinv);
     dev_free(L.x); dev_free(L.y); dev_free(L.rhs); dev_free(L.res); dev_free(L.tmp); dev_free(L.wa); dev_free(L.wb);
   }
@@ -788,6 +807,35 @@ void Amg::build_level_layout(Level &L, const DevCsr &dA)
     dev_free(aos);
   }
   dev_free(d_err);
+  // small levels: row-major copies of the triangles for the warp-per-row sweep (kernels_rm.cuh)
+  if (L.sm_type == SM_GS && !L.tiled && L.npad <= std::min(tri_small_rows, tri_rm_max_rows) && tri_rm && !level_launch(L)) {
+    build_rm(L.L, L.rmL, false, L.nonfree_pad);
+    build_rm(L.U, L.rmU, true, L.nonfree_pad);
+  }
+}
+
+// SELL triangle -> row-major copy (entries of a row contiguous, slot order kept)
+void Amg::build_rm(const Sell &S, Rm &R, bool upper, i64 nonfree)
+{
+  const i64 np = S.nrows_pad;
+  const int bs = S.bh * S.bw;
+  i64 *cnt = dev_alloc<i64>(np + 1);
+  R.ptr = dev_alloc<i64>(np + 1);
+  k_rm_count<<<nblk(np + 1), TB, 0, st>>>(np, S.view(), cnt);
+  size_t tb = 0;
+  cub::DeviceScan::ExclusiveSum(nullptr, tb, cnt, R.ptr, np + 1, st);
+  void *tmp = dev_alloc<char>(tb);
+  cub::DeviceScan::ExclusiveSum(tmp, tb, cnt, R.ptr, np + 1, st);
+  i64 total = 0;
+  NGB_CUDA(cudaMemcpyAsync(&total, R.ptr + np, sizeof(i64), cudaMemcpyDeviceToHost, st));
+  NGB_CUDA(cudaStreamSynchronize(st));
+  cudaFree(tmp);
+  dev_free(cnt);
+  R.col = dev_alloc<i32>(std::max<i64>(total, 1));
+  R.val = dev_alloc<double>(std::max<i64>(total * bs, 1));
+  R.gate = dev_alloc<i32>(std::max<i64>(np, 1));
+  k_rm_fill<<<nblk(np), TB, 0, st>>>(np, bs, S.view(), R.ptr, R.col, R.val, R.gate, upper ? 1 : 0, (i32)nonfree);
+  launches += 3;
 }
 
 // the instantiations of the CTA-per-tile sweep: 256-row tiles run on 128-thread CTAs (6 per SM), 512-row tiles on 256-thread CTAs (3 per SM)
@@ -1535,7 +1583,7 @@ void Amg::finalize_parallel()
         NGB_CUDA(cudaEventCreate(&N.ev1));
         N.num_sms = num_sms; N.use_graph = flags.flag("b200_cuda_graph", true) && !use_graph;
         N.tri_sleep_ns = tri_sleep_ns; N.tri_ctas_per_sm = tri_ctas_per_sm; N.tri_prepoll = tri_prepoll; N.tri_gate_all = tri_gate_all;
-        N.tri_small_rows = tri_small_rows; N.tri_gate_gap_levels = tri_gate_gap_levels; N.tri_level_launch_depth = tri_level_launch_depth;
+        N.tri_rm = tri_rm; N.tri_rm_rows_per_warp = tri_rm_rows_per_warp; N.tri_rm_gate_rows = tri_rm_gate_rows; N.tri_rm_max_rows = tri_rm_max_rows; N.tri_small_rows = tri_small_rows; N.tri_gate_gap_levels = tri_gate_gap_levels; N.tri_level_launch_depth = tri_level_launch_depth;
         N.tri_level_launch_rows = tri_level_launch_rows; N.tri_repoll_ns = tri_repoll_ns; N.tri_regate = tri_regate; N.tri_split = tri_split;
         auto NL = std::make_unique<Level>();
         NL->hA = std::move(ctr.A);
@@ -1762,7 +1810,7 @@ void Amg::tri(Level &L, bool backward, bool add_self, bool write_r, const double
   }
   // sentinel-fill the output: a row is "published" once its entry is no longer the all-ones NaN
   NGB_CUDA(cudaMemsetAsync(out, 0xFF, sizeof(double) * L.npad * L.b, st));
-  if (L.depth <= tri_level_launch_depth && L.npad > tri_level_launch_rows && (int)L.level_start.size() == L.depth + 1) {
+  if (level_launch(L)) {
     // shallow dependency DAG with many rows per level: one plain launch per level (cached gathers, no polling)
     if (!add_self && !write_r) throw Error("tri: unsupported mode");
     if (!add_self && L.nonfree_pad) NGB_CUDA(cudaMemsetAsync(out, 0, sizeof(double) * L.nonfree_pad * L.b, st));
@@ -1791,6 +1839,29 @@ void Amg::tri(Level &L, bool backward, bool add_self, bool write_r, const double
       launch_resident(kern, grid, 256, st, T.view(), (const double *)L.diag, (const double *)L.dinv, rin, self, out, rout, prm);
     };
     if (!add_self && !write_r) throw Error("tri: unsupported mode");
+    const Rm &R = backward ? L.rmU : L.rmL;
+    if (R.ptr && tri_rm) {
+      const int ridx = 32 + (B == 1 ? 0 : B == 2 ? 1 : B == 3 ? 2 : 3) * 2 + (add_self ? 1 : 0);
+      auto launch_rm = [&](auto kern) {
+        if (!tri_grid_cap[ridx]) {
+          int occ = 0;
+          NGB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, RM_THREADS, 0));
+          tri_grid_cap[ridx] = std::max(1, occ) * num_sms;
+        }
+        constexpr int WPC = RM_THREADS / 32;
+        const i64 want = (L.npad + WPC * tri_rm_rows_per_warp - 1) / (WPC * tri_rm_rows_per_warp);
+        const int grid = (int)std::max<i64>(1, std::min<i64>(want, tri_grid_cap[ridx]));
+        // tiny levels (a handful of warps): every lane polls its own entries, one L2 round trip per dependency level; larger levels gate on
+        // the newest dependency first (two round trips on the critical row, but a spinning warp costs one sector per poll instead of ~50)
+        const int gate = (tri_prepoll && L.npad > tri_rm_gate_rows) ? 1 : 0;
+        TriParams prm{L.npad / 32, backward ? 1 : 0, tri_sleep_ns, gate, tri_gate_all, 0, 0u, 0, L.nonfree_pad, d_err, tri_pollmode, nullptr, tri_trace};
+        launch_resident(kern, grid, RM_THREADS, st, R.view(), (const double *)L.diag, (const double *)L.dinv, rin, self, out, rout, prm);
+      };
+      if (add_self) launch_rm(k_gs_tri_rm<B, true, false>);
+      else launch_rm(k_gs_tri_rm<B, false, true>);
+      launches += 2;
+      return;
+    }
     if (add_self) launch_small(k_gs_tri_small<B, true, false>);
     else launch_small(k_gs_tri_small<B, false, true>);
     launches += 2;
@@ -2402,6 +2473,10 @@ static void create_impl(const char *type, const ngsamg_csr *A, const uint8_t *fr
   a.tri_prepoll = (int)a.flags.num("b200_tri_prepoll", 1);
   a.tri_gate_all = (int)a.flags.num("b200_tri_gate_all", 1);
   a.tri_small_rows = (i64)a.flags.num("b200_tri_small_rows", 1000000);
+  a.tri_rm = (int)a.flags.num("b200_tri_rm", 1);
+  a.tri_rm_rows_per_warp = std::max(1, (int)a.flags.num("b200_tri_rm_rows_per_warp", 8));
+  a.tri_rm_gate_rows = (i64)a.flags.num("b200_tri_rm_gate_rows", 4096);
+  a.tri_rm_max_rows = (i64)a.flags.num("b200_tri_rm_max_rows", 100000);
   a.tri_gate_gap_levels = a.flags.num("b200_tri_gate_gap", 0.0);
   a.tri_level_launch_depth = (int)a.flags.num("b200_tri_level_launch_depth", 24);
   a.tri_level_launch_rows = (i64)a.flags.num("b200_tri_level_launch_rows", 131072);
@@ -3000,12 +3075,12 @@ int ngsamg_b200_pcg(ngsamg_b200_t *h, const double *rhs, double *x, double tol, 
 int ngsamg_b200_num_levels(ngsamg_b200_t *h) { return (h && h->amg.finalized) ? (int)h->amg.lev.size() : 0; }
 
 // which kernel sweeps the level: 0 row-level (k_gs_tri / k_gs_level / k_gs_tri_small), 1 warp per tile, 2 CTA per tile, 3 CTA per tile on
-// prepared tile images; -1 = no such level
+// prepared tile images, 4 warp per row on the row-major copy of a small level (k_gs_tri_rm); -1 = no such level
 int ngsamg_b200_level_sweep_kind(ngsamg_b200_t *h, int level)
 {
   if (!h || !h->amg.finalized || level < 0 || level >= (int)h->amg.lev.size()) return -1;
   const Level &L = *h->amg.lev[level];
-  if (!L.tiled) return 0;
+  if (!L.tiled) return (L.rmL.ptr && L.npad <= h->amg.tri_small_rows && !h->amg.level_launch(L)) ? 4 : 0;
   if (L.tile_maxs <= 2) return 1;
   return L.itile ? 3 : 2;
 }
@@ -3300,6 +3375,26 @@ int ngsamg_b200_profile_kernel(ngsamg_b200_t *h, int level, int which, int reps,
         std::fwrite(ht.data(), sizeof(unsigned long long), ht.size(), f);
         std::fclose(f);
       }
+    } else if ((which == 0 || which == 3) && L.rmL.ptr && a.tri_rm && L.npad <= a.tri_small_rows && !a.level_launch(L)) {
+      // row-major warp-per-row sweep: 12 stamps per row (see k_gs_tri_rm)
+      const i64 nr = L.npad;
+      a.tri_trace = dev_alloc<unsigned long long>(nr * 12);
+      NGB_CUDA(cudaMemsetAsync(a.tri_trace, 0, sizeof(unsigned long long) * nr * 12, a.st));
+      run();
+      NGB_CUDA(cudaStreamSynchronize(a.st));
+      std::vector<unsigned long long> ht(nr * 12);
+      NGB_CUDA(cudaMemcpy(ht.data(), a.tri_trace, sizeof(unsigned long long) * nr * 12, cudaMemcpyDeviceToHost));
+      dev_free(a.tri_trace);
+      a.tri_trace = nullptr;
+      std::string fn = std::string(tf) + ".l" + std::to_string(level) + (which == 0 ? ".rm.fwd" : ".rm.bwd");
+      if (FILE *f = std::fopen(fn.c_str(), "wb")) {
+        const i64 nl = (i64)L.level_start.size();
+        std::fwrite(&nr, sizeof(i64), 1, f);
+        std::fwrite(&nl, sizeof(i64), 1, f);
+        std::fwrite(L.level_start.data(), sizeof(i64), nl, f);
+        std::fwrite(ht.data(), sizeof(unsigned long long), ht.size(), f);
+        std::fclose(f);
+      }
     } else if (which == 0 || which == 3) {
       const i64 ns = L.npad / 32;
       a.tri_trace = dev_alloc<unsigned long long>(ns * 3);
@@ -3323,6 +3418,29 @@ int ngsamg_b200_profile_kernel(ngsamg_b200_t *h, int level, int which, int reps,
   }
   NGB_CUDA(cudaGetLastError());
   a.check_watchdog();
+  NGB_CATCH
+}
+
+// measurement aid: change a run-time tunable of the sweeps on a finalized hierarchy (the captured V-cycle graph is dropped)
+int ngsamg_b200_set_tunable(ngsamg_b200_t *h, const char *name, double value)
+{
+  NGB_TRY
+  Amg &a = ready(h);
+  const std::string k = name ? name : "";
+  if (k == "tri_sleep_ns") a.tri_sleep_ns = (unsigned)value;
+  else if (k == "tri_repoll_ns") a.tri_repoll_ns = (unsigned)value;
+  else if (k == "tri_prepoll") a.tri_prepoll = (int)value;
+  else if (k == "tri_pollmode") a.tri_pollmode = (int)value;
+  else if (k == "tri_rm") a.tri_rm = (int)value;
+  else if (k == "tri_rm_rows_per_warp") a.tri_rm_rows_per_warp = std::max(1, (int)value);
+  else if (k == "tri_rm_gate_rows") a.tri_rm_gate_rows = (i64)value;
+  else if (k == "tri_small_rows") a.tri_small_rows = (i64)value;
+  else if (k == "tri_level_launch_depth") a.tri_level_launch_depth = (int)value;
+  else if (k == "tri_level_launch_rows") a.tri_level_launch_rows = (i64)value;
+  else if (k == "spmv_small_rows") a.spmv_small_rows = (i64)value;
+  else if (k == "use_graph") a.use_graph = value != 0;
+  else throw Error("set_tunable: unknown tunable '" + k + "'");
+  if (a.vgraph) { NGB_CUDA(cudaStreamSynchronize(a.st)); cudaGraphExecDestroy(a.vgraph); a.vgraph = nullptr; }
   NGB_CATCH
 }
 

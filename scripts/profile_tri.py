@@ -19,6 +19,10 @@ if not diri:   # regularise the pure Neumann matrix
 A = ng.SparseMatrix(p["n"], p["n"], 1, 1, p["rowptr"], p["col"], val)
 print("dirichlet", diri)
 pc = ng.h1_scal(A, p["free"], **extra)
+for kv in os.environ.get("TUNABLES", "").split(","):
+    if "=" in kv:
+        k, v = kv.split("=", 1)
+        pc.SetTunable(k.strip(), float(v))
 for lvl in [int(x) for x in os.environ.get('LEVELS', '0').split(',')]:
     for name in os.environ.get("KERNELS", "gs_tri_fwd,gs_tri_bwd").split(","):
         ms, by = pc.ProfileKernel(name, level=lvl, reps=5)

@@ -348,12 +348,17 @@ def test_golden_fixtures_gpu():
 @pytest.mark.parametrize("flags", [dict(ngs_amg_b200_tri_small_rows=0), dict(ngs_amg_b200_tri_small_rows=0, ngs_amg_b200_tri_level_launch_depth=0),
                                    dict(ngs_amg_b200_tri_small_rows=0, ngs_amg_b200_tri_level_launch_depth=1000, ngs_amg_b200_tri_level_launch_rows=0),
                                    dict(ngs_amg_b200_tri_small_rows=0, ngs_amg_b200_tri_level_launch_rows=0, ngs_amg_b200_sm_order="multicolor"),
-                                   dict(ngs_amg_b200_spmv_small_rows=0)])
+                                   dict(ngs_amg_b200_spmv_small_rows=0), dict(), dict(ngs_amg_b200_tri_rm=0),
+                                   dict(ngs_amg_b200_tri_rm_rows_per_warp=64)])
 def test_sweep_kernel_variants(flags):
-    """every implementation of the triangular half-sweep (warp-per-row, sync-free thread-per-row, level-by-level launches)
-    forced on the same small problem: V-cycle and PCG must agree with the oracle"""
+    """every implementation of the triangular half-sweep (warp-per-row on the row-major copy [default on small levels] and on the SELL
+    layout, sync-free thread-per-row, level-by-level launches) forced on the same small problem: V-cycle and PCG must agree with the oracle"""
     p, A = poisson(12)
     pc = ng.h1_scal(A, p["free"], ngs_amg_max_coarse_size=20, **flags)
+    if not flags or "ngs_amg_b200_tri_rm_rows_per_warp" in flags:
+        assert all(pc.SweepKind(l) == "rows_rm" for l in range(pc.GetNLevels() - 1))
+    elif "ngs_amg_b200_tri_rm" in flags or ("ngs_amg_b200_tri_small_rows" in flags and "ngs_amg_b200_sm_order" not in flags):
+        assert pc.SweepKind(0) == "rows"
     if "ngs_amg_b200_sm_order" in flags:
         return _check_multicolor(p, A, pc)
     amg = O.OracleAMG(to_oracle(A), p["free"], [to_oracle(P) for P in pc.GetMap()])
@@ -363,6 +368,32 @@ def test_sweep_kernel_variants(flags):
     cg.Solve(p["rhs"])
     _, ito, _ = amg.pcg(p["rhs"], tol=1e-8, maxsteps=60)
     assert cg.iterations == ito
+
+
+@pytest.mark.parametrize("bw", [40, 150])
+def test_wide_rows_on_a_small_level(bw):
+    """rows with more entries per triangle than the row-major sweep prefetches (2 x 32 for scalar matrices): a banded SPD matrix with
+    2*bw + 1 entries per row, two levels through injected piecewise-constant maps"""
+    import scipy.sparse as sp
+    n = 700
+    rng = np.random.default_rng(5)
+    diags = [rng.uniform(-1.0, -0.1, n - k) for k in range(1, bw + 1)]
+    Lo = sp.diags(diags, [-k for k in range(1, bw + 1)], shape=(n, n))
+    M = (Lo + Lo.T).tocsr()
+    M = (M + sp.diags(np.asarray(abs(M).sum(axis=1)).ravel() + 1.0)).tocsr()
+    M.sort_indices()
+    A = ng.SparseMatrix(n, n, 1, 1, M.indptr.astype(np.int64), M.indices.astype(np.int32), M.data)
+    nc = n // 4
+    free = np.ones(n, np.uint8)
+    free[::37] = 0
+    keep = free.astype(bool)                          # non-free vertices have empty rows in P (vertex_factory_impl.hpp:1624-1626)
+    rp = np.concatenate([[0], np.cumsum(keep)]).astype(np.int64)
+    P = ng.SparseMatrix(n, nc, 1, 1, rp, (np.arange(n) // 4)[keep].astype(np.int32), np.ones(int(keep.sum())))
+    pc = ng.h1_scal(A, free, prolongations=[P], ngs_amg_clev="none", ngs_amg_b200_color_coarse=0)
+    assert pc.SweepKind(0) == "rows_rm"
+    amg = O.OracleAMG(to_oracle(A), free, [to_oracle(P)], clev="none")
+    b = rand(41, n)
+    assert rel(pc * b, amg.apply(b)) < TOL_VCYCLE
 
 
 def _check_multicolor(p, A, pc):
