@@ -33,6 +33,7 @@ inline i64 round32(i64 n) { return (n + 31) / 32 * 32; }
 struct Sell {
   i64 nrows_pad = 0, nslices = 0, total_slots = 0, nnz = 0;
   int bh = 1, bw = 1;
+  i64 maxw = 0;          // slice width covering 97 % of the slices (0 = unknown): picks the row walk of the scalar SpMV (launch_spmv)
   i64 *slice_ptr = nullptr;
   i32 *col = nullptr;
   double *val = nullptr;
@@ -474,6 +475,22 @@ void build_sell(i64 nrows_pad, int bh, int bw, const i32 *d_len, Sell &S, cudaSt
   if (launches) *launches += 2;
 }
 
+// width that covers 97 % of the slices (the masked walks handle wider slices correctly, just with more blocks)
+i64 sell_max_width(const Sell &S, cudaStream_t st)
+{
+  std::vector<i64> sp(S.nslices + 1);
+  NGB_CUDA(cudaMemcpyAsync(sp.data(), S.slice_ptr, sizeof(i64) * (S.nslices + 1), cudaMemcpyDeviceToHost, st));
+  NGB_CUDA(cudaStreamSynchronize(st));
+  std::vector<i64> hist(66, 0);
+  for (i64 q = 0; q < S.nslices; q++) hist[std::min<i64>(sp[q + 1] - sp[q], 65)]++;
+  i64 acc = 0;
+  for (int w = 0; w < 66; w++) {
+    acc += hist[w];
+    if (acc >= 0.97 * (double)S.nslices) return std::max(w, 1);
+  }
+  return 65;
+}
+
 // dense inverse of an SPD-ish matrix by Gauss-Jordan with partial pivoting (host, setup only)
 bool dense_invert(int n, std::vector<double> &a)
 {
@@ -757,6 +774,8 @@ void Amg::build_level_layout(Level &L, const DevCsr &dA)
     const int force = (int)flags.num("b200_tri_pre", 0);
     L.pre_l = force ? force : pick(L.L);
     L.pre_u = force ? force : pick(L.U);
+    L.L.maxw = sell_max_width(L.L, st);
+    L.U.maxw = sell_max_width(L.U, st);
   }
   // dinv (GSS3::CalcDiags); the hybrid smoother passes a replacement diagonal (GSS3(A, repl_diag, ...), gssmoother.cpp:93-107)
   int *d_err = dev_alloc<int>(1);
@@ -1056,6 +1075,7 @@ void Amg::build_transfer_layout(Level &F, Level &C)
                                             F.P.val, nullptr, nullptr, nullptr, nullptr, 0, nullptr, nullptr, nullptr);
     F.P.nnz = dP.nnz;
     dev_free(len);
+    F.P.maxw = sell_max_width(F.P, st);
   }
   {
     // restriction matrix: rows stored sorted by length (uniform slices => little SELL padding); the kernel scatters its result
@@ -1919,8 +1939,16 @@ static void launch_spmv(cudaStream_t st, i64 small_rows, i64 npad, const Sell &a
                                                          xadd, s3, rowmap);
     return;
   }
-  k_sell_spmv<BH, BW, S2, D><<<nblk(npad), TB, 0, st>>>(npad, a.view(), b ? b->view() : a.view(), diag, v, y_in, y_out, alpha, beta, xadd,
-                                                       s3, rowmap);
+  // scalar matrices: rows of at most 4 / 8 slots are walked as ONE masked block of batched loads (prolongation; level-0 U-pass);
+  // everything else keeps the legacy walk (measured at 311^3: prolong 0.49 -> 0.34 ms, U-pass 0.69 -> 0.62 ms; the (L+D)-pass, the
+  // full SpMV and the level-1 passes lose occupancy / pipelining with the batched walk and stay on the legacy one)
+  if (BH == 1 && BW == 1 && !S2 && !D && !b && a.maxw > 0 && a.maxw <= 4)
+    k_sell_spmv<BH, BW, S2, D, 4><<<nblk(npad), TB, 0, st>>>(npad, a.view(), a.view(), diag, v, y_in, y_out, alpha, beta, xadd, s3, rowmap);
+  else if (BH == 1 && BW == 1 && !S2 && !D && !b && !rowmap && a.maxw > 0 && a.maxw <= 8)
+    k_sell_spmv<BH, BW, S2, D, 8><<<nblk(npad), TB, 0, st>>>(npad, a.view(), a.view(), diag, v, y_in, y_out, alpha, beta, xadd, s3, rowmap);
+  else
+    k_sell_spmv<BH, BW, S2, D, 0><<<nblk(npad), TB, 0, st>>>(npad, a.view(), b ? b->view() : a.view(), diag, v, y_in, y_out, alpha, beta, xadd,
+                                                            s3, rowmap);
 }
 
 void Amg::spmv_part(Level &L, int which, const double *v, const double *y_in, double *y_out, double alpha, double beta, double *xadd)

@@ -65,9 +65,35 @@ __device__ __forceinline__ void sell_row_mac(const SellView &S, i64 slice, int l
   }
 }
 
-// scalar fast path: issue all loads of the row before the FMAs (more bytes in flight per thread)
+// scalar fast path: the row is walked in blocks of U slots; ALL loads of a block (columns, values, then the gathered vector
+// entries) are issued before its FMAs, the tail block is masked instead of falling back to one slot at a time -- a slice of width 7
+// costs one round of dependent latencies (column -> gather), not four; a prolongation row (width <= 3) one instead of three.
+// predicated loads as volatile asm: the compiler keeps volatile asm statements in program order, so the loads of a block are ISSUED as
+// a batch (with plain C++ loads ptxas interleaves them with the FMAs to stay within 32 registers and the batch degenerates into a chain)
+__device__ __forceinline__ i32 ldp_nc_i32(const i32 *p, bool pred)
+{
+  i32 v;
+  asm volatile("{ .reg .pred q; setp.ne.b32 q, %2, 0; mov.b32 %0, -1; @q ld.global.nc.s32 %0, [%1]; }" : "=r"(v) : "l"(p), "r"((int)pred));
+  return v;
+}
+__device__ __forceinline__ double ldp_nc_f64(const double *p, bool pred)
+{
+  double v;
+  asm volatile("{ .reg .pred q; setp.ne.b32 q, %2, 0; mov.b64 %0, 0; @q ld.global.nc.f64 %0, [%1]; }" : "=d"(v) : "l"(p), "r"((int)pred));
+  return v;
+}
+__device__ __forceinline__ double ldp_f64(const double *p, bool pred, bool cg)
+{
+  double v;
+  if (cg) asm volatile("{ .reg .pred q; setp.ne.b32 q, %2, 0; mov.b64 %0, 0; @q ld.global.cg.f64 %0, [%1]; }" : "=d"(v) : "l"(p), "r"((int)pred));
+  else asm volatile("{ .reg .pred q; setp.ne.b32 q, %2, 0; mov.b64 %0, 0; @q ld.global.f64 %0, [%1]; }" : "=d"(v) : "l"(p), "r"((int)pred));
+  return v;
+}
+
+// legacy walk: blocks of 4 slots, then one slot at a time (the compiler pipelines the blocks of wide rows; best for wide slices and for
+// the register-heavy kernel variants)
 template <bool CG>
-__device__ __forceinline__ double sell_row_dot1(const SellView &S, i64 slice, int lane, const double *__restrict__ x)
+__device__ __forceinline__ double sell_row_dot1_legacy(const SellView &S, i64 slice, int lane, const double *__restrict__ x)
 {
   const i64 base = S.slice_ptr[slice];
   const int width = (int)(S.slice_ptr[slice + 1] - base);
@@ -93,12 +119,38 @@ __device__ __forceinline__ double sell_row_dot1(const SellView &S, i64 slice, in
   return s0 + s1;
 }
 
+// U = 0 selects the legacy walk
+template <bool CG, int U = 0>
+__device__ __forceinline__ double sell_row_dot1(const SellView &S, i64 slice, int lane, const double *__restrict__ x)
+{
+  if constexpr (U == 0) return sell_row_dot1_legacy<CG>(S, slice, lane, x);
+  constexpr int UU = U ? U : 4;
+  const i64 base = S.slice_ptr[slice];
+  const int width = (int)(S.slice_ptr[slice + 1] - base);
+  const i32 *cp = S.col + base * 32 + lane;
+  const double *vp = S.val + base * 32 + lane;
+  double s0 = 0.0, s1 = 0.0;
+  for (int k = 0; k < width; k += UU) {
+    i32 c[UU];
+    double v[UU], xv[UU];
+#pragma unroll
+    for (int j = 0; j < UU; j++) c[j] = ldp_nc_i32(cp + (i64)(k + j) * 32, k + j < width);
+#pragma unroll
+    for (int j = 0; j < UU; j++) v[j] = ldp_nc_f64(vp + (i64)(k + j) * 32, k + j < width);
+#pragma unroll
+    for (int j = 0; j < UU; j++) xv[j] = ldp_f64(x + (c[j] >= 0 ? c[j] : 0), c[j] >= 0, CG);
+#pragma unroll
+    for (int j = 0; j < UU; j += 2) { s0 = fma(v[j], xv[j], s0); if (j + 1 < UU) s1 = fma(v[j + 1], xv[j + 1], s1); }
+  }
+  return s0 + s1;
+}
+
 // ------------------------------------------------------------------------------------------------
 // K1/K2b/K3a/K5/K6: y_out = beta*y_in + alpha*(S1 v [+ S2 v] [+ D v]);  optionally xadd += v (own rows)
 //   plain SpMV (S1=L,S2=U,D), the U-pass of the forward sweep, the (L+D)-pass of the backward sweep,
 //   restriction (S1=PT) and prolongation-add (S1=P).  Thread per block row, warp per slice.
 // ------------------------------------------------------------------------------------------------
-template <int BH, int BW, bool HAS_S2, bool HAS_D>
+template <int BH, int BW, bool HAS_S2, bool HAS_D, int U = 0>
 __global__ void __launch_bounds__(256) k_sell_spmv(i64 nrows_pad, SellView S1, SellView S2, const double *__restrict__ diag,
                                                   const double *__restrict__ v, const double *y_in, double *y_out,
                                                   double alpha, double beta, double *xadd, SellView S3, const i32 *__restrict__ rowmap)
@@ -111,15 +163,18 @@ __global__ void __launch_bounds__(256) k_sell_spmv(i64 nrows_pad, SellView S1, S
   double acc[BH];
 #pragma unroll
   for (int p = 0; p < BH; p++) acc[p] = 0.0;
+  // scalar case without a row map: y_in is requested up front (it is only needed by the epilogue, after two dependent latencies)
+  double yin0 = 0.0;
+  if (U != 0 && BH == 1 && BW == 1 && !rowmap && beta != 0.0) yin0 = y_in[row];
   if (BH == 1 && BW == 1) {
-    acc[0] = sell_row_dot1<false>(S1, slice, lane, v);
-    if (HAS_S2) acc[0] += sell_row_dot1<false>(S2, slice, lane, v);
+    acc[0] = sell_row_dot1<false, U>(S1, slice, lane, v);
+    if (HAS_S2) acc[0] += sell_row_dot1<false, U>(S2, slice, lane, v);
   } else {
     sell_row_mac<BH, BW, false>(S1, slice, lane, v, acc, 1.0);
     if (HAS_S2) sell_row_mac<BH, BW, false>(S2, slice, lane, v, acc, 1.0);
   }
   if (HAS_D && S3.slice_ptr) {   // couplings to non-free rows travel with the diagonal (see k_layout_count)
-    if (BH == 1 && BW == 1) acc[0] += sell_row_dot1<false>(S3, slice, lane, v);
+    if (BH == 1 && BW == 1) acc[0] += sell_row_dot1<false, 0>(S3, slice, lane, v);
     else sell_row_mac<BH, BW, false>(S3, slice, lane, v, acc, 1.0);
   }
   if (HAS_D || xadd) {
@@ -143,7 +198,7 @@ __global__ void __launch_bounds__(256) k_sell_spmv(i64 nrows_pad, SellView S1, S
 #pragma unroll
   for (int p = 0; p < BH; p++) {
     double y = alpha * acc[p];
-    if (beta != 0.0) y = fma(beta, y_in[orow * BH + p], y);
+    if (beta != 0.0) y = fma(beta, (U != 0 && BH == 1 && BW == 1 && !rowmap) ? yin0 : y_in[orow * BH + p], y);
     y_out[orow * BH + p] = y;
   }
 }
