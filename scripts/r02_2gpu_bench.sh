@@ -1,8 +1,8 @@
 #!/usr/bin/env bash
 set -u
-OUT=gpurun_out/r02_2gpu_b
+OUT=gpurun_out/r02_s2_2gpu
 mkdir -p "$OUT"
-timeout 1200 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus 2 --steps 5 --warmup 3 > $OUT/bench2.log 2>&1; echo "rc=$?"
+timeout 1200 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus 2 --steps 3 --warmup 3 > $OUT/bench2.log 2>&1; echo "rc=$?"
 python - "$OUT/bench2.log" <<'PY'
 import json,sys
 for l in open(sys.argv[1]):
