@@ -462,7 +462,14 @@ def main():
             for l in range(nested.GetNLevels()):
                 i = nested.level_info(l)
                 levels.append({"n": int(i.n), "b": int(i.b), "nnz": int(i.nnz), "gs_depth": int(i.gs_depth), "contracted_on_rank0": True})
-        par_info = {"distributed_levels": npar, "transport": "nccl p2p" if comm.nccl else "host-staged (gloo callbacks)",
+        # one DIS2CO + one CO2CU of every distributed level, timed back to back (collective; no skew from the sweeps in between)
+        ex_ms = []
+        for l in range(npar):
+            ms, _ = pc.ProfileKernel("halo_exchange", level=l, reps=20)
+            ex_ms.append(round(ms, 4))
+        par_info = {"distributed_levels": npar, "transport": {"peer_memory": "NVLink peer memory (IPC-mapped receive buffers, push/pull kernels); NCCL for the coarse gather and the dot products",
+                                                              "nccl": "nccl p2p", "host": "host-staged (gloo callbacks)"}[pc.HaloTransport(0)],
+                    "halo_exchange_pair_ms_by_level": ex_ms,
                     "host_exchanges_setup": comm.n_exchange, "box_grid": list(grid), "neighbours_rank0": len(p["peers"]),
                     "shared_dofs_rank0": int(sum(len(e) for e in p["ex"])), "global_dims": list(p["global_dims"])}
 

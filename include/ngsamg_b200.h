@@ -209,6 +209,9 @@ int ngsamg_b200_get_hybrid(ngsamg_b200_t *h, int level, int which, int64_t *nnz,
                            double *mod_diag);
 /* number of distributed levels (levels 0 .. npar-1 are smoothed on every rank; level npar is contracted onto rank 0) */
 int ngsamg_b200_num_parallel_levels(ngsamg_b200_t *h);
+/* transport of the per-sweep halo exchange of a distributed level: 0 host-staged through the callbacks, 1 NCCL send/recv, 2 NVLink peer
+ * memory (IPC-mapped receive buffers, push / pull kernels -- the default with an NCCL communicator); -1 = not a distributed level */
+int ngsamg_b200_halo_transport(ngsamg_b200_t *h, int level);
 /* rank 0 only: the serial hierarchy below the contracted level (borrowed handle; all single-rank entry points work on it) and,
  * for every rank r, the map local DOF of the contracted level -> DOF of the merged level (CtrMap dof_maps). */
 ngsamg_b200_t *ngsamg_b200_get_contracted(ngsamg_b200_t *h);

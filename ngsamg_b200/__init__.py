@@ -326,7 +326,7 @@ class Preconditioner:
         return int(self._lib.ngsamg_b200_launch_count(self._h))
 
     KERNELS = {"gs_tri_fwd": 0, "gs_upass": 1, "gs_lpass": 2, "gs_tri_bwd": 3, "spmv": 4, "restrict": 5, "prolong": 6, "gs_tri_fwd_rhs": 7,
-               "gs_tri_bwd_res": 8}
+               "gs_tri_bwd_res": 8, "halo_exchange": 9}
 
     def ProfileKernel(self, which, level=0, reps=10):
         """(avg ms per launch, algorithmic bytes per launch) of one V-cycle kernel, CUDA events on the library stream"""

@@ -8,6 +8,7 @@
 #include <mutex>
 
 #include <dlfcn.h>
+#include <unistd.h>
 #include <nccl.h>   // types only: the library is dlopen'ed (libnccl.so.2), nothing links against it
 
 #include "../../include/ngsamg_b200.h"
@@ -17,6 +18,7 @@
 #include "kernels_ctile.cuh"
 #include "kernels_itile.cuh"
 #include "kernels_rm.cuh"
+#include "kernels_p2p.cuh"
 #include "par.hpp"
 #include "tiles.hpp"
 
@@ -103,6 +105,13 @@ struct Level {
   i64 *d_mu_ptr = nullptr, *d_mu_pos = nullptr;
   i64 n_mu = 0;
   double *sendbuf = nullptr, *recvbuf = nullptr, *h_send = nullptr, *h_recv = nullptr;
+  // peer-memory halo exchange (kernels_p2p.cuh): one IPC-exported arena per level [recv 2 x cap doubles | flag | ack | cnt | seq]
+  bool p2p = false;
+  unsigned char *p2p_arena = nullptr;
+  std::vector<void *> p2p_opened;    // arenas of the neighbours mapped with cudaIpcOpenMemHandle
+  P2PPeer *d_p2p_peer = nullptr;
+  i64 *d_m_off = nullptr, *d_g_off = nullptr;
+  P2PView p2p_view{};
   const std::vector<uint8_t> &mask() const { return par ? gs_mask : free_mask; }
   // ---- experimental two-level (tile) schedule of the triangular sweeps (flag b200_tile_sweep, tiles.hpp / kernels_tile.cuh)
   bool tiled = false;
@@ -268,6 +277,8 @@ struct Amg {
   i64 exchanges = 0;
   void finalize_parallel();
   void build_halo(Level &L);
+  void setup_p2p(Level &L);           // collective: exchange the IPC handles of the receive arenas of one distributed level
+  bool halo_p2p = false;
   void dev_exchange(const std::vector<i32> &peers, const double *sendbuf, const std::vector<i64> &soff, double *recvbuf,
                     const std::vector<i64> &roff, double *h_send, double *h_recv);
   void dis2co(Level &L, double *v);   // DCCMap::StartDIS2CO + ApplyDIS2CO: ghost values travel to the master and are added there
@@ -677,6 +688,8 @@ Amg::~Amg()
     for (int d = 0; d < 2; d++) { dev_free(L.d_img[d]); dev_free(L.d_imeta[d]); }
     dev_free(L.d_m_idx); dev_free(L.d_g_idx); dev_free(L.d_mu_dof); dev_free(L.d_mu_ptr); dev_free(L.d_mu_pos);
     dev_free(L.sendbuf); dev_free(L.recvbuf);
+    for (void *q : L.p2p_opened) cudaIpcCloseMemHandle(q);
+    dev_free(L.p2p_arena); dev_free(L.d_p2p_peer); dev_free(L.d_m_off); dev_free(L.d_g_off);
     if (L.h_send) cudaFreeHost(L.h_send);
     if (L.h_recv) cudaFreeHost(L.h_recv);
     dev_free(L.d_perm); dev_free(L.d_freep); dev_free(L.d_pt_rowmap); dev_free(L.d_bnd_fwd); dev_free(L.d_bnd_bwd);
@@ -1402,6 +1415,67 @@ void Amg::build_halo(Level &L)
   }
 }
 
+// Peer-memory halo exchange of one distributed level (kernels_p2p.cuh).  Collective over the ranks; on any failure (no peer access, IPC
+// not available) every rank falls back to the NCCL path.
+void Amg::setup_p2p(Level &L)
+{
+  struct Msg {
+    cudaIpcMemHandle_t handle;
+    i64 cap, m_off, g_off;
+    i32 slot, pid, np, pad;
+    unsigned long long raw;
+  };
+  const size_t np = L.peers.size();
+  const i64 cap = std::max<i64>(std::max(L.m_off[np], L.g_off[np]), 1) * L.b;
+  const size_t ctl_off = sizeof(double) * 2 * (size_t)cap;
+  const size_t bytes = ctl_off + sizeof(int) * (3 * np + 2);
+  double ok = 1.0;
+  std::vector<Msg> out(np), in(np);
+  try {
+    L.p2p_arena = dev_alloc<unsigned char>(bytes);
+    NGB_CUDA(cudaMemsetAsync(L.p2p_arena, 0, bytes, st));
+    NGB_CUDA(cudaStreamSynchronize(st));
+    cudaIpcMemHandle_t h;
+    NGB_CUDA(cudaIpcGetMemHandle(&h, L.p2p_arena));
+    for (size_t k = 0; k < np; k++) out[k] = Msg{h, cap, L.m_off[k], L.g_off[k], (i32)k, (i32)getpid(), (i32)np, 0, (unsigned long long)(uintptr_t)L.p2p_arena};
+  } catch (const Error &) { ok = 0.0; cudaGetLastError(); }
+  {
+    std::vector<const void *> sp;
+    std::vector<void *> rp;
+    std::vector<i64> sb(np, (i64)sizeof(Msg)), rb(np, (i64)sizeof(Msg));
+    for (size_t k = 0; k < np; k++) { sp.push_back(&out[k]); rp.push_back(&in[k]); }
+    comm.exchange_fixed(L.peers, sp, sb, rp, rb);
+  }
+  std::vector<P2PPeer> tab(np);
+  if (ok > 0) {
+    for (size_t k = 0; k < np; k++) {
+      void *base = nullptr;
+      if (in[k].pid == (i32)getpid()) base = (void *)(uintptr_t)in[k].raw;      // ranks that share a process
+      else {
+        if (cudaIpcOpenMemHandle(&base, in[k].handle, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { ok = 0.0; cudaGetLastError(); break; }
+        L.p2p_opened.push_back(base);
+      }
+      // the neighbour's control words: flag[np'] | ack[np'] | cnt | seq -- this rank's slot in both arrays
+      int *ctl = (int *)((unsigned char *)base + sizeof(double) * 2 * (size_t)in[k].cap);
+      tab[k] = P2PPeer{(double *)base, ctl + in[k].slot, ctl + in[k].np + in[k].slot, in[k].cap, in[k].m_off, in[k].g_off};
+    }
+  }
+  comm.allreduce_sum(&ok, 1);
+  if (ok < comm.size()) {
+    for (void *q : L.p2p_opened) cudaIpcCloseMemHandle(q);
+    L.p2p_opened.clear();
+    dev_free(L.p2p_arena);
+    L.p2p = false;
+    return;
+  }
+  L.d_p2p_peer = upload_vec(tab, st);
+  L.d_m_off = upload_vec(L.m_off, st);
+  L.d_g_off = upload_vec(L.g_off, st);
+  int *ctl = (int *)(L.p2p_arena + ctl_off);
+  L.p2p_view = P2PView{(int)np, L.d_p2p_peer, (double *)L.p2p_arena, cap, ctl, ctl + np, ctl + 2 * np, ctl + 3 * np + 1, L.d_m_off, L.d_g_off, d_err};
+  L.p2p = true;
+}
+
 // One neighbour exchange of doubles on the library stream.  NCCL point-to-point (NVLink) when a communicator was given, else
 // staged through pinned host memory and the caller's exchange callback.
 void Amg::dev_exchange(const std::vector<i32> &peers, const double *sendbuf, const std::vector<i64> &soff, double *recvbuf,
@@ -1451,6 +1525,13 @@ void Amg::dis2co(Level &L, double *v)
   const size_t np = L.peers.size();
   if (np == 0) { exchanges++; if (!nccl) NGB_CUDA(cudaStreamSynchronize(st)); return; }
   const i64 ng = L.g_off[np], nm = L.m_off[np];
+  if (L.p2p) {
+    exchanges++;
+    k_p2p_push<<<(unsigned)(np * P2P_CPB), P2P_THREADS, 0, st>>>(L.p2p_view, 0, L.b, L.d_g_idx, v);
+    k_p2p_pull<<<std::max(1u, nblk(L.n_mu * L.b, P2P_THREADS)), P2P_THREADS, 0, st>>>(L.p2p_view, 0, L.b, L.n_mu, L.d_mu_dof, L.d_mu_ptr, L.d_mu_pos, v);
+    launches += 2;
+    return;
+  }
   if (ng) { k_halo_pack<<<nblk(ng * L.b), TB, 0, st>>>(ng, L.b, L.d_g_idx, v, L.sendbuf, 1); launches++; }
   dev_exchange(L.peers, L.sendbuf, scaled(L.g_off, L.b), L.recvbuf, scaled(L.m_off, L.b), L.h_send, L.h_recv);
   if (nm) { k_halo_add<<<nblk(L.n_mu * L.b), TB, 0, st>>>(L.n_mu, L.b, L.d_mu_dof, L.d_mu_ptr, L.d_mu_pos, L.recvbuf, v); launches++; }
@@ -1462,6 +1543,13 @@ void Amg::co2cu(Level &L, double *v)
   const size_t np = L.peers.size();
   if (np == 0) { exchanges++; if (!nccl) NGB_CUDA(cudaStreamSynchronize(st)); return; }
   const i64 ng = L.g_off[np], nm = L.m_off[np];
+  if (L.p2p) {
+    exchanges++;
+    k_p2p_push<<<(unsigned)(np * P2P_CPB), P2P_THREADS, 0, st>>>(L.p2p_view, 1, L.b, L.d_m_idx, v);
+    k_p2p_pull<<<std::max(1u, nblk(ng * L.b, P2P_THREADS)), P2P_THREADS, 0, st>>>(L.p2p_view, 1, L.b, ng, L.d_g_idx, nullptr, nullptr, v);
+    launches += 2;
+    return;
+  }
   if (nm) { k_halo_pack<<<nblk(nm * L.b), TB, 0, st>>>(nm, L.b, L.d_m_idx, v, L.sendbuf, 0); launches++; }
   dev_exchange(L.peers, L.sendbuf, scaled(L.m_off, L.b), L.recvbuf, scaled(L.g_off, L.b), L.h_send, L.h_recv);
   if (ng) { k_halo_set<<<nblk(ng * L.b), TB, 0, st>>>(ng, L.b, L.d_g_idx, L.recvbuf, v); launches++; }
@@ -1724,6 +1812,7 @@ void Amg::finalize_parallel()
     }
     build_plain_sell(L.hG, L.d_perm, L.d_perm, L.npad, L.G, st, &launches);
     build_halo(L);
+    if (nccl && halo_p2p) setup_p2p(L);
     alloc_vectors(L);
     dev_csr_free(dA);
     dA = dAc;
@@ -2502,6 +2591,9 @@ static void create_impl(const char *type, const ngsamg_csr *A, const uint8_t *fr
   a.tri_gate_all = (int)a.flags.num("b200_tri_gate_all", 1);
   a.tri_small_rows = (i64)a.flags.num("b200_tri_small_rows", 1000000);
   a.tri_rm = (int)a.flags.num("b200_tri_rm", 1);
+  // opt-in: measured on 2 GPUs a DIS2CO + CO2CU pair costs 41 / 37 us (levels 0 / 1) over ncclSend/ncclRecv and 54 / 34 us through the
+  // peer-memory kernels (profiles/r02_bench_2gpu_halo_ab.txt) -- no gain yet, NCCL stays the default
+  a.halo_p2p = a.flags.flag("b200_halo_p2p", false);
   a.tri_rm_rows_per_warp = std::max(1, (int)a.flags.num("b200_tri_rm_rows_per_warp", 8));
   a.tri_rm_gate_rows = (i64)a.flags.num("b200_tri_rm_gate_rows", 4096);
   a.tri_rm_max_rows = (i64)a.flags.num("b200_tri_rm_max_rows", 100000);
@@ -2645,6 +2737,14 @@ int ngsamg_b200_get_hybrid(ngsamg_b200_t *h, int level, int which, int64_t *nnz,
 }
 
 int ngsamg_b200_num_parallel_levels(ngsamg_b200_t *h) { return (h && h->amg.finalized && h->amg.par) ? h->amg.npar : 0; }
+
+// transport of the per-sweep halo exchange of `level`: 0 host-staged callbacks, 1 NCCL send/recv, 2 NVLink peer memory; -1 = not a distributed level
+int ngsamg_b200_halo_transport(ngsamg_b200_t *h, int level)
+{
+  if (!h || !h->amg.finalized || !h->amg.par || level < 0 || level >= h->amg.npar) return -1;
+  const Level &L = *h->amg.lev[level];
+  return L.p2p ? 2 : (h->amg.nccl ? 1 : 0);
+}
 
 ngsamg_b200_t *ngsamg_b200_get_contracted(ngsamg_b200_t *h)
 {
@@ -3364,6 +3464,7 @@ int ngsamg_b200_profile_kernel(ngsamg_b200_t *h, int level, int which, int reps,
       case 6: a.transfer(L.P, C.x, L.x, L.x, 1.0, 1.0); B = pb + 2 * v + vc; break;
       case 7: a.tri_dispatch(L, false, true, false, L.tmp, L.x, L.y, nullptr); B = L.L.nnz * bb + D + 3 * v; break;   // forward, RHS form
       case 8: a.tri_dispatch(L, true, false, true, L.rhs, nullptr, L.x, L.res); B = L.U.nnz * bb + 2 * D + 3 * v; break;  // backward, RES form
+      case 9: a.dis2co(L, L.tmp); a.co2cu(L, L.tmp); B = 0; break;   // one DIS2CO + one CO2CU halo exchange (collective over the ranks)
       default: throw Error("profile_kernel: unknown kernel id");
     }
   };

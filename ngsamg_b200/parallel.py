@@ -264,6 +264,10 @@ class ParallelPreconditioner(Preconditioner):
     def GetNParallelLevels(self):
         return int(self._lib.ngsamg_b200_num_parallel_levels(self._h))
 
+    def HaloTransport(self, level=0):
+        """'host' | 'nccl' | 'peer_memory' (kernels_p2p.cuh) -- how the DIS2CO / CO2CU exchanges of a distributed level travel"""
+        return {0: "host", 1: "nccl", 2: "peer_memory", -1: "none"}[int(self._lib.ngsamg_b200_halo_transport(self._h, int(level)))]
+
     def GetHalo(self, level):
         npeers = C.c_int32()
         _lib.check(self._lib.ngsamg_b200_get_halo(self._h, int(level), C.byref(npeers), None, None, None))

@@ -36,10 +36,13 @@ def main():
     p = parts[rank]
     A = ng.SparseMatrix(p["n"], p["n"], 1, 1, p["rowptr"], p["col"], p["val"])
     ok = True
-    for graph in (0, 1):
+    # graph: the whole distributed V-cycle captured into a CUDA graph; p2p: halo exchange through NVLink peer memory
+    # (kernels_p2p.cuh, IPC-mapped receive buffers) instead of ncclSend/ncclRecv
+    for graph, p2p in ((0, 0), (1, 0), (0, 1), (1, 1)):
         pc = par.h1_scal_par(A, par.Halo(p["peers"], p["ex"]), comm, p["free"], device=local, ngs_amg_max_coarse_size=15,
-                             ngs_amg_b200_ctr_nv=400, ngs_amg_b200_cuda_graph_par=graph)
+                             ngs_amg_b200_ctr_nv=400, ngs_amg_b200_cuda_graph_par=graph, ngs_amg_b200_halo_p2p=p2p)
         npar = pc.GetNParallelLevels()
+        assert pc.HaloTransport(0) == ("peer_memory" if p2p else "nccl"), pc.HaloTransport(0)
         mine = dict(prols=[pc.GetProlongation(l) for l in range(npar)], halos=[(list(pc.GetHalo(l).peers), [np.asarray(e) for e in pc.GetHalo(l).ex]) for l in range(npar + 1)])
         if rank == 0:
             mine["maps"] = [pc.GetContractionMap(r) for r in range(size)]
@@ -62,8 +65,8 @@ def main():
         e2 = rel(xd.cpu().numpy(), uo[rank])
         good = e1 < 1e-10 and it == ito and e2 < 1e-8
         ok &= good
-        print("rank %d graph=%d: distributed levels %d, V-cycle rel err %.2e, PCG its %d (oracle %d), solution rel err %.2e -> %s"
-              % (rank, graph, npar, e1, it, ito, e2, "ok" if good else "FAIL"), flush=True)
+        print("rank %d graph=%d halo=%s: distributed levels %d, V-cycle rel err %.2e, PCG its %d (oracle %d), solution rel err %.2e -> %s"
+              % (rank, graph, pc.HaloTransport(0), npar, e1, it, ito, e2, "ok" if good else "FAIL"), flush=True)
         del pc
     flag = torch.tensor([0.0 if ok else 1.0], device="cuda")
     dist.all_reduce(flag)
