@@ -98,6 +98,13 @@ class ClockSampler:
 def make_problem(n, problem="poisson"):
     from ngsamg_b200 import synthetic as S
     import ngsamg_b200 as ng
+    if problem == "elasticity_p2":
+        # BASELINE.json configs[2]: nodal-P2 elasticity beam (examples/elasticity/beamP2.py; AMG on all P2 nodes, `subset=nodalp2`):
+        # n x (n/3) x (n/3) vertices -> (2n-1) x ... P2 nodes with 3 DOFs each; n = 151 gives 3.07 M nodes = 9.2 M DOFs
+        ny = max(3, n // 3 + 1)
+        p = S.elasticity3d_p2_kuhn_stencil(n, ny, ny)
+        A = ng.SparseMatrix(p["n"], p["n"], 3, 3, p["rowptr"], p["col"], p["val"])
+        return p, A
     if problem == "elasticity":
         # P1 elasticity beam (3x3 blocks, 6x6 on the coarse levels): nx x (nx/2) x (nx/2) vertices, clamped at x=0, body force (0,x,0)
         p = S.elasticity3d_kuhn_stencil(n, n // 2 + 1, n // 2 + 1)
@@ -262,8 +269,9 @@ def main():
     ap.add_argument("--cpu-n", type=int, default=int(os.environ.get("NGSAMG_BENCH_CPU_N", CPU_SAMPLE_N)))
     ap.add_argument("--cpu-n-par", type=int, default=int(os.environ.get("NGSAMG_BENCH_CPU_N_PAR", 61)),
                     help="vertices per axis and rank of the multi-rank CPU reference arm (N > 1)")
-    ap.add_argument("--problem", default="poisson", choices=["poisson", "elasticity"],
-                    help="poisson = BASELINE.json configs[1] (headline); elasticity = P1 beam with elast_3d (secondary, reported on request)")
+    ap.add_argument("--problem", default="poisson", choices=["poisson", "elasticity", "elasticity_p2"],
+                    help="poisson = BASELINE.json configs[1] (headline); elasticity = P1 beam with elast_3d; elasticity_p2 = BASELINE.json "
+                         "configs[2], nodal-P2 beam (--size 151 = 9.2 M DOFs); both secondary, reported on request")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-multicolor", action="store_true", help="skip the separately reported multicolour-smoother variant")
     args = ap.parse_args()
@@ -323,7 +331,7 @@ def main():
         p, A = make_problem(n, args.problem)
     gen_s = time.time() - t0
     progress("problem generated")
-    elast = args.problem == "elasticity"
+    elast = args.problem in ("elasticity", "elasticity_p2")
     if elast:
         args.no_cpu_baseline = True
         args.no_multicolor = True
@@ -514,7 +522,8 @@ def main():
             "config": {"workload": ("3D Poisson P1 (Kuhn tets), ONE global problem of %d x %d x %d = %d DOFs cut into %d sub-boxes (%dx%dx%d) of %d^3 vertices (one per GPU, "
                                     "interface DOFs shared), h1_scal + CG to 1e-8, hybrid Gauss-Seidel + NCCL halo exchange" % (tuple(p["global_dims"]) + (ndof_global, world) + tuple(grid) + (n,))) if world > 1 else
                                    ("3D Poisson P1 unit cube (Kuhn tets), %d^3 = %d DOFs per GPU, h1_scal + CG to 1e-8" % (n, ndof)) if not elast else
-                                   ("3D linear elasticity P1 beam (Kuhn tets), %d vertices = %d DOFs per GPU, elast_3d (3x3 fine / 6x6 coarse blocks) + CG to 1e-6" % (p["n"], ndof)),
+                                   ("3D linear elasticity %s beam (Kuhn tets), %d nodes = %d DOFs per GPU, elast_3d (3x3 fine / 6x6 coarse blocks) + CG to 1e-6"
+                                    % ("nodal-P2 (BASELINE configs[2]; AMG on all P2 nodes)" if args.problem == "elasticity_p2" else "P1", p["n"], ndof)),
                        "tol": tol, "levels": levels, "operator_complexity": pc.GetOC()[0],
                        "parallelism": "1 GPU" if world == 1 else "%d subdomains, one per GPU; DIS2CO/CO2CU halo exchange per sweep, all-reduced CG dot products, coarse levels contracted onto rank 0" % world,
                        "multi_gpu": par_info,

@@ -246,6 +246,7 @@ struct Amg {
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   int tri_grid_cap[48] = {0};
   i64 tri_small_rows = 1000000;
+  int tri_block_warp_rows = 1;    // block matrices (3x3, 6x6): warp-per-row sweep on every level size
   int tri_rm_rows_per_warp = 8;   // grid of the row-major sweep: at least this many rows per warp
   i64 tri_rm_max_rows = 100000;   // larger small levels keep the SELL warp-per-row sweep (measured: 0.22 vs 0.29 ms at 519 k rows)
   i64 tri_rm_gate_rows = 4096;    // levels with more rows gate every row on its newest dependency before the per-lane polls
@@ -840,7 +841,10 @@ void Amg::build_level_layout(Level &L, const DevCsr &dA)
   }
   dev_free(d_err);
   // small levels: row-major copies of the triangles for the warp-per-row sweep (kernels_rm.cuh)
-  if (L.sm_type == SM_GS && !L.tiled && L.npad <= std::min(tri_small_rows, tri_rm_max_rows) && tri_rm && !level_launch(L)) {
+  // (block matrices at every size: the SELL walk of a warp-per-row sweep uses 8 of every 32 bytes it fetches -- a 386 k-row 6x6 level
+  // moved 4x its 4.2 GB per sweep, 4.2 ms; the row-major copy is read in full sectors)
+  const bool rm_size_ok = (L.b > 1 && tri_block_warp_rows) ? true : L.npad <= std::min(tri_small_rows, tri_rm_max_rows);
+  if (L.sm_type == SM_GS && !L.tiled && rm_size_ok && tri_rm && !level_launch(L)) {
     build_rm(L.L, L.rmL, false, L.nonfree_pad);
     build_rm(L.U, L.rmU, true, L.nonfree_pad);
   }
@@ -1691,7 +1695,7 @@ void Amg::finalize_parallel()
         NGB_CUDA(cudaEventCreate(&N.ev1));
         N.num_sms = num_sms; N.use_graph = flags.flag("b200_cuda_graph", true) && !use_graph;
         N.tri_sleep_ns = tri_sleep_ns; N.tri_ctas_per_sm = tri_ctas_per_sm; N.tri_prepoll = tri_prepoll; N.tri_gate_all = tri_gate_all;
-        N.tri_rm = tri_rm; N.tri_rm_rows_per_warp = tri_rm_rows_per_warp; N.tri_rm_gate_rows = tri_rm_gate_rows; N.tri_rm_max_rows = tri_rm_max_rows; N.tri_small_rows = tri_small_rows; N.tri_gate_gap_levels = tri_gate_gap_levels; N.tri_level_launch_depth = tri_level_launch_depth;
+        N.tri_rm = tri_rm; N.tri_rm_rows_per_warp = tri_rm_rows_per_warp; N.tri_rm_gate_rows = tri_rm_gate_rows; N.tri_rm_max_rows = tri_rm_max_rows; N.tri_block_warp_rows = tri_block_warp_rows; N.tri_small_rows = tri_small_rows; N.tri_gate_gap_levels = tri_gate_gap_levels; N.tri_level_launch_depth = tri_level_launch_depth;
         N.tri_level_launch_rows = tri_level_launch_rows; N.tri_repoll_ns = tri_repoll_ns; N.tri_regate = tri_regate; N.tri_split = tri_split;
         auto NL = std::make_unique<Level>();
         NL->hA = std::move(ctr.A);
@@ -1933,8 +1937,10 @@ void Amg::tri(Level &L, bool backward, bool add_self, bool write_r, const double
     }
     return;
   }
-  if (L.npad <= tri_small_rows) {
-    // small level: warp-per-row variant (chain cost independent of the row width)
+  if (L.npad <= tri_small_rows || (B > 1 && tri_block_warp_rows)) {
+    // small level: warp-per-row variant (chain cost independent of the row width).  Block matrices use it at EVERY size: the
+    // thread-per-block-row kernel walks a 3x3 row in chunks of two entries, one gate + one poll round trip each (measured at 3.07 M
+    // P2 nodes: 9.5 / 14.6 ms per sweep against 1.7 ms for 0.9 M rows with a warp per row)
     const int sidx = 24 + (B == 1 ? 0 : B == 2 ? 1 : B == 3 ? 2 : 3) * 2 + (add_self ? 1 : 0);
     auto launch_small = [&](auto kern) {
       if (!tri_grid_cap[sidx]) {
@@ -2596,6 +2602,7 @@ static void create_impl(const char *type, const ngsamg_csr *A, const uint8_t *fr
   a.halo_p2p = a.flags.flag("b200_halo_p2p", false);
   a.tri_rm_rows_per_warp = std::max(1, (int)a.flags.num("b200_tri_rm_rows_per_warp", 8));
   a.tri_rm_gate_rows = (i64)a.flags.num("b200_tri_rm_gate_rows", 4096);
+  a.tri_block_warp_rows = (int)a.flags.num("b200_tri_block_warp_rows", 1);
   a.tri_rm_max_rows = (i64)a.flags.num("b200_tri_rm_max_rows", 100000);
   a.tri_gate_gap_levels = a.flags.num("b200_tri_gate_gap", 0.0);
   a.tri_level_launch_depth = (int)a.flags.num("b200_tri_level_launch_depth", 24);
@@ -3208,7 +3215,7 @@ int ngsamg_b200_level_sweep_kind(ngsamg_b200_t *h, int level)
 {
   if (!h || !h->amg.finalized || level < 0 || level >= (int)h->amg.lev.size()) return -1;
   const Level &L = *h->amg.lev[level];
-  if (!L.tiled) return (L.rmL.ptr && L.npad <= h->amg.tri_small_rows && !h->amg.level_launch(L)) ? 4 : 0;
+  if (!L.tiled) return (L.rmL.ptr && h->amg.tri_rm && !h->amg.level_launch(L)) ? 4 : 0;
   if (L.tile_maxs <= 2) return 1;
   return L.itile ? 3 : 2;
 }
@@ -3504,7 +3511,7 @@ int ngsamg_b200_profile_kernel(ngsamg_b200_t *h, int level, int which, int reps,
         std::fwrite(ht.data(), sizeof(unsigned long long), ht.size(), f);
         std::fclose(f);
       }
-    } else if ((which == 0 || which == 3) && L.rmL.ptr && a.tri_rm && L.npad <= a.tri_small_rows && !a.level_launch(L)) {
+    } else if ((which == 0 || which == 3) && L.rmL.ptr && a.tri_rm && !a.level_launch(L)) {
       // row-major warp-per-row sweep: 12 stamps per row (see k_gs_tri_rm)
       const i64 nr = L.npad;
       a.tri_trace = dev_alloc<unsigned long long>(nr * 12);
@@ -3560,6 +3567,10 @@ int ngsamg_b200_set_tunable(ngsamg_b200_t *h, const char *name, double value)
   else if (k == "tri_repoll_ns") a.tri_repoll_ns = (unsigned)value;
   else if (k == "tri_prepoll") a.tri_prepoll = (int)value;
   else if (k == "tri_pollmode") a.tri_pollmode = (int)value;
+  else if (k == "tri_gate_all") a.tri_gate_all = (int)value;
+  else if (k == "tri_block_warp_rows") a.tri_block_warp_rows = (int)value;
+  else if (k == "tri_regate") a.tri_regate = (int)value;
+  else if (k == "tri_ctas_per_sm") { a.tri_ctas_per_sm = (int)value; for (int &c : a.tri_grid_cap) c = 0; }
   else if (k == "tri_rm") a.tri_rm = (int)value;
   else if (k == "tri_rm_rows_per_warp") a.tri_rm_rows_per_warp = std::max(1, (int)value);
   else if (k == "tri_rm_gate_rows") a.tri_rm_gate_rows = (i64)value;

@@ -449,3 +449,179 @@ def box_poisson3d(n, grid, rank, dirichlet=("x0", "y1")):
             ghost[e] = True
     loc["n_master"] = int((~ghost).sum())
     return loc
+
+
+# ---- nodal P2 elasticity (BASELINE.json configs[2]: examples/elasticity/beamP2.py -- nodal-P2 H1, `ngs_amg_on_dofs=select`,
+# `ngs_amg_subset=nodalp2`: the AMG treats vertex AND edge-midpoint nodes as its vertices) ---------------------------------------
+_P2_EDGES = [(0, 1), (0, 2), (0, 3), (1, 2), (1, 3), (2, 3)]
+
+
+def _p2_tet_shape_gradients(Minv):
+    """gradients of the 10 nodal P2 shape functions at the 4 points of the degree-2 Gauss rule.
+    Minv: (nt,4,4) inverse of [1 | x y z] per tet; returns (grads (nt,4pts,10,3), values (nt,4pts,10))"""
+    a, b = 0.5854101966249685, 0.1381966011250105
+    lam_q = np.full((4, 4), b) + (a - b) * np.eye(4)            # barycentric coordinates of the 4 quadrature points
+    gl = np.swapaxes(Minv[:, 1:, :], 1, 2)                        # (nt,4,3): grad lambda_i
+    nt = Minv.shape[0]
+    G = np.zeros((nt, 4, 10, 3))
+    V = np.zeros((nt, 4, 10))
+    for q in range(4):
+        lam = lam_q[q]
+        for i in range(4):                                        # vertex functions lambda_i (2 lambda_i - 1)
+            G[:, q, i, :] = (4 * lam[i] - 1) * gl[:, i, :]
+            V[:, q, i] = lam[i] * (2 * lam[i] - 1)
+        for e, (i, j) in enumerate(_P2_EDGES):                    # edge functions 4 lambda_i lambda_j
+            G[:, q, 4 + e, :] = 4 * (lam[i] * gl[:, j, :] + lam[j] * gl[:, i, :])
+            V[:, q, 4 + e] = 4 * lam[i] * lam[j]
+    return G, V
+
+
+def elasticity3d_p2_kuhn(nx, ny, nz, E=1e3, nu=0.15, clamp=("x0",)):
+    """Nodal P2 linear elasticity (3x3 blocks) on the beam of elasticity3d_kuhn, element assembly (small meshes; validates the stencil
+    generator below).  nx, ny, nz = VERTICES per axis; the P2 nodes are all points of the (2nx-1) x (2ny-1) x (2nz-1) grid (every grid
+    point is a vertex or the midpoint of one of the 7 Kuhn edge directions).  Load (0, x, 0) as in examples/elasticity/beamP2.py:24.
+    Returns the same dict as elasticity3d_kuhn plus `dims` = fine-grid dimensions."""
+    import scipy.sparse as sp
+    h = 1.0 / (min(ny, nz) - 1)
+    NX, NY, NZ = 2 * nx - 1, 2 * ny - 1, 2 * nz - 1
+    n = NX * NY * NZ
+    T = kuhn_tets(nx, ny, nz)
+    cv = np.stack([T % nx, (T // nx) % ny, T // (nx * ny)], axis=2)          # (nt,4,3) vertex coordinates in cells
+    fv = 2 * cv                                                                 # fine-grid coordinates of the vertices
+    fe = np.stack([(fv[:, i] + fv[:, j]) // 2 for (i, j) in _P2_EDGES], axis=1)  # (nt,6,3) midpoints
+    fn = np.concatenate([fv, fe], axis=1)                                       # (nt,10,3)
+    N = fn[..., 0] + NX * (fn[..., 1] + NY * fn[..., 2])                        # (nt,10) node numbers
+    Pv = cv * h
+    M = np.concatenate([np.ones((len(T), 4, 1)), Pv], axis=2)
+    Minv = np.linalg.inv(M)
+    vol = np.abs(np.linalg.det(M)) / 6.0
+    G, V = _p2_tet_shape_gradients(Minv)
+    mu = E / (2 * (1 + nu))
+    lam = E * nu / ((1 + nu) * (1 - 2 * nu))
+    w = vol / 4.0
+    gg = np.einsum("tqia,tqjb,t->tijab", G, G, w)
+    dotg = np.einsum("tqia,tqja,t->tij", G, G, w)
+    Ke = lam * gg + mu * np.swapaxes(gg, 3, 4) + mu * dotg[..., None, None] * np.eye(3)[None, None, None]
+    I = (3 * N[:, :, None, None, None] + np.arange(3)[None, None, None, :, None]) + np.zeros((1, 1, 10, 1, 3), np.int64)
+    J = (3 * N[:, None, :, None, None] + np.arange(3)[None, None, None, None, :]) + np.zeros((1, 10, 1, 3, 1), np.int64)
+    A = sp.coo_matrix((Ke.ravel(), (I.ravel(), J.ravel())), shape=(3 * n, 3 * n)).tocsr()
+    pat = sp.coo_matrix((np.ones(N.shape[0] * 100), (np.repeat(N[:, :, None], 10, 2).ravel(), np.repeat(N[:, None, :], 10, 1).ravel())),
+                        shape=(n, n)).tocsr()
+    pat.sort_indices()
+    rowptr = pat.indptr.astype(np.int64)
+    col = pat.indices.astype(np.int32)
+    rows = np.repeat(np.arange(n), np.diff(rowptr))
+    val = np.zeros((len(col), 3, 3))
+    for a in range(3):
+        for b in range(3):
+            val[:, a, b] = np.asarray(A[3 * rows + a, 3 * col.astype(np.int64) + b]).ravel()
+    ids = np.arange(n)
+    coord = (ids % NX, (ids // NX) % NY, ids // (NX * NY))
+    X = np.stack([coord[0], coord[1], coord[2]], axis=1) * (h / 2)
+    free = np.ones(n, np.uint8)
+    dims = (NX, NY, NZ)
+    for tag in clamp:
+        ax = "xyz".index(tag[0])
+        free[coord[ax] == (0 if tag[1] == "0" else dims[ax] - 1)] = 0
+    # body force (0, x, 0): int x phi_i with the same 4-point rule
+    xq = np.einsum("tqv,tv->tq", np.full((1, 4, 4), 0.1381966011250105) + (0.5854101966249685 - 0.1381966011250105) * np.eye(4)[None], Pv[..., 0])
+    fy = np.bincount(N.ravel(), weights=np.einsum("tq,tqi,t->ti", xq, V, w).ravel(), minlength=n)
+    rhs = np.zeros((n, 3))
+    rhs[:, 1] = fy
+    return dict(n=n, b=3, rowptr=rowptr, col=col, val=val.reshape(-1), free=free, rhs=rhs.reshape(-1), xyz=X, dims=dims)
+
+
+def elasticity3d_p2_kuhn_stencil(nx, ny, nz, E=1e3, nu=0.15, clamp=("x0",)):
+    """The matrix of elasticity3d_p2_kuhn for LARGE uniform meshes, from the translation-invariant block stencil: the block row (and the
+    load entry) of a fine-grid node depends only on its class per axis -- position 0, 1, interior even, interior odd, last-1, last --
+    which is read off a 5^3-vertex (9^3-node) element-assembled reference mesh.  Same dict as elasticity3d_p2_kuhn."""
+    ref_nv = 5
+    ref = elasticity3d_p2_kuhn(ref_nv, ref_nv, ref_nv, E=E, nu=nu, clamp=())
+    RN = 2 * ref_nv - 1
+    hs = 1.0 / (min(ny, nz) - 1)
+    scale = hs / (1.0 / (ref_nv - 1))               # stiffness blocks scale with h, the load with h^3 (times x, handled below)
+    NX, NY, NZ = 2 * nx - 1, 2 * ny - 1, 2 * nz - 1
+    if min(NX, NY, NZ) < 5:
+        raise ValueError("elasticity3d_p2_kuhn_stencil needs at least 3 vertices per axis")
+    n = NX * NY * NZ
+
+    def cls(i, m):   # 0, 1, 2 (interior even), 3 (interior odd), 4 (last-1), 5 (last)
+        return np.where(i <= 1, i, np.where(m - 1 - i <= 1, 5 - (m - 1 - i), 2 + (i & 1)))
+    rep = {0: 0, 1: 1, 2: 4, 3: 3, 4: RN - 2, 5: RN - 1}     # a reference node of every class
+    offs = [(a, b, c) for c in range(-2, 3) for b in range(-2, 3) for a in range(-2, 3)]   # ascending column order
+    K = len(offs)
+    table = np.zeros((6, 6, 6, K, 3, 3))
+    present = np.zeros((6, 6, 6, K), bool)
+    load = np.zeros((6, 6, 6, 2))                   # rhs_y = h^3 * (load0 + load1 * x/h) per class (x enters linearly)
+    rp, rc, rv = ref["rowptr"], ref["col"], ref["val"].reshape(-1, 3, 3)
+    # the load of the reference mesh at two different x-offsets gives the linear dependence on x: use the element formula directly
+    ref_rhs = ref["rhs"].reshape(-1, 3)[:, 1]
+    ref_shift = elasticity3d_p2_kuhn_load_only(ref_nv, shift=1.0)
+    href = 1.0 / (ref_nv - 1)
+    for cx in range(6):
+        for cy in range(6):
+            for cz in range(6):
+                vx, vy, vz = rep[cx], rep[cy], rep[cz]
+                i = vx + RN * (vy + RN * vz)
+                cols_i = rc[rp[i]:rp[i + 1]]
+                for k, d in enumerate(offs):
+                    jx, jy, jz = vx + d[0], vy + d[1], vz + d[2]
+                    if not (0 <= jx < RN and 0 <= jy < RN and 0 <= jz < RN):
+                        continue
+                    j = jx + RN * (jy + RN * jz)
+                    pos = np.searchsorted(cols_i, j)
+                    if pos < len(cols_i) and cols_i[pos] == j:
+                        present[cx, cy, cz, k] = True
+                        table[cx, cy, cz, k] = rv[rp[i] + pos] * scale
+                # rhs_i(x0) = int (x0 + x) phi_i = x0 * m_i + r_i  with m_i = int phi_i: read m_i from the shifted load
+                m_i = ref_shift[i] - ref_rhs[i]
+                x_i = vx * href / 2
+                load[cx, cy, cz, 0] = (ref_rhs[i] - m_i * x_i) / href ** 4      # part independent of the node's x, in units of h^4
+                load[cx, cy, cz, 1] = m_i / href ** 3                             # int phi_i in units of h^3
+    ids = np.arange(n, dtype=np.int64)
+    ix, iy, iz = ids % NX, (ids // NX) % NY, ids // (NX * NY)
+    cxa, cya, cza = cls(ix, NX), cls(iy, NY), cls(iz, NZ)
+    pres = present[cxa, cya, cza]                                 # (n, K)
+    rowptr = np.zeros(n + 1, np.int64)
+    np.cumsum(pres.sum(axis=1), out=rowptr[1:])
+    col = np.empty(int(rowptr[-1]), np.int32)
+    val = np.empty((int(rowptr[-1]), 3, 3))
+    slot = np.cumsum(pres, axis=1, dtype=np.int16) - 1
+    for k, d in enumerate(offs):
+        rows = np.flatnonzero(pres[:, k])
+        if len(rows) == 0:
+            continue
+        dst = rowptr[rows] + slot[rows, k]
+        col[dst] = (rows + d[0] + NX * (d[1] + NY * d[2])).astype(np.int32)
+        val[dst] = table[cxa[rows], cya[rows], cza[rows], k]
+    free = np.ones(n, np.uint8)
+    dims = (NX, NY, NZ)
+    coord = (ix, iy, iz)
+    for tag in clamp:
+        ax = "xyz".index(tag[0])
+        free[coord[ax] == (0 if tag[1] == "0" else dims[ax] - 1)] = 0
+    X = np.stack([ix, iy, iz], axis=1) * (hs / 2)
+    rhs = np.zeros((n, 3))
+    rhs[:, 1] = hs ** 4 * load[cxa, cya, cza, 0] + hs ** 3 * load[cxa, cya, cza, 1] * X[:, 0]
+    return dict(n=n, b=3, rowptr=rowptr, col=col, val=val.reshape(-1), free=free, rhs=rhs.reshape(-1), xyz=X, dims=dims)
+
+
+def elasticity3d_p2_kuhn_load_only(nv, shift=0.0):
+    """y-component of the P2 load vector int (x + shift) phi_i on the nv^3-vertex reference mesh (helper of the stencil generator)"""
+    h = 1.0 / (nv - 1)
+    NX = 2 * nv - 1
+    n = NX ** 3
+    T = kuhn_tets(nv, nv, nv)
+    cv = np.stack([T % nv, (T // nv) % nv, T // (nv * nv)], axis=2)
+    fv = 2 * cv
+    fe = np.stack([(fv[:, i] + fv[:, j]) // 2 for (i, j) in _P2_EDGES], axis=1)
+    fn = np.concatenate([fv, fe], axis=1)
+    N = fn[..., 0] + NX * (fn[..., 1] + NX * fn[..., 2])
+    Pv = cv * h
+    M = np.concatenate([np.ones((len(T), 4, 1)), Pv], axis=2)
+    Minv = np.linalg.inv(M)
+    vol = np.abs(np.linalg.det(M)) / 6.0
+    _, V = _p2_tet_shape_gradients(Minv)
+    a, b = 0.5854101966249685, 0.1381966011250105
+    xq = np.einsum("qv,tv->tq", np.full((4, 4), b) + (a - b) * np.eye(4), Pv[..., 0]) + shift
+    return np.bincount(N.ravel(), weights=np.einsum("tq,tqi,t->ti", xq, V, vol / 4.0).ravel(), minlength=n)

@@ -311,11 +311,36 @@ def test_elasticity_3d():
         assert_same_pattern(Ag, Ao)
         assert rel(Ag.val, Ao.val) < TOL_VALUES
     b = rand(95, p["n"] * 3)
-    assert rel(pc * b, amg.apply(b)) < 1e-9
+    assert rel(pc * b, amg.apply(b)) < TOL_VCYCLE
     cg = ng.CGSolver(mat=A, pre=pc, maxsteps=100, tol=1e-6)
     cg.Solve(p["rhs"])
     _, ito, _ = amg.pcg(p["rhs"], tol=1e-6, maxsteps=100)
     assert cg.iterations == ito and ito < 40          # ceiling of tests/elasticity/mdim/simple/test_3d_lo.py:10
+
+
+def test_elasticity_every_level_vector_meets_the_bar():
+    """6x6-block hierarchies at the 1e-10 bar (round 1 compared them at 1e-9, suspecting the ill-conditioned regularised coarse solve):
+    every level's rhs / res on the way down, the coarse solution and the whole cycle, with and without the coarse solve.  Measured on
+    hardware: coarse-solve error 5e-15, V-cycle error 3e-15."""
+    p, A = elasticity(9, 4, 4)
+    pc = ng.elast_3d(A, p["free"], vertex_xyz=p["xyz"], ngs_amg_max_coarse_size=8)
+    prols = pc.GetMap()
+    amg = O.OracleAMG(to_oracle(A), p["free"], [to_oracle(P) for P in prols], pinv=True)
+    b = rand(95, p["n"] * 3)
+    xg, xo = pc * b, amg.apply(b)
+    NL = pc.GetNLevels()
+    for l in range(1, NL):
+        assert rel(pc.GetLevelVector("rhs", l), amg.level_vec("rhs", l)) < TOL_VCYCLE, ("rhs", l)
+    for l in range(1, NL - 1):
+        assert rel(pc.GetLevelVector("res", l), amg.level_vec("res", l)) < TOL_VCYCLE, ("res", l)
+    e_coarse = rel(pc.GetLevelVector("x", NL - 1), amg.level_vec("x", NL - 1))
+    e_fine = rel(xg, xo)
+    assert e_coarse < TOL_VCYCLE and e_fine < TOL_VCYCLE
+    print("coarse-solve error %.2e, V-cycle error %.2e" % (e_coarse, e_fine))
+    # without the coarse solve the whole cycle meets the bar
+    pc2 = ng.elast_3d(A, p["free"], vertex_xyz=p["xyz"], prolongations=prols, ngs_amg_clev="none")
+    amg2 = O.OracleAMG(to_oracle(A), p["free"], [to_oracle(P) for P in prols], pinv=True, clev="none")
+    assert rel(pc2 * b, amg2.apply(b)) < TOL_VCYCLE
 
 
 def test_golden_fixtures_gpu():
@@ -342,7 +367,7 @@ def test_golden_fixtures_gpu():
     Ac = pc.GetLevelMatrix(1)
     assert np.array_equal(Ac.rowptr, e["ac_rowptr"]) and np.array_equal(Ac.col, e["ac_col"])
     assert rel(Ac.val, e["ac_val"]) < TOL_VALUES
-    assert rel(pc * e["b"], e["vcycle_x"]) < 1e-9
+    assert rel(pc * e["b"], e["vcycle_x"]) < TOL_VCYCLE
 
 
 @pytest.mark.parametrize("flags", [dict(ngs_amg_b200_tri_small_rows=0), dict(ngs_amg_b200_tri_small_rows=0, ngs_amg_b200_tri_level_launch_depth=0),
@@ -494,7 +519,9 @@ def test_regularised_coarse_solve_with_a_lone_vertex():
     pc = ng.elast_3d(A, p["free"], vertex_xyz=p["xyz"], prolongations=[P0])
     amg = O.OracleAMG(to_oracle(A), p["free"], [to_oracle(P0)], pinv=True)
     b = rand(77, p["n"] * 3)
-    assert rel(pc * b, amg.apply(b)) < 1e-9
+    err = rel(pc * b, amg.apply(b))
+    print("regularised coarse solve: V-cycle error %.2e" % err)
+    assert err < TOL_VCYCLE
     with pytest.raises(Exception):
         ng.elast_3d(A, p["free"], vertex_xyz=p["xyz"], prolongations=[P0], ngs_amg_regularize_cmats=False)
 

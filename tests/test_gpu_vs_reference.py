@@ -89,7 +89,7 @@ def test_elasticity_3_to_6_vs_reference_code():
     b = rand(3, p["n"] * 3)
     x = np.zeros(p["n"] * 3)
     pc.Mult(b, x)
-    assert rel(x, ra.apply(b)) < 1e-9              # same bar as test_gpu_parity.py::test_elasticity_3d (dense coarse solves differ)
+    assert rel(x, ra.apply(b)) < 1e-10             # the north_star bar (measured 3e-15 on hardware against the oracle)
 
 
 @pytest.mark.parametrize("grid", [(1, 1, 2), (2, 2, 2)])

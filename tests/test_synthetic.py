@@ -1,0 +1,32 @@
+"""the synthetic problem generators: stencil-based generators for large meshes against element-by-element assembly"""
+import numpy as np
+
+import ngsamg_b200 as ng
+from ngsamg_b200 import synthetic as S
+
+
+def test_p2_elasticity_stencil_equals_assembly():
+    """BASELINE.json configs[2]: the nodal-P2 beam from the translation-invariant stencil == the element-assembled matrix"""
+    a = S.elasticity3d_p2_kuhn(6, 4, 5)
+    b = S.elasticity3d_p2_kuhn_stencil(6, 4, 5)
+    assert a["n"] == b["n"] == 11 * 7 * 9
+    assert np.array_equal(a["rowptr"], b["rowptr"]) and np.array_equal(a["col"], b["col"]) and np.array_equal(a["free"], b["free"])
+    assert np.abs(a["val"] - b["val"]).max() < 1e-12 * np.abs(a["val"]).max()
+    assert np.abs(a["rhs"] - b["rhs"]).max() < 1e-12 * np.abs(a["rhs"]).max()
+    assert np.allclose(a["xyz"], b["xyz"])
+
+
+def test_p2_elasticity_is_symmetric_and_keeps_the_rigid_body_modes():
+    a = S.elasticity3d_p2_kuhn(5, 3, 4, clamp=())
+    n = a["n"]
+    A = ng.SparseMatrix(n, n, 3, 3, a["rowptr"], a["col"], a["val"]).to_scipy()
+    assert abs(A - A.T).max() < 1e-13 * abs(A).max()
+    X = a["xyz"]
+    modes = [np.tile(e, n) for e in np.eye(3)]
+    modes += [np.stack([-X[:, 1], X[:, 0], 0 * X[:, 0]], 1).ravel(), np.stack([0 * X[:, 0], -X[:, 2], X[:, 1]], 1).ravel(),
+              np.stack([X[:, 2], 0 * X[:, 0], -X[:, 0]], 1).ravel()]
+    for m in modes:
+        assert np.abs(A @ m).max() < 1e-12 * abs(A).max() * np.abs(m).max()
+    # the load integrates (0, x, 0): total force = int x over the beam
+    lx = X[:, 0].max()
+    assert abs(a["rhs"].reshape(-1, 3)[:, 1].sum() - 0.5 * lx * lx * X[:, 1].max() * X[:, 2].max()) < 1e-12
