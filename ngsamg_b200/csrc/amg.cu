@@ -246,6 +246,7 @@ struct Amg {
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   int tri_grid_cap[48] = {0};
   i64 tri_small_rows = 1000000;
+  i64 rm_spmv_rows = 150000;      // block levels with at most this many rows run the parallel halves with a warp per row on the row-major copies
   int tri_block_warp_rows = 1;    // block matrices (3x3, 6x6): warp-per-row sweep on every level size
   int tri_rm_rows_per_warp = 8;   // grid of the row-major sweep: at least this many rows per warp
   i64 tri_rm_max_rows = 100000;   // larger small levels keep the SELL warp-per-row sweep (measured: 0.22 vs 0.29 ms at 519 k rows)
@@ -1695,7 +1696,7 @@ void Amg::finalize_parallel()
         NGB_CUDA(cudaEventCreate(&N.ev1));
         N.num_sms = num_sms; N.use_graph = flags.flag("b200_cuda_graph", true) && !use_graph;
         N.tri_sleep_ns = tri_sleep_ns; N.tri_ctas_per_sm = tri_ctas_per_sm; N.tri_prepoll = tri_prepoll; N.tri_gate_all = tri_gate_all;
-        N.tri_rm = tri_rm; N.tri_rm_rows_per_warp = tri_rm_rows_per_warp; N.tri_rm_gate_rows = tri_rm_gate_rows; N.tri_rm_max_rows = tri_rm_max_rows; N.tri_block_warp_rows = tri_block_warp_rows; N.tri_small_rows = tri_small_rows; N.tri_gate_gap_levels = tri_gate_gap_levels; N.tri_level_launch_depth = tri_level_launch_depth;
+        N.tri_rm = tri_rm; N.tri_rm_rows_per_warp = tri_rm_rows_per_warp; N.tri_rm_gate_rows = tri_rm_gate_rows; N.tri_rm_max_rows = tri_rm_max_rows; N.tri_block_warp_rows = tri_block_warp_rows; N.rm_spmv_rows = rm_spmv_rows; N.tri_small_rows = tri_small_rows; N.tri_gate_gap_levels = tri_gate_gap_levels; N.tri_level_launch_depth = tri_level_launch_depth;
         N.tri_level_launch_rows = tri_level_launch_rows; N.tri_repoll_ns = tri_repoll_ns; N.tri_regate = tri_regate; N.tri_split = tri_split;
         auto NL = std::make_unique<Level>();
         NL->hA = std::move(ctr.A);
@@ -1969,7 +1970,8 @@ void Amg::tri(Level &L, bool backward, bool add_self, bool write_r, const double
         // tiny levels (a handful of warps): every lane polls its own entries, one L2 round trip per dependency level; larger levels gate on
         // the newest dependency first (two round trips on the critical row, but a spinning warp costs one sector per poll instead of ~50)
         const int gate = (tri_prepoll && L.npad > tri_rm_gate_rows) ? 1 : 0;
-        TriParams prm{L.npad / 32, backward ? 1 : 0, tri_sleep_ns, gate, tri_gate_all, 0, 0u, 0, L.nonfree_pad, d_err, tri_pollmode, nullptr, tri_trace};
+        const int pf = L.npad <= tri_rm_max_rows ? 1 : 0;   // block values: L2 prefetch one row ahead on the latency-bound (small) levels only
+        TriParams prm{L.npad / 32, backward ? 1 : 0, tri_sleep_ns, gate, pf, 0, 0u, 0, L.nonfree_pad, d_err, tri_pollmode, nullptr, tri_trace};
         launch_resident(kern, grid, RM_THREADS, st, R.view(), (const double *)L.diag, (const double *)L.dinv, rin, self, out, rout, prm);
       };
       if (add_self) launch_rm(k_gs_tri_rm<B, true, false>);
@@ -2028,7 +2030,9 @@ static void launch_spmv(cudaStream_t st, i64 small_rows, i64 npad, const Sell &a
 {
   const SellView none{nullptr, nullptr, nullptr};
   const SellView s3 = (nfp && nfp->slice_ptr) ? nfp->view() : none;
-  if (npad <= small_rows) {
+  // warp-per-row SpMV on the SELL layout only where rows are scarce: the lanes of a row read strided (8 useful bytes per 32-byte sector
+  // for blocks), so block levels switch to it later (threshold in scalar entries per block row)
+  if (npad * (BH * BW > 1 ? (i64)BH * BW / 2 : 1) <= small_rows) {
     const unsigned grid = (unsigned)std::max<i64>(1, std::min<i64>((npad + 7) / 8, 148 * 8));
     k_sell_spmv_small<BH, BW, S2, D><<<grid, TB, 0, st>>>(npad, a.view(), b ? b->view() : a.view(), diag, v, y_in, y_out, alpha, beta,
                                                          xadd, s3, rowmap);
@@ -2046,9 +2050,31 @@ static void launch_spmv(cudaStream_t st, i64 small_rows, i64 npad, const Sell &a
                                                             s3, rowmap);
 }
 
+template <int B>
+static void launch_rm_spmv(cudaStream_t st, Level &L, int which, const double *v, const double *y_in, double *y_out, double alpha, double beta)
+{
+  const Rm &A1 = (which == 1 || which == 3) ? L.rmU : L.rmL;
+  const unsigned grid = (unsigned)std::max<i64>(1, std::min<i64>((L.npad + 7) / 8, 148 * 8));
+  if (which == 4) k_rm_spmv<B, true, true><<<grid, TB, 0, st>>>(L.npad, L.rmL.view(), L.rmU.view(), L.diag, v, y_in, y_out, alpha, beta);
+  else if (which >= 2) k_rm_spmv<B, false, true><<<grid, TB, 0, st>>>(L.npad, A1.view(), A1.view(), L.diag, v, y_in, y_out, alpha, beta);
+  else k_rm_spmv<B, false, false><<<grid, TB, 0, st>>>(L.npad, A1.view(), A1.view(), L.diag, v, y_in, y_out, alpha, beta);
+}
+
 void Amg::spmv_part(Level &L, int which, const double *v, const double *y_in, double *y_out, double alpha, double beta, double *xadd)
 {
   NGB_PHASE(PH_PASS);
+  // block levels with few rows (too few threads for the thread-per-row kernel, and its warp-per-row variant wastes 3/4 of every sector
+  // on blocks): warp per row on the row-major copies
+  if (L.b > 1 && L.rmL.ptr && L.rmU.ptr && !xadd && !L.N.slice_ptr && L.npad <= rm_spmv_rows) {
+    switch (L.b) {
+      case 2: launch_rm_spmv<2>(st, L, which, v, y_in, y_out, alpha, beta); break;
+      case 3: launch_rm_spmv<3>(st, L, which, v, y_in, y_out, alpha, beta); break;
+      case 6: launch_rm_spmv<6>(st, L, which, v, y_in, y_out, alpha, beta); break;
+      default: throw Error("unsupported block size");
+    }
+    launches++;
+    return;
+  }
   const Sell &A1 = (which == 1 || which == 3) ? L.U : L.L;
   const bool s2 = (which == 4), d = (which >= 2);
 #define NGB_SPMV(B)                                                                                                     \
@@ -2603,6 +2629,7 @@ static void create_impl(const char *type, const ngsamg_csr *A, const uint8_t *fr
   a.tri_rm_rows_per_warp = std::max(1, (int)a.flags.num("b200_tri_rm_rows_per_warp", 8));
   a.tri_rm_gate_rows = (i64)a.flags.num("b200_tri_rm_gate_rows", 4096);
   a.tri_block_warp_rows = (int)a.flags.num("b200_tri_block_warp_rows", 1);
+  a.rm_spmv_rows = (i64)a.flags.num("b200_rm_spmv_rows", 150000);
   a.tri_rm_max_rows = (i64)a.flags.num("b200_tri_rm_max_rows", 100000);
   a.tri_gate_gap_levels = a.flags.num("b200_tri_gate_gap", 0.0);
   a.tri_level_launch_depth = (int)a.flags.num("b200_tri_level_launch_depth", 24);
@@ -3569,6 +3596,7 @@ int ngsamg_b200_set_tunable(ngsamg_b200_t *h, const char *name, double value)
   else if (k == "tri_pollmode") a.tri_pollmode = (int)value;
   else if (k == "tri_gate_all") a.tri_gate_all = (int)value;
   else if (k == "tri_block_warp_rows") a.tri_block_warp_rows = (int)value;
+  else if (k == "rm_spmv_rows") a.rm_spmv_rows = (i64)value;
   else if (k == "tri_regate") a.tri_regate = (int)value;
   else if (k == "tri_ctas_per_sm") { a.tri_ctas_per_sm = (int)value; for (int &c : a.tri_grid_cap) c = 0; }
   else if (k == "tri_rm") a.tri_rm = (int)value;

@@ -122,6 +122,13 @@ __global__ void __launch_bounds__(RM_THREADS) k_gs_tri_rm(RmView T, const double
         if (B == 1) cp_async8(sa + St::VALS + (uint32_t)k * 8u, T.val + p0 + k);
       }
     }
+    if (B > 1 && prm.gate_all) {
+      // (small levels only; a bandwidth-bound level loses with the extra requests)  block values are loaded at use (36 doubles per entry do not fit the stage): pull the row's lines into L2 now, so that the loads
+      // behind the polls are L2 hits instead of DRAM misses on the critical path
+      const char *vb = (const char *)(T.val + p0 * BS);
+      const i64 nbytes = (p1 - p0) * (i64)(BS * 8);
+      for (i64 o = (i64)lane * 128; o < nbytes; o += 32 * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(vb + o));
+    }
     if (lane == 31) cp_async4(gate_a + (uint32_t)s * 4u, T.gate + row);
     const i64 slice = row >> 5;
     const int lr = (int)(row & 31);
@@ -321,6 +328,61 @@ __global__ void __launch_bounds__(RM_THREADS) k_gs_tri_rm(RmView T, const double
     p0 = q0; p1 = q1;
   }
   cp_async_wait_all();
+}
+
+// y_out = beta * y_in + alpha * (S1 v [+ S2 v] [+ D v]) on the row-major copies, one WARP per block row: the lanes split the row's entries
+// and read each block as 8*B*B contiguous bytes (full sectors; the SELL walk of k_sell_spmv_small uses a quarter of every sector for
+// blocks), fixed shuffle tree, lane p writes component p.  For block levels with too few rows for the thread-per-row kernel.
+template <int B, bool HAS_S2, bool HAS_D>
+__global__ void __launch_bounds__(256) k_rm_spmv(i64 nrows_pad, RmView S1, RmView S2, const double *__restrict__ diag, const double *__restrict__ v,
+                                                const double *y_in, double *y_out, double alpha, double beta)
+{
+  constexpr int BS = B * B;
+  constexpr unsigned FULL = 0xffffffffu;
+  const int lane = threadIdx.x & 31;
+  const i64 gw = ((i64)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const i64 nw = ((i64)gridDim.x * blockDim.x) >> 5;
+  for (i64 row = gw; row < nrows_pad; row += nw) {
+    double acc[B];
+#pragma unroll
+    for (int p = 0; p < B; p++) acc[p] = 0.0;
+    auto part = [&](const RmView &S) {
+      const i64 p0 = S.ptr[row], p1 = S.ptr[row + 1];
+      for (i64 k = p0 + lane; k < p1; k += 32) {
+        const i32 c = S.col[k];
+        double xv[B];
+#pragma unroll
+        for (int q = 0; q < B; q++) xv[q] = v[(i64)c * B + q];
+#pragma unroll
+        for (int p = 0; p < B; p++) {
+          double t = 0.0;
+#pragma unroll
+          for (int q = 0; q < B; q++) t = fma(S.val[k * BS + p * B + q], xv[q], t);
+          acc[p] += t;
+        }
+      }
+    };
+    part(S1);
+    if (HAS_S2) part(S2);
+#pragma unroll
+    for (int p = 0; p < B; p++)
+#pragma unroll
+      for (int o = 16; o; o >>= 1) acc[p] += __shfl_xor_sync(FULL, acc[p], o);
+    if (lane < B) {
+      double a = 0.0;
+#pragma unroll
+      for (int p = 0; p < B; p++)
+        if (lane == p) a = acc[p];
+      if (HAS_D) {
+        const double *dp = diag + (row >> 5) * (i64)BS * 32 + (row & 31);
+#pragma unroll
+        for (int q = 0; q < B; q++) a = fma(dp[(lane * B + q) * 32], v[row * B + q], a);
+      }
+      double y = alpha * a;
+      if (beta != 0.0) y = fma(beta, y_in[row * B + lane], y);
+      y_out[row * B + lane] = y;
+    }
+  }
 }
 
 }  // namespace ngb

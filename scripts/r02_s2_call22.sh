@@ -1,6 +1,6 @@
 #!/usr/bin/env bash
 set -u
-OUT=gpurun_out/r02_s2c23
+OUT=gpurun_out/r02_s2c25
 mkdir -p "$OUT"
 timeout 600 python -m pytest tests -m gpu -q 2>&1 | grep -v "^$" | tail -8
 for prob in elasticity_p2:151; do
