@@ -252,6 +252,7 @@ struct Amg {
   i64 tri_rm_max_rows = 100000;   // larger small levels keep the SELL warp-per-row sweep (measured: 0.22 vs 0.29 ms at 519 k rows)
   i64 tri_rm_gate_rows = 4096;    // levels with more rows gate every row on its newest dependency before the per-lane polls
   int tri_rm = 1;                 // small levels sweep a row-major copy of the triangle (k_gs_tri_rm) instead of the SELL layout
+  int tri_level_pdl = 1;          // colours of the per-colour launches overlap through programmatic dependent launch
   int tri_level_launch_depth = 24;
   i64 tri_level_launch_rows = 131072;
   double tri_gate_gap_levels = 0.0;
@@ -1696,7 +1697,7 @@ void Amg::finalize_parallel()
         NGB_CUDA(cudaEventCreate(&N.ev1));
         N.num_sms = num_sms; N.use_graph = flags.flag("b200_cuda_graph", true) && !use_graph;
         N.tri_sleep_ns = tri_sleep_ns; N.tri_ctas_per_sm = tri_ctas_per_sm; N.tri_prepoll = tri_prepoll; N.tri_gate_all = tri_gate_all;
-        N.tri_rm = tri_rm; N.tri_rm_rows_per_warp = tri_rm_rows_per_warp; N.tri_rm_gate_rows = tri_rm_gate_rows; N.tri_rm_max_rows = tri_rm_max_rows; N.tri_block_warp_rows = tri_block_warp_rows; N.rm_spmv_rows = rm_spmv_rows; N.tri_small_rows = tri_small_rows; N.tri_gate_gap_levels = tri_gate_gap_levels; N.tri_level_launch_depth = tri_level_launch_depth;
+        N.tri_rm = tri_rm; N.tri_rm_rows_per_warp = tri_rm_rows_per_warp; N.tri_rm_gate_rows = tri_rm_gate_rows; N.tri_rm_max_rows = tri_rm_max_rows; N.tri_block_warp_rows = tri_block_warp_rows; N.rm_spmv_rows = rm_spmv_rows; N.tri_small_rows = tri_small_rows; N.tri_gate_gap_levels = tri_gate_gap_levels; N.tri_level_launch_depth = tri_level_launch_depth; N.tri_level_pdl = tri_level_pdl;
         N.tri_level_launch_rows = tri_level_launch_rows; N.tri_repoll_ns = tri_repoll_ns; N.tri_regate = tri_regate; N.tri_split = tri_split;
         auto NL = std::make_unique<Level>();
         NL->hA = std::move(ctr.A);
@@ -1932,8 +1933,24 @@ void Amg::tri(Level &L, bool backward, bool add_self, bool write_r, const double
       const int lv = backward ? L.depth - 1 - q : q;
       const i64 r0 = L.level_start[lv], r1 = L.level_start[lv + 1];
       if (r1 <= r0) continue;
-      if (add_self) k_gs_level<B, true, false><<<nblk(r1 - r0), TB, 0, st>>>(T.view(), L.diag, L.dinv, rin, self, out, rout, r0, r1, L.nonfree_pad);
-      else k_gs_level<B, false, true><<<nblk(r1 - r0), TB, 0, st>>>(T.view(), L.diag, L.dinv, rin, self, out, rout, r0, r1, L.nonfree_pad);
+      // every colour but the first is launched with programmatic stream serialization behind the previous colour (see k_gs_level)
+      if (tri_level_pdl && q > 0) {
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = dim3(nblk(r1 - r0));
+        cfg.blockDim = dim3(TB);
+        cfg.stream = st;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        at[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = at;
+        cfg.numAttrs = 1;
+        const SellView tv = T.view();
+        const double *dg = L.diag, *di = L.dinv;
+        const i64 nf = L.nonfree_pad;
+        if (add_self) NGB_CUDA(cudaLaunchKernelEx(&cfg, k_gs_level<B, true, false, true>, tv, dg, di, rin, self, out, rout, r0, r1, nf));
+        else NGB_CUDA(cudaLaunchKernelEx(&cfg, k_gs_level<B, false, true, true>, tv, dg, di, rin, self, out, rout, r0, r1, nf));
+      } else if (add_self) k_gs_level<B, true, false, false><<<nblk(r1 - r0), TB, 0, st>>>(T.view(), L.diag, L.dinv, rin, self, out, rout, r0, r1, L.nonfree_pad);
+      else k_gs_level<B, false, true, false><<<nblk(r1 - r0), TB, 0, st>>>(T.view(), L.diag, L.dinv, rin, self, out, rout, r0, r1, L.nonfree_pad);
       launches++;
     }
     return;
@@ -2633,6 +2650,7 @@ static void create_impl(const char *type, const ngsamg_csr *A, const uint8_t *fr
   a.tri_rm_max_rows = (i64)a.flags.num("b200_tri_rm_max_rows", 100000);
   a.tri_gate_gap_levels = a.flags.num("b200_tri_gate_gap", 0.0);
   a.tri_level_launch_depth = (int)a.flags.num("b200_tri_level_launch_depth", 24);
+  a.tri_level_pdl = (int)a.flags.num("b200_tri_level_pdl", 1);
   a.tri_level_launch_rows = (i64)a.flags.num("b200_tri_level_launch_rows", 131072);
   a.tri_repoll_ns = (unsigned)a.flags.num("b200_tri_repoll_ns", 0);
   a.tri_regate = (int)a.flags.num("b200_tri_regate", 1);
@@ -3604,6 +3622,7 @@ int ngsamg_b200_set_tunable(ngsamg_b200_t *h, const char *name, double value)
   else if (k == "tri_rm_gate_rows") a.tri_rm_gate_rows = (i64)value;
   else if (k == "tri_small_rows") a.tri_small_rows = (i64)value;
   else if (k == "tri_level_launch_depth") a.tri_level_launch_depth = (int)value;
+  else if (k == "tri_level_pdl") a.tri_level_pdl = (int)value;
   else if (k == "tri_level_launch_rows") a.tri_level_launch_rows = (i64)value;
   else if (k == "spmv_small_rows") a.spmv_small_rows = (i64)value;
   else if (k == "use_graph") a.use_graph = value != 0;

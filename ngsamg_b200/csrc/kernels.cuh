@@ -582,11 +582,17 @@ __global__ void __launch_bounds__(256) k_gs_tri(SellView T, const double *__rest
 // colour): one launch per dependency level over the rows [row0, row1) of that level; plain cached gathers, no polling.
 // Used when the depth is small enough that ~depth launches cost less than the polling traffic of the sync-free sweep.
 // ------------------------------------------------------------------------------------------------
-template <int B, bool ADD_SELF, bool WRITE_R>
+// PDL = launched with programmatic stream serialization behind the previous colour's launch: the kernel starts while that one is
+// still running, lets ITS successor start (launch_dependents), pulls everything that does not depend on the sweep into registers / L1
+// (row pointers, the first 8 entries, the rest of the slice by prefetch, rhs, dinv) and only then waits for the previous colour
+// (griddepcontrol.wait = cudaGridDependencySynchronize).  A colour of a shallow level is a 10-20 us kernel: without the overlap half
+// of it is launch latency and the dependent load chain in front of the first gather.
+template <int B, bool ADD_SELF, bool WRITE_R, bool PDL>
 __global__ void __launch_bounds__(256) k_gs_level(SellView T, const double *__restrict__ diag, const double *__restrict__ dinv,
                                                  const double *rin, const double *__restrict__ self, double *out, double *rout,
                                                  i64 row0, i64 row1, i64 nonfree)
 {
+  if (PDL) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   const i64 row = row0 + (i64)blockIdx.x * blockDim.x + threadIdx.x;
   if (row >= row1) return;
   if (ADD_SELF && row < nonfree) {
@@ -600,19 +606,69 @@ __global__ void __launch_bounds__(256) k_gs_level(SellView T, const double *__re
   double acc[B];
 #pragma unroll
   for (int p = 0; p < B; p++) acc[p] = rin[row * B + p];
-  if (B == 1) acc[0] -= sell_row_dot1<false>(T, slice, lane, out);
-  else sell_row_mac<B, B, false>(T, slice, lane, out, acc, -1.0);
+  constexpr int PRE = (B == 1) ? 8 : 0;
+  i32 pc[PRE > 0 ? PRE : 1];
+  double pv[PRE > 0 ? PRE : 1];
+  int width = 0;
+  i64 base = 0;
+  if (PDL) {
+    base = T.slice_ptr[slice];
+    width = (int)(T.slice_ptr[slice + 1] - base);
+    if (B == 1) {
+#pragma unroll
+      for (int k = 0; k < PRE; k++) {
+        pc[k] = ldp_nc_i32(T.col + (base + k) * 32 + lane, k < width);
+        pv[k] = ldp_nc_f64(T.val + (base + k) * 32 + lane, k < width);
+      }
+    }
+    // the rest of the slice: one 128-byte line of columns and B*B*2 lines of values per slot
+    const char *cb = (const char *)(T.col + (base + PRE) * 32);
+    const char *vb = (const char *)(T.val + (base + PRE) * (i64)(B * B) * 32);
+    const int nlc = max(width - PRE, 0), nlv = nlc * B * B * 2;
+    for (int l = lane; l < nlc; l += 32) asm volatile("prefetch.global.L1 [%0];" ::"l"(cb + (i64)l * 128));
+    for (int l = lane; l < nlv; l += 32) asm volatile("prefetch.global.L1 [%0];" ::"l"(vb + (i64)l * 128));
+  }
   const double *dp = dinv + slice * (i64)(B * B) * 32 + lane;
+  double dv[B * B];
+#pragma unroll
+  for (int e = 0; e < B * B; e++) dv[e] = dp[e * 32];
+  double sv[B];
+#pragma unroll
+  for (int p = 0; p < B; p++) sv[p] = ADD_SELF ? self[row * B + p] : 0.0;
+  if (PDL) asm volatile("griddepcontrol.wait;" ::: "memory");
+  if (PDL && B == 1) {
+    double s0 = 0.0, s1 = 0.0;
+    double xk[PRE > 0 ? PRE : 1];
+#pragma unroll
+    for (int k = 0; k < PRE; k++) xk[k] = ldp_f64(out + (pc[k] >= 0 ? pc[k] : 0), pc[k] >= 0, true);
+#pragma unroll
+    for (int k = 0; k < PRE; k += 2) { s0 = fma(pv[k], xk[k], s0); if (k + 1 < PRE) s1 = fma(pv[k + 1], xk[k + 1], s1); }
+    const i32 *cp = T.col + base * 32 + lane;
+    const double *vp = T.val + base * 32 + lane;
+    for (int k = PRE; k < width; k += 4) {
+      i32 c[4];
+      double v[4], xv[4];
+#pragma unroll
+      for (int j = 0; j < 4; j++) c[j] = ldp_nc_i32(cp + (i64)(k + j) * 32, k + j < width);
+#pragma unroll
+      for (int j = 0; j < 4; j++) v[j] = ldp_nc_f64(vp + (i64)(k + j) * 32, k + j < width);
+#pragma unroll
+      for (int j = 0; j < 4; j++) xv[j] = ldp_f64(out + (c[j] >= 0 ? c[j] : 0), c[j] >= 0, true);
+      s0 = fma(v[0], xv[0], s0); s1 = fma(v[1], xv[1], s1); s0 = fma(v[2], xv[2], s0); s1 = fma(v[3], xv[3], s1);
+    }
+    acc[0] -= s0 + s1;
+  } else if (B == 1) acc[0] -= sell_row_dot1<false>(T, slice, lane, out);
+  else sell_row_mac<B, B, PDL>(T, slice, lane, out, acc, -1.0);
   double dl[B];
 #pragma unroll
   for (int p = 0; p < B; p++) {
     double t = 0.0;
 #pragma unroll
-    for (int q = 0; q < B; q++) t = fma(dp[(p * B + q) * 32], acc[q], t);
+    for (int q = 0; q < B; q++) t = fma(dv[p * B + q], acc[q], t);
     dl[p] = t;
   }
 #pragma unroll
-  for (int p = 0; p < B; p++) out[row * B + p] = ADD_SELF ? self[row * B + p] + dl[p] : dl[p];
+  for (int p = 0; p < B; p++) out[row * B + p] = ADD_SELF ? sv[p] + dl[p] : dl[p];
   if (WRITE_R) {
     const double *gp = diag + slice * (i64)(B * B) * 32 + lane;
 #pragma unroll
