@@ -240,6 +240,8 @@ struct Amg {
   double *pin_a = nullptr, *pin_b = nullptr;
   i64 pin_n = 0;
   double *io_a = nullptr, *io_b = nullptr, *io_c = nullptr;  // device staging in original numbering
+  static constexpr i64 IO_CHUNK = 1 << 23;                   // doubles per chunk of the pipelined host <-> device staging (64 MB)
+  std::vector<cudaEvent_t> io_ev;
   i64 io_n = 0;
   i64 launches = 0;
   double ms_apply = 0, ms_pcg = 0, ms_setup = 0, ms_rap = 0, ms_host = 0, bytes_rap = 0;
@@ -707,6 +709,7 @@ Amg::~Amg()
   if (vgraph) cudaGraphExecDestroy(vgraph);
   if (ev0) cudaEventDestroy(ev0);
   if (ev1) cudaEventDestroy(ev1);
+  for (auto e : io_ev) cudaEventDestroy(e);
   for (auto &m : d_ctr_map) dev_free(m);
   dev_free(ctr_buf);
   if (h_ctr) cudaFreeHost(h_ctr);
@@ -2508,8 +2511,12 @@ void Amg::ensure_io(i64 n)
 const double *Amg::to_device(const double *p, i64 n, double *stage)
 {
   if (is_device_ptr(p)) return p;
-  parallel_for(n, [&](i64 lo, i64 hi) { std::memcpy(pin_a + lo, p + lo, sizeof(double) * (hi - lo)); }, 1 << 18);  // pageable -> pinned (threads), then async H2D
-  NGB_CUDA(cudaMemcpyAsync(stage, pin_a, sizeof(double) * n, cudaMemcpyHostToDevice, st));
+  // pageable -> pinned (host threads) -> device, pipelined in chunks: the DMA of chunk c runs while the threads copy chunk c + 1
+  for (i64 off = 0; off < n; off += IO_CHUNK) {
+    const i64 len = std::min<i64>(IO_CHUNK, n - off);
+    parallel_for(len, [&](i64 lo, i64 hi) { std::memcpy(pin_a + off + lo, p + off + lo, sizeof(double) * (hi - lo)); }, 1 << 17);
+    NGB_CUDA(cudaMemcpyAsync(stage + off, pin_a + off, sizeof(double) * len, cudaMemcpyHostToDevice, st));
+  }
   NGB_CUDA(cudaStreamSynchronize(st));
   return stage;
 }
@@ -2521,9 +2528,19 @@ void Amg::from_device(double *dst, const double *src_dev, i64 n)
     NGB_CUDA(cudaStreamSynchronize(st));
     return;
   }
-  NGB_CUDA(cudaMemcpyAsync(pin_b, src_dev, sizeof(double) * n, cudaMemcpyDeviceToHost, st));
-  NGB_CUDA(cudaStreamSynchronize(st));
-  parallel_for(n, [&](i64 lo, i64 hi) { std::memcpy(dst + lo, pin_b + lo, sizeof(double) * (hi - lo)); }, 1 << 18);
+  // device -> pinned -> pageable, pipelined: the threads copy chunk c out of the pinned buffer while the DMA of the later chunks runs
+  const i64 nchunks = (n + IO_CHUNK - 1) / IO_CHUNK;
+  while ((i64)io_ev.size() < nchunks) { cudaEvent_t e; NGB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); io_ev.push_back(e); }
+  for (i64 c = 0; c < nchunks; c++) {
+    const i64 off = c * IO_CHUNK, len = std::min<i64>(IO_CHUNK, n - off);
+    NGB_CUDA(cudaMemcpyAsync(pin_b + off, src_dev + off, sizeof(double) * len, cudaMemcpyDeviceToHost, st));
+    NGB_CUDA(cudaEventRecord(io_ev[c], st));
+  }
+  for (i64 c = 0; c < nchunks; c++) {
+    const i64 off = c * IO_CHUNK, len = std::min<i64>(IO_CHUNK, n - off);
+    NGB_CUDA(cudaEventSynchronize(io_ev[c]));
+    parallel_for(len, [&](i64 lo, i64 hi) { std::memcpy(dst + off + lo, pin_b + off + lo, sizeof(double) * (hi - lo)); }, 1 << 17);
+  }
 }
 
 }  // namespace ngb
