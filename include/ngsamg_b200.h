@@ -120,6 +120,10 @@ int ngsamg_b200_num_levels(ngsamg_b200_t *h);
 /* which kernel sweeps the level (measurement / test aid): 0 row-level sync-free or per-colour launches, 1 warp per tile, 2 CTA per tile,
  * 3 CTA per tile on tile images prepared at setup, 4 warp per row on the row-major copy of a small level; -1 = no such level */
 int ngsamg_b200_level_sweep_kind(ngsamg_b200_t *h, int level);
+/* sm_type = bgs (block Gauss-Seidel, BSmoother2 loc_block_gssmoother_impl.hpp:244-268, 516-541, 656-706): the blocks of `level` as the
+ * reference builds them from the coarse map (GetGSBlocks, amg_pc_vertex_impl.hpp:1171-1269): block_of[v] = coarse vertex of v, -1 = in no
+ * block (not smoothed).  n entries.  Fails if the level is not smoothed by bgs (levels without a coarse map fall back to gs). */
+int ngsamg_b200_get_gs_blocks(ngsamg_b200_t *h, int level, int32_t *block_of);
 /* measurement aid: change a run-time tunable of the sweep kernels ("tri_sleep_ns", "tri_prepoll", "tri_rm", "tri_rm_rows_per_warp",
  * "tri_small_rows", "tri_level_launch_depth", "tri_level_launch_rows", "spmv_small_rows", "use_graph", ...) on a finalized hierarchy */
 int ngsamg_b200_set_tunable(ngsamg_b200_t *h, const char *name, double value);

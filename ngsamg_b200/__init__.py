@@ -334,6 +334,13 @@ class Preconditioner:
         _lib.check(self._lib.ngsamg_b200_profile_kernel(self._h, int(level), self.KERNELS[which], int(reps), C.byref(ms), C.byref(by)))
         return ms.value, by.value
 
+    def GetGSBlocks(self, level):
+        """block (= coarse vertex) of every vertex of a level smoothed by block Gauss-Seidel (sm_type=bgs), -1 = in no block
+        (GetGSBlocks, amg_pc_vertex_impl.hpp:1171-1269)"""
+        out = np.zeros(self.GetNDof(level), np.int32)
+        _lib.check(self._lib.ngsamg_b200_get_gs_blocks(self._h, int(level), _lib.ptr(out)))
+        return out
+
     def SetTunable(self, name, value):
         """measurement aid: change a run-time tunable of the sweep kernels on the finalized hierarchy (include/ngsamg_b200.h)"""
         _lib.check(self._lib.ngsamg_b200_set_tunable(self._h, str(name).encode(), float(value)))

@@ -22,7 +22,7 @@ EXPORTS = [
     "ngsamg_b200_vcycle_bytes", "ngsamg_b200_last_ms", "ngsamg_b200_launch_count", "ngsamg_b200_rap_begin",
     "ngsamg_b200_matmul_begin", "ngsamg_b200_transpose_begin", "ngsamg_b200_spm_fetch",
     "ngsamg_b200_coarsen_begin", "ngsamg_b200_coarsen_fetch", "ngsamg_b200_profile_kernel",
-    "ngsamg_b200_get_sweep_order", "ngsamg_b200_set_tunable",
+    "ngsamg_b200_get_sweep_order", "ngsamg_b200_set_tunable", "ngsamg_b200_get_gs_blocks",
     "ngsamg_b200_create_parallel", "ngsamg_b200_nccl_unique_id", "ngsamg_b200_nccl_comm_init", "ngsamg_b200_nccl_comm_destroy",
     "ngsamg_b200_get_halo", "ngsamg_b200_get_hybrid", "ngsamg_b200_num_parallel_levels", "ngsamg_b200_halo_transport", "ngsamg_b200_get_contracted",
     "ngsamg_b200_get_contraction_map", "ngsamg_b200_hybrid_host_begin", "ngsamg_b200_hybrid_host_fetch",
@@ -77,6 +77,7 @@ def lib():
     L.ngsamg_b200_level_sweep_kind.argtypes = [vp, ci]
     L.ngsamg_b200_set_tunable.argtypes = [vp, C.c_char_p, dbl]
     L.ngsamg_b200_halo_transport.argtypes = [vp, ci]
+    L.ngsamg_b200_get_gs_blocks.argtypes = [vp, ci, vp]
     L.ngsamg_b200_apply_phases.argtypes = [vp, vp, vp, vp]
     L.ngsamg_b200_smooth.argtypes = [vp, ci, vp, vp, vp, ci, ci, ci, ci]
     L.ngsamg_b200_restrict.argtypes = [vp, ci, vp, vp]

@@ -3,6 +3,7 @@
 #include <cub/cub.cuh>
 
 #include <atomic>
+#include <functional>
 #include <chrono>
 #include <memory>
 #include <mutex>
@@ -54,7 +55,7 @@ struct Rm {
   void release() { dev_free(ptr); dev_free(col); dev_free(val); dev_free(gate); ptr = nullptr; col = nullptr; val = nullptr; gate = nullptr; }
 };
 
-enum { SM_GS = 0, SM_JACOBI = 1 };
+enum { SM_GS = 0, SM_JACOBI = 1, SM_BGS = 2 };
 
 struct Level {
   i64 n = 0, npad = 0;
@@ -69,6 +70,10 @@ struct Level {
   uint8_t *d_freep = nullptr;
   Sell L, U, N;   // strictly lower / strictly upper / free-row couplings to non-free rows
   Rm rmL, rmU;    // row-major copies of L / U for the warp-per-row sweep of small levels (empty otherwise)
+  // ---- block Gauss-Seidel (sm_type = bgs; BSmoother2, loc_block_gssmoother_impl.hpp): blocks = the aggregates of the next coarse map
+  std::vector<i32> gs_block;        // vertex -> block (= coarse vertex), -1 = in no block (not smoothed)
+  std::unique_ptr<Level> bgs;       // shadow level: layout of A~ = DB^-1 A (unit diagonal, no couplings inside a block) in THIS level's numbering
+  Sell DBI;                         // DB^-1: the inverted dense diagonal blocks as a block-diagonal sparse matrix
   double *diag = nullptr, *dinv = nullptr;
   // Gauss-Seidel dependency structure
   int depth = 0;        // number of dependency levels (length of the critical path of a sweep)
@@ -299,6 +304,9 @@ struct Amg {
   void finalize();
   void build_level_layout(Level &L, const DevCsr &dA);
   void build_rm(const Sell &S, Rm &R, bool upper, i64 nonfree);
+  void setup_bgs(Level &L, const DevCsr &dA);   // block Gauss-Seidel: DB^-1, A~ = DB^-1 A, shadow level; fixes the level's numbering
+  void bgs_res(Level &L, bool backward, double *x, double *res);
+  void bgs_rhs(Level &L, bool backward, double *x, const double *b);
   // shallow dependency DAG with many rows per level: one plain launch per level (k_gs_level)
   bool level_launch(const Level &L) const { return L.depth <= tri_level_launch_depth && L.npad > tri_level_launch_rows && (int)L.level_start.size() == L.depth + 1; }
   void prepare_ctile(Level &L);
@@ -685,8 +693,7 @@ struct PhaseScope {
 Amg::~Amg()
 {
   if (device >= 0) cudaSetDevice(device);
-  for (auto &lp : lev) {
-    Level &L = *lp;
+  std::function<void(Level &)> free_level = [&](Level &L) {
     L.G.release();
     dev_free(L.d_tile_slice); dev_free(L.d_tile_nlev); dev_free(L.d_tile_pred); dev_free(L.d_tile_succ); dev_free(L.d_row_lvl);
     dev_free(L.d_tile_pred_ptr); dev_free(L.d_tile_succ_ptr); dev_free(L.d_tile_done); dev_free(L.d_meta_fwd); dev_free(L.d_meta_bwd);
@@ -701,7 +708,10 @@ Amg::~Amg()
     L.L.release(); L.U.release(); L.N.release(); L.P.release(); L.PT.release(); L.rmL.release(); L.rmU.release();
     dev_free(L.diag); dev_free(L.dinv);
     dev_free(L.x); dev_free(L.y); dev_free(L.rhs); dev_free(L.res); dev_free(L.tmp); dev_free(L.wa); dev_free(L.wb);
-  }
+    L.DBI.release();
+    if (L.bgs) free_level(*L.bgs);
+  };
+  for (auto &lp : lev) free_level(*lp);
   dev_free(d_cinv); dev_free(cg_u); dev_free(cg_s); dev_free(cg_q); dev_free(d_dot); dev_free(d_partial);
   dev_free(io_a); dev_free(io_b); dev_free(io_c); dev_free(d_err);
   if (pin_a) cudaFreeHost(pin_a);
@@ -877,6 +887,164 @@ void Amg::build_rm(const Sell &S, Rm &R, bool upper, i64 nonfree)
   R.gate = dev_alloc<i32>(std::max<i64>(np, 1));
   k_rm_fill<<<nblk(np), TB, 0, st>>>(np, bs, S.view(), R.ptr, R.col, R.val, R.gate, upper ? 1 : 0, (i32)nonfree);
   launches += 3;
+}
+
+// ---- block Gauss-Seidel (sm_type = bgs) --------------------------------------------------------------------------------------------
+// Reference: BSmoother2 (src/base/smoothers/loc_block_gssmoother_impl.hpp): blocks = the aggregates of the next coarse map in coarse
+// vertex order (GetGSBlocks, amg_pc_vertex_impl.hpp:1171-1269; vertices mapped to -1 are in no block and are not smoothed), per block
+// the dense diagonal block DB and its inverse; RichardsonUpdate (:244-268): x_B += DB^-1 (b_B - A_{B,:} x); RichardsonUpdate_RES
+// (:516-541): d = DB^-1 res_B, x_B += d, res -= A_{:,B} d; blocks ascending (forward) or descending (IterateBlocks :618-651), omega = 1.
+// Here: with A~ = DB^-1 A (unit diagonal, NO couplings inside a block) the block update of B is the point update of its rows on A~, and
+// the rows of a block are independent of each other -- a block sweep over A is an ordinary point sweep over A~ in block-major order.
+// The shadow level L.bgs holds A~ in the split layout (all sweep kernels, schedules and row-major copies apply unchanged); the level itself
+// keeps A in the same numbering for the residual updates and the SpMV.  A~ has the union pattern of a block's rows (more entries than
+// A: the price of reusing the point kernels; the reference applies DB^-1 densely instead).
+void Amg::setup_bgs(Level &L, const DevCsr &dA)
+{
+  const i64 n = L.n;
+  const int b = L.b, bs = b * b;
+  const HostBsr &A = L.hA;
+  i64 nb = 0;
+  for (i64 v = 0; v < n; v++) nb = std::max<i64>(nb, (i64)L.gs_block[v] + 1);
+  // members of every block, ascending
+  std::vector<i64> bptr(nb + 1, 0);
+  for (i64 v = 0; v < n; v++)
+    if (L.gs_block[v] >= 0 && (L.free_mask.empty() || L.free_mask[v])) bptr[L.gs_block[v] + 1]++;
+  for (i64 k = 0; k < nb; k++) bptr[k + 1] += bptr[k];
+  std::vector<i32> mem(bptr[nb]);
+  {
+    std::vector<i64> pos(bptr.begin(), bptr.end() - 1);
+    for (i64 v = 0; v < n; v++)
+      if (L.gs_block[v] >= 0 && (L.free_mask.empty() || L.free_mask[v])) mem[pos[L.gs_block[v]]++] = (i32)v;
+  }
+  std::vector<uint8_t> in_block(n, 0);
+  for (i32 v : mem) in_block[v] = 1;
+  // DB^-1 as a block-diagonal sparse matrix (original numbering); rows outside the blocks stay empty
+  HostBsr D;
+  D.nrows = D.ncols = n; D.bh = D.bw = b;
+  D.rowptr.assign(n + 1, 0);
+  for (i64 k = 0; k < nb; k++) for (i64 q = bptr[k]; q < bptr[k + 1]; q++) D.rowptr[mem[q] + 1] = bptr[k + 1] - bptr[k];
+  for (i64 v = 0; v < n; v++) D.rowptr[v + 1] += D.rowptr[v];
+  D.col.resize(D.rowptr[n]);
+  D.val.assign((size_t)D.rowptr[n] * bs, 0.0);
+  std::atomic<int> singular{0};
+  parallel_for(nb, [&](i64 lo, i64 hi) {
+    std::vector<double> dense;
+    for (i64 k = lo; k < hi; k++) {
+      const i64 m = bptr[k + 1] - bptr[k];
+      if (m == 0) continue;
+      const int N = (int)m * b;
+      dense.assign((size_t)N * N, 0.0);
+      for (i64 qi = 0; qi < m; qi++) {
+        const i32 i = mem[bptr[k] + qi];
+        for (i64 e = A.rowptr[i]; e < A.rowptr[i + 1]; e++) {
+          const i32 j = A.col[e];
+          if (L.gs_block[j] != (i32)k || !in_block[j]) continue;
+          const i64 qj = std::lower_bound(mem.begin() + bptr[k], mem.begin() + bptr[k + 1], j) - (mem.begin() + bptr[k]);
+          for (int p = 0; p < b; p++) for (int q = 0; q < b; q++) dense[(size_t)(qi * b + p) * N + qj * b + q] = A.val[e * bs + p * b + q];
+        }
+      }
+      if (!dense_invert(N, dense)) { singular.store(1); continue; }
+      for (i64 qi = 0; qi < m; qi++) {
+        const i32 i = mem[bptr[k] + qi];
+        for (i64 qj = 0; qj < m; qj++) {
+          const i64 e = D.rowptr[i] + qj;
+          D.col[e] = mem[bptr[k] + qj];
+          for (int p = 0; p < b; p++) for (int q = 0; q < b; q++) D.val[e * bs + p * b + q] = dense[(size_t)(qi * b + p) * N + qj * b + q];
+        }
+      }
+    }
+  }, 64);
+  if (singular.load()) throw Error("bgs: singular diagonal block");
+  // A~ = DB^-1 A on the device; inside a block it is the identity by construction: set it exactly (rounding leaves ~1e-17 couplings
+  // that would chain the rows of a block) and drop those entries from the pattern
+  HostBsr At;
+  {
+    DevCsr dD, dAt;
+    dev_csr_upload(D, dD, st);
+    dev_spgemm(dD, dA, dAt, st, &launches);
+    dev_csr_download(dAt, At, st, true);
+    dev_csr_free(dD); dev_csr_free(dAt);
+  }
+  {
+    HostBsr F;
+    F.nrows = F.ncols = n; F.bh = F.bw = b;
+    F.rowptr.assign(n + 1, 0);
+    for (i64 i = 0; i < n; i++) {
+      i64 c = in_block[i] ? 1 : 0;
+      if (in_block[i])
+        for (i64 e = At.rowptr[i]; e < At.rowptr[i + 1]; e++) c += (L.gs_block[At.col[e]] != L.gs_block[i] || !in_block[At.col[e]]);
+      F.rowptr[i + 1] = F.rowptr[i] + c;
+    }
+    F.col.resize(F.rowptr[n]);
+    F.val.assign((size_t)F.rowptr[n] * bs, 0.0);
+    parallel_for(n, [&](i64 lo, i64 hi) {
+      for (i64 i = lo; i < hi; i++) {
+        if (!in_block[i]) continue;
+        i64 o = F.rowptr[i];
+        bool diag_done = false;
+        auto put_diag = [&]() { F.col[o] = (i32)i; for (int p = 0; p < b; p++) F.val[o * bs + p * b + p] = 1.0; o++; diag_done = true; };
+        for (i64 e = At.rowptr[i]; e < At.rowptr[i + 1]; e++) {
+          const i32 j = At.col[e];
+          if (L.gs_block[j] == L.gs_block[i] && in_block[j]) continue;
+          if (!diag_done && j > i) put_diag();
+          F.col[o] = j;
+          for (int q = 0; q < bs; q++) F.val[o * bs + q] = At.val[e * bs + q];
+          o++;
+        }
+        if (!diag_done) put_diag();
+      }
+    }, 1024);
+    At = std::move(F);
+  }
+  // shadow level: A~ with the block-major sweep order
+  L.bgs = std::make_unique<Level>();
+  Level &S = *L.bgs;
+  S.n = n; S.b = b; S.nnz = At.nnz();
+  S.free_mask = in_block;
+  S.sweep_rank.assign(n, 0);
+  {
+    i32 r = 0;
+    for (i32 v : mem) S.sweep_rank[v] = r++;
+    for (i64 v = 0; v < n; v++) if (!in_block[v]) S.sweep_rank[v] = r++;
+  }
+  S.hA = std::move(At);
+  S.sm_type = SM_GS;
+  S.pinv = false;
+  level_schedule(S.hA, S.free_mask, true, S, st);
+  S.d_err = d_err;
+  {
+    DevCsr dAt;
+    dev_csr_upload(S.hA, dAt, st);
+    build_level_layout(S, dAt);
+    dev_csr_free(dAt);
+  }
+  alloc_vectors(S);
+  HostBsr().rowptr.swap(S.hA.rowptr); std::vector<i32>().swap(S.hA.col); std::vector<double>().swap(S.hA.val);
+  // the level itself lives in the same numbering (its own split is only used as a whole: residual, SpMV)
+  L.perm = S.perm; L.npad = S.npad; L.nonfree_pad = S.nonfree_pad; L.depth = S.depth; L.level_start = S.level_start;
+  L.hM = std::move(D);   // parked until the level's permutation is on the device (finish in finalize)
+}
+
+// SmoothRESSimple (loc_block_gssmoother_impl.hpp:691-706): d = (T~ + I)^-1 DB^-1 res over the blocks in sweep order, x += d, res -= A d
+void Amg::bgs_res(Level &L, bool backward, double *x, double *res)
+{
+  Level &S = *L.bgs;
+  const i64 np = L.npad * L.b;
+  transfer(L.DBI, res, nullptr, L.tmp, 1.0, 0.0);
+  tri_dispatch(S, backward, false, true, L.tmp, nullptr, L.y, S.res);
+  k_axpby<<<nblk(np), TB, 0, st>>>(np, 1.0, L.y, 1.0, x);
+  launches++;
+  spmv_part(L, 4, L.y, res, res, -1.0, 1.0, nullptr);
+}
+
+// SmoothSimple (:672-688): x_B += DB^-1 (b_B - A_{B,:} x) over the blocks in sweep order == point sweep on A~ against DB^-1 b
+void Amg::bgs_rhs(Level &L, bool backward, double *x, const double *b)
+{
+  Level &S = *L.bgs;
+  transfer(L.DBI, b, nullptr, S.rhs, 1.0, 0.0);
+  gs_rhs(S, backward, x, S.rhs, L.y);
+  NGB_CUDA(cudaMemcpyAsync(x, L.y, sizeof(double) * L.npad * L.b, cudaMemcpyDeviceToDevice, st));
 }
 
 // the instantiations of the CTA-per-tile sweep: 256-row tiles run on 128-thread CTAs (6 per SM), 512-row tiles on 256-thread CTAs (3 per SM)
@@ -1205,6 +1373,10 @@ void Amg::build_coarse_inverse(Level &L)
 // ------------------------------------------------------------------------------------------------
 // setup driver == BaseAMGPC::BuildAMGMat (amg_pc.cpp:565-736) + BaseAMGFactory::SetUpLevels (base_factory.cpp:219-353)
 // ------------------------------------------------------------------------------------------------
+namespace {
+void build_plain_sell(const HostBsr &H, const i32 *d_rperm, const i32 *d_cperm, i64 nrows_pad, Sell &S, cudaStream_t st, i64 *launches);
+}
+
 void Amg::finalize()
 {
   if (finalized) throw Error("finalize called twice");
@@ -1242,6 +1414,7 @@ void Amg::finalize()
     Level &L = *lev[l];
     L.n = L.hA.nrows; L.b = L.hA.bh; L.nnz = L.hA.nnz();
     bool coarsest = injected.empty() ? (l + 1 >= max_levels || L.n <= max_coarse) : (l >= (int)injected.size());
+    std::vector<i32> vmap;   // vertex -> coarse vertex of the built-in coarsening (the aggregates: blocks of the block smoother)
     if (!coarsest) {
       auto h0 = std::chrono::steady_clock::now();
       if (!injected.empty()) {
@@ -1251,10 +1424,9 @@ void Amg::finalize()
         // elasticity: displacement-only fine level (b = dim) maps to displacement+rotation coarse levels
         int bc = L.b;
         if (elast && l == 0 && L.b == dim) bc = (dim == 3) ? 6 : 3;
-        std::vector<i32> vmap;
         std::vector<double> cxyz;
         build_prolongation(L.hA, L.free_mask.empty() ? nullptr : L.free_mask.data(), bc, L.xyz, copt, L.hP, vmap, cxyz);
-        if (L.hP.ncols == 0 || L.hP.ncols > 0.8 * L.n) coarsest = true;  // coarsening stalled
+        if (L.hP.ncols == 0 || L.hP.ncols > 0.8 * L.n) { coarsest = true; vmap.clear(); }  // coarsening stalled
         else {
           auto nl = std::make_unique<Level>();
           nl->xyz = std::move(cxyz);
@@ -1269,7 +1441,8 @@ void Amg::finalize()
       const std::string smt = flags.spec("sm_type", l, "gs");
       if (smt == "gs") L.sm_type = SM_GS;
       else if (smt == "jacobi") L.sm_type = SM_JACOBI;
-      else throw Error("sm_type=" + smt + " is not supported by the B200 path (gs | jacobi)");
+      else if (smt == "bgs") L.sm_type = (coarsest || vmap.empty()) ? SM_GS : SM_BGS;   // no coarse map -> GS (SelectSmoother, amg_pc_vertex_impl.hpp:572-585)
+      else throw Error("sm_type=" + smt + " is not supported by the B200 path (gs | jacobi | bgs)");
       L.sm_steps = std::max(1, std::atoi(flags.spec("sm_steps", l, "1").c_str()));
       const std::string sy = flags.spec("sm_symm", l, "0");
       L.sm_symm = (sy == "1" || sy == "True" || sy == "true");
@@ -1306,6 +1479,7 @@ void Amg::finalize()
         greedy_coloring_perm(lev[l + 1]->hA, cperm, ncol);
         permute_symmetric(lev[l + 1]->hA, cperm);
         renumber_columns(L.hP, cperm);
+        for (i32 &c : vmap) if (c >= 0) c = cperm[c];
         std::vector<double> &cx = lev[l + 1]->xyz;
         if (!cx.empty()) {
           std::vector<double> nx(cx.size());
@@ -1326,9 +1500,15 @@ void Amg::finalize()
         int ncol = 0;
         greedy_coloring_perm(L.hA, L.sweep_rank, ncol);
       }
+      if (L.sm_type == SM_BGS) {
+        // block Gauss-Seidel: the blocks are the aggregates; the shadow level of A~ = DB^-1 A fixes the numbering of this level
+        L.gs_block = vmap;
+        setup_bgs(L, dA);
+      } else {
       // tile-major numbering + two-level schedule for big scalar levels with a deep sweep DAG (setup_tiles)
       if (!coarsest) setup_tiles(L, l, L.hA);
       if (!L.tiled) level_schedule(L.hA, L.mask(), !coarsest, L, st);
+      }
       L.d_err = d_err;
       host_s += tick(h0);
       if (verbose) std::fprintf(stderr, "[ngsamg_b200] level %d: level schedule %.2f s (depth %d)\n", l, tick(h0), L.depth);
@@ -1337,6 +1517,10 @@ void Amg::finalize()
     else {
       L.d_perm = upload_vec(L.perm, st);
       if (clev == "inv") build_coarse_inverse(L);
+    }
+    if (L.sm_type == SM_BGS) {   // DB^-1 in the level's numbering (parked in hM by setup_bgs)
+      build_plain_sell(L.hM, L.d_perm, L.d_perm, L.npad, L.DBI, st, &launches);
+      L.hM = HostBsr();
     }
     alloc_vectors(L);
     dev_csr_free(dA);
@@ -2167,6 +2351,14 @@ void Amg::smooth_once(Level &L, double *x, const double *b, double *res, bool ru
     } else {
       if (ur) { calc_residuum(L, x, b, res, xz); gs_res(L, backward, x, res, xz); }
       else { if (xz) NGB_CUDA(cudaMemsetAsync(x, 0, sizeof(double) * L.npad * L.b, st)); gs_rhs(L, backward, x, b, L.y); NGB_CUDA(cudaMemcpyAsync(x, L.y, sizeof(double) * L.npad * L.b, cudaMemcpyDeviceToDevice, st)); }
+    }
+  } else if (L.sm_type == SM_BGS) {
+    // BSmoother2::SmoothWO (loc_block_gssmoother_impl.hpp:656-669)
+    if (xz) NGB_CUDA(cudaMemsetAsync(x, 0, sizeof(double) * L.npad * L.b, st));
+    if (ru && ur) bgs_res(L, backward, x, res);
+    else {
+      bgs_rhs(L, backward, x, b);
+      if (ur) calc_residuum(L, x, b, res, false);
     }
   } else {
     if (xz) NGB_CUDA(cudaMemsetAsync(x, 0, sizeof(double) * L.npad * L.b, st));
@@ -3027,6 +3219,20 @@ static Level &get_level(Amg &a, int level)
   if (level < 0 || level >= (int)a.lev.size()) throw Error("level out of range");
   return *a.lev[level];
 }
+
+// blocks of the block Gauss-Seidel smoother of `level` (GetGSBlocks, amg_pc_vertex_impl.hpp:1171-1269): block_of[v] = block (coarse vertex) of
+// vertex v, -1 = in no block; returns 1 with an error if the level is not smoothed by bgs
+int ngsamg_b200_get_gs_blocks(ngsamg_b200_t *h, int level, int32_t *block_of)
+{
+  NGB_TRY
+  Amg &a = ready(h);
+  Level &L = get_level(a, level);
+  if (L.sm_type != SM_BGS) throw Error("get_gs_blocks: level " + std::to_string(level) + " is not smoothed by block Gauss-Seidel");
+  if (block_of)
+    for (i64 v = 0; v < L.n; v++) block_of[v] = (L.free_mask.empty() || L.free_mask[v]) ? L.gs_block[v] : -1;
+  NGB_CATCH
+}
+
 
 static void apply_impl(Amg &a, double s, const double *b, double *x, bool add)
 {

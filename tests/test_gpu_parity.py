@@ -421,6 +421,60 @@ def test_wide_rows_on_a_small_level(bw):
     assert rel(pc * b, amg.apply(b)) < TOL_VCYCLE
 
 
+@pytest.mark.parametrize("problem", ["poisson", "elasticity"])
+def test_block_gauss_seidel(problem):
+    """sm_type = bgs (what the reference's elasticity examples run, examples/elasticity/beamP2.py:60-61): blocks = the aggregates of
+    the next coarse map; every flag combination of the smoother protocol, forward and backward, on the two finest levels against the
+    restated BSmoother2 (oracle/oracle_bgs.py), then the whole V-cycle and the PCG iteration count against a V-cycle built from it."""
+    import scipy.sparse as sp
+    import scipy.sparse.linalg as spla
+    from oracle import oracle_bgs as OB
+    if problem == "poisson":
+        p, A = poisson(9)
+        pc = ng.h1_scal(A, p["free"], ngs_amg_max_coarse_size=20, ngs_amg_sm_type="bgs")
+        b = 1
+    else:
+        p, A = elasticity(7, 4, 4)
+        pc = ng.elast_3d(A, p["free"], vertex_xyz=p["xyz"], ngs_amg_max_coarse_size=6, ngs_amg_sm_type="bgs", ngs_amg_regularize_cmats=False)
+        b = 3
+    NL = pc.GetNLevels()
+    assert NL >= 3
+    mats = [pc.GetLevelMatrix(l).to_scipy().tocsr() for l in range(NL)]
+    prols = [P.to_scipy().tocsr() for P in pc.GetMap()]
+    sm = []
+    for l in range(NL - 1):
+        blk = pc.GetGSBlocks(l)
+        assert blk.max() + 1 == pc.GetNDof(l + 1) and (blk >= 0).sum() > 0
+        sm.append(OB.BlockGS(mats[l], pc.GetBlockSize(l), blk))
+    # --- the smoother protocol on levels 0 and 1
+    for l in (0, 1):
+        n = mats[l].shape[0]
+        for back in (False, True):
+            for ru, ur in ((True, True), (False, True), (False, False)):
+                x0, rhs = rand(200 + l, n), rand(210 + l, n)
+                res0 = rhs - mats[l] @ x0
+                xg, rg = x0.copy(), (res0.copy() if ru else rand(220, n))
+                pc._smooth(l, xg, rhs, rg, ru, ur, False, back)
+                xo, ro = x0.copy(), (res0.copy() if ru else np.zeros(n))
+                sm[l].smooth(xo, rhs, ro, ru, ur, False, back)
+                assert rel(xg, xo) < TOL_VCYCLE, (l, back, ru, ur)
+                if ur:
+                    assert np.linalg.norm(rg - ro) < TOL_VCYCLE * np.linalg.norm(rhs), (l, back, ru, ur)
+    # --- the V-cycle and PCG
+    Ac = mats[-1].toarray()
+    cs = lambda r: np.linalg.solve(Ac, r)
+    bvec = rand(230, mats[0].shape[0]) * np.repeat(p["free"], b)
+    assert rel(pc * bvec, OB.vcycle(mats, prols, sm, cs, bvec)) < TOL_VCYCLE
+    cg = ng.CGSolver(mat=A, pre=pc, maxsteps=100, tol=1e-8)
+    cg.Solve(p["rhs"])
+    its_bgs = cg.iterations
+    pc_gs = ng.h1_scal(A, p["free"], ngs_amg_max_coarse_size=20) if problem == "poisson" else \
+        ng.elast_3d(A, p["free"], vertex_xyz=p["xyz"], ngs_amg_max_coarse_size=6, ngs_amg_regularize_cmats=False)
+    cg2 = ng.CGSolver(mat=A, pre=pc_gs, maxsteps=100, tol=1e-8)
+    cg2.Solve(p["rhs"])
+    assert its_bgs <= cg2.iterations + 1          # a block smoother is at least as strong as the point smoother on these problems
+
+
 def _check_multicolor(p, A, pc):
     import scipy.sparse as sp
     n = p["n"]

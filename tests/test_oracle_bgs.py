@@ -1,0 +1,87 @@
+"""CPU checks of the restated block Gauss-Seidel smoother (oracle/oracle_bgs.py; BSmoother2, loc_block_gssmoother_impl.hpp)"""
+import numpy as np
+
+import ngsamg_b200 as ng
+from helpers import poisson, rand, rel, to_oracle
+from oracle import oracle as O
+from oracle import oracle_bgs as OB
+
+
+def _setup(n=6):
+    p, A = poisson(n)
+    return p, A, A.to_scipy().tocsr()
+
+
+def test_singleton_blocks_are_point_gauss_seidel():
+    """blocks of one vertex each: BSBlock::RichardsonUpdate is GSS3's row update (gssmoother.cpp:195-257), forward and backward"""
+    p, A, As = _setup()
+    n = p["n"]
+    blk = np.where(p["free"] > 0, np.cumsum(p["free"].astype(np.int64)) - 1, -1)
+    g = OB.BlockGS(As, 1, blk)
+    x0, b = rand(1, n), rand(2, n)
+    for back in (False, True):
+        x = x0.copy()
+        g.smooth_simple(x, b, reverse=back)
+        # independent literal point sweep
+        xs = x0.copy()
+        order = range(n - 1, -1, -1) if back else range(n)
+        for i in order:
+            if p["free"][i]:
+                xs[i] += (b[i] - As[i].dot(xs)[0]) / As[i, i]
+        assert rel(x, xs) < 1e-14
+
+
+def test_res_form_equals_rhs_form_and_keeps_the_residual():
+    """RichardsonUpdate_RES == RichardsonUpdate when res = b - A x on entry (symmetric A), and leaves res = b - A x_new"""
+    p, A, As = _setup(7)
+    n = p["n"]
+    blk = np.where(p["free"] > 0, (np.arange(n) // 5), -1)
+    # make the block ids contiguous
+    ids = np.unique(blk[blk >= 0])
+    remap = -np.ones(blk.max() + 2, np.int64)
+    remap[ids] = np.arange(len(ids))
+    blk = np.where(blk >= 0, remap[blk], -1)
+    g = OB.BlockGS(As, 1, blk)
+    x0, b = rand(3, n), rand(4, n)
+    for back in (False, True):
+        x1, r1 = x0.copy(), b - As @ x0
+        g.smooth(x1, b, r1, True, True, False, back)
+        x2, r2 = x0.copy(), np.zeros(n)
+        g.smooth(x2, b, r2, False, True, False, back)
+        assert rel(x1, x2) < 1e-13 and np.linalg.norm(r1 - r2) < 1e-13 * np.linalg.norm(b)
+        assert np.linalg.norm(r1 - (b - As @ x1)) < 1e-13 * np.linalg.norm(b)
+        # non-block (Dirichlet) vertices are never touched
+        assert np.array_equal(x1[blk < 0], x0[blk < 0])
+
+
+def test_block_sweep_is_a_point_sweep_on_the_prescaled_matrix():
+    """the identity the CUDA path rests on (csrc/amg.cu setup_bgs): with A~ = DB^-1 A the block update of B is the point update of its
+    rows on A~ (unit diagonal, no couplings inside a block) against DB^-1 b"""
+    import scipy.sparse as sp
+    p, A, As = _setup(6)
+    n = p["n"]
+    blk = np.where(p["free"] > 0, np.arange(n) // 4, -1)
+    ids = np.unique(blk[blk >= 0])
+    remap = -np.ones(blk.max() + 2, np.int64)
+    remap[ids] = np.arange(len(ids))
+    blk = np.where(blk >= 0, remap[blk], -1)
+    g = OB.BlockGS(As, 1, blk)
+    Dinv = sp.lil_matrix((n, n))
+    for dofs, DB, DBinv in g.blocks:
+        Dinv[np.ix_(dofs, dofs)] = DBinv
+    Dinv = Dinv.tocsr()
+    At = (Dinv @ As).toarray()
+    bt = Dinv @ rand(5, n)
+    b = rand(5, n)
+    x0 = rand(6, n)
+    x = x0.copy()
+    g.smooth_simple(x, b)
+    xs = x0.copy()
+    for dofs, _, _ in g.blocks:
+        new = {}
+        for i in dofs:
+            off = [j for j in range(n) if blk[j] != blk[i] or j == i]
+            new[i] = bt[i] - sum(At[i, j] * xs[j] for j in off if j != i)
+        for i in dofs:
+            xs[i] = new[i]
+    assert rel(x, xs) < 1e-12
