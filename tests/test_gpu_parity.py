@@ -266,7 +266,7 @@ def test_edge_cases():
     with pytest.raises(ng.NgsAMGError):
         ng.h1_scal(A3, p3["free"], ngs_amg_mg_cycle="F")      # V | W | BS are the reference's cycles (amg_pc.cpp:293)
     with pytest.raises(ng.NgsAMGError):
-        ng.h1_scal(A3, p3["free"], ngs_amg_sm_type="bgs")
+        ng.h1_scal(A3, p3["free"], ngs_amg_sm_type="dyn_block_gs")     # gs | jacobi | bgs
 
 
 def test_device_pointers_torch():
