@@ -17,6 +17,10 @@
  *   - vector arguments may be HOST or DEVICE pointers; the library detects which
  *     (cudaPointerGetAttributes) and stages host buffers through pinned memory.
  *   - there is no CPU fallback: without a CUDA device every call fails with an error.
+ *   - the Gauss-Seidel sweeps are sync-free kernels whose CTAs wait for each other's results: they are launched cooperatively
+ *     (cudaLaunchAttributeCooperative), so the driver rejects a grid that cannot be co-resident instead of letting it dead-lock, and
+ *     every wait loop shares one watchdog flag (a timed-out sweep makes apply / pcg return an error).  Run ONE process per GPU and
+ *     do not share the device with other long-running kernels while a V-cycle is in flight (MPS time-slicing is fine, it is only slow).
  */
 #ifndef NGSAMG_B200_H
 #define NGSAMG_B200_H

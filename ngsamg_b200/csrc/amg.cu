@@ -2661,6 +2661,7 @@ void Amg::check_watchdog()
     NGB_CUDA(cudaMemsetAsync(d_err, 0, sizeof(int), st));
     throw Error("Gauss-Seidel sweep: dependency wait timed out (watchdog) -- results invalid");
   }
+  if (nested) nested->check_watchdog();   // rank 0: the serial hierarchy below the contracted level has its own flag
 }
 
 double Amg::dot(i64 n, const double *a, const double *b)
