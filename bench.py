@@ -105,6 +105,12 @@ def make_problem(n, problem="poisson"):
         p = S.elasticity3d_p2_kuhn_stencil(n, ny, ny)
         A = ng.SparseMatrix(p["n"], p["n"], 3, 3, p["rowptr"], p["col"], p["val"])
         return p, A
+    if problem == "elasticity_jump":
+        # BASELINE.json configs[4] on ONE GPU: P1 elasticity with a jumping Young's modulus (checkerboard of 8^3-cell boxes, contrast 1e4; the
+        # 3D analogue of tests/elasticity/mdim/jump/test_2d_jump_lo.py); n = 201 gives 2.05 M vertices = 6.15 M DOFs (the per-GPU share of ~50 M on 8)
+        p = S.elasticity3d_kuhn_jump_stencil(n, n // 2 + 1, n // 2 + 1, S.checkerboard_modulus(8, 1e4))
+        A = ng.SparseMatrix(p["n"], p["n"], 3, 3, p["rowptr"], p["col"], p["val"])
+        return p, A
     if problem == "elasticity":
         # P1 elasticity beam (3x3 blocks, 6x6 on the coarse levels): nx x (nx/2) x (nx/2) vertices, clamped at x=0, body force (0,x,0)
         p = S.elasticity3d_kuhn_stencil(n, n // 2 + 1, n // 2 + 1)
@@ -269,9 +275,10 @@ def main():
     ap.add_argument("--cpu-n", type=int, default=int(os.environ.get("NGSAMG_BENCH_CPU_N", CPU_SAMPLE_N)))
     ap.add_argument("--cpu-n-par", type=int, default=int(os.environ.get("NGSAMG_BENCH_CPU_N_PAR", 61)),
                     help="vertices per axis and rank of the multi-rank CPU reference arm (N > 1)")
-    ap.add_argument("--problem", default="poisson", choices=["poisson", "elasticity", "elasticity_p2"],
+    ap.add_argument("--problem", default="poisson", choices=["poisson", "elasticity", "elasticity_p2", "elasticity_jump"],
                     help="poisson = BASELINE.json configs[1] (headline); elasticity = P1 beam with elast_3d; elasticity_p2 = BASELINE.json "
-                         "configs[2], nodal-P2 beam (--size 151 = 9.2 M DOFs); both secondary, reported on request")
+                         "configs[2], nodal-P2 beam (--size 151 = 9.2 M DOFs); elasticity_jump = the configs[4] workload on one GPU (P1, modulus jumping by "
+                         "1e4 on a checkerboard, --size 201 = 6.15 M DOFs); all secondary, reported on request")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-multicolor", action="store_true", help="skip the separately reported multicolour-smoother variant")
     args = ap.parse_args()
@@ -331,7 +338,7 @@ def main():
         p, A = make_problem(n, args.problem)
     gen_s = time.time() - t0
     progress("problem generated")
-    elast = args.problem in ("elasticity", "elasticity_p2")
+    elast = args.problem in ("elasticity", "elasticity_p2", "elasticity_jump")
     if elast:
         args.no_cpu_baseline = True
         args.no_multicolor = True
@@ -523,7 +530,7 @@ def main():
                                     "interface DOFs shared), h1_scal + CG to 1e-8, hybrid Gauss-Seidel + NCCL halo exchange" % (tuple(p["global_dims"]) + (ndof_global, world) + tuple(grid) + (n,))) if world > 1 else
                                    ("3D Poisson P1 unit cube (Kuhn tets), %d^3 = %d DOFs per GPU, h1_scal + CG to 1e-8" % (n, ndof)) if not elast else
                                    ("3D linear elasticity %s beam (Kuhn tets), %d nodes = %d DOFs per GPU, elast_3d (3x3 fine / 6x6 coarse blocks) + CG to 1e-6"
-                                    % ("nodal-P2 (BASELINE configs[2]; AMG on all P2 nodes)" if args.problem == "elasticity_p2" else "P1", p["n"], ndof)),
+                                    % ({"elasticity_p2": "nodal-P2 (BASELINE configs[2]; AMG on all P2 nodes)", "elasticity_jump": "P1, Young's modulus jumping by 1e4 on a checkerboard of 8^3-cell boxes (BASELINE configs[4] workload, one GPU),"}.get(args.problem, "P1"), p["n"], ndof)),
                        "tol": tol, "levels": levels, "operator_complexity": pc.GetOC()[0],
                        "parallelism": "1 GPU" if world == 1 else "%d subdomains, one per GPU; DIS2CO/CO2CU halo exchange per sweep, all-reduced CG dot products, coarse levels contracted onto rank 0" % world,
                        "multi_gpu": par_info,

@@ -308,7 +308,13 @@ struct Amg {
   void bgs_res(Level &L, bool backward, double *x, double *res);
   void bgs_rhs(Level &L, bool backward, double *x, const double *b);
   // shallow dependency DAG with many rows per level: one plain launch per level (k_gs_level)
-  bool level_launch(const Level &L) const { return L.depth <= tri_level_launch_depth && L.npad > tri_level_launch_rows && (int)L.level_start.size() == L.depth + 1; }
+  // (scalar levels only: a colour of a 6x6 level is a few thousand rows of ~25 blocks each -- too few threads with too long chains for a
+  // thread-per-row launch; measured 9.6 ms per V-cycle on a 258 k-row level against ~3 ms with a warp per row on the row-major copy)
+  bool level_launch(const Level &L) const
+  {
+    if (L.b > 1 && tri_block_warp_rows) return false;
+    return L.depth <= tri_level_launch_depth && L.npad > tri_level_launch_rows && (int)L.level_start.size() == L.depth + 1;
+  }
   void prepare_ctile(Level &L);
   bool prepare_itile(Level &L);
   bool setup_tiles(Level &L, int l, const HostBsr &A);

@@ -625,3 +625,73 @@ def elasticity3d_p2_kuhn_load_only(nv, shift=0.0):
     a, b = 0.5854101966249685, 0.1381966011250105
     xq = np.einsum("qv,tv->tq", np.full((4, 4), b) + (a - b) * np.eye(4), Pv[..., 0]) + shift
     return np.bincount(N.ravel(), weights=np.einsum("tq,tqi,t->ti", xq, V, vol / 4.0).ravel(), minlength=n)
+
+
+# ---- P1 elasticity with a jumping Young's modulus (BASELINE.json configs[4]; 3D analogue of tests/elasticity/mdim/jump/test_2d_jump_lo.py:4-9:
+# a checkerboard of sub-boxes whose modulus differs by `contrast`) -------------------------------------------------------------------
+def checkerboard_modulus(box_cells, contrast=1e4):
+    """E multiplier per CUBE (cx, cy, cz = cell indices): `contrast` on the odd boxes of a checkerboard of box_cells^3-cell sub-boxes"""
+    def f(cx, cy, cz):
+        odd = ((cx // box_cells) + (cy // box_cells) + (cz // box_cells)) % 2
+        return np.where(odd == 1, float(contrast), 1.0)
+    return f
+
+
+def elasticity3d_kuhn_jump_stencil(nx, ny, nz, cube_modulus, E=1e3, nu=0.15, clamp=("x0",)):
+    """elasticity3d_kuhn(..., jump=piecewise constant per cube) for LARGE uniform meshes.  Every cube of the Kuhn mesh carries the same
+    six tets, so A = sum over cubes of E_cube * K_cube with ONE 8x8-vertex block matrix K_cube (unit modulus, read off a 2^3-vertex
+    element-assembled mesh): the block row of a vertex is assembled from its (up to) 8 incident cubes, vectorised over all vertices.
+    cube_modulus(cx, cy, cz) -> multiplier of E for the cube with lower corner (cx, cy, cz).  Same dict as elasticity3d_kuhn."""
+    one = elasticity3d_kuhn(2, 2, 2, E=E, nu=nu, clamp=())                      # h = 1: blocks scale linearly with h
+    hs = 1.0 / (min(ny, nz) - 1)
+    rp, rc, rv = one["rowptr"], one["col"], one["val"].reshape(-1, 3, 3)
+    Kc = np.zeros((8, 8, 3, 3))
+    conn = np.zeros((8, 8), bool)
+    for a in range(8):
+        for e in range(rp[a], rp[a + 1]):
+            Kc[a, rc[e]] = rv[e] * hs
+            conn[a, rc[e]] = True
+    corner = [(a & 1, (a >> 1) & 1, (a >> 2) & 1) for a in range(8)]             # vertex a of the 2x2x2 mesh = x + 2 (y + 2 z)
+    n = nx * ny * nz
+    dirs = [(0, 0, 0)] + _POS_DIRS + [(-a, -b, -c) for (a, b, c) in _POS_DIRS]
+    dirs.sort(key=lambda d: d[0] + nx * (d[1] + ny * d[2]))
+    K = len(dirs)
+    dir_id = {d: k for k, d in enumerate(dirs)}
+    ids = np.arange(n, dtype=np.int64)
+    ix, iy, iz = ids % nx, (ids // nx) % ny, ids // (nx * ny)
+    mask = np.zeros((n, K), bool)
+    cols = np.zeros((n, K), np.int64)
+    for k, d in enumerate(dirs):
+        jx, jy, jz = ix + d[0], iy + d[1], iz + d[2]
+        mask[:, k] = (jx >= 0) & (jx < nx) & (jy >= 0) & (jy < ny) & (jz >= 0) & (jz < nz)
+        cols[:, k] = ids + d[0] + nx * (d[1] + ny * d[2])
+    rowptr = np.zeros(n + 1, np.int64)
+    np.cumsum(mask.sum(axis=1), out=rowptr[1:])
+    col = cols[mask].astype(np.int32)
+    del cols
+    slot = np.cumsum(mask, axis=1, dtype=np.int16) - 1
+    val = np.zeros((int(rowptr[-1]), 3, 3))
+    ntet_w = np.zeros(n)                                                          # (for the lumped load) tets incident to the vertex
+    for a, (ax, ay, az) in enumerate(corner):
+        # the cube in which vertex v is corner a has lower corner v - corner[a]
+        cx, cy, cz = ix - ax, iy - ay, iz - az
+        ok = (cx >= 0) & (cx <= nx - 2) & (cy >= 0) & (cy <= ny - 2) & (cz >= 0) & (cz <= nz - 2)
+        rows = np.flatnonzero(ok)
+        Ec = cube_modulus(cx[rows], cy[rows], cz[rows])
+        for b2, (bx, by, bz) in enumerate(corner):
+            if not conn[a, b2]:
+                continue
+            k = dir_id[(bx - ax, by - ay, bz - az)]
+            dst = rowptr[rows] + slot[rows, k]
+            val[dst] += Ec[:, None, None] * Kc[a, b2][None]
+        ntet_w[rows] += 6 if a in (0, 7) else 2
+    free = np.ones(n, np.uint8)
+    dims = (nx, ny, nz)
+    coord = (ix, iy, iz)
+    for tag in clamp:
+        ax_ = "xyz".index(tag[0])
+        free[coord[ax_] == (0 if tag[1] == "0" else dims[ax_] - 1)] = 0
+    X = np.stack([ix * hs, iy * hs, iz * hs], axis=1).astype(np.float64)
+    rhs = np.zeros((n, 3))
+    rhs[:, 1] = (hs ** 3 / 24.0) * ntet_w * X[:, 0]
+    return dict(n=n, b=3, rowptr=rowptr, col=col, val=val.reshape(-1), free=free, rhs=rhs.reshape(-1), xyz=X)

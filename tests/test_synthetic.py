@@ -30,3 +30,20 @@ def test_p2_elasticity_is_symmetric_and_keeps_the_rigid_body_modes():
     # the load integrates (0, x, 0): total force = int x over the beam
     lx = X[:, 0].max()
     assert abs(a["rhs"].reshape(-1, 3)[:, 1].sum() - 0.5 * lx * lx * X[:, 1].max() * X[:, 2].max()) < 1e-12
+
+
+def test_jump_elasticity_stencil_equals_assembly():
+    """BASELINE.json configs[4] workload: P1 elasticity with a modulus jumping by 1e4 on a checkerboard -- the cube-stencil generator
+    (A = sum of E_cube * K_cube) == element assembly with the same piecewise constant modulus; uniform modulus == the uniform generator"""
+    nx, ny, nz = 7, 5, 6
+    h = 1.0 / (min(ny, nz) - 1)
+    cm = S.checkerboard_modulus(2, 1e4)
+    jump = lambda cx, cy, cz: cm(np.floor(cx / h + 1e-9).astype(int), np.floor(cy / h + 1e-9).astype(int), np.floor(cz / h + 1e-9).astype(int))
+    a = S.elasticity3d_kuhn(nx, ny, nz, jump=jump)
+    b = S.elasticity3d_kuhn_jump_stencil(nx, ny, nz, cm)
+    assert np.array_equal(a["rowptr"], b["rowptr"]) and np.array_equal(a["col"], b["col"]) and np.array_equal(a["free"], b["free"])
+    assert np.abs(a["val"] - b["val"]).max() < 1e-13 * np.abs(a["val"]).max()
+    assert np.abs(a["val"]).max() > 1e3 * np.abs(S.elasticity3d_kuhn(nx, ny, nz)["val"]).max()      # the contrast is really there
+    u = S.elasticity3d_kuhn_stencil(nx, ny, nz)
+    c = S.elasticity3d_kuhn_jump_stencil(nx, ny, nz, lambda x, y, z: np.ones(len(x)))
+    assert np.abs(u["val"] - c["val"]).max() < 1e-13 * np.abs(u["val"]).max() and np.allclose(u["rhs"], c["rhs"])
