@@ -326,13 +326,18 @@ def main():
     t0 = time.time()
     comm = None
     if world > 1:
-        if args.problem != "poisson":
-            raise SystemExit("bench.py: the multi-GPU bench runs the Poisson workload")
+        if args.problem not in ("poisson", "elasticity_jump"):
+            raise SystemExit("bench.py: the multi-GPU bench runs the Poisson workload (configs[3]) or elasticity_jump (configs[4])")
         from ngsamg_b200 import parallel as par
         from ngsamg_b200 import synthetic as S
         grid = S.bench_grid(world)
-        p = S.box_poisson3d(n, grid, rank)
-        A = ng.SparseMatrix(p["n"], p["n"], 1, 1, p["rowptr"], p["col"], p["val"])
+        if args.problem == "elasticity_jump":
+            # BASELINE.json configs[4]: n^3 vertices per GPU (--size 128 on 8 GPUs: 255^3 vertices = 49.7 M DOFs), modulus jumping by 1e4
+            p = S.box_elasticity3d_jump(n, grid, rank)
+            A = ng.SparseMatrix(p["n"], p["n"], 3, 3, p["rowptr"], p["col"], p["val"])
+        else:
+            p = S.box_poisson3d(n, grid, rank)
+            A = ng.SparseMatrix(p["n"], p["n"], 1, 1, p["rowptr"], p["col"], p["val"])
         comm = par.TorchDistComm(use_nccl=os.environ.get("NGSAMG_BENCH_TRANSPORT", "nccl") == "nccl", device=local_rank)
     else:
         p, A = make_problem(n, args.problem)
@@ -351,7 +356,10 @@ def main():
     tol = 1e-6 if elast else TOL       # the reference's elasticity tests solve to 1e-6 (tests/elasticity/amg_utils.py:439)
     if world > 1:
         args.no_multicolor = True
-        pc = par.h1_scal_par(A, par.Halo(p["peers"], p["ex"]), comm, p["free"], device=local_rank, defer_finalize=True, **extra)
+        if elast:
+            pc = par.elast_3d_par(A, par.Halo(p["peers"], p["ex"]), comm, p["free"], vertex_xyz=p["xyz"], device=local_rank, defer_finalize=True, **extra)
+        else:
+            pc = par.h1_scal_par(A, par.Halo(p["peers"], p["ex"]), comm, p["free"], device=local_rank, defer_finalize=True, **extra)
         # the library holds its own copy now: release the generator's matrix arrays before the (memory-hungry) host setup
         empty_i, empty_d = np.zeros(0, np.int32), np.zeros(0)
         p["col"], p["val"], A.col, A.val = empty_i, empty_d, empty_i, empty_d
@@ -427,7 +435,7 @@ def main():
     ndof_global = ndof
     if world > 1:
         # whole-job figures: bytes of all ranks, V-cycle time = max over ranks, global DOF count = master DOFs
-        agg = torch.tensor([vbytes, float(p["n_master"])], dtype=torch.float64, device="cuda")
+        agg = torch.tensor([vbytes, float(p["n_master"]) * A.bh], dtype=torch.float64, device="cuda")   # master vertices x DOFs per vertex
         dist.all_reduce(agg)
         vt = torch.tensor([vcycle_ms], dtype=torch.float64, device="cuda")
         dist.all_reduce(vt, op=dist.ReduceOp.MAX)
@@ -526,7 +534,10 @@ def main():
             "metric": "pcg_amg_solve_dofs_per_s", "value": ndof_global / solve_s, "unit": "DOF/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": solve_s * 1e3, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": ("3D Poisson P1 (Kuhn tets), ONE global problem of %d x %d x %d = %d DOFs cut into %d sub-boxes (%dx%dx%d) of %d^3 vertices (one per GPU, "
+            "config": {"workload": ("3D linear elasticity P1 (Kuhn tets), Young's modulus jumping by 1e4 on a checkerboard of 8^3-cell boxes (BASELINE configs[4]), ONE global problem of "
+                                    "%d x %d x %d vertices = %d DOFs cut into %d sub-boxes (%dx%dx%d) of %d^3 vertices (one per GPU, interface DOFs shared), elast_3d + CG to 1e-6, "
+                                    "hybrid Gauss-Seidel + NCCL halo exchange" % (tuple(p["global_dims"]) + (ndof_global, world) + tuple(grid) + (n,))) if (world > 1 and elast) else
+                                   ("3D Poisson P1 (Kuhn tets), ONE global problem of %d x %d x %d = %d DOFs cut into %d sub-boxes (%dx%dx%d) of %d^3 vertices (one per GPU, "
                                     "interface DOFs shared), h1_scal + CG to 1e-8, hybrid Gauss-Seidel + NCCL halo exchange" % (tuple(p["global_dims"]) + (ndof_global, world) + tuple(grid) + (n,))) if world > 1 else
                                    ("3D Poisson P1 unit cube (Kuhn tets), %d^3 = %d DOFs per GPU, h1_scal + CG to 1e-8" % (n, ndof)) if not elast else
                                    ("3D linear elasticity %s beam (Kuhn tets), %d nodes = %d DOFs per GPU, elast_3d (3x3 fine / 6x6 coarse blocks) + CG to 1e-6"

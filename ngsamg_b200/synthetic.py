@@ -637,13 +637,15 @@ def checkerboard_modulus(box_cells, contrast=1e4):
     return f
 
 
-def elasticity3d_kuhn_jump_stencil(nx, ny, nz, cube_modulus, E=1e3, nu=0.15, clamp=("x0",)):
+def elasticity3d_kuhn_jump_stencil(nx, ny, nz, cube_modulus, E=1e3, nu=0.15, clamp=("x0",), h=None, origin=(0, 0, 0)):
     """elasticity3d_kuhn(..., jump=piecewise constant per cube) for LARGE uniform meshes.  Every cube of the Kuhn mesh carries the same
     six tets, so A = sum over cubes of E_cube * K_cube with ONE 8x8-vertex block matrix K_cube (unit modulus, read off a 2^3-vertex
     element-assembled mesh): the block row of a vertex is assembled from its (up to) 8 incident cubes, vectorised over all vertices.
-    cube_modulus(cx, cy, cz) -> multiplier of E for the cube with lower corner (cx, cy, cz).  Same dict as elasticity3d_kuhn."""
+    cube_modulus(cx, cy, cz) -> multiplier of E for the cube with lower corner (cx, cy, cz).  Same dict as elasticity3d_kuhn.
+    h / origin: the mesh is the sub-box of a larger one starting at vertex `origin` (cube indices passed to cube_modulus and the
+    coordinates are global); only the sub-box's own cubes are assembled (a rank's sub-assembled matrix, see box_elasticity3d_jump)."""
     one = elasticity3d_kuhn(2, 2, 2, E=E, nu=nu, clamp=())                      # h = 1: blocks scale linearly with h
-    hs = 1.0 / (min(ny, nz) - 1)
+    hs = 1.0 / (min(ny, nz) - 1) if h is None else float(h)
     rp, rc, rv = one["rowptr"], one["col"], one["val"].reshape(-1, 3, 3)
     Kc = np.zeros((8, 8, 3, 3))
     conn = np.zeros((8, 8), bool)
@@ -677,7 +679,7 @@ def elasticity3d_kuhn_jump_stencil(nx, ny, nz, cube_modulus, E=1e3, nu=0.15, cla
         cx, cy, cz = ix - ax, iy - ay, iz - az
         ok = (cx >= 0) & (cx <= nx - 2) & (cy >= 0) & (cy <= ny - 2) & (cz >= 0) & (cz <= nz - 2)
         rows = np.flatnonzero(ok)
-        Ec = cube_modulus(cx[rows], cy[rows], cz[rows])
+        Ec = cube_modulus(cx[rows] + origin[0], cy[rows] + origin[1], cz[rows] + origin[2])
         for b2, (bx, by, bz) in enumerate(corner):
             if not conn[a, b2]:
                 continue
@@ -691,7 +693,50 @@ def elasticity3d_kuhn_jump_stencil(nx, ny, nz, cube_modulus, E=1e3, nu=0.15, cla
     for tag in clamp:
         ax_ = "xyz".index(tag[0])
         free[coord[ax_] == (0 if tag[1] == "0" else dims[ax_] - 1)] = 0
-    X = np.stack([ix * hs, iy * hs, iz * hs], axis=1).astype(np.float64)
+    X = np.stack([(ix + origin[0]) * hs, (iy + origin[1]) * hs, (iz + origin[2]) * hs], axis=1).astype(np.float64)
     rhs = np.zeros((n, 3))
     rhs[:, 1] = (hs ** 3 / 24.0) * ntet_w * X[:, 0]
     return dict(n=n, b=3, rowptr=rowptr, col=col, val=val.reshape(-1), free=free, rhs=rhs.reshape(-1), xyz=X)
+
+
+def _box_halo(n, grid, rank):
+    """neighbours and shared-DOF lists of a sub-box of n^3 vertices in a grid = (px, py, pz) box partition (see box_poisson3d)"""
+    px, py, pz = grid
+    bx, by, bz = rank % px, (rank // px) % py, rank // (px * py)
+    peers, ex = [], []
+    sel = {-1: np.array([0]), 0: np.arange(n), 1: np.array([n - 1])}
+    for dz in (-1, 0, 1):
+        for dy in (-1, 0, 1):
+            for dx in (-1, 0, 1):
+                if dx == dy == dz == 0:
+                    continue
+                qx, qy, qz = bx + dx, by + dy, bz + dz
+                if not (0 <= qx < px and 0 <= qy < py and 0 <= qz < pz):
+                    continue
+                idx = (sel[dx][None, None, :] + n * (sel[dy][None, :, None] + n * sel[dz][:, None, None])).ravel()
+                peers.append(qx + px * (qy + py * qz))
+                ex.append(idx.astype(np.int32))
+    order = np.argsort(peers)
+    peers, ex = [peers[i] for i in order], [ex[i] for i in order]
+    ghost = np.zeros(n ** 3, bool)
+    for q, e in zip(peers, ex):
+        if q < rank:
+            ghost[e] = True
+    return peers, ex, int((~ghost).sum())
+
+
+def box_elasticity3d_jump(n, grid, rank, box_cells=8, contrast=1e4, E=1e3, nu=0.15):
+    """rank's local problem of BASELINE.json configs[4]: P1 elasticity on the cube of ((n-1)p+1)^3 vertices cut into grid = (px, py, pz)
+    sub-boxes of n^3 vertices, Young's modulus jumping by `contrast` on a GLOBAL checkerboard of box_cells^3-cell boxes, clamped at the
+    global face x = 0, body force (0, x, 0).  Sub-assembled local matrix (only the rank's own cubes), shared DOFs duplicated, halo
+    lists as box_poisson3d.  n = 128 on 2x2x2 ranks: 255^3 vertices = 49.7 M DOFs."""
+    px, py, pz = grid
+    bx, by, bz = rank % px, (rank // px) % py, rank // (px * py)
+    gd = ((n - 1) * px + 1, (n - 1) * py + 1, (n - 1) * pz + 1)
+    h = 1.0 / (max(gd) - 1)
+    origin = (bx * (n - 1), by * (n - 1), bz * (n - 1))
+    loc = elasticity3d_kuhn_jump_stencil(n, n, n, checkerboard_modulus(box_cells, contrast), E=E, nu=nu,
+                                         clamp=("x0",) if origin[0] == 0 else (), h=h, origin=origin)
+    loc["peers"], loc["ex"], loc["n_master"] = _box_halo(n, grid, rank)
+    loc["global_dims"] = gd
+    return loc

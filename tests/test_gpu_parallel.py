@@ -143,8 +143,14 @@ def test_parallel_tiled_sweeps_match_oracle(grid, rows, image):
     assert all(it == ito for it in _collective(pcs, solve))
 
 
-def test_parallel_elasticity_matches_oracle():
-    parts = S.partition_elasticity3d(9, 5, 9, 2)
+@pytest.mark.parametrize("problem", ["beam_2_slabs", "jump_2x2x2_boxes"])
+def test_parallel_elasticity_matches_oracle(problem):
+    """multi-rank elast_3d (3x3 / 6x6 blocks, hybrid smoothers) against the multi-rank oracle; the second case is the BASELINE configs[4]
+    workload in small: modulus jumping by 1e4 on a checkerboard, 2x2x2 sub-boxes (DOFs shared by up to 8 ranks), bench.py's generator"""
+    if problem == "beam_2_slabs":
+        parts = S.partition_elasticity3d(9, 5, 9, 2)
+    else:
+        parts = [S.box_elasticity3d_jump(4, (2, 2, 2), r, box_cells=2) for r in range(8)]
     pcs = _build_ranks(parts, par.elast_3d_par, 3, ngs_amg_max_coarse_size=10, ngs_amg_b200_ctr_nv=60)
     amg, npar = _oracle_for(parts, pcs, 3, pinv=True)
     assert npar >= 1

@@ -47,3 +47,38 @@ def test_jump_elasticity_stencil_equals_assembly():
     u = S.elasticity3d_kuhn_stencil(nx, ny, nz)
     c = S.elasticity3d_kuhn_jump_stencil(nx, ny, nz, lambda x, y, z: np.ones(len(x)))
     assert np.abs(u["val"] - c["val"]).max() < 1e-13 * np.abs(u["val"]).max() and np.allclose(u["rhs"], c["rhs"])
+
+
+def test_box_partition_of_the_jump_problem_sums_to_the_global_matrix():
+    """configs[4] on N ranks: the ranks' sub-assembled matrices (box_elasticity3d_jump) add up to the global jump problem, shared DOFs
+    are listed consistently on both sides, the loads add up, the clamp is the global face x = 0"""
+    import scipy.sparse as sp
+    n, grid = 4, (2, 1, 2)
+    px, py, pz = grid
+    gd = tuple((n - 1) * q + 1 for q in grid)
+    glob = S.elasticity3d_kuhn_jump_stencil(*gd, S.checkerboard_modulus(2, 1e4), h=1.0 / (max(gd) - 1))
+    N = glob["n"]
+    Ag = ng.SparseMatrix(N, N, 3, 3, glob["rowptr"], glob["col"], glob["val"]).to_scipy()
+    acc = sp.csr_matrix((3 * N, 3 * N))
+    rhs = np.zeros(3 * N)
+    parts = [S.box_elasticity3d_jump(n, grid, r, box_cells=2) for r in range(px * py * pz)]
+    gids = []
+    for r, p in enumerate(parts):
+        bx, by, bz = r % px, (r // px) % py, r // (px * py)
+        ids = np.arange(n ** 3)
+        gx, gy, gz = ids % n + bx * (n - 1), (ids // n) % n + by * (n - 1), ids // (n * n) + bz * (n - 1)
+        g = gx + gd[0] * (gy + gd[1] * gz)
+        gids.append(g)
+        dof = (3 * g[:, None] + np.arange(3)[None, :]).ravel()
+        Al = ng.SparseMatrix(p["n"], p["n"], 3, 3, p["rowptr"], p["col"], p["val"]).to_scipy().tocoo()
+        acc = acc + sp.csr_matrix((Al.data, (dof[Al.row], dof[Al.col])), shape=(3 * N, 3 * N))
+        rhs[dof] += p["rhs"]
+        assert np.allclose(p["xyz"], glob["xyz"][g])
+        assert np.array_equal(p["free"], glob["free"][g])
+    assert abs(acc - Ag).max() < 1e-12 * abs(Ag).max()
+    assert np.allclose(rhs, glob["rhs"])
+    for r, p in enumerate(parts):                         # k-th shared DOF with rank q here == k-th shared DOF with rank r on q
+        for q, e in zip(p["peers"], p["ex"]):
+            eq = parts[q]["ex"][parts[q]["peers"].index(r)]
+            assert np.array_equal(gids[r][e], gids[q][eq])
+    assert sum(p["n_master"] for p in parts) == N
