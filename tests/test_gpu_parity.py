@@ -299,6 +299,23 @@ def test_config1_size_properties():
     assert 1.0 < pc.GetOC()[0] < 2.0 and pc.GetOC()[1] == 1.0 and pc.GetOC()[-1] == 0.0   # [OC, OC_l0, ..., 0 for the exactly solved level]
 
 
+def test_deep_sweep_dag_on_the_production_kernels():
+    """101^3 = 1.03 M DOFs: a level-0 row DAG of 301 levels (round 1 never checked more than ~180 against the oracle while the bench runs
+    930) on the kernels the bench uses -- the tile-image sweep on level 0 (8x8x4 boxes), the per-colour PDL launches or the sync-free
+    row sweep on level 1, the row-major warp-per-row sweeps below -- V-cycle <= 1e-10 and identical PCG iteration count"""
+    p, A = poisson(101)
+    pc = ng.h1_scal(A, p["free"])
+    assert pc.SweepKind(0) == "tile_images" and pc.level_info(0).gs_depth < 100        # tile-DAG depth; the row DAG has 3 * 101 - 2 levels
+    assert any(pc.SweepKind(l) == "rows_rm" for l in range(1, pc.GetNLevels() - 1))
+    amg = O.OracleAMG(to_oracle(A), p["free"], [to_oracle(P) for P in pc.GetMap()])
+    b = rand(93, p["n"])
+    assert rel(pc * b, amg.apply(b)) < TOL_VCYCLE
+    cg = ng.CGSolver(mat=A, pre=pc, maxsteps=100, tol=1e-8)
+    cg.Solve(p["rhs"])
+    _, ito, _ = amg.pcg(p["rhs"], tol=1e-8, maxsteps=100)
+    assert cg.iterations == ito
+
+
 def test_elasticity_3d():
     """elast_3d: 3x3 fine blocks, 3x6 first prolongation, 6x6 coarse blocks (elasticity_pc_impl.hpp:668-685)"""
     p, A = elasticity(9, 4, 4)
