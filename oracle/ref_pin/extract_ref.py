@@ -205,11 +205,22 @@ def extract(root, name, rel, anchor, start, after):
         rel, s + 1, l1, body), (rel, s + 1, l1)
 
 
+# second, independent group (own library _ref/libngsamg_ref_bgs.so, own stand-in ngs_standin_bgs.hpp): the two update routines of the
+# block Gauss-Seidel smoother
+FRAGMENTS_BGS = [
+    ("bgs_richardson", "src/base/smoothers/loc_block_gssmoother_impl.hpp",
+     r"^\s*INLINE void BSmoother2<TM>::BSBlock :: RichardsonUpdate \(double omega, FlatVector<TV> smallsol, FlatVector<TV> bigsol,", "template", None),
+    ("bgs_richardson_res", "src/base/smoothers/loc_block_gssmoother_impl.hpp",
+     r"^\s*INLINE void BSmoother2<TM>::BSBlock :: RichardsonUpdate_RES \(double omega, FlatVector<TV> smallupdate, FlatVector<TV> bigsol,", "template", None),
+]
+
+
 def main():
     root, out = sys.argv[1], sys.argv[2]
+    group = sys.argv[3] if len(sys.argv) > 3 else "main"
     os.makedirs(out, exist_ok=True)
     index = []
-    for name, rel, anchor, start, after in FRAGMENTS:
+    for name, rel, anchor, start, after in (FRAGMENTS_BGS if group == "bgs" else FRAGMENTS):
         frag, where = extract(root, name, rel, anchor, start, after)
         with open(os.path.join(out, name + ".inc"), "w") as f:
             f.write(frag)

@@ -1,0 +1,120 @@
+// ngs_standin_bgs.hpp -- the handful of NGSolve container / expression features that the reference's block Gauss-Seidel update
+// routines use (BSmoother2<TM>::BSBlock::RichardsonUpdate / RichardsonUpdate_RES, loc_block_gssmoother_impl.hpp:244-268, 516-541),
+// written for this repository.  TEST INFRASTRUCTURE ONLY.  Independent of ngs_standin.hpp so that the main pin library is untouched.
+// Evaluation order of the dense expressions: every matrix-vector product is a plain row-wise sum over ascending column index
+// (with omega = 1 -- the only value the smoother passes -- scaling is exact, so the grouping of `omega * M * v` does not matter).
+#pragma once
+#include <cstddef>
+#include <ostream>
+#include <string>
+#include <tuple>
+#include <vector>
+
+#define INLINE inline
+using std::ostream;
+using std::string;
+using std::tuple;
+
+template <class T> struct T_Range {
+  T first, next;
+  struct It { T v; T operator*() const { return v; } It &operator++() { ++v; return *this; } bool operator!=(const It &o) const { return v != o.v; } };
+  It begin() const { return It{first}; }
+  It end() const { return It{next}; }
+};
+template <class T> struct FlatArray {
+  size_t n = 0;
+  T *d = nullptr;
+  FlatArray() = default;
+  FlatArray(size_t an, T *p) : n(an), d(p) {}
+  size_t Size() const { return n; }
+  T &operator[](size_t i) const { return d[i]; }
+  T *Data() const { return d; }
+};
+INLINE T_Range<int> Range(int a, int b) { return T_Range<int>{a, b}; }
+template <class T> INLINE T_Range<int> Range(const FlatArray<T> &a) { return T_Range<int>{0, (int)a.Size()}; }
+
+template <int N> struct Vec {
+  double v[N];
+  Vec() { for (int i = 0; i < N; i++) v[i] = 0.0; }
+  Vec(double s) { for (int i = 0; i < N; i++) v[i] = s; }
+  double &operator()(int i) { return v[i]; }
+  double operator()(int i) const { return v[i]; }
+  Vec &operator+=(const Vec &o) { for (int i = 0; i < N; i++) v[i] += o.v[i]; return *this; }
+  Vec &operator-=(const Vec &o) { for (int i = 0; i < N; i++) v[i] -= o.v[i]; return *this; }
+};
+template <int N> INLINE Vec<N> operator*(double s, const Vec<N> &a) { Vec<N> r; for (int i = 0; i < N; i++) r.v[i] = s * a.v[i]; return r; }
+template <int H, int W> struct Mat {
+  double v[H * W];
+  Mat() { for (int i = 0; i < H * W; i++) v[i] = 0.0; }
+  double &operator()(int i, int j) { return v[i * W + j]; }
+  double operator()(int i, int j) const { return v[i * W + j]; }
+};
+template <int H, int W> INLINE Vec<H> operator*(const Mat<H, W> &a, const Vec<W> &x) {
+  Vec<H> r;
+  for (int i = 0; i < H; i++) { double s = 0.0; for (int j = 0; j < W; j++) s += a(i, j) * x(j); r(i) = s; }
+  return r;
+}
+template <int H, int W> INLINE Mat<W, H> Trans(const Mat<H, W> &a) { Mat<W, H> r; for (int i = 0; i < H; i++) for (int j = 0; j < W; j++) r(j, i) = a(i, j); return r; }
+template <int H, int W> INLINE Mat<H, W> operator*(double s, const Mat<H, W> &a) { Mat<H, W> r; for (int i = 0; i < H * W; i++) r.v[i] = s * a.v[i]; return r; }
+INLINE double Trans(double a) { return a; }
+
+template <class TV> struct OwnedVec { std::vector<TV> d; };
+template <class TV> struct ScaledVecView { double s; const TV *d; size_t n; };
+template <class TV> class FlatVector;
+template <class TV> struct IndirectVec {
+  TV *d;
+  FlatArray<int> idx;
+  size_t Size() const { return idx.Size(); }
+  TV &operator()(size_t i) const { return d[idx[i]]; }
+  void operator+=(const ScaledVecView<TV> &e) const { for (size_t i = 0; i < idx.Size(); i++) d[idx[i]] += e.s * e.d[i]; }
+  void operator+=(const FlatVector<TV> &e) const;
+  void operator-=(const OwnedVec<TV> &e) const { for (size_t i = 0; i < idx.Size(); i++) d[idx[i]] -= e.d[i]; }
+};
+template <class TV> class FlatVector {
+  size_t n = 0;
+  TV *d = nullptr;
+
+public:
+  FlatVector() = default;
+  FlatVector(size_t an, TV *p) : n(an), d(p) {}
+  size_t Size() const { return n; }
+  TV *Data() const { return d; }
+  TV &operator()(size_t i) const { return d[i]; }
+  TV &operator[](size_t i) const { return d[i]; }
+  IndirectVec<TV> operator()(FlatArray<int> ind) const { return IndirectVec<TV>{d, ind}; }
+  const FlatVector &operator=(const OwnedVec<TV> &o) const { for (size_t i = 0; i < n; i++) d[i] = o.d[i]; return *this; }
+  const FlatVector &operator-=(const OwnedVec<TV> &o) const { for (size_t i = 0; i < n; i++) d[i] -= o.d[i]; return *this; }
+};
+template <class TV> void IndirectVec<TV>::operator+=(const FlatVector<TV> &e) const { for (size_t i = 0; i < idx.Size(); i++) d[idx[i]] += e(i); }
+template <class TV> INLINE ScaledVecView<TV> operator*(double s, const FlatVector<TV> &v) { return ScaledVecView<TV>{s, v.Data(), v.Size()}; }
+
+template <class TM> class FlatMatrix {
+  size_t h = 0, w = 0;
+  TM *d = nullptr;
+
+public:
+  FlatMatrix() = default;
+  FlatMatrix(size_t ah, size_t aw, TM *p) : h(ah), w(aw), d(p) {}
+  size_t Height() const { return h; }
+  size_t Width() const { return w; }
+  TM &operator()(size_t i, size_t j) const { return d[i * w + j]; }
+};
+template <class TM> struct ScaledMatView { double s; const FlatMatrix<TM> *m; };
+template <class TM> INLINE ScaledMatView<TM> operator*(double s, const FlatMatrix<TM> &m) { return ScaledMatView<TM>{s, &m}; }
+// y_i = sum_j A(i,j) x_j, ascending j, starting from A(i,0) x_0
+template <class TM, class TV, class X> INLINE OwnedVec<TV> matvec(double s, const FlatMatrix<TM> &A, const X &x) {
+  OwnedVec<TV> r;
+  r.d.resize(A.Height());
+  for (size_t i = 0; i < A.Height(); i++) {
+    TV acc = A(i, 0) * x(0);
+    for (size_t j = 1; j < A.Width(); j++) acc += A(i, j) * x(j);
+    r.d[i] = s * acc;
+  }
+  return r;
+}
+template <class TM, class TV> INLINE OwnedVec<TV> operator*(const FlatMatrix<TM> &A, const FlatVector<TV> &x) { return matvec<TM, TV>(1.0, A, x); }
+template <class TM, class TV> INLINE OwnedVec<TV> operator*(const FlatMatrix<TM> &A, const IndirectVec<TV> &x) { return matvec<TM, TV>(1.0, A, x); }
+template <class TM, class TV> INLINE OwnedVec<TV> operator*(const ScaledMatView<TM> &A, const FlatVector<TV> &x) { return matvec<TM, TV>(A.s, *A.m, x); }
+
+template <class TM> struct bgs_vec_of { using type = double; };
+template <int N> struct bgs_vec_of<Mat<N, N>> { using type = Vec<N>; };

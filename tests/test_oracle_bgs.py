@@ -85,3 +85,52 @@ def test_block_sweep_is_a_point_sweep_on_the_prescaled_matrix():
         for i in dofs:
             xs[i] = new[i]
     assert rel(x, xs) < 1e-12
+
+
+# ---- pin: the restated updates against the reference's OWN code (oracle/_ref/libngsamg_ref_bgs.so) --------------------------------------
+import pytest
+from oracle.ref_pin import ref_bgs as RB
+
+needs_ref = pytest.mark.skipif(not RB.available(), reason="oracle/_ref/libngsamg_ref_bgs.so not built (needs /root/reference)")
+
+
+def _blocks(n, free, size):
+    blk = np.where(np.asarray(free) > 0, np.arange(n) // size, -1)
+    ids = np.unique(blk[blk >= 0])
+    remap = -np.ones(int(blk.max()) + 2, np.int64)
+    remap[ids] = np.arange(len(ids))
+    return np.where(blk >= 0, remap[blk], -1)
+
+
+@needs_ref
+@pytest.mark.parametrize("problem", ["poisson", "elasticity"])
+def test_restated_updates_match_the_reference_code(problem):
+    """BSBlock::RichardsonUpdate and RichardsonUpdate_RES (loc_block_gssmoother_impl.hpp:244-268, 516-541), compiled verbatim, against
+    oracle_bgs.BlockGS: both forms, forward and backward block order, scalar and 3x3 blocks, blocks of several vertices; the two sides
+    share numpy's dense block inverses, so they differ by summation order only"""
+    from helpers import elasticity
+    if problem == "poisson":
+        p, A = poisson(6)
+        b = 1
+    else:
+        p, A = elasticity(5, 3, 4)
+        b = 3
+    n = p["n"]
+    As = A.to_scipy().tocsr()
+    blk = _blocks(n, p["free"], 5)
+    g = OB.BlockGS(As, b, blk)
+    x0, rhs = rand(7, n * b), rand(8, n * b)
+    for back in (False, True):
+        # RHS form
+        xo = x0.copy()
+        g.smooth_simple(xo, rhs, reverse=back)
+        xr, rr = x0.copy(), rhs.copy()
+        RB.sweep(A, blk, xr, rr, res_form=False, reverse=back)
+        assert rel(xo, xr) < 1e-13 and np.array_equal(rr, rhs)
+        # RES form
+        xo, ro = x0.copy(), rhs - As @ x0
+        g.smooth_res_simple(xo, ro, reverse=back)
+        xr, rr = x0.copy(), rhs - As @ x0
+        RB.sweep(A, blk, xr, rr, res_form=True, reverse=back)
+        assert rel(xo, xr) < 1e-13
+        assert np.linalg.norm(ro - rr) < 1e-13 * max(np.linalg.norm(rhs), np.linalg.norm(rhs - As @ x0))
