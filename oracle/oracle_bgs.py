@@ -7,11 +7,11 @@ Follows src/base/smoothers/loc_block_gssmoother_impl.hpp of /root/reference:
   * BSmoother2::SmoothWO           (:656-669)  res_updated && update_res -> SmoothRESSimple, else SmoothSimple (+ res = b - A x)
   * blocks: GetGSBlocks (src/base/precond/amg_pc_vertex_impl.hpp:1171-1269): block cv = { v : vmap[v] == cv }, ascending; vertices with
     vmap == -1 are in no block and are not smoothed.
-omega = 1 (SmoothSimple / SmoothRESSimple pass 1.0).  PIN: the two update routines are checked against the reference's OWN code -- cut out of
+omega = 1 (SmoothSimple / SmoothRESSimple pass 1.0).  PIN: the update routines, the block order and the flag protocol are checked against the
+reference's OWN code -- RichardsonUpdate, RichardsonUpdate_RES, IterateBlocks, SmoothWO, SmoothSimple, SmoothRESSimple cut out of
 /root/reference at build time and compiled against oracle/ref_pin/ngs_standin_bgs.hpp into oracle/_ref/libngsamg_ref_bgs.so
-(tests/test_oracle_bgs.py::test_restated_updates_match_the_reference_code: both forms, forward / backward, scalar and 3x3 blocks, <= 1e-13;
-both sides use numpy's dense block inverses).  Unpinned: the block set-up (SetFromSPMat, CalcInverse / pseudo-inverse of D_B), the
-SmoothWO flag protocol and the block order are restated from the source only."""
+(tests/test_oracle_bgs.py: every flag combination, forward / reverse, scalar and 3x3 blocks, <= 1e-13; both sides use numpy's dense block
+inverses).  Unpinned: the block set-up (SetFromSPMat: CalcInverse / pseudo-inverse of D_B) and GetGSBlocks are restated from the source only."""
 import numpy as np
 
 

@@ -212,6 +212,11 @@ FRAGMENTS_BGS = [
      r"^\s*INLINE void BSmoother2<TM>::BSBlock :: RichardsonUpdate \(double omega, FlatVector<TV> smallsol, FlatVector<TV> bigsol,", "template", None),
     ("bgs_richardson_res", "src/base/smoothers/loc_block_gssmoother_impl.hpp",
      r"^\s*INLINE void BSmoother2<TM>::BSBlock :: RichardsonUpdate_RES \(double omega, FlatVector<TV> smallupdate, FlatVector<TV> bigsol,", "template", None),
+    # block order and the smoother's flag protocol
+    ("bgs_iterate", "src/base/smoothers/loc_block_gssmoother_impl.hpp", r"^\s*INLINE void BSmoother2<TM> :: IterateBlocks \(FlatArray<int> groups, bool reverse, TLAM smooth_block\) const", "template", None),
+    ("bgs_smoothwo", "src/base/smoothers/loc_block_gssmoother_impl.hpp", r"^\s*INLINE void BSmoother2<TM> :: SmoothWO \(FlatArray<int> groups, BaseVector & x, const BaseVector & b,", "template", None),
+    ("bgs_smoothsimple", "src/base/smoothers/loc_block_gssmoother_impl.hpp", r"^\s*INLINE void BSmoother2<TM> :: SmoothSimple \(FlatArray<int> groups, BaseVector & x, const BaseVector & b, int steps, bool reverse, bool symm\) const", "template", None),
+    ("bgs_smoothressimple", "src/base/smoothers/loc_block_gssmoother_impl.hpp", r"^\s*INLINE void BSmoother2<TM> :: SmoothRESSimple \(FlatArray<int> groups, BaseVector & x, BaseVector & res, int steps, bool reverse, bool symm\) const", "template", None),
 ]
 
 

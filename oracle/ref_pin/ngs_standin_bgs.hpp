@@ -5,6 +5,7 @@
 // (with omega = 1 -- the only value the smoother passes -- scaling is exact, so the grouping of `omega * M * v` does not matter).
 #pragma once
 #include <cstddef>
+#include <cstdint>
 #include <ostream>
 #include <string>
 #include <tuple>
@@ -115,6 +116,48 @@ template <class TM, class TV, class X> INLINE OwnedVec<TV> matvec(double s, cons
 template <class TM, class TV> INLINE OwnedVec<TV> operator*(const FlatMatrix<TM> &A, const FlatVector<TV> &x) { return matvec<TM, TV>(1.0, A, x); }
 template <class TM, class TV> INLINE OwnedVec<TV> operator*(const FlatMatrix<TM> &A, const IndirectVec<TV> &x) { return matvec<TM, TV>(1.0, A, x); }
 template <class TM, class TV> INLINE OwnedVec<TV> operator*(const ScaledMatView<TM> &A, const FlatVector<TV> &x) { return matvec<TM, TV>(A.s, *A.m, x); }
+
+// VectorMem<N, T>: a vector with its own storage; Range(a, b) gives a view
+template <int N, class TV> class VectorMem {
+  std::vector<TV> d;
+
+public:
+  explicit VectorMem(size_t n) : d(n) {}
+  FlatVector<TV> Range(size_t a, size_t b) { return FlatVector<TV>(b - a, d.data() + a); }
+};
+template <class T> struct Array {
+  std::vector<T> d;
+  size_t Size() const { return d.size(); }
+  T &operator[](size_t i) { return d[i]; }
+  const T &operator[](size_t i) const { return d[i]; }
+};
+INLINE T_Range<int> Range(int n) { return T_Range<int>{0, n}; }
+INLINE T_Range<int> Range(size_t a, size_t b) { return T_Range<int>{(int)a, (int)b}; }
+
+// BaseVector / BaseMatrix: just enough for  x.FV<TV>()  and  res = b - A * x  (evaluated as a block-CSR SpMV; this is glue, not pinned)
+struct BgsCsr { int64_t n; int b; const int64_t *rp; const int32_t *ci; const double *v; };
+struct BaseVector;
+struct BgsMatVec { const BgsCsr *A; const BaseVector *x; };
+struct BgsResid { const BaseVector *b; BgsMatVec e; };
+struct BaseVector {
+  double *d;
+  size_t n;   // scalars
+  template <class TV> FlatVector<TV> FV() const { return FlatVector<TV>(n * sizeof(double) / sizeof(TV), reinterpret_cast<TV *>(d)); }
+  BaseVector &operator=(const BgsResid &r) {
+    const BgsCsr &A = *r.e.A;
+    const int b = A.b;
+    for (int64_t i = 0; i < A.n; i++)
+      for (int p = 0; p < b; p++) {
+        double s = r.b->d[i * b + p];
+        for (int64_t e = A.rp[i]; e < A.rp[i + 1]; e++)
+          for (int q = 0; q < b; q++) s -= A.v[e * b * b + p * b + q] * r.e.x->d[(int64_t)A.ci[e] * b + q];
+        d[i * b + p] = s;
+      }
+    return *this;
+  }
+};
+INLINE BgsMatVec operator*(const BgsCsr &A, const BaseVector &x) { return BgsMatVec{&A, &x}; }
+INLINE BgsResid operator-(const BaseVector &b, const BgsMatVec &e) { return BgsResid{&b, e}; }
 
 template <class TM> struct bgs_vec_of { using type = double; };
 template <int N> struct bgs_vec_of<Mat<N, N>> { using type = Vec<N>; };

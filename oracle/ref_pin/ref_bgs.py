@@ -32,6 +32,8 @@ def lib():
         i64, ci, vp = C.c_int64, C.c_int, C.c_void_p
         L.ref_bgs_sweep.argtypes = [i64, ci, vp, vp, vp, i64, vp, vp, vp, vp, vp, vp, ci, ci]
         L.ref_bgs_sweep.restype = ci
+        L.ref_bgs_smooth_wo.argtypes = [i64, ci, vp, vp, vp, i64, vp, vp, vp, vp, vp, vp, vp, ci, ci, ci, ci, ci, ci]
+        L.ref_bgs_smooth_wo.restype = ci
         _lib = L
     return _lib
 
@@ -46,6 +48,44 @@ def available():
             sys.stderr.write("[oracle/ref_pin] bgs reference library unavailable: %s\n" % e)
             _avail = False
     return _avail
+
+
+def _prepare(A, block_of):
+    import scipy.sparse as sp
+    n, b = int(A.nrows), int(A.bh)
+    block_of = np.asarray(block_of).astype(np.int64)
+    nb = int(block_of.max()) + 1 if n else 0
+    order = np.argsort(block_of, kind="stable")
+    order = order[block_of[order] >= 0]
+    bptr = np.zeros(nb + 1, np.int64)
+    np.add.at(bptr, block_of[order] + 1, 1)
+    bptr = np.cumsum(bptr)
+    bverts = order.astype(np.int32)
+    S = sp.bsr_matrix((np.asarray(A.val, dtype=np.float64).reshape(-1, b, b), np.asarray(A.col), np.asarray(A.rowptr)), shape=(n * b, n * b)).tocsr()
+    dinv, off = [], np.zeros(nb + 1, np.int64)
+    for k in range(nb):
+        verts = bverts[bptr[k]:bptr[k + 1]]
+        dofs = (verts[:, None].astype(np.int64) * b + np.arange(b)[None, :]).ravel()
+        D = S[dofs][:, dofs].toarray() if len(dofs) else np.zeros((0, 0))
+        Di = np.linalg.inv(D) if len(dofs) else D
+        dinv.append(Di.ravel())
+        off[k + 1] = off[k] + Di.size
+    dinv = np.ascontiguousarray(np.concatenate(dinv) if dinv else np.zeros(0))
+    return (n, b, np.ascontiguousarray(A.rowptr, dtype=np.int64), np.ascontiguousarray(A.col, dtype=np.int32),
+            np.ascontiguousarray(A.val, dtype=np.float64), nb, bptr, bverts, dinv, off)
+
+
+def smooth_wo(A, block_of, x, b, res, res_updated, update_res, x_zero, reverse=False, steps=1, symm=False):
+    """BSmoother2::SmoothWO (loc_block_gssmoother_impl.hpp:655-668) through the reference's own IterateBlocks / SmoothSimple / SmoothRESSimple /
+    RichardsonUpdate[_RES], all blocks in one group; x and res are updated in place"""
+    n, bs, rp, ci, av, nb, bptr, bverts, dinv, off = _prepare(A, block_of)
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+    b = np.ascontiguousarray(b, dtype=np.float64)
+    assert x.dtype == np.float64 and res.dtype == np.float64 and x.flags.c_contiguous and res.flags.c_contiguous
+    rc = lib().ref_bgs_smooth_wo(n, bs, p(rp), p(ci), p(av), nb, p(bptr), p(bverts), p(dinv), p(off), p(x), p(b), p(res), int(steps), int(res_updated),
+                                 int(update_res), int(x_zero), int(reverse), int(symm))
+    if rc != 0:
+        raise RuntimeError("ref_bgs_smooth_wo failed (%d)" % rc)
 
 
 def sweep(A, block_of, x, r, res_form, reverse=False):

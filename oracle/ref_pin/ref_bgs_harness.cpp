@@ -6,6 +6,7 @@
 // stores it (LU = false, md = false); the dense inverse is handed in by the caller, so both sides of the comparison use the same one.
 // Block order: IterateBlocks (:618-651) with one group -- ascending, or descending when `reverse`.  TEST INFRASTRUCTURE ONLY.
 #include <cstdint>
+#include <algorithm>
 #include <cstring>
 #include <vector>
 
@@ -25,10 +26,27 @@ public:
     FlatArray<TM> vals, mdadd;
     INLINE void RichardsonUpdate(double omega, FlatVector<TV> smallsol, FlatVector<TV> bigsol, FlatVector<TV> smallrhs, FlatVector<TV> bigrhs) const;
     INLINE void RichardsonUpdate_RES(double omega, FlatVector<TV> smallupdate, FlatVector<TV> bigsol, FlatVector<TV> smallres, FlatVector<TV> bigres) const;
+    INLINE void Prefetch() const {}     // cache hint only (loc_block_gssmoother_impl.hpp:222-240)
   };
+  // the members the cut-out methods below use (loc_block_gssmoother.hpp:78-99)
+  Array<BSBlock> blocks;
+  Array<size_t> fi_blocks;
+  size_t maxbs = 0;
+  BgsCsr A;
+  const BgsCsr *GetAMatrix() const { return &A; }
+  template <class TLAM> INLINE void IterateBlocks(FlatArray<int> groups, bool reverse, TLAM smooth_block) const;
+  INLINE void SmoothWO(FlatArray<int> groups, BaseVector &x, const BaseVector &b, BaseVector &res, int steps, bool res_updated, bool update_res,
+                       bool x_zero, bool reverse, bool symm) const;
+  INLINE void SmoothSimple(FlatArray<int> groups, BaseVector &x, const BaseVector &b, int steps, bool reverse, bool symm) const;
+  INLINE void SmoothRESSimple(FlatArray<int> groups, BaseVector &x, BaseVector &res, int steps, bool reverse, bool symm) const;
 };
+#define LAMBDA_INLINE
 #include "../_ref/frag_bgs/bgs_richardson.inc"
 #include "../_ref/frag_bgs/bgs_richardson_res.inc"
+#include "../_ref/frag_bgs/bgs_iterate.inc"
+#include "../_ref/frag_bgs/bgs_smoothsimple.inc"
+#include "../_ref/frag_bgs/bgs_smoothressimple.inc"
+#include "../_ref/frag_bgs/bgs_smoothwo.inc"
 }  // namespace amg
 
 namespace {
@@ -90,7 +108,77 @@ int sweep(int64_t n, int b, const int64_t *rp, const int32_t *ci, const double *
 }
 }  // namespace
 
+namespace {
+// BSmoother2::SmoothWO (loc_block_gssmoother_impl.hpp:655-668) with the reference's own IterateBlocks / SmoothSimple / SmoothRESSimple:
+// all blocks in ONE group (the serial smoother), `steps` sweeps, optional symmetric sweeps
+template <class TM>
+int smooth_wo(int64_t n, int b, const int64_t *rp, const int32_t *ci, const double *av, int64_t nblocks, const int64_t *bptr, const int32_t *bverts,
+              const double *dinv, const int64_t *dinv_off, double *x, const double *rhs, double *res, int steps, int res_updated, int update_res, int x_zero,
+              int reverse, int symm)
+{
+  using S = amg::BSmoother2<TM>;
+  S sm;
+  sm.A = BgsCsr{n, b, rp, ci, av};
+  std::vector<int32_t> blk_of(n, -1), pos_in(n, -1);
+  for (int64_t k = 0; k < nblocks; k++)
+    for (int64_t q = bptr[k]; q < bptr[k + 1]; q++) { blk_of[bverts[q]] = (int32_t)k; pos_in[bverts[q]] = (int32_t)(q - bptr[k]); }
+  std::vector<TM> A(rp[n]);
+  for (int64_t e = 0; e < rp[n]; e++) set_block<TM>(A[e], av + e * b * b, b);
+  struct Store { std::vector<int> dofnrs, firsti, cols; std::vector<TM> vals, diag, dinvm; };
+  std::vector<Store> st(nblocks);
+  sm.blocks.d.resize(nblocks);
+  for (int64_t k = 0; k < nblocks; k++) {
+    const int m = (int)(bptr[k + 1] - bptr[k]);
+    Store &s = st[k];
+    s.dofnrs.resize(m); s.firsti.assign(m + 1, 0); s.diag.resize((size_t)m * m); s.dinvm.resize((size_t)m * m);
+    for (int q = 0; q < m; q++) {
+      const int v = bverts[bptr[k] + q];
+      s.dofnrs[q] = v;
+      for (int64_t e = rp[v]; e < rp[v + 1]; e++) {
+        if (blk_of[ci[e]] == (int32_t)k) s.diag[(size_t)q * m + pos_in[ci[e]]] = A[e];
+        else { s.cols.push_back(ci[e]); s.vals.push_back(A[e]); }
+      }
+      s.firsti[q + 1] = (int)s.cols.size();
+    }
+    const double *di = dinv + dinv_off[k];
+    for (int qi = 0; qi < m; qi++)
+      for (int qj = 0; qj < m; qj++) {
+        double blk[36];
+        for (int p = 0; p < b; p++) for (int q2 = 0; q2 < b; q2++) blk[p * b + q2] = di[(size_t)(qi * b + p) * (m * b) + qj * b + q2];
+        set_block<TM>(s.dinvm[(size_t)qi * m + qj], blk, b);
+      }
+    auto &B = sm.blocks[k];
+    B.dofnrs = FlatArray<int>(m, s.dofnrs.data());
+    B.firsti = FlatArray<int>(m + 1, s.firsti.data());
+    B.cols = FlatArray<int>(s.cols.size(), s.cols.data());
+    B.vals = FlatArray<TM>(s.vals.size(), s.vals.data());
+    B.diag = FlatMatrix<TM>(m, m, s.diag.data());
+    B.diag_inv = FlatMatrix<TM>(m, m, s.dinvm.data());
+    sm.maxbs = std::max<size_t>(sm.maxbs, (size_t)m);
+  }
+  sm.fi_blocks.d = {0, (size_t)nblocks};
+  int group0 = 0;
+  BaseVector vx{x, (size_t)n * b}, vb{const_cast<double *>(rhs), (size_t)n * b}, vr{res, (size_t)n * b};
+  sm.SmoothWO(FlatArray<int>(1, &group0), vx, vb, vr, steps, res_updated != 0, update_res != 0, x_zero != 0, reverse != 0, symm != 0);
+  return 0;
+}
+}  // namespace
+
 extern "C" {
+int ref_bgs_smooth_wo(int64_t n, int b, const int64_t *rp, const int32_t *ci, const double *av, int64_t nblocks, const int64_t *bptr, const int32_t *bverts,
+                      const double *dinv, const int64_t *dinv_off, double *x, const double *rhs, double *res, int steps, int res_updated, int update_res,
+                      int x_zero, int reverse, int symm)
+{
+  try {
+    switch (b) {
+      case 1: return smooth_wo<double>(n, b, rp, ci, av, nblocks, bptr, bverts, dinv, dinv_off, x, rhs, res, steps, res_updated, update_res, x_zero, reverse, symm);
+      case 2: return smooth_wo<Mat<2, 2>>(n, b, rp, ci, av, nblocks, bptr, bverts, dinv, dinv_off, x, rhs, res, steps, res_updated, update_res, x_zero, reverse, symm);
+      case 3: return smooth_wo<Mat<3, 3>>(n, b, rp, ci, av, nblocks, bptr, bverts, dinv, dinv_off, x, rhs, res, steps, res_updated, update_res, x_zero, reverse, symm);
+      case 6: return smooth_wo<Mat<6, 6>>(n, b, rp, ci, av, nblocks, bptr, bverts, dinv, dinv_off, x, rhs, res, steps, res_updated, update_res, x_zero, reverse, symm);
+      default: return 2;
+    }
+  } catch (...) { return 1; }
+}
 // A: block CSR (n block rows, b x b blocks, row-major); blocks: bptr / bverts (vertices ascending per block); dinv: per block the dense
 // (m b) x (m b) inverse, row-major, at dinv_off[k].  x and r (= rhs for mode 0, residual for mode 1) are updated in place.
 int ref_bgs_sweep(int64_t n, int b, const int64_t *rp, const int32_t *ci, const double *av, int64_t nblocks, const int64_t *bptr, const int32_t *bverts,

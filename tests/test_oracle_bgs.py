@@ -134,3 +134,36 @@ def test_restated_updates_match_the_reference_code(problem):
         RB.sweep(A, blk, xr, rr, res_form=True, reverse=back)
         assert rel(xo, xr) < 1e-13
         assert np.linalg.norm(ro - rr) < 1e-13 * max(np.linalg.norm(rhs), np.linalg.norm(rhs - As @ x0))
+
+
+@needs_ref
+@pytest.mark.parametrize("problem", ["poisson", "elasticity"])
+def test_smoother_protocol_and_block_order_match_the_reference_code(problem):
+    """BSmoother2::SmoothWO with the reference's own IterateBlocks / SmoothSimple / SmoothRESSimple (loc_block_gssmoother_impl.hpp:617-706),
+    compiled verbatim: every (res_updated, update_res) combination, forward and reverse block order, against oracle_bgs.BlockGS.smooth"""
+    from helpers import elasticity
+    if problem == "poisson":
+        p, A = poisson(6)
+        b = 1
+    else:
+        p, A = elasticity(5, 3, 4)
+        b = 3
+    n = p["n"]
+    As = A.to_scipy().tocsr()
+    blk = _blocks(n, p["free"], 4)
+    g = OB.BlockGS(As, b, blk)
+    x0, rhs = rand(9, n * b), rand(10, n * b)
+    scale = max(np.linalg.norm(rhs), np.linalg.norm(rhs - As @ x0))
+    for back in (False, True):
+        for ru in (False, True):
+            for ur in (False, True):
+                r0 = rhs - As @ x0 if ru else rand(11, n * b)
+                xo, ro = x0.copy(), r0.copy()
+                g.smooth(xo, rhs, ro, ru, ur, False, back)
+                xr, rr = x0.copy(), r0.copy()
+                RB.smooth_wo(A, blk, xr, rhs, rr, ru, ur, False, reverse=back)
+                assert rel(xo, xr) < 1e-13, (back, ru, ur)
+                if ur:
+                    assert np.linalg.norm(ro - rr) < 1e-13 * scale, (back, ru, ur)
+                else:
+                    assert np.array_equal(rr, r0)      # res is left alone when no update was asked for
