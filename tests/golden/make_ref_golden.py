@@ -141,7 +141,39 @@ def make_dense():
     print("refpin_dense: %d pinv cases, %d regularisation cases, %d transport blocks" % (k, len(regs), len(ts)))
 
 
+def make_bgs():
+    """block Gauss-Seidel: inputs and outputs of the reference's own SmoothWO (oracle/_ref/libngsamg_ref_bgs.so) for every flag combination,
+    forward and reverse block order, scalar and 3x3 blocks"""
+    from helpers import elasticity, poisson, rand
+    from oracle.ref_pin import ref_bgs as RB
+    out = {}
+    for tag, (p, A), b in (("h1", poisson(5), 1), ("el", elasticity(4, 3, 3), 3)):
+        n = p["n"]
+        blk = np.where(np.asarray(p["free"]) > 0, np.arange(n) // 3, -1)
+        ids = np.unique(blk[blk >= 0])
+        remap = -np.ones(int(blk.max()) + 2, np.int64)
+        remap[ids] = np.arange(len(ids))
+        blk = np.where(blk >= 0, remap[blk], -1)
+        As = A.to_scipy().tocsr()
+        x0, rhs = rand(31, n * b), rand(32, n * b)
+        out[tag + "_rowptr"], out[tag + "_col"], out[tag + "_val"], out[tag + "_b"] = A.rowptr, A.col, A.val, np.int64(b)
+        out[tag + "_blk"], out[tag + "_x0"], out[tag + "_rhs"] = blk, x0, rhs
+        for back in (0, 1):
+            for ru in (0, 1):
+                for ur in (0, 1):
+                    r0 = rhs - As @ x0 if ru else rand(33, n * b)
+                    x, r = x0.copy(), r0.copy()
+                    RB.smooth_wo(A, blk, x, rhs, r, ru, ur, False, reverse=bool(back))
+                    key = "%s_%d%d%d" % (tag, back, ru, ur)
+                    out[key + "_r0"], out[key + "_x"], out[key + "_r"] = r0, x, r
+    np.savez_compressed(os.path.join(HERE, "refpin_bgs.npz"), **out)
+    print("refpin_bgs.npz written")
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "bgs":
+        make_bgs()
+        sys.exit(0)
     p, A = poisson(7)
     make("refpin_poisson_n7", p, A, False, 1, False, max_coarse=20)
     make("refpin_poisson_n7_symm2", p, A, False, 2, True, max_coarse=20)
@@ -149,3 +181,4 @@ if __name__ == "__main__":
     make("refpin_elast_5x3x3", p, A, True, 1, False, max_coarse=4, max_per_row=4)
     make_hybrid()
     make_dense()
+    make_bgs()

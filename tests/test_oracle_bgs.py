@@ -167,3 +167,27 @@ def test_smoother_protocol_and_block_order_match_the_reference_code(problem):
                     assert np.linalg.norm(ro - rr) < 1e-13 * scale, (back, ru, ur)
                 else:
                     assert np.array_equal(rr, r0)      # res is left alone when no update was asked for
+
+
+@pytest.mark.parametrize("tag", ["h1", "el"])
+def test_oracle_against_the_reference_made_fixture(tag):
+    """tests/golden/refpin_bgs.npz (written by tests/golden/make_ref_golden.py from the reference's own SmoothWO): the oracle reproduces
+    every stored smoother call -- runs on machines without the pin library"""
+    import os
+    import scipy.sparse as sp
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "refpin_bgs.npz"))
+    b = int(g[tag + "_b"])
+    rp, ci, val = g[tag + "_rowptr"], g[tag + "_col"], g[tag + "_val"]
+    n = len(rp) - 1
+    As = sp.bsr_matrix((val.reshape(-1, b, b), ci, rp), shape=(n * b, n * b)).tocsr()
+    sm = OB.BlockGS(As, b, g[tag + "_blk"])
+    x0, rhs = g[tag + "_x0"], g[tag + "_rhs"]
+    scale = max(np.linalg.norm(rhs), np.linalg.norm(rhs - As @ x0))
+    for back in (0, 1):
+        for ru in (0, 1):
+            for ur in (0, 1):
+                key = "%s_%d%d%d" % (tag, back, ru, ur)
+                x, r = x0.copy(), g[key + "_r0"].copy()
+                sm.smooth(x, rhs, r, bool(ru), bool(ur), False, bool(back))
+                assert rel(x, g[key + "_x"]) < 1e-13, key
+                assert np.linalg.norm(r - g[key + "_r"]) < 1e-13 * scale, key
