@@ -33,6 +33,16 @@ def main():
     assert abs(got["G"].to_scipy() - HL.G[rank]).max() == 0
     assert np.allclose(got["mod_diag"], HL.md[rank].ravel(), rtol=1e-13, atol=0)
     assert (got["master"].astype(bool) == HL.master[rank]).all()
+    # the BASELINE configs[4] workload in small (3x3 blocks, modulus jumping by 1e4 on a checkerboard): bench.py's box generator
+    q = S.box_elasticity3d_jump(4, grid, rank, box_cells=2)
+    Aq = ng.SparseMatrix(q["n"], q["n"], 3, 3, q["rowptr"], q["col"], q["val"])
+    gq = par.hybrid_host(Aq, par.Halo(q["peers"], q["ex"]), comm, q["free"])
+    qs = [S.box_elasticity3d_jump(4, grid, r, box_cells=2) for r in range(size)]
+    HQ = OP.HybridLevel([O.Bsr(t["n"], t["n"], 3, 3, t["rowptr"], t["col"], t["val"]) for t in qs], [t["free"] for t in qs],
+                        [t["peers"] for t in qs], [t["ex"] for t in qs])
+    assert abs(gq["M"].to_scipy() - HQ.M[rank]).max() < 1e-9 * abs(HQ.M[rank]).max()
+    assert abs(gq["G"].to_scipy() - HQ.G[rank]).max() == 0
+    assert np.allclose(gq["mod_diag"], HQ.md[rank].ravel(), rtol=1e-12, atol=0)
     # all-reduce callback
     v = np.array([rank + 1.0, 2.0])
     assert np.allclose(comm._allreduce(v), [size * (size + 1) / 2, 2.0 * size])
