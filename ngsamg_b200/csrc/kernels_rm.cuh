@@ -123,8 +123,9 @@ __global__ void __launch_bounds__(RM_THREADS) k_gs_tri_rm(RmView T, const double
       }
     }
     if (B > 1 && prm.gate_all) {
-      // (small levels only; a bandwidth-bound level loses with the extra requests)  block values are loaded at use (36 doubles per entry do not fit the stage): pull the row's lines into L2 now, so that the loads
-      // behind the polls are L2 hits instead of DRAM misses on the critical path
+      // block values are loaded at use (36 doubles per entry do not fit the stage): on the latency-bound (small) levels pull the row's
+      // lines into L2 now, so that the loads behind the polls are L2 hits instead of DRAM misses on the critical path (a bandwidth-bound
+      // level loses with the extra requests: the host sets the flag below tri_rm_max_rows only)
       const char *vb = (const char *)(T.val + p0 * BS);
       const i64 nbytes = (p1 - p0) * (i64)(BS * 8);
       for (i64 o = (i64)lane * 128; o < nbytes; o += 32 * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(vb + o));
