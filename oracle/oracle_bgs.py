@@ -11,7 +11,8 @@ omega = 1 (SmoothSimple / SmoothRESSimple pass 1.0).  PIN: the update routines, 
 reference's OWN code -- RichardsonUpdate, RichardsonUpdate_RES, IterateBlocks, SmoothWO, SmoothSimple, SmoothRESSimple cut out of
 /root/reference at build time and compiled against oracle/ref_pin/ngs_standin_bgs.hpp into oracle/_ref/libngsamg_ref_bgs.so
 (tests/test_oracle_bgs.py: every flag combination, forward / reverse, scalar and 3x3 blocks, <= 1e-13; both sides use numpy's dense block
-inverses).  Unpinned: the block set-up (SetFromSPMat: CalcInverse / pseudo-inverse of D_B) and GetGSBlocks are restated from the source only."""
+inverses), and so is the block set-up BSBlock::SetFromSPMat (sorted dofnrs, off-block rows, D_B; its CalcInverse is NGSolve's and replaced by a
+Gauss-Jordan in the stand-in: 1e-11).  Unpinned: GetGSBlocks (a six-line grouping of the vertices by coarse vertex) and the pseudo-inverse variant."""
 import numpy as np
 
 

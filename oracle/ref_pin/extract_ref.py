@@ -212,6 +212,9 @@ FRAGMENTS_BGS = [
      r"^\s*INLINE void BSmoother2<TM>::BSBlock :: RichardsonUpdate \(double omega, FlatVector<TV> smallsol, FlatVector<TV> bigsol,", "template", None),
     ("bgs_richardson_res", "src/base/smoothers/loc_block_gssmoother_impl.hpp",
      r"^\s*INLINE void BSmoother2<TM>::BSBlock :: RichardsonUpdate_RES \(double omega, FlatVector<TV> smallupdate, FlatVector<TV> bigsol,", "template", None),
+    # block set-up: off-block rows, dense diagonal block and its inverse
+    ("bgs_setfromspmat", "src/base/smoothers/loc_block_gssmoother_impl.hpp",
+     r"^\s*INLINE void BSmoother2<TM>::BSBlock :: SetFromSPMat \(const SparseMatrixTM<TM> & A, FlatArray<int> dofs, LocalHeap & lh, bool pinv,", "template", None),
     # block order and the smoother's flag protocol
     ("bgs_iterate", "src/base/smoothers/loc_block_gssmoother_impl.hpp", r"^\s*INLINE void BSmoother2<TM> :: IterateBlocks \(FlatArray<int> groups, bool reverse, TLAM smooth_block\) const", "template", None),
     ("bgs_smoothwo", "src/base/smoothers/loc_block_gssmoother_impl.hpp", r"^\s*INLINE void BSmoother2<TM> :: SmoothWO \(FlatArray<int> groups, BaseVector & x, const BaseVector & b,", "template", None),

@@ -4,6 +4,8 @@
 // Evaluation order of the dense expressions: every matrix-vector product is a plain row-wise sum over ascending column index
 // (with omega = 1 -- the only value the smoother passes -- scaling is exact, so the grouping of `omega * M * v` does not matter).
 #pragma once
+#include <algorithm>
+#include <cmath>
 #include <cstddef>
 #include <cstdint>
 #include <ostream>
@@ -22,14 +24,21 @@ template <class T> struct T_Range {
   It begin() const { return It{first}; }
   It end() const { return It{next}; }
 };
+// NGSolve semantics: operator= copies the ELEMENTS (or fills with a scalar), Assign re-seats the view
 template <class T> struct FlatArray {
   size_t n = 0;
   T *d = nullptr;
   FlatArray() = default;
   FlatArray(size_t an, T *p) : n(an), d(p) {}
+  FlatArray(const FlatArray &) = default;
   size_t Size() const { return n; }
   T &operator[](size_t i) const { return d[i]; }
   T *Data() const { return d; }
+  void Assign(const FlatArray &o) { n = o.n; d = o.d; }
+  const FlatArray &operator=(const FlatArray &o) const { for (size_t i = 0; i < n; i++) d[i] = o.d[i]; return *this; }
+  const FlatArray &operator=(const T &s) const { for (size_t i = 0; i < n; i++) d[i] = s; return *this; }
+  T *begin() const { return d; }
+  T *end() const { return d + n; }
 };
 INLINE T_Range<int> Range(int a, int b) { return T_Range<int>{a, b}; }
 template <class T> INLINE T_Range<int> Range(const FlatArray<T> &a) { return T_Range<int>{0, (int)a.Size()}; }
@@ -47,6 +56,7 @@ template <int N> INLINE Vec<N> operator*(double s, const Vec<N> &a) { Vec<N> r; 
 template <int H, int W> struct Mat {
   double v[H * W];
   Mat() { for (int i = 0; i < H * W; i++) v[i] = 0.0; }
+  Mat(double s) { for (int i = 0; i < H * W; i++) v[i] = s; }
   double &operator()(int i, int j) { return v[i * W + j]; }
   double operator()(int i, int j) const { return v[i * W + j]; }
 };
@@ -56,6 +66,7 @@ template <int H, int W> INLINE Vec<H> operator*(const Mat<H, W> &a, const Vec<W>
   return r;
 }
 template <int H, int W> INLINE Mat<W, H> Trans(const Mat<H, W> &a) { Mat<W, H> r; for (int i = 0; i < H; i++) for (int j = 0; j < W; j++) r(j, i) = a(i, j); return r; }
+template <int H, int W> INLINE Mat<H, W> operator-(const Mat<H, W> &a, const Mat<H, W> &b) { Mat<H, W> r; for (int i = 0; i < H * W; i++) r.v[i] = a.v[i] - b.v[i]; return r; }
 template <int H, int W> INLINE Mat<H, W> operator*(double s, const Mat<H, W> &a) { Mat<H, W> r; for (int i = 0; i < H * W; i++) r.v[i] = s * a.v[i]; return r; }
 INLINE double Trans(double a) { return a; }
 
@@ -99,6 +110,9 @@ public:
   size_t Height() const { return h; }
   size_t Width() const { return w; }
   TM &operator()(size_t i, size_t j) const { return d[i * w + j]; }
+  void AssignMemory(size_t ah, size_t aw, TM *p) { h = ah; w = aw; d = p; }
+  const FlatMatrix &operator=(const FlatMatrix &o) const { for (size_t i = 0; i < h * w; i++) d[i] = o.d[i]; return *this; }
+  const FlatMatrix &operator=(double s) const { for (size_t i = 0; i < h * w; i++) d[i] = TM(s); return *this; }
 };
 template <class TM> struct ScaledMatView { double s; const FlatMatrix<TM> *m; };
 template <class TM> INLINE ScaledMatView<TM> operator*(double s, const FlatMatrix<TM> &m) { return ScaledMatView<TM>{s, &m}; }
@@ -158,6 +172,56 @@ struct BaseVector {
 };
 INLINE BgsMatVec operator*(const BgsCsr &A, const BaseVector &x) { return BgsMatVec{&A, &x}; }
 INLINE BgsResid operator-(const BaseVector &b, const BgsMatVec &e) { return BgsResid{&b, e}; }
+
+// what BSBlock::SetFromSPMat needs: row access of a sparse matrix with TM entries, find_in_sorted_array, QuickSort, LocalHeap / HeapReset,
+// CalcInverse of a matrix of TM blocks (NGSolve's own routine is third-party: here a Gauss-Jordan on the scalar matrix, partial pivoting)
+template <class TM> struct SparseMatrixTM {
+  int64_t n;
+  const int64_t *rp;
+  const int32_t *ci;
+  std::vector<int> cols;      // int copy of the column indices
+  std::vector<TM> vals;
+  FlatArray<int> GetRowIndices(int i) const { return FlatArray<int>(rp[i + 1] - rp[i], const_cast<int *>(cols.data()) + rp[i]); }
+  FlatVector<TM> GetRowValues(int i) const { return FlatVector<TM>(rp[i + 1] - rp[i], const_cast<TM *>(vals.data()) + rp[i]); }
+};
+template <class T> INLINE T_Range<int> Range(const FlatVector<T> &a) { return T_Range<int>{0, (int)a.Size()}; }
+INLINE int find_in_sorted_array(int x, FlatArray<int> a) {
+  size_t lo = 0, hi = a.Size();
+  while (lo < hi) { const size_t mid = (lo + hi) / 2; if (a[mid] < x) lo = mid + 1; else hi = mid; }
+  return (lo < a.Size() && a[lo] == x) ? (int)lo : -1;
+}
+INLINE void QuickSort(FlatArray<int> a) { std::sort(a.begin(), a.end()); }     // distinct keys: every correct sort gives the same array
+struct LocalHeap {};
+struct HeapReset { explicit HeapReset(LocalHeap &) {} };
+template <class TM> struct bgs_block_dim { static constexpr int value = 1; };
+template <int N> struct bgs_block_dim<Mat<N, N>> { static constexpr int value = N; };
+INLINE double &bgs_entry(double &m, int, int) { return m; }
+template <int N> INLINE double &bgs_entry(Mat<N, N> &m, int p, int q) { return m(p, q); }
+template <class TM> INLINE void CalcInverse(const FlatMatrix<TM> &M) {
+  constexpr int B = bgs_block_dim<TM>::value;
+  const int m = (int)M.Height(), N = m * B;
+  std::vector<double> a((size_t)N * N), inv((size_t)N * N, 0.0);
+  for (int i = 0; i < m; i++) for (int j = 0; j < m; j++) for (int p = 0; p < B; p++) for (int q = 0; q < B; q++)
+    a[(size_t)(i * B + p) * N + j * B + q] = bgs_entry(M(i, j), p, q);
+  for (int i = 0; i < N; i++) inv[(size_t)i * N + i] = 1.0;
+  for (int c = 0; c < N; c++) {
+    int piv = c;
+    for (int r = c + 1; r < N; r++) if (std::fabs(a[(size_t)r * N + c]) > std::fabs(a[(size_t)piv * N + c])) piv = r;
+    if (a[(size_t)piv * N + c] == 0.0) throw 1;
+    if (piv != c) for (int q = 0; q < N; q++) { std::swap(a[(size_t)c * N + q], a[(size_t)piv * N + q]); std::swap(inv[(size_t)c * N + q], inv[(size_t)piv * N + q]); }
+    const double f = 1.0 / a[(size_t)c * N + c];
+    for (int q = 0; q < N; q++) { a[(size_t)c * N + q] *= f; inv[(size_t)c * N + q] *= f; }
+    for (int r = 0; r < N; r++) {
+      if (r == c) continue;
+      const double g = a[(size_t)r * N + c];
+      if (g == 0.0) continue;
+      for (int q = 0; q < N; q++) { a[(size_t)r * N + q] -= g * a[(size_t)c * N + q]; inv[(size_t)r * N + q] -= g * inv[(size_t)c * N + q]; }
+    }
+  }
+  for (int i = 0; i < m; i++) for (int j = 0; j < m; j++) for (int p = 0; p < B; p++) for (int q = 0; q < B; q++)
+    bgs_entry(M(i, j), p, q) = inv[(size_t)(i * B + p) * N + j * B + q];
+}
+template <class TM> INLINE void CalcPseudoInverseTryNormal(const FlatMatrix<TM> &, LocalHeap &) { throw 2; }   // pinv blocks are not part of this pin
 
 template <class TM> struct bgs_vec_of { using type = double; };
 template <int N> struct bgs_vec_of<Mat<N, N>> { using type = Vec<N>; };

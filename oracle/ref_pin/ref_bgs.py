@@ -75,14 +75,20 @@ def _prepare(A, block_of):
             np.ascontiguousarray(A.val, dtype=np.float64), nb, bptr, bverts, dinv, off)
 
 
-def smooth_wo(A, block_of, x, b, res, res_updated, update_res, x_zero, reverse=False, steps=1, symm=False):
+def smooth_wo(A, block_of, x, b, res, res_updated, update_res, x_zero, reverse=False, steps=1, symm=False, ref_setup=False):
     """BSmoother2::SmoothWO (loc_block_gssmoother_impl.hpp:655-668) through the reference's own IterateBlocks / SmoothSimple / SmoothRESSimple /
-    RichardsonUpdate[_RES], all blocks in one group; x and res are updated in place"""
+    RichardsonUpdate[_RES], all blocks in one group; x and res are updated in place.
+    ref_setup: the blocks are built by the reference's own BSBlock::SetFromSPMat (:67-132, dense inverse by the stand-in's Gauss-Jordan)
+    instead of being laid out by the harness with numpy's inverses."""
     n, bs, rp, ci, av, nb, bptr, bverts, dinv, off = _prepare(A, block_of)
     p = lambda a: a.ctypes.data_as(C.c_void_p)
+    if ref_setup:
+        p_dinv = None
+    else:
+        p_dinv = p(dinv)
     b = np.ascontiguousarray(b, dtype=np.float64)
     assert x.dtype == np.float64 and res.dtype == np.float64 and x.flags.c_contiguous and res.flags.c_contiguous
-    rc = lib().ref_bgs_smooth_wo(n, bs, p(rp), p(ci), p(av), nb, p(bptr), p(bverts), p(dinv), p(off), p(x), p(b), p(res), int(steps), int(res_updated),
+    rc = lib().ref_bgs_smooth_wo(n, bs, p(rp), p(ci), p(av), nb, p(bptr), p(bverts), p_dinv, p(off), p(x), p(b), p(res), int(steps), int(res_updated),
                                  int(update_res), int(x_zero), int(reverse), int(symm))
     if rc != 0:
         raise RuntimeError("ref_bgs_smooth_wo failed (%d)" % rc)

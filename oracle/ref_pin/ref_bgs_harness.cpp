@@ -27,6 +27,7 @@ public:
     INLINE void RichardsonUpdate(double omega, FlatVector<TV> smallsol, FlatVector<TV> bigsol, FlatVector<TV> smallrhs, FlatVector<TV> bigrhs) const;
     INLINE void RichardsonUpdate_RES(double omega, FlatVector<TV> smallupdate, FlatVector<TV> bigsol, FlatVector<TV> smallres, FlatVector<TV> bigres) const;
     INLINE void Prefetch() const {}     // cache hint only (loc_block_gssmoother_impl.hpp:222-240)
+    INLINE void SetFromSPMat(const SparseMatrixTM<TM> &A, FlatArray<int> dofs, LocalHeap &lh, bool pinv, FlatArray<TM> md);
   };
   // the members the cut-out methods below use (loc_block_gssmoother.hpp:78-99)
   Array<BSBlock> blocks;
@@ -43,6 +44,7 @@ public:
 #define LAMBDA_INLINE
 #include "../_ref/frag_bgs/bgs_richardson.inc"
 #include "../_ref/frag_bgs/bgs_richardson_res.inc"
+#include "../_ref/frag_bgs/bgs_setfromspmat.inc"
 #include "../_ref/frag_bgs/bgs_iterate.inc"
 #include "../_ref/frag_bgs/bgs_smoothsimple.inc"
 #include "../_ref/frag_bgs/bgs_smoothressimple.inc"
@@ -93,12 +95,12 @@ int sweep(int64_t n, int b, const int64_t *rp, const int32_t *ci, const double *
         set_block<TM>(dinvm[(size_t)qi * m + qj], blk, b);
       }
     typename S::BSBlock B;
-    B.dofnrs = FlatArray<int>(m, dofnrs.data());
-    B.firsti = FlatArray<int>(m + 1, firsti.data());
-    B.cols = FlatArray<int>(cols.size(), cols.data());
-    B.vals = FlatArray<TM>(vals.size(), vals.data());
-    B.diag = FlatMatrix<TM>(m, m, diag.data());
-    B.diag_inv = FlatMatrix<TM>(m, m, dinvm.data());
+    B.dofnrs.Assign(FlatArray<int>(m, dofnrs.data()));
+    B.firsti.Assign(FlatArray<int>(m + 1, firsti.data()));
+    B.cols.Assign(FlatArray<int>(cols.size(), cols.data()));
+    B.vals.Assign(FlatArray<TM>(vals.size(), vals.data()));
+    B.diag.AssignMemory(m, m, diag.data());
+    B.diag_inv.AssignMemory(m, m, dinvm.data());
     std::vector<TV> h1(m), h2(m);
     FlatVector<TV> hx(m, h1.data()), hb(m, h2.data());
     if (mode == 0) B.RichardsonUpdate(1.0, hx, bigx, hb, bigr);
@@ -124,6 +126,10 @@ int smooth_wo(int64_t n, int b, const int64_t *rp, const int32_t *ci, const doub
     for (int64_t q = bptr[k]; q < bptr[k + 1]; q++) { blk_of[bverts[q]] = (int32_t)k; pos_in[bverts[q]] = (int32_t)(q - bptr[k]); }
   std::vector<TM> A(rp[n]);
   for (int64_t e = 0; e < rp[n]; e++) set_block<TM>(A[e], av + e * b * b, b);
+  SparseMatrixTM<TM> spm;
+  spm.n = n; spm.rp = rp; spm.ci = ci;
+  spm.cols.assign(ci, ci + rp[n]);
+  spm.vals = A;
   struct Store { std::vector<int> dofnrs, firsti, cols; std::vector<TM> vals, diag, dinvm; };
   std::vector<Store> st(nblocks);
   sm.blocks.d.resize(nblocks);
@@ -140,6 +146,29 @@ int smooth_wo(int64_t n, int b, const int64_t *rp, const int32_t *ci, const doub
       }
       s.firsti[q + 1] = (int)s.cols.size();
     }
+    auto &B = sm.blocks[k];
+    if (dinv == nullptr) {
+      // the reference's OWN block set-up: BSBlock::SetFromSPMat (loc_block_gssmoother_impl.hpp:67-132) fills dofnrs (sorted), the off-block
+      // rows, diag and diag_inv = CalcInverse(diag) (the stand-in's Gauss-Jordan; NGSolve's routine is third-party).  The vertices are
+      // handed over in DESCENDING order so that its QuickSort has something to do.
+      const size_t noff = s.cols.size();
+      std::vector<int> dofs_in(s.dofnrs.rbegin(), s.dofnrs.rend());
+      std::fill(s.dofnrs.begin(), s.dofnrs.end(), -7);
+      std::fill(s.firsti.begin(), s.firsti.end(), -7);
+      s.cols.assign(noff, -7);
+      s.vals.assign(noff, TM(0.0));
+      std::fill(s.diag.begin(), s.diag.end(), TM(-7.0));
+      B.dofnrs.Assign(FlatArray<int>(m, s.dofnrs.data()));
+      B.firsti.Assign(FlatArray<int>(m + 1, s.firsti.data()));
+      B.cols.Assign(FlatArray<int>(noff, s.cols.data()));
+      B.vals.Assign(FlatArray<TM>(noff, s.vals.data()));
+      B.diag.AssignMemory(m, m, s.diag.data());
+      B.diag_inv.AssignMemory(m, m, s.dinvm.data());
+      LocalHeap lh;
+      B.SetFromSPMat(spm, FlatArray<int>(m, dofs_in.data()), lh, false, FlatArray<TM>(0, nullptr));
+      sm.maxbs = std::max<size_t>(sm.maxbs, (size_t)m);
+      continue;
+    }
     const double *di = dinv + dinv_off[k];
     for (int qi = 0; qi < m; qi++)
       for (int qj = 0; qj < m; qj++) {
@@ -147,13 +176,12 @@ int smooth_wo(int64_t n, int b, const int64_t *rp, const int32_t *ci, const doub
         for (int p = 0; p < b; p++) for (int q2 = 0; q2 < b; q2++) blk[p * b + q2] = di[(size_t)(qi * b + p) * (m * b) + qj * b + q2];
         set_block<TM>(s.dinvm[(size_t)qi * m + qj], blk, b);
       }
-    auto &B = sm.blocks[k];
-    B.dofnrs = FlatArray<int>(m, s.dofnrs.data());
-    B.firsti = FlatArray<int>(m + 1, s.firsti.data());
-    B.cols = FlatArray<int>(s.cols.size(), s.cols.data());
-    B.vals = FlatArray<TM>(s.vals.size(), s.vals.data());
-    B.diag = FlatMatrix<TM>(m, m, s.diag.data());
-    B.diag_inv = FlatMatrix<TM>(m, m, s.dinvm.data());
+    B.dofnrs.Assign(FlatArray<int>(m, s.dofnrs.data()));
+    B.firsti.Assign(FlatArray<int>(m + 1, s.firsti.data()));
+    B.cols.Assign(FlatArray<int>(s.cols.size(), s.cols.data()));
+    B.vals.Assign(FlatArray<TM>(s.vals.size(), s.vals.data()));
+    B.diag.AssignMemory(m, m, s.diag.data());
+    B.diag_inv.AssignMemory(m, m, s.dinvm.data());
     sm.maxbs = std::max<size_t>(sm.maxbs, (size_t)m);
   }
   sm.fi_blocks.d = {0, (size_t)nblocks};

@@ -191,3 +191,34 @@ def test_oracle_against_the_reference_made_fixture(tag):
                 sm.smooth(x, rhs, r, bool(ru), bool(ur), False, bool(back))
                 assert rel(x, g[key + "_x"]) < 1e-13, key
                 assert np.linalg.norm(r - g[key + "_r"]) < 1e-13 * scale, key
+
+
+@needs_ref
+@pytest.mark.parametrize("problem", ["poisson", "elasticity"])
+def test_block_setup_by_the_reference_code(problem):
+    """the blocks built by the reference's own BSBlock::SetFromSPMat (loc_block_gssmoother_impl.hpp:67-132: sorted dofnrs, off-block rows,
+    dense diagonal block, its inverse) instead of the harness: the smoother calls still agree with the oracle (the dense inverse is the
+    stand-in's Gauss-Jordan there and numpy's here: 1e-11)"""
+    from helpers import elasticity
+    if problem == "poisson":
+        p, A = poisson(6)
+        b = 1
+    else:
+        p, A = elasticity(5, 3, 4)
+        b = 3
+    n = p["n"]
+    As = A.to_scipy().tocsr()
+    blk = _blocks(n, p["free"], 4)
+    g = OB.BlockGS(As, b, blk)
+    x0, rhs = rand(12, n * b), rand(13, n * b)
+    scale = max(np.linalg.norm(rhs), np.linalg.norm(rhs - As @ x0))
+    for back in (False, True):
+        for ru, ur in ((True, True), (False, True), (False, False)):
+            r0 = rhs - As @ x0 if ru else np.zeros(n * b)
+            xo, ro = x0.copy(), r0.copy()
+            g.smooth(xo, rhs, ro, ru, ur, False, back)
+            xr, rr = x0.copy(), r0.copy()
+            RB.smooth_wo(A, blk, xr, rhs, rr, ru, ur, False, reverse=back, ref_setup=True)
+            assert rel(xo, xr) < 1e-11, (back, ru, ur)
+            if ur:
+                assert np.linalg.norm(ro - rr) < 1e-11 * scale, (back, ru, ur)
